@@ -1,0 +1,118 @@
+/* nwsolve.h -- C ABI of libnwsolve.so, the B200-native replacement for NAHRwhals' mutation-space solver.
+ *
+ * Each entry point names the reference interface it replaces.  Paths are relative to the reference tree;
+ * "solver.jl" = inst/extdata/scripts/scripts_nw_main/solver.jl.
+ *
+ * Conventions: plain pointers + sizes, caller owns every input buffer, results are opaque handles freed by
+ * the caller.  Return 0 on success, a negative NW_ERR_* otherwise; nw_last_error() gives the message of the
+ * last failure on the calling thread.  A context is bound to one CUDA device and is single-threaded;
+ * distinct contexts may be used from distinct threads or processes (one per GPU, or several per GPU).
+ * There is no CPU fallback: every compute entry point fails with NW_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef NWSOLVE_H
+#define NWSOLVE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NW_OK 0
+#define NW_ERR_ARG (-1)    /* bad argument / shape */
+#define NW_ERR_IO (-2)     /* cannot read or write a file */
+#define NW_ERR_PARSE (-3)  /* malformed TSV (solver.jl:102, :128-130) */
+#define NW_ERR_CUDA (-4)   /* CUDA runtime error or no device */
+#define NW_ERR_RANGE (-5)  /* lengths not integral / exceed the int32 DP range */
+#define NW_ERR_NOMEM (-6)  /* search does not fit device memory */
+
+#define NW_MOVE_DUP 0 /* MoveKind, solver.jl:34 */
+#define NW_MOVE_DEL 1
+#define NW_MOVE_INV 2
+
+typedef struct nw_ctx nw_ctx;
+typedef struct nw_result nw_result;
+
+/* Command line of solver.jl (:756-791) as a struct.  maxwidth / maxreport < 0 mean `nothing`. */
+typedef struct nw_opts {
+  int32_t maxdepth;  /* -d, default 3 */
+  int32_t maxdup;    /* -u, default 3 */
+  int64_t maxwidth;  /* -w, default nothing (-1) */
+  double minreport;  /* -r, default 0.95 */
+  int64_t maxreport; /* -R, default nothing (-1) */
+  int32_t keep_ids;  /* diagnostics: keep per-id cost/score arrays in the result (parity tests) */
+  int32_t flags;     /* NW_FLAG_* */
+} nw_opts;
+
+#define NW_FLAG_GENERIC_DP 1 /* force the generic (non register-resident) DP kernel; parity cross-check */
+#define NW_FLAG_NO_TRAJ 2    /* skip trajectory enumeration (benchmarking the search itself) */
+
+typedef struct nw_stats {
+  int32_t n_levels;
+  int32_t kernel_launches;  /* CUDA kernels launched by this solve */
+  int64_t generated[16];    /* candidates emitted per level (every (parent,i,j,kind)) */
+  int64_t scored[16];       /* unique new indices scored per level == reference slow_score calls */
+  int64_t cells[16];        /* DP band cells evaluated per level (SURVEY 8d definition) */
+  int64_t frontier[16];     /* parents expanded per level */
+  float level_ms[16];       /* device time per level (CUDA events) */
+  float total_ms;           /* device time of the whole search (events, excludes H2D of inputs) */
+  int64_t n_ids;            /* unique indices incl. the root */
+  double best;              /* best Float64 score over all children (solver.jl:660, 539-541) */
+} nw_stats;
+
+void nw_default_opts(nw_opts* o);
+const char* nw_last_error(void);
+const char* nw_version(void);
+
+/* One context per (process, GPU).  device < 0 picks LOCAL_RANK % device_count. */
+int nw_ctx_create(int device, nw_ctx** out);
+void nw_ctx_destroy(nw_ctx* ctx);
+
+/* Replaces aln_bfs_scored + get_good_trajectories (solver.jl:644-686, :727-745) on an in-memory problem.
+ * aln_sign: n_x*n_y int8 in {-1,0,1}, x-major (aln[x*n_y+y]) == transpose(sign(raw)) of solver.jl:103-106.
+ * len_x / len_y: block lengths in bp (lengths[2] / lengths[1] of solver.jl:121-138). */
+int nw_solve(nw_ctx* ctx, const int8_t* aln_sign, int32_t n_x, int32_t n_y, const int64_t* len_x,
+             const int64_t* len_y, const nw_opts* opts, nw_result** out);
+
+/* Replaces main() of solver.jl (:755-812) minus argument parsing: read_tsv + read_length_tsv + search +
+ * write_trajectories.  This is what `julia solver.jl ... inmat inlens out` does for R/juliasolver.R:34-53.
+ * On any failure no output file is left behind (written to out+".tmp" then renamed). */
+int nw_solve_files(nw_ctx* ctx, const char* inmat_path, const char* inlens_path, const char* out_path,
+                   const nw_opts* opts, nw_stats* stats_or_null);
+
+/* Result accessors (trajectories in report order, solver.jl:739-743). */
+int64_t nw_result_count(const nw_result* r);
+/* score as Float32 (solver.jl:714), number of moves, pointer to n_moves*3 int32 (kind,start,stop; :44-48) */
+int nw_result_get(const nw_result* r, int64_t k, float* score, int32_t* n_moves, const int32_t** moves3);
+/* DP terminal cost / total in bp of the index trajectory k leads to (cost < 0: early exit, no DP ran) */
+int nw_result_cost(const nw_result* r, int64_t k, int64_t* cost_bp, int64_t* total_bp, int64_t* index_id);
+/* The exact bytes write_trajectories (solver.jl:747-753) would write. */
+int nw_result_tsv(const nw_result* r, const char** data, int64_t* len);
+int nw_result_stats(const nw_result* r, nw_stats* out);
+/* keep_ids diagnostics: per id (1-based, root = 1; arrays of n_ids): Float32 score (-inf if unreachable),
+ * DP cost in bp (-1 early exit, -2 unreachable), total in bp (0 on early exit), discovery level. */
+int nw_result_ids(const nw_result* r, float* score, int64_t* cost_bp, int64_t* total_bp, int32_t* level);
+/* keep_ids diagnostics: all provenance edges in discovery order: child id, parent id, (kind,start,stop). */
+int64_t nw_result_edge_count(const nw_result* r);
+int nw_result_edges(const nw_result* r, int32_t* child, int32_t* parent, int32_t* moves3);
+void nw_result_free(nw_result* r);
+
+/* Replaces slow_score (solver.jl:329-376) for a raw list of candidate indices (flat int16 + offsets).
+ * force != 0 selects the R twin's forcecalc branch (R/evaltools.R:203-205; corridor 1.0, no early exit) that
+ * produces res_ref.  Outputs per candidate: cost_bp (-1 early exit, -2 unreachable), total_bp, Float64 score. */
+int nw_score_batch(nw_ctx* ctx, const int8_t* aln_sign, int32_t n_x, int32_t n_y, const int64_t* len_x,
+                   const int64_t* len_y, const int16_t* flat, const int64_t* off, int64_t n, int32_t force,
+                   int32_t flags, int64_t* cost_bp, int64_t* total_bp, double* score);
+
+/* Replaces to_moveset (solver.jl:217-231): two n_x*n_x uint8 matrices (duplicate_delete, invert). */
+int nw_moveset(nw_ctx* ctx, const int8_t* aln_sign, int32_t n_x, int32_t n_y, uint8_t* dup_del, uint8_t* invert);
+
+/* TSV readers of solver.jl:101-107 / :121-138 (host side; exposed for the bindings). Caller frees with nw_free. */
+int nw_read_problem(const char* inmat_path, const char* inlens_path, int8_t** aln_sign, int32_t* n_x,
+                    int32_t* n_y, int64_t** len_x, int64_t** len_y);
+void nw_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NWSOLVE_H */

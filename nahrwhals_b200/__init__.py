@@ -1,0 +1,8 @@
+"""nahrwhals_b200 -- B200-native (sm_100a) implementation of NAHRwhals' mutation-space solver.
+
+Only the hot path of the reference (its Julia script solver.jl, called from R/juliasolver.R) lives here:
+`csrc/` holds the CUDA kernels and the C ABI (include/nwsolve.h); `solver.py` mirrors the reference's solver
+interface on top of that ABI.  There is no CPU fallback.
+"""
+from .solver import Solver, SolveResult, read_problem, main, MOVE_NAMES  # noqa: F401
+from .sdgrid import sdgrid, to_solver_inputs, write_tsvs  # noqa: F401

@@ -1,0 +1,115 @@
+// nw_band.h -- corridor geometry of slow_score, evaluated on the host in IEEE double exactly as written in
+// solver.jl:378-386 (determine_corridor_pct), :390 / :400 (first column / first row) and :412-413 (interior):
+//     first column  i>=2 : valid iff !(i/row > pct)
+//     first row     j>=2 : valid iff !(j/col > pct)
+//     interior           : valid iff !(i/row > j/col + pct) && !(j/col > i/row + pct)
+// No integer cross-multiplication: the predicates are evaluated with the same divisions and additions as Julia.
+#pragma once
+#include <stdint.h>
+
+#include <vector>
+
+namespace nw {
+
+struct BandRowHost {
+  int a, b;  // valid real columns [a, b], 1-based; a > b == empty row
+};
+
+struct BandTable {
+  int L = 0, n_y = 0;
+  bool force = false;
+  bool contiguous = true;        // every row's valid set is one interval
+  std::vector<BandRowHost> row;  // row[1..L]; row[0] unused
+  int64_t cells = 0;             // sum of valid cells == SURVEY 8d "cells(L, n_y)"
+  // --- derived data for the register-resident kernel (extended with virtual row 0 / column 0) ---
+  bool fast_ok = false;
+  int max_width = 0;             // max over rows of eb - ea + 1
+  std::vector<int16_t> eb;       // eb[0..L]
+  std::vector<int16_t> ea;       // ea[0..L]
+  std::vector<uint8_t> sb;       // sb[1..L] = eb[i] - eb[i-1]
+  std::vector<uint32_t> mask;    // mask[i*4 + w]: diag-allowed bits of row i, bit k <-> column eb[i]-k (k < 128)
+};
+
+inline double corridor_pct(int row, bool force) {
+  if (force) return 1.0;  // R/evaltools.R:203-205
+  if (row < 10) return 1.0;
+  if (row < 30) return 0.3;
+  return 0.2;
+}
+
+inline bool band_valid(int i, int j, int row, int col, double pct) {
+  if (i == 1 && j == 1) return true;
+  if (j == 1) return !((double)i / (double)row > pct);
+  if (i == 1) return !((double)j / (double)col > pct);
+  const double im = (double)i / (double)row, jm = (double)j / (double)col;
+  return !(im > (jm + pct)) && !(jm > (im + pct));
+}
+
+inline BandTable build_band(int L, int n_y, bool force, int max_window = 128) {
+  BandTable T;
+  T.L = L;
+  T.n_y = n_y;
+  T.force = force;
+  const double pct = corridor_pct(L, force);
+  T.row.assign(L + 1, BandRowHost{1, 0});
+  for (int i = 1; i <= L; ++i) {
+    int a = 0, b = -1, cnt = 0;
+    for (int j = 1; j <= n_y; ++j)
+      if (band_valid(i, j, L, n_y, pct)) {
+        if (cnt == 0) a = j;
+        b = j;
+        ++cnt;
+      }
+    if (cnt == 0) {
+      T.row[i] = BandRowHost{1, 0};
+    } else {
+      T.row[i] = BandRowHost{a, b};
+      if (b - a + 1 != cnt) T.contiguous = false;
+    }
+    T.cells += cnt;
+  }
+  // ---- fast-path derivation ----
+  T.eb.assign(L + 1, 0);
+  T.ea.assign(L + 1, 0);
+  T.sb.assign(L + 1, 0);
+  T.mask.assign((size_t)(L + 1) * 4, 0u);
+  bool ok = T.contiguous && L >= 1 && n_y >= 1;
+  for (int i = 1; i <= L && ok; ++i)
+    if (T.row[i].a > T.row[i].b) ok = false;
+  if (ok && T.row[L].b != n_y) ok = false;
+  if (ok) {
+    T.ea[0] = 0;
+    T.eb[0] = (int16_t)T.row[1].b;
+    for (int i = 1; i <= L; ++i) {
+      T.ea[i] = (int16_t)(T.row[i].a == 1 ? 0 : T.row[i].a);
+      T.eb[i] = (int16_t)T.row[i].b;
+    }
+    for (int i = 1; i <= L && ok; ++i) {
+      const int s = T.eb[i] - T.eb[i - 1];
+      if (s < 0 || s > 255) ok = false;
+      if (T.ea[i] < T.ea[i - 1]) ok = false;
+      if (T.row[i].a > T.eb[i - 1]) ok = false;  // the new row must overlap the old one (entering cells are fed by right moves)
+      T.sb[i] = (uint8_t)(s < 0 ? 0 : s);
+      const int w = T.eb[i] - T.ea[i] + 1;
+      if (w > T.max_width) T.max_width = w;
+    }
+    if (T.eb[0] - T.ea[0] + 1 > T.max_width) T.max_width = T.eb[0] - T.ea[0] + 1;
+    if (T.max_width > max_window) ok = false;
+  }
+  if (ok) {
+    for (int i = 1; i <= L; ++i) {
+      for (int j = T.row[i].a; j <= T.row[i].b; ++j) {
+        // diag move into (i,j) needs (i-1, j-1) valid in the extended grid
+        const int pj = j - 1;
+        const bool pv = pj >= T.ea[i - 1] && pj <= T.eb[i - 1];
+        if (!pv) continue;
+        const int k = T.eb[i] - j;
+        T.mask[(size_t)i * 4 + (k >> 5)] |= 1u << (k & 31);
+      }
+    }
+  }
+  T.fast_ok = ok;
+  return T;
+}
+
+}  // namespace nw

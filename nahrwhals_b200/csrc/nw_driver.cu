@@ -1,0 +1,1147 @@
+// nw_driver.cu -- host frontier driver + C ABI of libnwsolve.so.
+//
+// Restates the control flow of aln_bfs_scored / get_good_trajectories / main of the reference
+// (inst/extdata/scripts/scripts_nw_main/solver.jl:644-686, :727-745, :755-812) around the CUDA kernels of
+// nw_kernels.cu / nw_score_fast.cu.  Per BFS level: count -> scan -> emit+fingerprint+dedup -> resolve first
+// discoverers -> assign ids -> bucket by child length -> banded DP -> select the next frontier -> materialise.
+// There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/nwsolve.h"
+#include "nw_band.h"
+#include "nw_host.h"
+#include "nw_kernels.cuh"
+#include "nw_launch.h"
+
+using namespace nw;
+
+static thread_local std::string g_last_error;
+
+namespace {
+
+struct Err {
+  int code;
+  std::string msg;
+};
+[[noreturn]] void fail(int code, const std::string& m) { throw Err{code, m}; }
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      fail(e_ == cudaErrorMemoryAllocation ? NW_ERR_NOMEM : NW_ERR_CUDA,                           \
+           std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) {
+    o.p = nullptr;
+    o.cap = 0;
+  }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    release();
+    p = o.p;
+    cap = o.cap;
+    o.p = nullptr;
+    o.cap = 0;
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  void* ensure(size_t bytes, bool grow_slack = false) {
+    if (bytes == 0) bytes = 16;
+    if (bytes > cap) {
+      release();
+      size_t want = grow_slack ? bytes + bytes / 4 : bytes;
+      want = (want + 255) & ~(size_t)255;
+      CK(cudaMalloc(&p, want));
+      cap = want;
+    }
+    return p;
+  }
+  template <typename T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct BandStore {  // host cache + device mirror of per-length corridor tables for one (n_y, force)
+  int n_y = -1;
+  bool force = false;
+  std::map<int, BandTable> tabs;
+  std::vector<int32_t> off;  // [LMAX+2] row offset or -1
+  std::vector<int16_t> ab, eb;
+  std::vector<uint8_t> sb;
+  std::vector<uint32_t> mask;
+  DevBuf d_off, d_ab, d_eb, d_sb, d_mask;
+  bool dirty = true;
+  void reset(int ny, bool f) {
+    n_y = ny;
+    force = f;
+    tabs.clear();
+    off.assign(LMAX + 2, -1);
+    ab.clear();
+    eb.clear();
+    sb.clear();
+    mask.clear();
+    dirty = true;
+  }
+  const BandTable& get(int L) {
+    auto it = tabs.find(L);
+    if (it != tabs.end()) return it->second;
+    BandTable T = build_band(L, n_y, force, WINDOW_MAX);
+    off[L] = (int32_t)eb.size();
+    for (int i = 0; i <= L; ++i) {
+      ab.push_back((int16_t)(i ? T.row[i].a : 1));
+      ab.push_back((int16_t)(i ? T.row[i].b : 0));
+      eb.push_back(T.eb[i]);
+      sb.push_back(T.sb[i]);
+      for (int w = 0; w < 4; ++w) mask.push_back(T.mask[(size_t)i * 4 + w]);
+    }
+    dirty = true;
+    return tabs.emplace(L, std::move(T)).first->second;
+  }
+  void upload(cudaStream_t st) {
+    if (!dirty) return;
+    CK(cudaMemcpyAsync(d_off.ensure(off.size() * 4), off.data(), off.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_ab.ensure(ab.size() * 2, true), ab.data(), ab.size() * 2, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_eb.ensure(eb.size() * 2, true), eb.data(), eb.size() * 2, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_sb.ensure(sb.size(), true), sb.data(), sb.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_mask.ensure(mask.size() * 4, true), mask.data(), mask.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // host vectors may be reallocated by the next get()
+    dirty = false;
+  }
+};
+
+}  // namespace
+
+struct nw_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<U4> h_pow;
+  DevBuf d_pow;
+  // region
+  RegionHost RH;
+  RegionDev RD{};
+  DevBuf d_ctx, d_rt, d_cumr, d_msdd, d_msinv;
+  BandStore bands;
+  // dedup table
+  DevBuf table;
+  uint64_t table_cap = 0;
+  // per-level scratch
+  DevBuf cnt, off, bsum, slot, is_new, newrank, new_len, hist, bstart, cursor, work, scratch, flag, pre, sel, keys,
+      misc;
+  void* pinned = nullptr;  // small pinned staging area for D2H scalars / histograms
+  int launches = 0;
+  nw_ctx() = default;
+};
+
+struct nw_result {
+  nw_stats stats{};
+  std::vector<float> t_score;
+  std::vector<int32_t> t_k3;
+  std::vector<int64_t> t_cost, t_total, t_id;
+  std::vector<int64_t> t_off;  // into t_moves (triples)
+  std::vector<int32_t> t_moves;
+  std::string tsv;
+  // keep_ids
+  std::vector<float> id_score;
+  std::vector<int64_t> id_cost, id_total;
+  std::vector<int32_t> id_level;
+  std::vector<int32_t> e_child, e_parent, e_moves;
+};
+
+namespace {
+
+constexpr size_t PINNED_BYTES = 64 * 1024;
+
+struct Level {
+  // frontier expanded at this level
+  int P = 0, LS = 0;
+  uint32_t pstride = 0;
+  DevBuf fblob, flen, fid, fdup;
+  // candidates generated at this level
+  uint32_t G = 0, gbase = 0, n_new = 0;
+  int32_t id_base = 0;
+  DevBuf desc, cand_id, newlist, k3, cost, total;
+  FrontierDev frontier() const {
+    FrontierDev F;
+    F.P = P;
+    F.LS = LS;
+    F.pstride = pstride;
+    F.blob = fblob.as<unsigned char>();
+    F.len = flen.as<int32_t>();
+    F.id = fid.as<int32_t>();
+    F.dupok = fdup.as<uint8_t>();
+    return F;
+  }
+};
+
+void setup_region(nw_ctx* c, const int8_t* aln, int n_x, int n_y, const int64_t* len_x, const int64_t* len_y,
+                  int maxdepth, bool force) {
+  try {
+    c->RH = build_region(aln, n_x, n_y, len_x, len_y, maxdepth);
+  } catch (const HostError& e) {
+    fail(e.code, e.what());
+  }
+  RegionHost& H = c->RH;
+  cudaStream_t st = c->stream;
+  CK(cudaMemcpyAsync(c->d_ctx.ensure(H.ctx.size()), H.ctx.data(), H.ctx.size(), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(c->d_rt.ensure(H.rt.size() * 4), H.rt.data(), H.rt.size() * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(c->d_cumr.ensure(H.cumr.size() * 4), H.cumr.data(), H.cumr.size() * 4, cudaMemcpyHostToDevice, st));
+  const size_t msb = (size_t)(n_x + 1) * H.MW * 4;
+  CK(cudaMemsetAsync(c->d_msdd.ensure(msb), 0, msb, st));
+  CK(cudaMemsetAsync(c->d_msinv.ensure(msb), 0, msb, st));
+  RegionDev& D = c->RD;
+  D.n_x = n_x;
+  D.n_y = n_y;
+  D.NYP = H.NYP;
+  D.PWS = H.PWS;
+  D.MW = H.MW;
+  D.sum_rt = (int)H.sum_rt;
+  D.rid1 = 1;
+  D.ctx_bytes = (uint32_t)H.ctx.size();
+  D.ctx = c->d_ctx.as<unsigned char>();
+  D.off_upx = H.off_upx;
+  D.off_rtrev = H.off_rtrev;
+  D.rt_copy_stride = H.rt_copy_stride;
+  D.rt = c->d_rt.as<int32_t>();
+  D.cumr = c->d_cumr.as<int32_t>();
+  D.ms_dd = c->d_msdd.as<uint32_t>();
+  D.ms_inv = c->d_msinv.as<uint32_t>();
+  if (D.ctx_bytes > 200 * 1024) fail(NW_ERR_RANGE, "region context exceeds shared memory");
+  c->launches += launch_moveset(D, st);
+  if (c->bands.n_y != n_y || c->bands.force != force) c->bands.reset(n_y, force);
+}
+
+void table_reserve(nw_ctx* c, uint64_t need_entries) {
+  uint64_t want = 1024;
+  while (want < need_entries * 2) want <<= 1;
+  if (want <= c->table_cap) return;
+  if (want > (1ull << 32)) fail(NW_ERR_NOMEM, "dedup table would exceed 2^32 slots");
+  DevBuf nt;
+  nt.ensure(want * TBL_WORDS * 8);
+  CK(cudaMemsetAsync(nt.p, 0xFF, want * TBL_WORDS * 8, c->stream));
+  if (c->table_cap) c->launches += launch_rehash(c->table.as<uint64_t>(), c->table_cap, nt.as<uint64_t>(), want - 1, c->stream);
+  CK(cudaStreamSynchronize(c->stream));
+  c->table = std::move(nt);
+  c->table_cap = want;
+}
+
+// Buckets the `n_new` fresh candidates of a level by child length and runs the DP kernels.
+// hist (host copy) gives the number of DP-needing candidates per length.
+struct ScoreView {
+  FrontierDev F;
+  uint32_t n_new;
+  const uint32_t* newlist;
+  const uint64_t* desc;
+  int32_t *k3, *cost, *total;
+};
+ScoreView view_of(const Level& L) {
+  return ScoreView{L.frontier(),          L.n_new,           L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(),
+                   L.k3.as<int32_t>(),    L.cost.as<int32_t>(), L.total.as<int32_t>()};
+}
+void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int force, int flags, int* best_dev,
+                 int64_t* cells_out) {
+  cudaStream_t st = c->stream;
+  struct Bucket {
+    int L, cls;  // cls: window W (fast) or 0 (generic)
+    uint32_t n;
+  };
+  std::vector<Bucket> bk;
+  int64_t cells = 0;
+  for (int L = 1; L <= LMAX; ++L) {
+    if (!hist_h[L]) continue;
+    const BandTable& T = c->bands.get(L);
+    int cls = 0;
+    if (!(flags & NW_FLAG_GENERIC_DP) && T.fast_ok) cls = score_fast_window(T.max_width);
+    bk.push_back(Bucket{L, cls, hist_h[L]});
+    cells += (int64_t)hist_h[L] * T.cells;
+  }
+  if (cells_out) *cells_out = cells;
+  if (bk.empty()) return;
+  c->bands.upload(st);
+  std::stable_sort(bk.begin(), bk.end(), [](const Bucket& a, const Bucket& b) {
+    const int ka = a.cls ? a.cls : 1 << 20, kb = b.cls ? b.cls : 1 << 20;
+    return ka < kb;
+  });
+  std::vector<uint32_t> bstart(LMAX + 2, 0);
+  struct Range {
+    int cls;
+    uint32_t begin, end;
+  };
+  std::vector<Range> ranges;
+  uint32_t pos = 0;
+  for (const Bucket& b : bk) {
+    if (ranges.empty() || ranges.back().cls != b.cls) {
+      pos = (pos + 127) & ~127u;  // class ranges start on a CTA boundary
+      ranges.push_back(Range{b.cls, pos, pos});
+    }
+    bstart[b.L] = pos;
+    pos += (b.n + 31) & ~31u;
+    ranges.back().end = pos;
+  }
+  const uint32_t n_work = pos;
+  CK(cudaMemcpyAsync(c->bstart.ensure((LMAX + 2) * 4), bstart.data(), (LMAX + 2) * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(c->cursor.ensure((LMAX + 2) * 4), 0, (LMAX + 2) * 4, st));
+  CK(cudaMemsetAsync(c->work.ensure((size_t)n_work * 4, true), 0xFF, (size_t)n_work * 4, st));
+  c->launches += launch_bucket_scatter(c->new_len.as<uint16_t>(), Lv.n_new, c->RD.n_y, force, c->bstart.as<uint32_t>(),
+                                       c->cursor.as<uint32_t>(), c->work.as<uint32_t>(), st);
+  CK(cudaStreamSynchronize(st));  // bstart host vector goes out of scope
+  ScoreArgs A{};
+  A.R = c->RD;
+  A.F = Lv.F;
+  A.newlist = Lv.newlist;
+  A.desc = Lv.desc;
+  A.band_off = c->bands.d_off.as<int32_t>();
+  A.band_ab = c->bands.d_ab.as<int16_t>();
+  A.band_eb = c->bands.d_eb.as<int16_t>();
+  A.band_sb = c->bands.d_sb.as<uint8_t>();
+  A.band_mask = c->bands.d_mask.as<uint32_t>();
+  A.k3 = Lv.k3;
+  A.cost = Lv.cost;
+  A.total = Lv.total;
+  A.best_k3 = best_dev;
+  A.cells = nullptr;
+  A.force = force;
+  for (const Range& r : ranges) {
+    A.work = c->work.as<uint32_t>() + r.begin;
+    A.n_work = r.end - r.begin;
+    if (r.cls) {
+      const int l = launch_score_fast(r.cls, A, st);
+      if (l < 0) fail(NW_ERR_CUDA, "no register-DP kernel for window " + std::to_string(r.cls));
+      c->launches += l;
+    } else {
+      const size_t sc = (size_t)2 * (c->RD.n_y + 2) * generic_threads() * 4;
+      A.scratch = (int32_t*)c->scratch.ensure(sc);
+      c->launches += launch_score_generic(A, st);
+    }
+  }
+  CK(cudaGetLastError());
+}
+
+struct Search {
+  nw_ctx* c;
+  nw_opts o;
+  std::vector<Level> lv;  // lv[0] = root pseudo-level, lv[d] = BFS level d
+  int32_t n_ids = 0;
+  uint32_t gtotal = 0;
+  int root_k3 = 0, root_cost = -1, root_total = 0;
+  int best_k3 = 0;
+  nw_stats st{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> lev;
+
+  explicit Search(nw_ctx* ctx, const nw_opts& opts) : c(ctx), o(opts) {}
+  ~Search() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    for (auto e : lev) cudaEventDestroy(e);
+  }
+
+  uint32_t* pin_u32() { return reinterpret_cast<uint32_t*>(c->pinned); }
+
+  void init_root() {
+    cudaStream_t s = c->stream;
+    const int n_x = c->RD.n_x;
+    if (n_x > LMAX) fail(NW_ERR_RANGE, "n_x exceeds the supported index length");
+    lv.clear();
+    lv.emplace_back();  // level 0 (root pseudo level)
+    lv.emplace_back();  // level 1 frontier = {root}
+    Level& L0 = lv[0];
+    Level& L1 = lv[1];
+    std::vector<int16_t> root(n_x);
+    for (int i = 0; i < n_x; ++i) root[i] = (int16_t)(i + 1);
+    L1.P = 1;
+    L1.LS = round_ls(n_x);
+    L1.pstride = blob_stride(L1.LS);
+    std::vector<unsigned char> blob(L1.pstride);
+    fill_blob(blob.data(), L1.LS, root.data(), n_x, c->h_pow.data());
+    CK(cudaMemcpyAsync(L1.fblob.ensure(blob.size()), blob.data(), blob.size(), cudaMemcpyHostToDevice, s));
+    const int32_t len = n_x, id = 1;
+    const uint8_t dupok = (1 <= o.maxdup) ? 1 : 0;  // duplication_count(root) == 1 (solver.jl:611)
+    CK(cudaMemcpyAsync(L1.flen.ensure(4), &len, 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(L1.fid.ensure(4), &id, 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(L1.fdup.ensure(1), &dupok, 1, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    // level 0: one pseudo candidate (the root itself, KIND_ID over frontier slot 0 of level 1), id 1
+    L0.G = 1;
+    L0.gbase = 0;
+    L0.n_new = 1;
+    L0.id_base = 1;
+    const uint64_t d0 = pack_desc(0, 0, 0, KIND_ID);
+    const int32_t one = 1;
+    const uint32_t zero = 0;
+    CK(cudaMemcpyAsync(L0.desc.ensure(8), &d0, 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(L0.cand_id.ensure(4), &one, 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(L0.newlist.ensure(4), &zero, 4, cudaMemcpyHostToDevice, s));
+    L0.k3.ensure(4);
+    L0.cost.ensure(4);
+    L0.total.ensure(4);
+    // frontier view for scoring the root: borrow level 1's frontier
+    n_ids = 1;
+    gtotal = 1;
+    // dedup table
+    c->table_cap = 0;
+    c->table.release();
+    table_reserve(c, 1 << 12);
+    c->launches += launch_insert_root(L1.fblob.as<int16_t>(), n_x, c->d_pow.as<U4>(), c->RD.rid1, c->table.as<uint64_t>(),
+                                      c->table_cap - 1, s);
+    // score the root (solver.jl:599) -- its score never updates `best` (:606)
+    int32_t* misc = (int32_t*)c->misc.ensure(256);
+    CK(cudaMemsetAsync(misc, 0, 256, s));
+    std::vector<uint32_t> hist(LMAX + 2, 0);
+    const uint16_t rl = (uint16_t)n_x;
+    CK(cudaMemcpyAsync(c->new_len.ensure(2), &rl, 2, cudaMemcpyHostToDevice, s));
+    if (early_exit(n_x, c->RD.n_y)) {
+      root_k3 = 0;
+      root_cost = -1;
+      root_total = 0;
+      const int32_t v[3] = {0, -1, 0};
+      CK(cudaMemcpyAsync(L0.k3.p, &v[0], 4, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(L0.cost.p, &v[1], 4, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(L0.total.p, &v[2], 4, cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));
+    } else {
+      hist[n_x] = 1;
+      ScoreView view = view_of(L0);  // candidates of level 0 against the frontier of level 1
+      view.F = L1.frontier();
+      run_scoring(c, view, hist.data(), 0, o.flags, misc + 1 /*dummy best*/, nullptr);
+      int32_t v[3];
+      CK(cudaMemcpyAsync(&v[0], L0.k3.p, 4, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(&v[1], L0.cost.p, 4, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(&v[2], L0.total.p, 4, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      root_k3 = v[0];
+      root_cost = v[1];
+      root_total = v[2];
+    }
+  }
+
+  // one BFS level: expand lv[d]'s frontier.  Returns false when the frontier is empty.
+  bool run_level(int d) {
+    cudaStream_t s = c->stream;
+    Level& L = lv[d];
+    int32_t* misc = (int32_t*)c->misc.p;  // [0]=best_k3, [1]=dummy, [2]=maxlen, [4..]=totals
+    st.frontier[d - 1] = L.P;
+    if (L.P == 0) return false;
+    ExpandArgs E{};
+    E.R = c->RD;
+    E.F = L.frontier();
+    E.cnt = (uint32_t*)c->cnt.ensure((size_t)L.P * 4, true);
+    E.maxlen = misc + 2;
+    CK(cudaMemsetAsync(misc + 2, 0, 4, s));
+    c->launches += launch_expand(false, E, s);
+    uint32_t* off = (uint32_t*)c->off.ensure((size_t)L.P * 4, true);
+    uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items((uint64_t)L.P) * 4, true);
+    c->launches += launch_scan(E.cnt, off, (uint64_t)L.P, bsum, (uint32_t*)(misc + 4), s);
+    CK(cudaMemcpyAsync(pin_u32(), misc, 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    const uint32_t G = pin_u32()[4];
+    const int maxlen = (int)pin_u32()[2];
+    if (maxlen > LMAX) fail(NW_ERR_RANGE, "a child index exceeds the supported length");
+    if ((uint64_t)gtotal + G >= 0xfffffff0ull || G >= 0x7ffffff0u) fail(NW_ERR_NOMEM, "more than 2^32 candidates");
+    L.G = G;
+    L.gbase = gtotal;
+    L.id_base = n_ids + 1;
+    st.generated[d - 1] = G;
+    if (G == 0) {
+      L.n_new = 0;
+      return false;
+    }
+    table_reserve(c, (uint64_t)n_ids + G);
+    E.off = off;
+    E.desc = (uint64_t*)L.desc.ensure((size_t)G * 8);
+    E.slot = (uint32_t*)c->slot.ensure((size_t)G * 4, true);
+    E.table = c->table.as<uint64_t>();
+    E.tmask = c->table_cap - 1;
+    E.gbase = L.gbase;
+    E.pw = c->d_pow.as<U4>();
+    c->launches += launch_expand(true, E, s);
+    uint32_t* is_new = (uint32_t*)c->is_new.ensure((size_t)G * 4, true);
+    c->launches += launch_resolve(E.slot, E.table, L.gbase, G, is_new, s);
+    uint32_t* newrank = (uint32_t*)c->newrank.ensure((size_t)G * 4, true);
+    bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(G) * 4, true);
+    c->launches += launch_scan(is_new, newrank, G, bsum, (uint32_t*)(misc + 5), s);
+    CK(cudaMemcpyAsync(pin_u32(), misc, 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    const uint32_t n_new = pin_u32()[5];
+    L.n_new = n_new;
+    st.scored[d - 1] = n_new;
+    // ids / edges / histogram of child lengths
+    AssignArgs A{};
+    A.LT.n_levels = d;
+    for (int l = 0; l < d; ++l) {
+      A.LT.gbase[l] = lv[l].gbase;
+      A.LT.cand_id[l] = lv[l].cand_id.as<int32_t>();
+    }
+    A.LT.gbase[d] = L.gbase;
+    A.slot = E.slot;
+    A.table = E.table;
+    A.is_new = is_new;
+    A.newrank = newrank;
+    A.desc = E.desc;
+    A.front_len = L.flen.as<int32_t>();
+    A.gbase = L.gbase;
+    A.G = G;
+    A.id_base = L.id_base;
+    A.n_y = c->RD.n_y;
+    A.force = 0;
+    A.cand_id = (int32_t*)L.cand_id.ensure((size_t)G * 4);
+    A.newlist = (uint32_t*)L.newlist.ensure((size_t)n_new * 4);
+    A.new_len = (uint16_t*)c->new_len.ensure((size_t)n_new * 2, true);
+    A.k3 = (int32_t*)L.k3.ensure((size_t)n_new * 4);
+    A.cost = (int32_t*)L.cost.ensure((size_t)n_new * 4);
+    A.total = (int32_t*)L.total.ensure((size_t)n_new * 4);
+    A.hist = (uint32_t*)c->hist.ensure((LMAX + 2) * 4);
+    CK(cudaMemsetAsync(A.hist, 0, (LMAX + 2) * 4, s));
+    c->launches += launch_assign(A, s);
+    uint32_t* hist_h = pin_u32() + 64;
+    CK(cudaMemcpyAsync(hist_h, A.hist, (LMAX + 2) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    int64_t cells = 0;
+    run_scoring(c, view_of(L), hist_h, 0, o.flags, misc + 0, &cells);
+    st.cells[d - 1] = cells;
+    gtotal += G;
+    n_ids += (int32_t)n_new;
+    return n_new > 0;
+  }
+
+  // frontier of level d+1 from the fresh candidates of level d (solver.jl:551-553, :669-672)
+  void select_next(int d) {
+    cudaStream_t s = c->stream;
+    Level& L = lv[d];
+    lv.emplace_back();
+    Level& N = lv[d + 1];
+    Level& Lr = lv[d];  // re-take reference (emplace_back may reallocate)
+    (void)L;
+    const uint32_t n = Lr.n_new;
+    int32_t* misc = (int32_t*)c->misc.p;
+    if (n == 0) {
+      N.P = 0;
+      return;
+    }
+    uint32_t* flag = (uint32_t*)c->flag.ensure((size_t)n * 4, true);
+    uint32_t* pre = (uint32_t*)c->pre.ensure((size_t)n * 4, true);
+    uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(n) * 4, true);
+    c->launches += launch_valid_flags(Lr.k3.as<int32_t>(), n, flag, s);
+    c->launches += launch_scan(flag, pre, n, bsum, (uint32_t*)(misc + 6), s);
+    CK(cudaMemcpyAsync(pin_u32(), misc, 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint32_t nvalid = pin_u32()[6];
+    uint32_t P2 = nvalid;
+    uint32_t* sel = (uint32_t*)c->sel.ensure((size_t)std::max<uint32_t>(nvalid, 1) * 4, true);
+    if (o.maxwidth < 0) {
+      c->launches += launch_compact_ranks(flag, pre, n, sel, s);
+    } else {
+      uint64_t npad = 2048;
+      while (npad < nvalid) npad <<= 1;
+      uint64_t* keys = (uint64_t*)c->keys.ensure(npad * 8, true);
+      c->launches += launch_make_keys(Lr.k3.as<int32_t>(), flag, pre, n, keys, nvalid, npad, s);
+      c->launches += launch_sort_u64(keys, npad, s);
+      if ((int64_t)P2 > o.maxwidth) P2 = (uint32_t)o.maxwidth;
+      c->launches += launch_keys_to_sel(keys, P2, sel, s);
+    }
+    N.P = (int)P2;
+    if (P2 == 0) return;
+    // child lengths are bounded by the level's maxlen (misc[2]) -- use it for the stride
+    int maxlen = (int)pin_u32()[2];
+    if (maxlen < c->RD.n_x) maxlen = c->RD.n_x;
+    // inversions keep the parent's length: include the longest parent
+    maxlen = std::max(maxlen, Lr.LS);
+    N.LS = round_ls(maxlen);
+    N.pstride = blob_stride(N.LS);
+    MaterialiseArgs M{};
+    M.F = Lr.frontier();
+    M.sel = sel;
+    M.newlist = Lr.newlist.as<uint32_t>();
+    M.desc = Lr.desc.as<uint64_t>();
+    M.id_base = Lr.id_base;
+    M.maxdup = o.maxdup;
+    M.n_x = c->RD.n_x;
+    M.P2 = (int)P2;
+    M.LS2 = N.LS;
+    M.pstride2 = N.pstride;
+    M.blob2 = (unsigned char*)N.fblob.ensure((size_t)P2 * N.pstride);
+    M.len2 = (int32_t*)N.flen.ensure((size_t)P2 * 4);
+    M.id2 = (int32_t*)N.fid.ensure((size_t)P2 * 4);
+    M.dupok2 = (uint8_t*)N.fdup.ensure((size_t)P2);
+    M.pw = c->d_pow.as<U4>();
+    c->launches += launch_materialise(M, s);
+    CK(cudaGetLastError());
+  }
+
+  void run() {
+    cudaStream_t s = c->stream;
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    CK(cudaEventRecord(ev0, s));
+    init_root();
+    int32_t* misc = (int32_t*)c->misc.p;
+    CK(cudaMemsetAsync(misc, 0, 4, s));  // best_k3 = 0  (best = 0.0, solver.jl:660)
+    const int D = std::min(o.maxdepth, MAX_LEVELS - 1);
+    st.n_levels = 0;
+    for (int d = 1; d <= D; ++d) {
+      cudaEvent_t a, b;
+      CK(cudaEventCreate(&a));
+      CK(cudaEventCreate(&b));
+      lev.push_back(a);
+      lev.push_back(b);
+      CK(cudaEventRecord(a, s));
+      const bool any = run_level(d);
+      st.n_levels = d;
+      if (d < D) {
+        select_next(d);
+      }
+      CK(cudaEventRecord(b, s));
+      // the frontier blob of level d is no longer needed once level d+1 is materialised (ids are kept)
+      lv[d].fblob.release();
+      if (d < D && (!any || lv[d + 1].P == 0)) {
+        // solver.jl keeps looping over empty frontiers; nothing more can be generated
+        for (int e = d + 1; e <= D; ++e) {
+          if ((int)lv.size() <= e) lv.emplace_back();
+          st.n_levels = e;
+        }
+        break;
+      }
+    }
+    CK(cudaMemcpyAsync(pin_u32(), misc, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ev1, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    best_k3 = (int)pin_u32()[0];
+    for (size_t k = 0; k + 1 < lev.size(); k += 2) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, lev[k], lev[k + 1]);
+      st.level_ms[k / 2] = ms;
+    }
+    cudaEventElapsedTime(&st.total_ms, ev0, ev1);
+    st.n_ids = n_ids;
+    st.best = k3_to_score(best_k3);
+    st.kernel_launches = c->launches;
+  }
+
+  // ---- report: get_good_trajectories (solver.jl:727-745) ----
+  struct Node {
+    int32_t k3 = 0, cost = -1, total = 0;
+    std::vector<EdgeRec> in;
+  };
+  std::unordered_map<int32_t, Node> nodes;
+
+  static float score_f32(int k3) { return k3 < 0 ? -INFINITY : (float)k3_to_score(k3); }
+
+  void extract(double thr) {
+    cudaStream_t s = c->stream;
+    uint8_t* needed = (uint8_t*)c->flag.ensure((size_t)n_ids + 16, true);
+    CK(cudaMemsetAsync(needed, 0, (size_t)n_ids + 16, s));
+    const int nl = (int)lv.size();
+    for (int l = 1; l < nl; ++l)
+      c->launches += launch_good_flags(lv[l].k3.as<int32_t>(), lv[l].n_new, lv[l].id_base, thr, needed, s);
+    for (int pass = 0; pass <= o.maxdepth + 1; ++pass)
+      for (int l = nl - 1; l >= 1; --l)
+        c->launches += launch_mark_parents(lv[l].cand_id.as<int32_t>(), lv[l].desc.as<uint64_t>(),
+                                           lv[l].fid.as<int32_t>(), lv[l].G, needed, s);
+    int32_t* misc = (int32_t*)c->misc.p;
+    nodes.clear();
+    nodes[1] = Node{root_k3, root_cost, root_total, {}};
+    for (int l = 1; l < nl; ++l) {
+      const Level& L = lv[l];
+      if (L.G == 0) continue;
+      // edges into needed ids
+      uint32_t* eflag = (uint32_t*)c->is_new.ensure((size_t)L.G * 4, true);
+      uint32_t* epre = (uint32_t*)c->newrank.ensure((size_t)L.G * 4, true);
+      uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.G) * 4, true);
+      c->launches += launch_edge_flags(L.cand_id.as<int32_t>(), L.G, needed, eflag, s);
+      c->launches += launch_scan(eflag, epre, L.G, bsum, (uint32_t*)(misc + 8), s);
+      CK(cudaMemcpyAsync(pin_u32(), misc, 64, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      const uint32_t ne = pin_u32()[8];
+      if (ne) {
+        EdgeRec* d_e = (EdgeRec*)c->keys.ensure((size_t)ne * sizeof(EdgeRec), true);
+        c->launches += launch_edge_compact(L.cand_id.as<int32_t>(), L.desc.as<uint64_t>(), L.fid.as<int32_t>(), L.G,
+                                           eflag, epre, d_e, s);
+        std::vector<EdgeRec> he(ne);
+        CK(cudaMemcpyAsync(he.data(), d_e, (size_t)ne * sizeof(EdgeRec), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (const EdgeRec& e : he) nodes[e.child].in.push_back(e);
+      }
+      // per-id records of needed ids discovered at this level
+      if (L.n_new) {
+        uint32_t* iflag = (uint32_t*)c->is_new.ensure((size_t)L.n_new * 4, true);
+        uint32_t* ipre = (uint32_t*)c->newrank.ensure((size_t)L.n_new * 4, true);
+        bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.n_new) * 4, true);
+        c->launches += launch_id_flags(needed, L.id_base, L.n_new, iflag, s);
+        c->launches += launch_scan(iflag, ipre, L.n_new, bsum, (uint32_t*)(misc + 9), s);
+        CK(cudaMemcpyAsync(pin_u32(), misc, 64, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const uint32_t ni = pin_u32()[9];
+        if (ni) {
+          IdRec* d_i = (IdRec*)c->keys.ensure((size_t)ni * sizeof(IdRec), true);
+          c->launches += launch_id_compact(L.k3.as<int32_t>(), L.cost.as<int32_t>(), L.total.as<int32_t>(), L.id_base,
+                                           L.n_new, iflag, ipre, d_i, s);
+          std::vector<IdRec> hi(ni);
+          CK(cudaMemcpyAsync(hi.data(), d_i, (size_t)ni * sizeof(IdRec), cudaMemcpyDeviceToHost, s));
+          CK(cudaStreamSynchronize(s));
+          for (const IdRec& r : hi) {
+            Node& nd = nodes[r.id];
+            nd.k3 = r.k3;
+            nd.cost = r.cost;
+            nd.total = r.total;
+          }
+        }
+      }
+    }
+    CK(cudaGetLastError());
+  }
+
+  // solver.jl:688-705
+  bool concat(int32_t cur, int depth, std::vector<std::vector<EdgeRec>>& result) {
+    result.clear();
+    if (cur == 1) {
+      result.emplace_back();
+      return true;
+    } else if (depth > o.maxdepth) {
+      result.emplace_back();
+      return false;
+    }
+    auto it = nodes.find(cur);
+    if (it == nodes.end()) return true;
+    std::vector<std::vector<EdgeRec>> sub;
+    for (const EdgeRec& e : it->second.in) {
+      const bool valid = concat(e.parent, depth + 1, sub);
+      if (valid)
+        for (auto& t : sub) {
+          std::vector<EdgeRec> nt(t);
+          nt.push_back(e);
+          result.push_back(std::move(nt));
+        }
+    }
+    return true;
+  }
+
+  void report(nw_result* R) {
+    const double best = k3_to_score(best_k3);
+    const double thr = o.minreport * best;  // solver.jl:733
+    extract(thr);
+    struct Traj {
+      int32_t id, k3;
+      std::vector<EdgeRec> mv;
+    };
+    std::vector<Traj> tr;
+    std::vector<int32_t> good;
+    for (auto& kv : nodes) {
+      const int k3 = kv.second.k3;
+      if (k3 >= 0 && (double)score_f32(k3) >= thr) good.push_back(kv.first);
+    }
+    std::sort(good.begin(), good.end());  // canonical Dict order: ascending discovery id
+    std::vector<std::vector<EdgeRec>> res;
+    for (int32_t id : good) {
+      concat(id, 0, res);
+      for (auto& t : res) tr.push_back(Traj{id, nodes[id].k3, t});
+    }
+    std::stable_sort(tr.begin(), tr.end(), [](const Traj& a, const Traj& b) {  // :739
+      if (a.k3 != b.k3) return a.k3 > b.k3;
+      return a.mv.size() < b.mv.size();
+    });
+    if (o.maxreport >= 0 && (int64_t)tr.size() > o.maxreport) tr.resize((size_t)o.maxreport);  // :740-743
+    static const char* names[3] = {"move_dup", "move_del", "move_inv"};
+    R->t_off.push_back(0);
+    for (const Traj& t : tr) {
+      const Node& nd = nodes[t.id];
+      R->t_score.push_back(score_f32(t.k3));
+      R->t_k3.push_back(t.k3);
+      R->t_id.push_back(t.id);
+      R->t_cost.push_back(nd.cost < 0 ? nd.cost : (int64_t)nd.cost * c->RH.gcd);
+      R->t_total.push_back((int64_t)nd.total * c->RH.gcd);
+      std::string line = score_string(t.k3) + "\t" + std::to_string(t.mv.size()) + "\t";  // :723
+      bool first = true;
+      for (const EdgeRec& e : t.mv) {
+        const int kind = e.kind_i & 3, i = e.kind_i >> 2, j = e.j;
+        R->t_moves.push_back(kind);
+        R->t_moves.push_back(i);
+        R->t_moves.push_back(j);
+        if (!first) line += "\t";
+        first = false;
+        line += std::string(names[kind]) + "\t" + std::to_string(i) + "\t" + std::to_string(j);  // :719
+      }
+      R->t_off.push_back((int64_t)R->t_moves.size());
+      R->tsv += line + "\n";
+    }
+  }
+
+  void dump_ids(nw_result* R) {
+    cudaStream_t s = c->stream;
+    R->id_score.assign(n_ids, 0.f);
+    R->id_cost.assign(n_ids, -1);
+    R->id_total.assign(n_ids, 0);
+    R->id_level.assign(n_ids, 0);
+    auto put = [&](int32_t id, int k3, int cost, int total, int level) {
+      R->id_score[id - 1] = score_f32(k3);
+      R->id_cost[id - 1] = cost < 0 ? cost : (int64_t)cost * c->RH.gcd;
+      R->id_total[id - 1] = (int64_t)total * c->RH.gcd;
+      R->id_level[id - 1] = level;
+    };
+    put(1, root_k3, root_cost, root_total, 0);
+    for (int l = 1; l < (int)lv.size(); ++l) {
+      const Level& L = lv[l];
+      if (L.n_new) {
+        std::vector<int32_t> k3(L.n_new), cost(L.n_new), total(L.n_new);
+        CK(cudaMemcpyAsync(k3.data(), L.k3.p, (size_t)L.n_new * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(cost.data(), L.cost.p, (size_t)L.n_new * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(total.data(), L.total.p, (size_t)L.n_new * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (uint32_t r = 0; r < L.n_new; ++r) put(L.id_base + (int32_t)r, k3[r], cost[r], total[r], l);
+      }
+      if (L.G) {
+        std::vector<int32_t> cid(L.G), fid(L.P);
+        std::vector<uint64_t> desc(L.G);
+        CK(cudaMemcpyAsync(cid.data(), L.cand_id.p, (size_t)L.G * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(desc.data(), L.desc.p, (size_t)L.G * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(fid.data(), L.fid.p, (size_t)L.P * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (uint32_t g = 0; g < L.G; ++g) {
+          R->e_child.push_back(cid[g]);
+          R->e_parent.push_back(fid[desc_parent(desc[g])]);
+          R->e_moves.push_back(desc_kind(desc[g]));
+          R->e_moves.push_back(desc_i(desc[g]));
+          R->e_moves.push_back(desc_j(desc[g]));
+        }
+      }
+    }
+  }
+};
+
+int guard(const std::function<void()>& fn) {
+  try {
+    fn();
+    return NW_OK;
+  } catch (const Err& e) {
+    g_last_error = e.msg;
+    return e.code;
+  } catch (const HostError& e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    g_last_error = "host out of memory";
+    return NW_ERR_NOMEM;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return NW_ERR_ARG;
+  }
+}
+
+void check_opts(const nw_opts* o) {
+  if (!o) fail(NW_ERR_ARG, "opts is null");
+  if (o->maxdepth < 1 || o->maxdepth >= MAX_LEVELS) fail(NW_ERR_ARG, "maxdepth must be in [1, 15]");
+  if (o->maxdup < 0) fail(NW_ERR_ARG, "maxdup must be >= 0");
+}
+
+void do_solve(nw_ctx* c, const int8_t* aln, int n_x, int n_y, const int64_t* len_x, const int64_t* len_y,
+              const nw_opts* o, nw_result* R) {
+  CK(cudaSetDevice(c->device));
+  c->launches = 0;
+  setup_region(c, aln, n_x, n_y, len_x, len_y, o->maxdepth, false);
+  Search S(c, *o);
+  S.run();
+  if (!(o->flags & NW_FLAG_NO_TRAJ)) S.report(R);
+  if (o->keep_ids) S.dump_ids(R);
+  S.st.kernel_launches = c->launches;
+  R->stats = S.st;
+}
+
+}  // namespace
+
+extern "C" {
+
+void nw_default_opts(nw_opts* o) {
+  if (!o) return;
+  o->maxdepth = 3;
+  o->maxdup = 3;
+  o->maxwidth = -1;
+  o->minreport = 0.95;
+  o->maxreport = -1;
+  o->keep_ids = 0;
+  o->flags = 0;
+}
+const char* nw_last_error(void) { return g_last_error.c_str(); }
+const char* nw_version(void) { return "nwsolve-b200 0.1 (sm_100a)"; }
+
+int nw_ctx_create(int device, nw_ctx** out) {
+  if (!out) return NW_ERR_ARG;
+  *out = nullptr;
+  return guard([&] {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      fail(NW_ERR_CUDA, std::string("no CUDA device: ") + (e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)));
+    if (device < 0) {
+      const char* lr = getenv("LOCAL_RANK");
+      device = lr ? atoi(lr) % ndev : 0;
+    }
+    if (device >= ndev) fail(NW_ERR_ARG, "device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) fail(NW_ERR_CUDA, std::string("device is not sm_100 (Blackwell B200): ") + prop.name);
+    nw_ctx* c = new nw_ctx();
+    c->device = device;
+    try {
+      CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      CK(cudaMallocHost(&c->pinned, PINNED_BYTES));
+      c->h_pow = build_pow_table();
+      CK(cudaMemcpy(c->d_pow.ensure(c->h_pow.size() * sizeof(U4)), c->h_pow.data(), c->h_pow.size() * sizeof(U4),
+                    cudaMemcpyHostToDevice));
+      c->misc.ensure(256);
+    } catch (...) {
+      nw_ctx_destroy(c);
+      throw;
+    }
+    *out = c;
+  });
+}
+
+void nw_ctx_destroy(nw_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->pinned) cudaFreeHost(c->pinned);
+  cudaStream_t s = c->stream;
+  delete c;
+  if (s) cudaStreamDestroy(s);
+}
+
+int nw_solve(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const int64_t* len_x, const int64_t* len_y,
+             const nw_opts* o, nw_result** out) {
+  if (!c || !aln || !len_x || !len_y || !out) {
+    g_last_error = "null argument";
+    return NW_ERR_ARG;
+  }
+  *out = nullptr;
+  nw_result* R = new nw_result();
+  const int rc = guard([&] {
+    check_opts(o);
+    do_solve(c, aln, n_x, n_y, len_x, len_y, o, R);
+  });
+  if (rc != NW_OK) {
+    delete R;
+    cudaGetLastError();
+    return rc;
+  }
+  *out = R;
+  return NW_OK;
+}
+
+int nw_solve_files(nw_ctx* c, const char* inmat, const char* inlens, const char* outp, const nw_opts* o,
+                   nw_stats* stats) {
+  if (!c || !inmat || !inlens || !outp) {
+    g_last_error = "null argument";
+    return NW_ERR_ARG;
+  }
+  nw_result R;
+  const int rc = guard([&] {
+    check_opts(o);
+    ProblemHost P = read_problem(inmat, inlens);
+    do_solve(c, P.aln.data(), P.n_x, P.n_y, P.len_x.data(), P.len_y.data(), o, &R);
+    const std::string tmp = std::string(outp) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) fail(NW_ERR_IO, std::string("cannot write ") + tmp);
+    const size_t w = fwrite(R.tsv.data(), 1, R.tsv.size(), f);
+    const int cl = fclose(f);
+    if (w != R.tsv.size() || cl != 0) {
+      remove(tmp.c_str());
+      fail(NW_ERR_IO, std::string("short write to ") + tmp);
+    }
+    if (rename(tmp.c_str(), outp) != 0) {
+      remove(tmp.c_str());
+      fail(NW_ERR_IO, std::string("cannot rename to ") + outp);
+    }
+  });
+  if (rc != NW_OK) cudaGetLastError();
+  if (rc == NW_OK && stats) *stats = R.stats;
+  return rc;
+}
+
+int64_t nw_result_count(const nw_result* r) { return r ? (int64_t)r->t_score.size() : 0; }
+int nw_result_get(const nw_result* r, int64_t k, float* score, int32_t* n_moves, const int32_t** moves3) {
+  if (!r || k < 0 || k >= (int64_t)r->t_score.size()) return NW_ERR_ARG;
+  if (score) *score = r->t_score[k];
+  if (n_moves) *n_moves = (int32_t)((r->t_off[k + 1] - r->t_off[k]) / 3);
+  if (moves3) *moves3 = r->t_moves.data() + r->t_off[k];
+  return NW_OK;
+}
+int nw_result_cost(const nw_result* r, int64_t k, int64_t* cost_bp, int64_t* total_bp, int64_t* index_id) {
+  if (!r || k < 0 || k >= (int64_t)r->t_score.size()) return NW_ERR_ARG;
+  if (cost_bp) *cost_bp = r->t_cost[k];
+  if (total_bp) *total_bp = r->t_total[k];
+  if (index_id) *index_id = r->t_id[k];
+  return NW_OK;
+}
+int nw_result_tsv(const nw_result* r, const char** data, int64_t* len) {
+  if (!r || !data || !len) return NW_ERR_ARG;
+  *data = r->tsv.data();
+  *len = (int64_t)r->tsv.size();
+  return NW_OK;
+}
+int nw_result_stats(const nw_result* r, nw_stats* out) {
+  if (!r || !out) return NW_ERR_ARG;
+  *out = r->stats;
+  return NW_OK;
+}
+int nw_result_ids(const nw_result* r, float* score, int64_t* cost_bp, int64_t* total_bp, int32_t* level) {
+  if (!r || r->id_score.empty()) return NW_ERR_ARG;
+  const size_t n = r->id_score.size();
+  if (score) memcpy(score, r->id_score.data(), n * 4);
+  if (cost_bp) memcpy(cost_bp, r->id_cost.data(), n * 8);
+  if (total_bp) memcpy(total_bp, r->id_total.data(), n * 8);
+  if (level) memcpy(level, r->id_level.data(), n * 4);
+  return NW_OK;
+}
+int64_t nw_result_edge_count(const nw_result* r) { return r ? (int64_t)r->e_child.size() : 0; }
+int nw_result_edges(const nw_result* r, int32_t* child, int32_t* parent, int32_t* moves3) {
+  if (!r) return NW_ERR_ARG;
+  const size_t n = r->e_child.size();
+  if (child) memcpy(child, r->e_child.data(), n * 4);
+  if (parent) memcpy(parent, r->e_parent.data(), n * 4);
+  if (moves3) memcpy(moves3, r->e_moves.data(), n * 12);
+  return NW_OK;
+}
+void nw_result_free(nw_result* r) { delete r; }
+
+int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const int64_t* len_x, const int64_t* len_y,
+                   const int16_t* flat, const int64_t* off, int64_t n, int32_t force, int32_t flags, int64_t* cost_bp,
+                   int64_t* total_bp, double* score) {
+  if (!c || !aln || !len_x || !len_y || !flat || !off || n < 0) {
+    g_last_error = "null argument";
+    return NW_ERR_ARG;
+  }
+  const int rc = guard([&] {
+    CK(cudaSetDevice(c->device));
+    if (n == 0) return;
+    if (n >= (1ll << 31)) fail(NW_ERR_ARG, "too many candidates");
+    cudaStream_t s = c->stream;
+    int maxlen = 1;
+    for (int64_t k = 0; k < n; ++k) {
+      const int64_t l = off[k + 1] - off[k];
+      if (l < 1 || l > LMAX) fail(NW_ERR_ARG, "candidate length out of range");
+      maxlen = std::max<int>(maxlen, (int)l);
+      for (int64_t t = off[k]; t < off[k + 1]; ++t) {
+        const int v = flat[t];
+        if (v == 0 || v > n_x || v < -n_x) fail(NW_ERR_ARG, "candidate element out of range");
+      }
+    }
+    // depth bound for the int32 range: candidates may hold each block up to maxlen/n_x times
+    int depth_equiv = 0;
+    while (((int64_t)n_x << depth_equiv) < maxlen) ++depth_equiv;
+    setup_region(c, aln, n_x, n_y, len_x, len_y, depth_equiv, force != 0);
+    // candidates as a "frontier" of n parents scored through KIND_ID descriptors
+    Level L;
+    L.P = (int)n;
+    L.LS = round_ls(maxlen);
+    L.pstride = (uint32_t)L.LS * 2;  // sequence only (no prefix tables needed for scoring)
+    std::vector<int16_t> seqs((size_t)n * L.LS, 0);
+    std::vector<int32_t> lens(n);
+    std::vector<uint64_t> desc(n);
+    std::vector<uint32_t> newlist(n);
+    std::vector<uint16_t> nlen(n);
+    std::vector<uint32_t> hist(LMAX + 2, 0);
+    std::vector<int32_t> k3(n, 0), cost(n, -1), total(n, 0);
+    for (int64_t k = 0; k < n; ++k) {
+      const int l = (int)(off[k + 1] - off[k]);
+      memcpy(&seqs[(size_t)k * L.LS], flat + off[k], (size_t)l * 2);
+      lens[k] = l;
+      desc[k] = pack_desc((uint32_t)k, 0, 0, KIND_ID);
+      newlist[k] = (uint32_t)k;
+      nlen[k] = (uint16_t)l;
+      if (force || !early_exit(l, n_y)) hist[l]++;
+    }
+    L.G = (uint32_t)n;
+    L.n_new = (uint32_t)n;
+    CK(cudaMemcpyAsync(L.fblob.ensure(seqs.size() * 2), seqs.data(), seqs.size() * 2, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(L.flen.ensure(n * 4), lens.data(), n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(L.desc.ensure(n * 8), desc.data(), n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(L.newlist.ensure(n * 4), newlist.data(), n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->new_len.ensure(n * 2, true), nlen.data(), n * 2, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(L.k3.ensure(n * 4), k3.data(), n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(L.cost.ensure(n * 4), cost.data(), n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(L.total.ensure(n * 4), total.data(), n * 4, cudaMemcpyHostToDevice, s));
+    int32_t* misc = (int32_t*)c->misc.ensure(256);
+    CK(cudaMemsetAsync(misc, 0, 256, s));
+    CK(cudaStreamSynchronize(s));
+    run_scoring(c, view_of(L), hist.data(), force, flags, misc + 1, nullptr);
+    CK(cudaMemcpyAsync(k3.data(), L.k3.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(cost.data(), L.cost.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(total.data(), L.total.p, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    for (int64_t k = 0; k < n; ++k) {
+      if (cost_bp) cost_bp[k] = cost[k] < 0 ? cost[k] : (int64_t)cost[k] * c->RH.gcd;
+      if (total_bp) total_bp[k] = (int64_t)total[k] * c->RH.gcd;
+      if (score) score[k] = k3[k] < 0 ? -INFINITY : k3_to_score(k3[k]);
+    }
+  });
+  if (rc != NW_OK) cudaGetLastError();
+  return rc;
+}
+
+int nw_moveset(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, uint8_t* dup_del, uint8_t* invert) {
+  if (!c || !aln || !dup_del || !invert) {
+    g_last_error = "null argument";
+    return NW_ERR_ARG;
+  }
+  const int rc = guard([&] {
+    CK(cudaSetDevice(c->device));
+    std::vector<int64_t> lx(n_x, 1), ly(n_y, 1);
+    setup_region(c, aln, n_x, n_y, lx.data(), ly.data(), 1, false);
+    const int MW = c->RH.MW;
+    std::vector<uint32_t> dd((size_t)(n_x + 1) * MW), iv((size_t)(n_x + 1) * MW);
+    CK(cudaMemcpyAsync(dd.data(), c->d_msdd.p, dd.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(iv.data(), c->d_msinv.p, iv.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    for (int a = 1; a <= n_x; ++a)
+      for (int b = 1; b <= n_x; ++b) {
+        dup_del[(size_t)(a - 1) * n_x + (b - 1)] = (dd[(size_t)a * MW + (b >> 5)] >> (b & 31)) & 1u;
+        invert[(size_t)(a - 1) * n_x + (b - 1)] = (iv[(size_t)a * MW + (b >> 5)] >> (b & 31)) & 1u;
+      }
+  });
+  if (rc != NW_OK) cudaGetLastError();
+  return rc;
+}
+
+int nw_read_problem(const char* inmat, const char* inlens, int8_t** aln, int32_t* n_x, int32_t* n_y, int64_t** len_x,
+                    int64_t** len_y) {
+  if (!inmat || !inlens || !aln || !n_x || !n_y || !len_x || !len_y) return NW_ERR_ARG;
+  return guard([&] {
+    ProblemHost P = read_problem(inmat, inlens);
+    *n_x = P.n_x;
+    *n_y = P.n_y;
+    *aln = (int8_t*)malloc(P.aln.size());
+    *len_x = (int64_t*)malloc(P.len_x.size() * 8);
+    *len_y = (int64_t*)malloc(P.len_y.size() * 8);
+    memcpy(*aln, P.aln.data(), P.aln.size());
+    memcpy(*len_x, P.len_x.data(), P.len_x.size() * 8);
+    memcpy(*len_y, P.len_y.data(), P.len_y.size() * 8);
+  });
+}
+void nw_free(void* p) { free(p); }
+
+}  // extern "C"

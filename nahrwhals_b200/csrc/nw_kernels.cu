@@ -1,0 +1,734 @@
+// nw_kernels.cu -- sm_100a kernels of the mutation-space search (everything except the register-resident DP,
+// which lives in nw_score_fast.cu).  Reference semantics: inst/extdata/scripts/scripts_nw_main/solver.jl.
+#include "nw_kernels.cuh"
+#include "nw_launch.h"
+
+namespace nw {
+
+// =====================================================================================================
+// to_moveset  (solver.jl:217-231, compute_possible_moves :159-165)
+// One thread per (a, b): dup_del = any_y aln[a,y]*aln[b,y] == +1 ; invert = any_y product == -1, on bit-planes.
+// =====================================================================================================
+__global__ void k_moveset(RegionDev R) {
+  const int n = R.n_x;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)n * n) return;
+  const int a = (int)(t / n) + 1, b = (int)(t % n) + 1;
+  if (a == b) return;
+  const uint32_t* planes = reinterpret_cast<const uint32_t*>(R.ctx);
+  const uint32_t* pa = planes + (size_t)(a * 2) * R.PWS;
+  const uint32_t* pb = planes + (size_t)(b * 2) * R.PWS;
+  uint32_t dd = 0, iv = 0;
+  for (int w = 0; w < R.PWS; ++w) {
+    const uint32_t ap = pa[w], an = pa[R.PWS + w], bp = pb[w], bn = pb[R.PWS + w];
+    dd |= (ap & bp) | (an & bn);
+    iv |= (ap & bn) | (an & bp);
+  }
+  if (dd) atomicOr(&R.ms_dd[(size_t)a * R.MW + (b >> 5)], 1u << (b & 31));
+  if (iv) atomicOr(&R.ms_inv[(size_t)a * R.MW + (b >> 5)], 1u << (b & 31));
+}
+
+// =====================================================================================================
+// hash table: exact-dedup stand-in (solver.jl:535 haskey / :544 insert).  First discoverer = min gpos.
+// =====================================================================================================
+__device__ __forceinline__ uint32_t table_insert(uint64_t* T, uint64_t mask, uint64_t k0, uint64_t k1, uint64_t gpos) {
+  uint64_t s = fp_slot_hash(k0, k1) & mask;
+  while (true) {
+    unsigned long long* e = reinterpret_cast<unsigned long long*>(T + s * TBL_WORDS);
+    unsigned long long o0 = e[0];
+    if (o0 == TBL_EMPTY) o0 = atomicCAS(e, (unsigned long long)TBL_EMPTY, (unsigned long long)k0);
+    if (o0 == TBL_EMPTY || o0 == k0) {
+      unsigned long long o1 = atomicCAS(e + 1, (unsigned long long)TBL_EMPTY, (unsigned long long)k1);
+      if (o1 == TBL_EMPTY || o1 == k1) {
+        atomicMin(e + 2, (unsigned long long)gpos);
+        return (uint32_t)s;
+      }
+    }
+    s = (s + 1) & mask;
+  }
+}
+
+__global__ void k_table_rehash(const uint64_t* oldT, uint64_t old_cap, uint64_t* newT, uint64_t new_mask) {
+  for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < old_cap; s += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t k0 = oldT[s * TBL_WORDS];
+    if (k0 == TBL_EMPTY) continue;
+    table_insert(newT, new_mask, k0, oldT[s * TBL_WORDS + 1], oldT[s * TBL_WORDS + 2]);
+  }
+}
+
+// insert the root (gpos 0) -- solver.jl:596-604
+__global__ void k_insert_root(const int16_t* seq, int L, const U4* pw, uint32_t rid1, uint64_t* table, uint64_t tmask) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    U4 f = seq_fingerprint(seq, L, pw, rid1);
+    table_insert(table, tmask, fp_key0(f), fp_key1(f), 0ull);
+  }
+}
+
+// =====================================================================================================
+// expand: one CTA per parent.  Pair loop + retrieve_possible_moves + emission order dup, del, inv
+// (solver.jl:607-638, :180-190).  EMIT=false counts, EMIT=true writes descriptors in discovery order,
+// fingerprints each child through the index map and inserts it into the dedup table.
+// The parent blob (sequence + prefix-hash tables) is staged into shared memory with one TMA bulk copy.
+// =====================================================================================================
+__device__ __forceinline__ int pair_moves(const RegionDev& R, int a, int b, int dupok, int& can_dd, int& can_inv) {
+  const int aa = a < 0 ? -a : a, bb = b < 0 ? -b : b;
+  const bool flip = (a ^ b) < 0;
+  const bool dd = (__ldg(&R.ms_dd[(size_t)aa * R.MW + (bb >> 5)]) >> (bb & 31)) & 1u;
+  const bool iv = (__ldg(&R.ms_inv[(size_t)aa * R.MW + (bb >> 5)]) >> (bb & 31)) & 1u;
+  can_dd = flip ? iv : dd;   // :187
+  can_inv = flip ? dd : iv;  // :188
+  return can_dd * (1 + dupok) + can_inv;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_warp_tot[4];
+  const int parent = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = A.F.len[parent];
+  const int LS = A.F.LS;
+  const int dupok = A.F.dupok[parent];
+  int16_t* seq = reinterpret_cast<int16_t*>(smem);
+  const U4* Ft = reinterpret_cast<const U4*>(smem + (size_t)LS * 2);
+  const U4* Gt = Ft + (LS + 1);
+  const uint32_t blob_bytes = EMIT ? A.F.pstride : (uint32_t)LS * 2;
+  uint32_t* rowcnt = reinterpret_cast<uint32_t*>(smem + (EMIT ? A.F.pstride : (uint32_t)LS * 2));
+
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, blob_bytes);
+    tma_bulk_g2s(smem, A.F.blob + (size_t)parent * A.F.pstride, blob_bytes, &bar);
+  }
+  mbar_wait(&bar, 0);
+
+  // ---- pass 1: candidates per row i ----
+  int maxlen = 0;
+  for (int i = warp + 1; i <= L; i += 4) {
+    const int a = seq[i - 1];
+    uint32_t n = 0;
+    for (int j = i + 1 + lane; j <= L; j += 32) {
+      int cdd, civ;
+      n += pair_moves(A.R, a, seq[j - 1], dupok, cdd, civ);
+      if (cdd && dupok) maxlen = max(maxlen, L + (j - i));
+    }
+    for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (lane == 0) rowcnt[i - 1] = n;
+  }
+  __syncthreads();
+  // ---- exclusive scan of rowcnt over rows (warp 0) ----
+  if (warp == 0) {
+    uint32_t carry = 0;
+    for (int r0 = 0; r0 < L; r0 += 32) {
+      const int r = r0 + lane;
+      const uint32_t v = r < L ? rowcnt[r] : 0;
+      uint32_t inc = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (r < L) rowcnt[r] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) s_warp_tot[0] = carry;
+  }
+  __syncthreads();
+  if (!EMIT) {
+    if (tid == 0) A.cnt[parent] = s_warp_tot[0];
+    for (int o = 16; o; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    if (lane == 0 && maxlen > 0) atomicMax(A.maxlen, maxlen);
+    return;
+  }
+  // ---- pass 2: emit ----
+  const uint32_t base = A.off[parent];
+  for (int i = warp + 1; i <= L; i += 4) {
+    const int a = seq[i - 1];
+    uint32_t rowpos = base + rowcnt[i - 1];
+    for (int j0 = i + 1; j0 <= L; j0 += 32) {
+      const int j = j0 + lane;
+      int cdd = 0, civ = 0;
+      uint32_t n = 0;
+      if (j <= L) n = pair_moves(A.R, a, seq[j - 1], dupok, cdd, civ);
+      uint32_t inc = n;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      uint32_t pos = rowpos + inc - n;
+      rowpos += __shfl_sync(0xffffffffu, inc, 31);
+      if (n) {
+        int kinds[3];
+        int nk = 0;
+        if (cdd && dupok) kinds[nk++] = KIND_DUP;
+        if (cdd) kinds[nk++] = KIND_DEL;
+        if (civ) kinds[nk++] = KIND_INV;
+        for (int e = 0; e < nk; ++e) {
+          const int kind = kinds[e];
+          const U4 f = child_fingerprint(Ft, Gt, A.pw, L, kind, i, j, A.R.rid1);
+          const uint32_t s = table_insert(A.table, A.tmask, fp_key0(f), fp_key1(f), (uint64_t)A.gbase + pos);
+          A.desc[pos] = pack_desc((uint32_t)parent, i, j, kind);
+          A.slot[pos] = s;
+          ++pos;
+        }
+      }
+    }
+  }
+}
+
+int launch_expand(bool emit, const ExpandArgs& A, cudaStream_t st) {
+  if (A.F.P <= 0) return 0;
+  const size_t rows = (size_t)A.F.LS * 4;
+  if (emit) {
+    const size_t sm = A.F.pstride + rows;
+    cudaFuncSetAttribute(k_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    k_expand<true><<<A.F.P, 128, sm, st>>>(A);
+  } else {
+    const size_t sm = (size_t)A.F.LS * 2 + rows;
+    cudaFuncSetAttribute(k_expand<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    k_expand<false><<<A.F.P, 128, sm, st>>>(A);
+  }
+  return 1;
+}
+
+// =====================================================================================================
+// exclusive scan (uint32) -- three kernels, 4096 items per block
+// =====================================================================================================
+constexpr int SCAN_T = 256, SCAN_I = 16, SCAN_B = SCAN_T * SCAN_I;
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* sh /*[33]*/, uint32_t& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint32_t inc = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) sh[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < nw ? sh[lane] : 0;
+    uint32_t wi = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    sh[lane] = wi - w;
+    if (lane == 31) sh[32] = wi;
+  }
+  __syncthreads();
+  const uint32_t r = sh[warp] + inc - v;
+  total = sh[32];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_partial(const uint32_t* in, uint64_t n, uint32_t* bsum) {
+  __shared__ uint32_t sh[33];
+  const uint64_t b0 = (uint64_t)blockIdx.x * SCAN_B;
+  uint32_t s = 0;
+  for (int k = 0; k < SCAN_I; ++k) {
+    const uint64_t idx = b0 + (uint64_t)k * SCAN_T + threadIdx.x;
+    if (idx < n) s += in[idx];
+  }
+  uint32_t tot;
+  block_excl_scan(s, sh, tot);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(1024) k_scan_bsums(uint32_t* bsum, uint32_t nb, uint32_t* total_out) {
+  __shared__ uint32_t sh[33];
+  uint32_t carry = 0;
+  for (uint32_t c0 = 0; c0 < nb; c0 += 1024) {
+    const uint32_t idx = c0 + threadIdx.x;
+    const uint32_t v = idx < nb ? bsum[idx] : 0;
+    uint32_t tot;
+    const uint32_t e = block_excl_scan(v, sh, tot);
+    if (idx < nb) bsum[idx] = carry + e;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_final(const uint32_t* in, uint32_t* out, uint64_t n, const uint32_t* bsum) {
+  __shared__ uint32_t sh[33];
+  const uint64_t b0 = (uint64_t)blockIdx.x * SCAN_B + (uint64_t)threadIdx.x * SCAN_I;
+  uint32_t v[SCAN_I];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_I; ++k) {
+    v[k] = (b0 + k < n) ? in[b0 + k] : 0;
+    s += v[k];
+  }
+  uint32_t tot;
+  uint32_t e = block_excl_scan(s, sh, tot) + bsum[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_I; ++k) {
+    if (b0 + k < n) out[b0 + k] = e;
+    e += v[k];
+  }
+}
+
+int launch_scan(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* bsum_scratch, uint32_t* total_out,
+                cudaStream_t st) {
+  if (n == 0) {
+    cudaMemsetAsync(total_out, 0, sizeof(uint32_t), st);
+    return 0;
+  }
+  const uint32_t nb = (uint32_t)((n + SCAN_B - 1) / SCAN_B);
+  k_scan_partial<<<nb, SCAN_T, 0, st>>>(in, n, bsum_scratch);
+  k_scan_bsums<<<1, 1024, 0, st>>>(bsum_scratch, nb, total_out);
+  k_scan_final<<<nb, SCAN_T, 0, st>>>(in, out, n, bsum_scratch);
+  return 3;
+}
+uint64_t scan_scratch_items(uint64_t n) { return (n + SCAN_B - 1) / SCAN_B + 1; }
+
+// =====================================================================================================
+// resolve / assign: which candidate is the first discoverer of its index (solver.jl:535-561)
+// =====================================================================================================
+__global__ void k_resolve(const uint32_t* slot, const uint64_t* table, uint32_t gbase, uint32_t G, uint32_t* is_new) {
+  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= G) return;
+  is_new[pos] = table[(uint64_t)slot[pos] * TBL_WORDS + 2] == (uint64_t)gbase + pos ? 1u : 0u;
+}
+
+__device__ __forceinline__ int32_t owner_id(const LevelTable& LT, uint32_t g) {
+  int l = 0;
+  while (l + 1 < LT.n_levels && g >= LT.gbase[l + 1]) ++l;
+  return LT.cand_id[l][g - LT.gbase[l]];
+}
+
+__global__ void k_assign(AssignArgs A) {
+  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = pos < A.G;
+  int Lc = 0xffff;  // histogram key of lanes that need a DP; 0xffff = none
+  if (in) {
+    const uint64_t og = A.table[(uint64_t)A.slot[pos] * TBL_WORDS + 2];
+    if (A.is_new[pos]) {
+      const uint32_t r = A.newrank[pos];
+      A.cand_id[pos] = A.id_base + (int32_t)r;
+      A.newlist[r] = pos;
+      const uint64_t d = A.desc[pos];
+      const int len = child_len(A.front_len[desc_parent(d)], desc_kind(d), desc_i(d), desc_j(d));
+      A.new_len[r] = (uint16_t)len;
+      if (!A.force && early_exit(len, A.n_y)) {  // solver.jl:332-334 -> score 0.0, no DP
+        A.k3[r] = 0;
+        A.cost[r] = -1;
+        A.total[r] = 0;
+      } else {
+        Lc = len;
+      }
+    } else {
+      const uint32_t g = (uint32_t)og;
+      A.cand_id[pos] = g >= A.gbase ? A.id_base + (int32_t)A.newrank[g - A.gbase] : owner_id(A.LT, g);
+    }
+  }
+  // warp-aggregated histogram over child lengths (all 32 lanes converge here)
+  const uint32_t peers = __match_any_sync(0xffffffffu, Lc);
+  if (Lc != 0xffff && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31))
+    atomicAdd(&A.hist[Lc], (uint32_t)__popc(peers));
+}
+
+int launch_assign(const AssignArgs& A, cudaStream_t st) {
+  if (A.G == 0) return 0;
+  k_assign<<<(A.G + 255) / 256, 256, 0, st>>>(A);
+  return 1;
+}
+int launch_resolve(const uint32_t* slot, const uint64_t* table, uint32_t gbase, uint32_t G, uint32_t* is_new,
+                   cudaStream_t st) {
+  if (G == 0) return 0;
+  k_resolve<<<(G + 255) / 256, 256, 0, st>>>(slot, table, gbase, G, is_new);
+  return 1;
+}
+
+// scatter the DP-needing new candidates into per-length buckets (each padded to a multiple of 32 lanes)
+__global__ void k_bucket_scatter(const uint16_t* new_len, uint32_t n_new, int n_y, int force, const uint32_t* bstart,
+                                 uint32_t* cursor, uint32_t* work) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  int Lc = 0xffff;
+  if (r < n_new) {
+    const int len = new_len[r];
+    if (force || !early_exit(len, n_y)) Lc = len;
+  }
+  const uint32_t peers = __match_any_sync(0xffffffffu, Lc);
+  const int leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if (Lc != 0xffff && (int)(threadIdx.x & 31) == leader) base = atomicAdd(&cursor[Lc], (uint32_t)__popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (Lc != 0xffff) {
+    const uint32_t mine = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+    work[bstart[Lc] + base + mine] = r;
+  }
+}
+int launch_bucket_scatter(const uint16_t* new_len, uint32_t n_new, int n_y, int force, const uint32_t* bstart,
+                          uint32_t* cursor, uint32_t* work, cudaStream_t st) {
+  if (n_new == 0) return 0;
+  k_bucket_scatter<<<(n_new + 255) / 256, 256, 0, st>>>(new_len, n_new, n_y, force, bstart, cursor, work);
+  return 1;
+}
+
+// =====================================================================================================
+// generic DP: literal cost-form transcription of slow_score (solver.jl:362-423) in int32 units, any geometry.
+// Thread per candidate; the two DP rows live in a coalesced global scratch [2][n_y+2][threads].
+// =====================================================================================================
+__device__ __forceinline__ int sat_add(int a, int b) { return a >= DP_INF ? DP_INF : min(a + b, DP_INF); }
+
+__global__ void __launch_bounds__(128) k_score_generic(ScoreArgs A) {
+  const uint32_t T = gridDim.x * blockDim.x;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ny = A.R.n_y;
+  int32_t* row0 = A.scratch + tid;
+  const size_t rstride = (size_t)(ny + 2) * T;
+  const uint32_t* planes = reinterpret_cast<const uint32_t*>(A.R.ctx);
+  const int32_t* upx = reinterpret_cast<const int32_t*>(A.R.ctx + A.R.off_upx);
+  unsigned long long cells = 0;
+  int best = -1;
+  for (uint32_t w = tid; w < A.n_work; w += T) {
+    const uint32_t r = A.work[w];
+    if (r == WORK_PAD) continue;
+    const uint64_t d = A.desc[A.newlist[r]];
+    const uint32_t ps = desc_parent(d);
+    const int kind = desc_kind(d), p = desc_i(d), q = desc_j(d);
+    const int L = A.F.len[ps];
+    const int16_t* seq = reinterpret_cast<const int16_t*>(A.F.blob + (size_t)ps * A.F.pstride);
+    const int Lc = child_len(L, kind, p, q);
+    const int16_t* ab = A.band_ab + (size_t)A.band_off[Lc] * 2;
+    int cur = 0;
+    int cumU = 0;
+    for (int i = 1; i <= Lc; ++i) {
+      const int c = child_elem(seq, kind, p, q, i);
+      const int x = c < 0 ? -c : c;
+      const uint32_t* pl = planes + (size_t)(x * 2 + (c < 0 ? 1 : 0)) * A.R.PWS;
+      const int up = upx[x];
+      const int a = ab[i * 2], b = ab[i * 2 + 1];
+      int32_t* rc = row0 + (size_t)cur * rstride;
+      const int32_t* rp = row0 + (size_t)(cur ^ 1) * rstride;
+      int left = DP_INF;  // C[i][j-1]
+      for (int j = 1; j <= ny; ++j) {
+        int v = DP_INF;
+        if (j >= a && j <= b) {
+          const int rr = A.R.NYP - 1 - j;
+          const bool match = (pl[rr >> 5] >> (rr & 31)) & 1u;
+          const int dcost = match ? 0 : DP_INF;
+          const int rt = A.R.rt[j];
+          if (i == 1 && j == 1) {
+            v = min(up + rt, dcost);  // :362
+          } else if (j == 1) {
+            v = min(sat_add(rp[(size_t)1 * T], up), sat_add(dcost, cumU));  // :393 (cumU = cumsum_u[i-1])
+          } else if (i == 1) {
+            v = min(sat_add(left, rt), sat_add(dcost, A.R.cumr[j - 1]));  // :403
+          } else {
+            v = min(sat_add(rp[(size_t)(j - 1) * T], dcost),
+                    min(sat_add(rp[(size_t)j * T], up), sat_add(left, rt)));  // :420-422
+          }
+          ++cells;
+        }
+        rc[(size_t)j * T] = v;
+        left = v;
+      }
+      cumU += up;
+      cur ^= 1;
+    }
+    const int32_t* rl = row0 + (size_t)(cur ^ 1) * rstride;
+    const int fin = rl[(size_t)ny * T];
+    const int total = cumU + A.R.sum_rt;
+    A.total[r] = total;
+    if (fin >= DP_INF) {
+      A.cost[r] = -2;
+      A.k3[r] = K3_NEGINF;
+    } else {
+      A.cost[r] = fin;
+      const int k3 = score_k3(fin, total);
+      A.k3[r] = k3;
+      best = max(best, k3);
+    }
+  }
+  if (best >= 0) atomicMax(A.best_k3, best);
+  if (cells && A.cells) atomicAdd(A.cells, cells);
+}
+
+int generic_threads() { return 148 * 4 * 128; }
+int launch_score_generic(const ScoreArgs& A, cudaStream_t st) {
+  if (A.n_work == 0) return 0;
+  k_score_generic<<<148 * 4, 128, 0, st>>>(A);
+  return 1;
+}
+
+// =====================================================================================================
+// frontier selection (solver.jl:551-553 push if score >= 0 ; :669-672 stable sort by -score, keep max_count)
+// =====================================================================================================
+__global__ void k_valid_flags(const int32_t* k3, uint32_t n, uint32_t* flag) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) flag[r] = k3[r] >= 0 ? 1u : 0u;
+}
+__global__ void k_compact_ranks(const uint32_t* flag, const uint32_t* pre, uint32_t n, uint32_t* sel) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n && flag[r]) sel[pre[r]] = r;
+}
+// sort key: ascending key == descending Float32 score, ties by discovery rank (stable order of solver.jl:670)
+__global__ void k_make_keys(const int32_t* k3, const uint32_t* flag, const uint32_t* pre, uint32_t n, uint64_t* keys) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n && flag[r]) keys[pre[r]] = ((uint64_t)(uint32_t)(100000 - k3[r]) << 32) | r;
+}
+__global__ void k_fill_u64(uint64_t* p, uint64_t n0, uint64_t n1, uint64_t v) {
+  const uint64_t i = n0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n1) p[i] = v;
+}
+// bitonic sort: local (shared memory, 2048 keys / CTA) + global steps
+constexpr int BIT_CHUNK = 2048;
+__global__ void __launch_bounds__(1024) k_bitonic_local(uint64_t* keys, uint32_t kstart) {
+  // kstart == 0: full local sort of each chunk (k = 2..BIT_CHUNK); otherwise finish stage k=kstart for j < BIT_CHUNK
+  __shared__ uint64_t s[BIT_CHUNK];
+  const uint64_t base = (uint64_t)blockIdx.x * BIT_CHUNK;
+  s[threadIdx.x] = keys[base + threadIdx.x];
+  s[threadIdx.x + 1024] = keys[base + threadIdx.x + 1024];
+  __syncthreads();
+  const uint32_t k0 = kstart ? kstart : 2;
+  const uint32_t k1 = kstart ? kstart : BIT_CHUNK;
+  for (uint32_t k = k0; k <= k1; k <<= 1) {
+    for (uint32_t j = min(k >> 1, (uint32_t)BIT_CHUNK >> 1); j > 0; j >>= 1) {
+      const uint32_t t = threadIdx.x;
+      const uint32_t lo = ((t / j) * 2 * j) + (t % j);
+      const uint32_t hi = lo + j;
+      const uint64_t gi = base + lo;
+      const bool asc = ((gi & k) == 0);
+      const uint64_t a = s[lo], b = s[hi];
+      if ((a > b) == asc) {
+        s[lo] = b;
+        s[hi] = a;
+      }
+      __syncthreads();
+    }
+  }
+  keys[base + threadIdx.x] = s[threadIdx.x];
+  keys[base + threadIdx.x + 1024] = s[threadIdx.x + 1024];
+}
+__global__ void k_bitonic_global(uint64_t* keys, uint64_t n, uint32_t j, uint32_t k) {
+  const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (t >= n / 2) return;
+  const uint64_t lo = ((t / j) * 2 * j) + (t % j);
+  const uint64_t hi = lo + j;
+  const bool asc = ((lo & k) == 0);
+  const uint64_t a = keys[lo], b = keys[hi];
+  if ((a > b) == asc) {
+    keys[lo] = b;
+    keys[hi] = a;
+  }
+}
+// sorts keys[0..npad) ascending; npad power of two >= BIT_CHUNK
+int launch_sort_u64(uint64_t* keys, uint64_t npad, cudaStream_t st) {
+  int launches = 0;
+  k_bitonic_local<<<(uint32_t)(npad / BIT_CHUNK), 1024, 0, st>>>(keys, 0);
+  ++launches;
+  for (uint64_t k = (uint64_t)BIT_CHUNK * 2; k <= npad; k <<= 1) {
+    for (uint64_t j = k >> 1; j >= BIT_CHUNK; j >>= 1) {
+      k_bitonic_global<<<(uint32_t)((npad / 2 + 255) / 256), 256, 0, st>>>(keys, npad, (uint32_t)j, (uint32_t)k);
+      ++launches;
+    }
+    k_bitonic_local<<<(uint32_t)(npad / BIT_CHUNK), 1024, 0, st>>>(keys, (uint32_t)k);
+    ++launches;
+  }
+  return launches;
+}
+__global__ void k_keys_to_sel(const uint64_t* keys, uint32_t n, uint32_t* sel) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) sel[t] = (uint32_t)(keys[t] & 0xffffffffu);
+}
+
+int launch_valid_flags(const int32_t* k3, uint32_t n, uint32_t* flag, cudaStream_t st) {
+  if (!n) return 0;
+  k_valid_flags<<<(n + 255) / 256, 256, 0, st>>>(k3, n, flag);
+  return 1;
+}
+int launch_compact_ranks(const uint32_t* flag, const uint32_t* pre, uint32_t n, uint32_t* sel, cudaStream_t st) {
+  if (!n) return 0;
+  k_compact_ranks<<<(n + 255) / 256, 256, 0, st>>>(flag, pre, n, sel);
+  return 1;
+}
+int launch_make_keys(const int32_t* k3, const uint32_t* flag, const uint32_t* pre, uint32_t n, uint64_t* keys,
+                     uint64_t nvalid, uint64_t npad, cudaStream_t st) {
+  int l = 0;
+  if (npad > nvalid) {
+    k_fill_u64<<<(uint32_t)((npad - nvalid + 255) / 256), 256, 0, st>>>(keys, nvalid, npad, ~0ull);
+    ++l;
+  }
+  if (n) {
+    k_make_keys<<<(n + 255) / 256, 256, 0, st>>>(k3, flag, pre, n, keys);
+    ++l;
+  }
+  return l;
+}
+int launch_keys_to_sel(const uint64_t* keys, uint32_t n, uint32_t* sel, cudaStream_t st) {
+  if (!n) return 0;
+  k_keys_to_sel<<<(n + 255) / 256, 256, 0, st>>>(keys, n, sel);
+  return 1;
+}
+
+// =====================================================================================================
+// materialise the next frontier: child sequences (apply_* :244-278 through the index map), duplication_count
+// guard of the *next* expansion (:292-298, :611) and the prefix-hash tables used by k_expand.
+// One CTA (256 threads = 8 warps: one per (base, F|G) table) per selected child.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_materialise(MaterialiseArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  int16_t* cs = reinterpret_cast<int16_t*>(smem);                                        // [LS2]
+  int* cntx = reinterpret_cast<int*>(smem + (((size_t)A.LS2 * 2 + 15) & ~(size_t)15));  // [n_x+1]
+  __shared__ int s_max;
+  const int e = blockIdx.x;
+  const uint32_t r = A.sel[e];
+  const uint64_t d = A.desc[A.newlist[r]];
+  const uint32_t ps = desc_parent(d);
+  const int kind = desc_kind(d), p = desc_i(d), q = desc_j(d);
+  const int L = A.F.len[ps];
+  const int16_t* seq = reinterpret_cast<const int16_t*>(A.F.blob + (size_t)ps * A.F.pstride);
+  const int Lc = child_len(L, kind, p, q);
+  unsigned char* out = A.blob2 + (size_t)e * A.pstride2;
+  int16_t* oseq = reinterpret_cast<int16_t*>(out);
+  if (threadIdx.x == 0) s_max = 0;
+  for (int x = threadIdx.x; x <= A.n_x; x += blockDim.x) cntx[x] = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < A.LS2; t += blockDim.x) {
+    int c = 0;
+    if (t < Lc) {
+      c = child_elem(seq, kind, p, q, t + 1);
+      const int m = atomicAdd(&cntx[c < 0 ? -c : c], 1) + 1;
+      atomicMax(&s_max, m);
+    }
+    cs[t] = (int16_t)c;
+    oseq[t] = (int16_t)c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    A.len2[e] = Lc;
+    A.id2[e] = A.id_base + (int32_t)r;
+    A.dupok2[e] = s_max <= A.maxdup ? 1 : 0;
+  }
+  // prefix tables: warp w -> base (w & 3), table (w >> 2): 0 = F (B^t), 1 = G (B^-t)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = warp & 3, which = warp >> 2;
+  U4* tab = reinterpret_cast<U4*>(out + (size_t)A.LS2 * 2) + (which ? (A.LS2 + 1) : 0);
+  uint32_t carry = 0;
+  if (lane == 0) tab[0].v[k] = 0;
+  for (int t0 = 0; t0 < Lc; t0 += 32) {
+    const int t = t0 + lane;
+    uint32_t term = 0;
+    if (t < Lc) term = mulmod(elem_val(cs[t]), A.pw[FP_EMAX + (which ? -t : t)].v[k]);
+    uint32_t inc = term;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc = addmod(inc, u);
+    }
+    if (t < Lc) tab[t + 1].v[k] = addmod(carry, inc);
+    carry = addmod(carry, __shfl_sync(0xffffffffu, inc, 31));
+  }
+  // entries beyond Lc are never read (k_expand indexes F[<=L], G[<=L])
+}
+
+int launch_materialise(const MaterialiseArgs& A, cudaStream_t st) {
+  if (A.P2 <= 0) return 0;
+  const size_t sm = (((size_t)A.LS2 * 2 + 15) & ~(size_t)15) + (size_t)(A.n_x + 1) * 4;
+  cudaFuncSetAttribute(k_materialise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k_materialise<<<A.P2, 256, sm, st>>>(A);
+  return 1;
+}
+
+// =====================================================================================================
+// report extraction: which ids are good (solver.jl:733), which ancestors/edges are needed (:688-705)
+// =====================================================================================================
+__global__ void k_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, double thr, uint8_t* needed) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int v = k3[r];
+  if (v < 0) return;  // -Inf is never >= minreport*best (best >= 0)
+  const float s32 = (float)k3_to_score(v);  // Float32 storage, solver.jl:84/:547
+  if ((double)s32 >= thr) needed[id_base + r] = 1;
+}
+__global__ void k_mark_parents(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
+                               uint8_t* needed) {
+  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= G) return;
+  if (needed[cand_id[pos]]) {
+    const int32_t pid = front_id[desc_parent(desc[pos])];
+    if (!needed[pid]) needed[pid] = 1;
+  }
+}
+__global__ void k_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* needed, uint32_t* flag) {
+  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos < G) flag[pos] = needed[cand_id[pos]] ? 1u : 0u;
+}
+__global__ void k_edge_compact(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
+                               const uint32_t* flag, const uint32_t* pre, EdgeRec* out) {
+  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= G || !flag[pos]) return;
+  const uint64_t d = desc[pos];
+  EdgeRec e;
+  e.child = cand_id[pos];
+  e.parent = front_id[desc_parent(d)];
+  e.kind_i = desc_kind(d) | (desc_i(d) << 2);
+  e.j = desc_j(d);
+  out[pre[pos]] = e;
+}
+__global__ void k_id_flags(const uint8_t* needed, int32_t id_base, uint32_t n, uint32_t* flag) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) flag[r] = needed[id_base + r] ? 1u : 0u;
+}
+__global__ void k_id_compact(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,
+                             const uint32_t* flag, const uint32_t* pre, IdRec* out) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n || !flag[r]) return;
+  IdRec o;
+  o.id = id_base + (int32_t)r;
+  o.k3 = k3[r];
+  o.cost = cost[r];
+  o.total = total[r];
+  out[pre[r]] = o;
+}
+
+int launch_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, double thr, uint8_t* needed, cudaStream_t st) {
+  if (!n) return 0;
+  k_good_flags<<<(n + 255) / 256, 256, 0, st>>>(k3, n, id_base, thr, needed);
+  return 1;
+}
+int launch_mark_parents(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
+                        uint8_t* needed, cudaStream_t st) {
+  if (!G) return 0;
+  k_mark_parents<<<(G + 255) / 256, 256, 0, st>>>(cand_id, desc, front_id, G, needed);
+  return 1;
+}
+int launch_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* needed, uint32_t* flag, cudaStream_t st) {
+  if (!G) return 0;
+  k_edge_flags<<<(G + 255) / 256, 256, 0, st>>>(cand_id, G, needed, flag);
+  return 1;
+}
+int launch_edge_compact(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
+                        const uint32_t* flag, const uint32_t* pre, void* out, cudaStream_t st) {
+  if (!G) return 0;
+  k_edge_compact<<<(G + 255) / 256, 256, 0, st>>>(cand_id, desc, front_id, G, flag, pre, (EdgeRec*)out);
+  return 1;
+}
+int launch_id_flags(const uint8_t* needed, int32_t id_base, uint32_t n, uint32_t* flag, cudaStream_t st) {
+  if (!n) return 0;
+  k_id_flags<<<(n + 255) / 256, 256, 0, st>>>(needed, id_base, n, flag);
+  return 1;
+}
+int launch_id_compact(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,
+                      const uint32_t* flag, const uint32_t* pre, void* out, cudaStream_t st) {
+  if (!n) return 0;
+  k_id_compact<<<(n + 255) / 256, 256, 0, st>>>(k3, cost, total, id_base, n, flag, pre, (IdRec*)out);
+  return 1;
+}
+
+int launch_moveset(const RegionDev& R, cudaStream_t st) {
+  const long long n = (long long)R.n_x * R.n_x;
+  k_moveset<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R);
+  return 1;
+}
+int launch_insert_root(const int16_t* seq, int L, const U4* pw, uint32_t rid1, uint64_t* table, uint64_t tmask,
+                       cudaStream_t st) {
+  k_insert_root<<<1, 32, 0, st>>>(seq, L, pw, rid1, table, tmask);
+  return 1;
+}
+int launch_rehash(const uint64_t* oldT, uint64_t old_cap, uint64_t* newT, uint64_t new_mask, cudaStream_t st) {
+  k_table_rehash<<<148 * 8, 256, 0, st>>>(oldT, old_cap, newT, new_mask);
+  return 1;
+}
+
+}  // namespace nw

@@ -1,0 +1,163 @@
+// nw_kernels.cuh -- device-side structures and launch prototypes shared by nw_kernels.cu, nw_score_fast.cu
+// and the host driver (nw_driver.cu).  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nw_device.h"
+
+namespace nw {
+
+constexpr uint64_t TBL_EMPTY = ~0ull;
+constexpr int TBL_WORDS = 4;  // slot = {key0, key1, first-discoverer gpos, unused} (32 B)
+constexpr int MAX_LEVELS = 16;
+constexpr uint32_t WORK_PAD = 0xffffffffu;
+
+// Per-region read-only context in device memory.  [planes | upx | rt_rev] is one contiguous, 16-B aligned
+// blob of ctx_bytes so the scoring kernels can stage it with a single TMA bulk copy.
+struct RegionDev {
+  int n_x, n_y;
+  int NYP;     // padded number of (reversed) columns incl. the virtual column 0; multiple of 32
+  int PWS;     // 32-bit words per (block, strand) bit-plane row, incl. zero padding
+  int MW;      // 32-bit words per moveset row
+  int sum_rt;  // sum of y lengths in units
+  uint32_t rid1;
+  uint32_t ctx_bytes;
+  const unsigned char* ctx;  // blob base
+  uint32_t off_upx, off_rtrev;  // byte offsets inside the blob (planes at 0)
+  int rt_copy_stride;           // ints between the 4 shifted copies of rt_rev (copy c holds rt_rev[t + c])
+  const int32_t* rt;     // rt[1..n_y] units
+  const int32_t* cumr;   // cumr[j] = sum_{j'<=j} rt
+  uint32_t* ms_dd;       // [(n_x+1) * MW] bit rows, 1-based block ids
+  uint32_t* ms_inv;
+};
+
+// One BFS level's frontier: P parents, each a blob [seq int16 x LS | F U4 x (LS+1) | G U4 x (LS+1)].
+struct FrontierDev {
+  int P, LS;
+  uint32_t pstride;  // bytes per parent blob (multiple of 16)
+  const unsigned char* blob;
+  const int32_t* len;
+  const int32_t* id;
+  const uint8_t* dupok;
+};
+
+struct LevelTable {  // candidate -> id lookup across levels (owner resolution)
+  int n_levels;                      // levels already finished (level 0 = root pseudo-level)
+  uint32_t gbase[MAX_LEVELS + 1];    // first global position of each finished level; gbase[n_levels] = current base
+  const int32_t* cand_id[MAX_LEVELS];
+};
+
+struct ExpandArgs {
+  RegionDev R;
+  FrontierDev F;
+  uint32_t* cnt;         // [P] candidates per parent (count pass out)
+  const uint32_t* off;   // [P] exclusive offsets (emit pass in)
+  int* maxlen;           // max child length (count pass out)
+  uint64_t* desc;        // [G] (emit)
+  uint32_t* slot;        // [G] hash-table slot of each candidate (emit)
+  uint64_t* table;
+  uint64_t tmask;
+  uint32_t gbase;
+  const U4* pw;
+};
+
+struct ScoreArgs {
+  RegionDev R;
+  FrontierDev F;
+  const uint32_t* work;     // [n_work] new-rank per lane slot, WORK_PAD = idle
+  uint32_t n_work;
+  const uint32_t* newlist;  // rank -> candidate position in this level
+  const uint64_t* desc;
+  const int32_t* band_off;  // [Lmax+1] offset (in rows) of the band table of length L, -1 if absent
+  const int16_t* band_ab;   // generic: {a,b} pairs per row (row 0 unused)
+  const int16_t* band_eb;   // fast: eb per row (row 0 = virtual)
+  const uint8_t* band_sb;   // fast: sb per row
+  const uint32_t* band_mask;  // fast: 4 words per row
+  int32_t* k3;              // [n_new] out
+  int32_t* cost;            // [n_new] out (units; -2 unreachable)
+  int32_t* total;           // [n_new] out (units)
+  int* best_k3;
+  unsigned long long* cells;  // DP cells evaluated (stat)
+  int32_t* scratch;         // generic kernel rows
+  int force;
+};
+
+struct AssignArgs {
+  LevelTable LT;
+  const uint32_t* slot;
+  const uint64_t* table;
+  const uint32_t* is_new;
+  const uint32_t* newrank;  // exclusive scan of is_new
+  const uint64_t* desc;
+  const int32_t* front_len;
+  uint32_t gbase, G;
+  int32_t id_base;  // id of new-rank 0
+  int n_y, force;
+  int32_t* cand_id;   // [G] out
+  uint32_t* newlist;  // [n_new] out: rank -> pos
+  uint16_t* new_len;  // [n_new] out: child length
+  int32_t* k3;        // [n_new] (early exits are settled here)
+  int32_t* cost;
+  int32_t* total;
+  uint32_t* hist;     // [Lcap] count of DP-needing new candidates per child length
+};
+
+struct MaterialiseArgs {
+  FrontierDev F;           // parents (current level)
+  const uint32_t* sel;     // [P2] selected new-ranks, in frontier order
+  const uint32_t* newlist;
+  const uint64_t* desc;
+  int32_t id_base;
+  int maxdup, n_x;
+  int P2, LS2;
+  uint32_t pstride2;
+  unsigned char* blob2;
+  int32_t* len2;
+  int32_t* id2;
+  uint8_t* dupok2;
+  const U4* pw;
+};
+
+struct EdgeRec {
+  int32_t child, parent;
+  int32_t kind_i;  // kind | i << 2
+  int32_t j;
+};
+struct IdRec {
+  int32_t id, k3, cost, total;
+};
+// ---- launchers (return the number of kernels launched) ----
+int launch_score_fast(int W, const ScoreArgs& A, cudaStream_t st);
+bool score_fast_supports(int width);  // true if some compiled window >= width
+int score_fast_window(int width);     // smallest compiled window >= width (0 if none)
+
+// ---- small device helpers ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (SASS: UBLKCP).  dst/src 16-B aligned, bytes % 16 == 0.
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+}  // namespace nw

@@ -1,0 +1,40 @@
+// nw_launch.h -- host-callable launch wrappers implemented in nw_kernels.cu.  Each returns the number of CUDA
+// kernels it launched (the driver sums them into nw_stats.kernel_launches).
+#pragma once
+#include "nw_kernels.cuh"
+
+namespace nw {
+
+int launch_moveset(const RegionDev& R, cudaStream_t st);
+int launch_insert_root(const int16_t* seq, int L, const U4* pw, uint32_t rid1, uint64_t* table, uint64_t tmask,
+                       cudaStream_t st);
+int launch_rehash(const uint64_t* oldT, uint64_t old_cap, uint64_t* newT, uint64_t new_mask, cudaStream_t st);
+int launch_expand(bool emit, const ExpandArgs& A, cudaStream_t st);
+int launch_scan(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* bsum_scratch, uint32_t* total_out,
+                cudaStream_t st);
+uint64_t scan_scratch_items(uint64_t n);
+int launch_resolve(const uint32_t* slot, const uint64_t* table, uint32_t gbase, uint32_t G, uint32_t* is_new,
+                   cudaStream_t st);
+int launch_assign(const AssignArgs& A, cudaStream_t st);
+int launch_bucket_scatter(const uint16_t* new_len, uint32_t n_new, int n_y, int force, const uint32_t* bstart,
+                          uint32_t* cursor, uint32_t* work, cudaStream_t st);
+int generic_threads();
+int launch_score_generic(const ScoreArgs& A, cudaStream_t st);
+int launch_valid_flags(const int32_t* k3, uint32_t n, uint32_t* flag, cudaStream_t st);
+int launch_compact_ranks(const uint32_t* flag, const uint32_t* pre, uint32_t n, uint32_t* sel, cudaStream_t st);
+int launch_make_keys(const int32_t* k3, const uint32_t* flag, const uint32_t* pre, uint32_t n, uint64_t* keys,
+                     uint64_t nvalid, uint64_t npad, cudaStream_t st);
+int launch_sort_u64(uint64_t* keys, uint64_t npad, cudaStream_t st);
+int launch_keys_to_sel(const uint64_t* keys, uint32_t n, uint32_t* sel, cudaStream_t st);
+int launch_materialise(const MaterialiseArgs& A, cudaStream_t st);
+int launch_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, double thr, uint8_t* needed, cudaStream_t st);
+int launch_mark_parents(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
+                        uint8_t* needed, cudaStream_t st);
+int launch_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* needed, uint32_t* flag, cudaStream_t st);
+int launch_edge_compact(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
+                        const uint32_t* flag, const uint32_t* pre, void* out, cudaStream_t st);
+int launch_id_flags(const uint8_t* needed, int32_t id_base, uint32_t n, uint32_t* flag, cudaStream_t st);
+int launch_id_compact(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,
+                      const uint32_t* flag, const uint32_t* pre, void* out, cudaStream_t st);
+
+}  // namespace nw

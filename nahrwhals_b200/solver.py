@@ -1,0 +1,218 @@
+"""Host-side mirror of the reference solver interface over the C ABI (include/nwsolve.h).
+
+The option names and meanings are solver.jl's (reference: inst/extdata/scripts/scripts_nw_main/solver.jl:756-791):
+maxdepth (-d), maxdup (-u), maxwidth (-w, None = nothing), maxoffset (-O, parsed and ignored like the reference),
+minreport (-r), maxreport (-R, None = nothing).  `main(argv)` is the drop-in for `julia solver.jl ...`
+(R/juliasolver.R:34-53 builds exactly that command line).
+"""
+import argparse
+import ctypes as C
+import sys
+
+import numpy as np
+
+from . import _lib
+
+MOVE_NAMES = ("move_dup", "move_del", "move_inv")  # solver.jl:34
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class SolveResult:
+    """Trajectories in report order (solver.jl:739-743) + counters."""
+
+    def __init__(self):
+        self.tsv = ""
+        self.scores = np.zeros(0, np.float32)
+        self.moves = []          # list of [(kind, start, stop), ...]
+        self.cost_bp = np.zeros(0, np.int64)
+        self.total_bp = np.zeros(0, np.int64)
+        self.index_id = np.zeros(0, np.int64)
+        self.stats = None
+        self.ids = None          # keep_ids: dict(score, cost_bp, total_bp, level)
+        self.edges = None        # keep_ids: dict(child, parent, moves)
+
+    @property
+    def generated(self):
+        return [int(v) for v in self.stats.generated[:self.stats.n_levels]]
+
+    @property
+    def scored(self):
+        return [int(v) for v in self.stats.scored[:self.stats.n_levels]]
+
+    @property
+    def cells(self):
+        return [int(v) for v in self.stats.cells[:self.stats.n_levels]]
+
+
+class Solver:
+    """One solver context on one GPU (nw_ctx).  Not thread-safe; make one per thread / per rank."""
+
+    def __init__(self, device=-1):
+        self.L = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.L.nw_ctx_create(int(device), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.nw_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _opts(self, maxdepth=3, maxdup=3, maxwidth=None, minreport=0.95, maxreport=None, keep_ids=False,
+              generic_dp=False, no_traj=False, maxoffset=4):
+        o = _lib.NwOpts()
+        self.L.nw_default_opts(C.byref(o))
+        o.maxdepth, o.maxdup = int(maxdepth), int(maxdup)
+        o.maxwidth = -1 if maxwidth is None else int(maxwidth)
+        o.minreport = float(minreport)
+        o.maxreport = -1 if maxreport is None else int(maxreport)
+        o.keep_ids = 1 if keep_ids else 0
+        o.flags = (_lib.FLAG_GENERIC_DP if generic_dp else 0) | (_lib.FLAG_NO_TRAJ if no_traj else 0)
+        return o
+
+    @staticmethod
+    def _problem(aln, len_x, len_y):
+        aln = np.ascontiguousarray(aln, dtype=np.int8)
+        if aln.ndim != 2:
+            raise ValueError("aln must be [n_x, n_y]")
+        lx = np.ascontiguousarray(len_x, dtype=np.int64)
+        ly = np.ascontiguousarray(len_y, dtype=np.int64)
+        if lx.shape != (aln.shape[0],) or ly.shape != (aln.shape[1],):
+            raise ValueError("length vectors do not match the gridmatrix")
+        return aln, lx, ly
+
+    def solve(self, aln, len_x, len_y, **kw):
+        """aln_bfs_scored + get_good_trajectories (solver.jl:644-686, :727-745).  aln: int8 [n_x, n_y]."""
+        aln, lx, ly = self._problem(aln, len_x, len_y)
+        o = self._opts(**kw)
+        r = C.c_void_p()
+        _lib.check(self.L.nw_solve(self.h, _p(aln), aln.shape[0], aln.shape[1], _p(lx), _p(ly), C.byref(o), C.byref(r)))
+        try:
+            return self._unpack(r, o)
+        finally:
+            self.L.nw_result_free(r)
+
+    def _unpack(self, r, o):
+        L = self.L
+        R = SolveResult()
+        st = _lib.NwStats()
+        L.nw_result_stats(r, C.byref(st))
+        R.stats = st
+        data, ln = C.c_void_p(), C.c_int64()
+        L.nw_result_tsv(r, C.byref(data), C.byref(ln))
+        R.tsv = C.string_at(data, ln.value).decode() if ln.value else ""
+        n = L.nw_result_count(r)
+        R.scores = np.zeros(n, np.float32)
+        R.cost_bp = np.zeros(n, np.int64)
+        R.total_bp = np.zeros(n, np.int64)
+        R.index_id = np.zeros(n, np.int64)
+        sc, nm, mv = C.c_float(), C.c_int32(), C.POINTER(C.c_int32)()
+        c1, c2, c3 = C.c_int64(), C.c_int64(), C.c_int64()
+        for k in range(n):
+            L.nw_result_get(r, k, C.byref(sc), C.byref(nm), C.byref(mv))
+            L.nw_result_cost(r, k, C.byref(c1), C.byref(c2), C.byref(c3))
+            R.scores[k] = sc.value
+            R.moves.append([(mv[3 * t], mv[3 * t + 1], mv[3 * t + 2]) for t in range(nm.value)])
+            R.cost_bp[k], R.total_bp[k], R.index_id[k] = c1.value, c2.value, c3.value
+        if o.keep_ids:
+            nid = int(st.n_ids)
+            ids = dict(score=np.zeros(nid, np.float32), cost_bp=np.zeros(nid, np.int64),
+                       total_bp=np.zeros(nid, np.int64), level=np.zeros(nid, np.int32))
+            _lib.check(L.nw_result_ids(r, _p(ids["score"]), _p(ids["cost_bp"]), _p(ids["total_bp"]), _p(ids["level"])))
+            R.ids = ids
+            ne = L.nw_result_edge_count(r)
+            ed = dict(child=np.zeros(ne, np.int32), parent=np.zeros(ne, np.int32), moves=np.zeros((ne, 3), np.int32))
+            L.nw_result_edges(r, _p(ed["child"]), _p(ed["parent"]), _p(ed["moves"]))
+            R.edges = ed
+        return R
+
+    def solve_files(self, inmat, inlens, out, **kw):
+        """main() of solver.jl (:755-812): TSVs in, ranked trajectory TSV out.  Returns NwStats."""
+        o = self._opts(**kw)
+        st = _lib.NwStats()
+        _lib.check(self.L.nw_solve_files(self.h, str(inmat).encode(), str(inlens).encode(), str(out).encode(),
+                                         C.byref(o), C.byref(st)))
+        return st
+
+    def score_batch(self, aln, len_x, len_y, seqs, force=False, generic_dp=False):
+        """slow_score (solver.jl:329-376) for raw candidate indices.  Returns (score f64, cost_bp, total_bp);
+        cost_bp == -1: early exit (score 0.0, no DP), -2: unreachable (score -inf)."""
+        aln, lx, ly = self._problem(aln, len_x, len_y)
+        n = len(seqs)
+        off = np.zeros(n + 1, np.int64)
+        for k, s in enumerate(seqs):
+            off[k + 1] = off[k] + len(s)
+        flat = np.zeros(max(int(off[-1]), 1), np.int16)
+        for k, s in enumerate(seqs):
+            flat[off[k]:off[k + 1]] = s
+        cost = np.zeros(n, np.int64)
+        total = np.zeros(n, np.int64)
+        score = np.zeros(n, np.float64)
+        _lib.check(self.L.nw_score_batch(self.h, _p(aln), aln.shape[0], aln.shape[1], _p(lx), _p(ly), _p(flat), _p(off),
+                                         n, 1 if force else 0, _lib.FLAG_GENERIC_DP if generic_dp else 0, _p(cost),
+                                         _p(total), _p(score)))
+        return score, cost, total
+
+    def moveset(self, aln):
+        """to_moveset (solver.jl:217-231) -> (duplicate_delete, invert) bool [n_x, n_x]."""
+        aln = np.ascontiguousarray(aln, dtype=np.int8)
+        n_x, n_y = aln.shape
+        dd = np.zeros((n_x, n_x), np.uint8)
+        iv = np.zeros((n_x, n_x), np.uint8)
+        _lib.check(self.L.nw_moveset(self.h, _p(aln), n_x, n_y, _p(dd), _p(iv)))
+        return dd.astype(bool), iv.astype(bool)
+
+
+def read_problem(inmat, inlens):
+    """read_tsv + read_length_tsv (solver.jl:101-107, :121-138) -> (aln int8 [n_x,n_y], len_x, len_y)."""
+    L = _lib.load()
+    a, lx, ly = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    nx, ny = C.c_int32(), C.c_int32()
+    _lib.check(L.nw_read_problem(str(inmat).encode(), str(inlens).encode(), C.byref(a), C.byref(nx), C.byref(ny),
+                                 C.byref(lx), C.byref(ly)))
+    try:
+        aln = np.ctypeslib.as_array(C.cast(a, C.POINTER(C.c_int8)), (nx.value, ny.value)).copy()
+        len_x = np.ctypeslib.as_array(C.cast(lx, C.POINTER(C.c_int64)), (nx.value,)).copy()
+        len_y = np.ctypeslib.as_array(C.cast(ly, C.POINTER(C.c_int64)), (ny.value,)).copy()
+    finally:
+        L.nw_free(a)
+        L.nw_free(lx)
+        L.nw_free(ly)
+    return aln, len_x, len_y
+
+
+def main(argv=None):
+    """Drop-in for `julia solver.jl` (argument table solver.jl:756-791)."""
+    ap = argparse.ArgumentParser(prog="nwsolve")
+    ap.add_argument("--maxdepth", "-d", type=int, default=3)
+    ap.add_argument("--maxdup", "-u", type=int, default=3)
+    ap.add_argument("--maxwidth", "-w", type=float, default=None)
+    ap.add_argument("--maxoffset", "-O", type=int, default=4)
+    ap.add_argument("--minreport", "-r", type=float, default=0.95)
+    ap.add_argument("--maxreport", "-R", type=float, default=None)
+    ap.add_argument("compressed_alignment")
+    ap.add_argument("compressed_lengths")
+    ap.add_argument("out_path")
+    a = ap.parse_args(argv)
+    try:
+        s = Solver()
+        s.solve_files(a.compressed_alignment, a.compressed_lengths, a.out_path, maxdepth=a.maxdepth, maxdup=a.maxdup,
+                      maxwidth=None if a.maxwidth is None else int(a.maxwidth), minreport=a.minreport,
+                      maxreport=None if a.maxreport is None else int(a.maxreport))
+    except Exception as e:  # non-zero exit, message on stderr, no output file (R/juliasolver.R:56-59)
+        print("nwsolve: %s" % e, file=sys.stderr)
+        return 1
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,137 @@
+// CPU unit-test harness for the host/device-shared logic of nahrwhals_b200/csrc (nw_device.h, nw_band.h,
+// nw_host.h).  TEST INFRASTRUCTURE ONLY: it lets `pytest -m "not gpu"` check, without a GPU, the exact integer
+// code the kernels execute per item (index maps, fingerprint composition, the register-DP row step and the band
+// tables) against the oracle.  It is never loaded by the product and is not a CPU fallback: it cannot run a search.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../nahrwhals_b200/csrc/nw_band.h"
+#include "../../nahrwhals_b200/csrc/nw_device.h"
+#include "../../nahrwhals_b200/csrc/nw_host.h"
+
+using namespace nw;
+
+template <int W>
+static int run_fast(const RegionHost& R, const BandTable& T, const int16_t* parent, int kind, int p, int q, int Lc,
+                    int* sumup_out) {
+  constexpr int NWORD = (W + 31) / 32;
+  int S[W];
+  for (int k = 0; k < W; ++k) S[k] = 0;
+  int sumup = 0;
+  const uint32_t* planes = R.planes();
+  const int32_t* upx = R.upx();
+  const int32_t* rtrev = R.rtrev();
+  for (int i = 1; i <= Lc; ++i) {
+    const int c = child_elem(parent, kind, p, q, i);
+    const int x = c < 0 ? -c : c;
+    const int up = upx[x];
+    sumup += up;
+    const int r0 = R.NYP - 1 - T.eb[i];
+    int sb = T.sb[i];
+    const uint32_t* pl = planes + (size_t)(x * 2 + (c < 0 ? 1 : 0)) * R.PWS + (r0 >> 5);
+    const int sh = r0 & 31;
+    uint32_t m[NWORD];
+    for (int t = 0; t < NWORD; ++t) {
+      const uint64_t two = (uint64_t)pl[t] | ((uint64_t)pl[t + 1] << 32);
+      m[t] = (uint32_t)(two >> sh) & T.mask[(size_t)i * 4 + t];
+    }
+    const int* rtw = rtrev + (size_t)(r0 & 3) * R.rt_copy_stride + (r0 & ~3);
+    while (sb > 2) {
+      dp_row_shift1<W>(S);
+      --sb;
+    }
+    if (sb == 0) dp_row_step<W, 0>(S, m, up, rtw);
+    else if (sb == 1) dp_row_step<W, 1>(S, m, up, rtw);
+    else dp_row_step<W, 2>(S, m, up, rtw);
+  }
+  *sumup_out = sumup;
+  return S[0];
+}
+
+extern "C" {
+
+// Scores child(parent, kind, p, q) with the register-DP code path.  Returns 1 if the fast path applies
+// (cost/total in bp written), 0 if the geometry needs the generic kernel, -1 on early exit.
+int h_score_fast(const int8_t* aln, int n_x, int n_y, const int64_t* len_x, const int64_t* len_y, const int16_t* parent,
+                 int L, int kind, int p, int q, int force, int64_t* cost_bp, int64_t* total_bp, int* window) {
+  RegionHost R = build_region(aln, n_x, n_y, len_x, len_y, 4);
+  const int Lc = child_len(L, kind, p, q);
+  if (!force && early_exit(Lc, n_y)) return -1;
+  BandTable T = build_band(Lc, n_y, force != 0, WINDOW_MAX);
+  if (!T.fast_ok) return 0;
+  static const int wins[] = {8, 16, 24, 32, 40, 48, 64, 80, 96, 128};
+  int W = 0;
+  for (int w : wins)
+    if (w >= T.max_width) {
+      W = w;
+      break;
+    }
+  if (!W) return 0;
+  int sumup = 0, s = 0;
+  switch (W) {
+    case 8: s = run_fast<8>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 16: s = run_fast<16>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 24: s = run_fast<24>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 32: s = run_fast<32>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 40: s = run_fast<40>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 48: s = run_fast<48>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 64: s = run_fast<64>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 80: s = run_fast<80>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 96: s = run_fast<96>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    default: s = run_fast<128>(R, T, parent, kind, p, q, Lc, &sumup); break;
+  }
+  const int64_t total = (int64_t)sumup + R.sum_rt;
+  *cost_bp = (total - s) * R.gcd;
+  *total_bp = total * R.gcd;
+  *window = W;
+  return 1;
+}
+
+// k3 (score*1000) from integer cost/total, the product's scoring arithmetic
+int h_score_k3(int64_t cost, int64_t total) { return score_k3(cost, total); }
+
+// materialises the child through the index map; returns its length
+int h_child(const int16_t* parent, int L, int kind, int p, int q, int16_t* out) {
+  const int Lc = child_len(L, kind, p, q);
+  for (int t = 1; t <= Lc; ++t) out[t - 1] = (int16_t)child_elem(parent, kind, p, q, t);
+  return Lc;
+}
+
+// 1 iff the O(1) composed fingerprint of child(parent, move) equals the direct fingerprint of the materialised child
+int h_fp_check(const int16_t* parent, int L, int kind, int p, int q) {
+  static std::vector<U4> pw = build_pow_table();
+  const int LS = round_ls(L);
+  std::vector<unsigned char> blob(blob_stride(LS));
+  fill_blob(blob.data(), LS, parent, L, pw.data());
+  const U4* F = reinterpret_cast<const U4*>(blob.data() + (size_t)LS * 2);
+  const U4* G = F + (LS + 1);
+  const U4 a = child_fingerprint(F, G, pw.data(), L, kind, p, q, 1);
+  std::vector<int16_t> ch(2 * L + 2);
+  const int Lc = h_child(parent, L, kind, p, q, ch.data());
+  const U4 b = seq_fingerprint(ch.data(), Lc, pw.data(), 1);
+  return memcmp(&a, &b, sizeof(U4)) == 0;
+}
+void h_fp(const int16_t* seq, int L, uint32_t* out4) {
+  static std::vector<U4> pw = build_pow_table();
+  const U4 f = seq_fingerprint(seq, L, pw.data(), 1);
+  memcpy(out4, &f, 16);
+}
+
+// band geometry: cells, fast_ok, max_width
+void h_band(int L, int n_y, int force, int64_t* cells, int* fast_ok, int* max_width, int* contiguous) {
+  BandTable T = build_band(L, n_y, force != 0, WINDOW_MAX);
+  *cells = T.cells;
+  *fast_ok = T.fast_ok;
+  *max_width = T.max_width;
+  *contiguous = T.contiguous;
+}
+
+// Julia-style Float32 score string of the product's TSV writer
+int h_score_string(int k3, char* buf, int cap) {
+  std::string s = score_string(k3);
+  snprintf(buf, cap, "%s", s.c_str());
+  return (int)s.size();
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+"""GPU parity tests (B200): the CUDA path through the C ABI vs the oracle on identical inputs.
+Bit-exact integer DP costs, Float32 scores, discovery ids, provenance edges and the output TSV."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from nahrwhals_b200.sdgrid import random_grid, sdgrid, to_solver_inputs, write_tsvs
+from tests.util import assert_search_equal
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_moveset(solver, oracle, testrun):
+    from oracle import nw_oracle_py as op
+    for aln in (testrun[0], to_solver_inputs(sdgrid(40, [5, 4, 3], seed=3)[0])):
+        dd, iv = solver.moveset(aln)
+        pdd, piv = op.to_moveset(aln.tolist())
+        assert np.array_equal(dd, np.array(pdd)) and np.array_equal(iv, np.array(piv))
+
+
+def test_readme_known_answers(solver, testrun):
+    """README.md:135-139 of the reference through the CUDA scorer."""
+    aln, lx, ly = testrun
+    sc, cost, total = solver.score_batch(aln, lx, ly, [list(range(1, 20))], force=True)
+    assert (sc[0], cost[0], total[0]) == (71.378, 810000, 2830000)
+    sc, cost, total = solver.score_batch(aln, lx, ly, [[1, 2, 3, 4, -11, -10, -9, -8, -7, -6, 18, 19]])
+    assert (sc[0], cost[0], total[0]) == (99.595, 10000, 2470000)
+    sc, cost, total = solver.score_batch(aln, lx, ly, [list(range(1, 20))])
+    assert sc[0] == 0.0 and cost[0] == -1
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_testrun_search(solver, oracle, testrun, generic):
+    """Config 1: the bundled test run with the flags R passes (R/juliasolver.R:42-47)."""
+    aln, lx, ly = testrun
+    kw = dict(maxdepth=3, maxdup=2, maxwidth=1000, minreport=0.98, maxreport=1000)
+    G = solver.solve(aln, lx, ly, keep_ids=True, generic_dp=generic, **kw)
+    O = oracle.solve(aln, lx, ly, **kw)
+    assert_search_equal(G, O)
+    assert G.tsv == open(os.path.join(GOLD, "testrun_oracle_res.tsv")).read()
+    assert G.generated == [17, 291, 4484]
+
+
+def test_testrun_files_and_cli(solver, tmp_path):
+    """File + CLI contract (solver.jl:755-812): same TSV bytes as the committed golden result."""
+    out = tmp_path / "res.tsv"
+    solver.solve_files(os.path.join(GOLD, "testrun_grid_mut.tsv"), os.path.join(GOLD, "testrun_grid_mut_lens.tsv"),
+                       out, maxdepth=3, maxdup=2, maxwidth=1000, minreport=0.98, maxreport=1000)
+    gold = open(os.path.join(GOLD, "testrun_oracle_res.tsv")).read()
+    assert out.read_text() == gold
+    out2 = tmp_path / "res2.tsv"
+    cli = os.path.join(ROOT, "nahrwhals_b200", "csrc", "nwsolve")
+    subprocess.check_call([cli, "-d", "3", "-u", "2", "-w", "1000", "-r", "0.98", "-R", "1000",
+                           os.path.join(GOLD, "testrun_grid_mut.tsv"), os.path.join(GOLD, "testrun_grid_mut_lens.tsv"),
+                           str(out2)])
+    assert out2.read_text() == gold
+    # failure: non-zero exit and no output file (R/juliasolver.R:56-59 relies on the file's absence)
+    out3 = tmp_path / "res3.tsv"
+    rc = subprocess.call([cli, os.path.join(GOLD, "nope.tsv"), os.path.join(GOLD, "testrun_grid_mut_lens.tsv"),
+                          str(out3)], stderr=subprocess.DEVNULL)
+    assert rc != 0 and not out3.exists()
+
+
+def _random_candidates(rng, n_x, count, maxmult=3):
+    seqs = []
+    for _ in range(count):
+        mode = rng.integers(0, 3)
+        if mode == 0:
+            L = int(rng.integers(1, maxmult * n_x + 1))
+            s = rng.integers(1, n_x + 1, L) * rng.choice([-1, 1], L)
+        else:
+            s = np.arange(1, n_x + 1)
+            for _ in range(int(rng.integers(0, 4))):
+                L = len(s)
+                if L < 3:
+                    break
+                a = int(rng.integers(0, L - 1))
+                b = int(rng.integers(a + 1, L))
+                k = rng.integers(0, 3)
+                if k == 0 and L + (b - a) <= maxmult * n_x:
+                    s = np.concatenate([s[:b + 1], s[a + 1:]])
+                elif k == 1:
+                    s = np.concatenate([s[:a], s[b:]])
+                else:
+                    s = np.concatenate([s[:a + 1], -s[a + 1:b][::-1], s[b:]])
+        seqs.append([int(v) for v in s])
+    return seqs
+
+
+@pytest.mark.parametrize("shape", [(19, 11), (64, 64), (150, 150), (150, 110), (9, 8), (30, 10), (5, 1), (1, 7),
+                                   (33, 12), (120, 250), (250, 120), (200, 330)])
+def test_score_batch_random(solver, oracle, shape):
+    """slow_score parity on raw candidates: every corridor regime (row<10, <30, >=30), early exit boundary,
+    unreachable terminals, n_y == 1, both DP kernels, and the forcecalc twin."""
+    n_x, n_y = shape
+    rng = np.random.default_rng(n_x * 1000 + n_y)
+    if min(n_x, n_y) >= 19:
+        fams = [int(rng.integers(2, 7)) for _ in range(4)]
+        mat, lx, ly, _ = sdgrid(n_x, fams, seed=n_y, chain_depth=2)
+        if mat.shape[0] != n_y:  # fix the target length by cropping/tiling rows
+            idx = np.arange(n_y) % mat.shape[0]
+            mat, ly = mat[idx], ly[idx]
+    else:
+        mat, lx, ly = random_grid(n_x, n_y, 0.25, n_x + n_y)
+    aln = to_solver_inputs(mat)
+    seqs = _random_candidates(rng, n_x, 600 if n_x * n_y < 30000 else 200)
+    for force in (False, True):
+        osc, ocost, ototal, _ = oracle.score_batch(aln, lx, ly, seqs, force=force)
+        ocost_i = np.where(np.isnan(ocost), -1.0, np.where(np.isinf(ocost), -2.0, ocost)).astype(np.int64)
+        for generic in (False, True):
+            sc, cost, total = solver.score_batch(aln, lx, ly, seqs, force=force, generic_dp=generic)
+            assert np.array_equal(cost, ocost_i), (shape, force, generic)
+            assert np.array_equal(total, ototal.astype(np.int64))
+            assert np.array_equal(sc, osc)  # Float64 scores incl. -inf, exact
+
+
+CASES = [
+    # (name, generator args, solver flags)
+    ("sd24_exh", dict(n_x=24, families=[4, 3, 3], seed=11, chain_depth=3), dict(maxdepth=3, maxdup=2)),
+    ("sd40_w50", dict(n_x=40, families=[5, 4, 3, 2], seed=12, chain_depth=3), dict(maxdepth=4, maxdup=2, maxwidth=50)),
+    ("sd64_exh", dict(n_x=64, families=[6, 5, 5, 4], seed=1, chain_depth=3), dict(maxdepth=3, maxdup=2)),
+    ("sd64_d2", dict(n_x=64, families=[10, 9, 8, 8, 7], seed=1, chain_depth=3), dict(maxdepth=2, maxdup=2)),
+    ("sd150_w100", dict(n_x=150, families=[6, 5, 4, 4, 3], seed=7, chain_depth=4),
+     dict(maxdepth=4, maxdup=2, maxwidth=100)),
+    ("sd30_dup0", dict(n_x=30, families=[4, 4, 3], seed=5, chain_depth=2), dict(maxdepth=3, maxdup=0, maxwidth=1000)),
+    ("sd30_dup3_w7", dict(n_x=30, families=[5, 4], seed=6, chain_depth=3), dict(maxdepth=5, maxdup=3, maxwidth=7)),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_search_parity(solver, oracle, case):
+    """Full BFS parity: counts per level, every id's level/cost/total/score, every provenance edge, TSV."""
+    _, gen, flags = case
+    mat, lx, ly, _ = sdgrid(**gen)
+    aln = to_solver_inputs(mat)
+    kw = dict(minreport=0.98, maxreport=1000, **flags)
+    O = oracle.solve(aln, lx, ly, **kw)
+    G = solver.solve(aln, lx, ly, keep_ids=True, **kw)
+    assert_search_equal(G, O)
+
+
+def test_search_small_and_degenerate(solver, oracle):
+    """n_y <= 10 (no early exit, unreachable terminals -> -Inf dropped from the frontier), no moves at all,
+    minreport 0 (everything reported incl. the 0-move ref line with its trailing tab), maxreport truncation."""
+    for seed, (n_x, n_y, dens) in enumerate([(6, 5, 0.5), (12, 9, 0.3), (8, 3, 0.6), (4, 4, 0.0), (14, 1, 0.7)]):
+        mat, lx, ly = random_grid(n_x, n_y, dens, 100 + seed)
+        aln = to_solver_inputs(mat)
+        for kw in (dict(maxdepth=3, maxdup=2, minreport=0.0, maxreport=300),
+                   dict(maxdepth=2, maxdup=1, maxwidth=5, minreport=0.5)):
+            O = oracle.solve(aln, lx, ly, **kw)
+            G = solver.solve(aln, lx, ly, keep_ids=True, **kw)
+            assert_search_equal(G, O)
+
+
+def test_roundtrip_property_full_size(solver):
+    """Size-independent property at a bench-sized problem (no oracle): the hidden move chain that generated the
+    target must be found, i.e. best == 100.0 within chain_depth moves, and rerunning is deterministic."""
+    mat, lx, ly, hidden = sdgrid(64, [6, 5, 5, 4, 4], seed=21, chain_depth=2)
+    aln = to_solver_inputs(mat)
+    A = solver.solve(aln, lx, ly, maxdepth=2, maxdup=2, minreport=0.98, maxreport=100)
+    B = solver.solve(aln, lx, ly, maxdepth=2, maxdup=2, minreport=0.98, maxreport=100)
+    assert A.stats.best == 100.0 and A.tsv == B.tsv
+    assert A.tsv.startswith("100.0\t")
+    assert A.generated == B.generated and A.scored == B.scored
