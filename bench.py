@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the mutation-space solver (BASELINE.json metric: candidates scored/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload s64|s150]
+
+One "step" = one complete exhaustive depth-3 search (BFS + dedup + banded DP + report) of a synthetic 64-block
+signed gridmatrix (BASELINE.json configs[1]).  With N > 1 (launched under torchrun, one rank per GPU) every rank
+solves its own region of the same shape (independent regions shard per GPU with no collective -- SURVEY 8e,
+regionfile mode), so scaling is weak.
+
+Prints ONE JSON line.  `value` is whole-job unique candidates scored per second, timed on the device with CUDA
+events inside the library (inputs already resident in HBM); `e2e` is the same metric through the public API from
+host numpy buffers (host->device copies of the inputs and device->host copies of the results inside the timed
+region).  `--impl reference` times the CPU restatement of the reference (oracle/) on the host cores instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mutation_candidates_scored_per_s"
+UNIT = "candidates/s"
+
+WORKLOADS = {
+    # name: (sdgrid args, solver flags, description)
+    "s64": (dict(n_x=64, families=[10, 9, 8, 8, 7], chain_depth=3),
+            dict(maxdepth=3, maxdup=2, maxwidth=None, minreport=0.98, maxreport=1000),
+            "synthetic 64-block signed gridmatrix (sdgrid 64 blocks, families 10/9/8/8/7 = 158 repeat pairs), "
+            "exhaustive depth-3 inv/del/dup search, -d 3 -u 2 -r 0.98 -R 1000"),
+    "s150": (dict(n_x=150, families=[8, 7, 6, 6, 5, 5, 4], chain_depth=4),
+             dict(maxdepth=4, maxdup=2, maxwidth=1000, minreport=0.98, maxreport=1000),
+             "synthetic 150-block gridmatrix, depth-4 search, -d 4 -u 2 -w 1000 -r 0.98 -R 1000"),
+}
+
+
+def make_workload(name, seed):
+    from nahrwhals_b200.sdgrid import sdgrid, to_solver_inputs
+    gen, flags, desc = WORKLOADS[name]
+    mat, lx, ly, _ = sdgrid(seed=seed, **gen)
+    return to_solver_inputs(mat), lx, ly, flags, desc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = str(gpu_index)
+        self.lines = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms",
+                                       "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for ln in self.p.stdout:
+            self.lines.append(ln)
+
+    def stop(self):
+        if not self.p:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8 or f[0] != self.idx:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_sample(aln, lx, ly, flags, max_scored, threads):
+    """Oracle (CPU restatement of solver.jl) on a bounded sample of the workload: the first `max_scored` unique
+    candidates of the same search, one independent replica per host thread (what R's threads= does for regions).
+    Returns (candidates/s over all threads, seconds)."""
+    from oracle import oracle_lib
+    oracle_lib.lib()
+    kw = dict(maxdepth=flags["maxdepth"], maxdup=flags["maxdup"], maxwidth=flags["maxwidth"],
+              minreport=flags["minreport"], maxreport=flags["maxreport"], max_scored=max_scored)
+    res = [None] * threads
+
+    def work(k):
+        res[k] = oracle_lib.solve(aln, lx, ly, want_trajs=False, full=False, **kw)
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    scored = sum(int(r.scored.sum()) for r in res)
+    return scored / dt, dt, scored
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    aln, lx, ly, flags, desc = make_workload(args.workload, 1)
+    cores = os.cpu_count() or 1
+    sample_n = args.cpu_sample
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_sample(aln, lx, ly, flags, max(1000, sample_n // 20), cores)
+    tot_scored, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        v, dt, sc = cpu_sample(aln, lx, ly, flags, sample_n, cores)
+        tot_scored += sc
+        tot_t += dt
+    value = tot_scored / tot_t
+    sample = ("first %d unique candidates of the same search per replica, %d independent replicas (one per host "
+              "thread), C++ restatement of solver.jl (oracle/nw_oracle.cpp, -O2)" % (sample_n, cores))
+    line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * tot_t / args.steps, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=desc, l2="n/a (CPU)"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=150000, help="unique candidates per CPU replica (bounded sample)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import nahrwhals_b200 as nb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    aln, lx, ly, flags, desc = make_workload(args.workload, 1 + rank)
+    solver = nb.Solver(local)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def l2_flush():
+        flush.fill_(rank & 0xff)
+        torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W = max(3, args.warmup)
+    for _ in range(W):
+        solver.solve(aln, lx, ly, **flags)
+    peaks = solver.bench_peaks()
+
+    # ---- timed region 1: device-resident throughput (events inside the library on its own stream) ----
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    dev_ms, score_ms, scored, cells, launches, score_launches = 0.0, 0.0, 0, 0, 0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        l2_flush()
+        R = solver.solve(aln, lx, ly, **flags)
+        st = R.stats
+        dev_ms += st.total_ms
+        score_ms += st.score_ms
+        scored += sum(R.scored)
+        cells += sum(R.cells)
+        launches += st.kernel_launches
+        score_launches += st.score_launches
+    barrier()
+    wall1 = time.perf_counter() - t0
+    # ---- timed region 2: end to end through the public API from host buffers ----
+    e2e_t, h2d, d2h = 0.0, 0, 0
+    for _ in range(args.steps):
+        l2_flush()
+        barrier()
+        t1 = time.perf_counter()
+        R = solver.solve(np.array(aln), np.array(lx), np.array(ly), **flags)
+        ntraj = len(R.scores)  # result already on the host (trajectories, costs, TSV bytes)
+        e2e_t += time.perf_counter() - t1
+        h2d += R.stats.h2d_bytes
+        d2h += R.stats.d2h_bytes
+    clocks = sampler.stop()
+
+    # ---- reduce over ranks: max time, summed work ----
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_t, score_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_t, score_ms_max = t.tolist()
+        s = torch.tensor([scored, cells, launches, h2d, d2h], dtype=torch.float64, device="cuda")
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        scored_all, cells_all, launches_all, h2d_all, d2h_all = s.tolist()
+    else:
+        scored_all, cells_all, launches_all, h2d_all, d2h_all = scored, cells, launches, h2d, d2h
+    value = scored_all / (dev_ms * 1e-3)
+    e2e_value = scored_all / e2e_t
+
+    # ---- roofline of the dominant kernel (banded DP, k_score_fast<W>): integer ALU bound ----
+    # algorithmic int-ops = 5 per band cell (3 adds + 2 mins); duration = CUDA events around every DP launch
+    intops = 5.0 * cells
+    ach = intops / (score_ms * 1e-3) / 1e12 if score_ms > 0 else 0.0
+    # measured peak: best of (VIADDMNMX = 2 int-ops/instr), (IADD3 = 2), (VIADDMNMX + IMAD interleaved = 3 per pair)
+    peak = max(2.0 * peaks["viaddmnmx_ips"], 2.0 * peaks["iadd3_ips"], 1.5 * peaks["mixed_ips"]) / 1e12
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = 44.0 * scored  # 8 B descriptor in + 36 B record out per scored candidate
+    hbm_ach = alg_bytes / (score_ms * 1e-3) / 1e9 if score_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dp_kernel_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = dict(bound="int_alu", kernel="k_score_fast<W> (banded DP)", achieved=ach, peak=peak, unit="Tintop/s",
+                    frac=(ach / peak if peak else None), traffic=traffic,
+                    launches=score_launches, avg_launch_ms=(score_ms / score_launches if score_launches else None),
+                    peak_basis="measured on this GPU (nw_bench_peaks): VIADDMNMX %.2f, IADD3 %.2f, VIADDMNMX+IMAD %.2f "
+                               "T thread-instr/s" % (peaks["viaddmnmx_ips"] / 1e12, peaks["iadd3_ips"] / 1e12,
+                                                     peaks["mixed_ips"] / 1e12),
+                    hbm=dict(bound="hbm", achieved=hbm_ach, peak=hbm_peak, unit="GB/s",
+                             frac=hbm_ach / hbm_peak if hbm_peak else None, peak_source=hbm_src,
+                             copy_measured_gbs=peaks["copy_Bps"] / 1e9))
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=W,
+                ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32",
+                data="synthetic",
+                config=dict(workload=desc + ("; one region per GPU, seeds 1..%d" % world if world > 1 else ""),
+                            scored_per_step=scored_all / args.steps, l2="flushed between timed steps (256 MiB write)",
+                            dp_share_of_step=(score_ms / (dev_ms if dist is None else max(dev_ms, 1e-9)))),
+                clocks=clocks,
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_all / args.steps,
+                         d2h_bytes_per_step=d2h_all / args.steps, ms_per_step=1e3 * e2e_t / args.steps),
+                gpu_launches=int(launches_all), roofline=roofline, wall_s_timed=wall1)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v, dt, sc = cpu_sample(aln, lx, ly, flags, args.cpu_sample, cores)
+        line["cpu_baseline"] = dict(
+            value=v, unit=UNIT, cores=cores, kind="port",
+            sample="first %d unique candidates of the same search per replica, %d independent replicas (one per host "
+                   "thread), %.1f s; C++ restatement of solver.jl (the reference itself needs julia, absent here)" %
+                   (args.cpu_sample, cores, dt))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    solver.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -58,6 +58,10 @@ typedef struct nw_stats {
   float total_ms;           /* device time of the whole search (events, excludes H2D of inputs) */
   int64_t n_ids;            /* unique indices incl. the root */
   double best;              /* best Float64 score over all children (solver.jl:660, 539-541) */
+  int64_t h2d_bytes;        /* host->device bytes copied by this call */
+  int64_t d2h_bytes;        /* device->host bytes copied by this call */
+  float score_ms;           /* device time inside the banded-DP kernels (events on the launch stream) */
+  int32_t score_launches;   /* number of banded-DP kernel launches */
 } nw_stats;
 
 void nw_default_opts(nw_opts* o);
@@ -106,6 +110,11 @@ int nw_score_batch(nw_ctx* ctx, const int8_t* aln_sign, int32_t n_x, int32_t n_y
 
 /* Replaces to_moveset (solver.jl:217-231): two n_x*n_x uint8 matrices (duplicate_delete, invert). */
 int nw_moveset(nw_ctx* ctx, const int8_t* aln_sign, int32_t n_x, int32_t n_y, uint8_t* dup_del, uint8_t* invert);
+
+/* Roofline denominators measured on this device with dependency-free micro-kernels:
+ * out[0] VIADDMNMX, out[1] IADD3, out[2] VIADDMNMX+IMAD interleaved -- thread-instructions per second;
+ * out[3] device-to-device copy bandwidth in bytes/s (read + write). */
+int nw_bench_peaks(nw_ctx* ctx, double out[4]);
 
 /* TSV readers of solver.jl:101-107 / :121-138 (host side; exposed for the bindings). Caller frees with nw_free. */
 int nw_read_problem(const char* inmat_path, const char* inlens_path, int8_t** aln_sign, int32_t* n_x,

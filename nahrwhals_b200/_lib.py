@@ -15,7 +15,9 @@ class NwOpts(C.Structure):
 class NwStats(C.Structure):
     _fields_ = [("n_levels", C.c_int32), ("kernel_launches", C.c_int32), ("generated", C.c_int64 * 16),
                 ("scored", C.c_int64 * 16), ("cells", C.c_int64 * 16), ("frontier", C.c_int64 * 16),
-                ("level_ms", C.c_float * 16), ("total_ms", C.c_float), ("n_ids", C.c_int64), ("best", C.c_double)]
+                ("level_ms", C.c_float * 16), ("total_ms", C.c_float), ("n_ids", C.c_int64), ("best", C.c_double),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("score_ms", C.c_float),
+                ("score_launches", C.c_int32)]
 
 
 FLAG_GENERIC_DP = 1
@@ -25,7 +27,7 @@ FLAG_NO_TRAJ = 2
 SYMBOLS = ["nw_default_opts", "nw_last_error", "nw_version", "nw_ctx_create", "nw_ctx_destroy", "nw_solve",
            "nw_solve_files", "nw_result_count", "nw_result_get", "nw_result_cost", "nw_result_tsv", "nw_result_stats",
            "nw_result_ids", "nw_result_edge_count", "nw_result_edges", "nw_result_free", "nw_score_batch",
-           "nw_moveset", "nw_read_problem", "nw_free"]
+           "nw_moveset", "nw_bench_peaks", "nw_read_problem", "nw_free"]
 
 _lib = None
 
@@ -59,6 +61,7 @@ def load():
     L.nw_result_free.argtypes = [vp]
     L.nw_score_batch.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp]
     L.nw_moveset.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.nw_bench_peaks.argtypes = [vp, C.POINTER(C.c_double * 4)]
     L.nw_read_problem.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32),
                                   C.POINTER(vp), C.POINTER(vp)]
     L.nw_free.argtypes = [vp]

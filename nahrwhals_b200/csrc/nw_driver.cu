@@ -23,6 +23,7 @@
 using namespace nw;
 
 static thread_local std::string g_last_error;
+struct nw_ctx;
 
 namespace {
 
@@ -81,6 +82,10 @@ struct DevBuf {
   }
 };
 
+// counted copies (nw_stats.h2d_bytes / d2h_bytes)
+void h2d(nw_ctx* c, void* dst, const void* src, size_t n);
+void d2h(nw_ctx* c, void* dst, const void* src, size_t n);
+
 struct BandStore {  // host cache + device mirror of per-length corridor tables for one (n_y, force)
   int n_y = -1;
   bool force = false;
@@ -117,13 +122,13 @@ struct BandStore {  // host cache + device mirror of per-length corridor tables 
     dirty = true;
     return tabs.emplace(L, std::move(T)).first->second;
   }
-  void upload(cudaStream_t st) {
+  void upload(nw_ctx* c, cudaStream_t st) {
     if (!dirty) return;
-    CK(cudaMemcpyAsync(d_off.ensure(off.size() * 4), off.data(), off.size() * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d_ab.ensure(ab.size() * 2, true), ab.data(), ab.size() * 2, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d_eb.ensure(eb.size() * 2, true), eb.data(), eb.size() * 2, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d_sb.ensure(sb.size(), true), sb.data(), sb.size(), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d_mask.ensure(mask.size() * 4, true), mask.data(), mask.size() * 4, cudaMemcpyHostToDevice, st));
+    h2d(c, d_off.ensure(off.size() * 4), off.data(), off.size() * 4);
+    h2d(c, d_ab.ensure(ab.size() * 2, true), ab.data(), ab.size() * 2);
+    h2d(c, d_eb.ensure(eb.size() * 2, true), eb.data(), eb.size() * 2);
+    h2d(c, d_sb.ensure(sb.size(), true), sb.data(), sb.size());
+    h2d(c, d_mask.ensure(mask.size() * 4, true), mask.data(), mask.size() * 4);
     CK(cudaStreamSynchronize(st));  // host vectors may be reallocated by the next get()
     dirty = false;
   }
@@ -149,8 +154,24 @@ struct nw_ctx {
       misc;
   void* pinned = nullptr;  // small pinned staging area for D2H scalars / histograms
   int launches = 0;
+  int64_t h2d_bytes = 0, d2h_bytes = 0;
+  // device time of the dominant (DP) kernels, measured with events on the launching stream
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> score_events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
+  int64_t score_work_items = 0;
   nw_ctx() = default;
 };
+
+namespace {
+void h2d(nw_ctx* c, void* dst, const void* src, size_t n) {
+  CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, c->stream));
+  c->h2d_bytes += (int64_t)n;
+}
+void d2h(nw_ctx* c, void* dst, const void* src, size_t n) {
+  CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, c->stream));
+  c->d2h_bytes += (int64_t)n;
+}
+}  // namespace
 
 struct nw_result {
   nw_stats stats{};
@@ -202,9 +223,9 @@ void setup_region(nw_ctx* c, const int8_t* aln, int n_x, int n_y, const int64_t*
   }
   RegionHost& H = c->RH;
   cudaStream_t st = c->stream;
-  CK(cudaMemcpyAsync(c->d_ctx.ensure(H.ctx.size()), H.ctx.data(), H.ctx.size(), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(c->d_rt.ensure(H.rt.size() * 4), H.rt.data(), H.rt.size() * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(c->d_cumr.ensure(H.cumr.size() * 4), H.cumr.data(), H.cumr.size() * 4, cudaMemcpyHostToDevice, st));
+  h2d(c, c->d_ctx.ensure(H.ctx.size()), H.ctx.data(), H.ctx.size());
+  h2d(c, c->d_rt.ensure(H.rt.size() * 4), H.rt.data(), H.rt.size() * 4);
+  h2d(c, c->d_cumr.ensure(H.cumr.size() * 4), H.cumr.data(), H.cumr.size() * 4);
   const size_t msb = (size_t)(n_x + 1) * H.MW * 4;
   CK(cudaMemsetAsync(c->d_msdd.ensure(msb), 0, msb, st));
   CK(cudaMemsetAsync(c->d_msinv.ensure(msb), 0, msb, st));
@@ -276,7 +297,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
   }
   if (cells_out) *cells_out = cells;
   if (bk.empty()) return;
-  c->bands.upload(st);
+  c->bands.upload(c, st);
   std::stable_sort(bk.begin(), bk.end(), [](const Bucket& a, const Bucket& b) {
     const int ka = a.cls ? a.cls : 1 << 20, kb = b.cls ? b.cls : 1 << 20;
     return ka < kb;
@@ -298,7 +319,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
     ranges.back().end = pos;
   }
   const uint32_t n_work = pos;
-  CK(cudaMemcpyAsync(c->bstart.ensure((LMAX + 2) * 4), bstart.data(), (LMAX + 2) * 4, cudaMemcpyHostToDevice, st));
+  h2d(c, c->bstart.ensure((LMAX + 2) * 4), bstart.data(), (LMAX + 2) * 4);
   CK(cudaMemsetAsync(c->cursor.ensure((LMAX + 2) * 4), 0, (LMAX + 2) * 4, st));
   CK(cudaMemsetAsync(c->work.ensure((size_t)n_work * 4, true), 0xFF, (size_t)n_work * 4, st));
   c->launches += launch_bucket_scatter(c->new_len.as<uint16_t>(), Lv.n_new, c->RD.n_y, force, c->bstart.as<uint32_t>(),
@@ -323,6 +344,15 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
   for (const Range& r : ranges) {
     A.work = c->work.as<uint32_t>() + r.begin;
     A.n_work = r.end - r.begin;
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!c->event_pool.empty()) {
+      ev = c->event_pool.back();
+      c->event_pool.pop_back();
+    } else {
+      CK(cudaEventCreate(&ev.first));
+      CK(cudaEventCreate(&ev.second));
+    }
+    CK(cudaEventRecord(ev.first, st));
     if (r.cls) {
       const int l = launch_score_fast(r.cls, A, st);
       if (l < 0) fail(NW_ERR_CUDA, "no register-DP kernel for window " + std::to_string(r.cls));
@@ -332,8 +362,24 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
       A.scratch = (int32_t*)c->scratch.ensure(sc);
       c->launches += launch_score_generic(A, st);
     }
+    CK(cudaEventRecord(ev.second, st));
+    c->score_events.push_back(ev);
   }
   CK(cudaGetLastError());
+}
+
+// sums and recycles the DP-kernel event pairs (stream must be idle)
+void collect_score_time(nw_ctx* c, float* ms_out, int* launches_out) {
+  float tot = 0;
+  for (auto& ev : c->score_events) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev.first, ev.second);
+    tot += ms;
+    c->event_pool.push_back(ev);
+  }
+  if (ms_out) *ms_out = tot;
+  if (launches_out) *launches_out = (int)c->score_events.size();
+  c->score_events.clear();
 }
 
 struct Search {
@@ -373,12 +419,12 @@ struct Search {
     L1.pstride = blob_stride(L1.LS);
     std::vector<unsigned char> blob(L1.pstride);
     fill_blob(blob.data(), L1.LS, root.data(), n_x, c->h_pow.data());
-    CK(cudaMemcpyAsync(L1.fblob.ensure(blob.size()), blob.data(), blob.size(), cudaMemcpyHostToDevice, s));
+    h2d(c, L1.fblob.ensure(blob.size()), blob.data(), blob.size());
     const int32_t len = n_x, id = 1;
     const uint8_t dupok = (1 <= o.maxdup) ? 1 : 0;  // duplication_count(root) == 1 (solver.jl:611)
-    CK(cudaMemcpyAsync(L1.flen.ensure(4), &len, 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(L1.fid.ensure(4), &id, 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(L1.fdup.ensure(1), &dupok, 1, cudaMemcpyHostToDevice, s));
+    h2d(c, L1.flen.ensure(4), &len, 4);
+    h2d(c, L1.fid.ensure(4), &id, 4);
+    h2d(c, L1.fdup.ensure(1), &dupok, 1);
     CK(cudaStreamSynchronize(s));
     // level 0: one pseudo candidate (the root itself, KIND_ID over frontier slot 0 of level 1), id 1
     L0.G = 1;
@@ -388,9 +434,9 @@ struct Search {
     const uint64_t d0 = pack_desc(0, 0, 0, KIND_ID);
     const int32_t one = 1;
     const uint32_t zero = 0;
-    CK(cudaMemcpyAsync(L0.desc.ensure(8), &d0, 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(L0.cand_id.ensure(4), &one, 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(L0.newlist.ensure(4), &zero, 4, cudaMemcpyHostToDevice, s));
+    h2d(c, L0.desc.ensure(8), &d0, 8);
+    h2d(c, L0.cand_id.ensure(4), &one, 4);
+    h2d(c, L0.newlist.ensure(4), &zero, 4);
     L0.k3.ensure(4);
     L0.cost.ensure(4);
     L0.total.ensure(4);
@@ -408,15 +454,15 @@ struct Search {
     CK(cudaMemsetAsync(misc, 0, 256, s));
     std::vector<uint32_t> hist(LMAX + 2, 0);
     const uint16_t rl = (uint16_t)n_x;
-    CK(cudaMemcpyAsync(c->new_len.ensure(2), &rl, 2, cudaMemcpyHostToDevice, s));
+    h2d(c, c->new_len.ensure(2), &rl, 2);
     if (early_exit(n_x, c->RD.n_y)) {
       root_k3 = 0;
       root_cost = -1;
       root_total = 0;
       const int32_t v[3] = {0, -1, 0};
-      CK(cudaMemcpyAsync(L0.k3.p, &v[0], 4, cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(L0.cost.p, &v[1], 4, cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(L0.total.p, &v[2], 4, cudaMemcpyHostToDevice, s));
+      h2d(c, L0.k3.p, &v[0], 4);
+      h2d(c, L0.cost.p, &v[1], 4);
+      h2d(c, L0.total.p, &v[2], 4);
       CK(cudaStreamSynchronize(s));
     } else {
       hist[n_x] = 1;
@@ -424,9 +470,9 @@ struct Search {
       view.F = L1.frontier();
       run_scoring(c, view, hist.data(), 0, o.flags, misc + 1 /*dummy best*/, nullptr);
       int32_t v[3];
-      CK(cudaMemcpyAsync(&v[0], L0.k3.p, 4, cudaMemcpyDeviceToHost, s));
-      CK(cudaMemcpyAsync(&v[1], L0.cost.p, 4, cudaMemcpyDeviceToHost, s));
-      CK(cudaMemcpyAsync(&v[2], L0.total.p, 4, cudaMemcpyDeviceToHost, s));
+      d2h(c, &v[0], L0.k3.p, 4);
+      d2h(c, &v[1], L0.cost.p, 4);
+      d2h(c, &v[2], L0.total.p, 4);
       CK(cudaStreamSynchronize(s));
       root_k3 = v[0];
       root_cost = v[1];
@@ -451,7 +497,7 @@ struct Search {
     uint32_t* off = (uint32_t*)c->off.ensure((size_t)L.P * 4, true);
     uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items((uint64_t)L.P) * 4, true);
     c->launches += launch_scan(E.cnt, off, (uint64_t)L.P, bsum, (uint32_t*)(misc + 4), s);
-    CK(cudaMemcpyAsync(pin_u32(), misc, 32, cudaMemcpyDeviceToHost, s));
+    d2h(c, pin_u32(), misc, 32);
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     const uint32_t G = pin_u32()[4];
@@ -480,7 +526,7 @@ struct Search {
     uint32_t* newrank = (uint32_t*)c->newrank.ensure((size_t)G * 4, true);
     bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(G) * 4, true);
     c->launches += launch_scan(is_new, newrank, G, bsum, (uint32_t*)(misc + 5), s);
-    CK(cudaMemcpyAsync(pin_u32(), misc, 32, cudaMemcpyDeviceToHost, s));
+    d2h(c, pin_u32(), misc, 32);
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     const uint32_t n_new = pin_u32()[5];
@@ -515,7 +561,7 @@ struct Search {
     CK(cudaMemsetAsync(A.hist, 0, (LMAX + 2) * 4, s));
     c->launches += launch_assign(A, s);
     uint32_t* hist_h = pin_u32() + 64;
-    CK(cudaMemcpyAsync(hist_h, A.hist, (LMAX + 2) * 4, cudaMemcpyDeviceToHost, s));
+    d2h(c, hist_h, A.hist, (LMAX + 2) * 4);
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     int64_t cells = 0;
@@ -545,7 +591,7 @@ struct Search {
     uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(n) * 4, true);
     c->launches += launch_valid_flags(Lr.k3.as<int32_t>(), n, flag, s);
     c->launches += launch_scan(flag, pre, n, bsum, (uint32_t*)(misc + 6), s);
-    CK(cudaMemcpyAsync(pin_u32(), misc, 32, cudaMemcpyDeviceToHost, s));
+    d2h(c, pin_u32(), misc, 32);
     CK(cudaStreamSynchronize(s));
     const uint32_t nvalid = pin_u32()[6];
     uint32_t P2 = nvalid;
@@ -624,7 +670,7 @@ struct Search {
         break;
       }
     }
-    CK(cudaMemcpyAsync(pin_u32(), misc, 4, cudaMemcpyDeviceToHost, s));
+    d2h(c, pin_u32(), misc, 4);
     CK(cudaEventRecord(ev1, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
@@ -672,7 +718,7 @@ struct Search {
       uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.G) * 4, true);
       c->launches += launch_edge_flags(L.cand_id.as<int32_t>(), L.G, needed, eflag, s);
       c->launches += launch_scan(eflag, epre, L.G, bsum, (uint32_t*)(misc + 8), s);
-      CK(cudaMemcpyAsync(pin_u32(), misc, 64, cudaMemcpyDeviceToHost, s));
+      d2h(c, pin_u32(), misc, 64);
       CK(cudaStreamSynchronize(s));
       const uint32_t ne = pin_u32()[8];
       if (ne) {
@@ -680,7 +726,7 @@ struct Search {
         c->launches += launch_edge_compact(L.cand_id.as<int32_t>(), L.desc.as<uint64_t>(), L.fid.as<int32_t>(), L.G,
                                            eflag, epre, d_e, s);
         std::vector<EdgeRec> he(ne);
-        CK(cudaMemcpyAsync(he.data(), d_e, (size_t)ne * sizeof(EdgeRec), cudaMemcpyDeviceToHost, s));
+        d2h(c, he.data(), d_e, (size_t)ne * sizeof(EdgeRec));
         CK(cudaStreamSynchronize(s));
         for (const EdgeRec& e : he) nodes[e.child].in.push_back(e);
       }
@@ -691,7 +737,7 @@ struct Search {
         bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.n_new) * 4, true);
         c->launches += launch_id_flags(needed, L.id_base, L.n_new, iflag, s);
         c->launches += launch_scan(iflag, ipre, L.n_new, bsum, (uint32_t*)(misc + 9), s);
-        CK(cudaMemcpyAsync(pin_u32(), misc, 64, cudaMemcpyDeviceToHost, s));
+        d2h(c, pin_u32(), misc, 64);
         CK(cudaStreamSynchronize(s));
         const uint32_t ni = pin_u32()[9];
         if (ni) {
@@ -699,7 +745,7 @@ struct Search {
           c->launches += launch_id_compact(L.k3.as<int32_t>(), L.cost.as<int32_t>(), L.total.as<int32_t>(), L.id_base,
                                            L.n_new, iflag, ipre, d_i, s);
           std::vector<IdRec> hi(ni);
-          CK(cudaMemcpyAsync(hi.data(), d_i, (size_t)ni * sizeof(IdRec), cudaMemcpyDeviceToHost, s));
+          d2h(c, hi.data(), d_i, (size_t)ni * sizeof(IdRec));
           CK(cudaStreamSynchronize(s));
           for (const IdRec& r : hi) {
             Node& nd = nodes[r.id];
@@ -805,18 +851,18 @@ struct Search {
       const Level& L = lv[l];
       if (L.n_new) {
         std::vector<int32_t> k3(L.n_new), cost(L.n_new), total(L.n_new);
-        CK(cudaMemcpyAsync(k3.data(), L.k3.p, (size_t)L.n_new * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(cost.data(), L.cost.p, (size_t)L.n_new * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(total.data(), L.total.p, (size_t)L.n_new * 4, cudaMemcpyDeviceToHost, s));
+        d2h(c, k3.data(), L.k3.p, (size_t)L.n_new * 4);
+        d2h(c, cost.data(), L.cost.p, (size_t)L.n_new * 4);
+        d2h(c, total.data(), L.total.p, (size_t)L.n_new * 4);
         CK(cudaStreamSynchronize(s));
         for (uint32_t r = 0; r < L.n_new; ++r) put(L.id_base + (int32_t)r, k3[r], cost[r], total[r], l);
       }
       if (L.G) {
         std::vector<int32_t> cid(L.G), fid(L.P);
         std::vector<uint64_t> desc(L.G);
-        CK(cudaMemcpyAsync(cid.data(), L.cand_id.p, (size_t)L.G * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(desc.data(), L.desc.p, (size_t)L.G * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(fid.data(), L.fid.p, (size_t)L.P * 4, cudaMemcpyDeviceToHost, s));
+        d2h(c, cid.data(), L.cand_id.p, (size_t)L.G * 4);
+        d2h(c, desc.data(), L.desc.p, (size_t)L.G * 8);
+        d2h(c, fid.data(), L.fid.p, (size_t)L.P * 4);
         CK(cudaStreamSynchronize(s));
         for (uint32_t g = 0; g < L.G; ++g) {
           R->e_child.push_back(cid[g]);
@@ -859,12 +905,18 @@ void do_solve(nw_ctx* c, const int8_t* aln, int n_x, int n_y, const int64_t* len
               const nw_opts* o, nw_result* R) {
   CK(cudaSetDevice(c->device));
   c->launches = 0;
+  c->h2d_bytes = c->d2h_bytes = 0;
+  collect_score_time(c, nullptr, nullptr);
   setup_region(c, aln, n_x, n_y, len_x, len_y, o->maxdepth, false);
   Search S(c, *o);
   S.run();
+  collect_score_time(c, &S.st.score_ms, &S.st.score_launches);
   if (!(o->flags & NW_FLAG_NO_TRAJ)) S.report(R);
   if (o->keep_ids) S.dump_ids(R);
+  collect_score_time(c, nullptr, nullptr);
   S.st.kernel_launches = c->launches;
+  S.st.h2d_bytes = c->h2d_bytes;
+  S.st.d2h_bytes = c->d2h_bytes;
   R->stats = S.st;
 }
 
@@ -924,6 +976,11 @@ void nw_ctx_destroy(nw_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->pinned) cudaFreeHost(c->pinned);
+  for (auto& ev : c->score_events) c->event_pool.push_back(ev);
+  for (auto& ev : c->event_pool) {
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
   cudaStream_t s = c->stream;
   delete c;
   if (s) cudaStreamDestroy(s);
@@ -1075,21 +1132,21 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
     }
     L.G = (uint32_t)n;
     L.n_new = (uint32_t)n;
-    CK(cudaMemcpyAsync(L.fblob.ensure(seqs.size() * 2), seqs.data(), seqs.size() * 2, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(L.flen.ensure(n * 4), lens.data(), n * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(L.desc.ensure(n * 8), desc.data(), n * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(L.newlist.ensure(n * 4), newlist.data(), n * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(c->new_len.ensure(n * 2, true), nlen.data(), n * 2, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(L.k3.ensure(n * 4), k3.data(), n * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(L.cost.ensure(n * 4), cost.data(), n * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(L.total.ensure(n * 4), total.data(), n * 4, cudaMemcpyHostToDevice, s));
+    h2d(c, L.fblob.ensure(seqs.size() * 2), seqs.data(), seqs.size() * 2);
+    h2d(c, L.flen.ensure(n * 4), lens.data(), n * 4);
+    h2d(c, L.desc.ensure(n * 8), desc.data(), n * 8);
+    h2d(c, L.newlist.ensure(n * 4), newlist.data(), n * 4);
+    h2d(c, c->new_len.ensure(n * 2, true), nlen.data(), n * 2);
+    h2d(c, L.k3.ensure(n * 4), k3.data(), n * 4);
+    h2d(c, L.cost.ensure(n * 4), cost.data(), n * 4);
+    h2d(c, L.total.ensure(n * 4), total.data(), n * 4);
     int32_t* misc = (int32_t*)c->misc.ensure(256);
     CK(cudaMemsetAsync(misc, 0, 256, s));
     CK(cudaStreamSynchronize(s));
     run_scoring(c, view_of(L), hist.data(), force, flags, misc + 1, nullptr);
-    CK(cudaMemcpyAsync(k3.data(), L.k3.p, n * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(cost.data(), L.cost.p, n * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(total.data(), L.total.p, n * 4, cudaMemcpyDeviceToHost, s));
+    d2h(c, k3.data(), L.k3.p, n * 4);
+    d2h(c, cost.data(), L.cost.p, n * 4);
+    d2h(c, total.data(), L.total.p, n * 4);
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     for (int64_t k = 0; k < n; ++k) {
@@ -1113,8 +1170,8 @@ int nw_moveset(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, uint8_t* 
     setup_region(c, aln, n_x, n_y, lx.data(), ly.data(), 1, false);
     const int MW = c->RH.MW;
     std::vector<uint32_t> dd((size_t)(n_x + 1) * MW), iv((size_t)(n_x + 1) * MW);
-    CK(cudaMemcpyAsync(dd.data(), c->d_msdd.p, dd.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(iv.data(), c->d_msinv.p, iv.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    d2h(c, dd.data(), c->d_msdd.p, dd.size() * 4);
+    d2h(c, iv.data(), c->d_msinv.p, iv.size() * 4);
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     for (int a = 1; a <= n_x; ++a)
@@ -1122,6 +1179,51 @@ int nw_moveset(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, uint8_t* 
         dup_del[(size_t)(a - 1) * n_x + (b - 1)] = (dd[(size_t)a * MW + (b >> 5)] >> (b & 31)) & 1u;
         invert[(size_t)(a - 1) * n_x + (b - 1)] = (iv[(size_t)a * MW + (b >> 5)] >> (b & 31)) & 1u;
       }
+  });
+  if (rc != NW_OK) cudaGetLastError();
+  return rc;
+}
+
+int nw_bench_peaks(nw_ctx* c, double out[4]) {
+  if (!c || !out) return NW_ERR_ARG;
+  const int rc = guard([&] {
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    int* sink = (int*)c->scratch.ensure((size_t)148 * 8 * 256 * 4);
+    for (int mode = 0; mode < 3; ++mode) {
+      double best = 0;
+      for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(a, s));
+        const double n = launch_int_peak(mode, sink, 4096, s);
+        CK(cudaEventRecord(b, s));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep) best = std::max(best, n / (ms * 1e-3));
+      }
+      out[mode] = best;
+    }
+    const size_t bytes = (size_t)1 << 30;
+    DevBuf x, y;
+    x.ensure(bytes);
+    y.ensure(bytes);
+    double bw = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+      CK(cudaEventRecord(a, s));
+      CK(cudaMemcpyAsync(y.p, x.p, bytes, cudaMemcpyDeviceToDevice, s));
+      CK(cudaEventRecord(b, s));
+      CK(cudaEventSynchronize(b));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, a, b);
+      if (rep) bw = std::max(bw, 2.0 * bytes / (ms * 1e-3));
+    }
+    out[3] = bw;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    CK(cudaGetLastError());
   });
   if (rc != NW_OK) cudaGetLastError();
   return rc;

@@ -716,6 +716,48 @@ int launch_id_compact(const int32_t* k3, const int32_t* cost, const int32_t* tot
   return 1;
 }
 
+// =====================================================================================================
+// integer-pipe roofline denominators: dependency-free micro-kernels, 8 independent chains / thread.
+// MODE 0: VIADDMNMX (DPX add+max, alu pipe)   MODE 1: IADD3 (alu pipe)   MODE 2: VIADDMNMX + IMAD interleaved
+// (alu + fma pipes).  Reported as thread-instructions per second.
+// =====================================================================================================
+template <int MODE>
+__global__ void __launch_bounds__(256) k_int_peak(int* out, int iters, int a, int b, int m) {
+  int x[8], y[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    x[k] = threadIdx.x + k;
+    y[k] = blockIdx.x - k;
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (MODE == 0) x[k] = __viaddmax_s32(x[k], a, b + k);
+        if (MODE == 1) x[k] = x[k] + x[(k + 1) & 7] + a;  // IADD3; operands change every step, nothing is loop-invariant
+        if (MODE == 2) {
+          x[k] = __viaddmax_s32(x[k], a, b + k);
+          y[k] = y[k] * m + a;
+        }
+      }
+    }
+  }
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += x[k] ^ y[k];
+  if (s == 0x7fffffff) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// returns thread-instructions issued per launch
+double launch_int_peak(int mode, int* out, int iters, cudaStream_t st) {
+  const int grid = 148 * 8, block = 256;
+  if (mode == 0) k_int_peak<0><<<grid, block, 0, st>>>(out, iters, 3, 1000, 1);
+  if (mode == 1) k_int_peak<1><<<grid, block, 0, st>>>(out, iters, 3, 1000, 1);
+  if (mode == 2) k_int_peak<2><<<grid, block, 0, st>>>(out, iters, 3, 1000, 1);
+  const double per_thread = (double)iters * 4 * 8 * (mode == 2 ? 2 : 1);
+  return per_thread * grid * block;
+}
+
 int launch_moveset(const RegionDev& R, cudaStream_t st) {
   const long long n = (long long)R.n_x * R.n_x;
   k_moveset<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R);

@@ -162,6 +162,12 @@ class Solver:
                                          _p(total), _p(score)))
         return score, cost, total
 
+    def bench_peaks(self):
+        """Measured roofline denominators: dict of thread-instr/s for VIADDMNMX, IADD3, mixed alu+fma; copy B/s."""
+        out = (C.c_double * 4)()
+        _lib.check(self.L.nw_bench_peaks(self.h, C.byref(out)))
+        return dict(viaddmnmx_ips=out[0], iadd3_ips=out[1], mixed_ips=out[2], copy_Bps=out[3])
+
     def moveset(self, aln):
         """to_moveset (solver.jl:217-231) -> (duplicate_delete, invert) bool [n_x, n_x]."""
         aln = np.ascontiguousarray(aln, dtype=np.int8)

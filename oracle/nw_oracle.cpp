@@ -67,6 +67,7 @@ struct Opts {
   int64_t maxwidth = -1;  // -1 == nothing
   double minreport = 0.95;
   int64_t maxreport = -1;  // -1 == nothing
+  int64_t max_scored = -1; // bench only: stop the search after this many slow_score calls (bounded CPU sample)
 };
 
 struct ScoreOut {
@@ -253,6 +254,8 @@ struct Search {
   ScoreScratch ws;
   Stats st;
   int cur_level = 0;
+  int64_t scored_total = 0;
+  bool stop = false;
   explicit Search(const Problem& p, const Opts& o) : P(p), O(o) { ms = to_moveset(p); }
 
   void record(const Index& index, double score, const ScoreOut& so) {
@@ -273,6 +276,7 @@ struct Search {
     if (it == im.map.end()) {
       ScoreOut so = slow_score(P, index.data(), (int)index.size(), ws);
       st.scored.back() += 1;
+      if (O.max_scored >= 0 && ++scored_total >= O.max_scored) stop = true;
       st.cells.back() += so.cells;
       double score = so.score;
       if (score > best) best = score;
@@ -301,8 +305,8 @@ struct Search {
     const int64_t parent_id = it->second;
     const double current_best = best;
     const int L = (int)index.size();
-    for (int i = 1; i <= L; ++i) {
-      for (int j = i + 1; j <= L; ++j) {
+    for (int i = 1; i <= L && !stop; ++i) {
+      for (int j = i + 1; j <= L && !stop; ++j) {
         // :180-190 retrieve_possible_moves
         int i1 = index[i - 1], i2 = index[j - 1];
         bool flip = (i1 * i2) < 0;
@@ -368,7 +372,10 @@ struct Search {
       }
       std::vector<Index> new_indices;
       open_level(indices.size());
-      for (const Index& cur : indices) best = all_moves_scored(cur, best, new_indices, subopt);
+      for (const Index& cur : indices) {
+        if (stop) break;
+        best = all_moves_scored(cur, best, new_indices, subopt);
+      }
       indices.swap(new_indices);
       now = std::chrono::steady_clock::now();
       st.level_seconds.push_back(std::chrono::duration<double>(now - tl).count());
@@ -556,6 +563,7 @@ struct nwo_opts {
   int64_t maxwidth;  // -1 none
   double minreport;
   int64_t maxreport;  // -1 none
+  int64_t max_scored; // -1 none (bench-only bounded sample)
 };
 
 struct nwo_result {
@@ -588,6 +596,7 @@ static nwo_result* solve_impl(Problem&& P, const nwo_opts* o, int want_trajs) {
   R->O.maxwidth = o->maxwidth;
   R->O.minreport = o->minreport;
   R->O.maxreport = o->maxreport;
+  R->O.max_scored = o->max_scored;
   Search S(R->P, R->O);
   R->best = S.run(R->O.maxdepth);
   R->im = std::move(S.im);
@@ -716,7 +725,7 @@ int nwo_f32_string(float v, char* buf, int cap) {
 #ifdef NWO_MAIN
 // CLI with solver.jl's argument table (:756-791).
 int main(int argc, char** argv) {
-  nwo_opts o{3, 3, -1, 0.95, -1};
+  nwo_opts o{3, 3, -1, 0.95, -1, -1};
   std::vector<const char*> pos;
   for (int a = 1; a < argc; ++a) {
     std::string s = argv[a];

@@ -14,7 +14,7 @@ _LIB = None
 
 class NwoOpts(C.Structure):
     _fields_ = [("maxdepth", C.c_int32), ("maxdup", C.c_int32), ("maxwidth", C.c_int64),
-                ("minreport", C.c_double), ("maxreport", C.c_int64)]
+                ("minreport", C.c_double), ("maxreport", C.c_int64), ("max_scored", C.c_int64)]
 
 
 def build():
@@ -59,9 +59,9 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def make_opts(maxdepth=3, maxdup=3, maxwidth=None, minreport=0.95, maxreport=None):
+def make_opts(maxdepth=3, maxdup=3, maxwidth=None, minreport=0.95, maxreport=None, max_scored=None):
     return NwoOpts(maxdepth, maxdup, -1 if maxwidth is None else int(maxwidth), float(minreport),
-                   -1 if maxreport is None else int(maxreport))
+                   -1 if maxreport is None else int(maxreport), -1 if max_scored is None else int(max_scored))
 
 
 class OracleResult:
