@@ -41,6 +41,34 @@ struct Err {
            std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
   } while (0)
 
+// Device memory pool: a solve allocates ~2 GB of per-level arrays; cudaMalloc/cudaFree of that size costs tens of
+// milliseconds and synchronises the device, so freed blocks are kept per context and reused by later solves.
+struct DevPool {
+  std::multimap<size_t, void*> free_blocks;
+  size_t pooled_bytes = 0;
+  void* take(size_t bytes, size_t* cap_out) {
+    auto it = free_blocks.lower_bound(bytes);
+    if (it != free_blocks.end() && it->first <= bytes * 2 + (1 << 20)) {
+      void* p = it->second;
+      *cap_out = it->first;
+      pooled_bytes -= it->first;
+      free_blocks.erase(it);
+      return p;
+    }
+    return nullptr;
+  }
+  void give(void* p, size_t cap) {
+    free_blocks.emplace(cap, p);
+    pooled_bytes += cap;
+  }
+  void trim() {
+    for (auto& kv : free_blocks) cudaFree(kv.second);
+    free_blocks.clear();
+    pooled_bytes = 0;
+  }
+};
+static thread_local DevPool* g_pool = nullptr;  // set by the ABI entry points to the calling context's pool
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
@@ -61,7 +89,12 @@ struct DevBuf {
   }
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (g_pool)
+        g_pool->give(p, cap);
+      else
+        cudaFree(p);
+    }
     p = nullptr;
     cap = 0;
   }
@@ -71,7 +104,18 @@ struct DevBuf {
       release();
       size_t want = grow_slack ? bytes + bytes / 4 : bytes;
       want = (want + 255) & ~(size_t)255;
-      CK(cudaMalloc(&p, want));
+      if (g_pool) {
+        p = g_pool->take(want, &cap);
+        if (p) return p;
+      }
+      cudaError_t e = cudaMalloc(&p, want);
+      if (e == cudaErrorMemoryAllocation && g_pool && g_pool->pooled_bytes) {
+        cudaGetLastError();
+        g_pool->trim();
+        e = cudaMalloc(&p, want);
+      }
+      if (e != cudaSuccess) p = nullptr;
+      CK(e);
       cap = want;
     }
     return p;
@@ -153,6 +197,7 @@ struct nw_ctx {
   DevBuf cnt, off, bsum, slot, is_new, newrank, new_len, hist, bstart, cursor, work, scratch, flag, pre, sel, keys,
       misc;
   void* pinned = nullptr;  // small pinned staging area for D2H scalars / histograms
+  DevPool pool;
   int launches = 0;
   int64_t h2d_bytes = 0, d2h_bytes = 0;
   // device time of the dominant (DP) kernels, measured with events on the launching stream
@@ -256,10 +301,17 @@ void table_reserve(nw_ctx* c, uint64_t need_entries) {
   while (want < need_entries * 2) want <<= 1;
   if (want <= c->table_cap) return;
   if (want > (1ull << 32)) fail(NW_ERR_NOMEM, "dedup table would exceed 2^32 slots");
+  const size_t bytes = want * TBL_WORDS * 8;
+  if (c->table_cap == 0) {  // fresh search: reuse the physical buffer when it is large enough
+    c->table.ensure(bytes);
+    CK(cudaMemsetAsync(c->table.p, 0xFF, bytes, c->stream));
+    c->table_cap = want;
+    return;
+  }
   DevBuf nt;
-  nt.ensure(want * TBL_WORDS * 8);
-  CK(cudaMemsetAsync(nt.p, 0xFF, want * TBL_WORDS * 8, c->stream));
-  if (c->table_cap) c->launches += launch_rehash(c->table.as<uint64_t>(), c->table_cap, nt.as<uint64_t>(), want - 1, c->stream);
+  nt.ensure(bytes);
+  CK(cudaMemsetAsync(nt.p, 0xFF, bytes, c->stream));
+  c->launches += launch_rehash(c->table.as<uint64_t>(), c->table_cap, nt.as<uint64_t>(), want - 1, c->stream);
   CK(cudaStreamSynchronize(c->stream));
   c->table = std::move(nt);
   c->table_cap = want;
@@ -444,9 +496,8 @@ struct Search {
     n_ids = 1;
     gtotal = 1;
     // dedup table
-    c->table_cap = 0;
-    c->table.release();
-    table_reserve(c, 1 << 12);
+    c->table_cap = 0;  // logical capacity; the physical buffer is kept across solves
+    table_reserve(c, 1 << 15);
     c->launches += launch_insert_root(L1.fblob.as<int16_t>(), n_x, c->d_pow.as<U4>(), c->RD.rid1, c->table.as<uint64_t>(),
                                       c->table_cap - 1, s);
     // score the root (solver.jl:599) -- its score never updates `best` (:606)
@@ -895,6 +946,12 @@ int guard(const std::function<void()>& fn) {
   }
 }
 
+struct PoolScope {
+  DevPool* prev;
+  explicit PoolScope(nw_ctx* c) : prev(g_pool) { g_pool = c ? &c->pool : nullptr; }
+  ~PoolScope() { g_pool = prev; }
+};
+
 void check_opts(const nw_opts* o) {
   if (!o) fail(NW_ERR_ARG, "opts is null");
   if (o->maxdepth < 1 || o->maxdepth >= MAX_LEVELS) fail(NW_ERR_ARG, "maxdepth must be in [1, 15]");
@@ -956,6 +1013,7 @@ int nw_ctx_create(int device, nw_ctx** out) {
     if (prop.major != 10) fail(NW_ERR_CUDA, std::string("device is not sm_100 (Blackwell B200): ") + prop.name);
     nw_ctx* c = new nw_ctx();
     c->device = device;
+    PoolScope pool_scope(c);
     try {
       CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
       CK(cudaMallocHost(&c->pinned, PINNED_BYTES));
@@ -982,7 +1040,16 @@ void nw_ctx_destroy(nw_ctx* c) {
     cudaEventDestroy(ev.second);
   }
   cudaStream_t s = c->stream;
-  delete c;
+  {
+    // member buffers return to the pool while it is current; the pool itself is then freed explicitly
+    c->pool.trim();
+    DevPool keep;
+    DevPool* prev = g_pool;
+    g_pool = &keep;
+    delete c;
+    g_pool = prev;
+    keep.trim();
+  }
   if (s) cudaStreamDestroy(s);
 }
 
@@ -994,6 +1061,7 @@ int nw_solve(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const int64
   }
   *out = nullptr;
   nw_result* R = new nw_result();
+  PoolScope pool_scope(c);
   const int rc = guard([&] {
     check_opts(o);
     do_solve(c, aln, n_x, n_y, len_x, len_y, o, R);
@@ -1014,6 +1082,7 @@ int nw_solve_files(nw_ctx* c, const char* inmat, const char* inlens, const char*
     return NW_ERR_ARG;
   }
   nw_result R;
+  PoolScope pool_scope(c);
   const int rc = guard([&] {
     check_opts(o);
     ProblemHost P = read_problem(inmat, inlens);
@@ -1090,6 +1159,7 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
     g_last_error = "null argument";
     return NW_ERR_ARG;
   }
+  PoolScope pool_scope(c);
   const int rc = guard([&] {
     CK(cudaSetDevice(c->device));
     if (n == 0) return;
@@ -1164,6 +1234,7 @@ int nw_moveset(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, uint8_t* 
     g_last_error = "null argument";
     return NW_ERR_ARG;
   }
+  PoolScope pool_scope(c);
   const int rc = guard([&] {
     CK(cudaSetDevice(c->device));
     std::vector<int64_t> lx(n_x, 1), ly(n_y, 1);
@@ -1186,6 +1257,7 @@ int nw_moveset(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, uint8_t* 
 
 int nw_bench_peaks(nw_ctx* c, double out[4]) {
   if (!c || !out) return NW_ERR_ARG;
+  PoolScope pool_scope(c);
   const int rc = guard([&] {
     CK(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;

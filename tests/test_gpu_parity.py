@@ -146,7 +146,7 @@ def test_search_parity(solver, oracle, case):
 def test_search_small_and_degenerate(solver, oracle):
     """n_y <= 10 (no early exit, unreachable terminals -> -Inf dropped from the frontier), no moves at all,
     minreport 0 (everything reported incl. the 0-move ref line with its trailing tab), maxreport truncation."""
-    for seed, (n_x, n_y, dens) in enumerate([(6, 5, 0.5), (12, 9, 0.3), (8, 3, 0.6), (4, 4, 0.0), (14, 1, 0.7)]):
+    for seed, (n_x, n_y, dens) in enumerate([(6, 5, 0.5), (10, 9, 0.15), (8, 3, 0.6), (4, 4, 0.0), (14, 1, 0.7)]):
         mat, lx, ly = random_grid(n_x, n_y, dens, 100 + seed)
         aln = to_solver_inputs(mat)
         for kw in (dict(maxdepth=3, maxdup=2, minreport=0.0, maxreport=300),
