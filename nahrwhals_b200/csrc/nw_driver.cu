@@ -344,6 +344,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
     const BandTable& T = c->bands.get(L);
     int cls = 0;
     if (!(flags & NW_FLAG_GENERIC_DP) && T.fast_ok) cls = score_fast_window(T.max_width);
+    if (cls && score_fast_smem(cls, c->RD.ctx_bytes, L) > 200 * 1024) cls = 0;  // tiles would not fit: generic kernel
     bk.push_back(Bucket{L, cls, hist_h[L]});
     cells += (int64_t)hist_h[L] * T.cells;
   }
@@ -358,17 +359,19 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
   struct Range {
     int cls;
     uint32_t begin, end;
+    int lmax;
   };
   std::vector<Range> ranges;
   uint32_t pos = 0;
   for (const Bucket& b : bk) {
     if (ranges.empty() || ranges.back().cls != b.cls) {
       pos = (pos + 127) & ~127u;  // class ranges start on a CTA boundary
-      ranges.push_back(Range{b.cls, pos, pos});
+      ranges.push_back(Range{b.cls, pos, pos, 0});
     }
     bstart[b.L] = pos;
     pos += (b.n + 31) & ~31u;
     ranges.back().end = pos;
+    ranges.back().lmax = std::max(ranges.back().lmax, b.L);
   }
   const uint32_t n_work = pos;
   h2d(c, c->bstart.ensure((LMAX + 2) * 4), bstart.data(), (LMAX + 2) * 4);
@@ -396,6 +399,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
   for (const Range& r : ranges) {
     A.work = c->work.as<uint32_t>() + r.begin;
     A.n_work = r.end - r.begin;
+    A.lmax = r.lmax;
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     if (!c->event_pool.empty()) {
       ev = c->event_pool.back();

@@ -67,6 +67,7 @@ struct ScoreArgs {
   FrontierDev F;
   const uint32_t* work;     // [n_work] new-rank per lane slot, WORK_PAD = idle
   uint32_t n_work;
+  int lmax;                 // longest child in this launch (sizes the shared-memory tiles of k_score_fast)
   const uint32_t* newlist;  // rank -> candidate position in this level
   const uint64_t* desc;
   const int32_t* band_off;  // [Lmax+1] offset (in rows) of the band table of length L, -1 if absent
@@ -131,6 +132,7 @@ struct IdRec {
 int launch_score_fast(int W, const ScoreArgs& A, cudaStream_t st);
 bool score_fast_supports(int width);  // true if some compiled window >= width
 int score_fast_window(int width);     // smallest compiled window >= width (0 if none)
+size_t score_fast_smem(int W, uint32_t ctx_bytes, int lmax);  // dynamic shared memory of one CTA
 
 // ---- small device helpers ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -10,14 +10,19 @@
 
 namespace nw {
 
+// Shared-memory layout per CTA (128 threads = 4 warps):
+//   [ region context (TMA bulk copy) | child rows int16 [Lmax][128] | band rows (per warp) uint32 [4][Lmax+1][1+NWORD] ]
+// The child's block ids are materialised once through the index map into a lane-interleaved smem tile so the row
+// loop never waits on global memory; the warp's band table (one length per warp) is copied next to it.
 template <int W>
 __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
   constexpr int NWORD = (W + 31) / 32;
-  constexpr bool RTREG = (W <= 64);         // rt window in registers (LDS.128) vs predicated scalar LDS per cell
+  constexpr bool RTREG = (W <= 64);  // rt window in registers (LDS.128) vs predicated scalar LDS per cell
   constexpr int RTW = RTREG ? W : 4;
+  constexpr int BROW = 1 + NWORD;    // uint32 words per band row: meta (r0 | sb << 16 | extra << 24), masks
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (tid == 0) {
@@ -27,6 +32,9 @@ __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
   const uint32_t* planes = reinterpret_cast<const uint32_t*>(smem);
   const int32_t* upx = reinterpret_cast<const int32_t*>(smem + A.R.off_upx);
   const int32_t* rtrev = reinterpret_cast<const int32_t*>(smem + A.R.off_rtrev);
+  const int Lmax = A.lmax;
+  int16_t* crow = reinterpret_cast<int16_t*>(smem + A.R.ctx_bytes);
+  uint32_t* brow = reinterpret_cast<uint32_t*>(smem + A.R.ctx_bytes + (size_t)Lmax * 256) + (size_t)warp * (Lmax + 1) * BROW;
 
   const uint32_t w = blockIdx.x * 128u + tid;
   uint32_t r = w < A.n_work ? A.work[w] : WORK_PAD;
@@ -44,32 +52,61 @@ __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
   const int L = A.F.len[ps];
   const int16_t* seq = reinterpret_cast<const int16_t*>(A.F.blob + (size_t)ps * A.F.pstride);
   const int Lc = child_len(L, kind, p, q);  // warp-uniform by construction of the buckets
-  const int boff = A.band_off[Lc];
-  const int16_t* eb_t = A.band_eb + boff;
-  const uint8_t* sb_t = A.band_sb + boff;
-  const uint32_t* mk_t = A.band_mask + (size_t)boff * 4;
-  const int NYP1 = A.R.NYP - 1, PWS = A.R.PWS;
+  // ---- stage this lane's child sequence (index map over the parent, branch-free) ----
+  {
+    // child[t] = sgn(t) * seq[src(t)]:  dup: t<=q ? t : t-q+p ; del: t<p ? t : t+q-p ; inv: p<t<q ? p+q-t (negated) : t
+    const int lo = kind == KIND_DEL ? p - 1 : (kind == KIND_DUP ? q : (kind == KIND_INV ? p : Lc));
+    const int hi = kind == KIND_INV ? q : 0x7fffffff;  // inversion window is (lo, hi)
+    const int shift = kind == KIND_DUP ? p - q : (kind == KIND_DEL ? q - p : 0);
+#pragma unroll 4
+    for (int t = 1; t <= Lc; ++t) {
+      int src = t > lo ? t + shift : t;
+      const bool flip = kind == KIND_INV && t > lo && t < hi;
+      src = flip ? p + q - t : src;
+      const int v = seq[src - 1];
+      crow[(size_t)(t - 1) * 128 + tid] = (int16_t)(flip ? -v : v);
+    }
+  }
+  // ---- stage the warp's band rows ----
+  {
+    const int boff = A.band_off[Lc];
+    const int16_t* eb_t = A.band_eb + boff;
+    const uint8_t* sb_t = A.band_sb + boff;
+    const uint32_t* mk_t = A.band_mask + (size_t)boff * 4;
+    const int NYP1 = A.R.NYP - 1;
+    for (int i = 1 + lane; i <= Lc; i += 32) {
+      const int r0 = NYP1 - (int)eb_t[i];
+      const int sb = sb_t[i];
+      brow[i * BROW] = (uint32_t)r0 | ((uint32_t)min(sb, 2) << 16) | ((uint32_t)max(sb - 2, 0) << 24);
+#pragma unroll
+      for (int t = 0; t < NWORD; ++t) brow[i * BROW + 1 + t] = mk_t[(size_t)i * 4 + t];
+    }
+  }
+  const int PWS = A.R.PWS;
+  const int rt_stride = A.R.rt_copy_stride;
+  const int sum_rt = A.R.sum_rt;
+  __syncwarp();
+  mbar_wait(&bar, 0);
 
   int S[W];
 #pragma unroll
   for (int k = 0; k < W; ++k) S[k] = 0;
   int sumup = 0;
-  int c = child_elem(seq, kind, p, q, 1);
-  mbar_wait(&bar, 0);
   for (int i = 1; i <= Lc; ++i) {
-    const int cn = (i < Lc) ? child_elem(seq, kind, p, q, i + 1) : 0;  // software prefetch of the next row's block
+    const int c = crow[(size_t)(i - 1) * 128 + tid];
+    const uint32_t meta = brow[i * BROW];
     const int x = c < 0 ? -c : c;
     const int up = upx[x];
     sumup += up;
-    const int r0 = NYP1 - (int)eb_t[i];
-    int sb = sb_t[i];
-    const uint32_t* pl = planes + (size_t)(x * 2 + (c < 0 ? 1 : 0)) * PWS + (r0 >> 5);
+    const int r0 = meta & 0xffff;
+    const int sb = (meta >> 16) & 3;
+    const uint32_t* pl = planes + (x * 2 + (c < 0 ? 1 : 0)) * PWS + (r0 >> 5);
     const int sh = r0 & 31;
     uint32_t m[NWORD];
 #pragma unroll
-    for (int t = 0; t < NWORD; ++t) m[t] = __funnelshift_r(pl[t], pl[t + 1], sh) & mk_t[(size_t)i * 4 + t];
+    for (int t = 0; t < NWORD; ++t) m[t] = __funnelshift_r(pl[t], pl[t + 1], sh) & brow[i * BROW + 1 + t];
     // rt of the window columns: 4 shifted copies of rt_rev make the window start 16-B aligned for LDS.128
-    const int* rtw = rtrev + (size_t)(r0 & 3) * A.R.rt_copy_stride + (r0 & ~3);
+    const int* rtw = rtrev + (r0 & 3) * rt_stride + (r0 & ~3);
     int rtr[RTW];
     if (RTREG) {
 #pragma unroll
@@ -81,9 +118,8 @@ __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
         rtr[4 * g + 3] = v.w;
       }
     }
-    while (sb > 2) {
-      dp_row_shift1<W>(S);
-      --sb;
+    if (meta >> 24) {  // rare: window moved by more than two columns (first rows of steep corridors)
+      for (int e = meta >> 24; e > 0; --e) dp_row_shift1<W>(S);
     }
     if (RTREG) {
       if (sb == 0)
@@ -100,9 +136,8 @@ __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
       else
         dp_row_step<W, 2>(S, m, up, rtw);
     }
-    c = cn;
   }
-  const int total = sumup + A.R.sum_rt;
+  const int total = sumup + sum_rt;
   const int cost = total - S[0];
   const int k3 = score_k3(cost, total);
   if (mine) {
@@ -115,7 +150,7 @@ __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
   if (lane == 0) atomicMax(A.best_k3, b);
 }
 
-static const int kWindows[] = {8, 16, 24, 32, 40, 48, 64, 80, 96, 128};
+static const int kWindows[] = {8, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64, 72, 80, 96, 112, 128};
 
 int score_fast_window(int width) {
   for (int w : kWindows)
@@ -124,9 +159,14 @@ int score_fast_window(int width) {
 }
 bool score_fast_supports(int width) { return score_fast_window(width) != 0; }
 
+size_t score_fast_smem(int W, uint32_t ctx_bytes, int lmax) {
+  const int nword = (W + 31) / 32;
+  return (size_t)ctx_bytes + (size_t)lmax * 256 + (size_t)4 * (lmax + 1) * (1 + nword) * 4;
+}
+
 template <int W>
 static int launch_w(const ScoreArgs& A, cudaStream_t st) {
-  const size_t sm = A.R.ctx_bytes;
+  const size_t sm = score_fast_smem(W, A.R.ctx_bytes, A.lmax);
   cudaFuncSetAttribute(k_score_fast<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   k_score_fast<W><<<(A.n_work + 127) / 128, 128, sm, st>>>(A);
   return 1;
@@ -136,14 +176,24 @@ int launch_score_fast(int W, const ScoreArgs& A, cudaStream_t st) {
   if (A.n_work == 0) return 0;
   switch (W) {
     case 8: return launch_w<8>(A, st);
+    case 12: return launch_w<12>(A, st);
     case 16: return launch_w<16>(A, st);
+    case 20: return launch_w<20>(A, st);
     case 24: return launch_w<24>(A, st);
+    case 28: return launch_w<28>(A, st);
     case 32: return launch_w<32>(A, st);
+    case 36: return launch_w<36>(A, st);
     case 40: return launch_w<40>(A, st);
+    case 44: return launch_w<44>(A, st);
     case 48: return launch_w<48>(A, st);
+    case 52: return launch_w<52>(A, st);
+    case 56: return launch_w<56>(A, st);
+    case 60: return launch_w<60>(A, st);
     case 64: return launch_w<64>(A, st);
+    case 72: return launch_w<72>(A, st);
     case 80: return launch_w<80>(A, st);
     case 96: return launch_w<96>(A, st);
+    case 112: return launch_w<112>(A, st);
     case 128: return launch_w<128>(A, st);
     default: return -1;
   }

@@ -60,7 +60,7 @@ int h_score_fast(const int8_t* aln, int n_x, int n_y, const int64_t* len_x, cons
   if (!force && early_exit(Lc, n_y)) return -1;
   BandTable T = build_band(Lc, n_y, force != 0, WINDOW_MAX);
   if (!T.fast_ok) return 0;
-  static const int wins[] = {8, 16, 24, 32, 40, 48, 64, 80, 96, 128};
+  static const int wins[] = {8, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64, 72, 80, 96, 112, 128};
   int W = 0;
   for (int w : wins)
     if (w >= T.max_width) {
@@ -71,14 +71,24 @@ int h_score_fast(const int8_t* aln, int n_x, int n_y, const int64_t* len_x, cons
   int sumup = 0, s = 0;
   switch (W) {
     case 8: s = run_fast<8>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 12: s = run_fast<12>(R, T, parent, kind, p, q, Lc, &sumup); break;
     case 16: s = run_fast<16>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 20: s = run_fast<20>(R, T, parent, kind, p, q, Lc, &sumup); break;
     case 24: s = run_fast<24>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 28: s = run_fast<28>(R, T, parent, kind, p, q, Lc, &sumup); break;
     case 32: s = run_fast<32>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 36: s = run_fast<36>(R, T, parent, kind, p, q, Lc, &sumup); break;
     case 40: s = run_fast<40>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 44: s = run_fast<44>(R, T, parent, kind, p, q, Lc, &sumup); break;
     case 48: s = run_fast<48>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 52: s = run_fast<52>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 56: s = run_fast<56>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 60: s = run_fast<60>(R, T, parent, kind, p, q, Lc, &sumup); break;
     case 64: s = run_fast<64>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 72: s = run_fast<72>(R, T, parent, kind, p, q, Lc, &sumup); break;
     case 80: s = run_fast<80>(R, T, parent, kind, p, q, Lc, &sumup); break;
     case 96: s = run_fast<96>(R, T, parent, kind, p, q, Lc, &sumup); break;
+    case 112: s = run_fast<112>(R, T, parent, kind, p, q, Lc, &sumup); break;
     default: s = run_fast<128>(R, T, parent, kind, p, q, Lc, &sumup); break;
   }
   const int64_t total = (int64_t)sumup + R.sum_rt;
