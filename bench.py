@@ -35,9 +35,12 @@ WORKLOADS = {
             dict(maxdepth=3, maxdup=2, maxwidth=None, minreport=0.98, maxreport=1000),
             "synthetic 64-block signed gridmatrix (sdgrid 64 blocks, families 10/9/8/8/7 = 158 repeat pairs), "
             "exhaustive depth-3 inv/del/dup search, -d 3 -u 2 -r 0.98 -R 1000"),
-    "s150": (dict(n_x=150, families=[8, 7, 6, 6, 5, 5, 4], chain_depth=4),
+    "s150": (dict(n_x=150, families=[8, 7, 6, 6, 5, 5, 4], chain_depth=4, len_tol=0.12),
              dict(maxdepth=4, maxdup=2, maxwidth=1000, minreport=0.98, maxreport=1000),
-             "synthetic 150-block gridmatrix, depth-4 search, -d 4 -u 2 -w 1000 -r 0.98 -R 1000"),
+             "synthetic 150-block gridmatrix (105 repeat pairs), depth-4 search, -d 4 -u 2 -w 1000 -r 0.98 -R 1000"),
+    "s150d3": (dict(n_x=150, families=[8, 7, 6, 6, 5, 5, 4], chain_depth=3, len_tol=0.12),
+               dict(maxdepth=3, maxdup=2, maxwidth=None, minreport=0.98, maxreport=1000),
+               "synthetic 150-block gridmatrix (105 repeat pairs), exhaustive depth-3 search, -d 3 -u 2 -r 0.98 -R 1000"),
 }
 
 

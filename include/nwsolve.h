@@ -62,6 +62,7 @@ typedef struct nw_stats {
   int64_t d2h_bytes;        /* device->host bytes copied by this call */
   float score_ms;           /* device time inside the banded-DP kernels (events on the launch stream) */
   int32_t score_launches;   /* number of banded-DP kernel launches */
+  float host_ms[4];         /* host wall time: [0] region setup + upload, [1] search, [2] report, [3] keep_ids dump */
 } nw_stats;
 
 void nw_default_opts(nw_opts* o);

@@ -17,7 +17,7 @@ class NwStats(C.Structure):
                 ("scored", C.c_int64 * 16), ("cells", C.c_int64 * 16), ("frontier", C.c_int64 * 16),
                 ("level_ms", C.c_float * 16), ("total_ms", C.c_float), ("n_ids", C.c_int64), ("best", C.c_double),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("score_ms", C.c_float),
-                ("score_launches", C.c_int32)]
+                ("score_launches", C.c_int32), ("host_ms", C.c_float * 4)]
 
 
 FLAG_GENERIC_DP = 1

@@ -69,28 +69,36 @@ struct U4 {
   uint32_t v[4];
 };
 
-// Prefix tables of a parent d (0-based t):  F[n] = sum_{t<n} val(d_t) B^t ,  G[n] = sum_{t<n} val(d_t) B^-t.
-// pw[e + FP_EMAX] = B^e.  Child hash over its own 0-based positions, then finalised with the region id as a
-// leading element:  H = val(rid+1) + B * Hseq.
-NW_HD U4 child_fingerprint(const U4* F, const U4* G, const U4* pw, int L, int kind, int p, int q, uint32_t rid1) {
+// Prefix tables of a parent d (0-based t), already "finalised" with the region id as leading element:
+//   F'[n] = val(rid+1) + B * sum_{t<n} val(d_t) B^t ,   G'[n] = B * sum_{t<n} val(d_t) B^-t ,   pw[e + FP_EMAX] = B^e.
+// The child's fingerprint  H = val(rid+1) + B * sum_t val(c_t) B^t  is composed from differences of these tables in
+// O(1) (the rid term cancels in every difference and survives exactly once through the leading F' term).
+NW_HD U4 child_fingerprint(const U4* F, const U4* G, const U4* pw, int L, int kind, int p, int q) {
   U4 out;
+  const U4 FLv = F[L];
+  if (kind == KIND_DUP) {  // d[0..q-1] ++ d[p..L-1] placed at q
+    const U4 a = F[q], b = F[p], w = pw[FP_EMAX + (q - p)];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int k = 0; k < 4; ++k) {
-    uint32_t h;
-    const uint32_t FL = F[L].v[k];
-    if (kind == KIND_DUP) {  // d[0..q-1] ++ d[p..L-1] placed at q
-      h = addmod(F[q].v[k], mulmod(submod(FL, F[p].v[k]), pw[FP_EMAX + (q - p)].v[k]));
-    } else if (kind == KIND_DEL) {  // d[0..p-2] ++ d[q-1..L-1] placed at p-1
-      h = addmod(F[p - 1].v[k], mulmod(submod(FL, F[q - 1].v[k]), pw[FP_EMAX - (q - p)].v[k]));
-    } else if (kind == KIND_INV) {  // d[0..p-1] ++ -rev(d[p..q-2]) ++ d[q-1..L-1]
-      uint32_t mid = mulmod(submod(G[q - 1].v[k], G[p].v[k]), pw[FP_EMAX + (p + q - 2)].v[k]);
-      h = addmod(submod(F[p].v[k], mid), submod(FL, F[q - 1].v[k]));
-    } else {
-      h = FL;
+    for (int k = 0; k < 4; ++k) out.v[k] = addmod(a.v[k], mulmod(submod(FLv.v[k], b.v[k]), w.v[k]));
+  } else if (kind == KIND_DEL) {  // d[0..p-2] ++ d[q-1..L-1] placed at p-1
+    const U4 a = F[p - 1], b = F[q - 1], w = pw[FP_EMAX - (q - p)];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) out.v[k] = addmod(a.v[k], mulmod(submod(FLv.v[k], b.v[k]), w.v[k]));
+  } else if (kind == KIND_INV) {  // d[0..p-1] ++ -rev(d[p..q-2]) ++ d[q-1..L-1]
+    const U4 a = F[p], b = F[q - 1], g1 = G[q - 1], g0 = G[p], w = pw[FP_EMAX + (p + q - 2)];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t mid = mulmod(submod(g1.v[k], g0.v[k]), w.v[k]);
+      out.v[k] = addmod(submod(a.v[k], mid), submod(FLv.v[k], b.v[k]));
     }
-    out.v[k] = addmod(rid1, mulmod(h, pw[FP_EMAX + 1].v[k]));
+  } else {
+    out = FLv;
   }
   return out;
 }

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <functional>
 #include <map>
 #include <string>
@@ -474,7 +475,7 @@ struct Search {
     L1.LS = round_ls(n_x);
     L1.pstride = blob_stride(L1.LS);
     std::vector<unsigned char> blob(L1.pstride);
-    fill_blob(blob.data(), L1.LS, root.data(), n_x, c->h_pow.data());
+    fill_blob(blob.data(), L1.LS, root.data(), n_x, c->h_pow.data(), c->RD.rid1);
     h2d(c, L1.fblob.ensure(blob.size()), blob.data(), blob.size());
     const int32_t len = n_x, id = 1;
     const uint8_t dupok = (1 <= o.maxdup) ? 1 : 0;  // duplication_count(root) == 1 (solver.jl:611)
@@ -576,6 +577,7 @@ struct Search {
     E.gbase = L.gbase;
     E.pw = c->d_pow.as<U4>();
     c->launches += launch_expand(true, E, s);
+    c->launches += launch_hash_insert(E, G, s);
     uint32_t* is_new = (uint32_t*)c->is_new.ensure((size_t)G * 4, true);
     c->launches += launch_resolve(E.slot, E.table, L.gbase, G, is_new, s);
     uint32_t* newrank = (uint32_t*)c->newrank.ensure((size_t)G * 4, true);
@@ -687,6 +689,7 @@ struct Search {
     M.id2 = (int32_t*)N.fid.ensure((size_t)P2 * 4);
     M.dupok2 = (uint8_t*)N.fdup.ensure((size_t)P2);
     M.pw = c->d_pow.as<U4>();
+    M.rid1 = c->RD.rid1;
     c->launches += launch_materialise(M, s);
     CK(cudaGetLastError());
   }
@@ -750,13 +753,13 @@ struct Search {
 
   static float score_f32(int k3) { return k3 < 0 ? -INFINITY : (float)k3_to_score(k3); }
 
-  void extract(double thr) {
+  void extract(int k3_min) {
     cudaStream_t s = c->stream;
     uint8_t* needed = (uint8_t*)c->flag.ensure((size_t)n_ids + 16, true);
     CK(cudaMemsetAsync(needed, 0, (size_t)n_ids + 16, s));
     const int nl = (int)lv.size();
     for (int l = 1; l < nl; ++l)
-      c->launches += launch_good_flags(lv[l].k3.as<int32_t>(), lv[l].n_new, lv[l].id_base, thr, needed, s);
+      c->launches += launch_good_flags(lv[l].k3.as<int32_t>(), lv[l].n_new, lv[l].id_base, k3_min, needed, s);
     for (int pass = 0; pass <= o.maxdepth + 1; ++pass)
       for (int l = nl - 1; l >= 1; --l)
         c->launches += launch_mark_parents(lv[l].cand_id.as<int32_t>(), lv[l].desc.as<uint64_t>(),
@@ -842,7 +845,39 @@ struct Search {
   void report(nw_result* R) {
     const double best = k3_to_score(best_k3);
     const double thr = o.minreport * best;  // solver.jl:733
-    extract(thr);
+    // smallest k3 whose Float32 score passes `score >= suboptimality * best` (monotone in k3)
+    int k3_min = 100001;
+    {
+      int lo = 0, hi = 100001;  // first k3 in [0, 100000] with (double)(float)(k3/1000) >= thr
+      while (lo < hi) {
+        const int mid = (lo + hi) / 2;
+        if ((double)score_f32(mid) >= thr) hi = mid; else lo = mid + 1;
+      }
+      k3_min = lo;
+    }
+    if (o.maxreport >= 0 && n_ids > o.maxreport) {
+      // every id has at least one trajectory (its discovery chain), so ids below the k3 of the maxreport-th best id
+      // cannot appear among the first maxreport trajectories of the sorted report: raise the threshold to it.
+      cudaStream_t s = c->stream;
+      uint32_t* hist = (uint32_t*)c->keys.ensure((size_t)100002 * 4, true);
+      CK(cudaMemsetAsync(hist, 0, (size_t)100002 * 4, s));
+      for (size_t l = 1; l < lv.size(); ++l) c->launches += launch_k3_hist(lv[l].k3.as<int32_t>(), lv[l].n_new, hist, s);
+      std::vector<uint32_t> hh(100002);
+      d2h(c, hh.data(), hist, hh.size() * 4);
+      CK(cudaStreamSynchronize(s));
+      if (root_k3 >= 0) hh[root_k3] += 1;
+      int64_t cum = 0;
+      int k3_star = 0;
+      for (int k = 100000; k >= 0; --k) {
+        cum += hh[k];
+        if (cum >= o.maxreport) {
+          k3_star = k;
+          break;
+        }
+      }
+      k3_min = std::max(k3_min, k3_star);
+    }
+    extract(k3_min);
     struct Traj {
       int32_t id, k3;
       std::vector<EdgeRec> mv;
@@ -851,7 +886,7 @@ struct Search {
     std::vector<int32_t> good;
     for (auto& kv : nodes) {
       const int k3 = kv.second.k3;
-      if (k3 >= 0 && (double)score_f32(k3) >= thr) good.push_back(kv.first);
+      if (k3 >= 0 && k3 >= k3_min) good.push_back(kv.first);
     }
     std::sort(good.begin(), good.end());  // canonical Dict order: ascending discovery id
     std::vector<std::vector<EdgeRec>> res;
@@ -968,12 +1003,25 @@ void do_solve(nw_ctx* c, const int8_t* aln, int n_x, int n_y, const int64_t* len
   c->launches = 0;
   c->h2d_bytes = c->d2h_bytes = 0;
   collect_score_time(c, nullptr, nullptr);
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<float, std::milli>(b - a).count();
+  };
+  const auto t0 = now();
   setup_region(c, aln, n_x, n_y, len_x, len_y, o->maxdepth, false);
   Search S(c, *o);
+  const auto t1 = now();
   S.run();
+  const auto t2 = now();
   collect_score_time(c, &S.st.score_ms, &S.st.score_launches);
   if (!(o->flags & NW_FLAG_NO_TRAJ)) S.report(R);
+  const auto t3 = now();
   if (o->keep_ids) S.dump_ids(R);
+  const auto t4 = now();
+  S.st.host_ms[0] = ms(t0, t1);
+  S.st.host_ms[1] = ms(t1, t2);
+  S.st.host_ms[2] = ms(t2, t3);
+  S.st.host_ms[3] = ms(t3, t4);
   collect_score_time(c, nullptr, nullptr);
   S.st.kernel_launches = c->launches;
   S.st.h2d_bytes = c->h2d_bytes;

@@ -140,17 +140,17 @@ inline std::vector<U4> build_pow_table() {
 // parent blob: [seq int16 x LS | F U4 x (LS+1) | G U4 x (LS+1)]
 inline uint32_t blob_stride(int LS) { return (uint32_t)LS * 2 + 2u * (uint32_t)(LS + 1) * 16u; }
 inline int round_ls(int L) { return (L + 7) & ~7; }
-inline void fill_blob(unsigned char* out, int LS, const int16_t* seq, int L, const U4* pw) {
+inline void fill_blob(unsigned char* out, int LS, const int16_t* seq, int L, const U4* pw, uint32_t rid1) {
   int16_t* s = reinterpret_cast<int16_t*>(out);
   for (int t = 0; t < LS; ++t) s[t] = t < L ? seq[t] : 0;
   U4* F = reinterpret_cast<U4*>(out + (size_t)LS * 2);
   U4* G = F + (LS + 1);
   for (int k = 0; k < 4; ++k) {
-    F[0].v[k] = 0;
-    G[0].v[k] = 0;
+    F[0].v[k] = rid1;  // F'[n] = rid + B * F[n]
+    G[0].v[k] = 0;     // G'[n] = B * G[n]
     for (int t = 0; t < L; ++t) {
-      F[t + 1].v[k] = addmod(F[t].v[k], mulmod(elem_val(seq[t]), pw[FP_EMAX + t].v[k]));
-      G[t + 1].v[k] = addmod(G[t].v[k], mulmod(elem_val(seq[t]), pw[FP_EMAX - t].v[k]));
+      F[t + 1].v[k] = addmod(F[t].v[k], mulmod(elem_val(seq[t]), pw[FP_EMAX + t + 1].v[k]));
+      G[t + 1].v[k] = addmod(G[t].v[k], mulmod(elem_val(seq[t]), pw[FP_EMAX + 1 - t].v[k]));
     }
     for (int t = L + 1; t <= LS; ++t) {
       F[t].v[k] = F[L].v[k];

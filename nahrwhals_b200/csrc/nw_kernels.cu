@@ -31,18 +31,31 @@ __global__ void k_moveset(RegionDev R) {
 // =====================================================================================================
 // hash table: exact-dedup stand-in (solver.jl:535 haskey / :544 insert).  First discoverer = min gpos.
 // =====================================================================================================
+// 128-bit compare-and-swap (SASS: ATOMG.E.CAS.128); addr must be 16-B aligned
+__device__ __forceinline__ void cas128(uint64_t* addr, uint64_t cl, uint64_t ch, uint64_t vl, uint64_t vh, uint64_t& ol,
+                                       uint64_t& oh) {
+  asm volatile(
+      "{\n .reg .b128 c, v, o;\n mov.b128 c, {%3, %4};\n mov.b128 v, {%5, %6};\n"
+      " atom.global.cas.b128 o, [%2], c, v;\n mov.b128 {%0, %1}, o;\n}"
+      : "=l"(ol), "=l"(oh)
+      : "l"(addr), "l"(cl), "l"(ch), "l"(vl), "l"(vh)
+      : "memory");
+}
+
+// Insert (k0,k1) with discovery position gpos; returns the slot.  Slot = {k0, k1, min gpos, pad}, all-ones = empty.
+// Reads come first: a slot's key never changes once set and its position only decreases, so a stale read can only
+// cause a redundant atomic, never a wrong result.  Duplicates of an index discovered earlier need no atomic at all.
 __device__ __forceinline__ uint32_t table_insert(uint64_t* T, uint64_t mask, uint64_t k0, uint64_t k1, uint64_t gpos) {
   uint64_t s = fp_slot_hash(k0, k1) & mask;
   while (true) {
-    unsigned long long* e = reinterpret_cast<unsigned long long*>(T + s * TBL_WORDS);
-    unsigned long long o0 = e[0];
-    if (o0 == TBL_EMPTY) o0 = atomicCAS(e, (unsigned long long)TBL_EMPTY, (unsigned long long)k0);
-    if (o0 == TBL_EMPTY || o0 == k0) {
-      unsigned long long o1 = atomicCAS(e + 1, (unsigned long long)TBL_EMPTY, (unsigned long long)k1);
-      if (o1 == TBL_EMPTY || o1 == k1) {
-        atomicMin(e + 2, (unsigned long long)gpos);
-        return (uint32_t)s;
-      }
+    uint64_t* e = T + s * TBL_WORDS;
+    const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(e));
+    uint64_t o0 = cur.x, o1 = cur.y;
+    if (o0 == TBL_EMPTY && o1 == TBL_EMPTY) cas128(e, TBL_EMPTY, TBL_EMPTY, k0, k1, o0, o1);
+    if ((o0 == TBL_EMPTY && o1 == TBL_EMPTY) || (o0 == k0 && o1 == k1)) {
+      const uint64_t v = __ldcg(reinterpret_cast<const unsigned long long*>(e + 2));
+      if (v > gpos) atomicMin(reinterpret_cast<unsigned long long*>(e + 2), (unsigned long long)gpos);
+      return (uint32_t)s;
     }
     s = (s + 1) & mask;
   }
@@ -66,9 +79,8 @@ __global__ void k_insert_root(const int16_t* seq, int L, const U4* pw, uint32_t 
 
 // =====================================================================================================
 // expand: one CTA per parent.  Pair loop + retrieve_possible_moves + emission order dup, del, inv
-// (solver.jl:607-638, :180-190).  EMIT=false counts, EMIT=true writes descriptors in discovery order,
-// fingerprints each child through the index map and inserts it into the dedup table.
-// The parent blob (sequence + prefix-hash tables) is staged into shared memory with one TMA bulk copy.
+// (solver.jl:607-638, :180-190).  EMIT=false counts, EMIT=true writes the candidate descriptors in discovery
+// order.  The parent sequence is staged into shared memory with one TMA bulk copy.
 // =====================================================================================================
 __device__ __forceinline__ int pair_moves(const RegionDev& R, int a, int b, int dupok, int& can_dd, int& can_inv) {
   const int aa = a < 0 ? -a : a, bb = b < 0 ? -b : b;
@@ -91,10 +103,8 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
   const int LS = A.F.LS;
   const int dupok = A.F.dupok[parent];
   int16_t* seq = reinterpret_cast<int16_t*>(smem);
-  const U4* Ft = reinterpret_cast<const U4*>(smem + (size_t)LS * 2);
-  const U4* Gt = Ft + (LS + 1);
-  const uint32_t blob_bytes = EMIT ? A.F.pstride : (uint32_t)LS * 2;
-  uint32_t* rowcnt = reinterpret_cast<uint32_t*>(smem + (EMIT ? A.F.pstride : (uint32_t)LS * 2));
+  const uint32_t blob_bytes = (uint32_t)LS * 2;
+  uint32_t* rowcnt = reinterpret_cast<uint32_t*>(smem + blob_bytes);
 
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
@@ -164,14 +174,7 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
         if (cdd && dupok) kinds[nk++] = KIND_DUP;
         if (cdd) kinds[nk++] = KIND_DEL;
         if (civ) kinds[nk++] = KIND_INV;
-        for (int e = 0; e < nk; ++e) {
-          const int kind = kinds[e];
-          const U4 f = child_fingerprint(Ft, Gt, A.pw, L, kind, i, j, A.R.rid1);
-          const uint32_t s = table_insert(A.table, A.tmask, fp_key0(f), fp_key1(f), (uint64_t)A.gbase + pos);
-          A.desc[pos] = pack_desc((uint32_t)parent, i, j, kind);
-          A.slot[pos] = s;
-          ++pos;
-        }
+        for (int e = 0; e < nk; ++e) A.desc[pos++] = pack_desc((uint32_t)parent, i, j, kinds[e]);
       }
     }
   }
@@ -181,7 +184,7 @@ int launch_expand(bool emit, const ExpandArgs& A, cudaStream_t st) {
   if (A.F.P <= 0) return 0;
   const size_t rows = (size_t)A.F.LS * 4;
   if (emit) {
-    const size_t sm = A.F.pstride + rows;
+    const size_t sm = (size_t)A.F.LS * 2 + rows;
     cudaFuncSetAttribute(k_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     k_expand<true><<<A.F.P, 128, sm, st>>>(A);
   } else {
@@ -189,6 +192,29 @@ int launch_expand(bool emit, const ExpandArgs& A, cudaStream_t st) {
     cudaFuncSetAttribute(k_expand<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     k_expand<false><<<A.F.P, 128, sm, st>>>(A);
   }
+  return 1;
+}
+
+// =====================================================================================================
+// dedup insert: one thread per candidate (full lanes, maximal memory-level parallelism for the table atomics).
+// The child is fingerprinted through the index map from its parent's prefix tables (read via the read-only path;
+// candidates of one parent are adjacent, so the tables stay in L1) -- the stand-in for the exact Dict key of
+// solver.jl:535/:544.  The first discoverer of an index is the candidate with the smallest discovery position.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_hash_insert(ExpandArgs A, uint32_t G) {
+  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= G) return;
+  const uint64_t d = A.desc[pos];
+  const uint32_t ps = desc_parent(d);
+  const unsigned char* blob = A.F.blob + (size_t)ps * A.F.pstride;
+  const U4* Ft = reinterpret_cast<const U4*>(blob + (size_t)A.F.LS * 2);
+  const U4* Gt = Ft + (A.F.LS + 1);
+  const U4 f = child_fingerprint(Ft, Gt, A.pw, A.F.len[ps], desc_kind(d), desc_i(d), desc_j(d));
+  A.slot[pos] = table_insert(A.table, A.tmask, fp_key0(f), fp_key1(f), (uint64_t)A.gbase + pos);
+}
+int launch_hash_insert(const ExpandArgs& A, uint32_t G, cudaStream_t st) {
+  if (G == 0) return 0;
+  k_hash_insert<<<(G + 255) / 256, 256, 0, st>>>(A, G);
   return 1;
 }
 
@@ -605,12 +631,13 @@ __global__ void __launch_bounds__(256) k_materialise(MaterialiseArgs A) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = warp & 3, which = warp >> 2;
   U4* tab = reinterpret_cast<U4*>(out + (size_t)A.LS2 * 2) + (which ? (A.LS2 + 1) : 0);
-  uint32_t carry = 0;
-  if (lane == 0) tab[0].v[k] = 0;
+  // F'[n] = rid + B * sum_{t<n} val B^t ;  G'[n] = B * sum_{t<n} val B^-t  (see child_fingerprint)
+  uint32_t carry = which ? 0u : A.rid1;
+  if (lane == 0) tab[0].v[k] = carry;
   for (int t0 = 0; t0 < Lc; t0 += 32) {
     const int t = t0 + lane;
     uint32_t term = 0;
-    if (t < Lc) term = mulmod(elem_val(cs[t]), A.pw[FP_EMAX + (which ? -t : t)].v[k]);
+    if (t < Lc) term = mulmod(elem_val(cs[t]), A.pw[FP_EMAX + (which ? 1 - t : t + 1)].v[k]);
     uint32_t inc = term;
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
@@ -633,13 +660,22 @@ int launch_materialise(const MaterialiseArgs& A, cudaStream_t st) {
 // =====================================================================================================
 // report extraction: which ids are good (solver.jl:733), which ancestors/edges are needed (:688-705)
 // =====================================================================================================
-__global__ void k_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, double thr, uint8_t* needed) {
+// k3_min is the integer image of solver.jl:733 `score >= suboptimality * best` (the Float32 score is monotone in
+// k3; the host finds the smallest passing k3 with the reference's own Float32/Float64 comparison), possibly raised
+// to the k3 of the maxreport-th best id (ids below it can never make the first maxreport trajectories).
+__global__ void k_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, int k3_min, uint8_t* needed) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const int v = k3[r];
-  if (v < 0) return;  // -Inf is never >= minreport*best (best >= 0)
-  const float s32 = (float)k3_to_score(v);  // Float32 storage, solver.jl:84/:547
-  if ((double)s32 >= thr) needed[id_base + r] = 1;
+  if (v >= 0 && v >= k3_min) needed[id_base + r] = 1;
+}
+// histogram of k3 over the fresh ids of a level (warp-aggregated atomics; k3 == 0 is a very hot bin)
+__global__ void k_k3_hist(const int32_t* k3, uint32_t n, uint32_t* hist) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  int key = -1;
+  if (r < n) key = k3[r];
+  const uint32_t peers = __match_any_sync(0xffffffffu, key);
+  if (key >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
 }
 __global__ void k_mark_parents(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
                                uint8_t* needed) {
@@ -682,9 +718,14 @@ __global__ void k_id_compact(const int32_t* k3, const int32_t* cost, const int32
   out[pre[r]] = o;
 }
 
-int launch_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, double thr, uint8_t* needed, cudaStream_t st) {
+int launch_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, int k3_min, uint8_t* needed, cudaStream_t st) {
   if (!n) return 0;
-  k_good_flags<<<(n + 255) / 256, 256, 0, st>>>(k3, n, id_base, thr, needed);
+  k_good_flags<<<(n + 255) / 256, 256, 0, st>>>(k3, n, id_base, k3_min, needed);
+  return 1;
+}
+int launch_k3_hist(const int32_t* k3, uint32_t n, uint32_t* hist, cudaStream_t st) {
+  if (!n) return 0;
+  k_k3_hist<<<(n + 255) / 256, 256, 0, st>>>(k3, n, hist);
   return 1;
 }
 int launch_mark_parents(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,

@@ -118,6 +118,7 @@ struct MaterialiseArgs {
   int32_t* id2;
   uint8_t* dupok2;
   const U4* pw;
+  uint32_t rid1;
 };
 
 struct EdgeRec {

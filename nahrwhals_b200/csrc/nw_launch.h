@@ -11,6 +11,7 @@ int launch_insert_root(const int16_t* seq, int L, const U4* pw, uint32_t rid1, u
                        cudaStream_t st);
 int launch_rehash(const uint64_t* oldT, uint64_t old_cap, uint64_t* newT, uint64_t new_mask, cudaStream_t st);
 int launch_expand(bool emit, const ExpandArgs& A, cudaStream_t st);
+int launch_hash_insert(const ExpandArgs& A, uint32_t G, cudaStream_t st);
 int launch_scan(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* bsum_scratch, uint32_t* total_out,
                 cudaStream_t st);
 uint64_t scan_scratch_items(uint64_t n);
@@ -28,7 +29,8 @@ int launch_make_keys(const int32_t* k3, const uint32_t* flag, const uint32_t* pr
 int launch_sort_u64(uint64_t* keys, uint64_t npad, cudaStream_t st);
 int launch_keys_to_sel(const uint64_t* keys, uint32_t n, uint32_t* sel, cudaStream_t st);
 int launch_materialise(const MaterialiseArgs& A, cudaStream_t st);
-int launch_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, double thr, uint8_t* needed, cudaStream_t st);
+int launch_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, int k3_min, uint8_t* needed, cudaStream_t st);
+int launch_k3_hist(const int32_t* k3, uint32_t n, uint32_t* hist, cudaStream_t st);
 int launch_mark_parents(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
                         uint8_t* needed, cudaStream_t st);
 int launch_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* needed, uint32_t* flag, cudaStream_t st);

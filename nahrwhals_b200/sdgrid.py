@@ -17,8 +17,9 @@ def _apply(kind, d, p, q):
     return d[:p] + [-v for v in reversed(d[p:q - 1])] + d[q - 1:]  # inv
 
 
-def sdgrid(n_x, families, p_inv=0.5, chain_depth=3, seed=1, max_ny=None):
-    """Returns (mat[n_y, n_x] int64, len_x[n_x] int64, len_y[n_y] int64, hidden_moves)."""
+def sdgrid(n_x, families, p_inv=0.5, chain_depth=3, seed=1, max_ny=None, len_tol=None):
+    """Returns (mat[n_y, n_x] int64, len_x[n_x] int64, len_y[n_y] int64, hidden_moves).
+    len_tol: if given, every step of the hidden chain keeps the target length within n_x*(1 +- len_tol)."""
     rng = np.random.default_rng(seed)
     fam = np.zeros(n_x, np.int64)  # 0 = unique block
     slots = rng.permutation(n_x)
@@ -43,9 +44,11 @@ def sdgrid(n_x, families, p_inv=0.5, chain_depth=3, seed=1, max_ny=None):
                     continue
                 rel = orient[abs(a) - 1] * orient[abs(b) - 1] * (1 if a * b > 0 else -1)
                 if rel > 0:
-                    if max_ny is None or L + (q - p) <= max_ny:
+                    hi = max_ny if len_tol is None else int(n_x * (1 + len_tol))
+                    lo = max(2, n_x // 2) if len_tol is None else int(np.ceil(n_x * (1 - len_tol)))
+                    if hi is None or L + (q - p) <= hi:
                         cands.append((0, p, q))
-                    if L - (q - p) >= max(2, n_x // 2):
+                    if L - (q - p) >= lo:
                         cands.append((1, p, q))
                 elif q > p + 1:
                     cands.append((2, p, q))

@@ -113,10 +113,10 @@ int h_fp_check(const int16_t* parent, int L, int kind, int p, int q) {
   static std::vector<U4> pw = build_pow_table();
   const int LS = round_ls(L);
   std::vector<unsigned char> blob(blob_stride(LS));
-  fill_blob(blob.data(), LS, parent, L, pw.data());
+  fill_blob(blob.data(), LS, parent, L, pw.data(), 1);
   const U4* F = reinterpret_cast<const U4*>(blob.data() + (size_t)LS * 2);
   const U4* G = F + (LS + 1);
-  const U4 a = child_fingerprint(F, G, pw.data(), L, kind, p, q, 1);
+  const U4 a = child_fingerprint(F, G, pw.data(), L, kind, p, q);
   std::vector<int16_t> ch(2 * L + 2);
   const int Lc = h_child(parent, L, kind, p, q, ch.data());
   const U4 b = seq_fingerprint(ch.data(), Lc, pw.data(), 1);

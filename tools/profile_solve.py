@@ -24,5 +24,6 @@ for r in range(reps):
     for l in range(nl):
         print("   level %d: frontier %d generated %d scored %d cells %d  %.3f ms" %
               (l + 1, st.frontier[l], st.generated[l], st.scored[l], st.cells[l], st.level_ms[l]))
-    print("   best %.3f, %d trajectories" % (st.best, len(R.scores)))
+    print("   best %.3f, %d trajectories; host ms: setup %.2f search %.2f report %.2f dump %.2f" %
+          (st.best, len(R.scores), st.host_ms[0], st.host_ms[1], st.host_ms[2], st.host_ms[3]))
 s.close()
