@@ -753,17 +753,37 @@ struct Search {
 
   static float score_f32(int k3) { return k3 < 0 ? -INFINITY : (float)k3_to_score(k3); }
 
-  void extract(int k3_min) {
+  void extract(int k3_min, int k3_star, int64_t quota) {
     cudaStream_t s = c->stream;
     uint8_t* needed = (uint8_t*)c->flag.ensure((size_t)n_ids + 16, true);
     CK(cudaMemsetAsync(needed, 0, (size_t)n_ids + 16, s));
     const int nl = (int)lv.size();
-    for (int l = 1; l < nl; ++l)
-      c->launches += launch_good_flags(lv[l].k3.as<int32_t>(), lv[l].n_new, lv[l].id_base, k3_min, needed, s);
-    for (int pass = 0; pass <= o.maxdepth + 1; ++pass)
+    int32_t* misc0 = (int32_t*)c->misc.p;
+    for (int l = 1; l < nl; ++l) {
+      const Level& L = lv[l];
+      if (!L.n_new) continue;
+      uint32_t* tie_rank = nullptr;
+      uint32_t q = 0xffffffffu;
+      if (k3_star >= 0) {  // rank of every id tied at k3_star, in id order (levels ascend with id)
+        uint32_t* tflag = (uint32_t*)c->is_new.ensure((size_t)L.n_new * 4, true);
+        tie_rank = (uint32_t*)c->newrank.ensure((size_t)L.n_new * 4, true);
+        uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.n_new) * 4, true);
+        c->launches += launch_tie_flags(L.k3.as<int32_t>(), L.n_new, k3_star, tflag, s);
+        c->launches += launch_scan(tflag, tie_rank, L.n_new, bsum, (uint32_t*)(misc0 + 10), s);
+        q = (uint32_t)std::min<int64_t>(std::max<int64_t>(quota, 0), 0xfffffff0ll);
+      }
+      c->launches += launch_good_flags(L.k3.as<int32_t>(), L.n_new, L.id_base, k3_min, k3_star, q, tie_rank, needed, s);
+      if (k3_star >= 0) {
+        d2h(c, pin_u32(), misc0, 64);
+        CK(cudaStreamSynchronize(s));
+        quota -= (int64_t)pin_u32()[10];
+      }
+    }
+    for (int pass = 1; pass <= o.maxdepth + 1; ++pass)  // pass = 1 + distance of the children looked at
       for (int l = nl - 1; l >= 1; --l)
-        c->launches += launch_mark_parents(lv[l].cand_id.as<int32_t>(), lv[l].desc.as<uint64_t>(),
-                                           lv[l].fid.as<int32_t>(), lv[l].G, needed, s);
+        if (l + pass <= o.maxdepth + 2)
+          c->launches += launch_mark_parents(lv[l].cand_id.as<int32_t>(), lv[l].desc.as<uint64_t>(),
+                                             lv[l].fid.as<int32_t>(), lv[l].G, needed, pass, l, o.maxdepth, s);
     int32_t* misc = (int32_t*)c->misc.p;
     nodes.clear();
     nodes[1] = Node{root_k3, root_cost, root_total, {}};
@@ -774,7 +794,7 @@ struct Search {
       uint32_t* eflag = (uint32_t*)c->is_new.ensure((size_t)L.G * 4, true);
       uint32_t* epre = (uint32_t*)c->newrank.ensure((size_t)L.G * 4, true);
       uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.G) * 4, true);
-      c->launches += launch_edge_flags(L.cand_id.as<int32_t>(), L.G, needed, eflag, s);
+      c->launches += launch_edge_flags(L.cand_id.as<int32_t>(), L.G, needed, eflag, l, o.maxdepth, s);
       c->launches += launch_scan(eflag, epre, L.G, bsum, (uint32_t*)(misc + 8), s);
       d2h(c, pin_u32(), misc, 64);
       CK(cudaStreamSynchronize(s));
@@ -855,9 +875,9 @@ struct Search {
       }
       k3_min = lo;
     }
+    int k3_star = -1;
+    int64_t quota = 0;
     if (o.maxreport >= 0 && n_ids > o.maxreport) {
-      // every id has at least one trajectory (its discovery chain), so ids below the k3 of the maxreport-th best id
-      // cannot appear among the first maxreport trajectories of the sorted report: raise the threshold to it.
       cudaStream_t s = c->stream;
       uint32_t* hist = (uint32_t*)c->keys.ensure((size_t)100002 * 4, true);
       CK(cudaMemsetAsync(hist, 0, (size_t)100002 * 4, s));
@@ -867,17 +887,17 @@ struct Search {
       CK(cudaStreamSynchronize(s));
       if (root_k3 >= 0) hh[root_k3] += 1;
       int64_t cum = 0;
-      int k3_star = 0;
       for (int k = 100000; k >= 0; --k) {
-        cum += hh[k];
-        if (cum >= o.maxreport) {
+        if (cum + hh[k] >= o.maxreport) {
           k3_star = k;
+          quota = o.maxreport - cum;  // ids to take from the tie bin, in id order
           break;
         }
+        cum += hh[k];
       }
-      k3_min = std::max(k3_min, k3_star);
+      if (k3_star >= 0 && root_k3 == k3_star) quota -= 1;  // the root (id 1) is the first of its tie bin
     }
-    extract(k3_min);
+    extract(k3_min, k3_star, quota);
     struct Traj {
       int32_t id, k3;
       std::vector<EdgeRec> mv;

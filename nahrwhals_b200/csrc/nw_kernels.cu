@@ -661,13 +661,22 @@ int launch_materialise(const MaterialiseArgs& A, cudaStream_t st) {
 // report extraction: which ids are good (solver.jl:733), which ancestors/edges are needed (:688-705)
 // =====================================================================================================
 // k3_min is the integer image of solver.jl:733 `score >= suboptimality * best` (the Float32 score is monotone in
-// k3; the host finds the smallest passing k3 with the reference's own Float32/Float64 comparison), possibly raised
-// to the k3 of the maxreport-th best id (ids below it can never make the first maxreport trajectories).
-__global__ void k_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, int k3_min, uint8_t* needed) {
+// k3; the host finds the smallest passing k3 with the reference's own Float32/Float64 comparison).
+// With a report limit R only the first R ids in (score desc, id asc) order can own one of the first R trajectories
+// (every id has a trajectory as short as its discovery level and ids ascend with level), so ids below the k3 of
+// the R-th best id (k3_star) are skipped, and of the ids tied at k3_star only the first `quota` in id order kept.
+__global__ void k_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, int k3_min, int k3_star, uint32_t quota,
+                             const uint32_t* tie_rank, uint8_t* needed) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const int v = k3[r];
-  if (v >= 0 && v >= k3_min) needed[id_base + r] = 1;
+  if (v < 0 || v < k3_min || v < k3_star) return;
+  if (v == k3_star && tie_rank[r] >= quota) return;
+  needed[id_base + r] = 1;
+}
+__global__ void k_tie_flags(const int32_t* k3, uint32_t n, int k3_star, uint32_t* flag) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) flag[r] = k3[r] == k3_star ? 1u : 0u;
 }
 // histogram of k3 over the fresh ids of a level (warp-aggregated atomics; k3 == 0 is a very hot bin)
 __global__ void k_k3_hist(const int32_t* k3, uint32_t n, uint32_t* hist) {
@@ -677,18 +686,26 @@ __global__ void k_k3_hist(const int32_t* k3, uint32_t n, uint32_t* hist) {
   const uint32_t peers = __match_any_sync(0xffffffffu, key);
   if (key >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
 }
+// needed[id] = 1 + (fewest moves from id to a reported id), 0 = not needed.  A node `dist` moves before a reported
+// id can only sit on a trajectory if level(node) + dist <= maxdepth + 1 (concatenate_moves_aux cuts longer paths,
+// solver.jl:688-693), which bounds the ancestor closure.  Candidates generated at BFS level `lvl` have parents of
+// level lvl-1, so an edge into a child with needed == v is useful iff lvl + v <= maxdepth + 2.
 __global__ void k_mark_parents(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
-                               uint8_t* needed) {
+                               uint8_t* needed, int pass, int lvl, int maxdepth) {
   const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= G) return;
-  if (needed[cand_id[pos]]) {
+  const int v = needed[cand_id[pos]];
+  if (v == pass && lvl + v <= maxdepth + 2) {
     const int32_t pid = front_id[desc_parent(desc[pos])];
-    if (!needed[pid]) needed[pid] = 1;
+    if (!needed[pid]) needed[pid] = (uint8_t)(pass + 1);
   }
 }
-__global__ void k_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* needed, uint32_t* flag) {
+__global__ void k_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* needed, uint32_t* flag, int lvl,
+                             int maxdepth) {
   const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos < G) flag[pos] = needed[cand_id[pos]] ? 1u : 0u;
+  if (pos >= G) return;
+  const int v = needed[cand_id[pos]];
+  flag[pos] = (v && lvl + v <= maxdepth + 2) ? 1u : 0u;
 }
 __global__ void k_edge_compact(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
                                const uint32_t* flag, const uint32_t* pre, EdgeRec* out) {
@@ -718,9 +735,15 @@ __global__ void k_id_compact(const int32_t* k3, const int32_t* cost, const int32
   out[pre[r]] = o;
 }
 
-int launch_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, int k3_min, uint8_t* needed, cudaStream_t st) {
+int launch_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, int k3_min, int k3_star, uint32_t quota,
+                      const uint32_t* tie_rank, uint8_t* needed, cudaStream_t st) {
   if (!n) return 0;
-  k_good_flags<<<(n + 255) / 256, 256, 0, st>>>(k3, n, id_base, k3_min, needed);
+  k_good_flags<<<(n + 255) / 256, 256, 0, st>>>(k3, n, id_base, k3_min, k3_star, quota, tie_rank, needed);
+  return 1;
+}
+int launch_tie_flags(const int32_t* k3, uint32_t n, int k3_star, uint32_t* flag, cudaStream_t st) {
+  if (!n) return 0;
+  k_tie_flags<<<(n + 255) / 256, 256, 0, st>>>(k3, n, k3_star, flag);
   return 1;
 }
 int launch_k3_hist(const int32_t* k3, uint32_t n, uint32_t* hist, cudaStream_t st) {
@@ -729,14 +752,15 @@ int launch_k3_hist(const int32_t* k3, uint32_t n, uint32_t* hist, cudaStream_t s
   return 1;
 }
 int launch_mark_parents(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
-                        uint8_t* needed, cudaStream_t st) {
+                        uint8_t* needed, int pass, int lvl, int maxdepth, cudaStream_t st) {
   if (!G) return 0;
-  k_mark_parents<<<(G + 255) / 256, 256, 0, st>>>(cand_id, desc, front_id, G, needed);
+  k_mark_parents<<<(G + 255) / 256, 256, 0, st>>>(cand_id, desc, front_id, G, needed, pass, lvl, maxdepth);
   return 1;
 }
-int launch_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* needed, uint32_t* flag, cudaStream_t st) {
+int launch_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* needed, uint32_t* flag, int lvl, int maxdepth,
+                      cudaStream_t st) {
   if (!G) return 0;
-  k_edge_flags<<<(G + 255) / 256, 256, 0, st>>>(cand_id, G, needed, flag);
+  k_edge_flags<<<(G + 255) / 256, 256, 0, st>>>(cand_id, G, needed, flag, lvl, maxdepth);
   return 1;
 }
 int launch_edge_compact(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,

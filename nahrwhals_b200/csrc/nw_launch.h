@@ -29,11 +29,14 @@ int launch_make_keys(const int32_t* k3, const uint32_t* flag, const uint32_t* pr
 int launch_sort_u64(uint64_t* keys, uint64_t npad, cudaStream_t st);
 int launch_keys_to_sel(const uint64_t* keys, uint32_t n, uint32_t* sel, cudaStream_t st);
 int launch_materialise(const MaterialiseArgs& A, cudaStream_t st);
-int launch_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, int k3_min, uint8_t* needed, cudaStream_t st);
+int launch_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, int k3_min, int k3_star, uint32_t quota,
+                      const uint32_t* tie_rank, uint8_t* needed, cudaStream_t st);
+int launch_tie_flags(const int32_t* k3, uint32_t n, int k3_star, uint32_t* flag, cudaStream_t st);
 int launch_k3_hist(const int32_t* k3, uint32_t n, uint32_t* hist, cudaStream_t st);
 int launch_mark_parents(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
-                        uint8_t* needed, cudaStream_t st);
-int launch_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* needed, uint32_t* flag, cudaStream_t st);
+                        uint8_t* needed, int pass, int lvl, int maxdepth, cudaStream_t st);
+int launch_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* needed, uint32_t* flag, int lvl, int maxdepth,
+                      cudaStream_t st);
 int launch_edge_compact(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
                         const uint32_t* flag, const uint32_t* pre, void* out, cudaStream_t st);
 int launch_id_flags(const uint8_t* needed, int32_t id_base, uint32_t n, uint32_t* flag, cudaStream_t st);
