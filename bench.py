@@ -64,8 +64,9 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms",
-                                       "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.p = subprocess.Popen(["nvidia-smi", "-i", self.idx, "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -179,7 +180,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    aln, lx, ly, flags, desc = make_workload(args.workload, 1 + rank)
+    # every rank solves its own copy of the same region (identical work per GPU: weak scaling of independent regions)
+    aln, lx, ly, flags, desc = make_workload(args.workload, 1)
     solver = nb.Solver(local)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
@@ -229,6 +231,8 @@ def main():
         d2h += R.stats.d2h_bytes
     clocks = sampler.stop()
 
+    print("[bench rank %d] device ms/step %.3f, e2e ms/step %.3f, scored/step %d" %
+          (rank, dev_ms / args.steps, 1e3 * e2e_t / args.steps, scored // args.steps), file=sys.stderr, flush=True)
     # ---- reduce over ranks: max time, summed work ----
     if dist is not None:
         t = torch.tensor([dev_ms, e2e_t, score_ms], dtype=torch.float64, device="cuda")
@@ -273,7 +277,7 @@ def main():
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=W,
                 ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32",
                 data="synthetic",
-                config=dict(workload=desc + ("; one region per GPU, seeds 1..%d" % world if world > 1 else ""),
+                config=dict(workload=desc + ("; one such region per GPU (%d independent regions, no collective on the data path)" % world if world > 1 else ""),
                             scored_per_step=scored_all / args.steps, l2="flushed between timed steps (256 MiB write)",
                             dp_share_of_step=(score_ms / (dev_ms if dist is None else max(dev_ms, 1e-9)))),
                 clocks=clocks,

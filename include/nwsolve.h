@@ -91,6 +91,11 @@ int64_t nw_result_count(const nw_result* r);
 int nw_result_get(const nw_result* r, int64_t k, float* score, int32_t* n_moves, const int32_t** moves3);
 /* DP terminal cost / total in bp of the index trajectory k leads to (cost < 0: early exit, no DP ran) */
 int nw_result_cost(const nw_result* r, int64_t k, int64_t* cost_bp, int64_t* total_bp, int64_t* index_id);
+/* Bulk form of nw_result_get / nw_result_cost: arrays of nw_result_count() entries (any pointer may be NULL);
+ * moves3 holds nw_result_move_count() (kind,start,stop) triples, move_off[k] is the first triple of trajectory k. */
+int nw_result_arrays(const nw_result* r, float* score, int32_t* n_moves, int64_t* move_off, int64_t* cost_bp,
+                     int64_t* total_bp, int64_t* index_id, int32_t* moves3);
+int64_t nw_result_move_count(const nw_result* r);
 /* The exact bytes write_trajectories (solver.jl:747-753) would write. */
 int nw_result_tsv(const nw_result* r, const char** data, int64_t* len);
 int nw_result_stats(const nw_result* r, nw_stats* out);

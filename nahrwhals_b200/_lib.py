@@ -25,7 +25,8 @@ FLAG_NO_TRAJ = 2
 
 # every symbol include/nwsolve.h declares (tests check that the library exports exactly these)
 SYMBOLS = ["nw_default_opts", "nw_last_error", "nw_version", "nw_ctx_create", "nw_ctx_destroy", "nw_solve",
-           "nw_solve_files", "nw_result_count", "nw_result_get", "nw_result_cost", "nw_result_tsv", "nw_result_stats",
+           "nw_solve_files", "nw_result_count", "nw_result_get", "nw_result_cost", "nw_result_arrays", "nw_result_move_count",
+           "nw_result_tsv", "nw_result_stats",
            "nw_result_ids", "nw_result_edge_count", "nw_result_edges", "nw_result_free", "nw_score_batch",
            "nw_moveset", "nw_bench_peaks", "nw_read_problem", "nw_free"]
 
@@ -52,6 +53,9 @@ def load():
     L.nw_result_count.argtypes = [vp]
     L.nw_result_get.argtypes = [vp, i64, C.POINTER(C.c_float), C.POINTER(i32), C.POINTER(C.POINTER(i32))]
     L.nw_result_cost.argtypes = [vp, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    L.nw_result_arrays.argtypes = [vp] * 8
+    L.nw_result_move_count.restype = i64
+    L.nw_result_move_count.argtypes = [vp]
     L.nw_result_tsv.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
     L.nw_result_stats.argtypes = [vp, C.POINTER(NwStats)]
     L.nw_result_ids.argtypes = [vp, vp, vp, vp, vp]

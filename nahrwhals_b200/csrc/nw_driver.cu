@@ -837,30 +837,86 @@ struct Search {
     CK(cudaGetLastError());
   }
 
-  // solver.jl:688-705
-  bool concat(int32_t cur, int depth, std::vector<std::vector<EdgeRec>>& result) {
-    result.clear();
-    if (cur == 1) {
-      result.emplace_back();
-      return true;
-    } else if (depth > o.maxdepth) {
-      result.emplace_back();
-      return false;
+  // ---- trajectory enumeration: concatenate_moves_aux + sort + truncate (solver.jl:688-705, :739-743) ----
+  // The reference enumerates every backward path from a reported id to the root (first visit of the root ends the
+  // path; at most maxdepth+1 moves), in edge order, then stable-sorts by (-score, n_moves) and keeps max_report.
+  // We produce exactly that sequence directly: groups by score desc, then n_moves asc, then id asc, then the
+  // reference's own enumeration order restricted to paths of that length -- and stop at max_report.
+  struct Enumerator {
+    Search& S;
+    std::unordered_map<int64_t, char> memo;  // (id, r) -> can the root be reached from id in exactly r moves
+    std::vector<EdgeRec> stack;              // edges from the target backwards
+    int64_t limit = -1, emitted = 0;
+    nw_result* R = nullptr;
+    int cur_id = 0, cur_k3 = 0;
+    explicit Enumerator(Search& s) : S(s) {}
+    bool reach(int32_t id, int r) {
+      if (id == 1) return r == 0;
+      if (r <= 0) return false;
+      const int64_t key = ((int64_t)id << 8) | r;
+      auto it = memo.find(key);
+      if (it != memo.end()) return it->second;
+      bool ok = false;
+      auto nd = S.nodes.find(id);
+      if (nd != S.nodes.end())
+        for (const EdgeRec& e : nd->second.in)
+          if (reach(e.parent, r - 1)) {
+            ok = true;
+            break;
+          }
+      memo.emplace(key, ok);
+      return ok;
     }
-    auto it = nodes.find(cur);
-    if (it == nodes.end()) return true;
-    std::vector<std::vector<EdgeRec>> sub;
-    for (const EdgeRec& e : it->second.in) {
-      const bool valid = concat(e.parent, depth + 1, sub);
-      if (valid)
-        for (auto& t : sub) {
-          std::vector<EdgeRec> nt(t);
-          nt.push_back(e);
-          result.push_back(std::move(nt));
-        }
+    bool full() const { return limit >= 0 && emitted >= limit; }
+    void emit() {
+      static const char* names[3] = {"move_dup", "move_del", "move_inv"};
+      const Node& nd = S.nodes[cur_id];
+      R->t_score.push_back(score_f32(cur_k3));
+      R->t_k3.push_back(cur_k3);
+      R->t_id.push_back(cur_id);
+      R->t_cost.push_back(nd.cost < 0 ? nd.cost : (int64_t)nd.cost * S.c->RH.gcd);
+      R->t_total.push_back((int64_t)nd.total * S.c->RH.gcd);
+      std::string& line = R->tsv;
+      line += score_string(cur_k3);
+      line += '\t';
+      line += std::to_string(stack.size());
+      line += '\t';  // :723
+      bool first = true;
+      for (size_t k = stack.size(); k-- > 0;) {  // stack holds the last move first; trajectories list moves root-first
+        const EdgeRec& e = stack[k];
+        const int kind = e.kind_i & 3, i = e.kind_i >> 2, j = e.j;
+        R->t_moves.push_back(kind);
+        R->t_moves.push_back(i);
+        R->t_moves.push_back(j);
+        if (!first) line += '\t';
+        first = false;
+        line += names[kind];
+        line += '\t';
+        line += std::to_string(i);
+        line += '\t';
+        line += std::to_string(j);  // :719
+      }
+      line += '\n';
+      R->t_off.push_back((int64_t)R->t_moves.size());
+      ++emitted;
     }
-    return true;
-  }
+    // all paths of exactly r more moves from `id` back to the root, in the reference's enumeration order
+    void walk(int32_t id, int r) {
+      if (id == 1) {
+        if (r == 0) emit();
+        return;
+      }
+      auto nd = S.nodes.find(id);
+      if (nd == S.nodes.end()) return;
+      for (const EdgeRec& e : nd->second.in) {
+        if (full()) return;
+        if (!reach(e.parent, r - 1)) continue;
+        stack.push_back(e);
+        walk(e.parent, r - 1);
+        stack.pop_back();
+      }
+    }
+  };
 
   void report(nw_result* R) {
     const double best = k3_to_score(best_k3);
@@ -898,49 +954,27 @@ struct Search {
       if (k3_star >= 0 && root_k3 == k3_star) quota -= 1;  // the root (id 1) is the first of its tie bin
     }
     extract(k3_min, k3_star, quota);
-    struct Traj {
-      int32_t id, k3;
-      std::vector<EdgeRec> mv;
-    };
-    std::vector<Traj> tr;
-    std::vector<int32_t> good;
+    std::vector<std::pair<int32_t, int32_t>> good;  // (-k3, id): canonical Dict order = ascending discovery id
     for (auto& kv : nodes) {
       const int k3 = kv.second.k3;
-      if (k3 >= 0 && k3 >= k3_min) good.push_back(kv.first);
+      if (k3 >= 0 && k3 >= k3_min) good.emplace_back(-k3, kv.first);
     }
-    std::sort(good.begin(), good.end());  // canonical Dict order: ascending discovery id
-    std::vector<std::vector<EdgeRec>> res;
-    for (int32_t id : good) {
-      concat(id, 0, res);
-      for (auto& t : res) tr.push_back(Traj{id, nodes[id].k3, t});
-    }
-    std::stable_sort(tr.begin(), tr.end(), [](const Traj& a, const Traj& b) {  // :739
-      if (a.k3 != b.k3) return a.k3 > b.k3;
-      return a.mv.size() < b.mv.size();
-    });
-    if (o.maxreport >= 0 && (int64_t)tr.size() > o.maxreport) tr.resize((size_t)o.maxreport);  // :740-743
-    static const char* names[3] = {"move_dup", "move_del", "move_inv"};
+    std::sort(good.begin(), good.end());
+    Enumerator E(*this);
+    E.limit = o.maxreport;
+    E.R = R;
     R->t_off.push_back(0);
-    for (const Traj& t : tr) {
-      const Node& nd = nodes[t.id];
-      R->t_score.push_back(score_f32(t.k3));
-      R->t_k3.push_back(t.k3);
-      R->t_id.push_back(t.id);
-      R->t_cost.push_back(nd.cost < 0 ? nd.cost : (int64_t)nd.cost * c->RH.gcd);
-      R->t_total.push_back((int64_t)nd.total * c->RH.gcd);
-      std::string line = score_string(t.k3) + "\t" + std::to_string(t.mv.size()) + "\t";  // :723
-      bool first = true;
-      for (const EdgeRec& e : t.mv) {
-        const int kind = e.kind_i & 3, i = e.kind_i >> 2, j = e.j;
-        R->t_moves.push_back(kind);
-        R->t_moves.push_back(i);
-        R->t_moves.push_back(j);
-        if (!first) line += "\t";
-        first = false;
-        line += std::string(names[kind]) + "\t" + std::to_string(i) + "\t" + std::to_string(j);  // :719
-      }
-      R->t_off.push_back((int64_t)R->t_moves.size());
-      R->tsv += line + "\n";
+    size_t g0 = 0;
+    while (g0 < good.size() && !E.full()) {
+      size_t g1 = g0;
+      while (g1 < good.size() && good[g1].first == good[g0].first) ++g1;
+      for (int m = 0; m <= o.maxdepth + 1 && !E.full(); ++m)
+        for (size_t g = g0; g < g1 && !E.full(); ++g) {
+          E.cur_id = good[g].second;
+          E.cur_k3 = -good[g].first;
+          if (E.reach(E.cur_id, m)) E.walk(E.cur_id, m);
+        }
+      g0 = g1;
     }
   }
 
@@ -1193,6 +1227,22 @@ int nw_result_cost(const nw_result* r, int64_t k, int64_t* cost_bp, int64_t* tot
   if (index_id) *index_id = r->t_id[k];
   return NW_OK;
 }
+int nw_result_arrays(const nw_result* r, float* score, int32_t* n_moves, int64_t* move_off, int64_t* cost_bp,
+                     int64_t* total_bp, int64_t* index_id, int32_t* moves3) {
+  if (!r) return NW_ERR_ARG;
+  const size_t n = r->t_score.size();
+  for (size_t k = 0; k < n; ++k) {
+    if (score) score[k] = r->t_score[k];
+    if (n_moves) n_moves[k] = (int32_t)((r->t_off[k + 1] - r->t_off[k]) / 3);
+    if (move_off) move_off[k] = r->t_off[k] / 3;
+    if (cost_bp) cost_bp[k] = r->t_cost[k];
+    if (total_bp) total_bp[k] = r->t_total[k];
+    if (index_id) index_id[k] = r->t_id[k];
+  }
+  if (moves3 && !r->t_moves.empty()) memcpy(moves3, r->t_moves.data(), r->t_moves.size() * 4);
+  return NW_OK;
+}
+int64_t nw_result_move_count(const nw_result* r) { return r ? (int64_t)(r->t_moves.size() / 3) : 0; }
 int nw_result_tsv(const nw_result* r, const char** data, int64_t* len) {
   if (!r || !data || !len) return NW_ERR_ARG;
   *data = r->tsv.data();

@@ -26,13 +26,22 @@ class SolveResult:
     def __init__(self):
         self.tsv = ""
         self.scores = np.zeros(0, np.float32)
-        self.moves = []          # list of [(kind, start, stop), ...]
+        self.n_moves = np.zeros(0, np.int32)
+        self.move_off = np.zeros(0, np.int64)
+        self.moves3 = np.zeros((0, 3), np.int32)   # (kind, start, stop) rows, trajectory k owns
+        #                                            moves3[move_off[k] : move_off[k] + n_moves[k]]
         self.cost_bp = np.zeros(0, np.int64)
         self.total_bp = np.zeros(0, np.int64)
         self.index_id = np.zeros(0, np.int64)
         self.stats = None
         self.ids = None          # keep_ids: dict(score, cost_bp, total_bp, level)
         self.edges = None        # keep_ids: dict(child, parent, moves)
+
+    @property
+    def moves(self):
+        """list of [(kind, start, stop), ...] per trajectory (solver.jl:44-48)"""
+        return [[tuple(int(v) for v in row) for row in self.moves3[o:o + n]]
+                for o, n in zip(self.move_off, self.n_moves)]
 
     @property
     def generated(self):
@@ -111,18 +120,16 @@ class Solver:
         L.nw_result_tsv(r, C.byref(data), C.byref(ln))
         R.tsv = C.string_at(data, ln.value).decode() if ln.value else ""
         n = L.nw_result_count(r)
+        nm = L.nw_result_move_count(r)
         R.scores = np.zeros(n, np.float32)
         R.cost_bp = np.zeros(n, np.int64)
         R.total_bp = np.zeros(n, np.int64)
         R.index_id = np.zeros(n, np.int64)
-        sc, nm, mv = C.c_float(), C.c_int32(), C.POINTER(C.c_int32)()
-        c1, c2, c3 = C.c_int64(), C.c_int64(), C.c_int64()
-        for k in range(n):
-            L.nw_result_get(r, k, C.byref(sc), C.byref(nm), C.byref(mv))
-            L.nw_result_cost(r, k, C.byref(c1), C.byref(c2), C.byref(c3))
-            R.scores[k] = sc.value
-            R.moves.append([(mv[3 * t], mv[3 * t + 1], mv[3 * t + 2]) for t in range(nm.value)])
-            R.cost_bp[k], R.total_bp[k], R.index_id[k] = c1.value, c2.value, c3.value
+        R.n_moves = np.zeros(n, np.int32)
+        R.move_off = np.zeros(n, np.int64)
+        R.moves3 = np.zeros((nm, 3), np.int32)
+        L.nw_result_arrays(r, _p(R.scores), _p(R.n_moves), _p(R.move_off), _p(R.cost_bp), _p(R.total_bp),
+                           _p(R.index_id), _p(R.moves3))
         if o.keep_ids:
             nid = int(st.n_ids)
             ids = dict(score=np.zeros(nid, np.float32), cost_bp=np.zeros(nid, np.int64),
