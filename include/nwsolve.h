@@ -117,6 +117,39 @@ int nw_score_batch(nw_ctx* ctx, const int8_t* aln_sign, int32_t n_x, int32_t n_y
 /* Replaces to_moveset (solver.jl:217-231): two n_x*n_x uint8 matrices (duplicate_delete, invert). */
 int nw_moveset(nw_ctx* ctx, const int8_t* aln_sign, int32_t n_x, int32_t n_y, uint8_t* dup_del, uint8_t* invert);
 
+/* ---- one deep search sharded over `world` ranks (config 3 of BASELINE.json) -------------------------
+ * One context per rank, the same problem and options on every rank.  The frontier is replicated; rank r expands the
+ * parents whose frontier slot is congruent to r modulo world, dedups and scores its own candidates, and contributes
+ * one NW_DIST_RECORD_BYTES record per locally-first candidate to a per-level all-gather that the CALLER performs
+ * (torch.distributed / NCCL in nahrwhals_b200/distributed.py; any transport works).  Every rank then runs the same
+ * deterministic merge (min global discovery position per fingerprint = the serial first-discoverer rule of
+ * solver.jl:535; ids in global discovery order; stable top-width), so results are bit-identical to nw_solve.
+ *
+ *   nw_dist_begin
+ *   do { nw_dist_expand(&n);  all-gather n -> counts[];  nw_dist_pack(send);  all-gather send -> all (padded to
+ *        stride = max(counts) records per rank);  nw_dist_merge(all, counts, stride, &more); } while (more);
+ *   nw_dist_report_begin(needed, n_ids+16)          -- needed: caller-owned device bytes, identical on all ranks
+ *   for pass = 1 .. maxdepth+1: nw_dist_report_mark(needed, pass);  all-reduce MAX over needed
+ *   nw_dist_report_edges(needed, &ne); all-gather ne; nw_dist_report_pack(send); all-gather (NW_DIST_EDGE_BYTES each)
+ *   nw_dist_finish(needed, all_edges, counts, stride, &result)      -- every rank builds the same result
+ * All pointers named dev_* / needed are DEVICE pointers on the context's GPU; every call returns with the
+ * context's stream idle, so the caller only has to order its own collectives. */
+#define NW_DIST_RECORD_BYTES 40
+#define NW_DIST_EDGE_BYTES 16
+int nw_dist_begin(nw_ctx* ctx, const int8_t* aln_sign, int32_t n_x, int32_t n_y, const int64_t* len_x,
+                  const int64_t* len_y, const nw_opts* opts, int32_t rank, int32_t world);
+int nw_dist_expand(nw_ctx* ctx, int64_t* n_records);
+int nw_dist_pack(nw_ctx* ctx, void* dev_out);
+int nw_dist_merge(nw_ctx* ctx, const void* dev_all, const int64_t* counts, int64_t stride_records, int32_t* more);
+int64_t nw_dist_n_ids(nw_ctx* ctx);
+int nw_dist_report_begin(nw_ctx* ctx, void* needed_dev, int64_t nbytes);
+int nw_dist_report_mark(nw_ctx* ctx, void* needed_dev, int32_t pass);
+int nw_dist_report_edges(nw_ctx* ctx, const void* needed_dev, int64_t* n_edges);
+int nw_dist_report_pack(nw_ctx* ctx, void* dev_out);
+int nw_dist_finish(nw_ctx* ctx, const void* needed_dev, const void* dev_edges_all, const int64_t* counts,
+                   int64_t stride_edges, nw_result** out);
+void nw_dist_abort(nw_ctx* ctx);
+
 /* Roofline denominators measured on this device with dependency-free micro-kernels:
  * out[0] VIADDMNMX, out[1] IADD3, out[2] VIADDMNMX+IMAD interleaved -- thread-instructions per second;
  * out[3] device-to-device copy bandwidth in bytes/s (read + write). */

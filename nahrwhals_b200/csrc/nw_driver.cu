@@ -196,7 +196,8 @@ struct nw_ctx {
   uint64_t table_cap = 0;
   // per-level scratch
   DevBuf cnt, off, bsum, slot, is_new, newrank, new_len, hist, bstart, cursor, work, scratch, flag, pre, sel, keys,
-      misc;
+      misc, rslot, newflag, grank, edgebuf;
+  void* dist = nullptr;  // active frontier-sharded search (Search*, nw_dist_*)
   void* pinned = nullptr;  // small pinned staging area for D2H scalars / histograms
   DevPool pool;
   int launches = 0;
@@ -247,6 +248,10 @@ struct Level {
   uint32_t G = 0, gbase = 0, n_new = 0;
   int32_t id_base = 0;
   DevBuf desc, cand_id, newlist, k3, cost, total;
+  // frontier-sharded search only: G counts this rank's candidates, G_all all ranks'; k3/cost/total are the merged
+  // (replicated) per-id arrays, l_* the rank-local ones of the candidates this rank scored
+  uint32_t G_all = 0, n_local_new = 0;
+  DevBuf off_loc, off_glob, desc_new, gid_at, l_k3, l_cost, l_total;
   FrontierDev frontier() const {
     FrontierDev F;
     F.P = P;
@@ -451,6 +456,13 @@ struct Search {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> lev;
 
+  int rank = 0, world = 1;      // frontier sharding (nw_dist_*); world == 1 is the plain single-GPU search
+  ExpandArgs curE{};            // expansion arguments of the level in flight (sharded search)
+  int cur_level = 0;
+  bool dist_more = false;
+  int dist_k3_min = 0;
+  int dist_maxlen = 0;
+  uint32_t dist_edges = 0;
   explicit Search(nw_ctx* ctx, const nw_opts& opts) : c(ctx), o(opts) {}
   ~Search() {
     if (ev0) cudaEventDestroy(ev0);
@@ -576,10 +588,13 @@ struct Search {
     E.tmask = c->table_cap - 1;
     E.gbase = L.gbase;
     E.pw = c->d_pow.as<U4>();
+    E.own_mod = 1;
+    E.own_rem = 0;
+    E.off_glob = nullptr;
     c->launches += launch_expand(true, E, s);
     c->launches += launch_hash_insert(E, G, s);
     uint32_t* is_new = (uint32_t*)c->is_new.ensure((size_t)G * 4, true);
-    c->launches += launch_resolve(E.slot, E.table, L.gbase, G, is_new, s);
+    c->launches += launch_resolve(E, G, is_new, s);
     uint32_t* newrank = (uint32_t*)c->newrank.ensure((size_t)G * 4, true);
     bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(G) * 4, true);
     c->launches += launch_scan(is_new, newrank, G, bsum, (uint32_t*)(misc + 5), s);
@@ -676,8 +691,8 @@ struct Search {
     MaterialiseArgs M{};
     M.F = Lr.frontier();
     M.sel = sel;
-    M.newlist = Lr.newlist.as<uint32_t>();
-    M.desc = Lr.desc.as<uint64_t>();
+    M.newlist = world > 1 ? nullptr : Lr.newlist.as<uint32_t>();  // sharded: descriptors of the merged new ids
+    M.desc = world > 1 ? Lr.desc_new.as<uint64_t>() : Lr.desc.as<uint64_t>();
     M.id_base = Lr.id_base;
     M.maxdup = o.maxdup;
     M.n_x = c->RD.n_x;
@@ -744,6 +759,235 @@ struct Search {
     st.kernel_launches = c->launches;
   }
 
+  // =================================================================================================
+  // frontier-sharded search: the level loop of run() cut at the point where ranks exchange records
+  // =================================================================================================
+  void dist_begin() {
+    cudaStream_t s = c->stream;
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    CK(cudaEventRecord(ev0, s));
+    init_root();
+    int32_t* misc = (int32_t*)c->misc.p;
+    CK(cudaMemsetAsync(misc, 0, 4, s));
+    cur_level = 1;
+    dist_more = o.maxdepth >= 1;
+    st.n_levels = 0;
+  }
+
+  // expand this rank's share of level cur_level; returns the number of records it contributes to the exchange
+  int64_t dist_expand() {
+    cudaStream_t s = c->stream;
+    const int d = cur_level;
+    Level& L = lv[d];
+    int32_t* misc = (int32_t*)c->misc.p;
+    st.frontier[d - 1] = L.P;
+    st.n_levels = d;
+    L.G = L.G_all = L.n_local_new = L.n_new = 0;
+    L.gbase = gtotal;
+    L.id_base = n_ids + 1;
+    curE = ExpandArgs{};
+    if (L.P == 0) return 0;
+    ExpandArgs E{};
+    E.R = c->RD;
+    E.F = L.frontier();
+    E.cnt = (uint32_t*)c->cnt.ensure((size_t)L.P * 4, true);
+    E.maxlen = misc + 2;
+    E.own_mod = 1;
+    CK(cudaMemsetAsync(misc + 2, 0, 4, s));
+    c->launches += launch_expand(false, E, s);  // every rank counts every parent: global offsets need no collective
+    uint32_t* off_glob = (uint32_t*)L.off_glob.ensure((size_t)L.P * 4);
+    uint32_t* off_loc = (uint32_t*)L.off_loc.ensure((size_t)L.P * 4);
+    uint32_t* own_cnt = (uint32_t*)c->off.ensure((size_t)L.P * 4, true);
+    uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items((uint64_t)L.P) * 4, true);
+    c->launches += launch_scan(E.cnt, off_glob, (uint64_t)L.P, bsum, (uint32_t*)(misc + 4), s);
+    c->launches += launch_mask_counts(E.cnt, (uint32_t)L.P, world, rank, own_cnt, s);
+    c->launches += launch_scan(own_cnt, off_loc, (uint64_t)L.P, bsum, (uint32_t*)(misc + 7), s);
+    d2h(c, pin_u32(), misc, 32);
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    const uint32_t G_all = pin_u32()[4], G = pin_u32()[7];
+    const int maxlen = (int)pin_u32()[2];
+    dist_maxlen = maxlen;
+    if (maxlen > LMAX) fail(NW_ERR_RANGE, "a child index exceeds the supported length");
+    if ((uint64_t)gtotal + G_all >= 0xfffffff0ull || G_all >= 0x7ffffff0u) fail(NW_ERR_NOMEM, "more than 2^32 candidates");
+    L.G = G;
+    L.G_all = G_all;
+    st.generated[d - 1] = G_all;
+    if (G_all == 0) return 0;
+    table_reserve(c, (uint64_t)n_ids + G_all);  // room for every rank's records: no rehash during the merge
+    E.off = off_loc;
+    E.off_glob = off_glob;
+    E.own_mod = world;
+    E.own_rem = rank;
+    E.desc = (uint64_t*)L.desc.ensure((size_t)std::max<uint32_t>(G, 1) * 8);
+    E.slot = (uint32_t*)c->slot.ensure((size_t)std::max<uint32_t>(G, 1) * 4, true);
+    E.table = c->table.as<uint64_t>();
+    E.tmask = c->table_cap - 1;
+    E.gbase = L.gbase;
+    E.pw = c->d_pow.as<U4>();
+    curE = E;
+    if (G == 0) return 0;
+    c->launches += launch_expand(true, E, s);
+    c->launches += launch_hash_insert(E, G, s);
+    uint32_t* is_new = (uint32_t*)c->is_new.ensure((size_t)G * 4, true);
+    c->launches += launch_resolve(E, G, is_new, s);
+    uint32_t* newrank = (uint32_t*)c->newrank.ensure((size_t)G * 4, true);
+    bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(G) * 4, true);
+    c->launches += launch_scan(is_new, newrank, G, bsum, (uint32_t*)(misc + 5), s);
+    d2h(c, pin_u32(), misc, 32);
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    const uint32_t n_loc = pin_u32()[5];
+    L.n_local_new = n_loc;
+    AssignArgs A{};
+    A.LT.n_levels = 0;
+    A.slot = E.slot;
+    A.table = E.table;
+    A.is_new = is_new;
+    A.newrank = newrank;
+    A.desc = E.desc;
+    A.front_len = L.flen.as<int32_t>();
+    A.gbase = L.gbase;
+    A.G = G;
+    A.id_base = 0;
+    A.n_y = c->RD.n_y;
+    A.force = 0;
+    A.skip_ids = 1;
+    A.cand_id = nullptr;
+    A.newlist = (uint32_t*)L.newlist.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
+    A.new_len = (uint16_t*)c->new_len.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 2, true);
+    A.k3 = (int32_t*)L.l_k3.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
+    A.cost = (int32_t*)L.l_cost.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
+    A.total = (int32_t*)L.l_total.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
+    A.hist = (uint32_t*)c->hist.ensure((LMAX + 2) * 4);
+    CK(cudaMemsetAsync(A.hist, 0, (LMAX + 2) * 4, s));
+    c->launches += launch_assign(A, s);
+    uint32_t* hist_h = pin_u32() + 64;
+    d2h(c, hist_h, A.hist, (LMAX + 2) * 4);
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    int64_t cells = 0;
+    ScoreView V{L.frontier(), n_loc, L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(), L.l_k3.as<int32_t>(),
+                L.l_cost.as<int32_t>(), L.l_total.as<int32_t>()};
+    run_scoring(c, V, hist_h, 0, o.flags, misc + 1 /*best is taken from the merged records*/, &cells);
+    st.cells[d - 1] = cells;  // cells evaluated by THIS rank (includes candidates another rank discovered first)
+    CK(cudaStreamSynchronize(s));
+    return n_loc;
+  }
+
+  void dist_pack(void* out) {
+    Level& L = lv[cur_level];
+    if (!L.n_local_new) return;
+    c->launches += launch_dist_pack(curE, L.newlist.as<uint32_t>(), L.n_local_new, L.l_k3.as<int32_t>(),
+                                    L.l_cost.as<int32_t>(), L.l_total.as<int32_t>(), out, c->stream);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+  }
+
+  // all: world segments of `stride` records each, segment r holding counts[r] records.  Identical on every rank.
+  void dist_merge(const void* all, const int64_t* counts, int64_t stride) {
+    cudaStream_t s = c->stream;
+    const int d = cur_level;
+    const int D = std::min(o.maxdepth, MAX_LEVELS - 1);
+    int32_t* misc = (int32_t*)c->misc.p;
+    {
+      Level& L = lv[d];
+      const DistRec* rec = (const DistRec*)all;
+      uint32_t n_new = 0;
+      if (L.G_all) {
+        uint32_t* rslot = (uint32_t*)c->rslot.ensure((size_t)std::max<int64_t>(world * stride, 1) * 4, true);
+        for (int r = 0; r < world; ++r)
+          c->launches += launch_dist_merge_insert(rec + (size_t)r * stride, (uint32_t)counts[r], c->table.as<uint64_t>(),
+                                                  c->table_cap - 1, rslot + (size_t)r * stride, s);
+        uint32_t* newflag = (uint32_t*)c->newflag.ensure((size_t)L.G_all * 4, true);
+        uint32_t* grank = (uint32_t*)c->grank.ensure((size_t)L.G_all * 4, true);
+        CK(cudaMemsetAsync(newflag, 0, (size_t)L.G_all * 4, s));
+        for (int r = 0; r < world; ++r)
+          c->launches += launch_dist_merge_flag(rec + (size_t)r * stride, (uint32_t)counts[r], rslot + (size_t)r * stride,
+                                                c->table.as<uint64_t>(), L.gbase, newflag, s);
+        uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.G_all) * 4, true);
+        c->launches += launch_scan(newflag, grank, L.G_all, bsum, (uint32_t*)(misc + 5), s);
+        d2h(c, pin_u32(), misc, 32);
+        CK(cudaStreamSynchronize(s));
+        n_new = pin_u32()[5];
+        L.n_new = n_new;
+        const size_t nn = std::max<uint32_t>(n_new, 1);
+        L.k3.ensure(nn * 4);
+        L.cost.ensure(nn * 4);
+        L.total.ensure(nn * 4);
+        L.desc_new.ensure(nn * 8);
+        L.gid_at.ensure((size_t)L.G_all * 4);
+        CK(cudaMemsetAsync(L.gid_at.p, 0, (size_t)L.G_all * 4, s));
+        for (int r = 0; r < world; ++r)
+          c->launches += launch_dist_scatter(rec + (size_t)r * stride, (uint32_t)counts[r], rslot + (size_t)r * stride,
+                                             c->table.as<uint64_t>(), L.gbase, grank, L.id_base, L.k3.as<int32_t>(),
+                                             L.cost.as<int32_t>(), L.total.as<int32_t>(), L.desc_new.as<uint64_t>(),
+                                             L.gid_at.as<int32_t>(), misc + 0, s);
+        if (L.G) {  // ids of the indices this rank's candidates produced (provenance edges)
+          LevelTable LT{};
+          LT.n_levels = d + 1;
+          for (int l = 0; l <= d; ++l) {
+            LT.gbase[l] = lv[l].gbase;
+            LT.cand_id[l] = l == 0 ? lv[0].cand_id.as<int32_t>() : lv[l].gid_at.as<int32_t>();
+          }
+          LT.gbase[d + 1] = L.gbase + L.G_all;
+          c->launches += launch_dist_cand_id(curE.slot, c->table.as<uint64_t>(), LT, L.G,
+                                             (int32_t*)L.cand_id.ensure((size_t)L.G * 4), s);
+        }
+      }
+      st.scored[d - 1] = n_new;
+      gtotal += L.G_all;
+      n_ids += (int32_t)n_new;
+      // select_next reads the level's maxlen from the pinned copy of misc: restore what dist_expand saw
+      CK(cudaMemcpyAsync(misc + 2, &dist_maxlen, 4, cudaMemcpyHostToDevice, s));
+    }
+    bool more = false;
+    if (d < D) {
+      select_next(d);
+      more = lv[d].n_new > 0 && lv[d + 1].P > 0;
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    lv[d].fblob.release();
+    if (!more) {
+      for (int e = d + 1; e <= D; ++e) {
+        if ((int)lv.size() <= e) lv.emplace_back();
+        st.n_levels = e;
+      }
+      d2h(c, pin_u32(), misc, 4);
+      CK(cudaEventRecord(ev1, s));
+      CK(cudaStreamSynchronize(s));
+      best_k3 = (int)pin_u32()[0];
+      cudaEventElapsedTime(&st.total_ms, ev0, ev1);
+      st.n_ids = n_ids;
+      st.best = k3_to_score(best_k3);
+    }
+    dist_more = more;
+    cur_level = d + 1;
+  }
+
+  void dist_report_begin(uint8_t* needed) {
+    int k3_star;
+    int64_t quota;
+    report_thresholds(dist_k3_min, k3_star, quota);
+    extract_good(needed, dist_k3_min, k3_star, quota);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+  }
+  void dist_finish(const uint8_t* needed, const void* all, const int64_t* counts, int64_t stride, nw_result* R) {
+    std::vector<EdgeRec> edges;
+    for (int r = 0; r < world; ++r) {
+      if (!counts[r]) continue;
+      const size_t at = edges.size();
+      edges.resize(at + (size_t)counts[r]);
+      d2h(c, edges.data() + at, (const EdgeRec*)all + (size_t)r * stride, (size_t)counts[r] * sizeof(EdgeRec));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    build_nodes(needed, edges);
+    enumerate(R, dist_k3_min);
+  }
+
   // ---- report: get_good_trajectories (solver.jl:727-745) ----
   struct Node {
     int32_t k3 = 0, cost = -1, total = 0;
@@ -753,9 +997,10 @@ struct Search {
 
   static float score_f32(int k3) { return k3 < 0 ? -INFINITY : (float)k3_to_score(k3); }
 
-  void extract(int k3_min, int k3_star, int64_t quota) {
+  // ---- report extraction, in phases so that the frontier-sharded search can interleave collectives ----
+  // phase 1: which ids are reported (identical on every rank: it only reads the replicated per-id arrays)
+  void extract_good(uint8_t* needed, int k3_min, int k3_star, int64_t quota) {
     cudaStream_t s = c->stream;
-    uint8_t* needed = (uint8_t*)c->flag.ensure((size_t)n_ids + 16, true);
     CK(cudaMemsetAsync(needed, 0, (size_t)n_ids + 16, s));
     const int nl = (int)lv.size();
     int32_t* misc0 = (int32_t*)c->misc.p;
@@ -779,62 +1024,100 @@ struct Search {
         quota -= (int64_t)pin_u32()[10];
       }
     }
-    for (int pass = 1; pass <= o.maxdepth + 1; ++pass)  // pass = 1 + distance of the children looked at
-      for (int l = nl - 1; l >= 1; --l)
-        if (l + pass <= o.maxdepth + 2)
-          c->launches += launch_mark_parents(lv[l].cand_id.as<int32_t>(), lv[l].desc.as<uint64_t>(),
-                                             lv[l].fid.as<int32_t>(), lv[l].G, needed, pass, l, o.maxdepth, s);
+  }
+  // phase 2: one step of the depth-bounded ancestor closure over this rank's edges (pass = 1 + child distance)
+  void extract_mark(uint8_t* needed, int pass) {
+    const int nl = (int)lv.size();
+    for (int l = nl - 1; l >= 1; --l)
+      if (l + pass <= o.maxdepth + 2)
+        c->launches += launch_mark_parents(lv[l].cand_id.as<int32_t>(), lv[l].desc.as<uint64_t>(),
+                                           lv[l].fid.as<int32_t>(), lv[l].G, needed, pass, l, o.maxdepth, c->stream);
+  }
+  // phase 3: compact this rank's edges into needed ids (all levels) into c->edgebuf; returns their number
+  uint32_t extract_edges(const uint8_t* needed) {
+    cudaStream_t s = c->stream;
     int32_t* misc = (int32_t*)c->misc.p;
-    nodes.clear();
-    nodes[1] = Node{root_k3, root_cost, root_total, {}};
-    for (int l = 1; l < nl; ++l) {
-      const Level& L = lv[l];
-      if (L.G == 0) continue;
-      // edges into needed ids
-      uint32_t* eflag = (uint32_t*)c->is_new.ensure((size_t)L.G * 4, true);
-      uint32_t* epre = (uint32_t*)c->newrank.ensure((size_t)L.G * 4, true);
-      uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.G) * 4, true);
-      c->launches += launch_edge_flags(L.cand_id.as<int32_t>(), L.G, needed, eflag, l, o.maxdepth, s);
-      c->launches += launch_scan(eflag, epre, L.G, bsum, (uint32_t*)(misc + 8), s);
-      d2h(c, pin_u32(), misc, 64);
-      CK(cudaStreamSynchronize(s));
-      const uint32_t ne = pin_u32()[8];
-      if (ne) {
-        EdgeRec* d_e = (EdgeRec*)c->keys.ensure((size_t)ne * sizeof(EdgeRec), true);
-        c->launches += launch_edge_compact(L.cand_id.as<int32_t>(), L.desc.as<uint64_t>(), L.fid.as<int32_t>(), L.G,
-                                           eflag, epre, d_e, s);
-        std::vector<EdgeRec> he(ne);
-        d2h(c, he.data(), d_e, (size_t)ne * sizeof(EdgeRec));
-        CK(cudaStreamSynchronize(s));
-        for (const EdgeRec& e : he) nodes[e.child].in.push_back(e);
-      }
-      // per-id records of needed ids discovered at this level
-      if (L.n_new) {
-        uint32_t* iflag = (uint32_t*)c->is_new.ensure((size_t)L.n_new * 4, true);
-        uint32_t* ipre = (uint32_t*)c->newrank.ensure((size_t)L.n_new * 4, true);
-        bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.n_new) * 4, true);
-        c->launches += launch_id_flags(needed, L.id_base, L.n_new, iflag, s);
-        c->launches += launch_scan(iflag, ipre, L.n_new, bsum, (uint32_t*)(misc + 9), s);
-        d2h(c, pin_u32(), misc, 64);
-        CK(cudaStreamSynchronize(s));
-        const uint32_t ni = pin_u32()[9];
-        if (ni) {
-          IdRec* d_i = (IdRec*)c->keys.ensure((size_t)ni * sizeof(IdRec), true);
-          c->launches += launch_id_compact(L.k3.as<int32_t>(), L.cost.as<int32_t>(), L.total.as<int32_t>(), L.id_base,
-                                           L.n_new, iflag, ipre, d_i, s);
-          std::vector<IdRec> hi(ni);
-          d2h(c, hi.data(), d_i, (size_t)ni * sizeof(IdRec));
+    const int nl = (int)lv.size();
+    std::vector<uint32_t> cnt(nl, 0);
+    uint32_t total = 0;
+    // pass A: counts per level (flags + scan are recomputed in pass B; both are cheap streaming kernels)
+    for (int pass = 0; pass < 2; ++pass) {
+      uint32_t at = 0;
+      if (pass == 1) c->edgebuf.ensure((size_t)std::max<uint32_t>(total, 1) * sizeof(EdgeRec), true);
+      for (int l = 1; l < nl; ++l) {
+        const Level& L = lv[l];
+        if (L.G == 0 || (pass == 1 && cnt[l] == 0)) continue;
+        uint32_t* eflag = (uint32_t*)c->is_new.ensure((size_t)L.G * 4, true);
+        uint32_t* epre = (uint32_t*)c->newrank.ensure((size_t)L.G * 4, true);
+        uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.G) * 4, true);
+        c->launches += launch_edge_flags(L.cand_id.as<int32_t>(), L.G, needed, eflag, l, o.maxdepth, s);
+        c->launches += launch_scan(eflag, epre, L.G, bsum, (uint32_t*)(misc + 8), s);
+        if (pass == 0) {
+          d2h(c, pin_u32(), misc, 64);
           CK(cudaStreamSynchronize(s));
-          for (const IdRec& r : hi) {
-            Node& nd = nodes[r.id];
-            nd.k3 = r.k3;
-            nd.cost = r.cost;
-            nd.total = r.total;
-          }
+          cnt[l] = pin_u32()[8];
+          total += cnt[l];
+        } else {
+          c->launches += launch_edge_compact(L.cand_id.as<int32_t>(), L.desc.as<uint64_t>(), L.fid.as<int32_t>(), L.G,
+                                             eflag, epre, L.gbase, world > 1 ? L.off_loc.as<uint32_t>() : nullptr,
+                                             world > 1 ? L.off_glob.as<uint32_t>() : nullptr,
+                                             c->edgebuf.as<EdgeRec>() + at, s);
+          at += cnt[l];
         }
       }
     }
+    CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
+    return total;
+  }
+  // phase 4: host graph of the needed ids from the edge records of all ranks (sorted into discovery order)
+  void build_nodes(const uint8_t* needed, std::vector<EdgeRec>& edges) {
+    cudaStream_t s = c->stream;
+    int32_t* misc = (int32_t*)c->misc.p;
+    const int nl = (int)lv.size();
+    if (world > 1)
+      std::sort(edges.begin(), edges.end(), [](const EdgeRec& a, const EdgeRec& b) { return a.gpos < b.gpos; });
+    nodes.clear();
+    nodes[1] = Node{root_k3, root_cost, root_total, {}};
+    for (const EdgeRec& e : edges) nodes[e.child].in.push_back(e);
+    for (int l = 1; l < nl; ++l) {
+      const Level& L = lv[l];
+      if (!L.n_new) continue;
+      uint32_t* iflag = (uint32_t*)c->is_new.ensure((size_t)L.n_new * 4, true);
+      uint32_t* ipre = (uint32_t*)c->newrank.ensure((size_t)L.n_new * 4, true);
+      uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.n_new) * 4, true);
+      c->launches += launch_id_flags(needed, L.id_base, L.n_new, iflag, s);
+      c->launches += launch_scan(iflag, ipre, L.n_new, bsum, (uint32_t*)(misc + 9), s);
+      d2h(c, pin_u32(), misc, 64);
+      CK(cudaStreamSynchronize(s));
+      const uint32_t ni = pin_u32()[9];
+      if (!ni) continue;
+      IdRec* d_i = (IdRec*)c->keys.ensure((size_t)ni * sizeof(IdRec), true);
+      c->launches += launch_id_compact(L.k3.as<int32_t>(), L.cost.as<int32_t>(), L.total.as<int32_t>(), L.id_base,
+                                       L.n_new, iflag, ipre, d_i, s);
+      std::vector<IdRec> hi(ni);
+      d2h(c, hi.data(), d_i, (size_t)ni * sizeof(IdRec));
+      CK(cudaStreamSynchronize(s));
+      for (const IdRec& r : hi) {
+        Node& nd = nodes[r.id];
+        nd.k3 = r.k3;
+        nd.cost = r.cost;
+        nd.total = r.total;
+      }
+    }
+    CK(cudaGetLastError());
+  }
+  void extract(int k3_min, int k3_star, int64_t quota) {  // single-rank composition of the phases
+    uint8_t* needed = (uint8_t*)c->flag.ensure((size_t)n_ids + 16, true);
+    extract_good(needed, k3_min, k3_star, quota);
+    for (int pass = 1; pass <= o.maxdepth + 1; ++pass) extract_mark(needed, pass);
+    const uint32_t ne = extract_edges(needed);
+    std::vector<EdgeRec> he(ne);
+    if (ne) {
+      d2h(c, he.data(), c->edgebuf.p, (size_t)ne * sizeof(EdgeRec));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+    build_nodes(needed, he);
   }
 
   // ---- trajectory enumeration: concatenate_moves_aux + sort + truncate (solver.jl:688-705, :739-743) ----
@@ -884,7 +1167,7 @@ struct Search {
       bool first = true;
       for (size_t k = stack.size(); k-- > 0;) {  // stack holds the last move first; trajectories list moves root-first
         const EdgeRec& e = stack[k];
-        const int kind = e.kind_i & 3, i = e.kind_i >> 2, j = e.j;
+        const int kind = edge_kind(e), i = edge_i(e), j = edge_j(e);
         R->t_moves.push_back(kind);
         R->t_moves.push_back(i);
         R->t_moves.push_back(j);
@@ -918,11 +1201,12 @@ struct Search {
     }
   };
 
-  void report(nw_result* R) {
+  // thresholds of the report (identical on every rank): k3_min from minreport, k3_star/quota from maxreport
+  void report_thresholds(int& k3_min, int& k3_star, int64_t& quota) {
     const double best = k3_to_score(best_k3);
     const double thr = o.minreport * best;  // solver.jl:733
     // smallest k3 whose Float32 score passes `score >= suboptimality * best` (monotone in k3)
-    int k3_min = 100001;
+    k3_min = 100001;
     {
       int lo = 0, hi = 100001;  // first k3 in [0, 100000] with (double)(float)(k3/1000) >= thr
       while (lo < hi) {
@@ -931,8 +1215,8 @@ struct Search {
       }
       k3_min = lo;
     }
-    int k3_star = -1;
-    int64_t quota = 0;
+    k3_star = -1;
+    quota = 0;
     if (o.maxreport >= 0 && n_ids > o.maxreport) {
       cudaStream_t s = c->stream;
       uint32_t* hist = (uint32_t*)c->keys.ensure((size_t)100002 * 4, true);
@@ -953,7 +1237,15 @@ struct Search {
       }
       if (k3_star >= 0 && root_k3 == k3_star) quota -= 1;  // the root (id 1) is the first of its tie bin
     }
+  }
+  void report(nw_result* R) {
+    int k3_min, k3_star;
+    int64_t quota;
+    report_thresholds(k3_min, k3_star, quota);
     extract(k3_min, k3_star, quota);
+    enumerate(R, k3_min);
+  }
+  void enumerate(nw_result* R, int k3_min) {
     std::vector<std::pair<int32_t, int32_t>> good;  // (-k3, id): canonical Dict order = ascending discovery id
     for (auto& kv : nodes) {
       const int k3 = kv.second.k3;
@@ -1138,6 +1430,7 @@ int nw_ctx_create(int device, nw_ctx** out) {
 void nw_ctx_destroy(nw_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  nw_dist_abort(c);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->pinned) cudaFreeHost(c->pinned);
   for (auto& ev : c->score_events) c->event_pool.push_back(ev);
@@ -1375,6 +1668,159 @@ int nw_moveset(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, uint8_t* 
   });
   if (rc != NW_OK) cudaGetLastError();
   return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// frontier-sharded single search: see include/nwsolve.h for the protocol
+// ---------------------------------------------------------------------------------------------------
+static Search* dist_of(nw_ctx* c) {
+  if (!c || !c->dist) fail(NW_ERR_ARG, "no sharded search in progress (call nw_dist_begin first)");
+  return static_cast<Search*>(c->dist);
+}
+void nw_dist_abort(nw_ctx* c) {
+  if (!c || !c->dist) return;
+  PoolScope pool_scope(c);
+  cudaSetDevice(c->device);
+  delete static_cast<Search*>(c->dist);
+  c->dist = nullptr;
+}
+int nw_dist_begin(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const int64_t* len_x, const int64_t* len_y,
+                  const nw_opts* o, int32_t rank, int32_t world) {
+  if (!c || !aln || !len_x || !len_y) {
+    g_last_error = "null argument";
+    return NW_ERR_ARG;
+  }
+  nw_dist_abort(c);
+  PoolScope pool_scope(c);
+  const int rc = guard([&] {
+    check_opts(o);
+    if (world < 1 || rank < 0 || rank >= world) fail(NW_ERR_ARG, "bad rank/world");
+    CK(cudaSetDevice(c->device));
+    c->launches = 0;
+    c->h2d_bytes = c->d2h_bytes = 0;
+    collect_score_time(c, nullptr, nullptr);
+    setup_region(c, aln, n_x, n_y, len_x, len_y, o->maxdepth, false);
+    Search* S = new Search(c, *o);
+    c->dist = S;
+    S->rank = rank;
+    S->world = world;
+    S->dist_begin();
+  });
+  if (rc != NW_OK) {
+    cudaGetLastError();
+    nw_dist_abort(c);
+  }
+  return rc;
+}
+int nw_dist_expand(nw_ctx* c, int64_t* n_records) {
+  PoolScope pool_scope(c);
+  const int rc = guard([&] {
+    Search* S = dist_of(c);
+    CK(cudaSetDevice(c->device));
+    if (!S->dist_more) fail(NW_ERR_ARG, "the sharded search has no further level");
+    const int64_t n = S->dist_expand();
+    if (n_records) *n_records = n;
+  });
+  if (rc != NW_OK) cudaGetLastError();
+  return rc;
+}
+int nw_dist_pack(nw_ctx* c, void* dev_out) {
+  PoolScope pool_scope(c);
+  const int rc = guard([&] {
+    Search* S = dist_of(c);
+    CK(cudaSetDevice(c->device));
+    S->dist_pack(dev_out);
+  });
+  if (rc != NW_OK) cudaGetLastError();
+  return rc;
+}
+int nw_dist_merge(nw_ctx* c, const void* dev_all, const int64_t* counts, int64_t stride_records, int32_t* more) {
+  PoolScope pool_scope(c);
+  const int rc = guard([&] {
+    Search* S = dist_of(c);
+    CK(cudaSetDevice(c->device));
+    if (!counts) fail(NW_ERR_ARG, "counts is null");
+    S->dist_merge(dev_all, counts, stride_records);
+    if (more) *more = S->dist_more ? 1 : 0;
+  });
+  if (rc != NW_OK) cudaGetLastError();
+  return rc;
+}
+int64_t nw_dist_n_ids(nw_ctx* c) { return (c && c->dist) ? (int64_t) static_cast<Search*>(c->dist)->n_ids : -1; }
+int nw_dist_report_begin(nw_ctx* c, void* needed_dev, int64_t nbytes) {
+  PoolScope pool_scope(c);
+  const int rc = guard([&] {
+    Search* S = dist_of(c);
+    CK(cudaSetDevice(c->device));
+    if (!needed_dev || nbytes < (int64_t)S->n_ids + 16) fail(NW_ERR_ARG, "needed buffer must hold n_ids + 16 bytes");
+    collect_score_time(c, &S->st.score_ms, &S->st.score_launches);
+    S->dist_report_begin((uint8_t*)needed_dev);
+  });
+  if (rc != NW_OK) cudaGetLastError();
+  return rc;
+}
+int nw_dist_report_mark(nw_ctx* c, void* needed_dev, int32_t pass) {
+  PoolScope pool_scope(c);
+  const int rc = guard([&] {
+    Search* S = dist_of(c);
+    CK(cudaSetDevice(c->device));
+    S->extract_mark((uint8_t*)needed_dev, pass);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+  });
+  if (rc != NW_OK) cudaGetLastError();
+  return rc;
+}
+int nw_dist_report_edges(nw_ctx* c, const void* needed_dev, int64_t* n_edges) {
+  PoolScope pool_scope(c);
+  const int rc = guard([&] {
+    Search* S = dist_of(c);
+    CK(cudaSetDevice(c->device));
+    const uint32_t n = S->extract_edges((const uint8_t*)needed_dev);
+    S->dist_edges = n;
+    if (n_edges) *n_edges = n;
+  });
+  if (rc != NW_OK) cudaGetLastError();
+  return rc;
+}
+int nw_dist_report_pack(nw_ctx* c, void* dev_out) {
+  PoolScope pool_scope(c);
+  const int rc = guard([&] {
+    Search* S = dist_of(c);
+    CK(cudaSetDevice(c->device));
+    if (S->dist_edges) {
+      CK(cudaMemcpyAsync(dev_out, c->edgebuf.p, (size_t)S->dist_edges * sizeof(EdgeRec), cudaMemcpyDeviceToDevice,
+                         c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+  });
+  if (rc != NW_OK) cudaGetLastError();
+  return rc;
+}
+int nw_dist_finish(nw_ctx* c, const void* needed_dev, const void* dev_edges_all, const int64_t* counts,
+                   int64_t stride_edges, nw_result** out) {
+  if (!out) return NW_ERR_ARG;
+  *out = nullptr;
+  PoolScope pool_scope(c);
+  nw_result* R = new nw_result();
+  const int rc = guard([&] {
+    Search* S = dist_of(c);
+    CK(cudaSetDevice(c->device));
+    if (!counts) fail(NW_ERR_ARG, "counts is null");
+    S->dist_finish((const uint8_t*)needed_dev, dev_edges_all, counts, stride_edges, R);
+    S->st.kernel_launches = c->launches;
+    S->st.h2d_bytes = c->h2d_bytes;
+    S->st.d2h_bytes = c->d2h_bytes;
+    R->stats = S->st;
+  });
+  nw_dist_abort(c);
+  if (rc != NW_OK) {
+    delete R;
+    cudaGetLastError();
+    return rc;
+  }
+  *out = R;
+  return NW_OK;
 }
 
 int nw_bench_peaks(nw_ctx* c, double out[4]) {

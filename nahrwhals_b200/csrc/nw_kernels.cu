@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t s_warp_tot[4];
   const int parent = blockIdx.x;
+  if (EMIT && A.own_mod > 1 && parent % A.own_mod != A.own_rem) return;  // another rank expands this parent
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = A.F.len[parent];
   const int LS = A.F.LS;
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(256) k_hash_insert(ExpandArgs A, uint32_t G) {
   const U4* Ft = reinterpret_cast<const U4*>(blob + (size_t)A.F.LS * 2);
   const U4* Gt = Ft + (A.F.LS + 1);
   const U4 f = child_fingerprint(Ft, Gt, A.pw, A.F.len[ps], desc_kind(d), desc_i(d), desc_j(d));
-  A.slot[pos] = table_insert(A.table, A.tmask, fp_key0(f), fp_key1(f), (uint64_t)A.gbase + pos);
+  A.slot[pos] = table_insert(A.table, A.tmask, fp_key0(f), fp_key1(f), (uint64_t)cand_gpos(A, pos, ps));
 }
 int launch_hash_insert(const ExpandArgs& A, uint32_t G, cudaStream_t st) {
   if (G == 0) return 0;
@@ -310,10 +311,11 @@ uint64_t scan_scratch_items(uint64_t n) { return (n + SCAN_B - 1) / SCAN_B + 1; 
 // =====================================================================================================
 // resolve / assign: which candidate is the first discoverer of its index (solver.jl:535-561)
 // =====================================================================================================
-__global__ void k_resolve(const uint32_t* slot, const uint64_t* table, uint32_t gbase, uint32_t G, uint32_t* is_new) {
+__global__ void k_resolve(ExpandArgs A, uint32_t G, uint32_t* is_new) {
   const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= G) return;
-  is_new[pos] = table[(uint64_t)slot[pos] * TBL_WORDS + 2] == (uint64_t)gbase + pos ? 1u : 0u;
+  const uint32_t g = cand_gpos(A, pos, desc_parent(A.desc[pos]));
+  is_new[pos] = A.table[(uint64_t)A.slot[pos] * TBL_WORDS + 2] == (uint64_t)g ? 1u : 0u;
 }
 
 __device__ __forceinline__ int32_t owner_id(const LevelTable& LT, uint32_t g) {
@@ -330,7 +332,7 @@ __global__ void k_assign(AssignArgs A) {
     const uint64_t og = A.table[(uint64_t)A.slot[pos] * TBL_WORDS + 2];
     if (A.is_new[pos]) {
       const uint32_t r = A.newrank[pos];
-      A.cand_id[pos] = A.id_base + (int32_t)r;
+      if (!A.skip_ids) A.cand_id[pos] = A.id_base + (int32_t)r;
       A.newlist[r] = pos;
       const uint64_t d = A.desc[pos];
       const int len = child_len(A.front_len[desc_parent(d)], desc_kind(d), desc_i(d), desc_j(d));
@@ -342,7 +344,7 @@ __global__ void k_assign(AssignArgs A) {
       } else {
         Lc = len;
       }
-    } else {
+    } else if (!A.skip_ids) {
       const uint32_t g = (uint32_t)og;
       A.cand_id[pos] = g >= A.gbase ? A.id_base + (int32_t)A.newrank[g - A.gbase] : owner_id(A.LT, g);
     }
@@ -358,10 +360,9 @@ int launch_assign(const AssignArgs& A, cudaStream_t st) {
   k_assign<<<(A.G + 255) / 256, 256, 0, st>>>(A);
   return 1;
 }
-int launch_resolve(const uint32_t* slot, const uint64_t* table, uint32_t gbase, uint32_t G, uint32_t* is_new,
-                   cudaStream_t st) {
+int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* is_new, cudaStream_t st) {
   if (G == 0) return 0;
-  k_resolve<<<(G + 255) / 256, 256, 0, st>>>(slot, table, gbase, G, is_new);
+  k_resolve<<<(G + 255) / 256, 256, 0, st>>>(A, G, is_new);
   return 1;
 }
 
@@ -600,7 +601,7 @@ __global__ void __launch_bounds__(256) k_materialise(MaterialiseArgs A) {
   __shared__ int s_max;
   const int e = blockIdx.x;
   const uint32_t r = A.sel[e];
-  const uint64_t d = A.desc[A.newlist[r]];
+  const uint64_t d = A.newlist ? A.desc[A.newlist[r]] : A.desc[r];
   const uint32_t ps = desc_parent(d);
   const int kind = desc_kind(d), p = desc_i(d), q = desc_j(d);
   const int L = A.F.len[ps];
@@ -708,15 +709,17 @@ __global__ void k_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* 
   flag[pos] = (v && lvl + v <= maxdepth + 2) ? 1u : 0u;
 }
 __global__ void k_edge_compact(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
-                               const uint32_t* flag, const uint32_t* pre, EdgeRec* out) {
+                               const uint32_t* flag, const uint32_t* pre, uint32_t gbase, const uint32_t* off_loc,
+                               const uint32_t* off_glob, EdgeRec* out) {
   const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= G || !flag[pos]) return;
   const uint64_t d = desc[pos];
+  const uint32_t ps = desc_parent(d);
   EdgeRec e;
   e.child = cand_id[pos];
-  e.parent = front_id[desc_parent(d)];
-  e.kind_i = desc_kind(d) | (desc_i(d) << 2);
-  e.j = desc_j(d);
+  e.parent = front_id[ps];
+  e.move = (uint32_t)desc_kind(d) | ((uint32_t)desc_i(d) << 2) | ((uint32_t)desc_j(d) << 17);
+  e.gpos = off_glob ? gbase + off_glob[ps] + (pos - off_loc[ps]) : gbase + pos;
   out[pre[pos]] = e;
 }
 __global__ void k_id_flags(const uint8_t* needed, int32_t id_base, uint32_t n, uint32_t* flag) {
@@ -764,9 +767,11 @@ int launch_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* needed,
   return 1;
 }
 int launch_edge_compact(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
-                        const uint32_t* flag, const uint32_t* pre, void* out, cudaStream_t st) {
+                        const uint32_t* flag, const uint32_t* pre, uint32_t gbase, const uint32_t* off_loc,
+                        const uint32_t* off_glob, void* out, cudaStream_t st) {
   if (!G) return 0;
-  k_edge_compact<<<(G + 255) / 256, 256, 0, st>>>(cand_id, desc, front_id, G, flag, pre, (EdgeRec*)out);
+  k_edge_compact<<<(G + 255) / 256, 256, 0, st>>>(cand_id, desc, front_id, G, flag, pre, gbase, off_loc, off_glob,
+                                                 (EdgeRec*)out);
   return 1;
 }
 int launch_id_flags(const uint8_t* needed, int32_t id_base, uint32_t n, uint32_t* flag, cudaStream_t st) {
@@ -778,6 +783,100 @@ int launch_id_compact(const int32_t* k3, const int32_t* cost, const int32_t* tot
                       const uint32_t* flag, const uint32_t* pre, void* out, cudaStream_t st) {
   if (!n) return 0;
   k_id_compact<<<(n + 255) / 256, 256, 0, st>>>(k3, cost, total, id_base, n, flag, pre, (IdRec*)out);
+  return 1;
+}
+
+// =====================================================================================================
+// frontier-sharded search (one deep search over several ranks).  Each rank expands the parents it owns,
+// dedups locally, scores its locally-first candidates and contributes one DistRec per such candidate to a per-level
+// all-gather.  Every rank then runs the same merge: min discovery position per fingerprint over all ranks decides
+// the owner (exactly the serial first-discoverer rule of solver.jl:535), ids follow global discovery order.
+// =====================================================================================================
+__global__ void k_mask_counts(const uint32_t* cnt, uint32_t P, int own_mod, int own_rem, uint32_t* out) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < P) out[s] = ((int)(s % (uint32_t)own_mod) == own_rem) ? cnt[s] : 0u;
+}
+__global__ void k_dist_pack(ExpandArgs A, const uint32_t* newlist, uint32_t n_new, const int32_t* k3, const int32_t* cost,
+                            const int32_t* total, DistRec* out) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_new) return;
+  const uint32_t pos = newlist[r];
+  const uint64_t s = A.slot[pos];
+  DistRec o;
+  o.k0 = A.table[s * TBL_WORDS];
+  o.k1 = A.table[s * TBL_WORDS + 1];
+  o.desc = A.desc[pos];
+  o.gpos = cand_gpos(A, pos, desc_parent(o.desc));
+  o.k3 = k3[r];
+  o.cost = cost[r];
+  o.total = total[r];
+  out[r] = o;
+}
+__global__ void k_dist_merge_insert(const DistRec* rec, uint32_t n, uint64_t* table, uint64_t mask, uint32_t* slot) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  slot[i] = table_insert(table, mask, rec[i].k0, rec[i].k1, (uint64_t)rec[i].gpos);
+}
+__global__ void k_dist_merge_flag(const DistRec* rec, uint32_t n, const uint32_t* slot, const uint64_t* table,
+                                  uint32_t gbase, uint32_t* newflag) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (table[(uint64_t)slot[i] * TBL_WORDS + 2] == (uint64_t)rec[i].gpos) newflag[rec[i].gpos - gbase] = 1u;
+}
+__global__ void k_dist_scatter(const DistRec* rec, uint32_t n, const uint32_t* slot, const uint64_t* table, uint32_t gbase,
+                               const uint32_t* grank, int32_t id_base, int32_t* k3, int32_t* cost, int32_t* total,
+                               uint64_t* desc_new, int32_t* gid_at, int* best_k3) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const DistRec o = rec[i];
+  if (table[(uint64_t)slot[i] * TBL_WORDS + 2] != (uint64_t)o.gpos) return;  // a smaller position owns this index
+  const uint32_t r = grank[o.gpos - gbase];
+  k3[r] = o.k3;
+  cost[r] = o.cost;
+  total[r] = o.total;
+  desc_new[r] = o.desc;
+  gid_at[o.gpos - gbase] = id_base + (int32_t)r;
+  if (o.k3 > 0) atomicMax(best_k3, o.k3);
+}
+__global__ void k_dist_cand_id(const uint32_t* slot, const uint64_t* table, LevelTable LT, uint32_t G, int32_t* cand_id) {
+  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= G) return;
+  cand_id[pos] = owner_id(LT, (uint32_t)table[(uint64_t)slot[pos] * TBL_WORDS + 2]);
+}
+int launch_mask_counts(const uint32_t* cnt, uint32_t P, int own_mod, int own_rem, uint32_t* out, cudaStream_t st) {
+  if (!P) return 0;
+  k_mask_counts<<<(P + 255) / 256, 256, 0, st>>>(cnt, P, own_mod, own_rem, out);
+  return 1;
+}
+int launch_dist_pack(const ExpandArgs& A, const uint32_t* newlist, uint32_t n_new, const int32_t* k3, const int32_t* cost,
+                     const int32_t* total, void* out, cudaStream_t st) {
+  if (!n_new) return 0;
+  k_dist_pack<<<(n_new + 255) / 256, 256, 0, st>>>(A, newlist, n_new, k3, cost, total, (DistRec*)out);
+  return 1;
+}
+int launch_dist_merge_insert(const void* rec, uint32_t n, uint64_t* table, uint64_t mask, uint32_t* slot, cudaStream_t st) {
+  if (!n) return 0;
+  k_dist_merge_insert<<<(n + 255) / 256, 256, 0, st>>>((const DistRec*)rec, n, table, mask, slot);
+  return 1;
+}
+int launch_dist_merge_flag(const void* rec, uint32_t n, const uint32_t* slot, const uint64_t* table, uint32_t gbase,
+                           uint32_t* newflag, cudaStream_t st) {
+  if (!n) return 0;
+  k_dist_merge_flag<<<(n + 255) / 256, 256, 0, st>>>((const DistRec*)rec, n, slot, table, gbase, newflag);
+  return 1;
+}
+int launch_dist_scatter(const void* rec, uint32_t n, const uint32_t* slot, const uint64_t* table, uint32_t gbase,
+                        const uint32_t* grank, int32_t id_base, int32_t* k3, int32_t* cost, int32_t* total,
+                        uint64_t* desc_new, int32_t* gid_at, int* best_k3, cudaStream_t st) {
+  if (!n) return 0;
+  k_dist_scatter<<<(n + 255) / 256, 256, 0, st>>>((const DistRec*)rec, n, slot, table, gbase, grank, id_base, k3, cost,
+                                                 total, desc_new, gid_at, best_k3);
+  return 1;
+}
+int launch_dist_cand_id(const uint32_t* slot, const uint64_t* table, const LevelTable& LT, uint32_t G, int32_t* cand_id,
+                        cudaStream_t st) {
+  if (!G) return 0;
+  k_dist_cand_id<<<(G + 255) / 256, 256, 0, st>>>(slot, table, LT, G, cand_id);
   return 1;
 }
 

@@ -60,6 +60,23 @@ struct ExpandArgs {
   uint64_t tmask;
   uint32_t gbase;
   const U4* pw;
+  // frontier sharding (single deep search over several ranks): this rank owns parents with slot % own_mod == own_rem;
+  // `off` then holds offsets into the rank-local candidate arrays and off_glob the offsets in global discovery order.
+  int own_mod, own_rem;
+  const uint32_t* off_glob;  // nullptr: local == global
+};
+
+// global discovery position of the candidate stored at local position `pos` (parent slot ps)
+__device__ __forceinline__ uint32_t cand_gpos(const ExpandArgs& A, uint32_t pos, uint32_t ps) {
+  return A.off_glob ? A.gbase + A.off_glob[ps] + (pos - A.off[ps]) : A.gbase + pos;
+}
+
+// record exchanged between ranks for every locally-first candidate of a level (40 bytes)
+struct DistRec {
+  uint64_t k0, k1;  // fingerprint
+  uint64_t desc;    // (global parent slot, i, j, kind)
+  uint32_t gpos;    // global discovery position
+  int32_t k3, cost, total;
 };
 
 struct ScoreArgs {
@@ -95,6 +112,7 @@ struct AssignArgs {
   uint32_t gbase, G;
   int32_t id_base;  // id of new-rank 0
   int n_y, force;
+  int skip_ids;     // sharded search: ids are assigned after the cross-rank merge
   int32_t* cand_id;   // [G] out
   uint32_t* newlist;  // [n_new] out: rank -> pos
   uint16_t* new_len;  // [n_new] out: child length
@@ -123,9 +141,12 @@ struct MaterialiseArgs {
 
 struct EdgeRec {
   int32_t child, parent;
-  int32_t kind_i;  // kind | i << 2
-  int32_t j;
+  uint32_t move;  // kind | i << 2 | j << 17
+  uint32_t gpos;  // global discovery position (edge order of solver.jl:559-560)
 };
+__host__ __device__ inline int edge_kind(const EdgeRec& e) { return (int)(e.move & 3u); }
+__host__ __device__ inline int edge_i(const EdgeRec& e) { return (int)((e.move >> 2) & 0x7fffu); }
+__host__ __device__ inline int edge_j(const EdgeRec& e) { return (int)((e.move >> 17) & 0x7fffu); }
 struct IdRec {
   int32_t id, k3, cost, total;
 };

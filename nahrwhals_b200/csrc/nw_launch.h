@@ -15,8 +15,7 @@ int launch_hash_insert(const ExpandArgs& A, uint32_t G, cudaStream_t st);
 int launch_scan(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* bsum_scratch, uint32_t* total_out,
                 cudaStream_t st);
 uint64_t scan_scratch_items(uint64_t n);
-int launch_resolve(const uint32_t* slot, const uint64_t* table, uint32_t gbase, uint32_t G, uint32_t* is_new,
-                   cudaStream_t st);
+int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* is_new, cudaStream_t st);
 int launch_assign(const AssignArgs& A, cudaStream_t st);
 int launch_bucket_scatter(const uint16_t* new_len, uint32_t n_new, int n_y, int force, const uint32_t* bstart,
                           uint32_t* cursor, uint32_t* work, cudaStream_t st);
@@ -38,7 +37,19 @@ int launch_mark_parents(const int32_t* cand_id, const uint64_t* desc, const int3
 int launch_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* needed, uint32_t* flag, int lvl, int maxdepth,
                       cudaStream_t st);
 int launch_edge_compact(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
-                        const uint32_t* flag, const uint32_t* pre, void* out, cudaStream_t st);
+                        const uint32_t* flag, const uint32_t* pre, uint32_t gbase, const uint32_t* off_loc,
+                        const uint32_t* off_glob, void* out, cudaStream_t st);
+int launch_mask_counts(const uint32_t* cnt, uint32_t P, int own_mod, int own_rem, uint32_t* out, cudaStream_t st);
+int launch_dist_pack(const ExpandArgs& A, const uint32_t* newlist, uint32_t n_new, const int32_t* k3, const int32_t* cost,
+                     const int32_t* total, void* out, cudaStream_t st);
+int launch_dist_merge_insert(const void* rec, uint32_t n, uint64_t* table, uint64_t mask, uint32_t* slot, cudaStream_t st);
+int launch_dist_merge_flag(const void* rec, uint32_t n, const uint32_t* slot, const uint64_t* table, uint32_t gbase,
+                           uint32_t* newflag, cudaStream_t st);
+int launch_dist_scatter(const void* rec, uint32_t n, const uint32_t* slot, const uint64_t* table, uint32_t gbase,
+                        const uint32_t* grank, int32_t id_base, int32_t* k3, int32_t* cost, int32_t* total,
+                        uint64_t* desc_new, int32_t* gid_at, int* best_k3, cudaStream_t st);
+int launch_dist_cand_id(const uint32_t* slot, const uint64_t* table, const LevelTable& LT, uint32_t G, int32_t* cand_id,
+                        cudaStream_t st);
 int launch_id_flags(const uint8_t* needed, int32_t id_base, uint32_t n, uint32_t* flag, cudaStream_t st);
 int launch_id_compact(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,
                       const uint32_t* flag, const uint32_t* pre, void* out, cudaStream_t st);

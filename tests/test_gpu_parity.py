@@ -166,3 +166,29 @@ def test_roundtrip_property_full_size(solver):
     assert A.stats.best == 100.0 and A.tsv == B.tsv
     assert A.tsv.startswith("100.0\t")
     assert A.generated == B.generated and A.scored == B.scored
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_search_emulated(oracle, world):
+    """Frontier-sharded single search with the ranks emulated on one GPU: every rank must reproduce the
+    single-GPU / oracle result bit for bit (ids, counts, TSV), for a beam search and an exhaustive one."""
+    import nahrwhals_b200 as nb
+    from nahrwhals_b200.distributed import solve_sharded_emulated
+    solvers = [nb.Solver(0) for _ in range(world)]
+    try:
+        for gen, flags in [(dict(n_x=40, families=[5, 4, 3, 2], seed=12, chain_depth=3), dict(maxdepth=4, maxdup=2, maxwidth=50)),
+                           (dict(n_x=24, families=[4, 3, 3], seed=11, chain_depth=3), dict(maxdepth=3, maxdup=2)),
+                           (dict(n_x=150, families=[6, 5, 4, 4, 3], seed=7, chain_depth=4), dict(maxdepth=4, maxdup=2, maxwidth=100))]:
+            mat, lx, ly, _ = sdgrid(**gen)
+            aln = to_solver_inputs(mat)
+            kw = dict(minreport=0.98, maxreport=1000, **flags)
+            O = oracle.solve(aln, lx, ly, **kw)
+            res = solve_sharded_emulated(solvers, aln, lx, ly, **kw)
+            for R in res:
+                assert R.tsv == O.tsv
+                assert R.generated == [int(v) for v in O.generated]
+                assert R.scored == [int(v) for v in O.scored]
+                assert int(R.stats.n_ids) == O.n_ids and R.stats.best == O.best
+    finally:
+        for s in solvers:
+            s.close()
