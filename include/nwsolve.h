@@ -117,6 +117,19 @@ int nw_score_batch(nw_ctx* ctx, const int8_t* aln_sign, int32_t n_x, int32_t n_y
 /* Replaces to_moveset (solver.jl:217-231): two n_x*n_x uint8 matrices (duplicate_delete, invert). */
 int nw_moveset(nw_ctx* ctx, const int8_t* aln_sign, int32_t n_x, int32_t n_y, uint8_t* dup_del, uint8_t* invert);
 
+/* Regionfile / whole-genome modes (R/nahrwhals.R:171-215, :240-290 run one solver process per region from PSOCK
+ * workers): n independent problems are solved by n_ctx contexts concurrently, one host thread + CUDA stream per
+ * context, regions handed out dynamically.  Contexts may sit on one GPU (small regions overlap on the device) or on
+ * several GPUs of the process.  outs[k] / rcs[k] receive the result handle / return code of problem k. */
+typedef struct nw_problem {
+  const int8_t* aln_sign; /* n_x*n_y, x-major */
+  int32_t n_x, n_y;
+  const int64_t* len_x;
+  const int64_t* len_y;
+} nw_problem;
+int nw_solve_batch(nw_ctx** ctxs, int32_t n_ctx, const nw_problem* probs, int64_t n, const nw_opts* opts,
+                   nw_result** outs, int32_t* rcs);
+
 /* ---- one deep search sharded over `world` ranks (config 3 of BASELINE.json) -------------------------
  * One context per rank, the same problem and options on every rank.  The frontier is replicated; rank r expands the
  * parents whose frontier slot is congruent to r modulo world, dedups and scores its own candidates, and contributes

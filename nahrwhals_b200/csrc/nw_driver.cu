@@ -11,6 +11,9 @@
 #include <chrono>
 #include <functional>
 #include <map>
+#include <atomic>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -1409,6 +1412,16 @@ int nw_ctx_create(int device, nw_ctx** out) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) fail(NW_ERR_CUDA, std::string("device is not sm_100 (Blackwell B200): ") + prop.name);
+    {
+      static std::mutex mu;
+      static bool done[64] = {false};
+      std::lock_guard<std::mutex> lk(mu);
+      if (device < 64 && !done[device]) {
+        init_kernel_attrs();
+        CK(cudaGetLastError());
+        done[device] = true;
+      }
+    }
     nw_ctx* c = new nw_ctx();
     c->device = device;
     PoolScope pool_scope(c);
@@ -1668,6 +1681,46 @@ int nw_moveset(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, uint8_t* 
   });
   if (rc != NW_OK) cudaGetLastError();
   return rc;
+}
+
+int nw_solve_batch(nw_ctx** ctxs, int32_t n_ctx, const nw_problem* probs, int64_t n, const nw_opts* opts,
+                   nw_result** outs, int32_t* rcs) {
+  if (!ctxs || n_ctx < 1 || !probs || n < 0 || !opts || !outs) {
+    g_last_error = "null argument";
+    return NW_ERR_ARG;
+  }
+  for (int t = 0; t < n_ctx; ++t)
+    if (!ctxs[t]) {
+      g_last_error = "null context";
+      return NW_ERR_ARG;
+    }
+  std::atomic<int64_t> next{0};
+  std::atomic<int> first_err{NW_OK};
+  std::mutex err_mu;
+  std::string err_msg;
+  auto worker = [&](int t) {
+    for (;;) {
+      const int64_t k = next.fetch_add(1);
+      if (k >= n) return;
+      outs[k] = nullptr;
+      const nw_problem& P = probs[k];
+      const int rc = nw_solve(ctxs[t], P.aln_sign, P.n_x, P.n_y, P.len_x, P.len_y, opts, &outs[k]);
+      if (rcs) rcs[k] = rc;
+      if (rc != NW_OK) {
+        std::lock_guard<std::mutex> lk(err_mu);
+        if (first_err.load() == NW_OK) {
+          first_err.store(rc);
+          err_msg = "problem " + std::to_string(k) + ": " + nw_last_error();
+        }
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_ctx; ++t) th.emplace_back(worker, t);
+  worker(0);
+  for (auto& x : th) x.join();
+  if (first_err.load() != NW_OK) g_last_error = err_msg;
+  return first_err.load();
 }
 
 // ---------------------------------------------------------------------------------------------------

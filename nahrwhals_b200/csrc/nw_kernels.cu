@@ -184,15 +184,11 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
 int launch_expand(bool emit, const ExpandArgs& A, cudaStream_t st) {
   if (A.F.P <= 0) return 0;
   const size_t rows = (size_t)A.F.LS * 4;
-  if (emit) {
-    const size_t sm = (size_t)A.F.LS * 2 + rows;
-    cudaFuncSetAttribute(k_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  const size_t sm = (size_t)A.F.LS * 2 + rows;
+  if (emit)
     k_expand<true><<<A.F.P, 128, sm, st>>>(A);
-  } else {
-    const size_t sm = (size_t)A.F.LS * 2 + rows;
-    cudaFuncSetAttribute(k_expand<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  else
     k_expand<false><<<A.F.P, 128, sm, st>>>(A);
-  }
   return 1;
 }
 
@@ -653,7 +649,6 @@ __global__ void __launch_bounds__(256) k_materialise(MaterialiseArgs A) {
 int launch_materialise(const MaterialiseArgs& A, cudaStream_t st) {
   if (A.P2 <= 0) return 0;
   const size_t sm = (((size_t)A.LS2 * 2 + 15) & ~(size_t)15) + (size_t)(A.n_x + 1) * 4;
-  cudaFuncSetAttribute(k_materialise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   k_materialise<<<A.P2, 256, sm, st>>>(A);
   return 1;
 }
@@ -920,6 +915,20 @@ double launch_int_peak(int mode, int* out, int iters, cudaStream_t st) {
   if (mode == 2) k_int_peak<2><<<grid, block, 0, st>>>(out, iters, 3, 1000, 1);
   const double per_thread = (double)iters * 4 * 8 * (mode == 2 ? 2 : 1);
   return per_thread * grid * block;
+}
+
+// Opt-in dynamic shared memory limits are per (device, function) state: they are raised ONCE per device here, never
+// per launch (a per-launch cudaFuncSetAttribute races between contexts running on different host threads).
+void init_score_fast_attrs();
+void init_kernel_attrs() {
+  int dev = 0, optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const int mx = optin - 2048;  // the limit covers static + dynamic shared memory of a block
+  cudaFuncSetAttribute(k_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_expand<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_materialise, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  init_score_fast_attrs();
 }
 
 int launch_moveset(const RegionDev& R, cudaStream_t st) {

@@ -6,6 +6,7 @@
 namespace nw {
 
 double launch_int_peak(int mode, int* out, int iters, cudaStream_t st);
+void init_kernel_attrs();  // once per device
 int launch_moveset(const RegionDev& R, cudaStream_t st);
 int launch_insert_root(const int16_t* seq, int L, const U4* pw, uint32_t rid1, uint64_t* table, uint64_t tmask,
                        cudaStream_t st);

@@ -167,9 +167,35 @@ size_t score_fast_smem(int W, uint32_t ctx_bytes, int lmax) {
 template <int W>
 static int launch_w(const ScoreArgs& A, cudaStream_t st) {
   const size_t sm = score_fast_smem(W, A.R.ctx_bytes, A.lmax);
-  cudaFuncSetAttribute(k_score_fast<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   k_score_fast<W><<<(A.n_work + 127) / 128, 128, sm, st>>>(A);
   return 1;
+}
+
+void init_score_fast_attrs() {
+  int dev = 0, optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const int mx = optin - 2048;  // the limit covers static + dynamic shared memory of a block
+  cudaFuncSetAttribute(k_score_fast<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<28>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<36>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<44>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<52>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<60>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<112>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_score_fast<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
 }
 
 int launch_score_fast(int W, const ScoreArgs& A, cudaStream_t st) {

@@ -185,6 +185,35 @@ class Solver:
         return dd.astype(bool), iv.astype(bool)
 
 
+def solve_batch(solvers, regions, **kw):
+    """Regionfile mode: solve independent regions [(aln, len_x, len_y), ...] on several contexts concurrently
+    (nw_solve_batch: one host thread + stream per context; contexts may share a GPU).  Returns SolveResults."""
+    L = _lib.load()
+    n = len(regions)
+    keep = [Solver._problem(*r) for r in regions]
+    probs = (_lib.NwProblem * max(n, 1))()
+    for k, (a, lx, ly) in enumerate(keep):
+        probs[k].aln_sign = a.ctypes.data
+        probs[k].n_x, probs[k].n_y = a.shape
+        probs[k].len_x = lx.ctypes.data
+        probs[k].len_y = ly.ctypes.data
+    ctxs = (C.c_void_p * len(solvers))(*[s.h for s in solvers])
+    outs = (C.c_void_p * max(n, 1))()
+    rcs = (C.c_int32 * max(n, 1))()
+    o = solvers[0]._opts(**kw)
+    rc = L.nw_solve_batch(ctxs, len(solvers), probs, n, C.byref(o), outs, rcs)
+    res = []
+    try:
+        _lib.check(rc)
+        for k in range(n):
+            res.append(solvers[0]._unpack(C.c_void_p(outs[k]), o))
+    finally:
+        for k in range(n):
+            if outs[k]:
+                L.nw_result_free(C.c_void_p(outs[k]))
+    return res
+
+
 def read_problem(inmat, inlens):
     """read_tsv + read_length_tsv (solver.jl:101-107, :121-138) -> (aln int8 [n_x,n_y], len_x, len_y)."""
     L = _lib.load()

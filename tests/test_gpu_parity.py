@@ -192,3 +192,27 @@ def test_sharded_search_emulated(oracle, world):
     finally:
         for s in solvers:
             s.close()
+
+
+def test_solve_batch_regions(oracle):
+    """Regionfile mode (nw_solve_batch): independent regions on several contexts sharing one GPU give, region by
+    region, exactly the TSV of the oracle."""
+    import nahrwhals_b200 as nb
+    rng = np.random.default_rng(3)
+    regions = []
+    for k in range(24):
+        n_x = int(rng.integers(20, 70))
+        fams = [int(rng.integers(2, 5)) for _ in range(int(rng.integers(2, 5)))]
+        mat, lx, ly, _ = sdgrid(n_x, fams, seed=500 + k, chain_depth=int(rng.integers(1, 4)), len_tol=0.3)
+        regions.append((to_solver_inputs(mat), lx, ly))
+    kw = dict(maxdepth=3, maxdup=2, maxwidth=1000, minreport=0.98, maxreport=1000)
+    solvers = [nb.Solver(0) for _ in range(4)]
+    try:
+        res = nb.solve_batch(solvers, regions, **kw)
+    finally:
+        for s in solvers:
+            s.close()
+    assert len(res) == len(regions)
+    for (aln, lx, ly), R in zip(regions, res):
+        O = oracle.solve(aln, lx, ly, full=False, **kw)
+        assert R.tsv == O.tsv and R.scored == [int(v) for v in O.scored]

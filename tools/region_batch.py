@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Regionfile-mode throughput (BASELINE.json config 4): N synthetic SD-flanked regions (20-120 blocks, 2-6 repeat
+families of size 2-4), -d 3 -u 2 -w 1000 -r 0.98 -R 1000, solved by T solver contexts on one GPU (one host thread
+and one CUDA stream each).  Prints regions/s next to the CPU oracle on all host cores.
+usage: python tools/region_batch.py [n_regions] [threads,...] [--cpu]"""
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import nahrwhals_b200 as nb  # noqa: E402
+from nahrwhals_b200.sdgrid import sdgrid, to_solver_inputs  # noqa: E402
+
+FLAGS = dict(maxdepth=3, maxdup=2, maxwidth=1000, minreport=0.98, maxreport=1000)
+
+
+def make_regions(n, seed=0):
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(n):
+        n_x = int(rng.integers(20, 121))
+        fams = [int(rng.integers(2, 5)) for _ in range(int(rng.integers(2, 7)))]
+        while sum(fams) > n_x:
+            fams.pop()
+        mat, lx, ly, _ = sdgrid(n_x, fams, seed=1000 + k, chain_depth=int(rng.integers(1, 4)), len_tol=0.3)
+        out.append((to_solver_inputs(mat), lx, ly))
+    return out
+
+
+def run_gpu(regions, threads, device=0):
+    solvers = [nb.Solver(device) for _ in range(threads)]
+    for s in solvers:  # warm-up (pool, module load)
+        s.solve(*regions[0], **FLAGS)
+    t0 = time.perf_counter()
+    res = nb.solve_batch(solvers, regions, **FLAGS)  # nw_solve_batch: native worker thread per context
+    dt = time.perf_counter() - t0
+    for s in solvers:
+        s.close()
+    return len(regions) / dt, sum(sum(R.scored) for R in res), dt
+
+
+def run_cpu(regions, threads):
+    from oracle import oracle_lib
+    oracle_lib.lib()
+    nxt = [0]
+    lock = threading.Lock()
+    scored = [0] * threads
+
+    def work(t):
+        while True:
+            with lock:
+                k = nxt[0]
+                nxt[0] += 1
+            if k >= len(regions):
+                return
+            aln, lx, ly = regions[k]
+            R = oracle_lib.solve(aln, lx, ly, full=False, **FLAGS)
+            scored[t] += int(R.scored.sum())
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    dt = time.perf_counter() - t0
+    return len(regions) / dt, sum(scored), dt
+
+
+if __name__ == "__main__":
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 500
+    tl = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 4, 16]
+    t0 = time.time()
+    regs = make_regions(n)
+    print("generated %d regions in %.1f s" % (n, time.time() - t0), flush=True)
+    if "--cpu" in sys.argv:
+        c = os.cpu_count()
+        r, sc, dt = run_cpu(regs, c)
+        print("CPU oracle, %d threads: %.1f regions/s, %.3g candidates/s (%.2f s)" % (c, r, sc / dt, dt), flush=True)
+    for t in tl:
+        r, sc, dt = run_gpu(regs, t)
+        print("GPU, %d contexts: %.1f regions/s, %.3g candidates/s (%.2f s)" % (t, r, sc / dt, dt), flush=True)
