@@ -192,13 +192,13 @@ struct nw_ctx {
   // region
   RegionHost RH;
   RegionDev RD{};
-  DevBuf d_ctx, d_rt, d_cumr, d_msdd, d_msinv;
+  DevBuf d_ctx, d_rt, d_cumr, d_msdd, d_msinv, d_msany;
   BandStore bands;
   // dedup table
   DevBuf table;
   uint64_t table_cap = 0;
   // per-level scratch
-  DevBuf cnt, off, bsum, slot, is_new, newrank, new_len, hist, bstart, cursor, work, scratch, flag, pre, sel, keys,
+  DevBuf cnt, off, bsum, slot, owner, is_new, newrank, new_len, hist, bstart, cursor, work, scratch, flag, pre, sel, keys,
       misc, rslot, newflag, grank, edgebuf;
   void* dist = nullptr;  // active frontier-sharded search (Search*, nw_dist_*)
   void* pinned = nullptr;  // small pinned staging area for D2H scalars / histograms
@@ -240,7 +240,8 @@ struct nw_result {
 
 namespace {
 
-constexpr size_t PINNED_BYTES = 64 * 1024;
+constexpr size_t PINNED_BYTES = 512 * 1024;
+constexpr size_t HIST_N = (size_t)(LMAX + 2) * NSUB;  // (child length, sub-counter) bins
 
 struct Level {
   // frontier expanded at this level
@@ -283,6 +284,7 @@ void setup_region(nw_ctx* c, const int8_t* aln, int n_x, int n_y, const int64_t*
   const size_t msb = (size_t)(n_x + 1) * H.MW * 4;
   CK(cudaMemsetAsync(c->d_msdd.ensure(msb), 0, msb, st));
   CK(cudaMemsetAsync(c->d_msinv.ensure(msb), 0, msb, st));
+  CK(cudaMemsetAsync(c->d_msany.ensure((size_t)(n_x + 1) * 4), 0, (size_t)(n_x + 1) * 4, st));
   RegionDev& D = c->RD;
   D.n_x = n_x;
   D.n_y = n_y;
@@ -300,6 +302,7 @@ void setup_region(nw_ctx* c, const int8_t* aln, int n_x, int n_y, const int64_t*
   D.cumr = c->d_cumr.as<int32_t>();
   D.ms_dd = c->d_msdd.as<uint32_t>();
   D.ms_inv = c->d_msinv.as<uint32_t>();
+  D.ms_any = c->d_msany.as<uint32_t>();
   if (D.ctx_bytes > 200 * 1024) fail(NW_ERR_RANGE, "region context exceeds shared memory");
   c->launches += launch_moveset(D, st);
   if (c->bands.n_y != n_y || c->bands.force != force) c->bands.reset(n_y, force);
@@ -349,13 +352,15 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
   std::vector<Bucket> bk;
   int64_t cells = 0;
   for (int L = 1; L <= LMAX; ++L) {
-    if (!hist_h[L]) continue;
+    uint32_t nL = 0;
+    for (int sb = 0; sb < NSUB; ++sb) nL += hist_h[(size_t)L * NSUB + sb];
+    if (!nL) continue;
     const BandTable& T = c->bands.get(L);
     int cls = 0;
     if (!(flags & NW_FLAG_GENERIC_DP) && T.fast_ok) cls = score_fast_window(T.max_width);
     if (cls && score_fast_smem(cls, c->RD.ctx_bytes, L) > 200 * 1024) cls = 0;  // tiles would not fit: generic kernel
-    bk.push_back(Bucket{L, cls, hist_h[L]});
-    cells += (int64_t)hist_h[L] * T.cells;
+    bk.push_back(Bucket{L, cls, nL});
+    cells += (int64_t)nL * T.cells;
   }
   if (cells_out) *cells_out = cells;
   if (bk.empty()) return;
@@ -364,7 +369,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
     const int ka = a.cls ? a.cls : 1 << 20, kb = b.cls ? b.cls : 1 << 20;
     return ka < kb;
   });
-  std::vector<uint32_t> bstart(LMAX + 2, 0);
+  std::vector<uint32_t> bstart(HIST_N, 0);
   struct Range {
     int cls;
     uint32_t begin, end;
@@ -377,14 +382,18 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
       pos = (pos + 127) & ~127u;  // class ranges start on a CTA boundary
       ranges.push_back(Range{b.cls, pos, pos, 0});
     }
-    bstart[b.L] = pos;
+    uint32_t at = pos;  // the sub-counters of one length share one contiguous, 32-padded bucket
+    for (int sb = 0; sb < NSUB; ++sb) {
+      bstart[(size_t)b.L * NSUB + sb] = at;
+      at += hist_h[(size_t)b.L * NSUB + sb];
+    }
     pos += (b.n + 31) & ~31u;
     ranges.back().end = pos;
     ranges.back().lmax = std::max(ranges.back().lmax, b.L);
   }
   const uint32_t n_work = pos;
-  h2d(c, c->bstart.ensure((LMAX + 2) * 4), bstart.data(), (LMAX + 2) * 4);
-  CK(cudaMemsetAsync(c->cursor.ensure((LMAX + 2) * 4), 0, (LMAX + 2) * 4, st));
+  h2d(c, c->bstart.ensure(HIST_N * 4), bstart.data(), HIST_N * 4);
+  CK(cudaMemsetAsync(c->cursor.ensure(HIST_N * 4), 0, HIST_N * 4, st));
   CK(cudaMemsetAsync(c->work.ensure((size_t)n_work * 4, true), 0xFF, (size_t)n_work * 4, st));
   c->launches += launch_bucket_scatter(c->new_len.as<uint16_t>(), Lv.n_new, c->RD.n_y, force, c->bstart.as<uint32_t>(),
                                        c->cursor.as<uint32_t>(), c->work.as<uint32_t>(), st);
@@ -523,7 +532,7 @@ struct Search {
     // score the root (solver.jl:599) -- its score never updates `best` (:606)
     int32_t* misc = (int32_t*)c->misc.ensure(256);
     CK(cudaMemsetAsync(misc, 0, 256, s));
-    std::vector<uint32_t> hist(LMAX + 2, 0);
+    std::vector<uint32_t> hist(HIST_N, 0);
     const uint16_t rl = (uint16_t)n_x;
     h2d(c, c->new_len.ensure(2), &rl, 2);
     if (early_exit(n_x, c->RD.n_y)) {
@@ -536,7 +545,7 @@ struct Search {
       h2d(c, L0.total.p, &v[2], 4);
       CK(cudaStreamSynchronize(s));
     } else {
-      hist[n_x] = 1;
+      hist[bucket_key(n_x, 0)] = 1;
       ScoreView view = view_of(L0);  // candidates of level 0 against the frontier of level 1
       view.F = L1.frontier();
       run_scoring(c, view, hist.data(), 0, o.flags, misc + 1 /*dummy best*/, nullptr);
@@ -597,7 +606,8 @@ struct Search {
     c->launches += launch_expand(true, E, s);
     c->launches += launch_hash_insert(E, G, s);
     uint32_t* is_new = (uint32_t*)c->is_new.ensure((size_t)G * 4, true);
-    c->launches += launch_resolve(E, G, is_new, s);
+    uint32_t* owner = (uint32_t*)c->owner.ensure((size_t)G * 4, true);
+    c->launches += launch_resolve(E, G, is_new, owner, s);
     uint32_t* newrank = (uint32_t*)c->newrank.ensure((size_t)G * 4, true);
     bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(G) * 4, true);
     c->launches += launch_scan(is_new, newrank, G, bsum, (uint32_t*)(misc + 5), s);
@@ -617,6 +627,7 @@ struct Search {
     A.LT.gbase[d] = L.gbase;
     A.slot = E.slot;
     A.table = E.table;
+    A.owner = owner;
     A.is_new = is_new;
     A.newrank = newrank;
     A.desc = E.desc;
@@ -632,11 +643,11 @@ struct Search {
     A.k3 = (int32_t*)L.k3.ensure((size_t)n_new * 4);
     A.cost = (int32_t*)L.cost.ensure((size_t)n_new * 4);
     A.total = (int32_t*)L.total.ensure((size_t)n_new * 4);
-    A.hist = (uint32_t*)c->hist.ensure((LMAX + 2) * 4);
-    CK(cudaMemsetAsync(A.hist, 0, (LMAX + 2) * 4, s));
+    A.hist = (uint32_t*)c->hist.ensure(HIST_N * 4);
+    CK(cudaMemsetAsync(A.hist, 0, HIST_N * 4, s));
     c->launches += launch_assign(A, s);
     uint32_t* hist_h = pin_u32() + 64;
-    d2h(c, hist_h, A.hist, (LMAX + 2) * 4);
+    d2h(c, hist_h, A.hist, HIST_N * 4);
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     int64_t cells = 0;
@@ -834,7 +845,8 @@ struct Search {
     c->launches += launch_expand(true, E, s);
     c->launches += launch_hash_insert(E, G, s);
     uint32_t* is_new = (uint32_t*)c->is_new.ensure((size_t)G * 4, true);
-    c->launches += launch_resolve(E, G, is_new, s);
+    uint32_t* owner = (uint32_t*)c->owner.ensure((size_t)G * 4, true);
+    c->launches += launch_resolve(E, G, is_new, owner, s);
     uint32_t* newrank = (uint32_t*)c->newrank.ensure((size_t)G * 4, true);
     bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(G) * 4, true);
     c->launches += launch_scan(is_new, newrank, G, bsum, (uint32_t*)(misc + 5), s);
@@ -847,6 +859,7 @@ struct Search {
     A.LT.n_levels = 0;
     A.slot = E.slot;
     A.table = E.table;
+    A.owner = owner;
     A.is_new = is_new;
     A.newrank = newrank;
     A.desc = E.desc;
@@ -863,11 +876,11 @@ struct Search {
     A.k3 = (int32_t*)L.l_k3.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
     A.cost = (int32_t*)L.l_cost.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
     A.total = (int32_t*)L.l_total.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
-    A.hist = (uint32_t*)c->hist.ensure((LMAX + 2) * 4);
-    CK(cudaMemsetAsync(A.hist, 0, (LMAX + 2) * 4, s));
+    A.hist = (uint32_t*)c->hist.ensure(HIST_N * 4);
+    CK(cudaMemsetAsync(A.hist, 0, HIST_N * 4, s));
     c->launches += launch_assign(A, s);
     uint32_t* hist_h = pin_u32() + 64;
-    d2h(c, hist_h, A.hist, (LMAX + 2) * 4);
+    d2h(c, hist_h, A.hist, HIST_N * 4);
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     int64_t cells = 0;
@@ -1617,7 +1630,7 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
     std::vector<uint64_t> desc(n);
     std::vector<uint32_t> newlist(n);
     std::vector<uint16_t> nlen(n);
-    std::vector<uint32_t> hist(LMAX + 2, 0);
+    std::vector<uint32_t> hist(HIST_N, 0);
     std::vector<int32_t> k3(n, 0), cost(n, -1), total(n, 0);
     for (int64_t k = 0; k < n; ++k) {
       const int l = (int)(off[k + 1] - off[k]);
@@ -1626,7 +1639,7 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
       desc[k] = pack_desc((uint32_t)k, 0, 0, KIND_ID);
       newlist[k] = (uint32_t)k;
       nlen[k] = (uint16_t)l;
-      if (force || !early_exit(l, n_y)) hist[l]++;
+      if (force || !early_exit(l, n_y)) hist[bucket_key(l, (uint32_t)k)]++;
     }
     L.G = (uint32_t)n;
     L.n_new = (uint32_t)n;

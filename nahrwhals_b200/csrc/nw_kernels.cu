@@ -26,6 +26,7 @@ __global__ void k_moveset(RegionDev R) {
   }
   if (dd) atomicOr(&R.ms_dd[(size_t)a * R.MW + (b >> 5)], 1u << (b & 31));
   if (iv) atomicOr(&R.ms_inv[(size_t)a * R.MW + (b >> 5)], 1u << (b & 31));
+  if (dd | iv) R.ms_any[a] = 1u;
 }
 
 // =====================================================================================================
@@ -120,6 +121,10 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
   for (int i = warp + 1; i <= L; i += 4) {
     const int a = seq[i - 1];
     uint32_t n = 0;
+    if (!__ldg(&A.R.ms_any[a < 0 ? -a : a])) {  // block without any partner: no move starts here (warp-uniform)
+      if (lane == 0) rowcnt[i - 1] = 0;
+      continue;
+    }
     for (int j = i + 1 + lane; j <= L; j += 32) {
       int cdd, civ;
       n += pair_moves(A.R, a, seq[j - 1], dupok, cdd, civ);
@@ -156,6 +161,7 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
   const uint32_t base = A.off[parent];
   for (int i = warp + 1; i <= L; i += 4) {
     const int a = seq[i - 1];
+    if (!__ldg(&A.R.ms_any[a < 0 ? -a : a])) continue;
     uint32_t rowpos = base + rowcnt[i - 1];
     for (int j0 = i + 1; j0 <= L; j0 += 32) {
       const int j = j0 + lane;
@@ -307,11 +313,13 @@ uint64_t scan_scratch_items(uint64_t n) { return (n + SCAN_B - 1) / SCAN_B + 1; 
 // =====================================================================================================
 // resolve / assign: which candidate is the first discoverer of its index (solver.jl:535-561)
 // =====================================================================================================
-__global__ void k_resolve(ExpandArgs A, uint32_t G, uint32_t* is_new) {
+__global__ void k_resolve(ExpandArgs A, uint32_t G, uint32_t* is_new, uint32_t* owner) {
   const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= G) return;
   const uint32_t g = cand_gpos(A, pos, desc_parent(A.desc[pos]));
-  is_new[pos] = A.table[(uint64_t)A.slot[pos] * TBL_WORDS + 2] == (uint64_t)g ? 1u : 0u;
+  const uint32_t o = (uint32_t)A.table[(uint64_t)A.slot[pos] * TBL_WORDS + 2];  // the one random table read
+  owner[pos] = o;
+  is_new[pos] = o == g ? 1u : 0u;
 }
 
 __device__ __forceinline__ int32_t owner_id(const LevelTable& LT, uint32_t g) {
@@ -323,9 +331,8 @@ __device__ __forceinline__ int32_t owner_id(const LevelTable& LT, uint32_t g) {
 __global__ void k_assign(AssignArgs A) {
   const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = pos < A.G;
-  int Lc = 0xffff;  // histogram key of lanes that need a DP; 0xffff = none
+  int key = -1;  // histogram key (child length, sub-counter) of lanes that need a DP; -1 = none
   if (in) {
-    const uint64_t og = A.table[(uint64_t)A.slot[pos] * TBL_WORDS + 2];
     if (A.is_new[pos]) {
       const uint32_t r = A.newrank[pos];
       if (!A.skip_ids) A.cand_id[pos] = A.id_base + (int32_t)r;
@@ -338,17 +345,16 @@ __global__ void k_assign(AssignArgs A) {
         A.cost[r] = -1;
         A.total[r] = 0;
       } else {
-        Lc = len;
+        key = bucket_key(len, r);
       }
     } else if (!A.skip_ids) {
-      const uint32_t g = (uint32_t)og;
+      const uint32_t g = A.owner[pos];
       A.cand_id[pos] = g >= A.gbase ? A.id_base + (int32_t)A.newrank[g - A.gbase] : owner_id(A.LT, g);
     }
   }
-  // warp-aggregated histogram over child lengths (all 32 lanes converge here)
-  const uint32_t peers = __match_any_sync(0xffffffffu, Lc);
-  if (Lc != 0xffff && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31))
-    atomicAdd(&A.hist[Lc], (uint32_t)__popc(peers));
+  // warp-aggregated histogram (all 32 lanes converge here)
+  const uint32_t peers = __match_any_sync(0xffffffffu, key);
+  if (key >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&A.hist[key], (uint32_t)__popc(peers));
 }
 
 int launch_assign(const AssignArgs& A, cudaStream_t st) {
@@ -356,9 +362,9 @@ int launch_assign(const AssignArgs& A, cudaStream_t st) {
   k_assign<<<(A.G + 255) / 256, 256, 0, st>>>(A);
   return 1;
 }
-int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* is_new, cudaStream_t st) {
+int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* is_new, uint32_t* owner, cudaStream_t st) {
   if (G == 0) return 0;
-  k_resolve<<<(G + 255) / 256, 256, 0, st>>>(A, G, is_new);
+  k_resolve<<<(G + 255) / 256, 256, 0, st>>>(A, G, is_new, owner);
   return 1;
 }
 
@@ -366,19 +372,19 @@ int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* is_new, cudaStream
 __global__ void k_bucket_scatter(const uint16_t* new_len, uint32_t n_new, int n_y, int force, const uint32_t* bstart,
                                  uint32_t* cursor, uint32_t* work) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  int Lc = 0xffff;
+  int key = -1;
   if (r < n_new) {
     const int len = new_len[r];
-    if (force || !early_exit(len, n_y)) Lc = len;
+    if (force || !early_exit(len, n_y)) key = bucket_key(len, r);
   }
-  const uint32_t peers = __match_any_sync(0xffffffffu, Lc);
+  const uint32_t peers = __match_any_sync(0xffffffffu, key);
   const int leader = __ffs(peers) - 1;
   uint32_t base = 0;
-  if (Lc != 0xffff && (int)(threadIdx.x & 31) == leader) base = atomicAdd(&cursor[Lc], (uint32_t)__popc(peers));
+  if (key >= 0 && (int)(threadIdx.x & 31) == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
   base = __shfl_sync(0xffffffffu, base, leader);
-  if (Lc != 0xffff) {
+  if (key >= 0) {
     const uint32_t mine = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
-    work[bstart[Lc] + base + mine] = r;
+    work[bstart[key] + base + mine] = r;
   }
 }
 int launch_bucket_scatter(const uint16_t* new_len, uint32_t n_new, int n_y, int force, const uint32_t* bstart,

@@ -12,6 +12,10 @@ constexpr uint64_t TBL_EMPTY = ~0ull;
 constexpr int TBL_WORDS = 4;  // slot = {key0, key1, first-discoverer gpos, unused} (32 B)
 constexpr int MAX_LEVELS = 16;
 constexpr uint32_t WORK_PAD = 0xffffffffu;
+// The per-length counters used to bucket fresh candidates are split NSUB ways (by new-rank / 256) to spread the
+// atomics of k_assign / k_bucket_scatter over more addresses.
+constexpr int NSUB = 8;
+__host__ __device__ inline int bucket_key(int len, uint32_t new_rank) { return len * NSUB + (int)((new_rank >> 8) & (NSUB - 1)); }
 
 // Per-region read-only context in device memory.  [planes | upx | rt_rev] is one contiguous, 16-B aligned
 // blob of ctx_bytes so the scoring kernels can stage it with a single TMA bulk copy.
@@ -30,6 +34,7 @@ struct RegionDev {
   const int32_t* cumr;   // cumr[j] = sum_{j'<=j} rt
   uint32_t* ms_dd;       // [(n_x+1) * MW] bit rows, 1-based block ids
   uint32_t* ms_inv;
+  uint32_t* ms_any;      // [n_x+1] non-zero iff the block has any dup/del or inversion partner
 };
 
 // One BFS level's frontier: P parents, each a blob [seq int16 x LS | F U4 x (LS+1) | G U4 x (LS+1)].
@@ -105,6 +110,7 @@ struct AssignArgs {
   LevelTable LT;
   const uint32_t* slot;
   const uint64_t* table;
+  const uint32_t* owner;    // first-discoverer position of each candidate's index (k_resolve)
   const uint32_t* is_new;
   const uint32_t* newrank;  // exclusive scan of is_new
   const uint64_t* desc;
