@@ -153,21 +153,159 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_regions(args, rank, world, local):
+    """BASELINE.json config 4: regionfile batch.  Every rank solves its own `--regions` synthetic SD-flanked regions
+    (20-120 blocks) with `--contexts` solver contexts on its GPU; no collective on the data path.  Metric: regions/s
+    (wall clock around the batch, max over ranks; many streams run concurrently so there is no single device
+    timeline).  --impl reference runs the CPU restatement on all host threads over a 10 x smaller sample."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from region_batch import FLAGS, make_regions, run_cpu
+    cores = os.cpu_count() or 1
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        regs = make_regions(max(50, args.regions // 10), seed=0)
+        r, sc, dt = run_cpu(regs, cores)
+        line = dict(impl="reference", metric="regions_solved_per_s", value=r, unit="regions/s", n_gpus=args.gpus,
+                    steps=1, warmup=0, ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f64", data="synthetic",
+                    config=dict(workload="regionfile batch: %d synthetic SD-flanked regions, 20-120 blocks, "
+                                         "-d 3 -u 2 -w 1000 -r 0.98 -R 1000" % len(regs)),
+                    cpu_baseline=dict(value=r, unit="regions/s", cores=cores, kind="port",
+                                      sample="%d regions, one per host thread at a time" % len(regs)),
+                    e2e=dict(value=r, unit="regions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line), flush=True)
+        return
+    import torch
+    import nahrwhals_b200 as nb
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    regs = make_regions(args.regions, seed=rank)
+    solvers = [nb.Solver(local) for _ in range(args.contexts)]
+    nb.solve_batch(solvers, regs[:min(len(regs), 4 * args.contexts)], **FLAGS)  # warm-up: pools, band tables
+    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    res = nb.solve_batch(solvers, regs, **FLAGS)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    scored = sum(sum(R.scored) for R in res)
+    launches = sum(R.stats.kernel_launches for R in res)
+    h2d = sum(R.stats.h2d_bytes for R in res)
+    d2h = sum(R.stats.d2h_bytes for R in res)
+    n = len(regs)
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        s = torch.tensor([n, scored, launches, h2d, d2h], dtype=torch.float64, device="cuda")
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        n, scored, launches, h2d, d2h = s.tolist()
+    line = dict(metric="regions_solved_per_s", value=n / dt, unit="regions/s", n_gpus=world, steps=1, warmup=1,
+                ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32",
+                data="synthetic",
+                config=dict(workload="regionfile batch: %d synthetic SD-flanked regions per GPU (20-120 blocks, 2-6 "
+                                     "repeat families), -d 3 -u 2 -w 1000 -r 0.98 -R 1000, %d contexts per GPU; "
+                                     "regions shard per GPU, no collective" % (args.regions, args.contexts),
+                            candidates_scored_per_s=scored / dt, l2="not flushed (every region is new data)"),
+                clocks=clocks,
+                e2e=dict(value=n / dt, unit="regions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                gpu_launches=int(launches))
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = make_regions(max(50, args.regions // 10), seed=0)
+        r, sc, cdt = run_cpu(sample, cores)
+        line["cpu_baseline"] = dict(value=r, unit="regions/s", cores=cores, kind="port",
+                                    sample="%d regions of the same generator, %.1f s, all host threads" % (len(sample), cdt))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    for s_ in solvers:
+        s_.close()
+
+
+def run_frontier(args, rank, world, local):
+    """BASELINE.json config 3: ONE deep search sharded over the GPUs (frontier round-robin, per-level all-gather of
+    40-byte records over NCCL, deterministic merge on every rank).  Strong scaling: total work is fixed."""
+    import torch
+    import torch.distributed as dist
+    import nahrwhals_b200 as nb
+    from nahrwhals_b200.distributed import solve_sharded
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    aln, lx, ly, flags, desc = make_workload(args.workload, 1)
+    solver = nb.Solver(local)
+    for _ in range(max(3, args.warmup)):
+        R = solve_sharded(solver, aln, lx, ly, **flags)
+    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler.start()
+    tot, scored, launches = 0.0, 0, 0
+    for _ in range(args.steps):
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        R = solve_sharded(solver, aln, lx, ly, **flags)
+        torch.cuda.synchronize()
+        tot += time.perf_counter() - t0
+        scored += sum(R.scored)
+        launches += R.stats.kernel_launches
+    clocks = sampler.stop()
+    t = torch.tensor([tot], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot = float(t.item())
+    s = torch.tensor([launches], dtype=torch.float64, device="cuda")
+    dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        v = scored / tot
+        print(json.dumps(dict(metric=METRIC, value=v, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+                              ms_per_step=1e3 * tot / args.steps, higher_is_better=True, scaling="strong",
+                              vs_baseline=None, dtype="int32", data="synthetic",
+                              config=dict(workload=desc + "; ONE search, frontier sharded over %d GPUs, per-level "
+                                                          "all-gather (NCCL)" % world, timing="wall clock, max over ranks"),
+                              clocks=clocks, e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=int(R.stats.h2d_bytes),
+                                                      d2h_bytes_per_step=int(R.stats.d2h_bytes)),
+                              gpu_launches=int(s.item()))), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    solver.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS) + ["regions"])
+    ap.add_argument("--regions", type=int, default=2000, help="regions per rank for --workload regions")
+    ap.add_argument("--contexts", type=int, default=8, help="solver contexts (streams) per GPU for --workload regions")
+    ap.add_argument("--mode", default="regions", choices=["regions", "frontier"],
+                    help="N > 1: 'regions' = one independent search per GPU (default, weak scaling); 'frontier' = ONE "
+                         "search sharded over the GPUs with a per-level all-gather (strong scaling, config 3)")
     ap.add_argument("--cpu-sample", type=int, default=150000, help="unique candidates per CPU replica (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "regions":
+        run_regions(args, rank, world, local)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.mode == "frontier" and world > 1:
+        run_frontier(args, rank, world, local)
         return
 
     import torch
