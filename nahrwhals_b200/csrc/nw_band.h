@@ -7,6 +7,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <algorithm>
 #include <vector>
 
 namespace nw {
@@ -45,13 +46,13 @@ inline bool band_valid(int i, int j, int row, int col, double pct) {
   return !(im > (jm + pct)) && !(jm > (im + pct));
 }
 
-inline BandTable build_band(int L, int n_y, bool force, int max_window = 128) {
-  BandTable T;
-  T.L = L;
-  T.n_y = n_y;
-  T.force = force;
+// exhaustive form (tests only): every (i, j) is evaluated with band_valid()
+inline void band_rows_bruteforce(int L, int n_y, bool force, std::vector<BandRowHost>& row, int64_t& cells,
+                                 bool& contiguous) {
   const double pct = corridor_pct(L, force);
-  T.row.assign(L + 1, BandRowHost{1, 0});
+  row.assign(L + 1, BandRowHost{1, 0});
+  cells = 0;
+  contiguous = true;
   for (int i = 1; i <= L; ++i) {
     int a = 0, b = -1, cnt = 0;
     for (int j = 1; j <= n_y; ++j)
@@ -60,14 +61,59 @@ inline BandTable build_band(int L, int n_y, bool force, int max_window = 128) {
         b = j;
         ++cnt;
       }
-    if (cnt == 0) {
-      T.row[i] = BandRowHost{1, 0};
-    } else {
-      T.row[i] = BandRowHost{a, b};
-      if (b - a + 1 != cnt) T.contiguous = false;
+    if (cnt) {
+      row[i] = BandRowHost{a, b};
+      if (b - a + 1 != cnt) contiguous = false;
     }
-    T.cells += cnt;
+    cells += cnt;
   }
+}
+
+// Row intervals in O(L + n_y) predicate evaluations.  For a fixed row, A(j) = (i/row > j/col + pct) is non-increasing
+// in j and B(j) = (j/col > i/row + pct) non-decreasing (IEEE division and addition are monotone), so the interior
+// valid set is the interval [lo_i, hi_i]; both ends are non-decreasing in i and are tracked with forward-moving
+// pointers that evaluate exactly the Float64 expressions of solver.jl:412-413 (no algebraic rewriting).
+inline void band_rows_fast(int L, int n_y, double pct, std::vector<BandRowHost>& row, int64_t& cells,
+                           bool& contiguous) {
+  row.assign(L + 1, BandRowHost{1, 0});
+  cells = 0;
+  contiguous = true;
+  {  // first row (solver.jl:400): columns 1..b with !(j/col > pct)
+    int b = 1;
+    while (b + 1 <= n_y && !((double)(b + 1) / (double)n_y > pct)) ++b;
+    if (L >= 1) {
+      row[1] = BandRowHost{1, b};
+      cells += b;
+    }
+  }
+  int lo = 2, hi = 1;
+  for (int i = 2; i <= L; ++i) {
+    const double im = (double)i / (double)L;
+    while (lo <= n_y && (im > ((double)lo / (double)n_y + pct))) ++lo;                 // A(lo) still true
+    while (hi + 1 <= n_y && !((double)(hi + 1) / (double)n_y > (im + pct))) ++hi;      // B(hi+1) false
+    const bool col1 = !(im > pct);                                                     // solver.jl:390
+    const bool interior = lo <= hi && lo <= n_y && hi >= 2;
+    int a = 1, b = 0;
+    if (interior) {
+      a = col1 ? 1 : lo;
+      b = hi;
+      if (col1 && lo > 2) contiguous = false;
+      cells += (hi - lo + 1) + (col1 ? 1 : 0);
+    } else if (col1) {
+      a = b = 1;
+      cells += 1;
+    }
+    row[i] = BandRowHost{a, b};
+  }
+}
+
+inline BandTable build_band(int L, int n_y, bool force, int max_window = 128) {
+  BandTable T;
+  T.L = L;
+  T.n_y = n_y;
+  T.force = force;
+  const double pct = corridor_pct(L, force);
+  band_rows_fast(L, n_y, pct, T.row, T.cells, T.contiguous);
   // ---- fast-path derivation ----
   T.eb.assign(L + 1, 0);
   T.ea.assign(L + 1, 0);
@@ -98,11 +144,9 @@ inline BandTable build_band(int L, int n_y, bool force, int max_window = 128) {
   }
   if (ok) {
     for (int i = 1; i <= L; ++i) {
-      for (int j = T.row[i].a; j <= T.row[i].b; ++j) {
-        // diag move into (i,j) needs (i-1, j-1) valid in the extended grid
-        const int pj = j - 1;
-        const bool pv = pj >= T.ea[i - 1] && pj <= T.eb[i - 1];
-        if (!pv) continue;
+      // diag move into (i,j) needs (i-1, j-1) valid in the extended grid: j-1 in [ea[i-1], eb[i-1]]
+      const int j0 = std::max(T.row[i].a, (int)T.ea[i - 1] + 1), j1 = std::min(T.row[i].b, (int)T.eb[i - 1] + 1);
+      for (int j = j0; j <= j1; ++j) {
         const int k = T.eb[i] - j;
         T.mask[(size_t)i * 4 + (k >> 5)] |= 1u << (k & 31);
       }

@@ -52,7 +52,7 @@ struct DevPool {
   size_t pooled_bytes = 0;
   void* take(size_t bytes, size_t* cap_out) {
     auto it = free_blocks.lower_bound(bytes);
-    if (it != free_blocks.end() && it->first <= bytes * 2 + (1 << 20)) {
+    if (it != free_blocks.end() && it->first <= bytes * 2) {
       void* p = it->second;
       *cap_out = it->first;
       pooled_bytes -= it->first;
@@ -106,8 +106,16 @@ struct DevBuf {
     if (bytes == 0) bytes = 16;
     if (bytes > cap) {
       release();
-      size_t want = grow_slack ? bytes + bytes / 4 : bytes;
-      want = (want + 255) & ~(size_t)255;
+      (void)grow_slack;
+      // size classes (powers of two up to 256 MiB, then multiples of 64 MiB) make pooled blocks reusable across
+      // regions of different shapes: a cudaMalloc in the middle of a batch stalls every context on the device
+      size_t want = 256;
+      if (bytes <= ((size_t)256 << 20)) {
+        while (want < bytes) want <<= 1;
+      } else {
+        const size_t q = (size_t)64 << 20;
+        want = (bytes + q - 1) / q * q;
+      }
       if (g_pool) {
         p = g_pool->take(want, &cap);
         if (p) return p;
@@ -193,7 +201,8 @@ struct nw_ctx {
   RegionHost RH;
   RegionDev RD{};
   DevBuf d_ctx, d_rt, d_cumr, d_msdd, d_msinv, d_msany;
-  BandStore bands;
+  std::map<int, BandStore> band_cache;  // corridor tables per (n_y, force), kept across regions
+  BandStore* bands_p = nullptr;
   // dedup table
   DevBuf table;
   uint64_t table_cap = 0;
@@ -305,7 +314,9 @@ void setup_region(nw_ctx* c, const int8_t* aln, int n_x, int n_y, const int64_t*
   D.ms_any = c->d_msany.as<uint32_t>();
   if (D.ctx_bytes > 200 * 1024) fail(NW_ERR_RANGE, "region context exceeds shared memory");
   c->launches += launch_moveset(D, st);
-  if (c->bands.n_y != n_y || c->bands.force != force) c->bands.reset(n_y, force);
+  BandStore& bs = c->band_cache[n_y * 2 + (force ? 1 : 0)];
+  if (bs.n_y != n_y || bs.force != force) bs.reset(n_y, force);
+  c->bands_p = &bs;
 }
 
 void table_reserve(nw_ctx* c, uint64_t need_entries) {
@@ -355,7 +366,8 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
     uint32_t nL = 0;
     for (int sb = 0; sb < NSUB; ++sb) nL += hist_h[(size_t)L * NSUB + sb];
     if (!nL) continue;
-    const BandTable& T = c->bands.get(L);
+    const BandTable& T = c->bands_p->get(L);
+    if (!T.contiguous) fail(NW_ERR_RANGE, "corridor rows are not intervals for this shape (unsupported)");
     int cls = 0;
     if (!(flags & NW_FLAG_GENERIC_DP) && T.fast_ok) cls = score_fast_window(T.max_width);
     if (cls && score_fast_smem(cls, c->RD.ctx_bytes, L) > 200 * 1024) cls = 0;  // tiles would not fit: generic kernel
@@ -364,7 +376,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
   }
   if (cells_out) *cells_out = cells;
   if (bk.empty()) return;
-  c->bands.upload(c, st);
+  c->bands_p->upload(c, st);
   std::stable_sort(bk.begin(), bk.end(), [](const Bucket& a, const Bucket& b) {
     const int ka = a.cls ? a.cls : 1 << 20, kb = b.cls ? b.cls : 1 << 20;
     return ka < kb;
@@ -403,11 +415,11 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
   A.F = Lv.F;
   A.newlist = Lv.newlist;
   A.desc = Lv.desc;
-  A.band_off = c->bands.d_off.as<int32_t>();
-  A.band_ab = c->bands.d_ab.as<int16_t>();
-  A.band_eb = c->bands.d_eb.as<int16_t>();
-  A.band_sb = c->bands.d_sb.as<uint8_t>();
-  A.band_mask = c->bands.d_mask.as<uint32_t>();
+  A.band_off = c->bands_p->d_off.as<int32_t>();
+  A.band_ab = c->bands_p->d_ab.as<int16_t>();
+  A.band_eb = c->bands_p->d_eb.as<int16_t>();
+  A.band_sb = c->bands_p->d_sb.as<uint8_t>();
+  A.band_mask = c->bands_p->d_mask.as<uint32_t>();
   A.k3 = Lv.k3;
   A.cost = Lv.cost;
   A.total = Lv.total;

@@ -296,11 +296,35 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_final(const uint32_t* in, uint3
   }
 }
 
+// small inputs (the common case in regionfile mode): one CTA, one launch
+constexpr uint32_t SCAN_SMALL = 65536;
+__global__ void __launch_bounds__(1024) k_scan_small(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* total_out) {
+  __shared__ uint32_t sh[33];
+  const uint32_t per = (n + 1023) / 1024;
+  const uint32_t b0 = threadIdx.x * per;
+  uint32_t s = 0;
+  for (uint32_t k = 0; k < per; ++k)
+    if (b0 + k < n) s += in[b0 + k];
+  uint32_t tot;
+  uint32_t e = block_excl_scan(s, sh, tot);
+  for (uint32_t k = 0; k < per; ++k)
+    if (b0 + k < n) {
+      const uint32_t v = in[b0 + k];
+      out[b0 + k] = e;
+      e += v;
+    }
+  if (threadIdx.x == 0) *total_out = tot;
+}
+
 int launch_scan(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* bsum_scratch, uint32_t* total_out,
                 cudaStream_t st) {
   if (n == 0) {
     cudaMemsetAsync(total_out, 0, sizeof(uint32_t), st);
     return 0;
+  }
+  if (n <= SCAN_SMALL && in != out) {
+    k_scan_small<<<1, 1024, 0, st>>>(in, out, (uint32_t)n, total_out);
+    return 1;
   }
   const uint32_t nb = (uint32_t)((n + SCAN_B - 1) / SCAN_B);
   k_scan_partial<<<nb, SCAN_T, 0, st>>>(in, n, bsum_scratch);

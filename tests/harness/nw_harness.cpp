@@ -137,6 +137,20 @@ void h_band(int L, int n_y, int force, int64_t* cells, int* fast_ok, int* max_wi
   *contiguous = T.contiguous;
 }
 
+// 1 iff the O(L + n_y) pointer construction of the corridor rows equals the exhaustive evaluation of every cell
+int h_band_check(int L, int n_y, int force) {
+  std::vector<BandRowHost> r1, r2;
+  int64_t c1 = 0, c2 = 0;
+  bool k1 = true, k2 = true;
+  band_rows_bruteforce(L, n_y, force != 0, r1, c1, k1);
+  band_rows_fast(L, n_y, corridor_pct(L, force != 0), r2, c2, k2);
+  if (c1 != c2 || k1 != k2) return 0;
+  if (!k1) return 1;  // non-contiguous rows go to the generic kernel, which uses only (a, b) of contiguous tables
+  for (int i = 1; i <= L; ++i)
+    if (r1[i].a != r2[i].a || r1[i].b != r2[i].b) return 0;
+  return 1;
+}
+
 // Julia-style Float32 score string of the product's TSV writer
 int h_score_string(int k3, char* buf, int cap) {
   std::string s = score_string(k3);

@@ -95,6 +95,15 @@ def test_band_cells_match_oracle(H, oracle):
                 assert out.value == c, (L, n_y, force)
 
 
+def test_band_rows_pointer_construction(H):
+    """O(L + n_y) construction of the corridor rows == exhaustive evaluation of every cell with the Float64
+    predicates of solver.jl:390/:400/:412-413, for every shape class incl. the reference's 250-gridline cap."""
+    for n_y in list(range(1, 70)) + [97, 128, 150, 200, 249, 250, 333]:
+        for L in range(1, 3 * n_y + 12, 1 if n_y < 40 else 5):
+            for force in (0, 1):
+                assert H.h_band_check(L, n_y, force) == 1, (L, n_y, force)
+
+
 def test_register_dp_matches_oracle(H, oracle):
     """dp_row_step (the code the sm_100a kernel runs per row) vs the oracle's Float64 DP, bit-exact cost/total."""
     rng = np.random.default_rng(0)
