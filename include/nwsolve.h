@@ -46,6 +46,7 @@ typedef struct nw_opts {
 
 #define NW_FLAG_GENERIC_DP 1 /* force the generic (non register-resident) DP kernel; parity cross-check */
 #define NW_FLAG_NO_TRAJ 2    /* skip trajectory enumeration (benchmarking the search itself) */
+#define NW_FLAG_PAIR_EXPAND 4 /* force the pair-testing expansion kernel (fallback for huge indices; parity cross-check) */
 
 typedef struct nw_stats {
   int32_t n_levels;

@@ -584,6 +584,7 @@ struct Search {
     E.F = L.frontier();
     E.cnt = (uint32_t*)c->cnt.ensure((size_t)L.P * 4, true);
     E.maxlen = misc + 2;
+    E.force_pairs = (o.flags & NW_FLAG_PAIR_EXPAND) ? 1 : 0;
     CK(cudaMemsetAsync(misc + 2, 0, 4, s));
     c->launches += launch_expand(false, E, s);
     uint32_t* off = (uint32_t*)c->off.ensure((size_t)L.P * 4, true);
@@ -820,6 +821,7 @@ struct Search {
     E.cnt = (uint32_t*)c->cnt.ensure((size_t)L.P * 4, true);
     E.maxlen = misc + 2;
     E.own_mod = 1;
+    E.force_pairs = (o.flags & NW_FLAG_PAIR_EXPAND) ? 1 : 0;
     CK(cudaMemsetAsync(misc + 2, 0, 4, s));
     c->launches += launch_expand(false, E, s);  // every rank counts every parent: global offsets need no collective
     uint32_t* off_glob = (uint32_t*)L.off_glob.ensure((size_t)L.P * 4);

@@ -94,7 +94,7 @@ __device__ __forceinline__ int pair_moves(const RegionDev& R, int a, int b, int 
 }
 
 template <bool EMIT>
-__global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
+__global__ void __launch_bounds__(128) k_expand_pairs(ExpandArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t s_warp_tot[4];
@@ -116,21 +116,22 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
   }
   mbar_wait(&bar, 0);
 
-  // ---- pass 1: candidates per row i ----
+  // ---- pass 1: candidates per row i (warp per row, lanes over j; counts from ballots, no shuffles) ----
   int maxlen = 0;
+  const uint32_t lt = (1u << lane) - 1u;
   for (int i = warp + 1; i <= L; i += 4) {
     const int a = seq[i - 1];
     uint32_t n = 0;
-    if (!__ldg(&A.R.ms_any[a < 0 ? -a : a])) {  // block without any partner: no move starts here (warp-uniform)
-      if (lane == 0) rowcnt[i - 1] = 0;
-      continue;
+    if (__ldg(&A.R.ms_any[a < 0 ? -a : a])) {  // a block without any partner starts no move (warp-uniform test)
+      for (int j0 = i + 1; j0 <= L; j0 += 32) {
+        const int j = j0 + lane;
+        int cdd = 0, civ = 0;
+        if (j <= L) pair_moves(A.R, a, seq[j - 1], dupok, cdd, civ);
+        const uint32_t mdd = __ballot_sync(0xffffffffu, cdd), minv = __ballot_sync(0xffffffffu, civ);
+        n += (uint32_t)(1 + dupok) * __popc(mdd) + __popc(minv);
+        if (mdd && dupok) maxlen = max(maxlen, L + (j0 + 31 - __clz(mdd) - i));
+      }
     }
-    for (int j = i + 1 + lane; j <= L; j += 32) {
-      int cdd, civ;
-      n += pair_moves(A.R, a, seq[j - 1], dupok, cdd, civ);
-      if (cdd && dupok) maxlen = max(maxlen, L + (j - i));
-    }
-    for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
     if (lane == 0) rowcnt[i - 1] = n;
   }
   __syncthreads();
@@ -153,11 +154,10 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
   __syncthreads();
   if (!EMIT) {
     if (tid == 0) A.cnt[parent] = s_warp_tot[0];
-    for (int o = 16; o; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-    if (lane == 0 && maxlen > 0) atomicMax(A.maxlen, maxlen);
+    if (lane == 0 && maxlen > 0) atomicMax(A.maxlen, maxlen);  // maxlen is warp-uniform
     return;
   }
-  // ---- pass 2: emit ----
+  // ---- pass 2: emit in discovery order (i, then j, then dup < del < inv; solver.jl:607-638) ----
   const uint32_t base = A.off[parent];
   for (int i = warp + 1; i <= L; i += 4) {
     const int a = seq[i - 1];
@@ -166,35 +166,205 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
     for (int j0 = i + 1; j0 <= L; j0 += 32) {
       const int j = j0 + lane;
       int cdd = 0, civ = 0;
-      uint32_t n = 0;
-      if (j <= L) n = pair_moves(A.R, a, seq[j - 1], dupok, cdd, civ);
-      uint32_t inc = n;
+      if (j <= L) pair_moves(A.R, a, seq[j - 1], dupok, cdd, civ);
+      const uint32_t mdd = __ballot_sync(0xffffffffu, cdd), minv = __ballot_sync(0xffffffffu, civ);
+      if ((mdd | minv) == 0) continue;
+      uint32_t pos = rowpos + (uint32_t)(1 + dupok) * __popc(mdd & lt) + __popc(minv & lt);
+      rowpos += (uint32_t)(1 + dupok) * __popc(mdd) + __popc(minv);
+      if (cdd && dupok) A.desc[pos++] = pack_desc((uint32_t)parent, i, j, KIND_DUP);
+      if (cdd) A.desc[pos++] = pack_desc((uint32_t)parent, i, j, KIND_DEL);
+      if (civ) A.desc[pos++] = pack_desc((uint32_t)parent, i, j, KIND_INV);
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------
+// k_expand: same enumeration, one THREAD per row.  Instead of testing all L-i pairs of a row, the row's partner
+// positions are assembled as bit masks over positions: occ[s][b] = positions where block b occurs with strand s
+// (built once per parent in shared memory); for row i with block a the duplication/deletion partners are
+//   OR_{b in dup_del(a)} occ[same strand][b]  |  OR_{b in invert(a)} occ[other strand][b]      (solver.jl:183-188)
+// and the inversion partners the mirror image.  Candidates of the row are the set bits above i, in bit order
+// (= j order, the discovery order of solver.jl:608).  Work per row ~ #partner blocks instead of L.  The masks
+// live in LWT registers per strand class (LWT = words covering the longest parent of the level).
+// Shared memory: seq int16[LS] | occ u32[2][n_x+1][LWT] | rowcnt u32[LS].
+// -----------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t expand_rows_smem(int LS, int n_x, int LW) {
+  return (((size_t)LS * 2 + 15) & ~(size_t)15) + (size_t)2 * (n_x + 1) * LW * 4 + (size_t)LS * 4;
+}
+
+template <int LWT>
+__device__ __forceinline__ uint32_t row_masks(const ExpandArgs& A, const int16_t* seq, const uint32_t* occ, int i, int dupok,
+                                              uint32_t (&ddm)[LWT], uint32_t (&ivm)[LWT], int& top) {
+  const int n_x = A.R.n_x, MW = A.R.MW;
+  const int a = seq[i - 1];
+  const int aa = a < 0 ? -a : a, sa = a < 0 ? 1 : 0;
+#pragma unroll
+  for (int x = 0; x < LWT; ++x) ddm[x] = ivm[x] = 0;
+  top = -1;
+  if (!__ldg(&A.R.ms_any[aa])) return 0;
+  const uint32_t* same = occ + (size_t)sa * (n_x + 1) * LWT;
+  const uint32_t* oppo = occ + (size_t)(1 - sa) * (n_x + 1) * LWT;
+  for (int w = 0; w < MW; ++w) {
+    uint32_t bits = __ldg(&A.R.ms_dd[(size_t)aa * MW + w]);  // dup_del table true (solver.jl:184)
+    while (bits) {
+      const int b = w * 32 + __ffs(bits) - 1;
+      bits &= bits - 1;
+#pragma unroll
+      for (int x = 0; x < LWT; ++x) {
+        ddm[x] |= same[(size_t)b * LWT + x];  // not flipped: dup/del
+        ivm[x] |= oppo[(size_t)b * LWT + x];  // flipped:     inversion   (:187-188)
+      }
+    }
+    bits = __ldg(&A.R.ms_inv[(size_t)aa * MW + w]);  // invert table true (:185)
+    while (bits) {
+      const int b = w * 32 + __ffs(bits) - 1;
+      bits &= bits - 1;
+#pragma unroll
+      for (int x = 0; x < LWT; ++x) {
+        ivm[x] |= same[(size_t)b * LWT + x];
+        ddm[x] |= oppo[(size_t)b * LWT + x];
+      }
+    }
+  }
+  uint32_t n = 0;
+#pragma unroll
+  for (int x = 0; x < LWT; ++x) {  // keep positions j > i only: bit index t = j-1 >= i
+    const int lo = x * 32;
+    uint32_t keep = 0xffffffffu;
+    if (lo + 32 <= i) keep = 0;
+    else if (lo < i) keep = ~((1u << (i - lo)) - 1u);
+    ddm[x] &= keep;
+    ivm[x] &= keep;
+    n += (uint32_t)(1 + dupok) * __popc(ddm[x]) + __popc(ivm[x]);
+    if (ddm[x]) top = lo + 31 - __clz(ddm[x]);
+  }
+  return n;
+}
+
+template <bool EMIT, int LWT>
+__global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_tot;
+  __shared__ int s_maxlen;
+  const int parent = blockIdx.x;
+  if (EMIT && A.own_mod > 1 && parent % A.own_mod != A.own_rem) return;  // another rank expands this parent
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = A.F.len[parent];
+  const int LS = A.F.LS;
+  const int dupok = A.F.dupok[parent];
+  const int n_x = A.R.n_x;
+  int16_t* seq = reinterpret_cast<int16_t*>(smem);
+  uint32_t* occ = reinterpret_cast<uint32_t*>(smem + (((size_t)LS * 2 + 15) & ~(size_t)15));
+  uint32_t* rowcnt = occ + (size_t)2 * (n_x + 1) * LWT;
+  const uint32_t blob_bytes = (uint32_t)LS * 2;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    s_maxlen = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, blob_bytes);
+    tma_bulk_g2s(smem, A.F.blob + (size_t)parent * A.F.pstride, blob_bytes, &bar);
+  }
+  for (int t = tid; t < 2 * (n_x + 1) * LWT; t += blockDim.x) occ[t] = 0;
+  mbar_wait(&bar, 0);
+  __syncthreads();
+  for (int t = tid; t < L; t += blockDim.x) {
+    const int v = seq[t];
+    const int b = v < 0 ? -v : v;
+    atomicOr(&occ[((size_t)(v < 0 ? 1 : 0) * (n_x + 1) + b) * LWT + (t >> 5)], 1u << (t & 31));
+  }
+  __syncthreads();
+  // ---- pass 1: candidate count of every row ----
+  int maxlen = 0;
+  for (int i = tid + 1; i <= L; i += blockDim.x) {
+    uint32_t ddm[LWT], ivm[LWT];
+    int top;
+    rowcnt[i - 1] = row_masks<LWT>(A, seq, occ, i, dupok, ddm, ivm, top);
+    if (dupok && top >= 0) maxlen = max(maxlen, L + (top + 1 - i));
+  }
+  if (!EMIT && maxlen > 0) atomicMax(&s_maxlen, maxlen);
+  __syncthreads();
+  // ---- exclusive scan of rowcnt over rows (warp 0) ----
+  if (warp == 0) {
+    uint32_t carry = 0;
+    for (int r0 = 0; r0 < L; r0 += 32) {
+      const int r = r0 + lane;
+      const uint32_t v = r < L ? rowcnt[r] : 0;
+      uint32_t inc = v;
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
       }
-      uint32_t pos = rowpos + inc - n;
-      rowpos += __shfl_sync(0xffffffffu, inc, 31);
-      if (n) {
-        int kinds[3];
-        int nk = 0;
-        if (cdd && dupok) kinds[nk++] = KIND_DUP;
-        if (cdd) kinds[nk++] = KIND_DEL;
-        if (civ) kinds[nk++] = KIND_INV;
-        for (int e = 0; e < nk; ++e) A.desc[pos++] = pack_desc((uint32_t)parent, i, j, kinds[e]);
+      if (r < L) rowcnt[r] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) s_tot = carry;
+  }
+  __syncthreads();
+  if (!EMIT) {
+    if (tid == 0) {
+      A.cnt[parent] = s_tot;
+      if (s_maxlen > 0) atomicMax(A.maxlen, s_maxlen);
+    }
+    return;
+  }
+  // ---- pass 2: emit in discovery order (i, then j, then dup < del < inv; solver.jl:607-638) ----
+  const uint32_t base = A.off[parent];
+  for (int i = tid + 1; i <= L; i += blockDim.x) {
+    uint32_t ddm[LWT], ivm[LWT];
+    int top;
+    if (row_masks<LWT>(A, seq, occ, i, dupok, ddm, ivm, top) == 0) continue;
+    uint32_t pos = base + rowcnt[i - 1];
+#pragma unroll
+    for (int x = 0; x < LWT; ++x) {
+      const uint32_t dd = ddm[x], iv = ivm[x];
+      uint32_t any = dd | iv;
+      while (any) {
+        const int bit = __ffs(any) - 1;
+        any &= any - 1;
+        const int j = x * 32 + bit + 1;
+        if ((dd >> bit) & 1u) {
+          if (dupok) A.desc[pos++] = pack_desc((uint32_t)parent, i, j, KIND_DUP);
+          A.desc[pos++] = pack_desc((uint32_t)parent, i, j, KIND_DEL);
+        }
+        if ((iv >> bit) & 1u) A.desc[pos++] = pack_desc((uint32_t)parent, i, j, KIND_INV);
       }
     }
   }
 }
 
+template <int LWT>
+static void launch_expand_rows(bool emit, const ExpandArgs& A, cudaStream_t st) {
+  const size_t sm = expand_rows_smem(A.F.LS, A.R.n_x, LWT);
+  if (emit)
+    k_expand<true, LWT><<<A.F.P, 128, sm, st>>>(A);
+  else
+    k_expand<false, LWT><<<A.F.P, 128, sm, st>>>(A);
+}
+
 int launch_expand(bool emit, const ExpandArgs& A, cudaStream_t st) {
   if (A.F.P <= 0) return 0;
+  const int LW = (A.F.LS + 31) / 32;
+  const int LWT = LW <= 1 ? 1 : LW <= 2 ? 2 : LW <= 4 ? 4 : LW <= 8 ? 8 : LW <= 16 ? 16 : 0;
+  if (LWT && !A.force_pairs && expand_rows_smem(A.F.LS, A.R.n_x, LWT) <= 160 * 1024) {
+    switch (LWT) {
+      case 1: launch_expand_rows<1>(emit, A, st); break;
+      case 2: launch_expand_rows<2>(emit, A, st); break;
+      case 4: launch_expand_rows<4>(emit, A, st); break;
+      case 8: launch_expand_rows<8>(emit, A, st); break;
+      default: launch_expand_rows<16>(emit, A, st); break;
+    }
+    return 1;
+  }
+  // very long indices / very many blocks: pair-testing kernel (the occurrence masks would not fit)
   const size_t rows = (size_t)A.F.LS * 4;
   const size_t sm = (size_t)A.F.LS * 2 + rows;
   if (emit)
-    k_expand<true><<<A.F.P, 128, sm, st>>>(A);
+    k_expand_pairs<true><<<A.F.P, 128, sm, st>>>(A);
   else
-    k_expand<false><<<A.F.P, 128, sm, st>>>(A);
+    k_expand_pairs<false><<<A.F.P, 128, sm, st>>>(A);
   return 1;
 }
 
@@ -955,8 +1125,18 @@ void init_kernel_attrs() {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const int mx = optin - 2048;  // the limit covers static + dynamic shared memory of a block
-  cudaFuncSetAttribute(k_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-  cudaFuncSetAttribute(k_expand<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_expand<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_expand<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_expand<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_expand<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_expand<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_expand<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_expand<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_expand<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_expand<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_expand<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_expand_pairs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_expand_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   cudaFuncSetAttribute(k_materialise, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   init_score_fast_attrs();
 }

@@ -69,6 +69,7 @@ struct ExpandArgs {
   // `off` then holds offsets into the rank-local candidate arrays and off_glob the offsets in global discovery order.
   int own_mod, own_rem;
   const uint32_t* off_glob;  // nullptr: local == global
+  int force_pairs;           // NW_FLAG_PAIR_EXPAND
 };
 
 // global discovery position of the candidate stored at local position `pos` (parent slot ps)

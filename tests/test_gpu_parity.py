@@ -35,10 +35,11 @@ def test_readme_known_answers(solver, testrun):
 
 @pytest.mark.parametrize("generic", [False, True])
 def test_testrun_search(solver, oracle, testrun, generic):
-    """Config 1: the bundled test run with the flags R passes (R/juliasolver.R:42-47)."""
+    """Config 1: the bundled test run with the flags R passes (R/juliasolver.R:42-47).  generic=True also forces the
+    fallback kernels (generic DP, pair-testing expansion)."""
     aln, lx, ly = testrun
     kw = dict(maxdepth=3, maxdup=2, maxwidth=1000, minreport=0.98, maxreport=1000)
-    G = solver.solve(aln, lx, ly, keep_ids=True, generic_dp=generic, **kw)
+    G = solver.solve(aln, lx, ly, keep_ids=True, generic_dp=generic, pair_expand=generic, **kw)
     O = oracle.solve(aln, lx, ly, **kw)
     assert_search_equal(G, O)
     assert G.tsv == open(os.path.join(GOLD, "testrun_oracle_res.tsv")).read()
@@ -141,6 +142,9 @@ def test_search_parity(solver, oracle, case):
     O = oracle.solve(aln, lx, ly, **kw)
     G = solver.solve(aln, lx, ly, keep_ids=True, **kw)
     assert_search_equal(G, O)
+    if case[0] in ("sd40_w50", "sd30_dup3_w7"):  # fallback expansion kernel must agree too
+        G2 = solver.solve(aln, lx, ly, keep_ids=True, pair_expand=True, **kw)
+        assert_search_equal(G2, O)
 
 
 def test_search_small_and_degenerate(solver, oracle):
