@@ -447,43 +447,53 @@ __global__ void __launch_bounds__(1024) k_scan_bsums(uint32_t* bsum, uint32_t nb
   }
   if (threadIdx.x == 0) *total_out = carry;
 }
-__global__ void __launch_bounds__(SCAN_T) k_scan_final(const uint32_t* in, uint32_t* out, uint64_t n, const uint32_t* bsum) {
+__global__ void __launch_bounds__(1024) k_scan_final(const uint32_t* in, uint32_t* out, uint64_t n, const uint32_t* bsum) {
   __shared__ uint32_t sh[33];
-  const uint64_t b0 = (uint64_t)blockIdx.x * SCAN_B + (uint64_t)threadIdx.x * SCAN_I;
-  uint32_t v[SCAN_I];
-  uint32_t s = 0;
+  const uint64_t b0 = (uint64_t)blockIdx.x * SCAN_B + (uint64_t)threadIdx.x * 4;  // one coalesced 16-B load per thread
+  uint32_t v[4] = {0, 0, 0, 0};
+  if (b0 + 3 < n) {
+    const uint4 q = *reinterpret_cast<const uint4*>(in + b0);
+    v[0] = q.x;
+    v[1] = q.y;
+    v[2] = q.z;
+    v[3] = q.w;
+  } else {
 #pragma unroll
-  for (int k = 0; k < SCAN_I; ++k) {
-    v[k] = (b0 + k < n) ? in[b0 + k] : 0;
-    s += v[k];
+    for (int k = 0; k < 4; ++k)
+      if (b0 + k < n) v[k] = in[b0 + k];
   }
   uint32_t tot;
-  uint32_t e = block_excl_scan(s, sh, tot) + bsum[blockIdx.x];
+  uint32_t e = block_excl_scan(v[0] + v[1] + v[2] + v[3], sh, tot) + bsum[blockIdx.x];
+  if (b0 + 3 < n) {
+    uint4 o;
+    o.x = e;
+    o.y = e + v[0];
+    o.z = e + v[0] + v[1];
+    o.w = e + v[0] + v[1] + v[2];
+    *reinterpret_cast<uint4*>(out + b0) = o;
+  } else {
 #pragma unroll
-  for (int k = 0; k < SCAN_I; ++k) {
-    if (b0 + k < n) out[b0 + k] = e;
-    e += v[k];
+    for (int k = 0; k < 4; ++k) {
+      if (b0 + k < n) out[b0 + k] = e;
+      e += v[k];
+    }
   }
 }
 
-// small inputs (the common case in regionfile mode): one CTA, one launch
-constexpr uint32_t SCAN_SMALL = 65536;
+// small inputs (the common case in regionfile mode): one CTA, one launch, coalesced tiles of 1024
+constexpr uint32_t SCAN_SMALL = 8192;
 __global__ void __launch_bounds__(1024) k_scan_small(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* total_out) {
   __shared__ uint32_t sh[33];
-  const uint32_t per = (n + 1023) / 1024;
-  const uint32_t b0 = threadIdx.x * per;
-  uint32_t s = 0;
-  for (uint32_t k = 0; k < per; ++k)
-    if (b0 + k < n) s += in[b0 + k];
-  uint32_t tot;
-  uint32_t e = block_excl_scan(s, sh, tot);
-  for (uint32_t k = 0; k < per; ++k)
-    if (b0 + k < n) {
-      const uint32_t v = in[b0 + k];
-      out[b0 + k] = e;
-      e += v;
-    }
-  if (threadIdx.x == 0) *total_out = tot;
+  uint32_t carry = 0;
+  for (uint32_t t0 = 0; t0 < n; t0 += 1024) {
+    const uint32_t idx = t0 + threadIdx.x;
+    const uint32_t v = idx < n ? in[idx] : 0;
+    uint32_t tot;
+    const uint32_t e = block_excl_scan(v, sh, tot);
+    if (idx < n) out[idx] = carry + e;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) *total_out = carry;
 }
 
 int launch_scan(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* bsum_scratch, uint32_t* total_out,
@@ -499,7 +509,7 @@ int launch_scan(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* bsum_sc
   const uint32_t nb = (uint32_t)((n + SCAN_B - 1) / SCAN_B);
   k_scan_partial<<<nb, SCAN_T, 0, st>>>(in, n, bsum_scratch);
   k_scan_bsums<<<1, 1024, 0, st>>>(bsum_scratch, nb, total_out);
-  k_scan_final<<<nb, SCAN_T, 0, st>>>(in, out, n, bsum_scratch);
+  k_scan_final<<<nb, 1024, 0, st>>>(in, out, n, bsum_scratch);
   return 3;
 }
 uint64_t scan_scratch_items(uint64_t n) { return (n + SCAN_B - 1) / SCAN_B + 1; }
