@@ -25,6 +25,7 @@ extern "C" {
 #define NW_ERR_CUDA (-4)   /* CUDA runtime error or no device */
 #define NW_ERR_RANGE (-5)  /* lengths not integral / exceed the int32 DP range */
 #define NW_ERR_NOMEM (-6)  /* search does not fit device memory */
+#define NW_ERR_COLLISION (-7) /* NW_FLAG_VERIFY_DEDUP found two different indices with one fingerprint */
 
 #define NW_MOVE_DUP 0 /* MoveKind, solver.jl:34 */
 #define NW_MOVE_DEL 1
@@ -47,6 +48,9 @@ typedef struct nw_opts {
 #define NW_FLAG_GENERIC_DP 1 /* force the generic (non register-resident) DP kernel; parity cross-check */
 #define NW_FLAG_NO_TRAJ 2    /* skip trajectory enumeration (benchmarking the search itself) */
 #define NW_FLAG_PAIR_EXPAND 4 /* force the pair-testing expansion kernel (fallback for huge indices; parity cross-check) */
+#define NW_FLAG_VERIFY_DEDUP 8 /* compare every deduplicated candidate element-wise with the index it was merged into:
+                                  turns the 124-bit fingerprint dedup into a verified exact one (NW_ERR_COLLISION) */
+#define NW_FLAG_DEBUG_WEAK_FP 16 /* TESTS ONLY: truncate fingerprints to 8 bits so that collisions occur */
 
 typedef struct nw_stats {
   int32_t n_levels;

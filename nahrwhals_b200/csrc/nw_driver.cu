@@ -572,6 +572,31 @@ struct Search {
     }
   }
 
+  // NW_FLAG_VERIFY_DEDUP: element-wise comparison of every merged candidate of level d with its owner
+  void verify_level(int d, const ExpandArgs& E, const uint32_t* is_new, const uint32_t* owner, uint32_t G) {
+    cudaStream_t s = c->stream;
+    int32_t* misc = (int32_t*)c->misc.p;
+    VerifyTable V{};
+    V.n_levels = d + 1;
+    for (int l = 0; l <= d; ++l) {
+      const Level& fl = lv[l == 0 ? 1 : l];  // the root pseudo-candidate lives in level 1's frontier
+      V.gbase[l] = lv[l].gbase;
+      V.desc[l] = lv[l].desc.as<uint64_t>();
+      V.blob[l] = fl.fblob.as<unsigned char>();
+      V.pstride[l] = fl.pstride;
+      V.len[l] = fl.flen.as<int32_t>();
+    }
+    V.gbase[d + 1] = lv[d].gbase + G;
+    CK(cudaMemsetAsync(misc + 12, 0, 4, s));
+    c->launches += launch_verify_dups(E, V, is_new, owner, G, (unsigned int*)(misc + 12), s);
+    d2h(c, pin_u32(), misc, 64);
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (pin_u32()[12])
+      fail(NW_ERR_COLLISION, std::to_string(pin_u32()[12]) + " candidates of level " + std::to_string(d) +
+                                 " were merged into a different index (fingerprint collision)");
+  }
+
   // one BFS level: expand lv[d]'s frontier.  Returns false when the frontier is empty.
   bool run_level(int d) {
     cudaStream_t s = c->stream;
@@ -585,6 +610,7 @@ struct Search {
     E.cnt = (uint32_t*)c->cnt.ensure((size_t)L.P * 4, true);
     E.maxlen = misc + 2;
     E.force_pairs = (o.flags & NW_FLAG_PAIR_EXPAND) ? 1 : 0;
+    E.weak_fp = (o.flags & NW_FLAG_DEBUG_WEAK_FP) ? 1 : 0;
     CK(cudaMemsetAsync(misc + 2, 0, 4, s));
     c->launches += launch_expand(false, E, s);
     uint32_t* off = (uint32_t*)c->off.ensure((size_t)L.P * 4, true);
@@ -659,6 +685,7 @@ struct Search {
     A.hist = (uint32_t*)c->hist.ensure(HIST_N * 4);
     CK(cudaMemsetAsync(A.hist, 0, HIST_N * 4, s));
     c->launches += launch_assign(A, s);
+    if (o.flags & NW_FLAG_VERIFY_DEDUP) verify_level(d, E, is_new, owner, G);
     uint32_t* hist_h = pin_u32() + 64;
     d2h(c, hist_h, A.hist, HIST_N * 4);
     CK(cudaStreamSynchronize(s));
@@ -760,7 +787,7 @@ struct Search {
       }
       CK(cudaEventRecord(b, s));
       // the frontier blob of level d is no longer needed once level d+1 is materialised (ids are kept)
-      lv[d].fblob.release();
+      if (!(o.flags & NW_FLAG_VERIFY_DEDUP)) lv[d].fblob.release();  // the verifier re-reads old frontiers
       if (d < D && (!any || lv[d + 1].P == 0)) {
         // solver.jl keeps looping over empty frontiers; nothing more can be generated
         for (int e = d + 1; e <= D; ++e) {

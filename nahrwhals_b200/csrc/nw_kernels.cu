@@ -382,7 +382,11 @@ __global__ void __launch_bounds__(256) k_hash_insert(ExpandArgs A, uint32_t G) {
   const unsigned char* blob = A.F.blob + (size_t)ps * A.F.pstride;
   const U4* Ft = reinterpret_cast<const U4*>(blob + (size_t)A.F.LS * 2);
   const U4* Gt = Ft + (A.F.LS + 1);
-  const U4 f = child_fingerprint(Ft, Gt, A.pw, A.F.len[ps], desc_kind(d), desc_i(d), desc_j(d));
+  U4 f = child_fingerprint(Ft, Gt, A.pw, A.F.len[ps], desc_kind(d), desc_i(d), desc_j(d));
+  if (A.weak_fp) {  // tests only: provoke collisions to exercise the verifier
+    f.v[0] &= 0xffu;
+    f.v[1] = f.v[2] = f.v[3] = 0;
+  }
   A.slot[pos] = table_insert(A.table, A.tmask, fp_key0(f), fp_key1(f), (uint64_t)cand_gpos(A, pos, ps));
 }
 int launch_hash_insert(const ExpandArgs& A, uint32_t G, cudaStream_t st) {
@@ -988,6 +992,41 @@ int launch_id_compact(const int32_t* k3, const int32_t* cost, const int32_t* tot
                       const uint32_t* flag, const uint32_t* pre, void* out, cudaStream_t st) {
   if (!n) return 0;
   k_id_compact<<<(n + 255) / 256, 256, 0, st>>>(k3, cost, total, id_base, n, flag, pre, (IdRec*)out);
+  return 1;
+}
+
+// =====================================================================================================
+// dedup verifier (NW_FLAG_VERIFY_DEDUP): every candidate that was merged into an already known index is compared
+// element by element with that index, both re-materialised through their index maps.  Equal sequences always have
+// equal fingerprints, so a clean run proves the dedup of this search exact (solver.jl:535 semantics).
+// =====================================================================================================
+__global__ void k_verify_dups(ExpandArgs A, VerifyTable V, const uint32_t* is_new, const uint32_t* owner, uint32_t G,
+                              unsigned int* mismatches) {
+  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= G || is_new[pos]) return;
+  const uint64_t d = A.desc[pos];
+  const uint32_t ps = desc_parent(d);
+  const int16_t* seq = reinterpret_cast<const int16_t*>(A.F.blob + (size_t)ps * A.F.pstride);
+  const int kind = desc_kind(d), p = desc_i(d), q = desc_j(d);
+  const int Lc = child_len(A.F.len[ps], kind, p, q);
+  // locate the owner: level, position inside the level, descriptor, parent sequence
+  const uint32_t g = owner[pos];
+  int l = 0;
+  while (l + 1 < V.n_levels && g >= V.gbase[l + 1]) ++l;
+  const uint32_t opos = g - V.gbase[l];
+  const uint64_t od = V.desc[l][opos];
+  const uint32_t ops = desc_parent(od);
+  const int16_t* oseq = reinterpret_cast<const int16_t*>(V.blob[l] + (size_t)ops * V.pstride[l]);
+  const int okind = desc_kind(od), op = desc_i(od), oq = desc_j(od);
+  const int oL = child_len(V.len[l][ops], okind, op, oq);
+  bool same = oL == Lc;
+  for (int t = 1; same && t <= Lc; ++t) same = child_elem(seq, kind, p, q, t) == child_elem(oseq, okind, op, oq, t);
+  if (!same) atomicAdd(mismatches, 1u);
+}
+int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t* is_new, const uint32_t* owner, uint32_t G,
+                       unsigned int* mismatches, cudaStream_t st) {
+  if (!G) return 0;
+  k_verify_dups<<<(G + 255) / 256, 256, 0, st>>>(A, V, is_new, owner, G, mismatches);
   return 1;
 }
 

@@ -70,12 +70,23 @@ struct ExpandArgs {
   int own_mod, own_rem;
   const uint32_t* off_glob;  // nullptr: local == global
   int force_pairs;           // NW_FLAG_PAIR_EXPAND
+  int weak_fp;               // NW_FLAG_DEBUG_WEAK_FP (tests only)
 };
 
 // global discovery position of the candidate stored at local position `pos` (parent slot ps)
 __device__ __forceinline__ uint32_t cand_gpos(const ExpandArgs& A, uint32_t pos, uint32_t ps) {
   return A.off_glob ? A.gbase + A.off_glob[ps] + (pos - A.off[ps]) : A.gbase + pos;
 }
+
+// Everything needed to re-materialise the index a candidate of any finished level stands for (dedup verifier)
+struct VerifyTable {
+  int n_levels;  // levels 0..n_levels-1 are valid; level 0 is the root pseudo-level
+  uint32_t gbase[MAX_LEVELS + 1];
+  const uint64_t* desc[MAX_LEVELS];
+  const unsigned char* blob[MAX_LEVELS];
+  uint32_t pstride[MAX_LEVELS];
+  const int32_t* len[MAX_LEVELS];
+};
 
 // record exchanged between ranks for every locally-first candidate of a level (40 bytes)
 struct DistRec {

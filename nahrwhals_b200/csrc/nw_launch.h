@@ -18,6 +18,8 @@ int launch_scan(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* bsum_sc
 uint64_t scan_scratch_items(uint64_t n);
 int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* is_new, uint32_t* owner, cudaStream_t st);
 int launch_assign(const AssignArgs& A, cudaStream_t st);
+int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t* is_new, const uint32_t* owner, uint32_t G,
+                       unsigned int* mismatches, cudaStream_t st);
 int launch_bucket_scatter(const uint16_t* new_len, uint32_t n_new, int n_y, int force, const uint32_t* bstart,
                           uint32_t* cursor, uint32_t* work, cudaStream_t st);
 int generic_threads();

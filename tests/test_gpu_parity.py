@@ -220,3 +220,25 @@ def test_solve_batch_regions(oracle):
     for (aln, lx, ly), R in zip(regions, res):
         O = oracle.solve(aln, lx, ly, full=False, **kw)
         assert R.tsv == O.tsv and R.scored == [int(v) for v in O.scored]
+
+
+def test_dedup_verifier(solver, oracle):
+    """NW_FLAG_VERIFY_DEDUP re-materialises every merged candidate and compares it element-wise with its owner: a
+    clean run proves the fingerprint dedup exact.  With fingerprints truncated to 8 bits (test-only flag) collisions
+    are certain and the verifier must report NW_ERR_COLLISION instead of returning a wrong search."""
+    from nahrwhals_b200._lib import NwError
+    mat, lx, ly, _ = sdgrid(n_x=64, families=[6, 5, 5, 4], seed=1, chain_depth=3)
+    aln = to_solver_inputs(mat)
+    kw = dict(maxdepth=3, maxdup=2, minreport=0.98, maxreport=1000)
+    O = oracle.solve(aln, lx, ly, **kw)
+    G = solver.solve(aln, lx, ly, keep_ids=True, verify_dedup=True, **kw)
+    assert_search_equal(G, O)
+    with pytest.raises(NwError) as e:
+        solver.solve(aln, lx, ly, verify_dedup=True, debug_weak_fp=True, **kw)
+    assert e.value.code == -7 and "collision" in str(e.value)
+    # without the verifier the truncated fingerprints silently merge different indices (fewer unique ids)
+    W = solver.solve(aln, lx, ly, debug_weak_fp=True, **kw)
+    assert sum(W.scored) < int(O.scored.sum())
+    # and the context is still usable afterwards
+    G2 = solver.solve(aln, lx, ly, **kw)
+    assert G2.tsv == O.tsv
