@@ -242,3 +242,66 @@ def test_dedup_verifier(solver, oracle):
     # and the context is still usable afterwards
     G2 = solver.solve(aln, lx, ly, **kw)
     assert G2.tsv == O.tsv
+
+
+def test_edge_shapes_and_options(solver, oracle):
+    """Shapes at the reference's size envelope (x + y grid lines = 250, R/nahrwhals.R:55), bp lengths with gcd 1 near
+    the 5 Mb window size, single-block inputs, depth 1, report limits 0 / none, minreport above 1."""
+    rng = np.random.default_rng(77)
+    # 130 x 120 blocks, realistic sparse structure, lengths without a common factor
+    mat, lx, ly, _ = sdgrid(130, [5, 4, 4, 3, 3, 2], seed=9, chain_depth=2, len_tol=0.1)
+    lx = lx // 10 + rng.integers(1, 97, lx.shape)          # ~1e3..2e4 bp, gcd 1
+    fam_fix = {}
+    n_y = mat.shape[0]
+    ly = np.array([lx[np.nonzero(mat[k])[0][0]] if np.any(mat[k]) else 1000 + k for k in range(n_y)], dtype=np.int64)
+    mat = np.sign(mat) * lx[None, :]
+    aln = to_solver_inputs(mat)
+    for kw in (dict(maxdepth=2, maxdup=2, maxwidth=200, minreport=0.98, maxreport=1000),
+               dict(maxdepth=1, maxdup=3, minreport=0.0, maxreport=None),
+               dict(maxdepth=2, maxdup=2, maxwidth=50, minreport=0.5, maxreport=0),
+               dict(maxdepth=2, maxdup=2, maxwidth=50, minreport=1.5, maxreport=10)):
+        O = oracle.solve(aln, lx, ly, **kw)
+        G = solver.solve(aln, lx, ly, keep_ids=True, **kw)
+        assert_search_equal(G, O)
+    # big bp lengths (5 Mb window, 1 bp resolution): int32 DP range after gcd reduction
+    big_lx = np.array([1_234_567, 999_983, 1_500_001, 765_432], dtype=np.int64)
+    big = np.array([[1, 0, 0, 0], [0, 1, 0, -1], [0, -1, 1, 0], [0, 0, 0, 1]], dtype=np.int64) * big_lx[None, :]
+    big_ly = np.array([1_234_567, 999_983, 1_500_001, 765_432], dtype=np.int64)
+    O = oracle.solve(to_solver_inputs(big), big_lx, big_ly, maxdepth=3, maxdup=2, minreport=0.0)
+    G = solver.solve(to_solver_inputs(big), big_lx, big_ly, keep_ids=True, maxdepth=3, maxdup=2, minreport=0.0)
+    assert_search_equal(G, O)
+    # one block: no pair, only the reference line with its trailing tab
+    one = np.array([[1]], dtype=np.int8)
+    O = oracle.solve(one, [5000], [5000], maxdepth=3, maxdup=2, minreport=0.0)
+    G = solver.solve(one, [5000], [5000], keep_ids=True, maxdepth=3, maxdup=2, minreport=0.0)
+    assert_search_equal(G, O)
+    assert G.tsv == "100.0\t0\t\n"
+
+
+def test_error_behaviour(solver, tmp_path):
+    """Failures are loud and leave no output file (R/juliasolver.R:56-59 only looks for the file)."""
+    import nahrwhals_b200 as nb
+    from nahrwhals_b200._lib import NwError
+    m = tmp_path / "m.tsv"
+    l = tmp_path / "l.tsv"
+    out = tmp_path / "out.tsv"
+    m.write_text("10\t0\n0\t10\n")
+    l.write_text("10\t10\n10\t10\t10\n")  # x lengths do not match the matrix
+    with pytest.raises(NwError):
+        solver.solve_files(m, l, out)
+    assert not out.exists() and not (tmp_path / "out.tsv.tmp").exists()
+    l.write_text("10\t10\n10.5\t10\n")  # non-integral bp length
+    with pytest.raises(NwError):
+        solver.solve_files(m, l, out)
+    assert not out.exists()
+    with pytest.raises(NwError):
+        solver.solve_files(tmp_path / "missing.tsv", l, out)
+    with pytest.raises(NwError):
+        solver.solve(np.ones((2, 2), np.int8), [1, 1], [1, 1], maxdepth=0)
+    with pytest.raises(NwError):  # lengths beyond the int32 DP range
+        solver.solve(np.ones((2, 2), np.int8), [2**40 + 1, 2**40 + 3], [2**40 + 1, 3], maxdepth=3)
+    # the context survives errors
+    l.write_text("10\t10\n10\t10\n")
+    solver.solve_files(m, l, out, maxdepth=2, minreport=0.0)
+    assert out.read_text().startswith("100.0\t0\t\n")
+    assert nb.main(["-d", "2", str(tmp_path / "missing.tsv"), str(l), str(tmp_path / "o2.tsv")]) == 1
