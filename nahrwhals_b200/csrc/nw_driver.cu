@@ -487,6 +487,7 @@ struct Search {
   int dist_k3_min = 0;
   int dist_maxlen = 0;
   uint32_t dist_edges = 0;
+  uint32_t edge_cap_hint = 0, id_cap_hint = 0;
   explicit Search(nw_ctx* ctx, const nw_opts& opts) : c(ctx), o(opts) {}
   ~Search() {
     if (ev0) cudaEventDestroy(ev0);
@@ -1095,72 +1096,66 @@ struct Search {
     cudaStream_t s = c->stream;
     int32_t* misc = (int32_t*)c->misc.p;
     const int nl = (int)lv.size();
-    std::vector<uint32_t> cnt(nl, 0);
-    uint32_t total = 0;
-    // pass A: counts per level (flags + scan are recomputed in pass B; both are cheap streaming kernels)
-    for (int pass = 0; pass < 2; ++pass) {
-      uint32_t at = 0;
-      if (pass == 1) c->edgebuf.ensure((size_t)std::max<uint32_t>(total, 1) * sizeof(EdgeRec), true);
+    uint32_t cap = std::max<uint32_t>(edge_cap_hint, 1u << 16);
+    for (;;) {  // one pass; repeated with a larger buffer only if the append counter overflowed the capacity
+      EdgeRec* buf = (EdgeRec*)c->edgebuf.ensure((size_t)cap * sizeof(EdgeRec));
+      CK(cudaMemsetAsync(misc + 8, 0, 4, s));
       for (int l = 1; l < nl; ++l) {
         const Level& L = lv[l];
-        if (L.G == 0 || (pass == 1 && cnt[l] == 0)) continue;
-        uint32_t* eflag = (uint32_t*)c->is_new.ensure((size_t)L.G * 4, true);
-        uint32_t* epre = (uint32_t*)c->newrank.ensure((size_t)L.G * 4, true);
-        uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.G) * 4, true);
-        c->launches += launch_edge_flags(L.cand_id.as<int32_t>(), L.G, needed, eflag, l, o.maxdepth, s);
-        c->launches += launch_scan(eflag, epre, L.G, bsum, (uint32_t*)(misc + 8), s);
-        if (pass == 0) {
-          d2h(c, pin_u32(), misc, 64);
-          CK(cudaStreamSynchronize(s));
-          cnt[l] = pin_u32()[8];
-          total += cnt[l];
-        } else {
-          c->launches += launch_edge_compact(L.cand_id.as<int32_t>(), L.desc.as<uint64_t>(), L.fid.as<int32_t>(), L.G,
-                                             eflag, epre, L.gbase, world > 1 ? L.off_loc.as<uint32_t>() : nullptr,
-                                             world > 1 ? L.off_glob.as<uint32_t>() : nullptr,
-                                             c->edgebuf.as<EdgeRec>() + at, s);
-          at += cnt[l];
-        }
+        c->launches += launch_edge_append(L.cand_id.as<int32_t>(), L.desc.as<uint64_t>(), L.fid.as<int32_t>(), L.G, needed,
+                                          l, o.maxdepth, L.gbase, world > 1 ? L.off_loc.as<uint32_t>() : nullptr,
+                                          world > 1 ? L.off_glob.as<uint32_t>() : nullptr, buf, cap,
+                                          (uint32_t*)(misc + 8), s);
       }
+      d2h(c, pin_u32(), misc, 64);
+      CK(cudaStreamSynchronize(s));
+      CK(cudaGetLastError());
+      const uint32_t n = pin_u32()[8];
+      if (n <= cap) {
+        edge_cap_hint = std::max(edge_cap_hint, n);
+        return n;
+      }
+      cap = n + n / 8;
     }
-    CK(cudaStreamSynchronize(s));
-    CK(cudaGetLastError());
-    return total;
   }
   // phase 4: host graph of the needed ids from the edge records of all ranks (sorted into discovery order)
   void build_nodes(const uint8_t* needed, std::vector<EdgeRec>& edges) {
     cudaStream_t s = c->stream;
     int32_t* misc = (int32_t*)c->misc.p;
     const int nl = (int)lv.size();
-    if (world > 1)
-      std::sort(edges.begin(), edges.end(), [](const EdgeRec& a, const EdgeRec& b) { return a.gpos < b.gpos; });
+    std::sort(edges.begin(), edges.end(), [](const EdgeRec& a, const EdgeRec& b) { return a.gpos < b.gpos; });
     nodes.clear();
     nodes[1] = Node{root_k3, root_cost, root_total, {}};
     for (const EdgeRec& e : edges) nodes[e.child].in.push_back(e);
-    for (int l = 1; l < nl; ++l) {
-      const Level& L = lv[l];
-      if (!L.n_new) continue;
-      uint32_t* iflag = (uint32_t*)c->is_new.ensure((size_t)L.n_new * 4, true);
-      uint32_t* ipre = (uint32_t*)c->newrank.ensure((size_t)L.n_new * 4, true);
-      uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.n_new) * 4, true);
-      c->launches += launch_id_flags(needed, L.id_base, L.n_new, iflag, s);
-      c->launches += launch_scan(iflag, ipre, L.n_new, bsum, (uint32_t*)(misc + 9), s);
+    uint32_t cap = std::max<uint32_t>(id_cap_hint, 1u << 14);
+    std::vector<IdRec> hi;
+    for (;;) {
+      IdRec* buf = (IdRec*)c->keys.ensure((size_t)cap * sizeof(IdRec));
+      CK(cudaMemsetAsync(misc + 9, 0, 4, s));
+      for (int l = 1; l < nl; ++l) {
+        const Level& L = lv[l];
+        c->launches += launch_id_append(L.k3.as<int32_t>(), L.cost.as<int32_t>(), L.total.as<int32_t>(), L.id_base, L.n_new,
+                                        needed, buf, cap, (uint32_t*)(misc + 9), s);
+      }
       d2h(c, pin_u32(), misc, 64);
       CK(cudaStreamSynchronize(s));
-      const uint32_t ni = pin_u32()[9];
-      if (!ni) continue;
-      IdRec* d_i = (IdRec*)c->keys.ensure((size_t)ni * sizeof(IdRec), true);
-      c->launches += launch_id_compact(L.k3.as<int32_t>(), L.cost.as<int32_t>(), L.total.as<int32_t>(), L.id_base,
-                                       L.n_new, iflag, ipre, d_i, s);
-      std::vector<IdRec> hi(ni);
-      d2h(c, hi.data(), d_i, (size_t)ni * sizeof(IdRec));
-      CK(cudaStreamSynchronize(s));
-      for (const IdRec& r : hi) {
-        Node& nd = nodes[r.id];
-        nd.k3 = r.k3;
-        nd.cost = r.cost;
-        nd.total = r.total;
+      const uint32_t n = pin_u32()[9];
+      if (n <= cap) {
+        id_cap_hint = std::max(id_cap_hint, n);
+        hi.resize(n);
+        if (n) {
+          d2h(c, hi.data(), buf, (size_t)n * sizeof(IdRec));
+          CK(cudaStreamSynchronize(s));
+        }
+        break;
       }
+      cap = n + n / 8;
+    }
+    for (const IdRec& r : hi) {
+      Node& nd = nodes[r.id];
+      nd.k3 = r.k3;
+      nd.cost = r.cost;
+      nd.total = r.total;
     }
     CK(cudaGetLastError());
   }
@@ -1278,11 +1273,12 @@ struct Search {
       cudaStream_t s = c->stream;
       uint32_t* hist = (uint32_t*)c->keys.ensure((size_t)100002 * 4, true);
       CK(cudaMemsetAsync(hist, 0, (size_t)100002 * 4, s));
-      for (size_t l = 1; l < lv.size(); ++l) c->launches += launch_k3_hist(lv[l].k3.as<int32_t>(), lv[l].n_new, hist, s);
-      std::vector<uint32_t> hh(100002);
-      d2h(c, hh.data(), hist, hh.size() * 4);
+      for (size_t l = 1; l < lv.size(); ++l)
+        c->launches += launch_k3_hist(lv[l].k3.as<int32_t>(), lv[l].n_new, k3_min, hist, s);
+      std::vector<uint32_t> hh(100002, 0);
+      if (k3_min <= 100000) d2h(c, hh.data() + k3_min, hist + k3_min, (size_t)(100001 - k3_min) * 4);  // bins below are empty
       CK(cudaStreamSynchronize(s));
-      if (root_k3 >= 0) hh[root_k3] += 1;
+      if (root_k3 >= 0 && root_k3 >= k3_min) hh[root_k3] += 1;
       int64_t cum = 0;
       for (int k = 100000; k >= 0; --k) {
         if (cum + hh[k] >= o.maxreport) {

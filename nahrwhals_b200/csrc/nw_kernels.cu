@@ -889,10 +889,11 @@ __global__ void k_tie_flags(const int32_t* k3, uint32_t n, int k3_star, uint32_t
   if (r < n) flag[r] = k3[r] == k3_star ? 1u : 0u;
 }
 // histogram of k3 over the fresh ids of a level (warp-aggregated atomics; k3 == 0 is a very hot bin)
-__global__ void k_k3_hist(const int32_t* k3, uint32_t n, uint32_t* hist) {
+__global__ void k_k3_hist(const int32_t* k3, uint32_t n, int k3_floor, uint32_t* hist) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   int key = -1;
   if (r < n) key = k3[r];
+  if (key < k3_floor) key = -1;  // ids below the minreport threshold can never be reported: no atomics for them
   const uint32_t peers = __match_any_sync(0xffffffffu, key);
   if (key >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
 }
@@ -947,6 +948,67 @@ __global__ void k_id_compact(const int32_t* k3, const int32_t* cost, const int32
   out[pre[r]] = o;
 }
 
+// single-pass extraction: records are appended through a warp-aggregated atomic counter (order restored on the
+// host by sorting on gpos / id); *counter keeps counting past `cap` so the host can detect an overflow and retry.
+__device__ __forceinline__ uint32_t warp_append(bool take, uint32_t* counter) {
+  const uint32_t m = __ballot_sync(0xffffffffu, take);
+  if (!m) return 0;
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+}
+__global__ void k_edge_append(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
+                              const uint8_t* needed, int lvl, int maxdepth, uint32_t gbase, const uint32_t* off_loc,
+                              const uint32_t* off_glob, EdgeRec* out, uint32_t cap, uint32_t* counter) {
+  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+  bool take = false;
+  int32_t child = 0;
+  if (pos < G) {
+    child = cand_id[pos];
+    const int v = needed[child];
+    take = v && lvl + v <= maxdepth + 2;
+  }
+  const uint32_t at = warp_append(take, counter);
+  if (!take || at >= cap) return;
+  const uint64_t d = desc[pos];
+  const uint32_t ps = desc_parent(d);
+  EdgeRec e;
+  e.child = child;
+  e.parent = front_id[ps];
+  e.move = (uint32_t)desc_kind(d) | ((uint32_t)desc_i(d) << 2) | ((uint32_t)desc_j(d) << 17);
+  e.gpos = off_glob ? gbase + off_glob[ps] + (pos - off_loc[ps]) : gbase + pos;
+  out[at] = e;
+}
+__global__ void k_id_append(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,
+                            const uint8_t* needed, IdRec* out, uint32_t cap, uint32_t* counter) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool take = r < n && needed[id_base + r];
+  const uint32_t at = warp_append(take, counter);
+  if (!take || at >= cap) return;
+  IdRec o;
+  o.id = id_base + (int32_t)r;
+  o.k3 = k3[r];
+  o.cost = cost[r];
+  o.total = total[r];
+  out[at] = o;
+}
+int launch_edge_append(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
+                       const uint8_t* needed, int lvl, int maxdepth, uint32_t gbase, const uint32_t* off_loc,
+                       const uint32_t* off_glob, void* out, uint32_t cap, uint32_t* counter, cudaStream_t st) {
+  if (!G) return 0;
+  k_edge_append<<<(G + 255) / 256, 256, 0, st>>>(cand_id, desc, front_id, G, needed, lvl, maxdepth, gbase, off_loc,
+                                                off_glob, (EdgeRec*)out, cap, counter);
+  return 1;
+}
+int launch_id_append(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,
+                     const uint8_t* needed, void* out, uint32_t cap, uint32_t* counter, cudaStream_t st) {
+  if (!n) return 0;
+  k_id_append<<<(n + 255) / 256, 256, 0, st>>>(k3, cost, total, id_base, n, needed, (IdRec*)out, cap, counter);
+  return 1;
+}
+
 int launch_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, int k3_min, int k3_star, uint32_t quota,
                       const uint32_t* tie_rank, uint8_t* needed, cudaStream_t st) {
   if (!n) return 0;
@@ -958,9 +1020,9 @@ int launch_tie_flags(const int32_t* k3, uint32_t n, int k3_star, uint32_t* flag,
   k_tie_flags<<<(n + 255) / 256, 256, 0, st>>>(k3, n, k3_star, flag);
   return 1;
 }
-int launch_k3_hist(const int32_t* k3, uint32_t n, uint32_t* hist, cudaStream_t st) {
+int launch_k3_hist(const int32_t* k3, uint32_t n, int k3_floor, uint32_t* hist, cudaStream_t st) {
   if (!n) return 0;
-  k_k3_hist<<<(n + 255) / 256, 256, 0, st>>>(k3, n, hist);
+  k_k3_hist<<<(n + 255) / 256, 256, 0, st>>>(k3, n, k3_floor, hist);
   return 1;
 }
 int launch_mark_parents(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,

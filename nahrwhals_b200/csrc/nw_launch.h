@@ -34,7 +34,12 @@ int launch_materialise(const MaterialiseArgs& A, cudaStream_t st);
 int launch_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, int k3_min, int k3_star, uint32_t quota,
                       const uint32_t* tie_rank, uint8_t* needed, cudaStream_t st);
 int launch_tie_flags(const int32_t* k3, uint32_t n, int k3_star, uint32_t* flag, cudaStream_t st);
-int launch_k3_hist(const int32_t* k3, uint32_t n, uint32_t* hist, cudaStream_t st);
+int launch_k3_hist(const int32_t* k3, uint32_t n, int k3_floor, uint32_t* hist, cudaStream_t st);
+int launch_edge_append(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
+                       const uint8_t* needed, int lvl, int maxdepth, uint32_t gbase, const uint32_t* off_loc,
+                       const uint32_t* off_glob, void* out, uint32_t cap, uint32_t* counter, cudaStream_t st);
+int launch_id_append(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,
+                     const uint8_t* needed, void* out, uint32_t cap, uint32_t* counter, cudaStream_t st);
 int launch_mark_parents(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
                         uint8_t* needed, int pass, int lvl, int maxdepth, cudaStream_t st);
 int launch_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* needed, uint32_t* flag, int lvl, int maxdepth,
