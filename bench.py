@@ -63,6 +63,8 @@ class ClockSampler:
         self.p = None
 
     def start(self):
+        if int(os.environ.get("RANK", "0")) != 0:  # one sampler per job: nvidia-smi polling competes with the ranks
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", self.idx, "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
@@ -78,7 +80,7 @@ class ClockSampler:
 
     def stop(self):
         if not self.p:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["not sampled on this rank / nvidia-smi unavailable"])
         time.sleep(0.25)
         self.p.terminate()
         try:
@@ -184,8 +186,10 @@ def run_regions(args, rank, world, local):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     regs = make_regions(args.regions, seed=rank)
-    solvers = [nb.Solver(local) for _ in range(args.contexts)]
-    nb.solve_batch(solvers, regs[:min(len(regs), 4 * args.contexts)], **FLAGS)  # warm-up: pools, band tables
+    # contexts per GPU: each one is a host thread issuing launches; do not oversubscribe the host cores
+    nctx = max(2, min(args.contexts, (os.cpu_count() or 8) // max(world, 1)))
+    solvers = [nb.Solver(local) for _ in range(nctx)]
+    nb.solve_batch(solvers, regs[:min(len(regs), 4 * nctx)], **FLAGS)  # warm-up: pools, band tables
     sampler = ClockSampler(local)
     torch.cuda.synchronize()
     if dist is not None:
@@ -213,7 +217,7 @@ def run_regions(args, rank, world, local):
                 data="synthetic",
                 config=dict(workload="regionfile batch: %d synthetic SD-flanked regions per GPU (20-120 blocks, 2-6 "
                                      "repeat families), -d 3 -u 2 -w 1000 -r 0.98 -R 1000, %d contexts per GPU; "
-                                     "regions shard per GPU, no collective" % (args.regions, args.contexts),
+                                     "regions shard per GPU, no collective" % (args.regions, nctx),
                             candidates_scored_per_s=scored / dt, l2="not flushed (every region is new data)"),
                 clocks=clocks,
                 e2e=dict(value=n / dt, unit="regions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),

@@ -47,6 +47,15 @@ struct Err {
 
 // Device memory pool: a solve allocates ~2 GB of per-level arrays; cudaMalloc/cudaFree of that size costs tens of
 // milliseconds and synchronises the device, so freed blocks are kept per context and reused by later solves.
+// Stream synchronisation by polling: the search makes several short host round trips per level, and a blocking
+// wait adds a scheduler wake-up (tens of microseconds, far more when ranks outnumber idle cores) to each of them.
+inline cudaError_t spin_sync(cudaStream_t s) {
+  cudaError_t e;
+  while ((e = cudaStreamQuery(s)) == cudaErrorNotReady) {
+  }
+  return e;
+}
+
 struct DevPool {
   std::multimap<size_t, void*> free_blocks;
   size_t pooled_bytes = 0;
@@ -185,7 +194,7 @@ struct BandStore {  // host cache + device mirror of per-length corridor tables 
     h2d(c, d_eb.ensure(eb.size() * 2, true), eb.data(), eb.size() * 2);
     h2d(c, d_sb.ensure(sb.size(), true), sb.data(), sb.size());
     h2d(c, d_mask.ensure(mask.size() * 4, true), mask.data(), mask.size() * 4);
-    CK(cudaStreamSynchronize(st));  // host vectors may be reallocated by the next get()
+    CK(spin_sync(st));  // host vectors may be reallocated by the next get()
     dirty = false;
   }
 };
@@ -335,7 +344,7 @@ void table_reserve(nw_ctx* c, uint64_t need_entries) {
   nt.ensure(bytes);
   CK(cudaMemsetAsync(nt.p, 0xFF, bytes, c->stream));
   c->launches += launch_rehash(c->table.as<uint64_t>(), c->table_cap, nt.as<uint64_t>(), want - 1, c->stream);
-  CK(cudaStreamSynchronize(c->stream));
+  CK(spin_sync(c->stream));
   c->table = std::move(nt);
   c->table_cap = want;
 }
@@ -409,7 +418,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
   CK(cudaMemsetAsync(c->work.ensure((size_t)n_work * 4, true), 0xFF, (size_t)n_work * 4, st));
   c->launches += launch_bucket_scatter(c->new_len.as<uint16_t>(), Lv.n_new, c->RD.n_y, force, c->bstart.as<uint32_t>(),
                                        c->cursor.as<uint32_t>(), c->work.as<uint32_t>(), st);
-  CK(cudaStreamSynchronize(st));  // bstart host vector goes out of scope
+  CK(spin_sync(st));  // bstart host vector goes out of scope
   ScoreArgs A{};
   A.R = c->RD;
   A.F = Lv.F;
@@ -519,7 +528,7 @@ struct Search {
     h2d(c, L1.flen.ensure(4), &len, 4);
     h2d(c, L1.fid.ensure(4), &id, 4);
     h2d(c, L1.fdup.ensure(1), &dupok, 1);
-    CK(cudaStreamSynchronize(s));
+    CK(spin_sync(s));
     // level 0: one pseudo candidate (the root itself, KIND_ID over frontier slot 0 of level 1), id 1
     L0.G = 1;
     L0.gbase = 0;
@@ -556,7 +565,7 @@ struct Search {
       h2d(c, L0.k3.p, &v[0], 4);
       h2d(c, L0.cost.p, &v[1], 4);
       h2d(c, L0.total.p, &v[2], 4);
-      CK(cudaStreamSynchronize(s));
+      CK(spin_sync(s));
     } else {
       hist[bucket_key(n_x, 0)] = 1;
       ScoreView view = view_of(L0);  // candidates of level 0 against the frontier of level 1
@@ -566,7 +575,7 @@ struct Search {
       d2h(c, &v[0], L0.k3.p, 4);
       d2h(c, &v[1], L0.cost.p, 4);
       d2h(c, &v[2], L0.total.p, 4);
-      CK(cudaStreamSynchronize(s));
+      CK(spin_sync(s));
       root_k3 = v[0];
       root_cost = v[1];
       root_total = v[2];
@@ -591,7 +600,7 @@ struct Search {
     CK(cudaMemsetAsync(misc + 12, 0, 4, s));
     c->launches += launch_verify_dups(E, V, is_new, owner, G, (unsigned int*)(misc + 12), s);
     d2h(c, pin_u32(), misc, 64);
-    CK(cudaStreamSynchronize(s));
+    CK(spin_sync(s));
     CK(cudaGetLastError());
     if (pin_u32()[12])
       fail(NW_ERR_COLLISION, std::to_string(pin_u32()[12]) + " candidates of level " + std::to_string(d) +
@@ -618,7 +627,7 @@ struct Search {
     uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items((uint64_t)L.P) * 4, true);
     c->launches += launch_scan(E.cnt, off, (uint64_t)L.P, bsum, (uint32_t*)(misc + 4), s);
     d2h(c, pin_u32(), misc, 32);
-    CK(cudaStreamSynchronize(s));
+    CK(spin_sync(s));
     CK(cudaGetLastError());
     const uint32_t G = pin_u32()[4];
     const int maxlen = (int)pin_u32()[2];
@@ -652,7 +661,7 @@ struct Search {
     bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(G) * 4, true);
     c->launches += launch_scan(is_new, newrank, G, bsum, (uint32_t*)(misc + 5), s);
     d2h(c, pin_u32(), misc, 32);
-    CK(cudaStreamSynchronize(s));
+    CK(spin_sync(s));
     CK(cudaGetLastError());
     const uint32_t n_new = pin_u32()[5];
     L.n_new = n_new;
@@ -689,7 +698,7 @@ struct Search {
     if (o.flags & NW_FLAG_VERIFY_DEDUP) verify_level(d, E, is_new, owner, G);
     uint32_t* hist_h = pin_u32() + 64;
     d2h(c, hist_h, A.hist, HIST_N * 4);
-    CK(cudaStreamSynchronize(s));
+    CK(spin_sync(s));
     CK(cudaGetLastError());
     int64_t cells = 0;
     run_scoring(c, view_of(L), hist_h, 0, o.flags, misc + 0, &cells);
@@ -719,7 +728,7 @@ struct Search {
     c->launches += launch_valid_flags(Lr.k3.as<int32_t>(), n, flag, s);
     c->launches += launch_scan(flag, pre, n, bsum, (uint32_t*)(misc + 6), s);
     d2h(c, pin_u32(), misc, 32);
-    CK(cudaStreamSynchronize(s));
+    CK(spin_sync(s));
     const uint32_t nvalid = pin_u32()[6];
     uint32_t P2 = nvalid;
     uint32_t* sel = (uint32_t*)c->sel.ensure((size_t)std::max<uint32_t>(nvalid, 1) * 4, true);
@@ -800,7 +809,7 @@ struct Search {
     }
     d2h(c, pin_u32(), misc, 4);
     CK(cudaEventRecord(ev1, s));
-    CK(cudaStreamSynchronize(s));
+    CK(spin_sync(s));
     CK(cudaGetLastError());
     best_k3 = (int)pin_u32()[0];
     for (size_t k = 0; k + 1 < lev.size(); k += 2) {
@@ -860,7 +869,7 @@ struct Search {
     c->launches += launch_mask_counts(E.cnt, (uint32_t)L.P, world, rank, own_cnt, s);
     c->launches += launch_scan(own_cnt, off_loc, (uint64_t)L.P, bsum, (uint32_t*)(misc + 7), s);
     d2h(c, pin_u32(), misc, 32);
-    CK(cudaStreamSynchronize(s));
+    CK(spin_sync(s));
     CK(cudaGetLastError());
     const uint32_t G_all = pin_u32()[4], G = pin_u32()[7];
     const int maxlen = (int)pin_u32()[2];
@@ -893,7 +902,7 @@ struct Search {
     bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(G) * 4, true);
     c->launches += launch_scan(is_new, newrank, G, bsum, (uint32_t*)(misc + 5), s);
     d2h(c, pin_u32(), misc, 32);
-    CK(cudaStreamSynchronize(s));
+    CK(spin_sync(s));
     CK(cudaGetLastError());
     const uint32_t n_loc = pin_u32()[5];
     L.n_local_new = n_loc;
@@ -923,14 +932,14 @@ struct Search {
     c->launches += launch_assign(A, s);
     uint32_t* hist_h = pin_u32() + 64;
     d2h(c, hist_h, A.hist, HIST_N * 4);
-    CK(cudaStreamSynchronize(s));
+    CK(spin_sync(s));
     CK(cudaGetLastError());
     int64_t cells = 0;
     ScoreView V{L.frontier(), n_loc, L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(), L.l_k3.as<int32_t>(),
                 L.l_cost.as<int32_t>(), L.l_total.as<int32_t>()};
     run_scoring(c, V, hist_h, 0, o.flags, misc + 1 /*best is taken from the merged records*/, &cells);
     st.cells[d - 1] = cells;  // cells evaluated by THIS rank (includes candidates another rank discovered first)
-    CK(cudaStreamSynchronize(s));
+    CK(spin_sync(s));
     return n_loc;
   }
 
@@ -939,7 +948,7 @@ struct Search {
     if (!L.n_local_new) return;
     c->launches += launch_dist_pack(curE, L.newlist.as<uint32_t>(), L.n_local_new, L.l_k3.as<int32_t>(),
                                     L.l_cost.as<int32_t>(), L.l_total.as<int32_t>(), out, c->stream);
-    CK(cudaStreamSynchronize(c->stream));
+    CK(spin_sync(c->stream));
     CK(cudaGetLastError());
   }
 
@@ -967,7 +976,7 @@ struct Search {
         uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.G_all) * 4, true);
         c->launches += launch_scan(newflag, grank, L.G_all, bsum, (uint32_t*)(misc + 5), s);
         d2h(c, pin_u32(), misc, 32);
-        CK(cudaStreamSynchronize(s));
+        CK(spin_sync(s));
         n_new = pin_u32()[5];
         L.n_new = n_new;
         const size_t nn = std::max<uint32_t>(n_new, 1);
@@ -1005,7 +1014,7 @@ struct Search {
       select_next(d);
       more = lv[d].n_new > 0 && lv[d + 1].P > 0;
     }
-    CK(cudaStreamSynchronize(s));
+    CK(spin_sync(s));
     CK(cudaGetLastError());
     lv[d].fblob.release();
     if (!more) {
@@ -1015,7 +1024,7 @@ struct Search {
       }
       d2h(c, pin_u32(), misc, 4);
       CK(cudaEventRecord(ev1, s));
-      CK(cudaStreamSynchronize(s));
+      CK(spin_sync(s));
       best_k3 = (int)pin_u32()[0];
       cudaEventElapsedTime(&st.total_ms, ev0, ev1);
       st.n_ids = n_ids;
@@ -1030,7 +1039,7 @@ struct Search {
     int64_t quota;
     report_thresholds(dist_k3_min, k3_star, quota);
     extract_good(needed, dist_k3_min, k3_star, quota);
-    CK(cudaStreamSynchronize(c->stream));
+    CK(spin_sync(c->stream));
     CK(cudaGetLastError());
   }
   void dist_finish(const uint8_t* needed, const void* all, const int64_t* counts, int64_t stride, nw_result* R) {
@@ -1041,7 +1050,7 @@ struct Search {
       edges.resize(at + (size_t)counts[r]);
       d2h(c, edges.data() + at, (const EdgeRec*)all + (size_t)r * stride, (size_t)counts[r] * sizeof(EdgeRec));
     }
-    CK(cudaStreamSynchronize(c->stream));
+    CK(spin_sync(c->stream));
     build_nodes(needed, edges);
     enumerate(R, dist_k3_min);
   }
@@ -1078,7 +1087,7 @@ struct Search {
       c->launches += launch_good_flags(L.k3.as<int32_t>(), L.n_new, L.id_base, k3_min, k3_star, q, tie_rank, needed, s);
       if (k3_star >= 0) {
         d2h(c, pin_u32(), misc0, 64);
-        CK(cudaStreamSynchronize(s));
+        CK(spin_sync(s));
         quota -= (int64_t)pin_u32()[10];
       }
     }
@@ -1108,7 +1117,7 @@ struct Search {
                                           (uint32_t*)(misc + 8), s);
       }
       d2h(c, pin_u32(), misc, 64);
-      CK(cudaStreamSynchronize(s));
+      CK(spin_sync(s));
       CK(cudaGetLastError());
       const uint32_t n = pin_u32()[8];
       if (n <= cap) {
@@ -1138,14 +1147,14 @@ struct Search {
                                         needed, buf, cap, (uint32_t*)(misc + 9), s);
       }
       d2h(c, pin_u32(), misc, 64);
-      CK(cudaStreamSynchronize(s));
+      CK(spin_sync(s));
       const uint32_t n = pin_u32()[9];
       if (n <= cap) {
         id_cap_hint = std::max(id_cap_hint, n);
         hi.resize(n);
         if (n) {
           d2h(c, hi.data(), buf, (size_t)n * sizeof(IdRec));
-          CK(cudaStreamSynchronize(s));
+          CK(spin_sync(s));
         }
         break;
       }
@@ -1167,7 +1176,7 @@ struct Search {
     std::vector<EdgeRec> he(ne);
     if (ne) {
       d2h(c, he.data(), c->edgebuf.p, (size_t)ne * sizeof(EdgeRec));
-      CK(cudaStreamSynchronize(c->stream));
+      CK(spin_sync(c->stream));
     }
     build_nodes(needed, he);
   }
@@ -1277,7 +1286,7 @@ struct Search {
         c->launches += launch_k3_hist(lv[l].k3.as<int32_t>(), lv[l].n_new, k3_min, hist, s);
       std::vector<uint32_t> hh(100002, 0);
       if (k3_min <= 100000) d2h(c, hh.data() + k3_min, hist + k3_min, (size_t)(100001 - k3_min) * 4);  // bins below are empty
-      CK(cudaStreamSynchronize(s));
+      CK(spin_sync(s));
       if (root_k3 >= 0 && root_k3 >= k3_min) hh[root_k3] += 1;
       int64_t cum = 0;
       for (int k = 100000; k >= 0; --k) {
@@ -1343,7 +1352,7 @@ struct Search {
         d2h(c, k3.data(), L.k3.p, (size_t)L.n_new * 4);
         d2h(c, cost.data(), L.cost.p, (size_t)L.n_new * 4);
         d2h(c, total.data(), L.total.p, (size_t)L.n_new * 4);
-        CK(cudaStreamSynchronize(s));
+        CK(spin_sync(s));
         for (uint32_t r = 0; r < L.n_new; ++r) put(L.id_base + (int32_t)r, k3[r], cost[r], total[r], l);
       }
       if (L.G) {
@@ -1352,7 +1361,7 @@ struct Search {
         d2h(c, cid.data(), L.cand_id.p, (size_t)L.G * 4);
         d2h(c, desc.data(), L.desc.p, (size_t)L.G * 8);
         d2h(c, fid.data(), L.fid.p, (size_t)L.P * 4);
-        CK(cudaStreamSynchronize(s));
+        CK(spin_sync(s));
         for (uint32_t g = 0; g < L.G; ++g) {
           R->e_child.push_back(cid[g]);
           R->e_parent.push_back(fid[desc_parent(desc[g])]);
@@ -1690,12 +1699,12 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
     h2d(c, L.total.ensure(n * 4), total.data(), n * 4);
     int32_t* misc = (int32_t*)c->misc.ensure(256);
     CK(cudaMemsetAsync(misc, 0, 256, s));
-    CK(cudaStreamSynchronize(s));
+    CK(spin_sync(s));
     run_scoring(c, view_of(L), hist.data(), force, flags, misc + 1, nullptr);
     d2h(c, k3.data(), L.k3.p, n * 4);
     d2h(c, cost.data(), L.cost.p, n * 4);
     d2h(c, total.data(), L.total.p, n * 4);
-    CK(cudaStreamSynchronize(s));
+    CK(spin_sync(s));
     CK(cudaGetLastError());
     for (int64_t k = 0; k < n; ++k) {
       if (cost_bp) cost_bp[k] = cost[k] < 0 ? cost[k] : (int64_t)cost[k] * c->RH.gcd;
@@ -1721,7 +1730,7 @@ int nw_moveset(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, uint8_t* 
     std::vector<uint32_t> dd((size_t)(n_x + 1) * MW), iv((size_t)(n_x + 1) * MW);
     d2h(c, dd.data(), c->d_msdd.p, dd.size() * 4);
     d2h(c, iv.data(), c->d_msinv.p, iv.size() * 4);
-    CK(cudaStreamSynchronize(c->stream));
+    CK(spin_sync(c->stream));
     CK(cudaGetLastError());
     for (int a = 1; a <= n_x; ++a)
       for (int b = 1; b <= n_x; ++b) {
@@ -1868,7 +1877,7 @@ int nw_dist_report_mark(nw_ctx* c, void* needed_dev, int32_t pass) {
     Search* S = dist_of(c);
     CK(cudaSetDevice(c->device));
     S->extract_mark((uint8_t*)needed_dev, pass);
-    CK(cudaStreamSynchronize(c->stream));
+    CK(spin_sync(c->stream));
     CK(cudaGetLastError());
   });
   if (rc != NW_OK) cudaGetLastError();
@@ -1894,7 +1903,7 @@ int nw_dist_report_pack(nw_ctx* c, void* dev_out) {
     if (S->dist_edges) {
       CK(cudaMemcpyAsync(dev_out, c->edgebuf.p, (size_t)S->dist_edges * sizeof(EdgeRec), cudaMemcpyDeviceToDevice,
                          c->stream));
-      CK(cudaStreamSynchronize(c->stream));
+      CK(spin_sync(c->stream));
     }
   });
   if (rc != NW_OK) cudaGetLastError();
