@@ -50,10 +50,12 @@ struct Err {
 // Stream synchronisation by polling: the search makes several short host round trips per level, and a blocking
 // wait adds a scheduler wake-up (tens of microseconds, far more when ranks outnumber idle cores) to each of them.
 inline cudaError_t spin_sync(cudaStream_t s) {
-  cudaError_t e;
-  while ((e = cudaStreamQuery(s)) == cudaErrorNotReady) {
+  cudaError_t e = cudaSuccess;
+  for (int it = 0; it < 64; ++it) {  // ~50-100 us of polling covers the short round trips ...
+    e = cudaStreamQuery(s);
+    if (e != cudaErrorNotReady) return e;
   }
-  return e;
+  return cudaStreamSynchronize(s);   // ... long kernels block instead of burning a core other contexts need
 }
 
 struct DevPool {
@@ -362,8 +364,11 @@ ScoreView view_of(const Level& L) {
   return ScoreView{L.frontier(),          L.n_new,           L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(),
                    L.k3.as<int32_t>(),    L.cost.as<int32_t>(), L.total.as<int32_t>()};
 }
-void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int force, int flags, int* best_dev,
+// `lmax` bounds the child lengths present (bins above it are untouched: keeps the per-level copies small).
+void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int lmax, int force, int flags, int* best_dev,
                  int64_t* cells_out) {
+  lmax = std::min(std::max(lmax, 1), LMAX);
+  const size_t nbins = (size_t)(lmax + 1) * NSUB;
   cudaStream_t st = c->stream;
   struct Bucket {
     int L, cls;  // cls: window W (fast) or 0 (generic)
@@ -371,7 +376,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
   };
   std::vector<Bucket> bk;
   int64_t cells = 0;
-  for (int L = 1; L <= LMAX; ++L) {
+  for (int L = 1; L <= lmax; ++L) {
     uint32_t nL = 0;
     for (int sb = 0; sb < NSUB; ++sb) nL += hist_h[(size_t)L * NSUB + sb];
     if (!nL) continue;
@@ -390,7 +395,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
     const int ka = a.cls ? a.cls : 1 << 20, kb = b.cls ? b.cls : 1 << 20;
     return ka < kb;
   });
-  std::vector<uint32_t> bstart(HIST_N, 0);
+  std::vector<uint32_t> bstart(nbins, 0);
   struct Range {
     int cls;
     uint32_t begin, end;
@@ -413,8 +418,8 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int for
     ranges.back().lmax = std::max(ranges.back().lmax, b.L);
   }
   const uint32_t n_work = pos;
-  h2d(c, c->bstart.ensure(HIST_N * 4), bstart.data(), HIST_N * 4);
-  CK(cudaMemsetAsync(c->cursor.ensure(HIST_N * 4), 0, HIST_N * 4, st));
+  h2d(c, c->bstart.ensure(HIST_N * 4), bstart.data(), nbins * 4);
+  CK(cudaMemsetAsync(c->cursor.ensure(HIST_N * 4), 0, nbins * 4, st));
   CK(cudaMemsetAsync(c->work.ensure((size_t)n_work * 4, true), 0xFF, (size_t)n_work * 4, st));
   c->launches += launch_bucket_scatter(c->new_len.as<uint16_t>(), Lv.n_new, c->RD.n_y, force, c->bstart.as<uint32_t>(),
                                        c->cursor.as<uint32_t>(), c->work.as<uint32_t>(), st);
@@ -570,7 +575,7 @@ struct Search {
       hist[bucket_key(n_x, 0)] = 1;
       ScoreView view = view_of(L0);  // candidates of level 0 against the frontier of level 1
       view.F = L1.frontier();
-      run_scoring(c, view, hist.data(), 0, o.flags, misc + 1 /*dummy best*/, nullptr);
+      run_scoring(c, view, hist.data(), n_x, 0, o.flags, misc + 1 /*dummy best*/, nullptr);
       int32_t v[3];
       d2h(c, &v[0], L0.k3.p, 4);
       d2h(c, &v[1], L0.cost.p, 4);
@@ -692,16 +697,18 @@ struct Search {
     A.k3 = (int32_t*)L.k3.ensure((size_t)n_new * 4);
     A.cost = (int32_t*)L.cost.ensure((size_t)n_new * 4);
     A.total = (int32_t*)L.total.ensure((size_t)n_new * 4);
+    const int lmax = std::min(std::max(maxlen, L.LS), LMAX);  // longest possible child of this level
+    const size_t nbins = (size_t)(lmax + 1) * NSUB;
     A.hist = (uint32_t*)c->hist.ensure(HIST_N * 4);
-    CK(cudaMemsetAsync(A.hist, 0, HIST_N * 4, s));
+    CK(cudaMemsetAsync(A.hist, 0, nbins * 4, s));
     c->launches += launch_assign(A, s);
     if (o.flags & NW_FLAG_VERIFY_DEDUP) verify_level(d, E, is_new, owner, G);
     uint32_t* hist_h = pin_u32() + 64;
-    d2h(c, hist_h, A.hist, HIST_N * 4);
+    d2h(c, hist_h, A.hist, nbins * 4);
     CK(spin_sync(s));
     CK(cudaGetLastError());
     int64_t cells = 0;
-    run_scoring(c, view_of(L), hist_h, 0, o.flags, misc + 0, &cells);
+    run_scoring(c, view_of(L), hist_h, lmax, 0, o.flags, misc + 0, &cells);
     st.cells[d - 1] = cells;
     gtotal += G;
     n_ids += (int32_t)n_new;
@@ -927,17 +934,19 @@ struct Search {
     A.k3 = (int32_t*)L.l_k3.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
     A.cost = (int32_t*)L.l_cost.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
     A.total = (int32_t*)L.l_total.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
+    const int lmax = std::min(std::max(maxlen, L.LS), LMAX);
+    const size_t nbins = (size_t)(lmax + 1) * NSUB;
     A.hist = (uint32_t*)c->hist.ensure(HIST_N * 4);
-    CK(cudaMemsetAsync(A.hist, 0, HIST_N * 4, s));
+    CK(cudaMemsetAsync(A.hist, 0, nbins * 4, s));
     c->launches += launch_assign(A, s);
     uint32_t* hist_h = pin_u32() + 64;
-    d2h(c, hist_h, A.hist, HIST_N * 4);
+    d2h(c, hist_h, A.hist, nbins * 4);
     CK(spin_sync(s));
     CK(cudaGetLastError());
     int64_t cells = 0;
     ScoreView V{L.frontier(), n_loc, L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(), L.l_k3.as<int32_t>(),
                 L.l_cost.as<int32_t>(), L.l_total.as<int32_t>()};
-    run_scoring(c, V, hist_h, 0, o.flags, misc + 1 /*best is taken from the merged records*/, &cells);
+    run_scoring(c, V, hist_h, lmax, 0, o.flags, misc + 1 /*best is taken from the merged records*/, &cells);
     st.cells[d - 1] = cells;  // cells evaluated by THIS rank (includes candidates another rank discovered first)
     CK(spin_sync(s));
     return n_loc;
@@ -1700,7 +1709,7 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
     int32_t* misc = (int32_t*)c->misc.ensure(256);
     CK(cudaMemsetAsync(misc, 0, 256, s));
     CK(spin_sync(s));
-    run_scoring(c, view_of(L), hist.data(), force, flags, misc + 1, nullptr);
+    run_scoring(c, view_of(L), hist.data(), maxlen, force, flags, misc + 1, nullptr);
     d2h(c, k3.data(), L.k3.p, n * 4);
     d2h(c, cost.data(), L.cost.p, n * 4);
     d2h(c, total.data(), L.total.p, n * 4);
