@@ -402,13 +402,22 @@ def main():
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = 44.0 * scored  # 8 B descriptor in + 36 B record out per scored candidate
     hbm_ach = alg_bytes / (score_ms * 1e-3) / 1e9 if score_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_note = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "dp_kernel_traffic.json")))["dram_bytes_per_launch"]
+        # ncu capture of the level-3 DP launch, which carries 99.6 % of a search's DP cells; `achieved` above averages
+        # over all DP launches of a search (root, level 1, 2, 3), so the per-launch average is that capture / launches
+        tj = json.load(open(os.path.join(ROOT, "profiles", "dp_kernel_traffic.json")))
+        per_search = score_launches / max(args.steps, 1)
+        if args.workload == "s64" and per_search > 0:
+            traffic = tj["dram_bytes_per_launch"] / per_search
+            traffic_note = ("dram__bytes_read+write of the level-3 launch (%d B, ncu --set full, profiles/"
+                            "r1_ncu_summary_s64.md) spread over the %d DP launches of a search; algorithmic bytes of "
+                            "that launch: %d" % (tj["dram_bytes_per_launch"], per_search,
+                                                 tj["algorithmic_bytes_per_launch"]))
     except Exception:
         pass
     roofline = dict(bound="int_alu", kernel="k_score_fast<W> (banded DP)", achieved=ach, peak=peak, unit="Tintop/s",
-                    frac=(ach / peak if peak else None), traffic=traffic,
+                    frac=(ach / peak if peak else None), traffic=traffic, traffic_note=traffic_note,
                     launches=score_launches, avg_launch_ms=(score_ms / score_launches if score_launches else None),
                     peak_basis="measured on this GPU (nw_bench_peaks): VIADDMNMX %.2f, IADD3 %.2f, VIADDMNMX+IMAD %.2f "
                                "T thread-instr/s" % (peaks["viaddmnmx_ips"] / 1e12, peaks["iadd3_ips"] / 1e12,
