@@ -135,6 +135,15 @@ typedef struct nw_problem {
 int nw_solve_batch(nw_ctx** ctxs, int32_t n_ctx, const nw_problem* probs, int64_t n, const nw_opts* opts,
                    nw_result** outs, int32_t* rcs);
 
+/* The same n independent problems on ONE context, max_regions_per_pass (<= 0: 256) regions at a time searched
+ * TOGETHER: their frontiers are concatenated, every kernel launch of a BFS level covers all regions of the pass
+ * (candidates carry their region through the parent; the dedup table is shared, fingerprints are salted with the
+ * region id; ids, beam selection, best score and report are per region).  Small regions are launch-bound when
+ * solved one by one; this path amortises every launch over the pass.  Results are identical, region by region, to
+ * nw_solve.  On error no result is returned (all outs[k] are NULL). */
+int nw_solve_many(nw_ctx* ctx, const nw_problem* probs, int64_t n, const nw_opts* opts, int32_t max_regions_per_pass,
+                  nw_result** outs);
+
 /* ---- one deep search sharded over `world` ranks (config 3 of BASELINE.json) -------------------------
  * One context per rank, the same problem and options on every rank.  The frontier is replicated; rank r expands the
  * parents whose frontier slot is congruent to r modulo world, dedups and scores its own candidates, and contributes

@@ -208,20 +208,24 @@ struct nw_ctx {
   cudaStream_t stream = nullptr;
   std::vector<U4> h_pow;
   DevBuf d_pow;
-  // region
-  RegionHost RH;
-  RegionDev RD{};
-  DevBuf d_ctx, d_rt, d_cumr, d_msdd, d_msinv, d_msany;
+  // regions of the current search (regionfile mode runs many independent regions through one pipeline)
+  std::vector<RegionHost> RH;
+  std::vector<RegionDev> RD;          // host copies; d_regions is the device array the kernels index by region id
+  std::vector<BandStore*> rbands;     // corridor tables of every region's n_y
+  DevBuf d_regions, d_ctx_all, d_small_all, d_ms_all;
+  int n_regions = 0, nx_max = 0, ny_max = 0;
+  uint32_t ctx_max = 0;
+  bool regions_dirty = true;          // RD changed (band pointers) and must be re-uploaded
   std::map<int, BandStore> band_cache;  // corridor tables per (n_y, force), kept across regions
-  BandStore* bands_p = nullptr;
   // dedup table
   DevBuf table;
   uint64_t table_cap = 0;
   // per-level scratch
   DevBuf cnt, off, bsum, slot, owner, is_new, newrank, new_len, hist, bstart, cursor, work, scratch, flag, pre, sel, keys,
-      misc, rslot, newflag, grank, edgebuf;
+      misc, rslot, newflag, grank, edgebuf, cta_rid, new_rid, best, gather;
   void* dist = nullptr;  // active frontier-sharded search (Search*, nw_dist_*)
-  void* pinned = nullptr;  // small pinned staging area for D2H scalars / histograms
+  void* pinned = nullptr;  // pinned staging area for D2H scalars / histograms (grown on demand)
+  size_t pinned_bytes = 0;
   DevPool pool;
   int launches = 0;
   int64_t h2d_bytes = 0, d2h_bytes = 0;
@@ -261,17 +265,18 @@ struct nw_result {
 namespace {
 
 constexpr size_t PINNED_BYTES = 512 * 1024;
-constexpr size_t HIST_N = (size_t)(LMAX + 2) * NSUB;  // (child length, sub-counter) bins
 
 struct Level {
   // frontier expanded at this level
   int P = 0, LS = 0;
   uint32_t pstride = 0;
-  DevBuf fblob, flen, fid, fdup;
+  DevBuf fblob, flen, fid, fdup, frid;  // frid: region of every parent (uint16)
   // candidates generated at this level
   uint32_t G = 0, gbase = 0, n_new = 0;
   int32_t id_base = 0;
-  DevBuf desc, cand_id, newlist, k3, cost, total;
+  DevBuf desc, cand_id, newlist, k3, cost, total, nrid;  // nrid: region of every fresh id (uint16)
+  // region boundaries (R+1 entries each): parents, candidate positions, new ranks of every region at this level
+  std::vector<uint32_t> fstart, cstart, nstart;
   // frontier-sharded search only: G counts this rank's candidates, G_all all ranks'; k3/cost/total are the merged
   // (replicated) per-id arrays, l_* the rank-local ones of the candidates this rank scored
   uint32_t G_all = 0, n_local_new = 0;
@@ -285,49 +290,122 @@ struct Level {
     F.len = flen.as<int32_t>();
     F.id = fid.as<int32_t>();
     F.dupok = fdup.as<uint8_t>();
+    F.rid = frid.p ? frid.as<uint16_t>() : nullptr;
+    F.regions = nullptr;  // filled by Search::frontier_of (device region table of the context)
     return F;
   }
 };
 
-void setup_region(nw_ctx* c, const int8_t* aln, int n_x, int n_y, const int64_t* len_x, const int64_t* len_y,
-                  int maxdepth, bool force) {
-  try {
-    c->RH = build_region(aln, n_x, n_y, len_x, len_y, maxdepth);
-  } catch (const HostError& e) {
-    fail(e.code, e.what());
-  }
-  RegionHost& H = c->RH;
+struct ProblemRef {
+  const int8_t* aln;
+  int n_x, n_y;
+  const int64_t* len_x;
+  const int64_t* len_y;
+};
+
+// Builds and uploads the context of every region of a search (packed into a few buffers: one copy each).
+void setup_regions(nw_ctx* c, const ProblemRef* probs, int R, int maxdepth, bool force) {
+  if (R < 1 || R > 65535) fail(NW_ERR_ARG, "a batch holds between 1 and 65535 regions");
   cudaStream_t st = c->stream;
-  h2d(c, c->d_ctx.ensure(H.ctx.size()), H.ctx.data(), H.ctx.size());
-  h2d(c, c->d_rt.ensure(H.rt.size() * 4), H.rt.data(), H.rt.size() * 4);
-  h2d(c, c->d_cumr.ensure(H.cumr.size() * 4), H.cumr.data(), H.cumr.size() * 4);
-  const size_t msb = (size_t)(n_x + 1) * H.MW * 4;
-  CK(cudaMemsetAsync(c->d_msdd.ensure(msb), 0, msb, st));
-  CK(cudaMemsetAsync(c->d_msinv.ensure(msb), 0, msb, st));
-  CK(cudaMemsetAsync(c->d_msany.ensure((size_t)(n_x + 1) * 4), 0, (size_t)(n_x + 1) * 4, st));
-  RegionDev& D = c->RD;
-  D.n_x = n_x;
-  D.n_y = n_y;
-  D.NYP = H.NYP;
-  D.PWS = H.PWS;
-  D.MW = H.MW;
-  D.sum_rt = (int)H.sum_rt;
-  D.rid1 = 1;
-  D.ctx_bytes = (uint32_t)H.ctx.size();
-  D.ctx = c->d_ctx.as<unsigned char>();
-  D.off_upx = H.off_upx;
-  D.off_rtrev = H.off_rtrev;
-  D.rt_copy_stride = H.rt_copy_stride;
-  D.rt = c->d_rt.as<int32_t>();
-  D.cumr = c->d_cumr.as<int32_t>();
-  D.ms_dd = c->d_msdd.as<uint32_t>();
-  D.ms_inv = c->d_msinv.as<uint32_t>();
-  D.ms_any = c->d_msany.as<uint32_t>();
-  if (D.ctx_bytes > 200 * 1024) fail(NW_ERR_RANGE, "region context exceeds shared memory");
-  c->launches += launch_moveset(D, st);
-  BandStore& bs = c->band_cache[n_y * 2 + (force ? 1 : 0)];
-  if (bs.n_y != n_y || bs.force != force) bs.reset(n_y, force);
-  c->bands_p = &bs;
+  c->RH.clear();
+  c->RH.reserve(R);
+  c->RD.assign(R, RegionDev{});
+  c->rbands.assign(R, nullptr);
+  c->n_regions = R;
+  c->nx_max = c->ny_max = 0;
+  c->ctx_max = 0;
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t ctx_bytes = 0, small_bytes = 0, ms_bytes = 0;
+  std::vector<size_t> o_ctx(R), o_rt(R), o_cumr(R), o_dd(R), o_inv(R), o_any(R);
+  for (int r = 0; r < R; ++r) {
+    try {
+      c->RH.push_back(build_region(probs[r].aln, probs[r].n_x, probs[r].n_y, probs[r].len_x, probs[r].len_y, maxdepth));
+    } catch (const HostError& e) {
+      fail(e.code, (R > 1 ? "region " + std::to_string(r) + ": " : std::string()) + e.what());
+    }
+    const RegionHost& H = c->RH.back();
+    if (H.ctx.size() > 200 * 1024) fail(NW_ERR_RANGE, "region context exceeds shared memory");
+    o_ctx[r] = ctx_bytes;
+    ctx_bytes += al(H.ctx.size());
+    o_rt[r] = small_bytes;
+    small_bytes += al(H.rt.size() * 4);
+    o_cumr[r] = small_bytes;
+    small_bytes += al(H.cumr.size() * 4);
+    const size_t msb = al((size_t)(H.n_x + 1) * H.MW * 4);
+    o_dd[r] = ms_bytes;
+    ms_bytes += msb;
+    o_inv[r] = ms_bytes;
+    ms_bytes += msb;
+    o_any[r] = ms_bytes;
+    ms_bytes += al((size_t)(H.n_x + 1) * 4);
+    c->nx_max = std::max(c->nx_max, H.n_x);
+    c->ny_max = std::max(c->ny_max, H.n_y);
+    c->ctx_max = std::max<uint32_t>(c->ctx_max, (uint32_t)H.ctx.size());
+  }
+  std::vector<unsigned char> h_ctx(ctx_bytes, 0), h_small(small_bytes, 0);
+  for (int r = 0; r < R; ++r) {
+    const RegionHost& H = c->RH[r];
+    memcpy(h_ctx.data() + o_ctx[r], H.ctx.data(), H.ctx.size());
+    memcpy(h_small.data() + o_rt[r], H.rt.data(), H.rt.size() * 4);
+    memcpy(h_small.data() + o_cumr[r], H.cumr.data(), H.cumr.size() * 4);
+  }
+  unsigned char* dctx = (unsigned char*)c->d_ctx_all.ensure(ctx_bytes);
+  unsigned char* dsm = (unsigned char*)c->d_small_all.ensure(small_bytes);
+  unsigned char* dms = (unsigned char*)c->d_ms_all.ensure(ms_bytes);
+  h2d(c, dctx, h_ctx.data(), ctx_bytes);
+  h2d(c, dsm, h_small.data(), small_bytes);
+  CK(cudaMemsetAsync(dms, 0, ms_bytes, st));
+  for (int r = 0; r < R; ++r) {
+    const RegionHost& H = c->RH[r];
+    RegionDev& D = c->RD[r];
+    D.n_x = H.n_x;
+    D.n_y = H.n_y;
+    D.NYP = H.NYP;
+    D.PWS = H.PWS;
+    D.MW = H.MW;
+    D.sum_rt = (int)H.sum_rt;
+    D.rid1 = (uint32_t)r + 1;  // leading element of every fingerprint of this region
+    D.ctx_bytes = (uint32_t)H.ctx.size();
+    D.ctx = dctx + o_ctx[r];
+    D.off_upx = H.off_upx;
+    D.off_rtrev = H.off_rtrev;
+    D.rt_copy_stride = H.rt_copy_stride;
+    D.rt = reinterpret_cast<const int32_t*>(dsm + o_rt[r]);
+    D.cumr = reinterpret_cast<const int32_t*>(dsm + o_cumr[r]);
+    D.ms_dd = reinterpret_cast<uint32_t*>(dms + o_dd[r]);
+    D.ms_inv = reinterpret_cast<uint32_t*>(dms + o_inv[r]);
+    D.ms_any = reinterpret_cast<uint32_t*>(dms + o_any[r]);
+    BandStore& bs = c->band_cache[H.n_y * 2 + (force ? 1 : 0)];
+    if (bs.n_y != H.n_y || bs.force != force) bs.reset(H.n_y, force);
+    c->rbands[r] = &bs;
+  }
+  c->d_regions.ensure((size_t)R * sizeof(RegionDev));
+  h2d(c, c->d_regions.p, c->RD.data(), (size_t)R * sizeof(RegionDev));
+  CK(spin_sync(st));  // the packed host buffers go out of scope
+  c->regions_dirty = false;
+  c->launches += launch_moveset(c->d_regions.as<RegionDev>(), R, c->nx_max, st);
+}
+
+// corridor tables may have been (re)allocated: refresh the device pointers of every region
+void refresh_region_bands(nw_ctx* c) {
+  bool changed = false;
+  for (int r = 0; r < c->n_regions; ++r) {
+    BandStore* b = c->rbands[r];
+    RegionDev& D = c->RD[r];
+    if (D.band_off != b->d_off.as<int32_t>() || D.band_ab != b->d_ab.as<int16_t>() || D.band_eb != b->d_eb.as<int16_t>() ||
+        D.band_sb != b->d_sb.as<uint8_t>() || D.band_mask != b->d_mask.as<uint32_t>()) {
+      D.band_off = b->d_off.as<int32_t>();
+      D.band_ab = b->d_ab.as<int16_t>();
+      D.band_eb = b->d_eb.as<int16_t>();
+      D.band_sb = b->d_sb.as<uint8_t>();
+      D.band_mask = b->d_mask.as<uint32_t>();
+      changed = true;
+    }
+  }
+  if (changed) {
+    h2d(c, c->d_regions.p, c->RD.data(), (size_t)c->n_regions * sizeof(RegionDev));
+    CK(spin_sync(c->stream));
+  }
 }
 
 void table_reserve(nw_ctx* c, uint64_t need_entries) {
@@ -364,36 +442,44 @@ ScoreView view_of(const Level& L) {
   return ScoreView{L.frontier(),          L.n_new,           L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(),
                    L.k3.as<int32_t>(),    L.cost.as<int32_t>(), L.total.as<int32_t>()};
 }
-// `lmax` bounds the child lengths present (bins above it are untouched: keeps the per-level copies small).
-void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int lmax, int force, int flags, int* best_dev,
-                 int64_t* cells_out) {
-  lmax = std::min(std::max(lmax, 1), LMAX);
-  const size_t nbins = (size_t)(lmax + 1) * NSUB;
+// Buckets the fresh candidates by (region, child length) and runs the DP kernels.  hist_h[bucket_key(...)] is the
+// host copy of the (region, length, sub-counter) histogram written by k_assign; lcap = longest child length + 1.
+// Work-list layout: kernel class (register window W ascending, generic last) > region > length; every bucket is
+// padded to a warp, every region segment of a register-kernel class to a CTA (a CTA stages one region context).
+void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int lcap, const uint16_t* new_rid_dev, int force,
+                 int flags, int* best_dev, int64_t* cells_out /* [n_regions] or nullptr */) {
+  const int R = c->n_regions;
+  const size_t nbins = (size_t)R * lcap * NSUB;
   cudaStream_t st = c->stream;
   struct Bucket {
-    int L, cls;  // cls: window W (fast) or 0 (generic)
+    int rid, L, cls;  // cls: window W (fast) or 0 (generic)
     uint32_t n;
   };
   std::vector<Bucket> bk;
-  int64_t cells = 0;
-  for (int L = 1; L <= lmax; ++L) {
-    uint32_t nL = 0;
-    for (int sb = 0; sb < NSUB; ++sb) nL += hist_h[(size_t)L * NSUB + sb];
-    if (!nL) continue;
-    const BandTable& T = c->bands_p->get(L);
-    if (!T.contiguous) fail(NW_ERR_RANGE, "corridor rows are not intervals for this shape (unsupported)");
-    int cls = 0;
-    if (!(flags & NW_FLAG_GENERIC_DP) && T.fast_ok) cls = score_fast_window(T.max_width);
-    if (cls && score_fast_smem(cls, c->RD.ctx_bytes, L) > 200 * 1024) cls = 0;  // tiles would not fit: generic kernel
-    bk.push_back(Bucket{L, cls, nL});
-    cells += (int64_t)nL * T.cells;
+  for (int r = 0; r < R; ++r) {
+    int64_t cells = 0;
+    for (int L = 1; L < lcap; ++L) {
+      uint32_t nL = 0;
+      const size_t k0 = ((size_t)r * lcap + L) * NSUB;
+      for (int sb = 0; sb < NSUB; ++sb) nL += hist_h[k0 + sb];
+      if (!nL) continue;
+      const BandTable& T = c->rbands[r]->get(L);
+      if (!T.contiguous) fail(NW_ERR_RANGE, "corridor rows are not intervals for this shape (unsupported)");
+      int cls = 0;
+      if (!(flags & NW_FLAG_GENERIC_DP) && T.fast_ok) cls = score_fast_window(T.max_width);
+      if (cls && score_fast_smem(cls, c->ctx_max, L) > 200 * 1024) cls = 0;  // tiles would not fit: generic kernel
+      bk.push_back(Bucket{r, L, cls, nL});
+      cells += (int64_t)nL * T.cells;
+    }
+    if (cells_out) cells_out[r] = cells;
   }
-  if (cells_out) *cells_out = cells;
   if (bk.empty()) return;
-  c->bands_p->upload(c, st);
+  for (int r = 0; r < R; ++r) c->rbands[r]->upload(c, st);
+  refresh_region_bands(c);
   std::stable_sort(bk.begin(), bk.end(), [](const Bucket& a, const Bucket& b) {
     const int ka = a.cls ? a.cls : 1 << 20, kb = b.cls ? b.cls : 1 << 20;
-    return ka < kb;
+    if (ka != kb) return ka < kb;
+    return a.rid < b.rid;  // lengths stay ascending inside a region (stable)
   });
   std::vector<uint32_t> bstart(nbins, 0);
   struct Range {
@@ -402,38 +488,48 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int lma
     int lmax;
   };
   std::vector<Range> ranges;
+  std::vector<uint16_t> cta_rid;  // region of every CTA, over the whole work list (CTA = 128 slots)
   uint32_t pos = 0;
+  int prev_rid = -1;
   for (const Bucket& b : bk) {
-    if (ranges.empty() || ranges.back().cls != b.cls) {
-      pos = (pos + 127) & ~127u;  // class ranges start on a CTA boundary
-      ranges.push_back(Range{b.cls, pos, pos, 0});
-    }
+    const bool new_class = ranges.empty() || ranges.back().cls != b.cls;
+    if (new_class || (b.cls && b.rid != prev_rid)) pos = (pos + 127) & ~127u;  // CTA boundary
+    if (new_class) ranges.push_back(Range{b.cls, pos, pos, 0});
+    prev_rid = b.rid;
     uint32_t at = pos;  // the sub-counters of one length share one contiguous, 32-padded bucket
+    const size_t k0 = ((size_t)b.rid * lcap + b.L) * NSUB;
     for (int sb = 0; sb < NSUB; ++sb) {
-      bstart[(size_t)b.L * NSUB + sb] = at;
-      at += hist_h[(size_t)b.L * NSUB + sb];
+      bstart[k0 + sb] = at;
+      at += hist_h[k0 + sb];
     }
     pos += (b.n + 31) & ~31u;
     ranges.back().end = pos;
     ranges.back().lmax = std::max(ranges.back().lmax, b.L);
+    if (R > 1) {
+      const size_t last_cta = (pos + 127) / 128;
+      if (cta_rid.size() < last_cta) cta_rid.resize(last_cta, (uint16_t)b.rid);
+    }
   }
   const uint32_t n_work = pos;
-  h2d(c, c->bstart.ensure(HIST_N * 4), bstart.data(), nbins * 4);
-  CK(cudaMemsetAsync(c->cursor.ensure(HIST_N * 4), 0, nbins * 4, st));
+  h2d(c, c->bstart.ensure(nbins * 4, true), bstart.data(), nbins * 4);
+  CK(cudaMemsetAsync(c->cursor.ensure(nbins * 4, true), 0, nbins * 4, st));
   CK(cudaMemsetAsync(c->work.ensure((size_t)n_work * 4, true), 0xFF, (size_t)n_work * 4, st));
-  c->launches += launch_bucket_scatter(c->new_len.as<uint16_t>(), Lv.n_new, c->RD.n_y, force, c->bstart.as<uint32_t>(),
-                                       c->cursor.as<uint32_t>(), c->work.as<uint32_t>(), st);
-  CK(spin_sync(st));  // bstart host vector goes out of scope
+  uint16_t* d_cta_rid = nullptr;
+  if (R > 1) {
+    d_cta_rid = (uint16_t*)c->cta_rid.ensure(cta_rid.size() * 2, true);
+    h2d(c, d_cta_rid, cta_rid.data(), cta_rid.size() * 2);
+  }
+  c->launches += launch_bucket_scatter(c->new_len.as<uint16_t>(), new_rid_dev, c->d_regions.as<RegionDev>(), lcap, Lv.n_new,
+                                       force, c->bstart.as<uint32_t>(), c->cursor.as<uint32_t>(), c->work.as<uint32_t>(),
+                                       st);
+  CK(spin_sync(st));  // bstart / cta_rid host vectors go out of scope
   ScoreArgs A{};
-  A.R = c->RD;
   A.F = Lv.F;
+  A.F.regions = c->d_regions.as<RegionDev>();
+  A.ctx_max = c->ctx_max;
+  A.ny_max = c->ny_max;
   A.newlist = Lv.newlist;
   A.desc = Lv.desc;
-  A.band_off = c->bands_p->d_off.as<int32_t>();
-  A.band_ab = c->bands_p->d_ab.as<int16_t>();
-  A.band_eb = c->bands_p->d_eb.as<int16_t>();
-  A.band_sb = c->bands_p->d_sb.as<uint8_t>();
-  A.band_mask = c->bands_p->d_mask.as<uint32_t>();
   A.k3 = Lv.k3;
   A.cost = Lv.cost;
   A.total = Lv.total;
@@ -444,6 +540,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int lma
     A.work = c->work.as<uint32_t>() + r.begin;
     A.n_work = r.end - r.begin;
     A.lmax = r.lmax;
+    A.cta_rid = d_cta_rid ? d_cta_rid + r.begin / 128 : nullptr;
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     if (!c->event_pool.empty()) {
       ev = c->event_pool.back();
@@ -458,7 +555,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int lma
       if (l < 0) fail(NW_ERR_CUDA, "no register-DP kernel for window " + std::to_string(r.cls));
       c->launches += l;
     } else {
-      const size_t sc = (size_t)2 * (c->RD.n_y + 2) * generic_threads() * 4;
+      const size_t sc = (size_t)2 * (c->ny_max + 2) * generic_threads() * 4;
       A.scratch = (int32_t*)c->scratch.ensure(sc);
       c->launches += launch_score_generic(A, st);
     }
@@ -488,9 +585,10 @@ struct Search {
   std::vector<Level> lv;  // lv[0] = root pseudo-level, lv[d] = BFS level d
   int32_t n_ids = 0;
   uint32_t gtotal = 0;
-  int root_k3 = 0, root_cost = -1, root_total = 0;
-  int best_k3 = 0;
-  nw_stats st{};
+  int R = 1;  // regions searched together (regionfile mode); region r has root id r+1
+  std::vector<int> root_k3, root_cost, root_total, best_k3;  // per region
+  std::vector<nw_stats> rst;                                   // per region
+  nw_stats st{};                                               // whole batch (timing, launches)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> lev;
 
@@ -502,6 +600,7 @@ struct Search {
   int dist_maxlen = 0;
   uint32_t dist_edges = 0;
   uint32_t edge_cap_hint = 0, id_cap_hint = 0;
+  int level_maxlen = 0;  // longest duplication child of the level in flight
   explicit Search(nw_ctx* ctx, const nw_opts& opts) : c(ctx), o(opts) {}
   ~Search() {
     if (ev0) cudaEventDestroy(ev0);
@@ -511,79 +610,126 @@ struct Search {
 
   uint32_t* pin_u32() { return reinterpret_cast<uint32_t*>(c->pinned); }
 
+  FrontierDev frontier_of(const Level& L) const {
+    FrontierDev F = L.frontier();
+    F.regions = c->d_regions.as<RegionDev>();
+    if (R == 1) F.rid = nullptr;
+    return F;
+  }
+  uint32_t* pinned(size_t bytes) {  // growable pinned staging area
+    if (bytes > c->pinned_bytes) {
+      if (c->pinned) cudaFreeHost(c->pinned);
+      c->pinned = nullptr;
+      c->pinned_bytes = 0;
+      const size_t want = std::max(bytes + bytes / 2, (size_t)512 * 1024);
+      CK(cudaMallocHost(&c->pinned, want));
+      c->pinned_bytes = want;
+    }
+    return reinterpret_cast<uint32_t*>(c->pinned);
+  }
+  // dst_host[i] = src_dev[idx[i]] (idx[i] < limit) else fill; one tiny H2D + kernel; the D2H is left to the caller
+  // (results land at gather_dev[0..n))
+  void gather_async(const uint32_t* src_dev, const std::vector<uint32_t>& idx, uint32_t limit, uint32_t fill) {
+    const uint32_t n = (uint32_t)idx.size();
+    uint32_t* g = (uint32_t*)c->gather.ensure((size_t)n * 8, true);
+    h2d(c, g + n, idx.data(), (size_t)n * 4);
+    c->launches += launch_gather_u32(src_dev, g + n, n, limit, fill, g, c->stream);
+  }
+
   void init_root() {
     cudaStream_t s = c->stream;
-    const int n_x = c->RD.n_x;
-    if (n_x > LMAX) fail(NW_ERR_RANGE, "n_x exceeds the supported index length");
+    R = c->n_regions;
+    root_k3.assign(R, 0);
+    root_cost.assign(R, -1);
+    root_total.assign(R, 0);
+    best_k3.assign(R, 0);
+    rst.assign(R, nw_stats{});
+    if (c->nx_max > LMAX) fail(NW_ERR_RANGE, "n_x exceeds the supported index length");
     lv.clear();
     lv.emplace_back();  // level 0 (root pseudo level)
-    lv.emplace_back();  // level 1 frontier = {root}
+    lv.emplace_back();  // level 1 frontier = the R roots
     Level& L0 = lv[0];
     Level& L1 = lv[1];
-    std::vector<int16_t> root(n_x);
-    for (int i = 0; i < n_x; ++i) root[i] = (int16_t)(i + 1);
-    L1.P = 1;
-    L1.LS = round_ls(n_x);
+    L1.P = R;
+    L1.LS = round_ls(c->nx_max);
     L1.pstride = blob_stride(L1.LS);
-    std::vector<unsigned char> blob(L1.pstride);
-    fill_blob(blob.data(), L1.LS, root.data(), n_x, c->h_pow.data(), c->RD.rid1);
+    std::vector<unsigned char> blob((size_t)R * L1.pstride);
+    std::vector<int32_t> len(R), id(R);
+    std::vector<uint8_t> dupok(R, (1 <= o.maxdup) ? 1 : 0);  // duplication_count(root) == 1 (solver.jl:611)
+    std::vector<uint16_t> rid(R);
+    std::vector<uint64_t> d0(R);
+    std::vector<uint32_t> iota(R);
+    std::vector<uint16_t> rl(R);
+    std::vector<int16_t> root;
+    for (int r = 0; r < R; ++r) {
+      const int n_x = c->RH[r].n_x;
+      root.resize(n_x);
+      for (int i = 0; i < n_x; ++i) root[i] = (int16_t)(i + 1);
+      fill_blob(blob.data() + (size_t)r * L1.pstride, L1.LS, root.data(), n_x, c->h_pow.data(), c->RD[r].rid1);
+      len[r] = n_x;
+      id[r] = r + 1;
+      rid[r] = (uint16_t)r;
+      d0[r] = pack_desc((uint32_t)r, 0, 0, KIND_ID);
+      iota[r] = (uint32_t)r;
+      rl[r] = (uint16_t)n_x;
+    }
     h2d(c, L1.fblob.ensure(blob.size()), blob.data(), blob.size());
-    const int32_t len = n_x, id = 1;
-    const uint8_t dupok = (1 <= o.maxdup) ? 1 : 0;  // duplication_count(root) == 1 (solver.jl:611)
-    h2d(c, L1.flen.ensure(4), &len, 4);
-    h2d(c, L1.fid.ensure(4), &id, 4);
-    h2d(c, L1.fdup.ensure(1), &dupok, 1);
-    CK(spin_sync(s));
-    // level 0: one pseudo candidate (the root itself, KIND_ID over frontier slot 0 of level 1), id 1
-    L0.G = 1;
+    h2d(c, L1.flen.ensure((size_t)R * 4), len.data(), (size_t)R * 4);
+    h2d(c, L1.fid.ensure((size_t)R * 4), id.data(), (size_t)R * 4);
+    h2d(c, L1.fdup.ensure((size_t)R), dupok.data(), (size_t)R);
+    h2d(c, L1.frid.ensure((size_t)R * 2), rid.data(), (size_t)R * 2);
+    L1.fstart.resize(R + 1);
+    for (int r = 0; r <= R; ++r) L1.fstart[r] = (uint32_t)r;
+    // level 0: one pseudo candidate per region (the root itself, KIND_ID over its level-1 frontier slot), ids 1..R
+    L0.G = (uint32_t)R;
     L0.gbase = 0;
-    L0.n_new = 1;
+    L0.n_new = (uint32_t)R;
     L0.id_base = 1;
-    const uint64_t d0 = pack_desc(0, 0, 0, KIND_ID);
-    const int32_t one = 1;
-    const uint32_t zero = 0;
-    h2d(c, L0.desc.ensure(8), &d0, 8);
-    h2d(c, L0.cand_id.ensure(4), &one, 4);
-    h2d(c, L0.newlist.ensure(4), &zero, 4);
-    L0.k3.ensure(4);
-    L0.cost.ensure(4);
-    L0.total.ensure(4);
-    // frontier view for scoring the root: borrow level 1's frontier
-    n_ids = 1;
-    gtotal = 1;
+    L0.fstart = L0.cstart = L0.nstart = L1.fstart;
+    h2d(c, L0.desc.ensure((size_t)R * 8), d0.data(), (size_t)R * 8);
+    h2d(c, L0.cand_id.ensure((size_t)R * 4), id.data(), (size_t)R * 4);
+    h2d(c, L0.newlist.ensure((size_t)R * 4), iota.data(), (size_t)R * 4);
+    h2d(c, L0.nrid.ensure((size_t)R * 2), rid.data(), (size_t)R * 2);
+    h2d(c, c->new_len.ensure((size_t)R * 2, true), rl.data(), (size_t)R * 2);
+    std::vector<int32_t> k3i(R, 0), ci(R, -1), ti(R, 0);
+    h2d(c, L0.k3.ensure((size_t)R * 4), k3i.data(), (size_t)R * 4);
+    h2d(c, L0.cost.ensure((size_t)R * 4), ci.data(), (size_t)R * 4);
+    h2d(c, L0.total.ensure((size_t)R * 4), ti.data(), (size_t)R * 4);
+    n_ids = R;
+    gtotal = (uint32_t)R;
     // dedup table
     c->table_cap = 0;  // logical capacity; the physical buffer is kept across solves
-    table_reserve(c, 1 << 15);
-    c->launches += launch_insert_root(L1.fblob.as<int16_t>(), n_x, c->d_pow.as<U4>(), c->RD.rid1, c->table.as<uint64_t>(),
-                                      c->table_cap - 1, s);
-    // score the root (solver.jl:599) -- its score never updates `best` (:606)
+    table_reserve(c, (uint64_t)(1 << 15) + 4 * (uint64_t)R);
+    c->launches += launch_insert_roots(L1.fblob.as<unsigned char>(), L1.pstride, L1.flen.as<int32_t>(), R, c->d_pow.as<U4>(),
+                                       c->d_regions.as<RegionDev>(), c->table.as<uint64_t>(), c->table_cap - 1, s);
     int32_t* misc = (int32_t*)c->misc.ensure(256);
     CK(cudaMemsetAsync(misc, 0, 256, s));
-    std::vector<uint32_t> hist(HIST_N, 0);
-    const uint16_t rl = (uint16_t)n_x;
-    h2d(c, c->new_len.ensure(2), &rl, 2);
-    if (early_exit(n_x, c->RD.n_y)) {
-      root_k3 = 0;
-      root_cost = -1;
-      root_total = 0;
-      const int32_t v[3] = {0, -1, 0};
-      h2d(c, L0.k3.p, &v[0], 4);
-      h2d(c, L0.cost.p, &v[1], 4);
-      h2d(c, L0.total.p, &v[2], 4);
-      CK(spin_sync(s));
-    } else {
-      hist[bucket_key(n_x, 0)] = 1;
+    CK(cudaMemsetAsync(c->best.ensure((size_t)(R + 1) * 4), 0, (size_t)(R + 1) * 4, s));
+    CK(spin_sync(s));
+    // score the roots (solver.jl:599) -- a root's score never updates `best` (:606): dummy best array
+    const int lcap = c->nx_max + 1;
+    std::vector<uint32_t> hist((size_t)R * lcap * NSUB, 0);
+    bool any = false;
+    for (int r = 0; r < R; ++r)
+      if (!early_exit(c->RH[r].n_x, c->RH[r].n_y)) {
+        hist[bucket_key(r, lcap, c->RH[r].n_x, (uint32_t)r)] += 1;
+        any = true;
+      }
+    if (any) {
       ScoreView view = view_of(L0);  // candidates of level 0 against the frontier of level 1
-      view.F = L1.frontier();
-      run_scoring(c, view, hist.data(), n_x, 0, o.flags, misc + 1 /*dummy best*/, nullptr);
-      int32_t v[3];
-      d2h(c, &v[0], L0.k3.p, 4);
-      d2h(c, &v[1], L0.cost.p, 4);
-      d2h(c, &v[2], L0.total.p, 4);
-      CK(spin_sync(s));
-      root_k3 = v[0];
-      root_cost = v[1];
-      root_total = v[2];
+      view.F = frontier_of(L1);
+      int* dummy_best = (int*)c->flag.ensure((size_t)(R + 1) * 4, true);
+      CK(cudaMemsetAsync(dummy_best, 0, (size_t)(R + 1) * 4, s));
+      run_scoring(c, view, hist.data(), lcap, L0.nrid.as<uint16_t>(), 0, o.flags, dummy_best, nullptr);
+    }
+    d2h(c, k3i.data(), L0.k3.p, (size_t)R * 4);
+    d2h(c, ci.data(), L0.cost.p, (size_t)R * 4);
+    d2h(c, ti.data(), L0.total.p, (size_t)R * 4);
+    CK(spin_sync(s));
+    for (int r = 0; r < R; ++r) {
+      root_k3[r] = k3i[r];
+      root_cost[r] = ci[r];
+      root_total[r] = ti[r];
     }
   }
 
@@ -612,16 +758,18 @@ struct Search {
                                  " were merged into a different index (fingerprint collision)");
   }
 
-  // one BFS level: expand lv[d]'s frontier.  Returns false when the frontier is empty.
+  // one BFS level: expand lv[d]'s frontier (all regions together).  Returns false when nothing new was found.
   bool run_level(int d) {
     cudaStream_t s = c->stream;
     Level& L = lv[d];
-    int32_t* misc = (int32_t*)c->misc.p;  // [0]=best_k3, [1]=dummy, [2]=maxlen, [4..]=totals
-    st.frontier[d - 1] = L.P;
+    int32_t* misc = (int32_t*)c->misc.p;  // [2]=maxlen, [4..]=totals
+    for (int r = 0; r < R; ++r) rst[r].frontier[d - 1] = L.fstart[r + 1] - L.fstart[r];
+    L.cstart.assign(R + 1, 0);
+    L.nstart.assign(R + 1, 0);
     if (L.P == 0) return false;
     ExpandArgs E{};
-    E.R = c->RD;
-    E.F = L.frontier();
+    E.F = frontier_of(L);
+    E.nx_max = c->nx_max;
     E.cnt = (uint32_t*)c->cnt.ensure((size_t)L.P * 4, true);
     E.maxlen = misc + 2;
     E.force_pairs = (o.flags & NW_FLAG_PAIR_EXPAND) ? 1 : 0;
@@ -631,17 +779,24 @@ struct Search {
     uint32_t* off = (uint32_t*)c->off.ensure((size_t)L.P * 4, true);
     uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items((uint64_t)L.P) * 4, true);
     c->launches += launch_scan(E.cnt, off, (uint64_t)L.P, bsum, (uint32_t*)(misc + 4), s);
+    if (R > 1) gather_async(off, L.fstart, (uint32_t)L.P, 0xffffffffu);  // first candidate of every region
     d2h(c, pin_u32(), misc, 32);
+    if (R > 1) d2h(c, pinned((size_t)(R + 1) * 4 + 256) + 64, c->gather.p, (size_t)(R + 1) * 4);
     CK(spin_sync(s));
     CK(cudaGetLastError());
     const uint32_t G = pin_u32()[4];
     const int maxlen = (int)pin_u32()[2];
+    for (int r = 0; r <= R; ++r) {
+      const uint32_t v = R > 1 ? pin_u32()[64 + r] : (r == 0 ? 0u : G);
+      L.cstart[r] = v == 0xffffffffu ? G : v;
+    }
     if (maxlen > LMAX) fail(NW_ERR_RANGE, "a child index exceeds the supported length");
     if ((uint64_t)gtotal + G >= 0xfffffff0ull || G >= 0x7ffffff0u) fail(NW_ERR_NOMEM, "more than 2^32 candidates");
     L.G = G;
     L.gbase = gtotal;
     L.id_base = n_ids + 1;
-    st.generated[d - 1] = G;
+    for (int r = 0; r < R; ++r) rst[r].generated[d - 1] = L.cstart[r + 1] - L.cstart[r];
+    level_maxlen = maxlen;
     if (G == 0) {
       L.n_new = 0;
       return false;
@@ -665,13 +820,22 @@ struct Search {
     uint32_t* newrank = (uint32_t*)c->newrank.ensure((size_t)G * 4, true);
     bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(G) * 4, true);
     c->launches += launch_scan(is_new, newrank, G, bsum, (uint32_t*)(misc + 5), s);
+    if (R > 1) gather_async(newrank, L.cstart, G, 0xffffffffu);  // first fresh rank of every region
     d2h(c, pin_u32(), misc, 32);
+    if (R > 1) d2h(c, pin_u32() + 64, c->gather.p, (size_t)(R + 1) * 4);
     CK(spin_sync(s));
     CK(cudaGetLastError());
     const uint32_t n_new = pin_u32()[5];
+    for (int r = 0; r <= R; ++r) {
+      const uint32_t v = R > 1 ? pin_u32()[64 + r] : (r == 0 ? 0u : n_new);
+      L.nstart[r] = v == 0xffffffffu ? n_new : v;
+    }
     L.n_new = n_new;
-    st.scored[d - 1] = n_new;
-    // ids / edges / histogram of child lengths
+    for (int r = 0; r < R; ++r) rst[r].scored[d - 1] = L.nstart[r + 1] - L.nstart[r];
+    // ids / edges / histogram of (region, child length)
+    const int lcap = std::min(std::max(maxlen, L.LS), LMAX) + 1;  // longest possible child of this level, + 1
+    const size_t nbins = (size_t)R * lcap * NSUB;
+    if (nbins > ((size_t)64 << 20)) fail(NW_ERR_NOMEM, "too many (region, length) buckets in one batch");
     AssignArgs A{};
     A.LT.n_levels = d;
     for (int l = 0; l < d; ++l) {
@@ -686,45 +850,47 @@ struct Search {
     A.newrank = newrank;
     A.desc = E.desc;
     A.front_len = L.flen.as<int32_t>();
+    A.front_rid = R > 1 ? L.frid.as<uint16_t>() : nullptr;
+    A.regions = c->d_regions.as<RegionDev>();
+    A.lcap = lcap;
     A.gbase = L.gbase;
     A.G = G;
     A.id_base = L.id_base;
-    A.n_y = c->RD.n_y;
     A.force = 0;
     A.cand_id = (int32_t*)L.cand_id.ensure((size_t)G * 4);
-    A.newlist = (uint32_t*)L.newlist.ensure((size_t)n_new * 4);
-    A.new_len = (uint16_t*)c->new_len.ensure((size_t)n_new * 2, true);
-    A.k3 = (int32_t*)L.k3.ensure((size_t)n_new * 4);
-    A.cost = (int32_t*)L.cost.ensure((size_t)n_new * 4);
-    A.total = (int32_t*)L.total.ensure((size_t)n_new * 4);
-    const int lmax = std::min(std::max(maxlen, L.LS), LMAX);  // longest possible child of this level
-    const size_t nbins = (size_t)(lmax + 1) * NSUB;
-    A.hist = (uint32_t*)c->hist.ensure(HIST_N * 4);
+    A.newlist = (uint32_t*)L.newlist.ensure((size_t)std::max<uint32_t>(n_new, 1) * 4);
+    A.new_len = (uint16_t*)c->new_len.ensure((size_t)std::max<uint32_t>(n_new, 1) * 2, true);
+    A.new_rid = (uint16_t*)L.nrid.ensure((size_t)std::max<uint32_t>(n_new, 1) * 2);
+    A.k3 = (int32_t*)L.k3.ensure((size_t)std::max<uint32_t>(n_new, 1) * 4);
+    A.cost = (int32_t*)L.cost.ensure((size_t)std::max<uint32_t>(n_new, 1) * 4);
+    A.total = (int32_t*)L.total.ensure((size_t)std::max<uint32_t>(n_new, 1) * 4);
+    A.hist = (uint32_t*)c->hist.ensure(nbins * 4, true);
     CK(cudaMemsetAsync(A.hist, 0, nbins * 4, s));
     c->launches += launch_assign(A, s);
     if (o.flags & NW_FLAG_VERIFY_DEDUP) verify_level(d, E, is_new, owner, G);
-    uint32_t* hist_h = pin_u32() + 64;
+    uint32_t* hist_h = pinned(nbins * 4 + 1024) + 128;
     d2h(c, hist_h, A.hist, nbins * 4);
     CK(spin_sync(s));
     CK(cudaGetLastError());
-    int64_t cells = 0;
-    run_scoring(c, view_of(L), hist_h, lmax, 0, o.flags, misc + 0, &cells);
-    st.cells[d - 1] = cells;
+    std::vector<int64_t> cells(R, 0);
+    run_scoring(c, ScoreView{frontier_of(L), L.n_new, L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(), L.k3.as<int32_t>(),
+                             L.cost.as<int32_t>(), L.total.as<int32_t>()},
+                hist_h, lcap, L.nrid.as<uint16_t>(), 0, o.flags, c->best.as<int>(), cells.data());
+    for (int r = 0; r < R; ++r) rst[r].cells[d - 1] = cells[r];
     gtotal += G;
     n_ids += (int32_t)n_new;
     return n_new > 0;
   }
 
-  // frontier of level d+1 from the fresh candidates of level d (solver.jl:551-553, :669-672)
+  // frontier of level d+1 from the fresh candidates of level d (solver.jl:551-553, :669-672), per region
   void select_next(int d) {
     cudaStream_t s = c->stream;
-    Level& L = lv[d];
     lv.emplace_back();
     Level& N = lv[d + 1];
-    Level& Lr = lv[d];  // re-take reference (emplace_back may reallocate)
-    (void)L;
+    Level& Lr = lv[d];
     const uint32_t n = Lr.n_new;
     int32_t* misc = (int32_t*)c->misc.p;
+    N.fstart.assign(R + 1, 0);
     if (n == 0) {
       N.P = 0;
       return;
@@ -734,39 +900,61 @@ struct Search {
     uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(n) * 4, true);
     c->launches += launch_valid_flags(Lr.k3.as<int32_t>(), n, flag, s);
     c->launches += launch_scan(flag, pre, n, bsum, (uint32_t*)(misc + 6), s);
+    if (R > 1) gather_async(pre, Lr.nstart, n, 0xffffffffu);  // first valid rank of every region
     d2h(c, pin_u32(), misc, 32);
+    if (R > 1) d2h(c, pin_u32() + 64, c->gather.p, (size_t)(R + 1) * 4);
     CK(spin_sync(s));
     const uint32_t nvalid = pin_u32()[6];
-    uint32_t P2 = nvalid;
+    std::vector<uint32_t> vstart(R + 1);
+    for (int r = 0; r <= R; ++r) {
+      const uint32_t v = R > 1 ? pin_u32()[64 + r] : (r == 0 ? 0u : nvalid);
+      vstart[r] = v == 0xffffffffu ? nvalid : v;
+    }
+    // how many children of every region enter the next frontier
+    std::vector<uint32_t> take(R), ostart(R + 1, 0);
+    for (int r = 0; r < R; ++r) {
+      const uint32_t v = vstart[r + 1] - vstart[r];
+      take[r] = (o.maxwidth >= 0 && (int64_t)v > o.maxwidth) ? (uint32_t)o.maxwidth : v;
+      ostart[r + 1] = ostart[r] + take[r];
+    }
+    const uint32_t P2 = ostart[R];
+    N.fstart = ostart;
+    N.P = (int)P2;
     uint32_t* sel = (uint32_t*)c->sel.ensure((size_t)std::max<uint32_t>(nvalid, 1) * 4, true);
     if (o.maxwidth < 0) {
-      c->launches += launch_compact_ranks(flag, pre, n, sel, s);
-    } else {
+      c->launches += launch_compact_ranks(flag, pre, n, sel, s);  // region-major already (candidates follow parents)
+    } else if (nvalid) {
       uint64_t npad = 2048;
       while (npad < nvalid) npad <<= 1;
       uint64_t* keys = (uint64_t*)c->keys.ensure(npad * 8, true);
-      c->launches += launch_make_keys(Lr.k3.as<int32_t>(), flag, pre, n, keys, nvalid, npad, s);
+      c->launches += launch_make_keys(Lr.k3.as<int32_t>(), R > 1 ? Lr.nrid.as<uint16_t>() : nullptr, flag, pre, n, keys, nvalid,
+                                      npad, s);
       c->launches += launch_sort_u64(keys, npad, s);
-      if ((int64_t)P2 > o.maxwidth) P2 = (uint32_t)o.maxwidth;
-      c->launches += launch_keys_to_sel(keys, P2, sel, s);
+      // sorted keys are region-major: region r occupies [vstart[r], vstart[r+1]); keep its first take[r]
+      uint32_t* seg = (uint32_t*)c->gather.ensure((size_t)(3 * R + 3) * 4, true);
+      std::vector<uint32_t> pack(3 * (size_t)R);
+      for (int r = 0; r < R; ++r) {
+        pack[r] = vstart[r];
+        pack[R + r] = take[r];
+        pack[2 * (size_t)R + r] = ostart[r];
+      }
+      h2d(c, seg, pack.data(), pack.size() * 4);
+      c->launches += launch_take_sorted(keys, nvalid, seg, seg + R, seg + 2 * (size_t)R, sel, s);
+      CK(spin_sync(s));  // pack goes out of scope
     }
-    N.P = (int)P2;
     if (P2 == 0) return;
-    // child lengths are bounded by the level's maxlen (misc[2]) -- use it for the stride
-    int maxlen = (int)pin_u32()[2];
-    if (maxlen < c->RD.n_x) maxlen = c->RD.n_x;
-    // inversions keep the parent's length: include the longest parent
-    maxlen = std::max(maxlen, Lr.LS);
+    int maxlen = std::max(level_maxlen, c->nx_max);
+    maxlen = std::max(maxlen, Lr.LS);  // inversions keep the parent's length
     N.LS = round_ls(maxlen);
     N.pstride = blob_stride(N.LS);
     MaterialiseArgs M{};
-    M.F = Lr.frontier();
+    M.F = frontier_of(Lr);
     M.sel = sel;
     M.newlist = world > 1 ? nullptr : Lr.newlist.as<uint32_t>();  // sharded: descriptors of the merged new ids
     M.desc = world > 1 ? Lr.desc_new.as<uint64_t>() : Lr.desc.as<uint64_t>();
     M.id_base = Lr.id_base;
     M.maxdup = o.maxdup;
-    M.n_x = c->RD.n_x;
+    M.nx_max = c->nx_max;
     M.P2 = (int)P2;
     M.LS2 = N.LS;
     M.pstride2 = N.pstride;
@@ -774,10 +962,48 @@ struct Search {
     M.len2 = (int32_t*)N.flen.ensure((size_t)P2 * 4);
     M.id2 = (int32_t*)N.fid.ensure((size_t)P2 * 4);
     M.dupok2 = (uint8_t*)N.fdup.ensure((size_t)P2);
+    M.rid2 = (uint16_t*)N.frid.ensure((size_t)P2 * 2);
     M.pw = c->d_pow.as<U4>();
-    M.rid1 = c->RD.rid1;
     c->launches += launch_materialise(M, s);
     CK(cudaGetLastError());
+  }
+
+  void pad_levels(int D) {  // levels that were never reached still exist (empty) for the report loops
+    for (int e = 0; e <= D; ++e) {
+      if ((int)lv.size() <= e) lv.emplace_back();
+      Level& L = lv[e];
+      if ((int)L.fstart.size() != R + 1) L.fstart.assign(R + 1, 0);
+      if ((int)L.cstart.size() != R + 1) L.cstart.assign(R + 1, 0);
+      if ((int)L.nstart.size() != R + 1) L.nstart.assign(R + 1, 0);
+    }
+  }
+  // per-region statistics once the search is over (best, ids, timing shared by the batch)
+  void finish_stats(int n_levels) {
+    cudaStream_t s = c->stream;
+    std::vector<int32_t> best(R, 0);
+    d2h(c, best.data(), c->best.p, (size_t)R * 4);
+    CK(spin_sync(s));
+    for (size_t k = 0; k + 1 < lev.size(); k += 2) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, lev[k], lev[k + 1]);
+      st.level_ms[k / 2] = ms;
+    }
+    if (ev0 && ev1) cudaEventElapsedTime(&st.total_ms, ev0, ev1);
+    st.n_levels = n_levels;
+    st.n_ids = n_ids;
+    st.kernel_launches = c->launches;
+    for (int r = 0; r < R; ++r) {
+      best_k3[r] = best[r];
+      nw_stats& q = rst[r];
+      q.n_levels = n_levels;
+      q.total_ms = st.total_ms;
+      for (int l = 0; l < 16; ++l) q.level_ms[l] = st.level_ms[l];
+      q.n_ids = 1;
+      for (int l = 1; l < (int)lv.size(); ++l) q.n_ids += lv[l].nstart[r + 1] - lv[l].nstart[r];
+      q.best = k3_to_score(best_k3[r]);
+      q.kernel_launches = c->launches;
+    }
+    st.best = rst[0].best;
   }
 
   void run() {
@@ -786,10 +1012,8 @@ struct Search {
     CK(cudaEventCreate(&ev1));
     CK(cudaEventRecord(ev0, s));
     init_root();
-    int32_t* misc = (int32_t*)c->misc.p;
-    CK(cudaMemsetAsync(misc, 0, 4, s));  // best_k3 = 0  (best = 0.0, solver.jl:660)
     const int D = std::min(o.maxdepth, MAX_LEVELS - 1);
-    st.n_levels = 0;
+    int n_levels = 0;
     for (int d = 1; d <= D; ++d) {
       cudaEvent_t a, b;
       CK(cudaEventCreate(&a));
@@ -798,36 +1022,21 @@ struct Search {
       lev.push_back(b);
       CK(cudaEventRecord(a, s));
       const bool any = run_level(d);
-      st.n_levels = d;
-      if (d < D) {
-        select_next(d);
-      }
+      n_levels = d;
+      if (d < D) select_next(d);
       CK(cudaEventRecord(b, s));
       // the frontier blob of level d is no longer needed once level d+1 is materialised (ids are kept)
       if (!(o.flags & NW_FLAG_VERIFY_DEDUP)) lv[d].fblob.release();  // the verifier re-reads old frontiers
       if (d < D && (!any || lv[d + 1].P == 0)) {
-        // solver.jl keeps looping over empty frontiers; nothing more can be generated
-        for (int e = d + 1; e <= D; ++e) {
-          if ((int)lv.size() <= e) lv.emplace_back();
-          st.n_levels = e;
-        }
+        n_levels = D;  // solver.jl keeps looping over empty frontiers; nothing more can be generated
         break;
       }
     }
-    d2h(c, pin_u32(), misc, 4);
+    pad_levels(D);
     CK(cudaEventRecord(ev1, s));
     CK(spin_sync(s));
     CK(cudaGetLastError());
-    best_k3 = (int)pin_u32()[0];
-    for (size_t k = 0; k + 1 < lev.size(); k += 2) {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, lev[k], lev[k + 1]);
-      st.level_ms[k / 2] = ms;
-    }
-    cudaEventElapsedTime(&st.total_ms, ev0, ev1);
-    st.n_ids = n_ids;
-    st.best = k3_to_score(best_k3);
-    st.kernel_launches = c->launches;
+    finish_stats(n_levels);
   }
 
   // =================================================================================================
@@ -839,8 +1048,6 @@ struct Search {
     CK(cudaEventCreate(&ev1));
     CK(cudaEventRecord(ev0, s));
     init_root();
-    int32_t* misc = (int32_t*)c->misc.p;
-    CK(cudaMemsetAsync(misc, 0, 4, s));
     cur_level = 1;
     dist_more = o.maxdepth >= 1;
     st.n_levels = 0;
@@ -852,16 +1059,18 @@ struct Search {
     const int d = cur_level;
     Level& L = lv[d];
     int32_t* misc = (int32_t*)c->misc.p;
-    st.frontier[d - 1] = L.P;
+    rst[0].frontier[d - 1] = L.P;
     st.n_levels = d;
     L.G = L.G_all = L.n_local_new = L.n_new = 0;
     L.gbase = gtotal;
     L.id_base = n_ids + 1;
+    L.cstart.assign(2, 0);
+    L.nstart.assign(2, 0);
     curE = ExpandArgs{};
     if (L.P == 0) return 0;
     ExpandArgs E{};
-    E.R = c->RD;
-    E.F = L.frontier();
+    E.F = frontier_of(L);
+    E.nx_max = c->nx_max;
     E.cnt = (uint32_t*)c->cnt.ensure((size_t)L.P * 4, true);
     E.maxlen = misc + 2;
     E.own_mod = 1;
@@ -885,7 +1094,7 @@ struct Search {
     if ((uint64_t)gtotal + G_all >= 0xfffffff0ull || G_all >= 0x7ffffff0u) fail(NW_ERR_NOMEM, "more than 2^32 candidates");
     L.G = G;
     L.G_all = G_all;
-    st.generated[d - 1] = G_all;
+    rst[0].generated[d - 1] = G_all;
     if (G_all == 0) return 0;
     table_reserve(c, (uint64_t)n_ids + G_all);  // room for every rank's records: no rehash during the merge
     E.off = off_loc;
@@ -922,32 +1131,37 @@ struct Search {
     A.newrank = newrank;
     A.desc = E.desc;
     A.front_len = L.flen.as<int32_t>();
+    A.front_rid = nullptr;
+    A.regions = c->d_regions.as<RegionDev>();
+    const int lcap = std::min(std::max(maxlen, L.LS), LMAX) + 1;
+    const size_t nbins = (size_t)lcap * NSUB;
+    A.lcap = lcap;
     A.gbase = L.gbase;
     A.G = G;
     A.id_base = 0;
-    A.n_y = c->RD.n_y;
     A.force = 0;
     A.skip_ids = 1;
     A.cand_id = nullptr;
     A.newlist = (uint32_t*)L.newlist.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
     A.new_len = (uint16_t*)c->new_len.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 2, true);
+    A.new_rid = (uint16_t*)L.nrid.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 2);
     A.k3 = (int32_t*)L.l_k3.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
     A.cost = (int32_t*)L.l_cost.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
     A.total = (int32_t*)L.l_total.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
-    const int lmax = std::min(std::max(maxlen, L.LS), LMAX);
-    const size_t nbins = (size_t)(lmax + 1) * NSUB;
-    A.hist = (uint32_t*)c->hist.ensure(HIST_N * 4);
+    A.hist = (uint32_t*)c->hist.ensure(nbins * 4, true);
     CK(cudaMemsetAsync(A.hist, 0, nbins * 4, s));
     c->launches += launch_assign(A, s);
-    uint32_t* hist_h = pin_u32() + 64;
+    uint32_t* hist_h = pinned(nbins * 4 + 1024) + 128;
     d2h(c, hist_h, A.hist, nbins * 4);
     CK(spin_sync(s));
     CK(cudaGetLastError());
     int64_t cells = 0;
-    ScoreView V{L.frontier(), n_loc, L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(), L.l_k3.as<int32_t>(),
+    ScoreView V{frontier_of(L), n_loc, L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(), L.l_k3.as<int32_t>(),
                 L.l_cost.as<int32_t>(), L.l_total.as<int32_t>()};
-    run_scoring(c, V, hist_h, lmax, 0, o.flags, misc + 1 /*best is taken from the merged records*/, &cells);
-    st.cells[d - 1] = cells;  // cells evaluated by THIS rank (includes candidates another rank discovered first)
+    int* dummy_best = (int*)c->flag.ensure(16, true);  // best is taken from the merged records
+    CK(cudaMemsetAsync(dummy_best, 0, 8, s));
+    run_scoring(c, V, hist_h, lcap, L.nrid.as<uint16_t>(), 0, o.flags, dummy_best, &cells);
+    rst[0].cells[d - 1] = cells;  // cells evaluated by THIS rank (includes candidates another rank discovered first)
     CK(spin_sync(s));
     return n_loc;
   }
@@ -999,7 +1213,7 @@ struct Search {
           c->launches += launch_dist_scatter(rec + (size_t)r * stride, (uint32_t)counts[r], rslot + (size_t)r * stride,
                                              c->table.as<uint64_t>(), L.gbase, grank, L.id_base, L.k3.as<int32_t>(),
                                              L.cost.as<int32_t>(), L.total.as<int32_t>(), L.desc_new.as<uint64_t>(),
-                                             L.gid_at.as<int32_t>(), misc + 0, s);
+                                             L.gid_at.as<int32_t>(), c->best.as<int>(), s);
         if (L.G) {  // ids of the indices this rank's candidates produced (provenance edges)
           LevelTable LT{};
           LT.n_levels = d + 1;
@@ -1012,11 +1226,12 @@ struct Search {
                                              (int32_t*)L.cand_id.ensure((size_t)L.G * 4), s);
         }
       }
-      st.scored[d - 1] = n_new;
+      rst[0].scored[d - 1] = n_new;
+      L.cstart = {0u, L.G};
+      L.nstart = {0u, n_new};
       gtotal += L.G_all;
       n_ids += (int32_t)n_new;
-      // select_next reads the level's maxlen from the pinned copy of misc: restore what dist_expand saw
-      CK(cudaMemcpyAsync(misc + 2, &dist_maxlen, 4, cudaMemcpyHostToDevice, s));
+      level_maxlen = dist_maxlen;
     }
     bool more = false;
     if (d < D) {
@@ -1027,17 +1242,10 @@ struct Search {
     CK(cudaGetLastError());
     lv[d].fblob.release();
     if (!more) {
-      for (int e = d + 1; e <= D; ++e) {
-        if ((int)lv.size() <= e) lv.emplace_back();
-        st.n_levels = e;
-      }
-      d2h(c, pin_u32(), misc, 4);
+      pad_levels(D);
       CK(cudaEventRecord(ev1, s));
       CK(spin_sync(s));
-      best_k3 = (int)pin_u32()[0];
-      cudaEventElapsedTime(&st.total_ms, ev0, ev1);
-      st.n_ids = n_ids;
-      st.best = k3_to_score(best_k3);
+      finish_stats(D);
     }
     dist_more = more;
     cur_level = d + 1;
@@ -1061,7 +1269,8 @@ struct Search {
     }
     CK(spin_sync(c->stream));
     build_nodes(needed, edges);
-    enumerate(R, dist_k3_min);
+    build_local_ids();
+    enumerate(R, 0, dist_k3_min);
   }
 
   // ---- report: get_good_trajectories (solver.jl:727-745) ----
@@ -1143,7 +1352,7 @@ struct Search {
     const int nl = (int)lv.size();
     std::sort(edges.begin(), edges.end(), [](const EdgeRec& a, const EdgeRec& b) { return a.gpos < b.gpos; });
     nodes.clear();
-    nodes[1] = Node{root_k3, root_cost, root_total, {}};
+    for (int r = 0; r < R; ++r) nodes[r + 1] = Node{root_k3[r], root_cost[r], root_total[r], {}};
     for (const EdgeRec& e : edges) nodes[e.child].in.push_back(e);
     uint32_t cap = std::max<uint32_t>(id_cap_hint, 1u << 14);
     std::vector<IdRec> hi;
@@ -1201,10 +1410,10 @@ struct Search {
     std::vector<EdgeRec> stack;              // edges from the target backwards
     int64_t limit = -1, emitted = 0;
     nw_result* R = nullptr;
-    int cur_id = 0, cur_k3 = 0;
+    int cur_id = 0, cur_k3 = 0, rid = 0;
     explicit Enumerator(Search& s) : S(s) {}
     bool reach(int32_t id, int r) {
-      if (id == 1) return r == 0;
+      if (id <= S.R) return r == 0;  // ids 1..R are the roots of the R regions
       if (r <= 0) return false;
       const int64_t key = ((int64_t)id << 8) | r;
       auto it = memo.find(key);
@@ -1226,9 +1435,14 @@ struct Search {
       const Node& nd = S.nodes[cur_id];
       R->t_score.push_back(score_f32(cur_k3));
       R->t_k3.push_back(cur_k3);
-      R->t_id.push_back(cur_id);
-      R->t_cost.push_back(nd.cost < 0 ? nd.cost : (int64_t)nd.cost * S.c->RH.gcd);
-      R->t_total.push_back((int64_t)nd.total * S.c->RH.gcd);
+      {
+        int lvl, rr;
+        int64_t local;
+        S.locate(cur_id, lvl, rr, local);
+        R->t_id.push_back(local);
+      }
+      R->t_cost.push_back(nd.cost < 0 ? nd.cost : (int64_t)nd.cost * S.c->RH[rid].gcd);
+      R->t_total.push_back((int64_t)nd.total * S.c->RH[rid].gcd);
       std::string& line = R->tsv;
       line += score_string(cur_k3);
       line += '\t';
@@ -1255,7 +1469,7 @@ struct Search {
     }
     // all paths of exactly r more moves from `id` back to the root, in the reference's enumeration order
     void walk(int32_t id, int r) {
-      if (id == 1) {
+      if (id <= S.R) {
         if (r == 0) emit();
         return;
       }
@@ -1272,19 +1486,19 @@ struct Search {
   };
 
   // thresholds of the report (identical on every rank): k3_min from minreport, k3_star/quota from maxreport
-  void report_thresholds(int& k3_min, int& k3_star, int64_t& quota) {
-    const double best = k3_to_score(best_k3);
-    const double thr = o.minreport * best;  // solver.jl:733
-    // smallest k3 whose Float32 score passes `score >= suboptimality * best` (monotone in k3)
-    k3_min = 100001;
-    {
-      int lo = 0, hi = 100001;  // first k3 in [0, 100000] with (double)(float)(k3/1000) >= thr
-      while (lo < hi) {
-        const int mid = (lo + hi) / 2;
-        if ((double)score_f32(mid) >= thr) hi = mid; else lo = mid + 1;
-      }
-      k3_min = lo;
+  // smallest k3 whose Float32 score passes `score >= suboptimality * best` (solver.jl:733; monotone in k3)
+  int k3_min_of(int best) const {
+    const double thr = o.minreport * k3_to_score(best);
+    int lo = 0, hi = 100001;  // first k3 in [0, 100000] with (double)(float)(k3/1000) >= thr
+    while (lo < hi) {
+      const int mid = (lo + hi) / 2;
+      if ((double)score_f32(mid) >= thr) hi = mid; else lo = mid + 1;
     }
+    return lo;
+  }
+  // thresholds of a single-region report (identical on every rank): k3_min from minreport, k3_star/quota from maxreport
+  void report_thresholds(int& k3_min, int& k3_star, int64_t& quota) {
+    k3_min = k3_min_of(best_k3[0]);
     k3_star = -1;
     quota = 0;
     if (o.maxreport >= 0 && n_ids > o.maxreport) {
@@ -1296,7 +1510,7 @@ struct Search {
       std::vector<uint32_t> hh(100002, 0);
       if (k3_min <= 100000) d2h(c, hh.data() + k3_min, hist + k3_min, (size_t)(100001 - k3_min) * 4);  // bins below are empty
       CK(spin_sync(s));
-      if (root_k3 >= 0 && root_k3 >= k3_min) hh[root_k3] += 1;
+      if (root_k3[0] >= 0 && root_k3[0] >= k3_min) hh[root_k3[0]] += 1;
       int64_t cum = 0;
       for (int k = 100000; k >= 0; --k) {
         if (cum + hh[k] >= o.maxreport) {
@@ -1306,27 +1520,131 @@ struct Search {
         }
         cum += hh[k];
       }
-      if (k3_star >= 0 && root_k3 == k3_star) quota -= 1;  // the root (id 1) is the first of its tie bin
+      if (k3_star >= 0 && root_k3[0] == k3_star) quota -= 1;  // the root (id 1) is the first of its tie bin
     }
   }
-  void report(nw_result* R) {
+
+  // ---- global id <-> (level, region, per-region id).  Ids are assigned level by level in global discovery order and
+  // a level's candidates are region-major, so the fresh ids of one region at one level are contiguous. ----
+  std::vector<std::vector<int64_t>> local_base;  // [level][region]: per-region id of the region's first fresh id
+  void build_local_ids() {
+    const int nl = (int)lv.size();
+    local_base.assign(nl, std::vector<int64_t>(R, 2));
+    for (int l = 2; l < nl; ++l)
+      for (int r = 0; r < R; ++r) local_base[l][r] = local_base[l - 1][r] + (lv[l - 1].nstart[r + 1] - lv[l - 1].nstart[r]);
+  }
+  void locate(int32_t gid, int& level, int& rid, int64_t& local) const {
+    if (gid <= R) {
+      level = 0;
+      rid = gid - 1;
+      local = 1;
+      return;
+    }
+    int l = 1;
+    while (l + 1 < (int)lv.size() && lv[l + 1].n_new > 0 && gid >= lv[l + 1].id_base) ++l;
+    const uint32_t rank = (uint32_t)(gid - lv[l].id_base);
+    const auto& ns = lv[l].nstart;
+    rid = (int)(std::upper_bound(ns.begin(), ns.end(), rank) - ns.begin()) - 1;
+    if (rid < 0) rid = 0;
+    if (rid >= R) rid = R - 1;
+    level = l;
+    local = local_base[l][rid] + (rank - ns[rid]);
+  }
+
+  // one search, one region (also every rank of a sharded search)
+  void report(nw_result* out) {
     int k3_min, k3_star;
     int64_t quota;
     report_thresholds(k3_min, k3_star, quota);
     extract(k3_min, k3_star, quota);
-    enumerate(R, k3_min);
+    build_local_ids();
+    enumerate(out, 0, k3_min);
   }
-  void enumerate(nw_result* R, int k3_min) {
+
+  // regionfile mode: several regions searched together; out[r] receives region r's report
+  void report_many(nw_result** out) {
+    if (R == 1) {
+      report(out[0]);
+      return;
+    }
+    cudaStream_t s = c->stream;
+    int32_t* misc = (int32_t*)c->misc.p;
+    build_local_ids();
+    std::vector<int32_t> k3min(R);
+    for (int r = 0; r < R; ++r) k3min[r] = k3_min_of(best_k3[r]);
+    int32_t* d_k3min = (int32_t*)c->gather.ensure((size_t)R * 4, true);
+    h2d(c, d_k3min, k3min.data(), (size_t)R * 4);
+    // ids that pass their region's threshold (usually few): (gid, k3, rid) records, selected per region on the host
+    struct Qual {
+      int32_t gid, k3, rid, pad;
+    };
+    std::vector<Qual> q;
+    uint32_t cap = 1u << 16;
+    for (;;) {
+      Qual* buf = (Qual*)c->keys.ensure((size_t)cap * sizeof(Qual));
+      CK(cudaMemsetAsync(misc + 9, 0, 4, s));
+      for (size_t l = 1; l < lv.size(); ++l)
+        c->launches += launch_qual_append(lv[l].k3.as<int32_t>(), lv[l].nrid.as<uint16_t>(), d_k3min, lv[l].id_base,
+                                          lv[l].n_new, buf, cap, (uint32_t*)(misc + 9), s);
+      d2h(c, pin_u32(), misc, 64);
+      CK(spin_sync(s));
+      const uint32_t n = pin_u32()[9];
+      if (n <= cap) {
+        q.resize(n);
+        if (n) {
+          d2h(c, q.data(), buf, (size_t)n * sizeof(Qual));
+          CK(spin_sync(s));
+        }
+        break;
+      }
+      cap = n + n / 8;
+    }
+    std::vector<std::vector<std::pair<int32_t, int32_t>>> good(R);  // (-k3, gid)
+    for (int r = 0; r < R; ++r)
+      if (root_k3[r] >= 0 && root_k3[r] >= k3min[r]) good[r].emplace_back(-root_k3[r], r + 1);
+    for (const Qual& e : q) good[e.rid].emplace_back(-e.k3, e.gid);
+    std::vector<int32_t> gids;
+    for (int r = 0; r < R; ++r) {
+      std::sort(good[r].begin(), good[r].end());
+      // only the first maxreport ids in (score desc, id asc) order can own one of the first maxreport trajectories
+      if (o.maxreport >= 0 && (int64_t)good[r].size() > o.maxreport) good[r].resize((size_t)o.maxreport);
+      for (auto& g : good[r]) gids.push_back(g.second);
+    }
+    uint8_t* needed = (uint8_t*)c->flag.ensure((size_t)n_ids + 16, true);
+    CK(cudaMemsetAsync(needed, 0, (size_t)n_ids + 16, s));
+    if (!gids.empty()) {
+      int32_t* dg = (int32_t*)c->keys.ensure(gids.size() * 4, true);
+      h2d(c, dg, gids.data(), gids.size() * 4);
+      c->launches += launch_set_needed(dg, (uint32_t)gids.size(), needed, s);
+      CK(spin_sync(s));
+    }
+    for (int pass = 1; pass <= o.maxdepth + 1; ++pass) extract_mark(needed, pass);
+    const uint32_t ne = extract_edges(needed);
+    std::vector<EdgeRec> he(ne);
+    if (ne) {
+      d2h(c, he.data(), c->edgebuf.p, (size_t)ne * sizeof(EdgeRec));
+      CK(spin_sync(s));
+    }
+    build_nodes(needed, he);
+    for (int r = 0; r < R; ++r) enumerate_list(out[r], r, good[r]);
+  }
+
+  void enumerate(nw_result* out, int rid, int k3_min) {
     std::vector<std::pair<int32_t, int32_t>> good;  // (-k3, id): canonical Dict order = ascending discovery id
     for (auto& kv : nodes) {
       const int k3 = kv.second.k3;
       if (k3 >= 0 && k3 >= k3_min) good.emplace_back(-k3, kv.first);
     }
     std::sort(good.begin(), good.end());
+    enumerate_list(out, rid, good);
+  }
+  // trajectories of the ids in `good` (sorted by score desc, id asc), in final report order, up to maxreport
+  void enumerate_list(nw_result* out, int rid, const std::vector<std::pair<int32_t, int32_t>>& good) {
     Enumerator E(*this);
     E.limit = o.maxreport;
-    E.R = R;
-    R->t_off.push_back(0);
+    E.R = out;
+    E.rid = rid;
+    out->t_off.push_back(0);
     size_t g0 = 0;
     while (g0 < good.size() && !E.full()) {
       size_t g1 = g0;
@@ -1341,19 +1659,26 @@ struct Search {
     }
   }
 
-  void dump_ids(nw_result* R) {
+  // keep_ids diagnostics: every id and every provenance edge, per region, with per-region (reference) ids
+  void dump_ids(nw_result** out) {
     cudaStream_t s = c->stream;
-    R->id_score.assign(n_ids, 0.f);
-    R->id_cost.assign(n_ids, -1);
-    R->id_total.assign(n_ids, 0);
-    R->id_level.assign(n_ids, 0);
-    auto put = [&](int32_t id, int k3, int cost, int total, int level) {
-      R->id_score[id - 1] = score_f32(k3);
-      R->id_cost[id - 1] = cost < 0 ? cost : (int64_t)cost * c->RH.gcd;
-      R->id_total[id - 1] = (int64_t)total * c->RH.gcd;
-      R->id_level[id - 1] = level;
+    if (local_base.empty()) build_local_ids();
+    for (int r = 0; r < R; ++r) {
+      nw_result* Q = out[r];
+      const size_t n = (size_t)rst[r].n_ids;
+      Q->id_score.assign(n, 0.f);
+      Q->id_cost.assign(n, -1);
+      Q->id_total.assign(n, 0);
+      Q->id_level.assign(n, 0);
+    }
+    auto put = [&](int r, int64_t id, int k3, int cost, int total, int level) {
+      nw_result* Q = out[r];
+      Q->id_score[id - 1] = score_f32(k3);
+      Q->id_cost[id - 1] = cost < 0 ? cost : (int64_t)cost * c->RH[r].gcd;
+      Q->id_total[id - 1] = (int64_t)total * c->RH[r].gcd;
+      Q->id_level[id - 1] = level;
     };
-    put(1, root_k3, root_cost, root_total, 0);
+    for (int r = 0; r < R; ++r) put(r, 1, root_k3[r], root_cost[r], root_total[r], 0);
     for (int l = 1; l < (int)lv.size(); ++l) {
       const Level& L = lv[l];
       if (L.n_new) {
@@ -1362,7 +1687,9 @@ struct Search {
         d2h(c, cost.data(), L.cost.p, (size_t)L.n_new * 4);
         d2h(c, total.data(), L.total.p, (size_t)L.n_new * 4);
         CK(spin_sync(s));
-        for (uint32_t r = 0; r < L.n_new; ++r) put(L.id_base + (int32_t)r, k3[r], cost[r], total[r], l);
+        for (int r = 0; r < R; ++r)
+          for (uint32_t q = L.nstart[r]; q < L.nstart[r + 1]; ++q)
+            put(r, local_base[l][r] + (q - L.nstart[r]), k3[q], cost[q], total[q], l);
       }
       if (L.G) {
         std::vector<int32_t> cid(L.G), fid(L.P);
@@ -1371,12 +1698,19 @@ struct Search {
         d2h(c, desc.data(), L.desc.p, (size_t)L.G * 8);
         d2h(c, fid.data(), L.fid.p, (size_t)L.P * 4);
         CK(spin_sync(s));
-        for (uint32_t g = 0; g < L.G; ++g) {
-          R->e_child.push_back(cid[g]);
-          R->e_parent.push_back(fid[desc_parent(desc[g])]);
-          R->e_moves.push_back(desc_kind(desc[g]));
-          R->e_moves.push_back(desc_i(desc[g]));
-          R->e_moves.push_back(desc_j(desc[g]));
+        for (int r = 0; r < R; ++r) {
+          nw_result* Q = out[r];
+          for (uint32_t g = L.cstart[r]; g < L.cstart[r + 1]; ++g) {
+            int lvl, rr;
+            int64_t lc, lp;
+            locate(cid[g], lvl, rr, lc);
+            locate(fid[desc_parent(desc[g])], lvl, rr, lp);
+            Q->e_child.push_back((int32_t)lc);
+            Q->e_parent.push_back((int32_t)lp);
+            Q->e_moves.push_back(desc_kind(desc[g]));
+            Q->e_moves.push_back(desc_i(desc[g]));
+            Q->e_moves.push_back(desc_j(desc[g]));
+          }
         }
       }
     }
@@ -1414,8 +1748,9 @@ void check_opts(const nw_opts* o) {
   if (o->maxdup < 0) fail(NW_ERR_ARG, "maxdup must be >= 0");
 }
 
-void do_solve(nw_ctx* c, const int8_t* aln, int n_x, int n_y, const int64_t* len_x, const int64_t* len_y,
-              const nw_opts* o, nw_result* R) {
+// Searches R regions together through one pipeline instance (R == 1: the plain single search).  out[r] receives
+// region r's report and statistics; timings / launch counts / byte counts are those of the whole batch.
+void do_solve_many(nw_ctx* c, const ProblemRef* probs, int R, const nw_opts* o, nw_result** out) {
   CK(cudaSetDevice(c->device));
   c->launches = 0;
   c->h2d_bytes = c->d2h_bytes = 0;
@@ -1425,25 +1760,38 @@ void do_solve(nw_ctx* c, const int8_t* aln, int n_x, int n_y, const int64_t* len
     return std::chrono::duration<float, std::milli>(b - a).count();
   };
   const auto t0 = now();
-  setup_region(c, aln, n_x, n_y, len_x, len_y, o->maxdepth, false);
+  setup_regions(c, probs, R, o->maxdepth, false);
   Search S(c, *o);
   const auto t1 = now();
   S.run();
   const auto t2 = now();
-  collect_score_time(c, &S.st.score_ms, &S.st.score_launches);
-  if (!(o->flags & NW_FLAG_NO_TRAJ)) S.report(R);
+  float score_ms = 0;
+  int score_launches = 0;
+  collect_score_time(c, &score_ms, &score_launches);
+  if (!(o->flags & NW_FLAG_NO_TRAJ)) S.report_many(out);
   const auto t3 = now();
-  if (o->keep_ids) S.dump_ids(R);
+  if (o->keep_ids) S.dump_ids(out);
   const auto t4 = now();
-  S.st.host_ms[0] = ms(t0, t1);
-  S.st.host_ms[1] = ms(t1, t2);
-  S.st.host_ms[2] = ms(t2, t3);
-  S.st.host_ms[3] = ms(t3, t4);
   collect_score_time(c, nullptr, nullptr);
-  S.st.kernel_launches = c->launches;
-  S.st.h2d_bytes = c->h2d_bytes;
-  S.st.d2h_bytes = c->d2h_bytes;
-  R->stats = S.st;
+  for (int r = 0; r < R; ++r) {
+    nw_stats q = S.rst[r];
+    q.score_ms = score_ms;
+    q.score_launches = score_launches;
+    q.host_ms[0] = ms(t0, t1);
+    q.host_ms[1] = ms(t1, t2);
+    q.host_ms[2] = ms(t2, t3);
+    q.host_ms[3] = ms(t3, t4);
+    q.kernel_launches = c->launches;
+    q.h2d_bytes = c->h2d_bytes;
+    q.d2h_bytes = c->d2h_bytes;
+    out[r]->stats = q;
+  }
+}
+
+void do_solve(nw_ctx* c, const int8_t* aln, int n_x, int n_y, const int64_t* len_x, const int64_t* len_y,
+              const nw_opts* o, nw_result* R) {
+  const ProblemRef P{aln, n_x, n_y, len_x, len_y};
+  do_solve_many(c, &P, 1, o, &R);
 }
 
 }  // namespace
@@ -1496,6 +1844,7 @@ int nw_ctx_create(int device, nw_ctx** out) {
     try {
       CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
       CK(cudaMallocHost(&c->pinned, PINNED_BYTES));
+      c->pinned_bytes = PINNED_BYTES;
       c->h_pow = build_pow_table();
       CK(cudaMemcpy(c->d_pow.ensure(c->h_pow.size() * sizeof(U4)), c->h_pow.data(), c->h_pow.size() * sizeof(U4),
                     cudaMemcpyHostToDevice));
@@ -1674,7 +2023,10 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
     // depth bound for the int32 range: candidates may hold each block up to maxlen/n_x times
     int depth_equiv = 0;
     while (((int64_t)n_x << depth_equiv) < maxlen) ++depth_equiv;
-    setup_region(c, aln, n_x, n_y, len_x, len_y, depth_equiv, force != 0);
+    {
+      const ProblemRef P{aln, n_x, n_y, len_x, len_y};
+      setup_regions(c, &P, 1, depth_equiv, force != 0);
+    }
     // candidates as a "frontier" of n parents scored through KIND_ID descriptors
     Level L;
     L.P = (int)n;
@@ -1685,7 +2037,9 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
     std::vector<uint64_t> desc(n);
     std::vector<uint32_t> newlist(n);
     std::vector<uint16_t> nlen(n);
-    std::vector<uint32_t> hist(HIST_N, 0);
+    const int lcap = maxlen + 1;
+    std::vector<uint32_t> hist((size_t)lcap * NSUB, 0);
+    std::vector<uint16_t> nrid(n, 0);
     std::vector<int32_t> k3(n, 0), cost(n, -1), total(n, 0);
     for (int64_t k = 0; k < n; ++k) {
       const int l = (int)(off[k + 1] - off[k]);
@@ -1694,7 +2048,7 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
       desc[k] = pack_desc((uint32_t)k, 0, 0, KIND_ID);
       newlist[k] = (uint32_t)k;
       nlen[k] = (uint16_t)l;
-      if (force || !early_exit(l, n_y)) hist[bucket_key(l, (uint32_t)k)]++;
+      if (force || !early_exit(l, n_y)) hist[bucket_key(0, lcap, l, (uint32_t)k)]++;
     }
     L.G = (uint32_t)n;
     L.n_new = (uint32_t)n;
@@ -1703,21 +2057,29 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
     h2d(c, L.desc.ensure(n * 8), desc.data(), n * 8);
     h2d(c, L.newlist.ensure(n * 4), newlist.data(), n * 4);
     h2d(c, c->new_len.ensure(n * 2, true), nlen.data(), n * 2);
+    h2d(c, L.nrid.ensure(n * 2), nrid.data(), n * 2);
     h2d(c, L.k3.ensure(n * 4), k3.data(), n * 4);
     h2d(c, L.cost.ensure(n * 4), cost.data(), n * 4);
     h2d(c, L.total.ensure(n * 4), total.data(), n * 4);
     int32_t* misc = (int32_t*)c->misc.ensure(256);
     CK(cudaMemsetAsync(misc, 0, 256, s));
     CK(spin_sync(s));
-    run_scoring(c, view_of(L), hist.data(), maxlen, force, flags, misc + 1, nullptr);
+    {
+      ScoreView V = view_of(L);
+      V.F.regions = c->d_regions.as<RegionDev>();
+      V.F.rid = nullptr;
+      int* dummy_best = (int*)c->best.ensure(16);
+      CK(cudaMemsetAsync(dummy_best, 0, 8, s));
+      run_scoring(c, V, hist.data(), lcap, L.nrid.as<uint16_t>(), force, flags, dummy_best, nullptr);
+    }
     d2h(c, k3.data(), L.k3.p, n * 4);
     d2h(c, cost.data(), L.cost.p, n * 4);
     d2h(c, total.data(), L.total.p, n * 4);
     CK(spin_sync(s));
     CK(cudaGetLastError());
     for (int64_t k = 0; k < n; ++k) {
-      if (cost_bp) cost_bp[k] = cost[k] < 0 ? cost[k] : (int64_t)cost[k] * c->RH.gcd;
-      if (total_bp) total_bp[k] = (int64_t)total[k] * c->RH.gcd;
+      if (cost_bp) cost_bp[k] = cost[k] < 0 ? cost[k] : (int64_t)cost[k] * c->RH[0].gcd;
+      if (total_bp) total_bp[k] = (int64_t)total[k] * c->RH[0].gcd;
       if (score) score[k] = k3[k] < 0 ? -INFINITY : k3_to_score(k3[k]);
     }
   });
@@ -1734,11 +2096,14 @@ int nw_moveset(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, uint8_t* 
   const int rc = guard([&] {
     CK(cudaSetDevice(c->device));
     std::vector<int64_t> lx(n_x, 1), ly(n_y, 1);
-    setup_region(c, aln, n_x, n_y, lx.data(), ly.data(), 1, false);
-    const int MW = c->RH.MW;
+    {
+      const ProblemRef P{aln, n_x, n_y, lx.data(), ly.data()};
+      setup_regions(c, &P, 1, 1, false);
+    }
+    const int MW = c->RH[0].MW;
     std::vector<uint32_t> dd((size_t)(n_x + 1) * MW), iv((size_t)(n_x + 1) * MW);
-    d2h(c, dd.data(), c->d_msdd.p, dd.size() * 4);
-    d2h(c, iv.data(), c->d_msinv.p, iv.size() * 4);
+    d2h(c, dd.data(), c->RD[0].ms_dd, dd.size() * 4);
+    d2h(c, iv.data(), c->RD[0].ms_inv, iv.size() * 4);
     CK(spin_sync(c->stream));
     CK(cudaGetLastError());
     for (int a = 1; a <= n_x; ++a)
@@ -1748,6 +2113,44 @@ int nw_moveset(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, uint8_t* 
       }
   });
   if (rc != NW_OK) cudaGetLastError();
+  return rc;
+}
+
+int nw_solve_many(nw_ctx* c, const nw_problem* probs, int64_t n, const nw_opts* opts, int32_t max_regions_per_pass,
+                  nw_result** outs) {
+  if (!c || !probs || n < 0 || !opts || !outs) {
+    g_last_error = "null argument";
+    return NW_ERR_ARG;
+  }
+  for (int64_t k = 0; k < n; ++k) outs[k] = nullptr;
+  PoolScope pool_scope(c);
+  const int rc = guard([&] {
+    check_opts(opts);
+    int per = max_regions_per_pass > 0 ? max_regions_per_pass : 256;
+    per = std::min(per, 4096);
+    std::vector<ProblemRef> P;
+    std::vector<nw_result*> R;
+    for (int64_t k0 = 0; k0 < n; k0 += per) {
+      const int m = (int)std::min<int64_t>(per, n - k0);
+      P.resize(m);
+      R.resize(m);
+      for (int k = 0; k < m; ++k) {
+        const nw_problem& q = probs[k0 + k];
+        if (!q.aln_sign || !q.len_x || !q.len_y) fail(NW_ERR_ARG, "null problem buffer");
+        P[k] = ProblemRef{q.aln_sign, q.n_x, q.n_y, q.len_x, q.len_y};
+        R[k] = new nw_result();
+        outs[k0 + k] = R[k];
+      }
+      do_solve_many(c, P.data(), m, opts, R.data());
+    }
+  });
+  if (rc != NW_OK) {
+    for (int64_t k = 0; k < n; ++k) {
+      delete outs[k];
+      outs[k] = nullptr;
+    }
+    cudaGetLastError();
+  }
   return rc;
 }
 
@@ -1820,7 +2223,10 @@ int nw_dist_begin(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const 
     c->launches = 0;
     c->h2d_bytes = c->d2h_bytes = 0;
     collect_score_time(c, nullptr, nullptr);
-    setup_region(c, aln, n_x, n_y, len_x, len_y, o->maxdepth, false);
+    {
+      const ProblemRef P{aln, n_x, n_y, len_x, len_y};
+      setup_regions(c, &P, 1, o->maxdepth, false);
+    }
     Search* S = new Search(c, *o);
     c->dist = S;
     S->rank = rank;
@@ -1874,7 +2280,7 @@ int nw_dist_report_begin(nw_ctx* c, void* needed_dev, int64_t nbytes) {
     Search* S = dist_of(c);
     CK(cudaSetDevice(c->device));
     if (!needed_dev || nbytes < (int64_t)S->n_ids + 16) fail(NW_ERR_ARG, "needed buffer must hold n_ids + 16 bytes");
-    collect_score_time(c, &S->st.score_ms, &S->st.score_launches);
+    collect_score_time(c, &S->rst[0].score_ms, &S->rst[0].score_launches);
     S->dist_report_begin((uint8_t*)needed_dev);
   });
   if (rc != NW_OK) cudaGetLastError();
@@ -1929,10 +2335,10 @@ int nw_dist_finish(nw_ctx* c, const void* needed_dev, const void* dev_edges_all,
     CK(cudaSetDevice(c->device));
     if (!counts) fail(NW_ERR_ARG, "counts is null");
     S->dist_finish((const uint8_t*)needed_dev, dev_edges_all, counts, stride_edges, R);
-    S->st.kernel_launches = c->launches;
-    S->st.h2d_bytes = c->h2d_bytes;
-    S->st.d2h_bytes = c->d2h_bytes;
-    R->stats = S->st;
+    S->rst[0].kernel_launches = c->launches;
+    S->rst[0].h2d_bytes = c->h2d_bytes;
+    S->rst[0].d2h_bytes = c->d2h_bytes;
+    R->stats = S->rst[0];
   });
   nw_dist_abort(c);
   if (rc != NW_OK) {

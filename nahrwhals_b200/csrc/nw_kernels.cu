@@ -9,7 +9,8 @@ namespace nw {
 // to_moveset  (solver.jl:217-231, compute_possible_moves :159-165)
 // One thread per (a, b): dup_del = any_y aln[a,y]*aln[b,y] == +1 ; invert = any_y product == -1, on bit-planes.
 // =====================================================================================================
-__global__ void k_moveset(RegionDev R) {
+__global__ void k_moveset(const RegionDev* regions) {
+  const RegionDev& R = regions[blockIdx.y];
   const int n = R.n_x;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)n * n) return;
@@ -70,12 +71,14 @@ __global__ void k_table_rehash(const uint64_t* oldT, uint64_t old_cap, uint64_t*
   }
 }
 
-// insert the root (gpos 0) -- solver.jl:596-604
-__global__ void k_insert_root(const int16_t* seq, int L, const U4* pw, uint32_t rid1, uint64_t* table, uint64_t tmask) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    U4 f = seq_fingerprint(seq, L, pw, rid1);
-    table_insert(table, tmask, fp_key0(f), fp_key1(f), 0ull);
-  }
+// insert the roots (region r: global position r) -- solver.jl:596-604
+__global__ void k_insert_roots(const unsigned char* blob, uint32_t pstride, const int32_t* len, int n_regions, const U4* pw,
+                               const RegionDev* regions, uint64_t* table, uint64_t tmask) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_regions) return;
+  const int16_t* seq = reinterpret_cast<const int16_t*>(blob + (size_t)r * pstride);
+  const U4 f = seq_fingerprint(seq, len[r], pw, regions[r].rid1);
+  table_insert(table, tmask, fp_key0(f), fp_key1(f), (uint64_t)r);
 }
 
 // =====================================================================================================
@@ -104,6 +107,7 @@ __global__ void __launch_bounds__(128) k_expand_pairs(ExpandArgs A) {
   const int L = A.F.len[parent];
   const int LS = A.F.LS;
   const int dupok = A.F.dupok[parent];
+  const RegionDev& R = A.F.regions[region_index(A.F, parent)];
   int16_t* seq = reinterpret_cast<int16_t*>(smem);
   const uint32_t blob_bytes = (uint32_t)LS * 2;
   uint32_t* rowcnt = reinterpret_cast<uint32_t*>(smem + blob_bytes);
@@ -122,11 +126,11 @@ __global__ void __launch_bounds__(128) k_expand_pairs(ExpandArgs A) {
   for (int i = warp + 1; i <= L; i += 4) {
     const int a = seq[i - 1];
     uint32_t n = 0;
-    if (__ldg(&A.R.ms_any[a < 0 ? -a : a])) {  // a block without any partner starts no move (warp-uniform test)
+    if (__ldg(&R.ms_any[a < 0 ? -a : a])) {  // a block without any partner starts no move (warp-uniform test)
       for (int j0 = i + 1; j0 <= L; j0 += 32) {
         const int j = j0 + lane;
         int cdd = 0, civ = 0;
-        if (j <= L) pair_moves(A.R, a, seq[j - 1], dupok, cdd, civ);
+        if (j <= L) pair_moves(R, a, seq[j - 1], dupok, cdd, civ);
         const uint32_t mdd = __ballot_sync(0xffffffffu, cdd), minv = __ballot_sync(0xffffffffu, civ);
         n += (uint32_t)(1 + dupok) * __popc(mdd) + __popc(minv);
         if (mdd && dupok) maxlen = max(maxlen, L + (j0 + 31 - __clz(mdd) - i));
@@ -161,12 +165,12 @@ __global__ void __launch_bounds__(128) k_expand_pairs(ExpandArgs A) {
   const uint32_t base = A.off[parent];
   for (int i = warp + 1; i <= L; i += 4) {
     const int a = seq[i - 1];
-    if (!__ldg(&A.R.ms_any[a < 0 ? -a : a])) continue;
+    if (!__ldg(&R.ms_any[a < 0 ? -a : a])) continue;
     uint32_t rowpos = base + rowcnt[i - 1];
     for (int j0 = i + 1; j0 <= L; j0 += 32) {
       const int j = j0 + lane;
       int cdd = 0, civ = 0;
-      if (j <= L) pair_moves(A.R, a, seq[j - 1], dupok, cdd, civ);
+      if (j <= L) pair_moves(R, a, seq[j - 1], dupok, cdd, civ);
       const uint32_t mdd = __ballot_sync(0xffffffffu, cdd), minv = __ballot_sync(0xffffffffu, civ);
       if ((mdd | minv) == 0) continue;
       uint32_t pos = rowpos + (uint32_t)(1 + dupok) * __popc(mdd & lt) + __popc(minv & lt);
@@ -193,19 +197,19 @@ __host__ __device__ inline size_t expand_rows_smem(int LS, int n_x, int LW) {
 }
 
 template <int LWT>
-__device__ __forceinline__ uint32_t row_masks(const ExpandArgs& A, const int16_t* seq, const uint32_t* occ, int i, int dupok,
-                                              uint32_t (&ddm)[LWT], uint32_t (&ivm)[LWT], int& top) {
-  const int n_x = A.R.n_x, MW = A.R.MW;
+__device__ __forceinline__ uint32_t row_masks(const RegionDev& R, int nx_max, const int16_t* seq, const uint32_t* occ, int i,
+                                              int dupok, uint32_t (&ddm)[LWT], uint32_t (&ivm)[LWT], int& top) {
+  const int n_x = nx_max, MW = R.MW;
   const int a = seq[i - 1];
   const int aa = a < 0 ? -a : a, sa = a < 0 ? 1 : 0;
 #pragma unroll
   for (int x = 0; x < LWT; ++x) ddm[x] = ivm[x] = 0;
   top = -1;
-  if (!__ldg(&A.R.ms_any[aa])) return 0;
+  if (!__ldg(&R.ms_any[aa])) return 0;
   const uint32_t* same = occ + (size_t)sa * (n_x + 1) * LWT;
   const uint32_t* oppo = occ + (size_t)(1 - sa) * (n_x + 1) * LWT;
   for (int w = 0; w < MW; ++w) {
-    uint32_t bits = __ldg(&A.R.ms_dd[(size_t)aa * MW + w]);  // dup_del table true (solver.jl:184)
+    uint32_t bits = __ldg(&R.ms_dd[(size_t)aa * MW + w]);  // dup_del table true (solver.jl:184)
     while (bits) {
       const int b = w * 32 + __ffs(bits) - 1;
       bits &= bits - 1;
@@ -215,7 +219,7 @@ __device__ __forceinline__ uint32_t row_masks(const ExpandArgs& A, const int16_t
         ivm[x] |= oppo[(size_t)b * LWT + x];  // flipped:     inversion   (:187-188)
       }
     }
-    bits = __ldg(&A.R.ms_inv[(size_t)aa * MW + w]);  // invert table true (:185)
+    bits = __ldg(&R.ms_inv[(size_t)aa * MW + w]);  // invert table true (:185)
     while (bits) {
       const int b = w * 32 + __ffs(bits) - 1;
       bits &= bits - 1;
@@ -253,7 +257,8 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
   const int L = A.F.len[parent];
   const int LS = A.F.LS;
   const int dupok = A.F.dupok[parent];
-  const int n_x = A.R.n_x;
+  const RegionDev& R = A.F.regions[region_index(A.F, parent)];
+  const int n_x = A.nx_max;  // layout of the occurrence masks (>= this region's n_x)
   int16_t* seq = reinterpret_cast<int16_t*>(smem);
   uint32_t* occ = reinterpret_cast<uint32_t*>(smem + (((size_t)LS * 2 + 15) & ~(size_t)15));
   uint32_t* rowcnt = occ + (size_t)2 * (n_x + 1) * LWT;
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
   for (int i = tid + 1; i <= L; i += blockDim.x) {
     uint32_t ddm[LWT], ivm[LWT];
     int top;
-    rowcnt[i - 1] = row_masks<LWT>(A, seq, occ, i, dupok, ddm, ivm, top);
+    rowcnt[i - 1] = row_masks<LWT>(R, n_x, seq, occ, i, dupok, ddm, ivm, top);
     if (dupok && top >= 0) maxlen = max(maxlen, L + (top + 1 - i));
   }
   if (!EMIT && maxlen > 0) atomicMax(&s_maxlen, maxlen);
@@ -315,7 +320,7 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
   for (int i = tid + 1; i <= L; i += blockDim.x) {
     uint32_t ddm[LWT], ivm[LWT];
     int top;
-    if (row_masks<LWT>(A, seq, occ, i, dupok, ddm, ivm, top) == 0) continue;
+    if (row_masks<LWT>(R, n_x, seq, occ, i, dupok, ddm, ivm, top) == 0) continue;
     uint32_t pos = base + rowcnt[i - 1];
 #pragma unroll
     for (int x = 0; x < LWT; ++x) {
@@ -337,7 +342,7 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
 
 template <int LWT>
 static void launch_expand_rows(bool emit, const ExpandArgs& A, cudaStream_t st) {
-  const size_t sm = expand_rows_smem(A.F.LS, A.R.n_x, LWT);
+  const size_t sm = expand_rows_smem(A.F.LS, A.nx_max, LWT);
   if (emit)
     k_expand<true, LWT><<<A.F.P, 128, sm, st>>>(A);
   else
@@ -348,7 +353,7 @@ int launch_expand(bool emit, const ExpandArgs& A, cudaStream_t st) {
   if (A.F.P <= 0) return 0;
   const int LW = (A.F.LS + 31) / 32;
   const int LWT = LW <= 1 ? 1 : LW <= 2 ? 2 : LW <= 4 ? 4 : LW <= 8 ? 8 : LW <= 16 ? 16 : 0;
-  if (LWT && !A.force_pairs && expand_rows_smem(A.F.LS, A.R.n_x, LWT) <= 160 * 1024) {
+  if (LWT && !A.force_pairs && expand_rows_smem(A.F.LS, A.nx_max, LWT) <= 160 * 1024) {
     switch (LWT) {
       case 1: launch_expand_rows<1>(emit, A, st); break;
       case 2: launch_expand_rows<2>(emit, A, st); break;
@@ -546,14 +551,17 @@ __global__ void k_assign(AssignArgs A) {
       if (!A.skip_ids) A.cand_id[pos] = A.id_base + (int32_t)r;
       A.newlist[r] = pos;
       const uint64_t d = A.desc[pos];
-      const int len = child_len(A.front_len[desc_parent(d)], desc_kind(d), desc_i(d), desc_j(d));
+      const uint32_t ps = desc_parent(d);
+      const int len = child_len(A.front_len[ps], desc_kind(d), desc_i(d), desc_j(d));
+      const int rid = A.front_rid ? (int)A.front_rid[ps] : 0;
       A.new_len[r] = (uint16_t)len;
-      if (!A.force && early_exit(len, A.n_y)) {  // solver.jl:332-334 -> score 0.0, no DP
+      A.new_rid[r] = (uint16_t)rid;
+      if (!A.force && early_exit(len, A.regions[rid].n_y)) {  // solver.jl:332-334 -> score 0.0, no DP
         A.k3[r] = 0;
         A.cost[r] = -1;
         A.total[r] = 0;
       } else {
-        key = bucket_key(len, r);
+        key = bucket_key(rid, A.lcap, len, r);
       }
     } else if (!A.skip_ids) {
       const uint32_t g = A.owner[pos];
@@ -577,13 +585,13 @@ int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* is_new, uint32_t* 
 }
 
 // scatter the DP-needing new candidates into per-length buckets (each padded to a multiple of 32 lanes)
-__global__ void k_bucket_scatter(const uint16_t* new_len, uint32_t n_new, int n_y, int force, const uint32_t* bstart,
-                                 uint32_t* cursor, uint32_t* work) {
+__global__ void k_bucket_scatter(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap,
+                                 uint32_t n_new, int force, const uint32_t* bstart, uint32_t* cursor, uint32_t* work) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   int key = -1;
   if (r < n_new) {
-    const int len = new_len[r];
-    if (force || !early_exit(len, n_y)) key = bucket_key(len, r);
+    const int len = new_len[r], rid = new_rid[r];
+    if (force || !early_exit(len, regions[rid].n_y)) key = bucket_key(rid, lcap, len, r);
   }
   const uint32_t peers = __match_any_sync(0xffffffffu, key);
   const int leader = __ffs(peers) - 1;
@@ -595,10 +603,11 @@ __global__ void k_bucket_scatter(const uint16_t* new_len, uint32_t n_new, int n_
     work[bstart[key] + base + mine] = r;
   }
 }
-int launch_bucket_scatter(const uint16_t* new_len, uint32_t n_new, int n_y, int force, const uint32_t* bstart,
-                          uint32_t* cursor, uint32_t* work, cudaStream_t st) {
+int launch_bucket_scatter(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap,
+                          uint32_t n_new, int force, const uint32_t* bstart, uint32_t* cursor, uint32_t* work,
+                          cudaStream_t st) {
   if (n_new == 0) return 0;
-  k_bucket_scatter<<<(n_new + 255) / 256, 256, 0, st>>>(new_len, n_new, n_y, force, bstart, cursor, work);
+  k_bucket_scatter<<<(n_new + 255) / 256, 256, 0, st>>>(new_len, new_rid, regions, lcap, n_new, force, bstart, cursor, work);
   return 1;
 }
 
@@ -611,29 +620,30 @@ __device__ __forceinline__ int sat_add(int a, int b) { return a >= DP_INF ? DP_I
 __global__ void __launch_bounds__(128) k_score_generic(ScoreArgs A) {
   const uint32_t T = gridDim.x * blockDim.x;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ny = A.R.n_y;
   int32_t* row0 = A.scratch + tid;
-  const size_t rstride = (size_t)(ny + 2) * T;
-  const uint32_t* planes = reinterpret_cast<const uint32_t*>(A.R.ctx);
-  const int32_t* upx = reinterpret_cast<const int32_t*>(A.R.ctx + A.R.off_upx);
+  const size_t rstride = (size_t)(A.ny_max + 2) * T;
   unsigned long long cells = 0;
-  int best = -1;
   for (uint32_t w = tid; w < A.n_work; w += T) {
     const uint32_t r = A.work[w];
     if (r == WORK_PAD) continue;
     const uint64_t d = A.desc[A.newlist[r]];
     const uint32_t ps = desc_parent(d);
+    const int rid = region_index(A.F, ps);
+    const RegionDev& R = A.F.regions[rid];
+    const int ny = R.n_y;
+    const uint32_t* planes = reinterpret_cast<const uint32_t*>(R.ctx);
+    const int32_t* upx = reinterpret_cast<const int32_t*>(R.ctx + R.off_upx);
     const int kind = desc_kind(d), p = desc_i(d), q = desc_j(d);
     const int L = A.F.len[ps];
     const int16_t* seq = reinterpret_cast<const int16_t*>(A.F.blob + (size_t)ps * A.F.pstride);
     const int Lc = child_len(L, kind, p, q);
-    const int16_t* ab = A.band_ab + (size_t)A.band_off[Lc] * 2;
+    const int16_t* ab = R.band_ab + (size_t)R.band_off[Lc] * 2;
     int cur = 0;
     int cumU = 0;
     for (int i = 1; i <= Lc; ++i) {
       const int c = child_elem(seq, kind, p, q, i);
       const int x = c < 0 ? -c : c;
-      const uint32_t* pl = planes + (size_t)(x * 2 + (c < 0 ? 1 : 0)) * A.R.PWS;
+      const uint32_t* pl = planes + (size_t)(x * 2 + (c < 0 ? 1 : 0)) * R.PWS;
       const int up = upx[x];
       const int a = ab[i * 2], b = ab[i * 2 + 1];
       int32_t* rc = row0 + (size_t)cur * rstride;
@@ -642,16 +652,16 @@ __global__ void __launch_bounds__(128) k_score_generic(ScoreArgs A) {
       for (int j = 1; j <= ny; ++j) {
         int v = DP_INF;
         if (j >= a && j <= b) {
-          const int rr = A.R.NYP - 1 - j;
+          const int rr = R.NYP - 1 - j;
           const bool match = (pl[rr >> 5] >> (rr & 31)) & 1u;
           const int dcost = match ? 0 : DP_INF;
-          const int rt = A.R.rt[j];
+          const int rt = R.rt[j];
           if (i == 1 && j == 1) {
             v = min(up + rt, dcost);  // :362
           } else if (j == 1) {
             v = min(sat_add(rp[(size_t)1 * T], up), sat_add(dcost, cumU));  // :393 (cumU = cumsum_u[i-1])
           } else if (i == 1) {
-            v = min(sat_add(left, rt), sat_add(dcost, A.R.cumr[j - 1]));  // :403
+            v = min(sat_add(left, rt), sat_add(dcost, R.cumr[j - 1]));  // :403
           } else {
             v = min(sat_add(rp[(size_t)(j - 1) * T], dcost),
                     min(sat_add(rp[(size_t)j * T], up), sat_add(left, rt)));  // :420-422
@@ -666,7 +676,7 @@ __global__ void __launch_bounds__(128) k_score_generic(ScoreArgs A) {
     }
     const int32_t* rl = row0 + (size_t)(cur ^ 1) * rstride;
     const int fin = rl[(size_t)ny * T];
-    const int total = cumU + A.R.sum_rt;
+    const int total = cumU + R.sum_rt;
     A.total[r] = total;
     if (fin >= DP_INF) {
       A.cost[r] = -2;
@@ -675,10 +685,9 @@ __global__ void __launch_bounds__(128) k_score_generic(ScoreArgs A) {
       A.cost[r] = fin;
       const int k3 = score_k3(fin, total);
       A.k3[r] = k3;
-      best = max(best, k3);
+      if (k3 > 0) atomicMax(&A.best_k3[rid], k3);
     }
   }
-  if (best >= 0) atomicMax(A.best_k3, best);
   if (cells && A.cells) atomicAdd(A.cells, cells);
 }
 
@@ -700,10 +709,29 @@ __global__ void k_compact_ranks(const uint32_t* flag, const uint32_t* pre, uint3
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n && flag[r]) sel[pre[r]] = r;
 }
-// sort key: ascending key == descending Float32 score, ties by discovery rank (stable order of solver.jl:670)
-__global__ void k_make_keys(const int32_t* k3, const uint32_t* flag, const uint32_t* pre, uint32_t n, uint64_t* keys) {
+// sort key: region (16 bits) | 100000 - k3 (17 bits) | discovery rank (31 bits).  Ascending key == region-major,
+// then descending Float32 score, ties by discovery rank (the stable order of solver.jl:670).
+__global__ void k_make_keys(const int32_t* k3, const uint16_t* new_rid, const uint32_t* flag, const uint32_t* pre, uint32_t n,
+                            uint64_t* keys) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n && flag[r]) keys[pre[r]] = ((uint64_t)(uint32_t)(100000 - k3[r]) << 32) | r;
+  if (r < n && flag[r])
+    keys[pre[r]] = ((uint64_t)(new_rid ? new_rid[r] : 0) << 48) | ((uint64_t)(uint32_t)(100000 - k3[r]) << 31) | r;
+}
+// first take[rid] keys of every region's sorted segment -> sel (new-ranks in next-frontier order)
+__global__ void k_take_sorted(const uint64_t* keys, uint32_t n, const uint32_t* seg_start, const uint32_t* take,
+                              const uint32_t* out_start, uint32_t* sel) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t key = keys[i];
+  const uint32_t rid = (uint32_t)(key >> 48);
+  const uint32_t j = i - seg_start[rid];
+  if (j < take[rid]) sel[out_start[rid] + j] = (uint32_t)(key & 0x7fffffffu);
+}
+// dst[i] = src[idx[i]] (idx[i] < limit) else fill   -- region boundaries of the scanned per-candidate arrays
+__global__ void k_gather_u32(const uint32_t* src, const uint32_t* idx, uint32_t n, uint32_t limit, uint32_t fill,
+                             uint32_t* dst) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = idx[i] < limit ? src[idx[i]] : fill;
 }
 __global__ void k_fill_u64(uint64_t* p, uint64_t n0, uint64_t n1, uint64_t v) {
   const uint64_t i = n0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -780,15 +808,27 @@ int launch_compact_ranks(const uint32_t* flag, const uint32_t* pre, uint32_t n, 
   k_compact_ranks<<<(n + 255) / 256, 256, 0, st>>>(flag, pre, n, sel);
   return 1;
 }
-int launch_make_keys(const int32_t* k3, const uint32_t* flag, const uint32_t* pre, uint32_t n, uint64_t* keys,
-                     uint64_t nvalid, uint64_t npad, cudaStream_t st) {
+int launch_take_sorted(const uint64_t* keys, uint32_t n, const uint32_t* seg_start, const uint32_t* take,
+                       const uint32_t* out_start, uint32_t* sel, cudaStream_t st) {
+  if (!n) return 0;
+  k_take_sorted<<<(n + 255) / 256, 256, 0, st>>>(keys, n, seg_start, take, out_start, sel);
+  return 1;
+}
+int launch_gather_u32(const uint32_t* src, const uint32_t* idx, uint32_t n, uint32_t limit, uint32_t fill, uint32_t* dst,
+                      cudaStream_t st) {
+  if (!n) return 0;
+  k_gather_u32<<<(n + 255) / 256, 256, 0, st>>>(src, idx, n, limit, fill, dst);
+  return 1;
+}
+int launch_make_keys(const int32_t* k3, const uint16_t* new_rid, const uint32_t* flag, const uint32_t* pre, uint32_t n,
+                     uint64_t* keys, uint64_t nvalid, uint64_t npad, cudaStream_t st) {
   int l = 0;
   if (npad > nvalid) {
     k_fill_u64<<<(uint32_t)((npad - nvalid + 255) / 256), 256, 0, st>>>(keys, nvalid, npad, ~0ull);
     ++l;
   }
   if (n) {
-    k_make_keys<<<(n + 255) / 256, 256, 0, st>>>(k3, flag, pre, n, keys);
+    k_make_keys<<<(n + 255) / 256, 256, 0, st>>>(k3, new_rid, flag, pre, n, keys);
     ++l;
   }
   return l;
@@ -817,10 +857,12 @@ __global__ void __launch_bounds__(256) k_materialise(MaterialiseArgs A) {
   const int L = A.F.len[ps];
   const int16_t* seq = reinterpret_cast<const int16_t*>(A.F.blob + (size_t)ps * A.F.pstride);
   const int Lc = child_len(L, kind, p, q);
+  const int rid = region_index(A.F, ps);
+  const uint32_t rid1 = A.F.regions[rid].rid1;
   unsigned char* out = A.blob2 + (size_t)e * A.pstride2;
   int16_t* oseq = reinterpret_cast<int16_t*>(out);
   if (threadIdx.x == 0) s_max = 0;
-  for (int x = threadIdx.x; x <= A.n_x; x += blockDim.x) cntx[x] = 0;
+  for (int x = threadIdx.x; x <= A.nx_max; x += blockDim.x) cntx[x] = 0;
   __syncthreads();
   for (int t = threadIdx.x; t < A.LS2; t += blockDim.x) {
     int c = 0;
@@ -837,13 +879,14 @@ __global__ void __launch_bounds__(256) k_materialise(MaterialiseArgs A) {
     A.len2[e] = Lc;
     A.id2[e] = A.id_base + (int32_t)r;
     A.dupok2[e] = s_max <= A.maxdup ? 1 : 0;
+    A.rid2[e] = (uint16_t)rid;
   }
   // prefix tables: warp w -> base (w & 3), table (w >> 2): 0 = F (B^t), 1 = G (B^-t)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = warp & 3, which = warp >> 2;
   U4* tab = reinterpret_cast<U4*>(out + (size_t)A.LS2 * 2) + (which ? (A.LS2 + 1) : 0);
   // F'[n] = rid + B * sum_{t<n} val B^t ;  G'[n] = B * sum_{t<n} val B^-t  (see child_fingerprint)
-  uint32_t carry = which ? 0u : A.rid1;
+  uint32_t carry = which ? 0u : rid1;
   if (lane == 0) tab[0].v[k] = carry;
   for (int t0 = 0; t0 < Lc; t0 += 32) {
     const int t = t0 + lane;
@@ -862,7 +905,7 @@ __global__ void __launch_bounds__(256) k_materialise(MaterialiseArgs A) {
 
 int launch_materialise(const MaterialiseArgs& A, cudaStream_t st) {
   if (A.P2 <= 0) return 0;
-  const size_t sm = (((size_t)A.LS2 * 2 + 15) & ~(size_t)15) + (size_t)(A.n_x + 1) * 4;
+  const size_t sm = (((size_t)A.LS2 * 2 + 15) & ~(size_t)15) + (size_t)(A.nx_max + 1) * 4;
   k_materialise<<<A.P2, 256, sm, st>>>(A);
   return 1;
 }
@@ -1006,6 +1049,40 @@ int launch_id_append(const int32_t* k3, const int32_t* cost, const int32_t* tota
                      const uint8_t* needed, void* out, uint32_t cap, uint32_t* counter, cudaStream_t st) {
   if (!n) return 0;
   k_id_append<<<(n + 255) / 256, 256, 0, st>>>(k3, cost, total, id_base, n, needed, (IdRec*)out, cap, counter);
+  return 1;
+}
+
+// regionfile mode: ids whose score passes their region's minreport threshold, appended as (gid, k3, rid) records
+struct QualRec {
+  int32_t gid, k3, rid, pad;
+};
+__global__ void k_qual_append(const int32_t* k3, const uint16_t* nrid, const int32_t* k3_min, int32_t id_base, uint32_t n,
+                              QualRec* out, uint32_t cap, uint32_t* counter) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  bool take = false;
+  int v = -1, rid = 0;
+  if (r < n) {
+    v = k3[r];
+    rid = nrid ? (int)nrid[r] : 0;
+    take = v >= 0 && v >= k3_min[rid];
+  }
+  const uint32_t at = warp_append(take, counter);
+  if (!take || at >= cap) return;
+  out[at] = QualRec{id_base + (int32_t)r, v, rid, 0};
+}
+__global__ void k_set_needed(const int32_t* gids, uint32_t n, uint8_t* needed) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) needed[gids[i]] = 1;
+}
+int launch_qual_append(const int32_t* k3, const uint16_t* nrid, const int32_t* k3_min, int32_t id_base, uint32_t n, void* out,
+                       uint32_t cap, uint32_t* counter, cudaStream_t st) {
+  if (!n) return 0;
+  k_qual_append<<<(n + 255) / 256, 256, 0, st>>>(k3, nrid, k3_min, id_base, n, (QualRec*)out, cap, counter);
+  return 1;
+}
+int launch_set_needed(const int32_t* gids, uint32_t n, uint8_t* needed, cudaStream_t st) {
+  if (!n) return 0;
+  k_set_needed<<<(n + 255) / 256, 256, 0, st>>>(gids, n, needed);
   return 1;
 }
 
@@ -1252,14 +1329,14 @@ void init_kernel_attrs() {
   init_score_fast_attrs();
 }
 
-int launch_moveset(const RegionDev& R, cudaStream_t st) {
-  const long long n = (long long)R.n_x * R.n_x;
-  k_moveset<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R);
+int launch_moveset(const RegionDev* regions_dev, int n_regions, int nx_max, cudaStream_t st) {
+  const long long n = (long long)nx_max * nx_max;
+  k_moveset<<<dim3((unsigned)((n + 255) / 256), (unsigned)n_regions), 256, 0, st>>>(regions_dev);
   return 1;
 }
-int launch_insert_root(const int16_t* seq, int L, const U4* pw, uint32_t rid1, uint64_t* table, uint64_t tmask,
-                       cudaStream_t st) {
-  k_insert_root<<<1, 32, 0, st>>>(seq, L, pw, rid1, table, tmask);
+int launch_insert_roots(const unsigned char* blob, uint32_t pstride, const int32_t* len, int n_regions, const U4* pw,
+                        const RegionDev* regions, uint64_t* table, uint64_t tmask, cudaStream_t st) {
+  k_insert_roots<<<(n_regions + 127) / 128, 128, 0, st>>>(blob, pstride, len, n_regions, pw, regions, table, tmask);
   return 1;
 }
 int launch_rehash(const uint64_t* oldT, uint64_t old_cap, uint64_t* newT, uint64_t new_mask, cudaStream_t st) {

@@ -15,7 +15,10 @@ constexpr uint32_t WORK_PAD = 0xffffffffu;
 // The per-length counters used to bucket fresh candidates are split NSUB ways (by new-rank / 256) to spread the
 // atomics of k_assign / k_bucket_scatter over more addresses.
 constexpr int NSUB = 8;
-__host__ __device__ inline int bucket_key(int len, uint32_t new_rank) { return len * NSUB + (int)((new_rank >> 8) & (NSUB - 1)); }
+// bins are (region, child length, sub-counter); lcap = (longest child length of the level) + 1
+__host__ __device__ inline int bucket_key(int rid, int lcap, int len, uint32_t new_rank) {
+  return (rid * lcap + len) * NSUB + (int)((new_rank >> 8) & (NSUB - 1));
+}
 
 // Per-region read-only context in device memory.  [planes | upx | rt_rev] is one contiguous, 16-B aligned
 // blob of ctx_bytes so the scoring kernels can stage it with a single TMA bulk copy.
@@ -35,6 +38,12 @@ struct RegionDev {
   uint32_t* ms_dd;       // [(n_x+1) * MW] bit rows, 1-based block ids
   uint32_t* ms_inv;
   uint32_t* ms_any;      // [n_x+1] non-zero iff the block has any dup/del or inversion partner
+  // corridor tables of this region's n_y (device mirror of BandStore; refreshed by the host before every DP launch)
+  const int32_t* band_off;   // [LMAX+2] row offset of the table of child length L, -1 if absent
+  const int16_t* band_ab;    // generic kernel: {a,b} per row
+  const int16_t* band_eb;    // register kernel: eb per row (row 0 = virtual)
+  const uint8_t* band_sb;    // register kernel: window shift per row
+  const uint32_t* band_mask; // register kernel: 4 mask words per row
 };
 
 // One BFS level's frontier: P parents, each a blob [seq int16 x LS | F U4 x (LS+1) | G U4 x (LS+1)].
@@ -45,7 +54,13 @@ struct FrontierDev {
   const int32_t* len;
   const int32_t* id;
   const uint8_t* dupok;
+  // several independent regions in one search (regionfile mode): region of every parent, region table
+  const uint16_t* rid;        // nullptr: every parent belongs to region 0
+  const RegionDev* regions;   // device array
 };
+__device__ __forceinline__ int region_index(const FrontierDev& F, uint32_t parent_slot) {
+  return F.rid ? (int)F.rid[parent_slot] : 0;
+}
 
 struct LevelTable {  // candidate -> id lookup across levels (owner resolution)
   int n_levels;                      // levels already finished (level 0 = root pseudo-level)
@@ -54,8 +69,8 @@ struct LevelTable {  // candidate -> id lookup across levels (owner resolution)
 };
 
 struct ExpandArgs {
-  RegionDev R;
   FrontierDev F;
+  int nx_max;            // largest n_x over the regions of this launch (shared-memory layout of k_expand)
   uint32_t* cnt;         // [P] candidates per parent (count pass out)
   const uint32_t* off;   // [P] exclusive offsets (emit pass in)
   int* maxlen;           // max child length (count pass out)
@@ -97,22 +112,19 @@ struct DistRec {
 };
 
 struct ScoreArgs {
-  RegionDev R;
   FrontierDev F;
+  uint32_t ctx_max;         // largest region context (shared-memory layout of k_score_fast)
+  int ny_max;               // largest n_y (scratch layout of k_score_generic)
+  const uint16_t* cta_rid;  // k_score_fast: region of every CTA of this launch (nullptr: region 0)
   const uint32_t* work;     // [n_work] new-rank per lane slot, WORK_PAD = idle
   uint32_t n_work;
   int lmax;                 // longest child in this launch (sizes the shared-memory tiles of k_score_fast)
   const uint32_t* newlist;  // rank -> candidate position in this level
   const uint64_t* desc;
-  const int32_t* band_off;  // [Lmax+1] offset (in rows) of the band table of length L, -1 if absent
-  const int16_t* band_ab;   // generic: {a,b} pairs per row (row 0 unused)
-  const int16_t* band_eb;   // fast: eb per row (row 0 = virtual)
-  const uint8_t* band_sb;   // fast: sb per row
-  const uint32_t* band_mask;  // fast: 4 words per row
   int32_t* k3;              // [n_new] out
   int32_t* cost;            // [n_new] out (units; -2 unreachable)
   int32_t* total;           // [n_new] out (units)
-  int* best_k3;
+  int* best_k3;             // [n_regions] best score*1000 per region
   unsigned long long* cells;  // DP cells evaluated (stat)
   int32_t* scratch;         // generic kernel rows
   int force;
@@ -129,7 +141,11 @@ struct AssignArgs {
   const int32_t* front_len;
   uint32_t gbase, G;
   int32_t id_base;  // id of new-rank 0
-  int n_y, force;
+  const uint16_t* front_rid;  // region of every parent (nullptr: region 0)
+  const RegionDev* regions;
+  int lcap;                   // bins per region = lcap * NSUB
+  uint16_t* new_rid;          // [n_new] out: region of every fresh candidate
+  int force;
   int skip_ids;     // sharded search: ids are assigned after the cross-rank merge
   int32_t* cand_id;   // [G] out
   uint32_t* newlist;  // [n_new] out: rank -> pos
@@ -146,15 +162,15 @@ struct MaterialiseArgs {
   const uint32_t* newlist;
   const uint64_t* desc;
   int32_t id_base;
-  int maxdup, n_x;
+  int maxdup, nx_max;
   int P2, LS2;
   uint32_t pstride2;
   unsigned char* blob2;
   int32_t* len2;
   int32_t* id2;
   uint8_t* dupok2;
+  uint16_t* rid2;  // region of every new parent
   const U4* pw;
-  uint32_t rid1;
 };
 
 struct EdgeRec {

@@ -7,9 +7,9 @@ namespace nw {
 
 double launch_int_peak(int mode, int* out, int iters, cudaStream_t st);
 void init_kernel_attrs();  // once per device
-int launch_moveset(const RegionDev& R, cudaStream_t st);
-int launch_insert_root(const int16_t* seq, int L, const U4* pw, uint32_t rid1, uint64_t* table, uint64_t tmask,
-                       cudaStream_t st);
+int launch_moveset(const RegionDev* regions_dev, int n_regions, int nx_max, cudaStream_t st);
+int launch_insert_roots(const unsigned char* blob, uint32_t pstride, const int32_t* len, int n_regions, const U4* pw,
+                        const RegionDev* regions, uint64_t* table, uint64_t tmask, cudaStream_t st);
 int launch_rehash(const uint64_t* oldT, uint64_t old_cap, uint64_t* newT, uint64_t new_mask, cudaStream_t st);
 int launch_expand(bool emit, const ExpandArgs& A, cudaStream_t st);
 int launch_hash_insert(const ExpandArgs& A, uint32_t G, cudaStream_t st);
@@ -20,14 +20,22 @@ int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* is_new, uint32_t* 
 int launch_assign(const AssignArgs& A, cudaStream_t st);
 int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t* is_new, const uint32_t* owner, uint32_t G,
                        unsigned int* mismatches, cudaStream_t st);
-int launch_bucket_scatter(const uint16_t* new_len, uint32_t n_new, int n_y, int force, const uint32_t* bstart,
-                          uint32_t* cursor, uint32_t* work, cudaStream_t st);
+int launch_bucket_scatter(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap,
+                          uint32_t n_new, int force, const uint32_t* bstart, uint32_t* cursor, uint32_t* work,
+                          cudaStream_t st);
 int generic_threads();
 int launch_score_generic(const ScoreArgs& A, cudaStream_t st);
 int launch_valid_flags(const int32_t* k3, uint32_t n, uint32_t* flag, cudaStream_t st);
 int launch_compact_ranks(const uint32_t* flag, const uint32_t* pre, uint32_t n, uint32_t* sel, cudaStream_t st);
-int launch_make_keys(const int32_t* k3, const uint32_t* flag, const uint32_t* pre, uint32_t n, uint64_t* keys,
-                     uint64_t nvalid, uint64_t npad, cudaStream_t st);
+int launch_make_keys(const int32_t* k3, const uint16_t* new_rid, const uint32_t* flag, const uint32_t* pre, uint32_t n,
+                     uint64_t* keys, uint64_t nvalid, uint64_t npad, cudaStream_t st);
+int launch_take_sorted(const uint64_t* keys, uint32_t n, const uint32_t* seg_start, const uint32_t* take,
+                       const uint32_t* out_start, uint32_t* sel, cudaStream_t st);
+int launch_gather_u32(const uint32_t* src, const uint32_t* idx, uint32_t n, uint32_t limit, uint32_t fill, uint32_t* dst,
+                      cudaStream_t st);
+int launch_qual_append(const int32_t* k3, const uint16_t* nrid, const int32_t* k3_min, int32_t id_base, uint32_t n, void* out,
+                       uint32_t cap, uint32_t* counter, cudaStream_t st);
+int launch_set_needed(const int32_t* gids, uint32_t n, uint8_t* needed, cudaStream_t st);
 int launch_sort_u64(uint64_t* keys, uint64_t npad, cudaStream_t st);
 int launch_keys_to_sel(const uint64_t* keys, uint32_t n, uint32_t* sel, cudaStream_t st);
 int launch_materialise(const MaterialiseArgs& A, cudaStream_t st);

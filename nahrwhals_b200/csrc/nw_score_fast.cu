@@ -23,18 +23,20 @@ __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // all candidates of a CTA belong to one region (the host pads region segments to CTA boundaries)
+  const RegionDev& R = A.F.regions[A.cta_rid ? (int)A.cta_rid[blockIdx.x] : 0];
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(&bar, A.R.ctx_bytes);
-    tma_bulk_g2s(smem, A.R.ctx, A.R.ctx_bytes, &bar);
+    mbar_expect_tx(&bar, R.ctx_bytes);
+    tma_bulk_g2s(smem, R.ctx, R.ctx_bytes, &bar);
   }
   const uint32_t* planes = reinterpret_cast<const uint32_t*>(smem);
-  const int32_t* upx = reinterpret_cast<const int32_t*>(smem + A.R.off_upx);
-  const int32_t* rtrev = reinterpret_cast<const int32_t*>(smem + A.R.off_rtrev);
+  const int32_t* upx = reinterpret_cast<const int32_t*>(smem + R.off_upx);
+  const int32_t* rtrev = reinterpret_cast<const int32_t*>(smem + R.off_rtrev);
   const int Lmax = A.lmax;
-  int16_t* crow = reinterpret_cast<int16_t*>(smem + A.R.ctx_bytes);
-  uint32_t* brow = reinterpret_cast<uint32_t*>(smem + A.R.ctx_bytes + (size_t)Lmax * 256) + (size_t)warp * (Lmax + 1) * BROW;
+  int16_t* crow = reinterpret_cast<int16_t*>(smem + A.ctx_max);
+  uint32_t* brow = reinterpret_cast<uint32_t*>(smem + A.ctx_max + (size_t)Lmax * 256) + (size_t)warp * (Lmax + 1) * BROW;
 
   const uint32_t w = blockIdx.x * 128u + tid;
   uint32_t r = w < A.n_work ? A.work[w] : WORK_PAD;
@@ -69,11 +71,11 @@ __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
   }
   // ---- stage the warp's band rows ----
   {
-    const int boff = A.band_off[Lc];
-    const int16_t* eb_t = A.band_eb + boff;
-    const uint8_t* sb_t = A.band_sb + boff;
-    const uint32_t* mk_t = A.band_mask + (size_t)boff * 4;
-    const int NYP1 = A.R.NYP - 1;
+    const int boff = R.band_off[Lc];
+    const int16_t* eb_t = R.band_eb + boff;
+    const uint8_t* sb_t = R.band_sb + boff;
+    const uint32_t* mk_t = R.band_mask + (size_t)boff * 4;
+    const int NYP1 = R.NYP - 1;
     for (int i = 1 + lane; i <= Lc; i += 32) {
       const int r0 = NYP1 - (int)eb_t[i];
       const int sb = sb_t[i];
@@ -82,9 +84,10 @@ __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
       for (int t = 0; t < NWORD; ++t) brow[i * BROW + 1 + t] = mk_t[(size_t)i * 4 + t];
     }
   }
-  const int PWS = A.R.PWS;
-  const int rt_stride = A.R.rt_copy_stride;
-  const int sum_rt = A.R.sum_rt;
+  const int PWS = R.PWS;
+  const int rt_stride = R.rt_copy_stride;
+  const int sum_rt = R.sum_rt;
+  int* best_slot = A.best_k3 + (A.cta_rid ? (int)A.cta_rid[blockIdx.x] : 0);
   __syncwarp();
   mbar_wait(&bar, 0);
 
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
   }
   int b = k3;  // warp max -> one atomic (shadow lanes carry a duplicate of a real value)
   for (int o = 16; o; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
-  if (lane == 0) atomicMax(A.best_k3, b);
+  if (lane == 0 && b > 0) atomicMax(best_slot, b);
 }
 
 static const int kWindows[] = {8, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64, 72, 80, 96, 112, 128};
@@ -159,14 +162,14 @@ int score_fast_window(int width) {
 }
 bool score_fast_supports(int width) { return score_fast_window(width) != 0; }
 
-size_t score_fast_smem(int W, uint32_t ctx_bytes, int lmax) {
+size_t score_fast_smem(int W, uint32_t ctx_bytes /* largest region context of the launch */, int lmax) {
   const int nword = (W + 31) / 32;
   return (size_t)ctx_bytes + (size_t)lmax * 256 + (size_t)4 * (lmax + 1) * (1 + nword) * 4;
 }
 
 template <int W>
 static int launch_w(const ScoreArgs& A, cudaStream_t st) {
-  const size_t sm = score_fast_smem(W, A.R.ctx_bytes, A.lmax);
+  const size_t sm = score_fast_smem(W, A.ctx_max, A.lmax);
   k_score_fast<W><<<(A.n_work + 127) / 128, 128, sm, st>>>(A);
   return 1;
 }

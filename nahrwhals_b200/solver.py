@@ -217,6 +217,33 @@ def solve_batch(solvers, regions, **kw):
     return res
 
 
+def solve_many(solver, regions, regions_per_pass=256, **kw):
+    """Regionfile mode on ONE context: `regions_per_pass` regions are searched together through one pipeline instance
+    (nw_solve_many), so every kernel launch is shared by all of them.  Returns one SolveResult per region."""
+    L = _lib.load()
+    n = len(regions)
+    keep = [Solver._problem(*r) for r in regions]
+    probs = (_lib.NwProblem * max(n, 1))()
+    for k, (a, lx, ly) in enumerate(keep):
+        probs[k].aln_sign = a.ctypes.data
+        probs[k].n_x, probs[k].n_y = a.shape
+        probs[k].len_x = lx.ctypes.data
+        probs[k].len_y = ly.ctypes.data
+    outs = (C.c_void_p * max(n, 1))()
+    o = solver._opts(**kw)
+    rc = L.nw_solve_many(solver.h, probs, n, C.byref(o), int(regions_per_pass), outs)
+    res = []
+    try:
+        _lib.check(rc)
+        for k in range(n):
+            res.append(solver._unpack(C.c_void_p(outs[k]), o))
+    finally:
+        for k in range(n):
+            if outs[k]:
+                L.nw_result_free(C.c_void_p(outs[k]))
+    return res
+
+
 def read_problem(inmat, inlens):
     """read_tsv + read_length_tsv (solver.jl:101-107, :121-138) -> (aln int8 [n_x,n_y], len_x, len_y)."""
     L = _lib.load()

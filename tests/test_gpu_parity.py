@@ -305,3 +305,31 @@ def test_error_behaviour(solver, tmp_path):
     solver.solve_files(m, l, out, maxdepth=2, minreport=0.0)
     assert out.read_text().startswith("100.0\t0\t\n")
     assert nb.main(["-d", "2", str(tmp_path / "missing.tsv"), str(l), str(tmp_path / "o2.tsv")]) == 1
+
+
+@pytest.mark.parametrize("per_pass", [1, 5, 64])
+def test_solve_many_regions(solver, oracle, per_pass):
+    """Regionfile mode through ONE pipeline instance (nw_solve_many): regions of different shapes searched together,
+    region by region identical to the oracle -- counts, every id's level/cost/total/score, every edge, the TSV."""
+    rng = np.random.default_rng(5)
+    regions = []
+    for k in range(23):
+        n_x = int(rng.integers(8, 70))
+        fams = [int(rng.integers(2, 5)) for _ in range(int(rng.integers(1, 5)))]
+        while sum(fams) > n_x:
+            fams.pop()
+        mat, lx, ly, _ = sdgrid(n_x, fams, seed=700 + k, chain_depth=int(rng.integers(0, 4)), len_tol=0.3)
+        if k % 7 == 3:  # a region with different length units
+            lx, ly = lx // 10 + 7, ly // 10 + 7
+            mat = np.sign(mat) * lx[None, :]
+        regions.append((to_solver_inputs(mat), lx, ly))
+    regions.append((np.array([[1]], dtype=np.int8), np.array([5000]), np.array([5000])))  # no pair at all
+    import nahrwhals_b200 as nb
+    for kw in (dict(maxdepth=3, maxdup=2, maxwidth=1000, minreport=0.98, maxreport=1000),
+               dict(maxdepth=3, maxdup=2, maxwidth=3, minreport=0.5, maxreport=5),
+               dict(maxdepth=2, maxdup=1, minreport=0.0)):
+        res = nb.solve_many(solver, regions, regions_per_pass=per_pass, keep_ids=True, **kw)
+        assert len(res) == len(regions)
+        for (aln, lx, ly), G in zip(regions, res):
+            O = oracle.solve(aln, lx, ly, **kw)
+            assert_search_equal(G, O)
