@@ -1274,11 +1274,22 @@ struct Search {
   }
 
   // ---- report: get_good_trajectories (solver.jl:727-745) ----
-  struct Node {
-    int32_t k3 = 0, cost = -1, total = 0;
-    std::vector<EdgeRec> in;
+  // host graph of the needed ids: ids sorted ascending (binary search), incoming edges in CSR form, every
+  // child's edges in discovery order (solver.jl:559-560 appends provenance in the order candidates are generated)
+  struct NodeTable {
+    std::vector<int32_t> id, k3, cost, total;
+    std::vector<uint32_t> estart;
+    std::vector<EdgeRec> edges;
+    std::vector<int32_t> eparent;  // node index of every edge's parent (-1: not in the table)
+    std::vector<signed char> memo; // reachability memo of the enumerator: [node][moves] 0 unknown, 1 yes, 2 no
+    int memo_w = 0;
+    int find(int32_t gid) const {
+      auto it = std::lower_bound(id.begin(), id.end(), gid);
+      return (it != id.end() && *it == gid) ? (int)(it - id.begin()) : -1;
+    }
+    size_t size() const { return id.size(); }
   };
-  std::unordered_map<int32_t, Node> nodes;
+  NodeTable nodes;
 
   static float score_f32(int k3) { return k3 < 0 ? -INFINITY : (float)k3_to_score(k3); }
 
@@ -1350,10 +1361,6 @@ struct Search {
     cudaStream_t s = c->stream;
     int32_t* misc = (int32_t*)c->misc.p;
     const int nl = (int)lv.size();
-    std::sort(edges.begin(), edges.end(), [](const EdgeRec& a, const EdgeRec& b) { return a.gpos < b.gpos; });
-    nodes.clear();
-    for (int r = 0; r < R; ++r) nodes[r + 1] = Node{root_k3[r], root_cost[r], root_total[r], {}};
-    for (const EdgeRec& e : edges) nodes[e.child].in.push_back(e);
     uint32_t cap = std::max<uint32_t>(id_cap_hint, 1u << 14);
     std::vector<IdRec> hi;
     for (;;) {
@@ -1378,12 +1385,42 @@ struct Search {
       }
       cap = n + n / 8;
     }
-    for (const IdRec& r : hi) {
-      Node& nd = nodes[r.id];
-      nd.k3 = r.k3;
-      nd.cost = r.cost;
-      nd.total = r.total;
+    // node table: roots + every needed id, sorted by id
+    for (int r = 0; r < R; ++r) hi.push_back(IdRec{r + 1, root_k3[r], root_cost[r], root_total[r]});
+    std::sort(hi.begin(), hi.end(), [](const IdRec& a, const IdRec& b) { return a.id < b.id; });
+    NodeTable& T = nodes;
+    const size_t nn = hi.size();
+    T.id.resize(nn);
+    T.k3.resize(nn);
+    T.cost.resize(nn);
+    T.total.resize(nn);
+    for (size_t k = 0; k < nn; ++k) {
+      T.id[k] = hi[k].id;
+      T.k3[k] = hi[k].k3;
+      T.cost[k] = hi[k].cost;
+      T.total[k] = hi[k].total;
     }
+    // CSR by child (counting sort), then discovery order inside every child's short list
+    T.estart.assign(nn + 1, 0);
+    std::vector<int32_t> slot(edges.size());
+    for (size_t e = 0; e < edges.size(); ++e) {
+      const int k = T.find(edges[e].child);
+      slot[e] = k;
+      if (k >= 0) T.estart[k + 1]++;
+    }
+    for (size_t k = 0; k < nn; ++k) T.estart[k + 1] += T.estart[k];
+    T.edges.resize(T.estart[nn]);
+    std::vector<uint32_t> cur(T.estart.begin(), T.estart.end() - 1);
+    for (size_t e = 0; e < edges.size(); ++e)
+      if (slot[e] >= 0) T.edges[cur[slot[e]]++] = edges[e];
+    for (size_t k = 0; k < nn; ++k)
+      if (T.estart[k + 1] - T.estart[k] > 1)
+        std::sort(T.edges.begin() + T.estart[k], T.edges.begin() + T.estart[k + 1],
+                  [](const EdgeRec& a, const EdgeRec& b) { return a.gpos < b.gpos; });
+    T.eparent.resize(T.edges.size());
+    for (size_t e = 0; e < T.edges.size(); ++e) T.eparent[e] = T.find(T.edges[e].parent);
+    T.memo_w = o.maxdepth + 3;
+    T.memo.assign(nn * (size_t)T.memo_w, 0);
     CK(cudaGetLastError());
   }
   void extract(int k3_min, int k3_star, int64_t quota) {  // single-rank composition of the phases
@@ -1406,47 +1443,58 @@ struct Search {
   // reference's own enumeration order restricted to paths of that length -- and stop at max_report.
   struct Enumerator {
     Search& S;
-    std::unordered_map<int64_t, char> memo;  // (id, r) -> can the root be reached from id in exactly r moves
-    std::vector<EdgeRec> stack;              // edges from the target backwards
+    std::vector<EdgeRec> stack;  // edges from the target backwards
     int64_t limit = -1, emitted = 0;
     nw_result* R = nullptr;
     int cur_id = 0, cur_k3 = 0, rid = 0;
     explicit Enumerator(Search& s) : S(s) {}
-    bool reach(int32_t id, int r) {
-      if (id <= S.R) return r == 0;  // ids 1..R are the roots of the R regions
+    // can a root be reached from node `nd` in exactly r moves (first visit of the root ends the path)
+    bool reach(int nd, int r) {
+      if (nd < 0) return false;
+      NodeTable& T = S.nodes;
+      if (T.id[nd] <= S.R) return r == 0;  // ids 1..R are the roots of the R regions
       if (r <= 0) return false;
-      const int64_t key = ((int64_t)id << 8) | r;
-      auto it = memo.find(key);
-      if (it != memo.end()) return it->second;
+      signed char& m = T.memo[(size_t)nd * T.memo_w + std::min(r, T.memo_w - 1)];
+      if (m) return m == 1;
       bool ok = false;
-      auto nd = S.nodes.find(id);
-      if (nd != S.nodes.end())
-        for (const EdgeRec& e : nd->second.in)
-          if (reach(e.parent, r - 1)) {
-            ok = true;
-            break;
-          }
-      memo.emplace(key, ok);
+      for (uint32_t e = T.estart[nd]; e < T.estart[nd + 1] && !ok; ++e) ok = reach(T.eparent[e], r - 1);
+      T.memo[(size_t)nd * T.memo_w + std::min(r, T.memo_w - 1)] = ok ? 1 : 2;
       return ok;
     }
     bool full() const { return limit >= 0 && emitted >= limit; }
+    // append a non-negative integer without allocating
+    static void put_int(std::string& s, long long v) {
+      char buf[24];
+      int n = 0;
+      do {
+        buf[n++] = (char)('0' + v % 10);
+        v /= 10;
+      } while (v);
+      while (n) s.push_back(buf[--n]);
+    }
+    int emit_id = -1, emit_cost = -1, emit_total = 0;
+    int64_t emit_local = 0;
+    std::string emit_score;
     void emit() {
       static const char* names[3] = {"move_dup", "move_del", "move_inv"};
-      const Node& nd = S.nodes[cur_id];
+      if (emit_id != cur_id) {  // per-id fields are looked up once, not once per trajectory
+        emit_id = cur_id;
+        const int nd = S.nodes.find(cur_id);
+        emit_cost = nd >= 0 ? S.nodes.cost[nd] : -1;
+        emit_total = nd >= 0 ? S.nodes.total[nd] : 0;
+        int lvl, rr;
+        S.locate(cur_id, lvl, rr, emit_local);
+        emit_score = score_string(cur_k3);
+      }
       R->t_score.push_back(score_f32(cur_k3));
       R->t_k3.push_back(cur_k3);
-      {
-        int lvl, rr;
-        int64_t local;
-        S.locate(cur_id, lvl, rr, local);
-        R->t_id.push_back(local);
-      }
-      R->t_cost.push_back(nd.cost < 0 ? nd.cost : (int64_t)nd.cost * S.c->RH[rid].gcd);
-      R->t_total.push_back((int64_t)nd.total * S.c->RH[rid].gcd);
+      R->t_id.push_back(emit_local);
+      R->t_cost.push_back(emit_cost < 0 ? emit_cost : (int64_t)emit_cost * S.c->RH[rid].gcd);
+      R->t_total.push_back((int64_t)emit_total * S.c->RH[rid].gcd);
       std::string& line = R->tsv;
-      line += score_string(cur_k3);
+      line += emit_score;
       line += '\t';
-      line += std::to_string(stack.size());
+      put_int(line, (long long)stack.size());
       line += '\t';  // :723
       bool first = true;
       for (size_t k = stack.size(); k-- > 0;) {  // stack holds the last move first; trajectories list moves root-first
@@ -1459,27 +1507,27 @@ struct Search {
         first = false;
         line += names[kind];
         line += '\t';
-        line += std::to_string(i);
+        put_int(line, i);
         line += '\t';
-        line += std::to_string(j);  // :719
+        put_int(line, j);  // :719
       }
       line += '\n';
       R->t_off.push_back((int64_t)R->t_moves.size());
       ++emitted;
     }
-    // all paths of exactly r more moves from `id` back to the root, in the reference's enumeration order
-    void walk(int32_t id, int r) {
-      if (id <= S.R) {
+    // all paths of exactly r more moves from node `nd` back to the root, in the reference's enumeration order
+    void walk(int nd, int r) {
+      if (nd < 0) return;
+      const NodeTable& T = S.nodes;
+      if (T.id[nd] <= S.R) {
         if (r == 0) emit();
         return;
       }
-      auto nd = S.nodes.find(id);
-      if (nd == S.nodes.end()) return;
-      for (const EdgeRec& e : nd->second.in) {
+      for (uint32_t q = T.estart[nd]; q < T.estart[nd + 1]; ++q) {
         if (full()) return;
-        if (!reach(e.parent, r - 1)) continue;
-        stack.push_back(e);
-        walk(e.parent, r - 1);
+        if (!reach(T.eparent[q], r - 1)) continue;
+        stack.push_back(T.edges[q]);
+        walk(T.eparent[q], r - 1);
         stack.pop_back();
       }
     }
@@ -1631,9 +1679,9 @@ struct Search {
 
   void enumerate(nw_result* out, int rid, int k3_min) {
     std::vector<std::pair<int32_t, int32_t>> good;  // (-k3, id): canonical Dict order = ascending discovery id
-    for (auto& kv : nodes) {
-      const int k3 = kv.second.k3;
-      if (k3 >= 0 && k3 >= k3_min) good.emplace_back(-k3, kv.first);
+    for (size_t k = 0; k < nodes.size(); ++k) {
+      const int k3 = nodes.k3[k];
+      if (k3 >= 0 && k3 >= k3_min) good.emplace_back(-k3, nodes.id[k]);
     }
     std::sort(good.begin(), good.end());
     enumerate_list(out, rid, good);
@@ -1653,7 +1701,8 @@ struct Search {
         for (size_t g = g0; g < g1 && !E.full(); ++g) {
           E.cur_id = good[g].second;
           E.cur_k3 = -good[g].first;
-          if (E.reach(E.cur_id, m)) E.walk(E.cur_id, m);
+          const int nd = nodes.find(E.cur_id);
+          if (E.reach(nd, m)) E.walk(nd, m);
         }
       g0 = g1;
     }

@@ -70,6 +70,24 @@ def run_cpu(regions, threads):
     return len(regions) / dt, sum(scored), dt
 
 
+def run_many(regions, per_pass, device=0):
+    s = nb.Solver(device)
+    nb.solve_many(s, regions[:min(len(regions), per_pass)], regions_per_pass=per_pass, **FLAGS)  # warm-up
+    t0 = time.perf_counter()
+    res = nb.solve_many(s, regions, regions_per_pass=per_pass, **FLAGS)
+    dt = time.perf_counter() - t0
+    s.close()
+    hs = [0.0, 0.0, 0.0]
+    dev = 0.0
+    for k in range(0, len(res), per_pass):
+        for q in range(3):
+            hs[q] += res[k].stats.host_ms[q]
+        dev += res[k].stats.total_ms
+    print("   native phases over all passes: setup %.1f ms, search %.1f ms (device timeline %.1f ms), report %.1f ms; "
+          "python wall %.1f ms" % (hs[0], hs[1], dev, hs[2], dt * 1e3))
+    return len(regions) / dt, sum(sum(R.scored) for R in res), dt
+
+
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 500
     tl = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 4, 16]
@@ -83,3 +101,7 @@ if __name__ == "__main__":
     for t in tl:
         r, sc, dt = run_gpu(regs, t)
         print("GPU, %d contexts: %.1f regions/s, %.3g candidates/s (%.2f s)" % (t, r, sc / dt, dt), flush=True)
+    for per in (16, 64, 256, 1024):
+        r, sc, dt = run_many(regs, per)
+        print("GPU, one pipeline, %d regions per pass: %.1f regions/s, %.3g candidates/s (%.2f s)" % (per, r, sc / dt, dt),
+              flush=True)
