@@ -146,9 +146,12 @@ inline BandTable build_band(int L, int n_y, bool force, int max_window = 128) {
     for (int i = 1; i <= L; ++i) {
       // diag move into (i,j) needs (i-1, j-1) valid in the extended grid: j-1 in [ea[i-1], eb[i-1]]
       const int j0 = std::max(T.row[i].a, (int)T.ea[i - 1] + 1), j1 = std::min(T.row[i].b, (int)T.eb[i - 1] + 1);
-      for (int j = j0; j <= j1; ++j) {
-        const int k = T.eb[i] - j;
-        T.mask[(size_t)i * 4 + (k >> 5)] |= 1u << (k & 31);
+      if (j0 > j1) continue;
+      const int k0 = T.eb[i] - j1, k1 = T.eb[i] - j0;  // bits k0..k1 (k1 < max_window <= 128)
+      for (int w = k0 >> 5; w <= (k1 >> 5); ++w) {
+        const int lo = std::max(k0 - w * 32, 0), hi = std::min(k1 - w * 32, 31);
+        const uint32_t bits = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+        T.mask[(size_t)i * 4 + w] |= bits;
       }
     }
   }

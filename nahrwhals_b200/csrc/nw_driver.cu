@@ -11,6 +11,7 @@
 #include <chrono>
 #include <functional>
 #include <map>
+#include <memory>
 #include <atomic>
 #include <mutex>
 #include <thread>
@@ -156,7 +157,7 @@ void d2h(nw_ctx* c, void* dst, const void* src, size_t n);
 struct BandStore {  // host cache + device mirror of per-length corridor tables for one (n_y, force)
   int n_y = -1;
   bool force = false;
-  std::map<int, BandTable> tabs;
+  std::vector<std::unique_ptr<BandTable>> tabs;  // [LMAX+2], built on first use
   std::vector<int32_t> off;  // [LMAX+2] row offset or -1
   std::vector<int16_t> ab, eb;
   std::vector<uint8_t> sb;
@@ -167,16 +168,17 @@ struct BandStore {  // host cache + device mirror of per-length corridor tables 
     n_y = ny;
     force = f;
     tabs.clear();
+    tabs.resize(LMAX + 2);
     off.assign(LMAX + 2, -1);
     ab.clear();
     eb.clear();
     sb.clear();
     mask.clear();
+    up_rows = 0;
     dirty = true;
   }
   const BandTable& get(int L) {
-    auto it = tabs.find(L);
-    if (it != tabs.end()) return it->second;
+    if (tabs[L]) return *tabs[L];
     BandTable T = build_band(L, n_y, force, WINDOW_MAX);
     off[L] = (int32_t)eb.size();
     for (int i = 0; i <= L; ++i) {
@@ -187,17 +189,34 @@ struct BandStore {  // host cache + device mirror of per-length corridor tables 
       for (int w = 0; w < 4; ++w) mask.push_back(T.mask[(size_t)i * 4 + w]);
     }
     dirty = true;
-    return tabs.emplace(L, std::move(T)).first->second;
+    tabs[L].reset(new BandTable(std::move(T)));
+    return *tabs[L];
   }
-  void upload(nw_ctx* c, cudaStream_t st) {
-    if (!dirty) return;
+  size_t up_rows = 0;  // table rows already on the device (tables are append-only)
+  // copies the rows added since the last upload (everything after a reallocation).  Asynchronous: the caller
+  // synchronises once after all stores, before the next get() can reallocate the host vectors.
+  bool upload(nw_ctx* c, cudaStream_t st) {
+    (void)st;
+    if (!dirty) return false;
+    const size_t rows = eb.size();
+    if (rows * 4 > d_ab.cap || rows * 2 > d_eb.cap || rows > d_sb.cap || rows * 16 > d_mask.cap) {
+      d_ab.ensure(rows * 4 * 2);  // slack: the next few tables append in place
+      d_eb.ensure(rows * 2 * 2);
+      d_sb.ensure(rows * 2);
+      d_mask.ensure(rows * 16 * 2);
+      up_rows = 0;
+    }
     h2d(c, d_off.ensure(off.size() * 4), off.data(), off.size() * 4);
-    h2d(c, d_ab.ensure(ab.size() * 2, true), ab.data(), ab.size() * 2);
-    h2d(c, d_eb.ensure(eb.size() * 2, true), eb.data(), eb.size() * 2);
-    h2d(c, d_sb.ensure(sb.size(), true), sb.data(), sb.size());
-    h2d(c, d_mask.ensure(mask.size() * 4, true), mask.data(), mask.size() * 4);
-    CK(spin_sync(st));  // host vectors may be reallocated by the next get()
+    const size_t r0 = up_rows, n = rows - up_rows;
+    if (n) {
+      h2d(c, d_ab.as<int16_t>() + r0 * 2, ab.data() + r0 * 2, n * 4);
+      h2d(c, d_eb.as<int16_t>() + r0, eb.data() + r0, n * 2);
+      h2d(c, d_sb.as<uint8_t>() + r0, sb.data() + r0, n);
+      h2d(c, d_mask.as<uint32_t>() + r0 * 4, mask.data() + r0 * 4, n * 16);
+    }
+    up_rows = rows;
     dirty = false;
+    return true;
   }
 };
 
@@ -221,8 +240,8 @@ struct nw_ctx {
   DevBuf table;
   uint64_t table_cap = 0;
   // per-level scratch
-  DevBuf cnt, off, bsum, slot, owner, is_new, newrank, new_len, hist, bstart, cursor, work, scratch, flag, pre, sel, keys,
-      misc, rslot, newflag, grank, edgebuf, cta_rid, new_rid, best, gather;
+  DevBuf cnt, off, bsum, slot, owner, is_new, newrank, nrank, new_len, hist, bstart, cursor, work, scratch, flag, pre, sel, keys,
+      misc, rslot, newflag, grank, edgebuf, cta_rid, new_rid, best, gather, binflag, binrank, binsum, binrec;
   void* dist = nullptr;  // active frontier-sharded search (Search*, nw_dist_*)
   void* pinned = nullptr;  // pinned staging area for D2H scalars / histograms (grown on demand)
   size_t pinned_bytes = 0;
@@ -442,46 +461,75 @@ ScoreView view_of(const Level& L) {
   return ScoreView{L.frontier(),          L.n_new,           L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(),
                    L.k3.as<int32_t>(),    L.cost.as<int32_t>(), L.total.as<int32_t>()};
 }
-// Buckets the fresh candidates by (region, child length) and runs the DP kernels.  hist_h[bucket_key(...)] is the
-// host copy of the (region, length, sub-counter) histogram written by k_assign; lcap = longest child length + 1.
+// Buckets the fresh candidates by (region, child length) and runs the DP kernels.  hist_dev[bucket_key(...)] is the
+// device histogram of (region, length, sub-counter) written by k_assign / k_len_hist; lcap = longest child length + 1.
+// Only the non-empty bins travel to the host (compacted on the device, in (region, length) order).
 // Work-list layout: kernel class (register window W ascending, generic last) > region > length; every bucket is
 // padded to a warp, every region segment of a register-kernel class to a CTA (a CTA stages one region context).
-void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int lcap, const uint16_t* new_rid_dev, int force,
+void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int lcap, const uint16_t* new_rid_dev, int force,
                  int flags, int* best_dev, int64_t* cells_out /* [n_regions] or nullptr */) {
   const int R = c->n_regions;
   const size_t nbins = (size_t)R * lcap * NSUB;
+  const uint32_t nb = (uint32_t)((size_t)R * lcap);
   cudaStream_t st = c->stream;
+  static const bool dbg = getenv("NW_DEBUG_TIMING") != nullptr;
+  auto tnow = [] { return std::chrono::steady_clock::now(); };
+  auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  const auto T0 = tnow();
+  if (cells_out) std::fill(cells_out, cells_out + R, (int64_t)0);
+  // non-empty bins -> host
+  std::vector<BinRec> bins;
+  {
+    uint32_t* bflag = (uint32_t*)c->binflag.ensure((size_t)nb * 4, true);
+    uint32_t* brank = (uint32_t*)c->binrank.ensure((size_t)nb * 4, true);
+    uint32_t* bsumn = (uint32_t*)c->binsum.ensure((size_t)nb * 4, true);
+    uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(nb) * 4, true);
+    int32_t* misc = (int32_t*)c->misc.p;
+    c->launches += launch_bin_flags(hist_dev, nb, bflag, bsumn, st);
+    c->launches += launch_scan(bflag, brank, nb, bsum, (uint32_t*)(misc + 13), st);
+    BinRec* brec = (BinRec*)c->binrec.ensure((size_t)std::min<uint64_t>(nb, (uint64_t)Lv.n_new + 1) * sizeof(BinRec), true);
+    c->launches += launch_bin_compact(bflag, brank, bsumn, nb, brec, st);
+    uint32_t* pin = (uint32_t*)c->pinned;
+    d2h(c, pin, misc, 64);
+    CK(spin_sync(st));
+    const uint32_t n = pin[13];
+    if (!n) return;
+    bins.resize(n);
+    d2h(c, bins.data(), brec, (size_t)n * sizeof(BinRec));
+    CK(spin_sync(st));
+  }
   struct Bucket {
     int rid, L, cls;  // cls: window W (fast) or 0 (generic)
-    uint32_t n;
+    uint32_t n, bin;
   };
-  std::vector<Bucket> bk;
-  for (int r = 0; r < R; ++r) {
-    int64_t cells = 0;
-    for (int L = 1; L < lcap; ++L) {
-      uint32_t nL = 0;
-      const size_t k0 = ((size_t)r * lcap + L) * NSUB;
-      for (int sb = 0; sb < NSUB; ++sb) nL += hist_h[k0 + sb];
-      if (!nL) continue;
-      const BandTable& T = c->rbands[r]->get(L);
-      if (!T.contiguous) fail(NW_ERR_RANGE, "corridor rows are not intervals for this shape (unsupported)");
-      int cls = 0;
-      if (!(flags & NW_FLAG_GENERIC_DP) && T.fast_ok) cls = score_fast_window(T.max_width);
-      if (cls && score_fast_smem(cls, c->ctx_max, L) > 200 * 1024) cls = 0;  // tiles would not fit: generic kernel
-      bk.push_back(Bucket{r, L, cls, nL});
-      cells += (int64_t)nL * T.cells;
-    }
-    if (cells_out) cells_out[r] = cells;
+  std::vector<Bucket> bk(bins.size());
+  std::vector<uint32_t> cls_count;  // counting sort by kernel class: register windows ascending, generic (0) last
+  auto cls_key = [](int cls) { return cls ? (uint32_t)cls : 1025u; };
+  cls_count.assign(1027, 0);
+  for (size_t k = 0; k < bins.size(); ++k) {
+    const int r = (int)(bins[k].bin / (uint32_t)lcap), L = (int)(bins[k].bin % (uint32_t)lcap);
+    const BandTable& T = c->rbands[r]->get(L);
+    if (!T.contiguous) fail(NW_ERR_RANGE, "corridor rows are not intervals for this shape (unsupported)");
+    int cls = 0;
+    if (!(flags & NW_FLAG_GENERIC_DP) && T.fast_ok) cls = score_fast_window(T.max_width);
+    if (cls && score_fast_smem(cls, c->ctx_max, L) > 200 * 1024) cls = 0;  // tiles would not fit: generic kernel
+    bk[k] = Bucket{r, L, cls, bins[k].n, bins[k].bin};
+    cls_count[cls_key(cls) + 1]++;
+    if (cells_out) cells_out[r] += (int64_t)bins[k].n * T.cells;
   }
-  if (bk.empty()) return;
-  for (int r = 0; r < R; ++r) c->rbands[r]->upload(c, st);
+  const auto T1 = tnow();
+  {
+    bool any = false;
+    for (int r = 0; r < R; ++r) any |= c->rbands[r]->upload(c, st);
+    if (any) CK(spin_sync(st));
+  }
   refresh_region_bands(c);
-  std::stable_sort(bk.begin(), bk.end(), [](const Bucket& a, const Bucket& b) {
-    const int ka = a.cls ? a.cls : 1 << 20, kb = b.cls ? b.cls : 1 << 20;
-    if (ka != kb) return ka < kb;
-    return a.rid < b.rid;  // lengths stay ascending inside a region (stable)
-  });
-  std::vector<uint32_t> bstart(nbins, 0);
+  const auto T2 = tnow();
+  for (size_t k = 1; k < cls_count.size(); ++k) cls_count[k] += cls_count[k - 1];
+  std::vector<uint32_t> order(bk.size());  // class-major; (region, length) ascending inside a class (stable)
+  for (size_t k = 0; k < bk.size(); ++k) order[cls_count[cls_key(bk[k].cls)]++] = (uint32_t)k;
   struct Range {
     int cls;
     uint32_t begin, end;
@@ -491,17 +539,13 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int lca
   std::vector<uint16_t> cta_rid;  // region of every CTA, over the whole work list (CTA = 128 slots)
   uint32_t pos = 0;
   int prev_rid = -1;
-  for (const Bucket& b : bk) {
+  for (uint32_t idx : order) {
+    const Bucket& b = bk[idx];
     const bool new_class = ranges.empty() || ranges.back().cls != b.cls;
     if (new_class || (b.cls && b.rid != prev_rid)) pos = (pos + 127) & ~127u;  // CTA boundary
     if (new_class) ranges.push_back(Range{b.cls, pos, pos, 0});
     prev_rid = b.rid;
-    uint32_t at = pos;  // the sub-counters of one length share one contiguous, 32-padded bucket
-    const size_t k0 = ((size_t)b.rid * lcap + b.L) * NSUB;
-    for (int sb = 0; sb < NSUB; ++sb) {
-      bstart[k0 + sb] = at;
-      at += hist_h[k0 + sb];
-    }
+    bins[idx].n = pos;  // the sub-counters of one length share one contiguous, 32-padded bucket (k_bucket_fill)
     pos += (b.n + 31) & ~31u;
     ranges.back().end = pos;
     ranges.back().lmax = std::max(ranges.back().lmax, b.L);
@@ -510,9 +554,14 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int lca
       if (cta_rid.size() < last_cta) cta_rid.resize(last_cta, (uint16_t)b.rid);
     }
   }
+  const auto T3 = tnow();
   const uint32_t n_work = pos;
-  h2d(c, c->bstart.ensure(nbins * 4, true), bstart.data(), nbins * 4);
-  CK(cudaMemsetAsync(c->cursor.ensure(nbins * 4, true), 0, nbins * 4, st));
+  {
+    BinRec* brec = c->binrec.as<BinRec>();
+    h2d(c, brec, bins.data(), bins.size() * sizeof(BinRec));
+    c->launches += launch_bucket_fill(brec, (uint32_t)bins.size(), hist_dev, (uint32_t*)c->bstart.ensure(nbins * 4, true),
+                                      (uint32_t*)c->cursor.ensure(nbins * 4, true), st);
+  }
   CK(cudaMemsetAsync(c->work.ensure((size_t)n_work * 4, true), 0xFF, (size_t)n_work * 4, st));
   uint16_t* d_cta_rid = nullptr;
   if (R > 1) {
@@ -523,6 +572,9 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_h, int lca
                                        force, c->bstart.as<uint32_t>(), c->cursor.as<uint32_t>(), c->work.as<uint32_t>(),
                                        st);
   CK(spin_sync(st));  // bstart / cta_rid host vectors go out of scope
+  if (dbg)
+    fprintf(stderr, "[nw scoring] buckets %zu, work %u for %u new, ranges %zu: bucket loop %.2f ms, bands %.2f, layout %.2f, scatter %.2f\n",
+            bk.size(), n_work, Lv.n_new, ranges.size(), tms(T0, T1), tms(T1, T2), tms(T2, T3), tms(T3, tnow()));
   ScoreArgs A{};
   A.F = Lv.F;
   A.F.regions = c->d_regions.as<RegionDev>();
@@ -708,19 +760,17 @@ struct Search {
     CK(spin_sync(s));
     // score the roots (solver.jl:599) -- a root's score never updates `best` (:606): dummy best array
     const int lcap = c->nx_max + 1;
-    std::vector<uint32_t> hist((size_t)R * lcap * NSUB, 0);
-    bool any = false;
-    for (int r = 0; r < R; ++r)
-      if (!early_exit(c->RH[r].n_x, c->RH[r].n_y)) {
-        hist[bucket_key(r, lcap, c->RH[r].n_x, (uint32_t)r)] += 1;
-        any = true;
-      }
-    if (any) {
+    {
+      const size_t nbins = (size_t)R * lcap * NSUB;
+      uint32_t* hist = (uint32_t*)c->hist.ensure(nbins * 4, true);
+      CK(cudaMemsetAsync(hist, 0, nbins * 4, s));
+      c->launches += launch_len_hist(c->new_len.as<uint16_t>(), L0.nrid.as<uint16_t>(), c->d_regions.as<RegionDev>(), lcap,
+                                     (uint32_t)R, 0, hist, s);
       ScoreView view = view_of(L0);  // candidates of level 0 against the frontier of level 1
       view.F = frontier_of(L1);
       int* dummy_best = (int*)c->flag.ensure((size_t)(R + 1) * 4, true);
       CK(cudaMemsetAsync(dummy_best, 0, (size_t)(R + 1) * 4, s));
-      run_scoring(c, view, hist.data(), lcap, L0.nrid.as<uint16_t>(), 0, o.flags, dummy_best, nullptr);
+      run_scoring(c, view, hist, lcap, L0.nrid.as<uint16_t>(), 0, o.flags, dummy_best, nullptr);
     }
     d2h(c, k3i.data(), L0.k3.p, (size_t)R * 4);
     d2h(c, ci.data(), L0.cost.p, (size_t)R * 4);
@@ -767,6 +817,12 @@ struct Search {
     L.cstart.assign(R + 1, 0);
     L.nstart.assign(R + 1, 0);
     if (L.P == 0) return false;
+    static const bool dbg = getenv("NW_DEBUG_TIMING") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const auto T0 = tnow();
     ExpandArgs E{};
     E.F = frontier_of(L);
     E.nx_max = c->nx_max;
@@ -784,6 +840,7 @@ struct Search {
     if (R > 1) d2h(c, pinned((size_t)(R + 1) * 4 + 256) + 64, c->gather.p, (size_t)(R + 1) * 4);
     CK(spin_sync(s));
     CK(cudaGetLastError());
+    const auto T1 = tnow();
     const uint32_t G = pin_u32()[4];
     const int maxlen = (int)pin_u32()[2];
     for (int r = 0; r <= R; ++r) {
@@ -825,6 +882,7 @@ struct Search {
     if (R > 1) d2h(c, pin_u32() + 64, c->gather.p, (size_t)(R + 1) * 4);
     CK(spin_sync(s));
     CK(cudaGetLastError());
+    const auto T2 = tnow();
     const uint32_t n_new = pin_u32()[5];
     for (int r = 0; r <= R; ++r) {
       const uint32_t v = R > 1 ? pin_u32()[64 + r] : (r == 0 ? 0u : n_new);
@@ -868,15 +926,20 @@ struct Search {
     CK(cudaMemsetAsync(A.hist, 0, nbins * 4, s));
     c->launches += launch_assign(A, s);
     if (o.flags & NW_FLAG_VERIFY_DEDUP) verify_level(d, E, is_new, owner, G);
-    uint32_t* hist_h = pinned(nbins * 4 + 1024) + 128;
-    d2h(c, hist_h, A.hist, nbins * 4);
-    CK(spin_sync(s));
     CK(cudaGetLastError());
+    const auto T3 = tnow();
     std::vector<int64_t> cells(R, 0);
     run_scoring(c, ScoreView{frontier_of(L), L.n_new, L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(), L.k3.as<int32_t>(),
                              L.cost.as<int32_t>(), L.total.as<int32_t>()},
-                hist_h, lcap, L.nrid.as<uint16_t>(), 0, o.flags, c->best.as<int>(), cells.data());
+                A.hist, lcap, L.nrid.as<uint16_t>(), 0, o.flags, c->best.as<int>(), cells.data());
     for (int r = 0; r < R; ++r) rst[r].cells[d - 1] = cells[r];
+    if (dbg) {
+      const auto T4 = tnow();
+      CK(spin_sync(s));
+      const auto T5 = tnow();
+      fprintf(stderr, "[nw level %d] R=%d P=%d G=%u new=%u lcap=%d: count %.2f ms, expand+dedup %.2f, assign %.2f, score prep %.2f, "
+                      "score wait %.2f\n", d, R, L.P, G, n_new, lcap, tms(T0, T1), tms(T1, T2), tms(T2, T3), tms(T3, T4), tms(T4, T5));
+    }
     gtotal += G;
     n_ids += (int32_t)n_new;
     return n_new > 0;
@@ -891,6 +954,8 @@ struct Search {
     const uint32_t n = Lr.n_new;
     int32_t* misc = (int32_t*)c->misc.p;
     N.fstart.assign(R + 1, 0);
+    static const bool dbg = getenv("NW_DEBUG_TIMING") != nullptr;
+    const auto S0 = std::chrono::steady_clock::now();
     if (n == 0) {
       N.P = 0;
       return;
@@ -966,6 +1031,11 @@ struct Search {
     M.pw = c->d_pow.as<U4>();
     c->launches += launch_materialise(M, s);
     CK(cudaGetLastError());
+    if (dbg) {
+      CK(spin_sync(s));
+      fprintf(stderr, "[nw select %d] valid=%u P2=%u: %.2f ms\n", d, nvalid, P2,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - S0).count());
+    }
   }
 
   void pad_levels(int D) {  // levels that were never reached still exist (empty) for the report loops
@@ -1151,16 +1221,13 @@ struct Search {
     A.hist = (uint32_t*)c->hist.ensure(nbins * 4, true);
     CK(cudaMemsetAsync(A.hist, 0, nbins * 4, s));
     c->launches += launch_assign(A, s);
-    uint32_t* hist_h = pinned(nbins * 4 + 1024) + 128;
-    d2h(c, hist_h, A.hist, nbins * 4);
-    CK(spin_sync(s));
     CK(cudaGetLastError());
     int64_t cells = 0;
     ScoreView V{frontier_of(L), n_loc, L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(), L.l_k3.as<int32_t>(),
                 L.l_cost.as<int32_t>(), L.l_total.as<int32_t>()};
     int* dummy_best = (int*)c->flag.ensure(16, true);  // best is taken from the merged records
     CK(cudaMemsetAsync(dummy_best, 0, 8, s));
-    run_scoring(c, V, hist_h, lcap, L.nrid.as<uint16_t>(), 0, o.flags, dummy_best, &cells);
+    run_scoring(c, V, A.hist, lcap, L.nrid.as<uint16_t>(), 0, o.flags, dummy_best, &cells);
     rst[0].cells[d - 1] = cells;  // cells evaluated by THIS rank (includes candidates another rank discovered first)
     CK(spin_sync(s));
     return n_loc;
@@ -1329,11 +1396,21 @@ struct Search {
         c->launches += launch_mark_parents(lv[l].cand_id.as<int32_t>(), lv[l].desc.as<uint64_t>(),
                                            lv[l].fid.as<int32_t>(), lv[l].G, needed, pass, l, o.maxdepth, c->stream);
   }
-  // phase 3: compact this rank's edges into needed ids (all levels) into c->edgebuf; returns their number
-  uint32_t extract_edges(const uint8_t* needed) {
+  // phase 3: node index of every needed id (exclusive scan of the needed flags: ascending id order, roots first),
+  // then this rank's edges into needed ids (all levels) compacted into c->edgebuf with node indices as end points;
+  // returns their number.  The ranks are identical on every rank of a sharded search (needed is replicated).
+  uint32_t n_nodes = 0;
+  uint32_t extract_edges(uint8_t* needed) {
     cudaStream_t s = c->stream;
     int32_t* misc = (int32_t*)c->misc.p;
     const int nl = (int)lv.size();
+    const uint32_t nflag = (uint32_t)n_ids + 1;
+    CK(cudaMemsetAsync(needed + 1, 1, (size_t)R, s));  // the roots are always nodes (index r for region r)
+    uint32_t* nflags = (uint32_t*)c->is_new.ensure((size_t)nflag * 4, true);
+    uint32_t* nrank = (uint32_t*)c->nrank.ensure((size_t)nflag * 4, true);
+    uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(nflag) * 4, true);
+    c->launches += launch_needed_flags(needed, nflag, nflags, s);
+    c->launches += launch_scan(nflags, nrank, nflag, bsum, (uint32_t*)(misc + 11), s);
     uint32_t cap = std::max<uint32_t>(edge_cap_hint, 1u << 16);
     for (;;) {  // one pass; repeated with a larger buffer only if the append counter overflowed the capacity
       EdgeRec* buf = (EdgeRec*)c->edgebuf.ensure((size_t)cap * sizeof(EdgeRec));
@@ -1341,7 +1418,7 @@ struct Search {
       for (int l = 1; l < nl; ++l) {
         const Level& L = lv[l];
         c->launches += launch_edge_append(L.cand_id.as<int32_t>(), L.desc.as<uint64_t>(), L.fid.as<int32_t>(), L.G, needed,
-                                          l, o.maxdepth, L.gbase, world > 1 ? L.off_loc.as<uint32_t>() : nullptr,
+                                          nrank, l, o.maxdepth, L.gbase, world > 1 ? L.off_loc.as<uint32_t>() : nullptr,
                                           world > 1 ? L.off_glob.as<uint32_t>() : nullptr, buf, cap,
                                           (uint32_t*)(misc + 8), s);
       }
@@ -1349,6 +1426,7 @@ struct Search {
       CK(spin_sync(s));
       CK(cudaGetLastError());
       const uint32_t n = pin_u32()[8];
+      n_nodes = pin_u32()[11];
       if (n <= cap) {
         edge_cap_hint = std::max(edge_cap_hint, n);
         return n;
@@ -1356,40 +1434,26 @@ struct Search {
       cap = n + n / 8;
     }
   }
-  // phase 4: host graph of the needed ids from the edge records of all ranks (sorted into discovery order)
+  // phase 4: host graph of the needed ids from the edge records of all ranks.  Node records arrive in node order
+  // and edges carry node indices, so this is one counting sort by child plus the discovery order inside every
+  // child's short edge list -- no searching.
   void build_nodes(const uint8_t* needed, std::vector<EdgeRec>& edges) {
     cudaStream_t s = c->stream;
-    int32_t* misc = (int32_t*)c->misc.p;
     const int nl = (int)lv.size();
-    uint32_t cap = std::max<uint32_t>(id_cap_hint, 1u << 14);
-    std::vector<IdRec> hi;
-    for (;;) {
-      IdRec* buf = (IdRec*)c->keys.ensure((size_t)cap * sizeof(IdRec));
-      CK(cudaMemsetAsync(misc + 9, 0, 4, s));
+    const size_t nn = n_nodes;
+    std::vector<IdRec> hi(nn);
+    if (nn) {
+      IdRec* buf = (IdRec*)c->keys.ensure(nn * sizeof(IdRec));
       for (int l = 1; l < nl; ++l) {
         const Level& L = lv[l];
-        c->launches += launch_id_append(L.k3.as<int32_t>(), L.cost.as<int32_t>(), L.total.as<int32_t>(), L.id_base, L.n_new,
-                                        needed, buf, cap, (uint32_t*)(misc + 9), s);
+        c->launches += launch_id_write(L.k3.as<int32_t>(), L.cost.as<int32_t>(), L.total.as<int32_t>(), L.id_base, L.n_new,
+                                       needed, c->nrank.as<uint32_t>(), buf, s);
       }
-      d2h(c, pin_u32(), misc, 64);
+      if (nn > (size_t)R) d2h(c, hi.data() + R, buf + R, (nn - (size_t)R) * sizeof(IdRec));
       CK(spin_sync(s));
-      const uint32_t n = pin_u32()[9];
-      if (n <= cap) {
-        id_cap_hint = std::max(id_cap_hint, n);
-        hi.resize(n);
-        if (n) {
-          d2h(c, hi.data(), buf, (size_t)n * sizeof(IdRec));
-          CK(spin_sync(s));
-        }
-        break;
-      }
-      cap = n + n / 8;
     }
-    // node table: roots + every needed id, sorted by id
-    for (int r = 0; r < R; ++r) hi.push_back(IdRec{r + 1, root_k3[r], root_cost[r], root_total[r]});
-    std::sort(hi.begin(), hi.end(), [](const IdRec& a, const IdRec& b) { return a.id < b.id; });
+    for (int r = 0; r < R && (size_t)r < nn; ++r) hi[r] = IdRec{r + 1, root_k3[r], root_cost[r], root_total[r]};
     NodeTable& T = nodes;
-    const size_t nn = hi.size();
     T.id.resize(nn);
     T.k3.resize(nn);
     T.cost.resize(nn);
@@ -1400,25 +1464,23 @@ struct Search {
       T.cost[k] = hi[k].cost;
       T.total[k] = hi[k].total;
     }
-    // CSR by child (counting sort), then discovery order inside every child's short list
     T.estart.assign(nn + 1, 0);
-    std::vector<int32_t> slot(edges.size());
-    for (size_t e = 0; e < edges.size(); ++e) {
-      const int k = T.find(edges[e].child);
-      slot[e] = k;
-      if (k >= 0) T.estart[k + 1]++;
-    }
+    for (const EdgeRec& e : edges) T.estart[(size_t)e.child + 1]++;
     for (size_t k = 0; k < nn; ++k) T.estart[k + 1] += T.estart[k];
-    T.edges.resize(T.estart[nn]);
+    T.edges.resize(edges.size());
     std::vector<uint32_t> cur(T.estart.begin(), T.estart.end() - 1);
-    for (size_t e = 0; e < edges.size(); ++e)
-      if (slot[e] >= 0) T.edges[cur[slot[e]]++] = edges[e];
-    for (size_t k = 0; k < nn; ++k)
-      if (T.estart[k + 1] - T.estart[k] > 1)
-        std::sort(T.edges.begin() + T.estart[k], T.edges.begin() + T.estart[k + 1],
+    for (const EdgeRec& e : edges) T.edges[cur[e.child]++] = e;
+    for (size_t k = 0; k < nn; ++k) {
+      const uint32_t e0 = T.estart[k], e1 = T.estart[k + 1];
+      if (e1 - e0 == 2) {
+        if (T.edges[e0 + 1].gpos < T.edges[e0].gpos) std::swap(T.edges[e0], T.edges[e0 + 1]);
+      } else if (e1 - e0 > 2) {
+        std::sort(T.edges.begin() + e0, T.edges.begin() + e1,
                   [](const EdgeRec& a, const EdgeRec& b) { return a.gpos < b.gpos; });
+      }
+    }
     T.eparent.resize(T.edges.size());
-    for (size_t e = 0; e < T.edges.size(); ++e) T.eparent[e] = T.find(T.edges[e].parent);
+    for (size_t e = 0; e < T.edges.size(); ++e) T.eparent[e] = T.edges[e].parent;
     T.memo_w = o.maxdepth + 3;
     T.memo.assign(nn * (size_t)T.memo_w, 0);
     CK(cudaGetLastError());
@@ -1616,6 +1678,12 @@ struct Search {
       return;
     }
     cudaStream_t s = c->stream;
+    const bool dbg = getenv("NW_DEBUG_TIMING") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const auto T0 = tnow();
     int32_t* misc = (int32_t*)c->misc.p;
     build_local_ids();
     std::vector<int32_t> k3min(R);
@@ -1647,6 +1715,7 @@ struct Search {
       }
       cap = n + n / 8;
     }
+    const auto T1 = tnow();
     std::vector<std::vector<std::pair<int32_t, int32_t>>> good(R);  // (-k3, gid)
     for (int r = 0; r < R; ++r)
       if (root_k3[r] >= 0 && root_k3[r] >= k3min[r]) good[r].emplace_back(-root_k3[r], r + 1);
@@ -1666,6 +1735,7 @@ struct Search {
       c->launches += launch_set_needed(dg, (uint32_t)gids.size(), needed, s);
       CK(spin_sync(s));
     }
+    const auto T2 = tnow();
     for (int pass = 1; pass <= o.maxdepth + 1; ++pass) extract_mark(needed, pass);
     const uint32_t ne = extract_edges(needed);
     std::vector<EdgeRec> he(ne);
@@ -1673,8 +1743,34 @@ struct Search {
       d2h(c, he.data(), c->edgebuf.p, (size_t)ne * sizeof(EdgeRec));
       CK(spin_sync(s));
     }
+    const auto T3 = tnow();
     build_nodes(needed, he);
-    for (int r = 0; r < R; ++r) enumerate_list(out[r], r, good[r]);
+    const auto T4 = tnow();
+    {  // regions are independent (disjoint nodes, own result object): enumerate them on a few host threads
+      const int nt = std::max(1, std::min({8, (int)std::thread::hardware_concurrency(), R / 32}));
+      std::atomic<int> next{0};
+      std::exception_ptr err;
+      std::mutex err_mu;
+      auto work = [&] {
+        try {
+          for (int r = next.fetch_add(1); r < R; r = next.fetch_add(1)) enumerate_list(out[r], r, good[r]);
+        } catch (...) {
+          std::lock_guard<std::mutex> g(err_mu);
+          if (!err) err = std::current_exception();
+          next.store(R);
+        }
+      };
+      std::vector<std::thread> th;
+      for (int t = 1; t < nt; ++t) th.emplace_back(work);
+      work();
+      for (auto& t : th) t.join();
+      if (err) std::rethrow_exception(err);
+    }
+    const auto T5 = tnow();
+    if (dbg)
+      fprintf(stderr, "[nw report_many] R=%d qual %.2f ms (%zu ids), select %.2f, mark+edges %.2f (%u edges), nodes %.2f (%zu), "
+                      "enumerate %.2f\n", R, tms(T0, T1), q.size(), tms(T1, T2), tms(T2, T3), ne, tms(T3, T4), nodes.size(),
+              tms(T4, T5));
   }
 
   void enumerate(nw_result* out, int rid, int k3_min) {
@@ -1692,6 +1788,17 @@ struct Search {
     E.limit = o.maxreport;
     E.R = out;
     E.rid = rid;
+    if (o.maxreport >= 0) {  // the usual report is full: size the output once
+      const size_t n = (size_t)std::min<int64_t>(o.maxreport, std::min<int64_t>(4096, 16 + 2 * (int64_t)good.size()));
+      out->t_score.reserve(n);
+      out->t_k3.reserve(n);
+      out->t_id.reserve(n);
+      out->t_cost.reserve(n);
+      out->t_total.reserve(n);
+      out->t_off.reserve(n + 1);
+      out->t_moves.reserve(n * 3 * (size_t)(o.maxdepth + 1));
+      out->tsv.reserve(n * (size_t)(16 + 20 * (o.maxdepth + 1)));
+    }
     out->t_off.push_back(0);
     size_t g0 = 0;
     while (g0 < good.size() && !E.full()) {
@@ -2087,7 +2194,6 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
     std::vector<uint32_t> newlist(n);
     std::vector<uint16_t> nlen(n);
     const int lcap = maxlen + 1;
-    std::vector<uint32_t> hist((size_t)lcap * NSUB, 0);
     std::vector<uint16_t> nrid(n, 0);
     std::vector<int32_t> k3(n, 0), cost(n, -1), total(n, 0);
     for (int64_t k = 0; k < n; ++k) {
@@ -2097,7 +2203,6 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
       desc[k] = pack_desc((uint32_t)k, 0, 0, KIND_ID);
       newlist[k] = (uint32_t)k;
       nlen[k] = (uint16_t)l;
-      if (force || !early_exit(l, n_y)) hist[bucket_key(0, lcap, l, (uint32_t)k)]++;
     }
     L.G = (uint32_t)n;
     L.n_new = (uint32_t)n;
@@ -2119,7 +2224,12 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
       V.F.rid = nullptr;
       int* dummy_best = (int*)c->best.ensure(16);
       CK(cudaMemsetAsync(dummy_best, 0, 8, s));
-      run_scoring(c, V, hist.data(), lcap, L.nrid.as<uint16_t>(), force, flags, dummy_best, nullptr);
+      const size_t nbins = (size_t)lcap * NSUB;
+      uint32_t* hist = (uint32_t*)c->hist.ensure(nbins * 4, true);
+      CK(cudaMemsetAsync(hist, 0, nbins * 4, s));
+      c->launches += launch_len_hist(c->new_len.as<uint16_t>(), nullptr, c->d_regions.as<RegionDev>(), lcap, (uint32_t)n,
+                                     force, hist, s);
+      run_scoring(c, V, hist, lcap, L.nrid.as<uint16_t>(), force, flags, dummy_best, nullptr);
     }
     d2h(c, k3.data(), L.k3.p, n * 4);
     d2h(c, cost.data(), L.cost.p, n * 4);
@@ -2352,7 +2462,7 @@ int nw_dist_report_edges(nw_ctx* c, const void* needed_dev, int64_t* n_edges) {
   const int rc = guard([&] {
     Search* S = dist_of(c);
     CK(cudaSetDevice(c->device));
-    const uint32_t n = S->extract_edges((const uint8_t*)needed_dev);
+    const uint32_t n = S->extract_edges((uint8_t*)needed_dev);
     S->dist_edges = n;
     if (n_edges) *n_edges = n;
   });

@@ -611,6 +611,67 @@ int launch_bucket_scatter(const uint16_t* new_len, const uint16_t* new_rid, cons
   return 1;
 }
 
+// ---- bucket bookkeeping on the device: the host only ever sees the non-empty (region, length) bins ----
+static_assert(NSUB == 8, "bin kernels read the sub-counters of a bin as two uint4");
+// histogram of (region, child length, sub-counter) from explicit lengths (roots, nw_score_batch)
+__global__ void k_len_hist(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap, uint32_t n,
+                           int force, uint32_t* hist) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int len = new_len[r], rid = new_rid ? new_rid[r] : 0;
+  if (force || !early_exit(len, regions[rid].n_y)) atomicAdd(&hist[bucket_key(rid, lcap, len, r)], 1u);
+}
+__global__ void k_bin_flags(const uint32_t* hist, uint32_t nb, uint32_t* flag, uint32_t* nsum) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const uint4* h = reinterpret_cast<const uint4*>(hist + (size_t)i * NSUB);
+  const uint4 a = h[0], b = h[1];
+  const uint32_t n = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+  nsum[i] = n;
+  flag[i] = n ? 1u : 0u;
+}
+__global__ void k_bin_compact(const uint32_t* flag, const uint32_t* rank, const uint32_t* nsum, uint32_t nb, BinRec* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb || !flag[i]) return;
+  out[rank[i]] = BinRec{i, nsum[i]};
+}
+// ent[k] = {bin, first work slot of the bin}: start of every sub-counter's run, and its cursor
+__global__ void k_bucket_fill(const BinRec* ent, uint32_t n, const uint32_t* hist, uint32_t* bstart, uint32_t* cursor) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const size_t k0 = (size_t)ent[k].bin * NSUB;
+  uint32_t at = ent[k].n;
+#pragma unroll
+  for (int sb = 0; sb < NSUB; ++sb) {
+    bstart[k0 + sb] = at;
+    cursor[k0 + sb] = 0;
+    at += hist[k0 + sb];
+  }
+}
+int launch_len_hist(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap, uint32_t n,
+                    int force, uint32_t* hist, cudaStream_t st) {
+  if (!n) return 0;
+  k_len_hist<<<(n + 255) / 256, 256, 0, st>>>(new_len, new_rid, regions, lcap, n, force, hist);
+  return 1;
+}
+int launch_bin_flags(const uint32_t* hist, uint32_t nb, uint32_t* flag, uint32_t* nsum, cudaStream_t st) {
+  if (!nb) return 0;
+  k_bin_flags<<<(nb + 255) / 256, 256, 0, st>>>(hist, nb, flag, nsum);
+  return 1;
+}
+int launch_bin_compact(const uint32_t* flag, const uint32_t* rank, const uint32_t* nsum, uint32_t nb, BinRec* out,
+                       cudaStream_t st) {
+  if (!nb) return 0;
+  k_bin_compact<<<(nb + 255) / 256, 256, 0, st>>>(flag, rank, nsum, nb, out);
+  return 1;
+}
+int launch_bucket_fill(const BinRec* ent, uint32_t n, const uint32_t* hist, uint32_t* bstart, uint32_t* cursor,
+                       cudaStream_t st) {
+  if (!n) return 0;
+  k_bucket_fill<<<(n + 255) / 256, 256, 0, st>>>(ent, n, hist, bstart, cursor);
+  return 1;
+}
+
 // =====================================================================================================
 // generic DP: literal cost-form transcription of slow_score (solver.jl:362-423) in int32 units, any geometry.
 // Thread per candidate; the two DP rows live in a coalesced global scratch [2][n_y+2][threads].
@@ -1002,9 +1063,12 @@ __device__ __forceinline__ uint32_t warp_append(bool take, uint32_t* counter) {
   base = __shfl_sync(0xffffffffu, base, leader);
   return base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
 }
+// child / parent are written as NODE INDICES (rank of the id among the needed ids, from an exclusive scan of the
+// needed flags; -1 = parent not needed), so the host builds its graph without any search
 __global__ void k_edge_append(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
-                              const uint8_t* needed, int lvl, int maxdepth, uint32_t gbase, const uint32_t* off_loc,
-                              const uint32_t* off_glob, EdgeRec* out, uint32_t cap, uint32_t* counter) {
+                              const uint8_t* needed, const uint32_t* nrank, int lvl, int maxdepth, uint32_t gbase,
+                              const uint32_t* off_loc, const uint32_t* off_glob, EdgeRec* out, uint32_t cap,
+                              uint32_t* counter) {
   const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
   bool take = false;
   int32_t child = 0;
@@ -1017,12 +1081,29 @@ __global__ void k_edge_append(const int32_t* cand_id, const uint64_t* desc, cons
   if (!take || at >= cap) return;
   const uint64_t d = desc[pos];
   const uint32_t ps = desc_parent(d);
+  const int32_t pid = front_id[ps];
   EdgeRec e;
-  e.child = child;
-  e.parent = front_id[ps];
+  e.child = (int32_t)nrank[child];
+  e.parent = needed[pid] ? (int32_t)nrank[pid] : -1;
   e.move = (uint32_t)desc_kind(d) | ((uint32_t)desc_i(d) << 2) | ((uint32_t)desc_j(d) << 17);
   e.gpos = off_glob ? gbase + off_glob[ps] + (pos - off_loc[ps]) : gbase + pos;
   out[at] = e;
+}
+// record of every needed id of a level, written at its node index (ascending id order, no sort on the host)
+__global__ void k_id_write(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,
+                           const uint8_t* needed, const uint32_t* nrank, IdRec* out) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n || !needed[id_base + r]) return;
+  IdRec o;
+  o.id = id_base + (int32_t)r;
+  o.k3 = k3[r];
+  o.cost = cost[r];
+  o.total = total[r];
+  out[nrank[id_base + r]] = o;
+}
+__global__ void k_needed_flags(const uint8_t* needed, uint32_t n, uint32_t* flag) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = needed[i] ? 1u : 0u;
 }
 __global__ void k_id_append(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,
                             const uint8_t* needed, IdRec* out, uint32_t cap, uint32_t* counter) {
@@ -1038,11 +1119,23 @@ __global__ void k_id_append(const int32_t* k3, const int32_t* cost, const int32_
   out[at] = o;
 }
 int launch_edge_append(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
-                       const uint8_t* needed, int lvl, int maxdepth, uint32_t gbase, const uint32_t* off_loc,
-                       const uint32_t* off_glob, void* out, uint32_t cap, uint32_t* counter, cudaStream_t st) {
+                       const uint8_t* needed, const uint32_t* nrank, int lvl, int maxdepth, uint32_t gbase,
+                       const uint32_t* off_loc, const uint32_t* off_glob, void* out, uint32_t cap, uint32_t* counter,
+                       cudaStream_t st) {
   if (!G) return 0;
-  k_edge_append<<<(G + 255) / 256, 256, 0, st>>>(cand_id, desc, front_id, G, needed, lvl, maxdepth, gbase, off_loc,
+  k_edge_append<<<(G + 255) / 256, 256, 0, st>>>(cand_id, desc, front_id, G, needed, nrank, lvl, maxdepth, gbase, off_loc,
                                                 off_glob, (EdgeRec*)out, cap, counter);
+  return 1;
+}
+int launch_id_write(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,
+                    const uint8_t* needed, const uint32_t* nrank, void* out, cudaStream_t st) {
+  if (!n) return 0;
+  k_id_write<<<(n + 255) / 256, 256, 0, st>>>(k3, cost, total, id_base, n, needed, nrank, (IdRec*)out);
+  return 1;
+}
+int launch_needed_flags(const uint8_t* needed, uint32_t n, uint32_t* flag, cudaStream_t st) {
+  if (!n) return 0;
+  k_needed_flags<<<(n + 255) / 256, 256, 0, st>>>(needed, n, flag);
   return 1;
 }
 int launch_id_append(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,

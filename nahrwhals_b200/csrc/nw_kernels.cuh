@@ -173,6 +173,11 @@ struct MaterialiseArgs {
   const U4* pw;
 };
 
+// non-empty (region, length) bin of the bucket histogram: bin = rid * lcap + len; n = candidates (device -> host) or
+// first work slot (host -> device)
+struct BinRec {
+  uint32_t bin, n;
+};
 struct EdgeRec {
   int32_t child, parent;
   uint32_t move;  // kind | i << 2 | j << 17

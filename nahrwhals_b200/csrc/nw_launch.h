@@ -20,6 +20,13 @@ int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* is_new, uint32_t* 
 int launch_assign(const AssignArgs& A, cudaStream_t st);
 int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t* is_new, const uint32_t* owner, uint32_t G,
                        unsigned int* mismatches, cudaStream_t st);
+int launch_len_hist(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap, uint32_t n,
+                    int force, uint32_t* hist, cudaStream_t st);
+int launch_bin_flags(const uint32_t* hist, uint32_t nb, uint32_t* flag, uint32_t* nsum, cudaStream_t st);
+int launch_bin_compact(const uint32_t* flag, const uint32_t* rank, const uint32_t* nsum, uint32_t nb, BinRec* out,
+                       cudaStream_t st);
+int launch_bucket_fill(const BinRec* ent, uint32_t n, const uint32_t* hist, uint32_t* bstart, uint32_t* cursor,
+                       cudaStream_t st);
 int launch_bucket_scatter(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap,
                           uint32_t n_new, int force, const uint32_t* bstart, uint32_t* cursor, uint32_t* work,
                           cudaStream_t st);
@@ -44,8 +51,12 @@ int launch_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, int k3_min
 int launch_tie_flags(const int32_t* k3, uint32_t n, int k3_star, uint32_t* flag, cudaStream_t st);
 int launch_k3_hist(const int32_t* k3, uint32_t n, int k3_floor, uint32_t* hist, cudaStream_t st);
 int launch_edge_append(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
-                       const uint8_t* needed, int lvl, int maxdepth, uint32_t gbase, const uint32_t* off_loc,
-                       const uint32_t* off_glob, void* out, uint32_t cap, uint32_t* counter, cudaStream_t st);
+                       const uint8_t* needed, const uint32_t* nrank, int lvl, int maxdepth, uint32_t gbase,
+                       const uint32_t* off_loc, const uint32_t* off_glob, void* out, uint32_t cap, uint32_t* counter,
+                       cudaStream_t st);
+int launch_id_write(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,
+                    const uint8_t* needed, const uint32_t* nrank, void* out, cudaStream_t st);
+int launch_needed_flags(const uint8_t* needed, uint32_t n, uint32_t* flag, cudaStream_t st);
 int launch_id_append(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,
                      const uint8_t* needed, void* out, uint32_t cap, uint32_t* counter, cudaStream_t st);
 int launch_mark_parents(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,

@@ -124,13 +124,13 @@ class Solver:
         R.tsv = C.string_at(data, ln.value).decode() if ln.value else ""
         n = L.nw_result_count(r)
         nm = L.nw_result_move_count(r)
-        R.scores = np.zeros(n, np.float32)
-        R.cost_bp = np.zeros(n, np.int64)
-        R.total_bp = np.zeros(n, np.int64)
-        R.index_id = np.zeros(n, np.int64)
-        R.n_moves = np.zeros(n, np.int32)
-        R.move_off = np.zeros(n, np.int64)
-        R.moves3 = np.zeros((nm, 3), np.int32)
+        R.scores = np.empty(n, np.float32)
+        R.cost_bp = np.empty(n, np.int64)
+        R.total_bp = np.empty(n, np.int64)
+        R.index_id = np.empty(n, np.int64)
+        R.n_moves = np.empty(n, np.int32)
+        R.move_off = np.empty(n, np.int64)
+        R.moves3 = np.empty((nm, 3), np.int32)
         L.nw_result_arrays(r, _p(R.scores), _p(R.n_moves), _p(R.move_off), _p(R.cost_bp), _p(R.total_bp),
                            _p(R.index_id), _p(R.moves3))
         if o.keep_ids:

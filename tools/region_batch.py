@@ -83,6 +83,10 @@ def run_many(regions, per_pass, device=0):
         for q in range(3):
             hs[q] += res[k].stats.host_ms[q]
         dev += res[k].stats.total_ms
+    st = res[0].stats
+    print("   first pass: levels %d, level_ms %s, generated %s, scored %s, launches %d" % (
+        st.n_levels, ["%.2f" % v for v in list(st.level_ms)[:st.n_levels]], list(st.generated)[:st.n_levels],
+        list(st.scored)[:st.n_levels], st.kernel_launches))
     print("   native phases over all passes: setup %.1f ms, search %.1f ms (device timeline %.1f ms), report %.1f ms; "
           "python wall %.1f ms" % (hs[0], hs[1], dev, hs[2], dt * 1e3))
     return len(regions) / dt, sum(sum(R.scored) for R in res), dt
