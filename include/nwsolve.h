@@ -101,6 +101,13 @@ int nw_result_cost(const nw_result* r, int64_t k, int64_t* cost_bp, int64_t* tot
 int nw_result_arrays(const nw_result* r, float* score, int32_t* n_moves, int64_t* move_off, int64_t* cost_bp,
                      int64_t* total_bp, int64_t* index_id, int32_t* moves3);
 int64_t nw_result_move_count(const nw_result* r);
+/* The results of a whole regionfile run in two calls (nw_solve_batch / nw_solve_many hand back n handles):
+ * per-result sizes, then every array of nw_result_arrays / nw_result_tsv / nw_result_stats concatenated in result
+ * order into caller buffers of the summed sizes (move_off stays relative to each result's own first triple). */
+int nw_results_sizes(nw_result* const* rs, int64_t n, int64_t* n_traj, int64_t* n_moves, int64_t* tsv_len);
+int nw_results_gather(nw_result* const* rs, int64_t n, float* score, int32_t* n_moves, int64_t* move_off,
+                      int64_t* cost_bp, int64_t* total_bp, int64_t* index_id, int32_t* moves3, char* tsv,
+                      nw_stats* stats);
 /* The exact bytes write_trajectories (solver.jl:747-753) would write. */
 int nw_result_tsv(const nw_result* r, const char** data, int64_t* len);
 int nw_result_stats(const nw_result* r, nw_stats* out);
@@ -143,6 +150,12 @@ int nw_solve_batch(nw_ctx** ctxs, int32_t n_ctx, const nw_problem* probs, int64_
  * nw_solve.  On error no result is returned (all outs[k] are NULL). */
 int nw_solve_many(nw_ctx* ctx, const nw_problem* probs, int64_t n, const nw_opts* opts, int32_t max_regions_per_pass,
                   nw_result** outs);
+
+/* nw_solve_many over n_ctx contexts (one host thread + CUDA stream each, on one GPU or several): the passes are
+ * handed out dynamically, so the host-side preparation and report of one pass overlap the device work of another.
+ * Results are identical to nw_solve_many / nw_solve; on error no result is returned. */
+int nw_solve_many_ctxs(nw_ctx** ctxs, int32_t n_ctx, const nw_problem* probs, int64_t n, const nw_opts* opts,
+                       int32_t max_regions_per_pass, nw_result** outs);
 
 /* ---- one deep search sharded over `world` ranks (config 3 of BASELINE.json) -------------------------
  * One context per rank, the same problem and options on every rank.  The frontier is replicated; rank r expands the

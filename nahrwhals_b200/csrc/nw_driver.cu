@@ -2121,6 +2121,38 @@ int nw_result_arrays(const nw_result* r, float* score, int32_t* n_moves, int64_t
   if (moves3 && !r->t_moves.empty()) memcpy(moves3, r->t_moves.data(), r->t_moves.size() * 4);
   return NW_OK;
 }
+// bulk accessors: the results of a whole regionfile run in two calls (an FFI host pays per call, not per region)
+int nw_results_sizes(nw_result* const* rs, int64_t n, int64_t* n_traj, int64_t* n_moves, int64_t* tsv_len) {
+  if (!rs || n < 0) return NW_ERR_ARG;
+  for (int64_t k = 0; k < n; ++k) {
+    const nw_result* r = rs[k];
+    if (!r) return NW_ERR_ARG;
+    if (n_traj) n_traj[k] = (int64_t)r->t_score.size();
+    if (n_moves) n_moves[k] = (int64_t)(r->t_moves.size() / 3);
+    if (tsv_len) tsv_len[k] = (int64_t)r->tsv.size();
+  }
+  return NW_OK;
+}
+int nw_results_gather(nw_result* const* rs, int64_t n, float* score, int32_t* n_moves, int64_t* move_off, int64_t* cost_bp,
+                      int64_t* total_bp, int64_t* index_id, int32_t* moves3, char* tsv, nw_stats* stats) {
+  if (!rs || n < 0) return NW_ERR_ARG;
+  size_t at = 0, mt = 0, tt = 0;  // trajectories, move triples, TSV bytes written so far
+  for (int64_t k = 0; k < n; ++k) {
+    const nw_result* r = rs[k];
+    if (!r) return NW_ERR_ARG;
+    const int rc = nw_result_arrays(r, score ? score + at : nullptr, n_moves ? n_moves + at : nullptr,
+                                    move_off ? move_off + at : nullptr, cost_bp ? cost_bp + at : nullptr,
+                                    total_bp ? total_bp + at : nullptr, index_id ? index_id + at : nullptr,
+                                    moves3 ? moves3 + mt * 3 : nullptr);
+    if (rc != NW_OK) return rc;
+    if (tsv && !r->tsv.empty()) memcpy(tsv + tt, r->tsv.data(), r->tsv.size());
+    if (stats) stats[k] = r->stats;
+    at += r->t_score.size();
+    mt += r->t_moves.size() / 3;
+    tt += r->tsv.size();
+  }
+  return NW_OK;
+}
 int64_t nw_result_move_count(const nw_result* r) { return r ? (int64_t)(r->t_moves.size() / 3) : 0; }
 int nw_result_tsv(const nw_result* r, const char** data, int64_t* len) {
   if (!r || !data || !len) return NW_ERR_ARG;
@@ -2275,42 +2307,81 @@ int nw_moveset(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, uint8_t* 
   return rc;
 }
 
-int nw_solve_many(nw_ctx* c, const nw_problem* probs, int64_t n, const nw_opts* opts, int32_t max_regions_per_pass,
-                  nw_result** outs) {
-  if (!c || !probs || n < 0 || !opts || !outs) {
+int nw_solve_many_ctxs(nw_ctx** ctxs, int32_t n_ctx, const nw_problem* probs, int64_t n, const nw_opts* opts,
+                       int32_t max_regions_per_pass, nw_result** outs) {
+  if (!ctxs || n_ctx < 1 || !probs || n < 0 || !opts || !outs) {
     g_last_error = "null argument";
     return NW_ERR_ARG;
   }
+  for (int t = 0; t < n_ctx; ++t)
+    if (!ctxs[t]) {
+      g_last_error = "null context";
+      return NW_ERR_ARG;
+    }
   for (int64_t k = 0; k < n; ++k) outs[k] = nullptr;
-  PoolScope pool_scope(c);
-  const int rc = guard([&] {
-    check_opts(opts);
-    int per = max_regions_per_pass > 0 ? max_regions_per_pass : 256;
-    per = std::min(per, 4096);
+  int per = max_regions_per_pass > 0 ? max_regions_per_pass : 256;
+  per = std::min(per, 4096);
+  const int64_t n_pass = (n + per - 1) / per;
+  std::atomic<int64_t> next{0};
+  std::atomic<int> first_err{NW_OK};
+  std::mutex err_mu;
+  std::string err_msg;
+  // passes are handed out dynamically; while one context's pass is on the device the others prepare the next
+  // regions / enumerate the previous report on the host
+  auto worker = [&](int t) {
+    nw_ctx* c = ctxs[t];
+    PoolScope pool_scope(c);
     std::vector<ProblemRef> P;
     std::vector<nw_result*> R;
-    for (int64_t k0 = 0; k0 < n; k0 += per) {
+    for (;;) {
+      const int64_t pass = next.fetch_add(1);
+      if (pass >= n_pass || first_err.load() != NW_OK) return;
+      const int64_t k0 = pass * per;
       const int m = (int)std::min<int64_t>(per, n - k0);
-      P.resize(m);
-      R.resize(m);
-      for (int k = 0; k < m; ++k) {
-        const nw_problem& q = probs[k0 + k];
-        if (!q.aln_sign || !q.len_x || !q.len_y) fail(NW_ERR_ARG, "null problem buffer");
-        P[k] = ProblemRef{q.aln_sign, q.n_x, q.n_y, q.len_x, q.len_y};
-        R[k] = new nw_result();
-        outs[k0 + k] = R[k];
+      const int rc = guard([&] {
+        check_opts(opts);
+        P.resize(m);
+        R.resize(m);
+        for (int k = 0; k < m; ++k) {
+          const nw_problem& q = probs[k0 + k];
+          if (!q.aln_sign || !q.len_x || !q.len_y) fail(NW_ERR_ARG, "null problem buffer");
+          P[k] = ProblemRef{q.aln_sign, q.n_x, q.n_y, q.len_x, q.len_y};
+        }
+        for (int k = 0; k < m; ++k) {
+          R[k] = new nw_result();
+          outs[k0 + k] = R[k];
+        }
+        do_solve_many(c, P.data(), m, opts, R.data());
+      });
+      if (rc != NW_OK) {
+        cudaGetLastError();
+        std::lock_guard<std::mutex> lk(err_mu);
+        if (first_err.load() == NW_OK) {
+          err_msg = g_last_error;
+          first_err.store(rc);
+        }
+        return;
       }
-      do_solve_many(c, P.data(), m, opts, R.data());
     }
-  });
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_ctx && t < n_pass; ++t) th.emplace_back(worker, t);
+  worker(0);
+  for (auto& x : th) x.join();
+  const int rc = first_err.load();
   if (rc != NW_OK) {
+    g_last_error = err_msg;
     for (int64_t k = 0; k < n; ++k) {
       delete outs[k];
       outs[k] = nullptr;
     }
-    cudaGetLastError();
   }
   return rc;
+}
+
+int nw_solve_many(nw_ctx* c, const nw_problem* probs, int64_t n, const nw_opts* opts, int32_t max_regions_per_pass,
+                  nw_result** outs) {
+  return nw_solve_many_ctxs(&c, 1, probs, n, opts, max_regions_per_pass, outs);
 }
 
 int nw_solve_batch(nw_ctx** ctxs, int32_t n_ctx, const nw_problem* probs, int64_t n, const nw_opts* opts,

@@ -23,19 +23,34 @@ def _p(a):
 class SolveResult:
     """Trajectories in report order (solver.jl:739-743) + counters."""
 
+    _E = dict(f32=np.zeros(0, np.float32), i32=np.zeros(0, np.int32), i64=np.zeros(0, np.int64),
+              m3=np.zeros((0, 3), np.int32))
+
     def __init__(self):
-        self.tsv = ""
-        self.scores = np.zeros(0, np.float32)
-        self.n_moves = np.zeros(0, np.int32)
-        self.move_off = np.zeros(0, np.int64)
-        self.moves3 = np.zeros((0, 3), np.int32)   # (kind, start, stop) rows, trajectory k owns
-        #                                            moves3[move_off[k] : move_off[k] + n_moves[k]]
-        self.cost_bp = np.zeros(0, np.int64)
-        self.total_bp = np.zeros(0, np.int64)
-        self.index_id = np.zeros(0, np.int64)
+        E = SolveResult._E
+        self._tsv = ""               # str, or bytes decoded on first access (bulk unpack)
+        self.scores = E["f32"]
+        self.n_moves = E["i32"]
+        self.move_off = E["i64"]
+        self.moves3 = E["m3"]        # (kind, start, stop) rows, trajectory k owns
+        #                              moves3[move_off[k] : move_off[k] + n_moves[k]]
+        self.cost_bp = E["i64"]
+        self.total_bp = E["i64"]
+        self.index_id = E["i64"]
         self.stats = None
         self.ids = None          # keep_ids: dict(score, cost_bp, total_bp, level)
         self.edges = None        # keep_ids: dict(child, parent, moves)
+
+    @property
+    def tsv(self):
+        """the exact text write_trajectories (solver.jl:747-753) would write"""
+        if not isinstance(self._tsv, str):
+            self._tsv = bytes(self._tsv).decode()
+        return self._tsv
+
+    @tsv.setter
+    def tsv(self, v):
+        self._tsv = v
 
     @property
     def moves(self):
@@ -188,18 +203,71 @@ class Solver:
         return dd.astype(bool), iv.astype(bool)
 
 
+def _problems(regions):
+    n = len(regions)
+    keep = [Solver._problem(*r) for r in regions]
+    probs = (_lib.NwProblem * max(n, 1))()
+    for k, (a, lx, ly) in enumerate(keep):
+        q = probs[k]
+        q.aln_sign = a.ctypes.data
+        q.n_x, q.n_y = a.shape
+        q.len_x = lx.ctypes.data
+        q.len_y = ly.ctypes.data
+    return keep, probs
+
+
+def _unpack_many(solver, outs, n, o):
+    """All results of a regionfile run through nw_results_sizes / nw_results_gather: two native calls, then views."""
+    L = _lib.load()
+    if n == 0:
+        return []
+    if o.keep_ids:  # diagnostics path: per-result accessors
+        return [solver._unpack(C.c_void_p(outs[k]), o) for k in range(n)]
+    nt = np.empty(n, np.int64)
+    nm = np.empty(n, np.int64)
+    tl = np.empty(n, np.int64)
+    _lib.check(L.nw_results_sizes(outs, n, _p(nt), _p(nm), _p(tl)))
+    T, M, B = int(nt.sum()), int(nm.sum()), int(tl.sum())
+    scores = np.empty(T, np.float32)
+    n_moves = np.empty(T, np.int32)
+    move_off = np.empty(T, np.int64)
+    cost = np.empty(T, np.int64)
+    total = np.empty(T, np.int64)
+    idx = np.empty(T, np.int64)
+    moves3 = np.empty((M, 3), np.int32)
+    tsv = np.empty(max(B, 1), np.uint8)
+    stats = (_lib.NwStats * n)()
+    _lib.check(L.nw_results_gather(outs, n, _p(scores), _p(n_moves), _p(move_off), _p(cost), _p(total), _p(idx),
+                                   _p(moves3), _p(tsv), stats))
+    t1 = np.cumsum(nt).tolist()
+    m1 = np.cumsum(nm).tolist()
+    b1 = np.cumsum(tl).tolist()
+    tsv_b = tsv.tobytes()
+    res = []
+    t0 = m0 = b0 = 0
+    for k in range(n):
+        R = SolveResult()
+        te, me, be = t1[k], m1[k], b1[k]
+        R.scores = scores[t0:te]
+        R.n_moves = n_moves[t0:te]
+        R.move_off = move_off[t0:te]
+        R.cost_bp = cost[t0:te]
+        R.total_bp = total[t0:te]
+        R.index_id = idx[t0:te]
+        R.moves3 = moves3[m0:me]
+        R._tsv = tsv_b[b0:be]
+        R.stats = stats[k]
+        res.append(R)
+        t0, m0, b0 = te, me, be
+    return res
+
+
 def solve_batch(solvers, regions, **kw):
     """Regionfile mode: solve independent regions [(aln, len_x, len_y), ...] on several contexts concurrently
     (nw_solve_batch: one host thread + stream per context; contexts may share a GPU).  Returns SolveResults."""
     L = _lib.load()
     n = len(regions)
-    keep = [Solver._problem(*r) for r in regions]
-    probs = (_lib.NwProblem * max(n, 1))()
-    for k, (a, lx, ly) in enumerate(keep):
-        probs[k].aln_sign = a.ctypes.data
-        probs[k].n_x, probs[k].n_y = a.shape
-        probs[k].len_x = lx.ctypes.data
-        probs[k].len_y = ly.ctypes.data
+    keep, probs = _problems(regions)
     ctxs = (C.c_void_p * len(solvers))(*[s.h for s in solvers])
     outs = (C.c_void_p * max(n, 1))()
     rcs = (C.c_int32 * max(n, 1))()
@@ -208,8 +276,7 @@ def solve_batch(solvers, regions, **kw):
     res = []
     try:
         _lib.check(rc)
-        for k in range(n):
-            res.append(solvers[0]._unpack(C.c_void_p(outs[k]), o))
+        res = _unpack_many(solvers[0], outs, n, o)
     finally:
         for k in range(n):
             if outs[k]:
@@ -218,25 +285,25 @@ def solve_batch(solvers, regions, **kw):
 
 
 def solve_many(solver, regions, regions_per_pass=256, **kw):
-    """Regionfile mode on ONE context: `regions_per_pass` regions are searched together through one pipeline instance
-    (nw_solve_many), so every kernel launch is shared by all of them.  Returns one SolveResult per region."""
+    """Regionfile mode: `regions_per_pass` regions are searched together through one pipeline instance
+    (nw_solve_many), so every kernel launch is shared by all of them.  `solver` may be a list of Solvers: the passes
+    are then handed out to the contexts dynamically (nw_solve_many_ctxs).  Returns one SolveResult per region."""
     L = _lib.load()
+    solvers = list(solver) if isinstance(solver, (list, tuple)) else [solver]
+    solver = solvers[0]
     n = len(regions)
-    keep = [Solver._problem(*r) for r in regions]
-    probs = (_lib.NwProblem * max(n, 1))()
-    for k, (a, lx, ly) in enumerate(keep):
-        probs[k].aln_sign = a.ctypes.data
-        probs[k].n_x, probs[k].n_y = a.shape
-        probs[k].len_x = lx.ctypes.data
-        probs[k].len_y = ly.ctypes.data
+    keep, probs = _problems(regions)
     outs = (C.c_void_p * max(n, 1))()
     o = solver._opts(**kw)
-    rc = L.nw_solve_many(solver.h, probs, n, C.byref(o), int(regions_per_pass), outs)
+    if len(solvers) == 1:
+        rc = L.nw_solve_many(solver.h, probs, n, C.byref(o), int(regions_per_pass), outs)
+    else:  # passes handed out to several contexts: host work of one pass overlaps device work of another
+        hs = (C.c_void_p * len(solvers))(*[s.h for s in solvers])
+        rc = L.nw_solve_many_ctxs(hs, len(solvers), probs, n, C.byref(o), int(regions_per_pass), outs)
     res = []
     try:
         _lib.check(rc)
-        for k in range(n):
-            res.append(solver._unpack(C.c_void_p(outs[k]), o))
+        res = _unpack_many(solver, outs, n, o)
     finally:
         for k in range(n):
             if outs[k]:

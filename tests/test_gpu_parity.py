@@ -333,3 +333,34 @@ def test_solve_many_regions(solver, oracle, per_pass):
         for (aln, lx, ly), G in zip(regions, res):
             O = oracle.solve(aln, lx, ly, **kw)
             assert_search_equal(G, O)
+
+
+@pytest.mark.gpu
+def test_solve_many_several_contexts(solver, oracle):
+    """nw_solve_many_ctxs: the passes of a regionfile run handed out to three contexts; results as from one."""
+    import nahrwhals_b200 as nb
+    rng = np.random.default_rng(11)
+    regions = []
+    for k in range(29):
+        n_x = int(rng.integers(8, 50))
+        fams = [int(rng.integers(2, 4)) for _ in range(int(rng.integers(1, 4)))]
+        while sum(fams) > n_x:
+            fams.pop()
+        mat, lx, ly, _ = sdgrid(n_x, fams, seed=900 + k, chain_depth=int(rng.integers(0, 3)), len_tol=0.3)
+        regions.append((to_solver_inputs(mat), lx, ly))
+    kw = dict(maxdepth=3, maxdup=2, maxwidth=200, minreport=0.9, maxreport=50)
+    extra = [nb.Solver(0), nb.Solver(0)]
+    try:
+        res = nb.solve_many([solver] + extra, regions, regions_per_pass=4, keep_ids=True, **kw)
+        bulk = nb.solve_many([solver] + extra, regions, regions_per_pass=8, **kw)  # nw_results_gather path
+    finally:
+        for s in extra:
+            s.close()
+    assert len(res) == len(regions)
+    for (aln, lx, ly), G in zip(regions, res):
+        assert_search_equal(G, oracle.solve(aln, lx, ly, **kw))
+    for G, B in zip(res, bulk):
+        assert B.tsv == G.tsv and B.moves == G.moves
+        for f in ("scores", "n_moves", "move_off", "cost_bp", "total_bp", "index_id"):
+            assert np.array_equal(getattr(B, f), getattr(G, f)), f
+        assert B.generated == G.generated and B.scored == G.scored and B.stats.n_ids == G.stats.n_ids

@@ -70,13 +70,15 @@ def run_cpu(regions, threads):
     return len(regions) / dt, sum(scored), dt
 
 
-def run_many(regions, per_pass, device=0):
-    s = nb.Solver(device)
-    nb.solve_many(s, regions[:min(len(regions), per_pass)], regions_per_pass=per_pass, **FLAGS)  # warm-up
+def run_many(regions, per_pass, device=0, nctx=1):
+    ss = [nb.Solver(device) for _ in range(nctx)]
+    s = ss if nctx > 1 else ss[0]
+    nb.solve_many(s, regions[:min(len(regions), per_pass * nctx)], regions_per_pass=per_pass, **FLAGS)  # warm-up
     t0 = time.perf_counter()
     res = nb.solve_many(s, regions, regions_per_pass=per_pass, **FLAGS)
     dt = time.perf_counter() - t0
-    s.close()
+    for q in ss:
+        q.close()
     hs = [0.0, 0.0, 0.0]
     dev = 0.0
     for k in range(0, len(res), per_pass):
@@ -105,7 +107,7 @@ if __name__ == "__main__":
     for t in tl:
         r, sc, dt = run_gpu(regs, t)
         print("GPU, %d contexts: %.1f regions/s, %.3g candidates/s (%.2f s)" % (t, r, sc / dt, dt), flush=True)
-    for per in (16, 64, 256, 1024):
-        r, sc, dt = run_many(regs, per)
-        print("GPU, one pipeline, %d regions per pass: %.1f regions/s, %.3g candidates/s (%.2f s)" % (per, r, sc / dt, dt),
-              flush=True)
+    for per, nctx in ((16, 1), (64, 1), (256, 1), (1024, 1), (256, 2), (256, 3), (512, 2), (512, 3), (1024, 2)):
+        r, sc, dt = run_many(regs, per, nctx=nctx)
+        print("GPU, %d pipeline(s), %d regions per pass: %.1f regions/s, %.3g candidates/s (%.2f s)" % (
+            nctx, per, r, sc / dt, dt), flush=True)
