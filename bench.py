@@ -157,9 +157,12 @@ def run_reference(args, rank, world):
 
 def run_regions(args, rank, world, local):
     """BASELINE.json config 4: regionfile batch.  Every rank solves its own `--regions` synthetic SD-flanked regions
-    (20-120 blocks) with `--contexts` solver contexts on its GPU; no collective on the data path.  Metric: regions/s
-    (wall clock around the batch, max over ranks; many streams run concurrently so there is no single device
-    timeline).  --impl reference runs the CPU restatement on all host threads over a 10 x smaller sample."""
+    (20-120 blocks) through nw_solve_many_ctxs: `--regions-per-pass` regions are searched TOGETHER by one pipeline
+    instance (every launch of a BFS level covers all of them) and the passes are handed out to `--contexts` contexts
+    so that the host side of one pass overlaps the device side of another.  No collective on the data path.
+    Metric: regions/s (wall clock around the batch, host buffers in, reports out, max over ranks; several streams run
+    concurrently so there is no single device timeline).  --impl reference runs the CPU restatement on all host
+    threads over a 10 x smaller sample."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     from region_batch import FLAGS, make_regions, run_cpu
     cores = os.cpu_count() or 1
@@ -187,23 +190,25 @@ def run_regions(args, rank, world, local):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     regs = make_regions(args.regions, seed=rank)
     # contexts per GPU: each one is a host thread issuing launches; do not oversubscribe the host cores
-    nctx = max(2, min(args.contexts, (os.cpu_count() or 8) // max(world, 1)))
+    nctx = max(1, min(args.contexts, (os.cpu_count() or 8) // max(world, 1)))
+    per = max(1, args.regions_per_pass)
     solvers = [nb.Solver(local) for _ in range(nctx)]
-    nb.solve_batch(solvers, regs[:min(len(regs), 4 * nctx)], **FLAGS)  # warm-up: pools, band tables
+    nb.solve_many(solvers, regs[:min(len(regs), per * nctx)], regions_per_pass=per, **FLAGS)  # warm-up: pools
     sampler = ClockSampler(local)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     sampler.start()
     t0 = time.perf_counter()
-    res = nb.solve_batch(solvers, regs, **FLAGS)
+    res = nb.solve_many(solvers, regs, regions_per_pass=per, **FLAGS)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     clocks = sampler.stop()
     scored = sum(sum(R.scored) for R in res)
-    launches = sum(R.stats.kernel_launches for R in res)
-    h2d = sum(R.stats.h2d_bytes for R in res)
-    d2h = sum(R.stats.d2h_bytes for R in res)
+    firsts = res[::per]  # launch / byte counters are per pass (shared by the regions of the pass)
+    launches = sum(R.stats.kernel_launches for R in firsts)
+    h2d = sum(R.stats.h2d_bytes for R in firsts)
+    d2h = sum(R.stats.d2h_bytes for R in firsts)
     n = len(regs)
     if dist is not None:
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -216,8 +221,9 @@ def run_regions(args, rank, world, local):
                 ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32",
                 data="synthetic",
                 config=dict(workload="regionfile batch: %d synthetic SD-flanked regions per GPU (20-120 blocks, 2-6 "
-                                     "repeat families), -d 3 -u 2 -w 1000 -r 0.98 -R 1000, %d contexts per GPU; "
-                                     "regions shard per GPU, no collective" % (args.regions, nctx),
+                                     "repeat families), -d 3 -u 2 -w 1000 -r 0.98 -R 1000; %d regions per pass "
+                                     "searched together, %d contexts per GPU; regions shard per GPU, no collective"
+                                     % (args.regions, per, nctx),
                             candidates_scored_per_s=scored / dt, l2="not flushed (every region is new data)"),
                 clocks=clocks,
                 e2e=dict(value=n / dt, unit="regions/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
@@ -291,8 +297,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS) + ["regions"])
-    ap.add_argument("--regions", type=int, default=2000, help="regions per rank for --workload regions")
-    ap.add_argument("--contexts", type=int, default=8, help="solver contexts (streams) per GPU for --workload regions")
+    ap.add_argument("--regions", type=int, default=6000, help="regions per rank for --workload regions")
+    ap.add_argument("--contexts", type=int, default=3, help="solver contexts (streams) per GPU for --workload regions")
+    ap.add_argument("--regions-per-pass", type=int, default=512,
+                    help="regions searched together by one pipeline instance (--workload regions)")
     ap.add_argument("--mode", default="regions", choices=["regions", "frontier"],
                     help="N > 1: 'regions' = one independent search per GPU (default, weak scaling); 'frontier' = ONE "
                          "search sharded over the GPUs with a per-level all-gather (strong scaling, config 3)")

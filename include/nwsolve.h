@@ -157,6 +157,14 @@ int nw_solve_many(nw_ctx* ctx, const nw_problem* probs, int64_t n, const nw_opts
 int nw_solve_many_ctxs(nw_ctx** ctxs, int32_t n_ctx, const nw_problem* probs, int64_t n, const nw_opts* opts,
                        int32_t max_regions_per_pass, nw_result** outs);
 
+/* File form of a regionfile run: region k is read from inmat[k] / inlens[k] (as nw_solve_files), the parsed regions
+ * go through nw_solve_many_ctxs, and report k is written to outp[k] (complete or not at all).  rcs (may be NULL)
+ * receives one return code per region: a region that does not parse, is out of range or cannot be written fails
+ * alone -- if the batch as a whole is refused, its regions are solved one by one.  Returns the first error. */
+int nw_solve_files_many(nw_ctx** ctxs, int32_t n_ctx, const char* const* inmat, const char* const* inlens,
+                        const char* const* outp, int64_t n, const nw_opts* opts, int32_t max_regions_per_pass,
+                        int32_t* rcs);
+
 /* ---- one deep search sharded over `world` ranks (config 3 of BASELINE.json) -------------------------
  * One context per rank, the same problem and options on every rank.  The frontier is replicated; rank r expands the
  * parents whose frontier slot is congruent to r modulo world, dedups and scores its own candidates, and contributes

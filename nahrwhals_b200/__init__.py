@@ -4,5 +4,6 @@ Only the hot path of the reference (its Julia script solver.jl, called from R/ju
 `csrc/` holds the CUDA kernels and the C ABI (include/nwsolve.h); `solver.py` mirrors the reference's solver
 interface on top of that ABI.  There is no CPU fallback.
 """
-from .solver import Solver, SolveResult, read_problem, solve_batch, solve_many, main, MOVE_NAMES  # noqa: F401
+from .solver import (Solver, SolveResult, read_problem, solve_batch, solve_many, solve_files_many, main,  # noqa: F401
+                     MOVE_NAMES)  # noqa: F401
 from .sdgrid import sdgrid, to_solver_inputs, write_tsvs  # noqa: F401

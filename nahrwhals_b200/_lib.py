@@ -36,7 +36,7 @@ SYMBOLS = ["nw_default_opts", "nw_last_error", "nw_version", "nw_ctx_create", "n
            "nw_moveset", "nw_bench_peaks", "nw_read_problem", "nw_free", "nw_dist_begin", "nw_dist_expand",
            "nw_dist_pack", "nw_dist_merge", "nw_dist_n_ids", "nw_dist_report_begin", "nw_dist_report_mark",
            "nw_dist_report_edges", "nw_dist_report_pack", "nw_dist_finish", "nw_dist_abort", "nw_solve_batch", "nw_solve_many",
-           "nw_solve_many_ctxs", "nw_results_sizes", "nw_results_gather"]
+           "nw_solve_many_ctxs", "nw_solve_files_many", "nw_results_sizes", "nw_results_gather"]
 
 _lib = None
 
@@ -93,6 +93,7 @@ def load():
     L.nw_solve_many.argtypes = [vp, vp, i64, C.POINTER(NwOpts), i32, vp]
     L.nw_results_sizes.argtypes = [vp, i64, vp, vp, vp]
     L.nw_results_gather.argtypes = [vp, i64] + [vp] * 9
+    L.nw_solve_files_many.argtypes = [vp, i32, vp, vp, vp, i64, C.POINTER(NwOpts), i32, vp]
     L.nw_solve_many_ctxs.argtypes = [vp, i32, vp, i64, C.POINTER(NwOpts), i32, vp]
     _lib = L
     return L

@@ -2060,6 +2060,23 @@ int nw_solve(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const int64
   return NW_OK;
 }
 
+// the output appears complete or not at all: R/juliasolver.R:56-59 only checks that the file exists
+static void write_file_atomic(const char* outp, const std::string& data) {
+  const std::string tmp = std::string(outp) + ".tmp";
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) fail(NW_ERR_IO, std::string("cannot write ") + tmp);
+  const size_t w = fwrite(data.data(), 1, data.size(), f);
+  const int cl = fclose(f);
+  if (w != data.size() || cl != 0) {
+    remove(tmp.c_str());
+    fail(NW_ERR_IO, std::string("short write to ") + tmp);
+  }
+  if (rename(tmp.c_str(), outp) != 0) {
+    remove(tmp.c_str());
+    fail(NW_ERR_IO, std::string("cannot rename to ") + outp);
+  }
+}
+
 int nw_solve_files(nw_ctx* c, const char* inmat, const char* inlens, const char* outp, const nw_opts* o,
                    nw_stats* stats) {
   if (!c || !inmat || !inlens || !outp) {
@@ -2072,23 +2089,65 @@ int nw_solve_files(nw_ctx* c, const char* inmat, const char* inlens, const char*
     check_opts(o);
     ProblemHost P = read_problem(inmat, inlens);
     do_solve(c, P.aln.data(), P.n_x, P.n_y, P.len_x.data(), P.len_y.data(), o, &R);
-    const std::string tmp = std::string(outp) + ".tmp";
-    FILE* f = fopen(tmp.c_str(), "wb");
-    if (!f) fail(NW_ERR_IO, std::string("cannot write ") + tmp);
-    const size_t w = fwrite(R.tsv.data(), 1, R.tsv.size(), f);
-    const int cl = fclose(f);
-    if (w != R.tsv.size() || cl != 0) {
-      remove(tmp.c_str());
-      fail(NW_ERR_IO, std::string("short write to ") + tmp);
-    }
-    if (rename(tmp.c_str(), outp) != 0) {
-      remove(tmp.c_str());
-      fail(NW_ERR_IO, std::string("cannot rename to ") + outp);
-    }
+    write_file_atomic(outp, R.tsv);
   });
   if (rc != NW_OK) cudaGetLastError();
   if (rc == NW_OK && stats) *stats = R.stats;
   return rc;
+}
+
+int nw_solve_files_many(nw_ctx** ctxs, int32_t n_ctx, const char* const* inmat, const char* const* inlens,
+                        const char* const* outp, int64_t n, const nw_opts* opts, int32_t max_regions_per_pass,
+                        int32_t* rcs) {
+  if (!ctxs || n_ctx < 1 || !ctxs[0] || !inmat || !inlens || !outp || n < 0 || !opts) {
+    g_last_error = "null argument";
+    return NW_ERR_ARG;
+  }
+  std::vector<int32_t> rc_local((size_t)n, NW_OK);
+  int32_t* rc_of = rcs ? rcs : rc_local.data();
+  int first_rc = NW_OK;
+  std::string first_msg;
+  auto note = [&](int64_t k, int rc) {
+    rc_of[k] = rc;
+    if (rc != NW_OK && first_rc == NW_OK) {
+      first_rc = rc;
+      first_msg = "region " + std::to_string(k) + ": " + g_last_error;
+    }
+  };
+  // 1. parse every region; a region that does not parse is reported and left out
+  std::vector<ProblemHost> P((size_t)n);
+  std::vector<int64_t> live;
+  for (int64_t k = 0; k < n; ++k) {
+    const int rc = guard([&] {
+      if (!inmat[k] || !inlens[k] || !outp[k]) fail(NW_ERR_ARG, "null path");
+      P[k] = read_problem(inmat[k], inlens[k]);
+    });
+    note(k, rc);
+    if (rc == NW_OK) live.push_back(k);
+  }
+  // 2. forest search of the parsed regions; if the batch as a whole is refused (one region out of range, ...)
+  //    the regions are solved one by one so that only the offending ones fail
+  const int64_t m = (int64_t)live.size();
+  std::vector<nw_problem> probs((size_t)m);
+  for (int64_t q = 0; q < m; ++q) {
+    const ProblemHost& H = P[live[q]];
+    probs[q] = nw_problem{H.aln.data(), H.n_x, H.n_y, H.len_x.data(), H.len_y.data()};
+  }
+  std::vector<nw_result*> res((size_t)m, nullptr);
+  int rc_all = m ? nw_solve_many_ctxs(ctxs, n_ctx, probs.data(), m, opts, max_regions_per_pass, res.data()) : NW_OK;
+  if (rc_all != NW_OK)
+    for (int64_t q = 0; q < m; ++q) {
+      const nw_problem& B = probs[q];
+      note(live[q], nw_solve(ctxs[0], B.aln_sign, B.n_x, B.n_y, B.len_x, B.len_y, opts, &res[q]));
+    }
+  // 3. reports
+  for (int64_t q = 0; q < m; ++q) {
+    if (!res[q]) continue;
+    note(live[q], guard([&] { write_file_atomic(outp[live[q]], res[q]->tsv); }));
+    delete res[q];
+  }
+  if (first_rc != NW_OK) g_last_error = first_msg;
+  return first_rc;
 }
 
 int64_t nw_result_count(const nw_result* r) { return r ? (int64_t)r->t_score.size() : 0; }

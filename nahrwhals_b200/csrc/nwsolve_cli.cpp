@@ -1,5 +1,9 @@
 // nwsolve -- command-line twin of `julia solver.jl` (argument table: solver.jl:756-791 in the reference).
 //   nwsolve [-d D] [-u U] [-w W] [-O O] [-r r] [-R R] compressed_alignment compressed_lengths out_path
+//   nwsolve [flags] --batch list.tsv [--contexts K] [--regions-per-pass N]
+// --batch is the regionfile / whole-genome form (R/nahrwhals.R:171-215, :240-290 run one solver process per region):
+// every line of list.tsv is "compressed_alignment<TAB>compressed_lengths<TAB>out_path"; all regions are searched by
+// one process through nw_solve_files_many (forest search).  A region that fails leaves no out_path and a message.
 // Exit status 0 and out_path written on success; non-zero, a message on stderr and NO out_path otherwise
 // (R/juliasolver.R:56-59 treats a missing file as failure).  -O/--maxoffset is accepted and ignored, as in the
 // reference where it lands in an unused positional of slow_score (solver.jl:329).
@@ -15,7 +19,72 @@ static void usage() {
   fprintf(stderr,
           "usage: nwsolve [--maxdepth|-d D] [--maxdup|-u U] [--maxwidth|-w W] [--maxoffset|-O O]\n"
           "               [--minreport|-r r] [--maxreport|-R R] [--device N] [--stats]\n"
-          "               compressed_alignment compressed_lengths out_path\n");
+          "               compressed_alignment compressed_lengths out_path\n"
+          "       nwsolve [flags] --batch list.tsv [--contexts K] [--regions-per-pass N]\n"
+          "               (list.tsv: compressed_alignment<TAB>compressed_lengths<TAB>out_path per line)\n");
+}
+
+static int run_batch(const char* list, const nw_opts& o, int device, int contexts, int per_pass, bool stats) {
+  FILE* f = fopen(list, "rb");
+  if (!f) {
+    fprintf(stderr, "nwsolve: cannot open %s\n", list);
+    return 1;
+  }
+  std::vector<std::string> a, b, c;
+  std::string line;
+  int ch;
+  auto flush = [&]() -> bool {
+    while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
+    if (line.empty()) return true;
+    const size_t t1 = line.find('\t'), t2 = t1 == std::string::npos ? t1 : line.find('\t', t1 + 1);
+    if (t2 == std::string::npos || line.find('\t', t2 + 1) != std::string::npos) return false;
+    a.push_back(line.substr(0, t1));
+    b.push_back(line.substr(t1 + 1, t2 - t1 - 1));
+    c.push_back(line.substr(t2 + 1));
+    line.clear();
+    return true;
+  };
+  bool ok = true;
+  while (ok && (ch = fgetc(f)) != EOF) {
+    if (ch == '\n') ok = flush();
+    else line.push_back((char)ch);
+  }
+  if (ok) ok = flush();
+  fclose(f);
+  if (!ok) {
+    fprintf(stderr, "nwsolve: %s: every line must hold three tab-separated paths\n", list);
+    return 2;
+  }
+  const int64_t n = (int64_t)a.size();
+  std::vector<nw_ctx*> ctxs;
+  for (int k = 0; k < contexts; ++k) {
+    nw_ctx* x = nullptr;
+    if (nw_ctx_create(device, &x) != NW_OK) {
+      fprintf(stderr, "nwsolve: %s\n", nw_last_error());
+      for (nw_ctx* y : ctxs) nw_ctx_destroy(y);
+      return 1;
+    }
+    ctxs.push_back(x);
+  }
+  std::vector<const char*> pa(n), pb(n), pc(n);
+  for (int64_t k = 0; k < n; ++k) {
+    pa[k] = a[k].c_str();
+    pb[k] = b[k].c_str();
+    pc[k] = c[k].c_str();
+  }
+  std::vector<int32_t> rcs(n, 0);
+  const int rc = nw_solve_files_many(ctxs.data(), (int32_t)ctxs.size(), pa.data(), pb.data(), pc.data(), n, &o, per_pass,
+                                     rcs.data());
+  int64_t bad = 0;
+  for (int64_t k = 0; k < n; ++k)
+    if (rcs[k] != NW_OK) {
+      ++bad;
+      fprintf(stderr, "nwsolve: region %lld (%s) failed with code %d\n", (long long)k, pa[k], rcs[k]);
+    }
+  if (rc != NW_OK) fprintf(stderr, "nwsolve: %s\n", nw_last_error());
+  if (stats) fprintf(stderr, "nwsolve: %lld regions, %lld failed\n", (long long)n, (long long)bad);
+  for (nw_ctx* y : ctxs) nw_ctx_destroy(y);
+  return bad ? 1 : 0;
 }
 
 int main(int argc, char** argv) {
@@ -23,6 +92,8 @@ int main(int argc, char** argv) {
   nw_default_opts(&o);
   int device = -1;
   bool stats = false;
+  const char* batch = nullptr;
+  int contexts = 3, per_pass = 512;
   std::vector<const char*> pos;
   for (int a = 1; a < argc; ++a) {
     const std::string s = argv[a];
@@ -41,6 +112,9 @@ int main(int argc, char** argv) {
     else if (s == "-R" || s == "--maxreport") o.maxreport = (int64_t)strtod(val("-R"), nullptr);
     else if (s == "--device") device = atoi(val("--device"));
     else if (s == "--stats") stats = true;
+    else if (s == "--batch") batch = val("--batch");
+    else if (s == "--contexts") contexts = atoi(val("--contexts"));
+    else if (s == "--regions-per-pass") per_pass = atoi(val("--regions-per-pass"));
     else if (s == "-h" || s == "--help") {
       usage();
       return 0;
@@ -49,6 +123,13 @@ int main(int argc, char** argv) {
       usage();
       return 2;
     } else pos.push_back(argv[a]);
+  }
+  if (batch) {
+    if (!pos.empty() || contexts < 1 || contexts > 64) {
+      usage();
+      return 2;
+    }
+    return run_batch(batch, o, device, contexts, per_pass, stats);
   }
   if (pos.size() != 3) {
     usage();

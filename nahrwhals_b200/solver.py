@@ -311,6 +311,20 @@ def solve_many(solver, regions, regions_per_pass=256, **kw):
     return res
 
 
+def solve_files_many(solvers, triples, regions_per_pass=512, **kw):
+    """Regionfile run from files: triples = [(inmat, inlens, out), ...] -> list of per-region return codes
+    (nw_solve_files_many: regions that fail leave no output file; the others are written)."""
+    L = _lib.load()
+    solvers = list(solvers) if isinstance(solvers, (list, tuple)) else [solvers]
+    n = len(triples)
+    cols = [(C.c_char_p * max(n, 1))(*[str(t[q]).encode() for t in triples]) for q in range(3)]
+    hs = (C.c_void_p * len(solvers))(*[s.h for s in solvers])
+    rcs = (C.c_int32 * max(n, 1))()
+    o = solvers[0]._opts(**kw)
+    L.nw_solve_files_many(hs, len(solvers), cols[0], cols[1], cols[2], n, C.byref(o), int(regions_per_pass), rcs)
+    return [int(rcs[k]) for k in range(n)]
+
+
 def read_problem(inmat, inlens):
     """read_tsv + read_length_tsv (solver.jl:101-107, :121-138) -> (aln int8 [n_x,n_y], len_x, len_y)."""
     L = _lib.load()

@@ -364,3 +364,49 @@ def test_solve_many_several_contexts(solver, oracle):
         for f in ("scores", "n_moves", "move_off", "cost_bp", "total_bp", "index_id"):
             assert np.array_equal(getattr(B, f), getattr(G, f)), f
         assert B.generated == G.generated and B.scored == G.scored and B.stats.n_ids == G.stats.n_ids
+
+
+@pytest.mark.gpu
+def test_files_many_and_cli_batch(solver, oracle, tmp_path):
+    """Regionfile run from files (nw_solve_files_many, `nwsolve --batch`): every report byte-identical to the oracle's
+    writer; a region whose gridmatrix is missing / malformed fails alone and leaves no output file."""
+    import nahrwhals_b200 as nb
+    rng = np.random.default_rng(3)
+    kw = dict(maxdepth=3, maxdup=2, maxwidth=300, minreport=0.95, maxreport=100)
+    triples, want = [], []
+    for k in range(9):
+        n_x = int(rng.integers(8, 40))
+        mat, lx, ly, _ = sdgrid(n_x, [3, 2], seed=40 + k, chain_depth=int(rng.integers(0, 3)), len_tol=0.3)
+        a, b, c = (str(tmp_path / ("r%d_%s.tsv" % (k, s))) for s in ("mat", "lens", "out"))
+        write_tsvs(mat, lx, ly, a, b)
+        triples.append((a, b, c))
+        ref = str(tmp_path / ("r%d_ref.tsv" % k))
+        assert oracle.solve_files(a, b, ref, **kw) == 0
+        want.append(open(ref, "rb").read())
+    bad = len(triples)
+    triples.append((str(tmp_path / "missing.tsv"), triples[0][1], str(tmp_path / "bad_out.tsv")))
+    with open(tmp_path / "ragged.tsv", "w") as f:
+        f.write("1000\t0\n0\n")
+    triples.append((str(tmp_path / "ragged.tsv"), triples[0][1], str(tmp_path / "bad_out2.tsv")))
+    rcs = nb.solve_files_many([solver], triples, regions_per_pass=4, **kw)
+    assert all(rc == 0 for rc in rcs[:bad]) and rcs[bad] < 0 and rcs[bad + 1] < 0
+    for (a, b, c), w in zip(triples[:bad], want):
+        assert open(c, "rb").read() == w
+        os.remove(c)
+    assert not os.path.exists(triples[bad][2]) and not os.path.exists(triples[bad + 1][2])
+    # the same through the command line
+    lst = tmp_path / "list.tsv"
+    with open(lst, "w") as f:
+        for t in triples:
+            f.write("\t".join(t) + "\n")
+    cli = os.path.join(ROOT, "nahrwhals_b200", "csrc", "nwsolve")
+    rc = subprocess.call([cli, "-d", "3", "-u", "2", "-w", "300", "-r", "0.95", "-R", "100", "--batch", str(lst),
+                          "--contexts", "2", "--regions-per-pass", "3"], stderr=subprocess.DEVNULL)
+    assert rc == 1  # two regions failed
+    for (a, b, c), w in zip(triples[:bad], want):
+        assert open(c, "rb").read() == w
+    assert not os.path.exists(triples[bad][2]) and not os.path.exists(triples[bad + 1][2])
+    with open(lst, "w") as f:
+        for t in triples[:bad]:
+            f.write("\t".join(t) + "\n")
+    assert subprocess.call([cli, "-d", "3", "-u", "2", "-w", "300", "-r", "0.95", "-R", "100", "--batch", str(lst)]) == 0
