@@ -51,11 +51,20 @@ __device__ __forceinline__ uint32_t table_insert(uint64_t* T, uint64_t mask, uin
   uint64_t s = fp_slot_hash(k0, k1) & mask;
   while (true) {
     uint64_t* e = T + s * TBL_WORDS;
+    // key and position of the slot arrive with one 32-byte sector (two loads in flight together)
     const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(e));
+    const uint64_t v = __ldcg(reinterpret_cast<const unsigned long long*>(e + 2));
     uint64_t o0 = cur.x, o1 = cur.y;
-    if (o0 == TBL_EMPTY && o1 == TBL_EMPTY) cas128(e, TBL_EMPTY, TBL_EMPTY, k0, k1, o0, o1);
-    if ((o0 == TBL_EMPTY && o1 == TBL_EMPTY) || (o0 == k0 && o1 == k1)) {
-      const uint64_t v = __ldcg(reinterpret_cast<const unsigned long long*>(e + 2));
+    if (o0 == TBL_EMPTY && o1 == TBL_EMPTY) {
+      cas128(e, TBL_EMPTY, TBL_EMPTY, k0, k1, o0, o1);
+      if ((o0 == TBL_EMPTY && o1 == TBL_EMPTY) || (o0 == k0 && o1 == k1)) {
+        // claimed now (by this thread or, a moment ago, by a sibling with the same key): the position read above
+        // is stale, so the minimum is sent unconditionally -- result unused, i.e. a fire-and-forget reduction
+        atomicMin(reinterpret_cast<unsigned long long*>(e + 2), (unsigned long long)gpos);
+        return (uint32_t)s;
+      }
+    } else if (o0 == k0 && o1 == k1) {
+      // a key never changes and a position only decreases: no atomic when the stored position is already smaller
       if (v > gpos) atomicMin(reinterpret_cast<unsigned long long*>(e + 2), (unsigned long long)gpos);
       return (uint32_t)s;
     }
@@ -546,11 +555,14 @@ __global__ void k_assign(AssignArgs A) {
   const bool in = pos < A.G;
   int key = -1;  // histogram key (child length, sub-counter) of lanes that need a DP; -1 = none
   if (in) {
-    if (A.is_new[pos]) {
-      const uint32_t r = A.newrank[pos];
+    // the four per-candidate records are independent: issue their loads together, then the dependent ones
+    const uint32_t fresh = A.is_new[pos];
+    const uint32_t r = A.newrank[pos];
+    const uint32_t own = A.owner[pos];
+    const uint64_t d = A.desc[pos];
+    if (fresh) {
       if (!A.skip_ids) A.cand_id[pos] = A.id_base + (int32_t)r;
       A.newlist[r] = pos;
-      const uint64_t d = A.desc[pos];
       const uint32_t ps = desc_parent(d);
       const int len = child_len(A.front_len[ps], desc_kind(d), desc_i(d), desc_j(d));
       const int rid = A.front_rid ? (int)A.front_rid[ps] : 0;
@@ -564,7 +576,7 @@ __global__ void k_assign(AssignArgs A) {
         key = bucket_key(rid, A.lcap, len, r);
       }
     } else if (!A.skip_ids) {
-      const uint32_t g = A.owner[pos];
+      const uint32_t g = own;
       A.cand_id[pos] = g >= A.gbase ? A.id_base + (int32_t)A.newrank[g - A.gbase] : owner_id(A.LT, g);
     }
   }
@@ -584,10 +596,22 @@ int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* is_new, uint32_t* 
   return 1;
 }
 
-// scatter the DP-needing new candidates into per-length buckets (each padded to a multiple of 32 lanes)
-__global__ void k_bucket_scatter(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap,
-                                 uint32_t n_new, int force, const uint32_t* bstart, uint32_t* cursor, uint32_t* work) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+// scatter the DP-needing new candidates into per-(region, length) buckets (each padded to a multiple of 32 lanes).
+// Positions inside a bucket come from a cursor per bucket; the few hot cursors are hit once per (CTA, bucket):
+// warps aggregate with match_any, the CTA aggregates in a small shared-memory table keyed by bucket.
+constexpr int SCAT_SLOTS = 64;
+__global__ void __launch_bounds__(1024) k_bucket_scatter(const uint16_t* new_len, const uint16_t* new_rid,
+                                                         const RegionDev* regions, int lcap, uint32_t n_new, int force,
+                                                         const uint32_t* bstart, uint32_t* cursor, uint32_t* work) {
+  __shared__ int s_key[SCAT_SLOTS];
+  __shared__ uint32_t s_cnt[SCAT_SLOTS], s_base[SCAT_SLOTS];
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < SCAT_SLOTS) {
+    s_key[tid] = -1;
+    s_cnt[tid] = 0;
+  }
+  __syncthreads();
+  const uint32_t r = blockIdx.x * blockDim.x + tid;
   int key = -1;
   if (r < n_new) {
     const int len = new_len[r], rid = new_rid[r];
@@ -595,19 +619,34 @@ __global__ void k_bucket_scatter(const uint16_t* new_len, const uint16_t* new_ri
   }
   const uint32_t peers = __match_any_sync(0xffffffffu, key);
   const int leader = __ffs(peers) - 1;
-  uint32_t base = 0;
-  if (key >= 0 && (int)(threadIdx.x & 31) == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (key >= 0) {
-    const uint32_t mine = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
-    work[bstart[key] + base + mine] = r;
+  const uint32_t mine = __popc(peers & ((1u << lane) - 1u));
+  int slot = -1;
+  uint32_t wbase = 0;
+  if (key >= 0 && lane == leader) {
+    int h = (int)(((uint32_t)key * 2654435761u) >> 26);  // 6 bits
+    for (int probe = 0; probe < SCAT_SLOTS; ++probe) {
+      const int old = atomicCAS(&s_key[h], -1, key);
+      if (old == -1 || old == key) {
+        slot = h;
+        break;
+      }
+      h = (h + 1) & (SCAT_SLOTS - 1);
+    }
+    if (slot >= 0) wbase = atomicAdd(&s_cnt[slot], (uint32_t)__popc(peers));
   }
+  __syncthreads();
+  if (tid < SCAT_SLOTS && s_key[tid] >= 0) s_base[tid] = atomicAdd(&cursor[s_key[tid]], s_cnt[tid]);
+  __syncthreads();
+  // more distinct buckets in this CTA than table slots: that warp goes to the global cursor directly
+  if (key >= 0 && lane == leader) wbase = slot >= 0 ? s_base[slot] + wbase : atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+  wbase = __shfl_sync(0xffffffffu, wbase, leader);
+  if (key >= 0) work[bstart[key] + wbase + mine] = r;
 }
 int launch_bucket_scatter(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap,
                           uint32_t n_new, int force, const uint32_t* bstart, uint32_t* cursor, uint32_t* work,
                           cudaStream_t st) {
   if (n_new == 0) return 0;
-  k_bucket_scatter<<<(n_new + 255) / 256, 256, 0, st>>>(new_len, new_rid, regions, lcap, n_new, force, bstart, cursor, work);
+  k_bucket_scatter<<<(n_new + 1023) / 1024, 1024, 0, st>>>(new_len, new_rid, regions, lcap, n_new, force, bstart, cursor, work);
   return 1;
 }
 

@@ -410,3 +410,62 @@ def test_files_many_and_cli_batch(solver, oracle, tmp_path):
         for t in triples[:bad]:
             f.write("\t".join(t) + "\n")
     assert subprocess.call([cli, "-d", "3", "-u", "2", "-w", "300", "-r", "0.95", "-R", "100", "--batch", str(lst)]) == 0
+
+
+@pytest.mark.gpu
+def test_full_size_properties_bench_workload(solver, oracle):
+    """BASELINE config 2 at full size (the bench workload: 17.5 M generated / 10.8 M scored candidates), where the
+    oracle would need minutes: size-independent properties instead.
+      * two independent DP kernels (register-resident savings form vs the literal cost-form transcription) agree on
+        the cost / total / score of every one of the 10.8 M ids, and on every provenance edge;
+      * the fingerprint dedup of this very search is exact (every merged candidate compared element-wise);
+      * both expansion kernels (occurrence masks vs pair testing) generate the same candidates in the same order;
+      * the search is deterministic and sharding it over two emulated ranks changes nothing;
+      * round trip: every reported trajectory, replayed move by move on the host, yields an index whose score by the
+        CPU oracle equals the reported score and whose DP cost equals the reported cost."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from bench import make_workload
+    from oracle.nw_oracle_py import apply_move
+    from nahrwhals_b200.distributed import solve_sharded_emulated
+    import nahrwhals_b200 as nb
+    aln, lx, ly, flags, _ = make_workload("s64", 1)
+    A = solver.solve(aln, lx, ly, keep_ids=True, verify_dedup=True, **flags)
+    assert sum(A.generated) > 1.5e7 and sum(A.scored) > 1.0e7  # really the full-size workload
+    assert A.stats.n_ids == 1 + sum(A.scored)
+    B = solver.solve(aln, lx, ly, keep_ids=True, generic_dp=True, **flags)
+    assert A.generated == B.generated and A.scored == B.scored and A.cells == B.cells
+    for f in ("score", "cost_bp", "total_bp", "level"):
+        assert np.array_equal(A.ids[f], B.ids[f]), f
+    for f in ("child", "parent", "moves"):
+        assert np.array_equal(A.edges[f], B.edges[f]), f
+    assert A.tsv == B.tsv
+    del B
+    C = solver.solve(aln, lx, ly, keep_ids=True, pair_expand=True, **flags)
+    assert C.generated == A.generated and C.scored == A.scored and C.tsv == A.tsv
+    for f in ("child", "parent", "moves"):
+        assert np.array_equal(A.edges[f], C.edges[f]), f
+    assert np.array_equal(A.ids["cost_bp"], C.ids["cost_bp"])
+    del C
+    extra = nb.Solver(0)
+    try:
+        S = solve_sharded_emulated([solver, extra], aln, lx, ly, **flags)
+    finally:
+        extra.close()
+    for R in S:
+        assert R.tsv == A.tsv and R.generated == A.generated and R.scored == A.scored
+    # round trip of the report through the CPU oracle
+    n_x = aln.shape[0]
+    root = tuple(range(1, n_x + 1))
+    seqs = []
+    for mv in A.moves:
+        d = root
+        for kind, p, q in mv:
+            d = apply_move(kind, d, p, q)
+        seqs.append(list(d))
+    assert len(seqs) == len(A.scores) and len(seqs) >= 100
+    osc, ocost, ototal, _ = oracle.score_batch(aln, lx, ly, seqs)
+    assert np.array_equal(osc.astype(np.float32), A.scores)
+    ocost_i = np.where(np.isnan(ocost), -1.0, ocost).astype(np.int64)
+    assert np.array_equal(ocost_i, A.cost_bp) and np.array_equal(ototal.astype(np.int64), A.total_bp)
+    assert A.tsv.count("\n") == len(seqs) and np.all(np.diff(A.scores) <= 0)  # report sorted by score desc
