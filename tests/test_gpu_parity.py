@@ -469,3 +469,30 @@ def test_full_size_properties_bench_workload(solver, oracle):
     ocost_i = np.where(np.isnan(ocost), -1.0, ocost).astype(np.int64)
     assert np.array_equal(ocost_i, A.cost_bp) and np.array_equal(ototal.astype(np.int64), A.total_bp)
     assert A.tsv.count("\n") == len(seqs) and np.all(np.diff(A.scores) <= 0)  # report sorted by score desc
+
+
+@pytest.mark.gpu
+def test_forest_equals_single_searches_at_bench_shapes(solver):
+    """BASELINE config 4 shapes (20-120 blocks, SD-flanked), too many for the oracle: the forest search
+    (256 regions per pass, two contexts) must reproduce nw_solve region by region -- report bytes, trajectory arrays,
+    per-level generated / scored / cell counts, id counts and best scores."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from region_batch import FLAGS, make_regions
+    import nahrwhals_b200 as nb
+    regs = make_regions(300, seed=5)
+    extra = nb.Solver(0)
+    try:
+        many = nb.solve_many([solver, extra], regs, regions_per_pass=256, **FLAGS)
+    finally:
+        extra.close()
+    assert len(many) == len(regs)
+    for k, (aln, lx, ly) in enumerate(regs):
+        one = solver.solve(aln, lx, ly, **FLAGS)
+        M = many[k]
+        assert M.tsv == one.tsv, k
+        assert M.generated == one.generated and M.scored == one.scored and M.cells == one.cells, k
+        assert M.stats.n_ids == one.stats.n_ids and M.stats.best == one.stats.best, k
+        for f in ("scores", "n_moves", "cost_bp", "total_bp", "index_id"):
+            assert np.array_equal(getattr(M, f), getattr(one, f)), (k, f)
+        assert np.array_equal(M.moves3, one.moves3), k
