@@ -481,7 +481,16 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
   if (cells_out) std::fill(cells_out, cells_out + R, (int64_t)0);
   // non-empty bins -> host
   std::vector<BinRec> bins;
-  {
+  if (nb <= BINS_SMALL_LIMIT) {  // single searches: one kernel, one copy, one sync
+    BinRec* brec = (BinRec*)c->binrec.ensure((size_t)(nb + 1) * sizeof(BinRec), true);
+    c->launches += launch_bins_small(hist_dev, nb, brec, st);
+    BinRec* pin = reinterpret_cast<BinRec*>(static_cast<unsigned char*>(c->pinned) + 4096);
+    d2h(c, pin, brec, (size_t)(nb + 1) * sizeof(BinRec));
+    CK(spin_sync(st));
+    const uint32_t n = pin[0].bin;
+    if (!n) return;
+    bins.assign(pin + 1, pin + 1 + n);
+  } else {
     uint32_t* bflag = (uint32_t*)c->binflag.ensure((size_t)nb * 4, true);
     uint32_t* brank = (uint32_t*)c->binrank.ensure((size_t)nb * 4, true);
     uint32_t* bsumn = (uint32_t*)c->binsum.ensure((size_t)nb * 4, true);
@@ -571,7 +580,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
   c->launches += launch_bucket_scatter(c->new_len.as<uint16_t>(), new_rid_dev, c->d_regions.as<RegionDev>(), lcap, Lv.n_new,
                                        force, c->bstart.as<uint32_t>(), c->cursor.as<uint32_t>(), c->work.as<uint32_t>(),
                                        st);
-  CK(spin_sync(st));  // bstart / cta_rid host vectors go out of scope
+  // no sync: cudaMemcpyAsync from pageable memory has consumed the host vectors (bins, cta_rid) when it returns
   if (dbg)
     fprintf(stderr, "[nw scoring] buckets %zu, work %u for %u new, ranges %zu: bucket loop %.2f ms, bands %.2f, layout %.2f, scatter %.2f\n",
             bk.size(), n_work, Lv.n_new, ranges.size(), tms(T0, T1), tms(T1, T2), tms(T2, T3), tms(T3, tnow()));
@@ -1005,7 +1014,7 @@ struct Search {
       }
       h2d(c, seg, pack.data(), pack.size() * 4);
       c->launches += launch_take_sorted(keys, nvalid, seg, seg + R, seg + 2 * (size_t)R, sel, s);
-      CK(spin_sync(s));  // pack goes out of scope
+      // no sync: the pageable source of the H2D above is consumed when cudaMemcpyAsync returns
     }
     if (P2 == 0) return;
     int maxlen = std::max(level_maxlen, c->nx_max);

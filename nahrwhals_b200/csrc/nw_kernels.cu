@@ -687,6 +687,52 @@ __global__ void k_bucket_fill(const BinRec* ent, uint32_t n, const uint32_t* his
     at += hist[k0 + sb];
   }
 }
+// small histograms (single search: one region): flags + scan + compaction in ONE block; out[0] = {count, 0},
+// records from out[1] on, in (region, length) order
+__global__ void __launch_bounds__(1024) k_bins_small(const uint32_t* hist, uint32_t nb, BinRec* out) {
+  __shared__ uint32_t s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t n[8];
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const uint32_t i = (uint32_t)tid * 8 + q;
+    n[q] = 0;
+    if (i < nb) {
+      const uint4* h = reinterpret_cast<const uint4*>(hist + (size_t)i * NSUB);
+      const uint4 a = h[0], b = h[1];
+      n[q] = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    }
+    cnt += n[q] ? 1u : 0u;
+  }
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += v;
+    }
+    s_warp[lane] = wi - w;  // exclusive
+    if (lane == 31) out[0] = BinRec{wi, 0u};
+  }
+  __syncthreads();
+  uint32_t at = s_warp[warp] + incl - cnt;
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (n[q]) out[1 + at++] = BinRec{(uint32_t)tid * 8 + q, n[q]};
+}
+int launch_bins_small(const uint32_t* hist, uint32_t nb, BinRec* out, cudaStream_t st) {
+  k_bins_small<<<1, 1024, 0, st>>>(hist, nb, out);
+  return 1;
+}
 int launch_len_hist(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap, uint32_t n,
                     int force, uint32_t* hist, cudaStream_t st) {
   if (!n) return 0;

@@ -22,6 +22,8 @@ int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t
                        unsigned int* mismatches, cudaStream_t st);
 int launch_len_hist(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap, uint32_t n,
                     int force, uint32_t* hist, cudaStream_t st);
+constexpr uint32_t BINS_SMALL_LIMIT = 8192;  // launch_bins_small handles up to this many (region, length) bins
+int launch_bins_small(const uint32_t* hist, uint32_t nb, BinRec* out /* 1 + nb records */, cudaStream_t st);
 int launch_bin_flags(const uint32_t* hist, uint32_t nb, uint32_t* flag, uint32_t* nsum, cudaStream_t st);
 int launch_bin_compact(const uint32_t* flag, const uint32_t* rank, const uint32_t* nsum, uint32_t nb, BinRec* out,
                        cudaStream_t st);
