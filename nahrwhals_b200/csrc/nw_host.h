@@ -30,7 +30,7 @@ struct RegionHost {
   int n_x = 0, n_y = 0, NYP = 0, PW = 0, PWS = 0, MW = 0;
   int64_t gcd = 1;
   int64_t sum_rt = 0, sum_up = 0;  // units
-  std::vector<unsigned char> ctx;  // [planes | upx | rt_rev x 4 shifted copies]
+  std::vector<unsigned char> ctx;  // [planes | upx (per plane row: index x*2+strand) | rt_rev x 4 shifted copies]
   uint32_t off_upx = 0, off_rtrev = 0;
   int rt_copy_stride = 0;
   std::vector<int32_t> rt, cumr;  // 1-based
@@ -70,7 +70,7 @@ inline RegionHost build_region(const int8_t* aln, int n_x, int n_y, const int64_
   R.PWS = R.PW + WINDOW_MAX / 32 + 1;
   R.MW = (n_x + 1 + 31) / 32;
   const size_t planes_bytes = (((size_t)(n_x + 1) * 2 * R.PWS * 4) + 15) & ~(size_t)15;
-  const size_t upx_bytes = (((size_t)(n_x + 1) * 4) + 15) & ~(size_t)15;
+  const size_t upx_bytes = (((size_t)(n_x + 1) * 2 * 4) + 15) & ~(size_t)15;
   R.rt_copy_stride = (R.NYP + RT_PAD + 3) & ~3;
   const size_t rt_bytes = (size_t)R.rt_copy_stride * 4 * 4;
   R.off_upx = (uint32_t)planes_bytes;
@@ -85,7 +85,7 @@ inline RegionHost build_region(const int8_t* aln, int n_x, int n_y, const int64_
       pl[(size_t)(x * 2 + (a < 0 ? 1 : 0)) * R.PWS + (r >> 5)] |= 1u << (r & 31);
     }
   int32_t* upx = reinterpret_cast<int32_t*>(R.ctx.data() + R.off_upx);
-  for (int x = 1; x <= n_x; ++x) upx[x] = (int32_t)(len_x[x - 1] / g);
+  for (int x = 1; x <= n_x; ++x) upx[2 * x] = upx[2 * x + 1] = (int32_t)(len_x[x - 1] / g);  // same index as the plane row
   int32_t* rr = reinterpret_cast<int32_t*>(R.ctx.data() + R.off_rtrev);
   R.rt.assign(n_y + 1, 0);
   R.cumr.assign(n_y + 1, 0);

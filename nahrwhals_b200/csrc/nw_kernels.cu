@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(128) k_score_generic(ScoreArgs A) {
       const int c = child_elem(seq, kind, p, q, i);
       const int x = c < 0 ? -c : c;
       const uint32_t* pl = planes + (size_t)(x * 2 + (c < 0 ? 1 : 0)) * R.PWS;
-      const int up = upx[x];
+      const int up = upx[2 * x];
       const int a = ab[i * 2], b = ab[i * 2 + 1];
       int32_t* rc = row0 + (size_t)cur * rstride;
       const int32_t* rp = row0 + (size_t)(cur ^ 1) * rstride;

@@ -11,15 +11,18 @@
 namespace nw {
 
 // Shared-memory layout per CTA (128 threads = 4 warps):
-//   [ region context (TMA bulk copy) | child rows int16 [Lmax][128] | band rows (per warp) uint32 [4][Lmax+1][1+NWORD] ]
-// The child's block ids are materialised once through the index map into a lane-interleaved smem tile so the row
+//   [ region context (TMA bulk copy) | child rows uint16 [Lmax][128] | band rows (per warp) uint32 [4][Lmax+1][3+NWORD] ]
+// The child's blocks are materialised once through the index map into a lane-interleaved smem tile -- stored as the
+// plane-row index (block * 2 + strand) that addresses both the match bit-plane and the up cost -- so the row
 // loop never waits on global memory; the warp's band table (one length per warp) is copied next to it.
 template <int W>
 __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
   constexpr int NWORD = (W + 31) / 32;
   constexpr bool RTREG = (W <= 64);  // rt window in registers (LDS.128) vs predicated scalar LDS per cell
   constexpr int RTW = RTREG ? W : 4;
-  constexpr int BROW = 1 + NWORD;    // uint32 words per band row: meta (r0 | sb << 16 | extra << 24), masks
+  // uint32 words per band row, everything the row loop needs ready-made (no unpacking on the ALU pipe):
+  //   r0 (window start in reversed columns), byte offset of the 16-B aligned rt window, sb | extra << 8, masks
+  constexpr int BROW = 3 + NWORD;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -35,7 +38,7 @@ __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
   const int32_t* upx = reinterpret_cast<const int32_t*>(smem + R.off_upx);
   const int32_t* rtrev = reinterpret_cast<const int32_t*>(smem + R.off_rtrev);
   const int Lmax = A.lmax;
-  int16_t* crow = reinterpret_cast<int16_t*>(smem + A.ctx_max);
+  uint16_t* crow = reinterpret_cast<uint16_t*>(smem + A.ctx_max);
   uint32_t* brow = reinterpret_cast<uint32_t*>(smem + A.ctx_max + (size_t)Lmax * 256) + (size_t)warp * (Lmax + 1) * BROW;
 
   const uint32_t w = blockIdx.x * 128u + tid;
@@ -66,7 +69,8 @@ __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
       const bool flip = kind == KIND_INV && t > lo && t < hi;
       src = flip ? p + q - t : src;
       const int v = seq[src - 1];
-      crow[(size_t)(t - 1) * 128 + tid] = (int16_t)(flip ? -v : v);
+      const int a = v < 0 ? -v : v;
+      crow[(size_t)(t - 1) * 128 + tid] = (uint16_t)(a * 2 + ((v < 0) != flip ? 1 : 0));
     }
   }
   // ---- stage the warp's band rows ----
@@ -76,16 +80,19 @@ __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
     const uint8_t* sb_t = R.band_sb + boff;
     const uint32_t* mk_t = R.band_mask + (size_t)boff * 4;
     const int NYP1 = R.NYP - 1;
+    const int rt_stride = R.rt_copy_stride;
     for (int i = 1 + lane; i <= Lc; i += 32) {
       const int r0 = NYP1 - (int)eb_t[i];
       const int sb = sb_t[i];
-      brow[i * BROW] = (uint32_t)r0 | ((uint32_t)min(sb, 2) << 16) | ((uint32_t)max(sb - 2, 0) << 24);
+      brow[i * BROW] = (uint32_t)r0;
+      // rt of the window columns: 4 shifted copies of rt_rev make the window start 16-B aligned for LDS.128
+      brow[i * BROW + 1] = (uint32_t)(((r0 & 3) * rt_stride + (r0 & ~3)) * 4);
+      brow[i * BROW + 2] = (uint32_t)min(sb, 2) | ((uint32_t)max(sb - 2, 0) << 8);
 #pragma unroll
-      for (int t = 0; t < NWORD; ++t) brow[i * BROW + 1 + t] = mk_t[(size_t)i * 4 + t];
+      for (int t = 0; t < NWORD; ++t) brow[i * BROW + 3 + t] = mk_t[(size_t)i * 4 + t];
     }
   }
   const int PWS = R.PWS;
-  const int rt_stride = R.rt_copy_stride;
   const int sum_rt = R.sum_rt;
   int* best_slot = A.best_k3 + (A.cta_rid ? (int)A.cta_rid[blockIdx.x] : 0);
   __syncwarp();
@@ -96,20 +103,17 @@ __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
   for (int k = 0; k < W; ++k) S[k] = 0;
   int sumup = 0;
   for (int i = 1; i <= Lc; ++i) {
-    const int c = crow[(size_t)(i - 1) * 128 + tid];
-    const uint32_t meta = brow[i * BROW];
-    const int x = c < 0 ? -c : c;
-    const int up = upx[x];
+    const uint32_t ci = crow[(size_t)(i - 1) * 128 + tid];  // plane row = block * 2 + strand
+    const uint32_t* bw = brow + i * BROW;                    // warp-uniform: broadcast loads
+    const uint32_t r0 = bw[0];
+    const uint32_t sbw = bw[2];
+    const int up = upx[ci];
     sumup += up;
-    const int r0 = meta & 0xffff;
-    const int sb = (meta >> 16) & 3;
-    const uint32_t* pl = planes + (x * 2 + (c < 0 ? 1 : 0)) * PWS + (r0 >> 5);
-    const int sh = r0 & 31;
+    const uint32_t* pl = planes + ci * PWS + (r0 >> 5);
     uint32_t m[NWORD];
 #pragma unroll
-    for (int t = 0; t < NWORD; ++t) m[t] = __funnelshift_r(pl[t], pl[t + 1], sh) & brow[i * BROW + 1 + t];
-    // rt of the window columns: 4 shifted copies of rt_rev make the window start 16-B aligned for LDS.128
-    const int* rtw = rtrev + (r0 & 3) * rt_stride + (r0 & ~3);
+    for (int t = 0; t < NWORD; ++t) m[t] = __funnelshift_r(pl[t], pl[t + 1], r0) & bw[3 + t];  // shift = r0 mod 32
+    const int* rtw = reinterpret_cast<const int*>(reinterpret_cast<const unsigned char*>(rtrev) + bw[1]);
     int rtr[RTW];
     if (RTREG) {
 #pragma unroll
@@ -121,9 +125,10 @@ __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
         rtr[4 * g + 3] = v.w;
       }
     }
-    if (meta >> 24) {  // rare: window moved by more than two columns (first rows of steep corridors)
-      for (int e = meta >> 24; e > 0; --e) dp_row_shift1<W>(S);
+    if (sbw >> 8) {  // rare: window moved by more than two columns (first rows of steep corridors)
+      for (int e = sbw >> 8; e > 0; --e) dp_row_shift1<W>(S);
     }
+    const int sb = sbw & 3;
     if (RTREG) {
       if (sb == 0)
         dp_row_step<W, 0>(S, m, up, rtr);
@@ -164,7 +169,7 @@ bool score_fast_supports(int width) { return score_fast_window(width) != 0; }
 
 size_t score_fast_smem(int W, uint32_t ctx_bytes /* largest region context of the launch */, int lmax) {
   const int nword = (W + 31) / 32;
-  return (size_t)ctx_bytes + (size_t)lmax * 256 + (size_t)4 * (lmax + 1) * (1 + nword) * 4;
+  return (size_t)ctx_bytes + (size_t)lmax * 256 + (size_t)4 * (lmax + 1) * (3 + nword) * 4;
 }
 
 template <int W>

@@ -25,7 +25,7 @@ static int run_fast(const RegionHost& R, const BandTable& T, const int16_t* pare
   for (int i = 1; i <= Lc; ++i) {
     const int c = child_elem(parent, kind, p, q, i);
     const int x = c < 0 ? -c : c;
-    const int up = upx[x];
+    const int up = upx[2 * x];
     sumup += up;
     const int r0 = R.NYP - 1 - T.eb[i];
     int sb = T.sb[i];
