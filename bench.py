@@ -193,7 +193,12 @@ def run_regions(args, rank, world, local):
     nctx = max(1, min(args.contexts, (os.cpu_count() or 8) // max(world, 1)))
     per = max(1, args.regions_per_pass)
     solvers = [nb.Solver(local) for _ in range(nctx)]
-    nb.solve_many(solvers, regs[:min(len(regs), per * nctx)], regions_per_pass=per, **FLAGS)  # warm-up: pools
+    # warm-up: one untimed run over an independent set of regions of the same generator (memory pools of every
+    # context, corridor tables of the shapes a long regionfile run keeps meeting); the timed run sees new regions
+    warm = make_regions(args.regions, seed=1000 + rank)
+    for _ in range(max(1, args.warmup_regions)):
+        nb.solve_many(solvers, warm, regions_per_pass=per, **FLAGS)
+    del warm
     sampler = ClockSampler(local)
     torch.cuda.synchronize()
     if dist is not None:
@@ -217,7 +222,7 @@ def run_regions(args, rank, world, local):
         s = torch.tensor([n, scored, launches, h2d, d2h], dtype=torch.float64, device="cuda")
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
         n, scored, launches, h2d, d2h = s.tolist()
-    line = dict(metric="regions_solved_per_s", value=n / dt, unit="regions/s", n_gpus=world, steps=1, warmup=1,
+    line = dict(metric="regions_solved_per_s", value=n / dt, unit="regions/s", n_gpus=world, steps=1, warmup=max(1, args.warmup_regions),
                 ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32",
                 data="synthetic",
                 config=dict(workload="regionfile batch: %d synthetic SD-flanked regions per GPU (20-120 blocks, 2-6 "
@@ -298,7 +303,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS) + ["regions"])
     ap.add_argument("--regions", type=int, default=6000, help="regions per rank for --workload regions")
-    ap.add_argument("--contexts", type=int, default=3, help="solver contexts (streams) per GPU for --workload regions")
+    ap.add_argument("--contexts", type=int, default=4, help="solver contexts (streams) per GPU for --workload regions")
+    ap.add_argument("--warmup-regions", type=int, default=2, help="untimed warm-up runs for --workload regions")
     ap.add_argument("--regions-per-pass", type=int, default=512,
                     help="regions searched together by one pipeline instance (--workload regions)")
     ap.add_argument("--mode", default="regions", choices=["regions", "frontier"],

@@ -154,51 +154,70 @@ struct DevBuf {
 void h2d(nw_ctx* c, void* dst, const void* src, size_t n);
 void d2h(nw_ctx* c, void* dst, const void* src, size_t n);
 
-struct BandStore {  // host cache + device mirror of per-length corridor tables for one (n_y, force)
-  int n_y = -1;
+// Corridor tables depend only on (child length, n_y, force): one process-wide host cache shared by all contexts
+// (a regionfile run meets the same few thousand shapes over and over, and every context would otherwise rebuild
+// them).  Tables are immutable once published; the packed arrays the device mirrors copy from are append-only and
+// guarded by the mutex.
+struct BandHost {
+  int n_y = 0;
   bool force = false;
-  std::vector<std::unique_ptr<BandTable>> tabs;  // [LMAX+2], built on first use
-  std::vector<int32_t> off;  // [LMAX+2] row offset or -1
+  std::mutex mu;
+  std::unique_ptr<std::atomic<BandTable*>[]> tabs;  // [LMAX+2], built on first use, never freed
+  std::vector<int32_t> off;                         // [LMAX+2] row offset or -1
   std::vector<int16_t> ab, eb;
   std::vector<uint8_t> sb;
   std::vector<uint32_t> mask;
+  BandHost(int ny, bool f) : n_y(ny), force(f), tabs(new std::atomic<BandTable*>[LMAX + 2]), off(LMAX + 2, -1) {
+    for (int i = 0; i < LMAX + 2; ++i) tabs[i].store(nullptr, std::memory_order_relaxed);
+  }
+  const BandTable& get(int L) {
+    BandTable* t = tabs[L].load(std::memory_order_acquire);
+    if (t) return *t;
+    std::lock_guard<std::mutex> lk(mu);
+    t = tabs[L].load(std::memory_order_relaxed);
+    if (t) return *t;
+    BandTable* T = new BandTable(build_band(L, n_y, force, WINDOW_MAX));
+    off[L] = (int32_t)eb.size();
+    for (int i = 0; i <= L; ++i) {
+      ab.push_back((int16_t)(i ? T->row[i].a : 1));
+      ab.push_back((int16_t)(i ? T->row[i].b : 0));
+      eb.push_back(T->eb[i]);
+      sb.push_back(T->sb[i]);
+      for (int w = 0; w < 4; ++w) mask.push_back(T->mask[(size_t)i * 4 + w]);
+    }
+    tabs[L].store(T, std::memory_order_release);
+    return *T;
+  }
+};
+BandHost& global_bands(int n_y, bool force) {
+  static std::mutex mu;
+  static std::map<int, std::unique_ptr<BandHost>> all;  // entries live for the life of the process
+  std::lock_guard<std::mutex> lk(mu);
+  std::unique_ptr<BandHost>& e = all[n_y * 2 + (force ? 1 : 0)];
+  if (!e) e.reset(new BandHost(n_y, force));
+  return *e;
+}
+
+struct BandStore {  // one context's device mirror of the tables of one (n_y, force)
+  int n_y = -1;
+  bool force = false;
+  BandHost* H = nullptr;
   DevBuf d_off, d_ab, d_eb, d_sb, d_mask;
-  bool dirty = true;
+  size_t up_rows = 0;  // table rows already on the device (tables are append-only)
   void reset(int ny, bool f) {
     n_y = ny;
     force = f;
-    tabs.clear();
-    tabs.resize(LMAX + 2);
-    off.assign(LMAX + 2, -1);
-    ab.clear();
-    eb.clear();
-    sb.clear();
-    mask.clear();
+    H = &global_bands(ny, f);
     up_rows = 0;
-    dirty = true;
   }
-  const BandTable& get(int L) {
-    if (tabs[L]) return *tabs[L];
-    BandTable T = build_band(L, n_y, force, WINDOW_MAX);
-    off[L] = (int32_t)eb.size();
-    for (int i = 0; i <= L; ++i) {
-      ab.push_back((int16_t)(i ? T.row[i].a : 1));
-      ab.push_back((int16_t)(i ? T.row[i].b : 0));
-      eb.push_back(T.eb[i]);
-      sb.push_back(T.sb[i]);
-      for (int w = 0; w < 4; ++w) mask.push_back(T.mask[(size_t)i * 4 + w]);
-    }
-    dirty = true;
-    tabs[L].reset(new BandTable(std::move(T)));
-    return *tabs[L];
-  }
-  size_t up_rows = 0;  // table rows already on the device (tables are append-only)
-  // copies the rows added since the last upload (everything after a reallocation).  Asynchronous: the caller
-  // synchronises once after all stores, before the next get() can reallocate the host vectors.
+  const BandTable& get(int L) { return H->get(L); }
+  // copies the rows added (by any context) since the last upload, everything after a reallocation.  The pageable
+  // sources are consumed when cudaMemcpyAsync returns, so the lock is held only for the duration of the calls.
   bool upload(nw_ctx* c, cudaStream_t st) {
     (void)st;
-    if (!dirty) return false;
-    const size_t rows = eb.size();
+    std::lock_guard<std::mutex> lk(H->mu);
+    const size_t rows = H->eb.size();
+    if (rows == up_rows) return false;
     if (rows * 4 > d_ab.cap || rows * 2 > d_eb.cap || rows > d_sb.cap || rows * 16 > d_mask.cap) {
       d_ab.ensure(rows * 4 * 2);  // slack: the next few tables append in place
       d_eb.ensure(rows * 2 * 2);
@@ -206,16 +225,13 @@ struct BandStore {  // host cache + device mirror of per-length corridor tables 
       d_mask.ensure(rows * 16 * 2);
       up_rows = 0;
     }
-    h2d(c, d_off.ensure(off.size() * 4), off.data(), off.size() * 4);
+    h2d(c, d_off.ensure(H->off.size() * 4), H->off.data(), H->off.size() * 4);
     const size_t r0 = up_rows, n = rows - up_rows;
-    if (n) {
-      h2d(c, d_ab.as<int16_t>() + r0 * 2, ab.data() + r0 * 2, n * 4);
-      h2d(c, d_eb.as<int16_t>() + r0, eb.data() + r0, n * 2);
-      h2d(c, d_sb.as<uint8_t>() + r0, sb.data() + r0, n);
-      h2d(c, d_mask.as<uint32_t>() + r0 * 4, mask.data() + r0 * 4, n * 16);
-    }
+    h2d(c, d_ab.as<int16_t>() + r0 * 2, H->ab.data() + r0 * 2, n * 4);
+    h2d(c, d_eb.as<int16_t>() + r0, H->eb.data() + r0, n * 2);
+    h2d(c, d_sb.as<uint8_t>() + r0, H->sb.data() + r0, n);
+    h2d(c, d_mask.as<uint32_t>() + r0 * 4, H->mask.data() + r0 * 4, n * 16);
     up_rows = rows;
-    dirty = false;
     return true;
   }
 };
