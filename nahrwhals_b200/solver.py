@@ -7,6 +7,7 @@ minreport (-r), maxreport (-R, None = nothing).  `main(argv)` is the drop-in for
 """
 import argparse
 import ctypes as C
+import time
 import sys
 
 import numpy as np
@@ -45,7 +46,7 @@ class SolveResult:
     def tsv(self):
         """the exact text write_trajectories (solver.jl:747-753) would write"""
         if not isinstance(self._tsv, str):
-            self._tsv = bytes(self._tsv).decode()
+            self._tsv = self._tsv.tobytes().decode() if hasattr(self._tsv, "tobytes") else bytes(self._tsv).decode()
         return self._tsv
 
     @tsv.setter
@@ -242,7 +243,6 @@ def _unpack_many(solver, outs, n, o):
     t1 = np.cumsum(nt).tolist()
     m1 = np.cumsum(nm).tolist()
     b1 = np.cumsum(tl).tolist()
-    tsv_b = tsv.tobytes()
     res = []
     t0 = m0 = b0 = 0
     for k in range(n):
@@ -255,7 +255,7 @@ def _unpack_many(solver, outs, n, o):
         R.total_bp = total[t0:te]
         R.index_id = idx[t0:te]
         R.moves3 = moves3[m0:me]
-        R._tsv = tsv_b[b0:be]
+        R._tsv = tsv[b0:be]  # view into the shared buffer; decoded on first access
         R.stats = stats[k]
         res.append(R)
         t0, m0, b0 = te, me, be
@@ -284,10 +284,11 @@ def solve_batch(solvers, regions, **kw):
     return res
 
 
-def solve_many(solver, regions, regions_per_pass=256, **kw):
+def solve_many(solver, regions, regions_per_pass=256, timing=None, **kw):
     """Regionfile mode: `regions_per_pass` regions are searched together through one pipeline instance
     (nw_solve_many), so every kernel launch is shared by all of them.  `solver` may be a list of Solvers: the passes
-    are then handed out to the contexts dynamically (nw_solve_many_ctxs).  Returns one SolveResult per region."""
+    are then handed out to the contexts dynamically (nw_solve_many_ctxs).  Returns one SolveResult per region;
+    `timing` (a dict) receives the wall time of the native call under "native_s"."""
     L = _lib.load()
     solvers = list(solver) if isinstance(solver, (list, tuple)) else [solver]
     solver = solvers[0]
@@ -295,11 +296,14 @@ def solve_many(solver, regions, regions_per_pass=256, **kw):
     keep, probs = _problems(regions)
     outs = (C.c_void_p * max(n, 1))()
     o = solver._opts(**kw)
+    t0 = time.perf_counter()
     if len(solvers) == 1:
         rc = L.nw_solve_many(solver.h, probs, n, C.byref(o), int(regions_per_pass), outs)
     else:  # passes handed out to several contexts: host work of one pass overlaps device work of another
         hs = (C.c_void_p * len(solvers))(*[s.h for s in solvers])
         rc = L.nw_solve_many_ctxs(hs, len(solvers), probs, n, C.byref(o), int(regions_per_pass), outs)
+    if timing is not None:  # wall time of the C-ABI call alone (host buffers in, reports in host memory out)
+        timing["native_s"] = time.perf_counter() - t0
     res = []
     try:
         _lib.check(rc)
