@@ -535,13 +535,31 @@ uint64_t scan_scratch_items(uint64_t n) { return (n + SCAN_B - 1) / SCAN_B + 1; 
 // =====================================================================================================
 // resolve / assign: which candidate is the first discoverer of its index (solver.jl:535-561)
 // =====================================================================================================
-__global__ void k_resolve(ExpandArgs A, uint32_t G, uint32_t* is_new, uint32_t* owner) {
-  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= G) return;
-  const uint32_t g = cand_gpos(A, pos, desc_parent(A.desc[pos]));
-  const uint32_t o = (uint32_t)A.table[(uint64_t)A.slot[pos] * TBL_WORDS + 2];  // the one random table read
-  owner[pos] = o;
-  is_new[pos] = o == g ? 1u : 0u;
+// four candidates per thread: four independent random table reads in flight; the descriptor is only needed for the
+// global position of a sharded search
+__global__ void __launch_bounds__(256) k_resolve(ExpandArgs A, uint32_t G, uint32_t* is_new, uint32_t* owner) {
+  const uint32_t pos0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+  if (pos0 >= G) return;
+  if (pos0 + 3 < G) {
+    const uint4 sl = *reinterpret_cast<const uint4*>(A.slot + pos0);
+    const uint32_t s4[4] = {sl.x, sl.y, sl.z, sl.w};
+    uint32_t o[4], g[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = (uint32_t)__ldg(&A.table[(uint64_t)s4[q] * TBL_WORDS + 2]);  // the random reads
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      g[q] = A.off_glob ? cand_gpos(A, pos0 + q, desc_parent(A.desc[pos0 + q])) : A.gbase + pos0 + q;
+    *reinterpret_cast<uint4*>(owner + pos0) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(is_new + pos0) =
+        make_uint4(o[0] == g[0] ? 1u : 0u, o[1] == g[1] ? 1u : 0u, o[2] == g[2] ? 1u : 0u, o[3] == g[3] ? 1u : 0u);
+    return;
+  }
+  for (uint32_t pos = pos0; pos < G; ++pos) {
+    const uint32_t g = A.off_glob ? cand_gpos(A, pos, desc_parent(A.desc[pos])) : A.gbase + pos;
+    const uint32_t o = (uint32_t)A.table[(uint64_t)A.slot[pos] * TBL_WORDS + 2];
+    owner[pos] = o;
+    is_new[pos] = o == g ? 1u : 0u;
+  }
 }
 
 __device__ __forceinline__ int32_t owner_id(const LevelTable& LT, uint32_t g) {
@@ -550,49 +568,68 @@ __device__ __forceinline__ int32_t owner_id(const LevelTable& LT, uint32_t g) {
   return LT.cand_id[l][g - LT.gbase[l]];
 }
 
-__global__ void k_assign(AssignArgs A) {
-  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in = pos < A.G;
-  int key = -1;  // histogram key (child length, sub-counter) of lanes that need a DP; -1 = none
-  if (in) {
-    // the four per-candidate records are independent: issue their loads together, then the dependent ones
-    const uint32_t fresh = A.is_new[pos];
-    const uint32_t r = A.newrank[pos];
-    const uint32_t own = A.owner[pos];
-    const uint64_t d = A.desc[pos];
-    if (fresh) {
-      if (!A.skip_ids) A.cand_id[pos] = A.id_base + (int32_t)r;
-      A.newlist[r] = pos;
-      const uint32_t ps = desc_parent(d);
-      const int len = child_len(A.front_len[ps], desc_kind(d), desc_i(d), desc_j(d));
-      const int rid = A.front_rid ? (int)A.front_rid[ps] : 0;
-      A.new_len[r] = (uint16_t)len;
-      A.new_rid[r] = (uint16_t)rid;
-      if (!A.force && early_exit(len, A.regions[rid].n_y)) {  // solver.jl:332-334 -> score 0.0, no DP
-        A.k3[r] = 0;
-        A.cost[r] = -1;
-        A.total[r] = 0;
-      } else {
-        key = bucket_key(rid, A.lcap, len, r);
-      }
-    } else if (!A.skip_ids) {
-      const uint32_t g = own;
-      A.cand_id[pos] = g >= A.gbase ? A.id_base + (int32_t)A.newrank[g - A.gbase] : owner_id(A.LT, g);
+// Four consecutive candidates per thread: the per-candidate records arrive as 16-byte vectors and the four dependent
+// chains (parent length / region, owner's id) are in flight together -- the kernel is bound by memory latency.
+__device__ __forceinline__ int assign_one(const AssignArgs& A, uint32_t pos, uint32_t fresh, uint32_t r, uint32_t own,
+                                          uint64_t d) {
+  int key = -1;  // histogram key (region, child length, sub-counter) of candidates that need a DP; -1 = none
+  if (fresh) {
+    if (!A.skip_ids) A.cand_id[pos] = A.id_base + (int32_t)r;
+    A.newlist[r] = pos;
+    const uint32_t ps = desc_parent(d);
+    const int len = child_len(A.front_len[ps], desc_kind(d), desc_i(d), desc_j(d));
+    const int rid = A.front_rid ? (int)A.front_rid[ps] : 0;
+    A.new_len[r] = (uint16_t)len;
+    A.new_rid[r] = (uint16_t)rid;
+    if (!A.force && early_exit(len, A.regions[rid].n_y)) {  // solver.jl:332-334 -> score 0.0, no DP
+      A.k3[r] = 0;
+      A.cost[r] = -1;
+      A.total[r] = 0;
+    } else {
+      key = bucket_key(rid, A.lcap, len, r);
+    }
+  } else if (!A.skip_ids) {
+    A.cand_id[pos] = own >= A.gbase ? A.id_base + (int32_t)A.newrank[own - A.gbase] : owner_id(A.LT, own);
+  }
+  return key;
+}
+__global__ void __launch_bounds__(256) k_assign(AssignArgs A) {
+  const uint32_t pos0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+  int key[4] = {-1, -1, -1, -1};
+  if (pos0 + 3 < A.G) {
+    const uint4 fr = *reinterpret_cast<const uint4*>(A.is_new + pos0);
+    const uint4 rk = *reinterpret_cast<const uint4*>(A.newrank + pos0);
+    const uint4 ow = *reinterpret_cast<const uint4*>(A.owner + pos0);
+    const ulonglong2 d01 = *reinterpret_cast<const ulonglong2*>(A.desc + pos0);
+    const ulonglong2 d23 = *reinterpret_cast<const ulonglong2*>(A.desc + pos0 + 2);
+    key[0] = assign_one(A, pos0, fr.x, rk.x, ow.x, d01.x);
+    key[1] = assign_one(A, pos0 + 1, fr.y, rk.y, ow.y, d01.y);
+    key[2] = assign_one(A, pos0 + 2, fr.z, rk.z, ow.z, d23.x);
+    key[3] = assign_one(A, pos0 + 3, fr.w, rk.w, ow.w, d23.y);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t pos = pos0 + q;
+      if (pos < A.G) key[q] = assign_one(A, pos, A.is_new[pos], A.newrank[pos], A.owner[pos], A.desc[pos]);
     }
   }
   // warp-aggregated histogram (all 32 lanes converge here)
-  const uint32_t peers = __match_any_sync(0xffffffffu, key);
-  if (key >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&A.hist[key], (uint32_t)__popc(peers));
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t peers = __match_any_sync(0xffffffffu, key[q]);
+    if (key[q] >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&A.hist[key[q]], (uint32_t)__popc(peers));
+  }
 }
 
 int launch_assign(const AssignArgs& A, cudaStream_t st) {
   if (A.G == 0) return 0;
-  k_assign<<<(A.G + 255) / 256, 256, 0, st>>>(A);
+  const uint32_t threads = (A.G + 3) / 4;
+  k_assign<<<(threads + 255) / 256, 256, 0, st>>>(A);
   return 1;
 }
 int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* is_new, uint32_t* owner, cudaStream_t st) {
   if (G == 0) return 0;
-  k_resolve<<<(G + 255) / 256, 256, 0, st>>>(A, G, is_new, owner);
+  k_resolve<<<((G + 3) / 4 + 255) / 256, 256, 0, st>>>(A, G, is_new, owner);
   return 1;
 }
 
