@@ -120,8 +120,9 @@ int nw_result_edges(const nw_result* r, int32_t* child, int32_t* parent, int32_t
 void nw_result_free(nw_result* r);
 
 /* Replaces slow_score (solver.jl:329-376) for a raw list of candidate indices (flat int16 + offsets).
- * force != 0 selects the R twin's forcecalc branch (R/evaltools.R:203-205; corridor 1.0, no early exit) that
- * produces res_ref.  Outputs per candidate: cost_bp (-1 early exit, -2 unreachable), total_bp, Float64 score. */
+ * force == 1 selects the R twin's forcecalc branch (R/evaltools.R:203-205; corridor 1.0, no early exit) that
+ * produces res_ref; force == 2 the R twin without forcecalc (R/evaltools.R:193-201: corridor chosen by n_y, the row
+ * count of R's matrix, and no early exit) that the depth-1 pre-pass uses (nwregion.h).  Outputs per candidate: cost_bp (-1 early exit, -2 unreachable), total_bp, Float64 score. */
 int nw_score_batch(nw_ctx* ctx, const int8_t* aln_sign, int32_t n_x, int32_t n_y, const int64_t* len_x,
                    const int64_t* len_y, const int16_t* flat, const int64_t* off, int64_t n, int32_t force,
                    int32_t flags, int64_t* cost_bp, int64_t* total_bp, double* score);

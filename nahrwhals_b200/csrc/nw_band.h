@@ -16,9 +16,16 @@ struct BandRowHost {
   int a, b;  // valid real columns [a, b], 1-based; a > b == empty row
 };
 
+// Corridor modes: NW_BAND_JULIA = slow_score (pct chosen by the child length, solver.jl:378-386);
+// NW_BAND_FORCE = the R twin's forcecalc branch (pct 1.0, R/evaltools.R:203-205);
+// NW_BAND_RTWIN = the R twin without forcecalc: pct chosen by dim(mat)[1] == n_y (R/evaltools.R:193-201; R's matrix
+// has y as rows).  The predicates themselves are symmetric in (i/row, j/col), so the R cell set is the transpose of
+// the Julia one for the same pct.
+enum { NW_BAND_JULIA = 0, NW_BAND_FORCE = 1, NW_BAND_RTWIN = 2 };
+
 struct BandTable {
   int L = 0, n_y = 0;
-  bool force = false;
+  int mode = NW_BAND_JULIA;
   bool contiguous = true;        // every row's valid set is one interval
   std::vector<BandRowHost> row;  // row[1..L]; row[0] unused
   int64_t cells = 0;             // sum of valid cells == SURVEY 8d "cells(L, n_y)"
@@ -31,8 +38,9 @@ struct BandTable {
   std::vector<uint32_t> mask;    // mask[i*4 + w]: diag-allowed bits of row i, bit k <-> column eb[i]-k (k < 128)
 };
 
-inline double corridor_pct(int row, bool force) {
-  if (force) return 1.0;  // R/evaltools.R:203-205
+inline double corridor_pct(int row, int mode, int n_y = 0) {
+  if (mode == NW_BAND_FORCE) return 1.0;  // R/evaltools.R:203-205
+  if (mode == NW_BAND_RTWIN) row = n_y;   // R/evaltools.R:193: dim_[1] is the y dimension
   if (row < 10) return 1.0;
   if (row < 30) return 0.3;
   return 0.2;
@@ -47,9 +55,9 @@ inline bool band_valid(int i, int j, int row, int col, double pct) {
 }
 
 // exhaustive form (tests only): every (i, j) is evaluated with band_valid()
-inline void band_rows_bruteforce(int L, int n_y, bool force, std::vector<BandRowHost>& row, int64_t& cells,
+inline void band_rows_bruteforce(int L, int n_y, int mode, std::vector<BandRowHost>& row, int64_t& cells,
                                  bool& contiguous) {
-  const double pct = corridor_pct(L, force);
+  const double pct = corridor_pct(L, mode, n_y);
   row.assign(L + 1, BandRowHost{1, 0});
   cells = 0;
   contiguous = true;
@@ -107,12 +115,12 @@ inline void band_rows_fast(int L, int n_y, double pct, std::vector<BandRowHost>&
   }
 }
 
-inline BandTable build_band(int L, int n_y, bool force, int max_window = 128) {
+inline BandTable build_band(int L, int n_y, int mode, int max_window = 128) {
   BandTable T;
   T.L = L;
   T.n_y = n_y;
-  T.force = force;
-  const double pct = corridor_pct(L, force);
+  T.mode = mode;
+  const double pct = corridor_pct(L, mode, n_y);
   band_rows_fast(L, n_y, pct, T.row, T.cells, T.contiguous);
   // ---- fast-path derivation ----
   T.eb.assign(L + 1, 0);

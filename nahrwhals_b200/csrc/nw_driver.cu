@@ -160,14 +160,14 @@ void d2h(nw_ctx* c, void* dst, const void* src, size_t n);
 // guarded by the mutex.
 struct BandHost {
   int n_y = 0;
-  bool force = false;
+  int force = 0;  // corridor mode (NW_BAND_*)
   std::mutex mu;
   std::unique_ptr<std::atomic<BandTable*>[]> tabs;  // [LMAX+2], built on first use, never freed
   std::vector<int32_t> off;                         // [LMAX+2] row offset or -1
   std::vector<int16_t> ab, eb;
   std::vector<uint8_t> sb;
   std::vector<uint32_t> mask;
-  BandHost(int ny, bool f) : n_y(ny), force(f), tabs(new std::atomic<BandTable*>[LMAX + 2]), off(LMAX + 2, -1) {
+  BandHost(int ny, int f) : n_y(ny), force(f), tabs(new std::atomic<BandTable*>[LMAX + 2]), off(LMAX + 2, -1) {
     for (int i = 0; i < LMAX + 2; ++i) tabs[i].store(nullptr, std::memory_order_relaxed);
   }
   const BandTable& get(int L) {
@@ -189,22 +189,22 @@ struct BandHost {
     return *T;
   }
 };
-BandHost& global_bands(int n_y, bool force) {
+BandHost& global_bands(int n_y, int force) {
   static std::mutex mu;
   static std::map<int, std::unique_ptr<BandHost>> all;  // entries live for the life of the process
   std::lock_guard<std::mutex> lk(mu);
-  std::unique_ptr<BandHost>& e = all[n_y * 2 + (force ? 1 : 0)];
+  std::unique_ptr<BandHost>& e = all[n_y * 3 + force];
   if (!e) e.reset(new BandHost(n_y, force));
   return *e;
 }
 
 struct BandStore {  // one context's device mirror of the tables of one (n_y, force)
   int n_y = -1;
-  bool force = false;
+  int force = 0;
   BandHost* H = nullptr;
   DevBuf d_off, d_ab, d_eb, d_sb, d_mask;
   size_t up_rows = 0;  // table rows already on the device (tables are append-only)
-  void reset(int ny, bool f) {
+  void reset(int ny, int f) {
     n_y = ny;
     force = f;
     H = &global_bands(ny, f);
@@ -339,7 +339,7 @@ struct ProblemRef {
 };
 
 // Builds and uploads the context of every region of a search (packed into a few buffers: one copy each).
-void setup_regions(nw_ctx* c, const ProblemRef* probs, int R, int maxdepth, bool force) {
+void setup_regions(nw_ctx* c, const ProblemRef* probs, int R, int maxdepth, int force) {
   if (R < 1 || R > 65535) fail(NW_ERR_ARG, "a batch holds between 1 and 65535 regions");
   cudaStream_t st = c->stream;
   c->RH.clear();
@@ -410,7 +410,7 @@ void setup_regions(nw_ctx* c, const ProblemRef* probs, int R, int maxdepth, bool
     D.ms_dd = reinterpret_cast<uint32_t*>(dms + o_dd[r]);
     D.ms_inv = reinterpret_cast<uint32_t*>(dms + o_inv[r]);
     D.ms_any = reinterpret_cast<uint32_t*>(dms + o_any[r]);
-    BandStore& bs = c->band_cache[H.n_y * 2 + (force ? 1 : 0)];
+    BandStore& bs = c->band_cache[H.n_y * 3 + force];
     if (bs.n_y != H.n_y || bs.force != force) bs.reset(H.n_y, force);
     c->rbands[r] = &bs;
   }
@@ -1941,7 +1941,7 @@ void do_solve_many(nw_ctx* c, const ProblemRef* probs, int R, const nw_opts* o, 
     return std::chrono::duration<float, std::milli>(b - a).count();
   };
   const auto t0 = now();
-  setup_regions(c, probs, R, o->maxdepth, false);
+  setup_regions(c, probs, R, o->maxdepth, NW_BAND_JULIA);
   Search S(c, *o);
   const auto t1 = now();
   S.run();
@@ -1977,6 +1977,15 @@ void do_solve(nw_ctx* c, const int8_t* aln, int n_x, int n_y, const int64_t* len
 
 }  // namespace
 
+// internal hooks for the other translation units of the library (nw_region.cu)
+namespace nw {
+void set_last_error(const std::string& m) { g_last_error = m; }
+int ctx_device(nw_ctx* c) { return c->device; }
+cudaStream_t ctx_stream(nw_ctx* c) { return c->stream; }
+void ctx_add_launches(nw_ctx* c, int n) { c->launches += n; }
+int ctx_launches(nw_ctx* c) { return c->launches; }
+}  // namespace nw
+
 extern "C" {
 
 void nw_default_opts(nw_opts* o) {
@@ -1990,6 +1999,7 @@ void nw_default_opts(nw_opts* o) {
   o->flags = 0;
 }
 const char* nw_last_error(void) { return g_last_error.c_str(); }
+
 const char* nw_version(void) { return "nwsolve-b200 0.1 (sm_100a)"; }
 
 int nw_ctx_create(int device, nw_ctx** out) {
@@ -2281,6 +2291,7 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
     CK(cudaSetDevice(c->device));
     if (n == 0) return;
     if (n >= (1ll << 31)) fail(NW_ERR_ARG, "too many candidates");
+    if (force < 0 || force > 2) fail(NW_ERR_ARG, "force must be 0 (slow_score), 1 (forcecalc) or 2 (R twin corridor)");
     cudaStream_t s = c->stream;
     int maxlen = 1;
     for (int64_t k = 0; k < n; ++k) {
@@ -2297,7 +2308,7 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
     while (((int64_t)n_x << depth_equiv) < maxlen) ++depth_equiv;
     {
       const ProblemRef P{aln, n_x, n_y, len_x, len_y};
-      setup_regions(c, &P, 1, depth_equiv, force != 0);
+      setup_regions(c, &P, 1, depth_equiv, force);
     }
     // candidates as a "frontier" of n parents scored through KIND_ID descriptors
     Level L;
@@ -2373,7 +2384,7 @@ int nw_moveset(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, uint8_t* 
     std::vector<int64_t> lx(n_x, 1), ly(n_y, 1);
     {
       const ProblemRef P{aln, n_x, n_y, lx.data(), ly.data()};
-      setup_regions(c, &P, 1, 1, false);
+      setup_regions(c, &P, 1, 1, NW_BAND_JULIA);
     }
     const int MW = c->RH[0].MW;
     std::vector<uint32_t> dd((size_t)(n_x + 1) * MW), iv((size_t)(n_x + 1) * MW);
@@ -2539,7 +2550,7 @@ int nw_dist_begin(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const 
     collect_score_time(c, nullptr, nullptr);
     {
       const ProblemRef P{aln, n_x, n_y, len_x, len_y};
-      setup_regions(c, &P, 1, o->maxdepth, false);
+      setup_regions(c, &P, 1, o->maxdepth, NW_BAND_JULIA);
     }
     Search* S = new Search(c, *o);
     c->dist = S;

@@ -1,0 +1,1077 @@
+// nw_region.cu -- the per-region steps either side of the solver call (include/nwregion.h).
+//
+// Reference control flow: R/wrapper_aln_and_analyse.R:176-191.  The reference manipulates the gridmatrix itself
+// (cbind of column ranges, R/seqmodder.R); here an arrangement is a list of positions (signed x block, length of the
+// position), the matrix is never materialised, and all children of the reference arrangement are evaluated in two
+// launches: k_est_diag (estimate pre-filter, R/evaltools.R:51-71) and the banded-DP kernels behind nw_score_batch
+// (corridor chosen the way the R twin chooses it, R/evaltools.R:193-205).  The sequential part of dfsutil
+// (visited-hash, running est_highest, > 90 filter) is then replayed on the host over the per-child numbers in the
+// reference's order.  No CPU fallback: without a device nw_region_prepass / nw_region_analyse fail.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <memory>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/nwregion.h"
+
+struct nw_ctx;
+namespace nw {
+void set_last_error(const std::string& m);
+int ctx_device(nw_ctx* c);
+cudaStream_t ctx_stream(nw_ctx* c);
+int ctx_launches(nw_ctx* c);
+}  // namespace nw
+
+namespace {
+
+const double kNA = std::numeric_limits<double>::quiet_NaN();
+
+struct RErr {
+  int code;
+  std::string msg;
+};
+[[noreturn]] void rfail(int code, const std::string& m) { throw RErr{code, m}; }
+#define RCK(call)                                                                         \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) rfail(NW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+#define NWCK(call)                                       \
+  do {                                                   \
+    int rc_ = (call);                                    \
+    if (rc_ != NW_OK) rfail(rc_, nw_last_error());       \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// GPU: estimate pre-filter of every child (calculate_estimated_aln_score, R/evaltools.R:51-71).
+//   matdiag = mat * (|row - col| < ncol * fact);  sum(rowMaxs(matdiag)) + sum(colMaxs(matdiag))
+// One warp per child.  The child matrix is read through its position list: mat[y][p] = sign(blk_p) * grid[y][|blk_p|].
+// fact = 1 when n_y < 10 (|d| < L), else 0.25 (|d| < L/4  <=>  4|d| < L, exact in integers).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_est_diag(const int64_t* __restrict__ grid, int n_x, int n_y,
+                                                  const int16_t* __restrict__ blk, const int64_t* __restrict__ off,
+                                                  int n, long long* __restrict__ sum_rows, long long* __restrict__ sum_cols) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const int16_t* b = blk + off[w];
+  const int L = (int)(off[w + 1] - off[w]);
+  const int fm = n_y < 10 ? 1 : 4;  // diagonalize_fact 1 (dim(mat)[1] < 10) or 0.25
+  auto inside = [&](int y, int p) { return fm * abs(y - p) < L; };
+  const long long NEG = LLONG_MIN;
+  long long sr = 0, sc = 0;
+  for (int y = lane; y < n_y; y += 32) {  // rowMaxs: the row also holds the zeros of the cells outside the band
+    long long m = NEG;
+    bool any_out = false;
+    for (int p = 0; p < L; ++p) {
+      if (inside(y, p)) {
+        const int v = b[p];
+        const long long g = grid[(size_t)y * n_x + (abs(v) - 1)];
+        m = max(m, v < 0 ? -g : g);
+      } else {
+        any_out = true;
+      }
+    }
+    if (any_out || m == NEG) m = max(m, 0ll);
+    sr += m;
+  }
+  for (int p = lane; p < L; p += 32) {  // colMaxs
+    const int v = b[p];
+    const int x = abs(v) - 1;
+    long long m = NEG;
+    bool any_out = false;
+    for (int y = 0; y < n_y; ++y) {
+      if (inside(y, p)) {
+        const long long g = grid[(size_t)y * n_x + x];
+        m = max(m, v < 0 ? -g : g);
+      } else {
+        any_out = true;
+      }
+    }
+    if (any_out || m == NEG) m = max(m, 0ll);
+    sc += m;
+  }
+  for (int o = 16; o; o >>= 1) {
+    sr += __shfl_xor_sync(0xffffffffu, sr, o);
+    sc += __shfl_xor_sync(0xffffffffu, sc, o);
+  }
+  if (lane == 0) {
+    sum_rows[w] = sr;
+    sum_cols[w] = sc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host model of the reference's matrices
+// ---------------------------------------------------------------------------------------------------------------
+struct Grid {
+  int ny = 0, nx = 0;
+  std::vector<int64_t> v;       // v[y*nx + x], signed bp
+  std::vector<int64_t> rn, cn;  // row.names (y lengths), colnames (x lengths)
+  int64_t at(int y, int x) const { return v[(size_t)y * nx + x]; }
+};
+
+struct Pos {
+  int16_t blk;  // signed 1-based x block of the (flipped) gridmatrix
+  int64_t len;  // colname of the position as R leaves it
+};
+typedef std::vector<Pos> Arr;
+
+struct Move {
+  int p1, p2;
+  int sv;  // 0 del, 1 dup, 2 inv   (names below)
+};
+const char* const kSvName[3] = {"del", "dup", "inv"};
+
+double r_round0(double x) { return std::nearbyint(x); }  // R round(x): IEC 60559 half-even (default rounding mode)
+
+// R/flip_bitl_y_if_needed.R:12-76
+Grid flip_if_needed(const Grid& g, bool& flipped, bool& unsure) {
+  std::vector<int64_t> f = g.v;
+  const int nr = g.ny, nc = g.nx;
+  if ((nr >= 4 || nc >= 4) && (nr >= 2 && nc >= 2)) {
+    const int y_min = (int)std::max(r_round0(nr * (1.0 / 4.0)), 2.0), y_max = (int)std::min(r_round0(nr * (3.0 / 4.0)), nr - 2.0);
+    const int x_min = (int)std::max(r_round0(nc * (1.0 / 4.0)), 2.0), x_max = (int)std::min(r_round0(nc * (3.0 / 4.0)), nc - 2.0);
+    // a:z counts down when a > z; subscript 0 selects nothing
+    for (int y = std::min(y_min, y_max); y <= std::max(y_min, y_max); ++y)
+      if (y >= 1 && y <= nr)
+        for (int x = 0; x < nc; ++x) f[(size_t)(y - 1) * nc + x] = 0;
+    for (int x = std::min(x_min, x_max); x <= std::max(x_min, x_max); ++x)
+      if (x >= 1 && x <= nc)
+        for (int y = 0; y < nr; ++y) f[(size_t)y * nc + (x - 1)] = 0;
+  }
+  double pos = 0, neg = 0;
+  for (int64_t t : f) {
+    if (t > 0) pos += (double)t;
+    if (t < 0) neg += (double)t;
+  }
+  neg = std::fabs(neg);
+  if (pos + neg == 0) pos = 1;
+  unsure = (std::max(pos, neg) / std::min(pos, neg)) < 2;  // x/0 = Inf
+  flipped = neg > pos;
+  if (!flipped) return g;
+  Grid o = g;
+  if (nr == 1) {
+    for (auto& t : o.v) t = -t;
+  } else {  // -apply(bitl, 2, rev): rows and their names reversed, signs negated
+    for (int y = 0; y < nr; ++y) {
+      o.rn[y] = g.rn[nr - 1 - y];
+      for (int x = 0; x < nc; ++x) o.v[(size_t)y * nc + x] = -g.at(nr - 1 - y, x);
+    }
+  }
+  return o;
+}
+
+// R/find_sv_opportunities.R:12-98
+std::vector<Move> find_sv_opportunities(const Grid& g) {
+  struct Key {
+    int p1, p2, ori;
+  };
+  std::vector<Key> rows;
+  std::map<std::pair<std::pair<int, int>, int>, int> seen;
+  std::vector<int> nz;
+  for (int y = 0; y < g.ny; ++y) {
+    nz.clear();
+    for (int x = 0; x < g.nx; ++x)
+      if (g.at(y, x) != 0) nz.push_back(x + 1);
+    if (nz.size() < 2) continue;
+    for (size_t a = 0; a < nz.size(); ++a)
+      for (size_t c = a + 1; c < nz.size(); ++c) {
+        const int p1 = nz[a], p2 = nz[c];
+        const int ori = ((g.at(y, p1 - 1) > 0) == (g.at(y, p2 - 1) > 0)) ? 1 : -1;
+        auto k = std::make_pair(std::make_pair(p1, p2), ori);
+        if (seen.emplace(k, 1).second) rows.push_back(Key{p1, p2, ori});
+      }
+  }
+  std::vector<Move> out;
+  for (const Key& k : rows) out.push_back(Move{k.p1, k.p2, k.ori == -1 ? 2 : 0});
+  for (const Key& k : rows)
+    if (k.ori == 1) out.push_back(Move{k.p1, k.p2, 1});
+  std::vector<Move> keep;
+  for (const Move& m : out)
+    if (!(m.p2 - m.p1 == 1 && m.sv == 2)) keep.push_back(m);
+  return keep;
+}
+
+// carry_out_compressed_sv (R/seqmodder.R:10-109) on the reference arrangement `a` (positions 1..n), including the
+// manual colname repairs of :25-31, :52, :63, :83-87, :93-97, which move LENGTHS between positions.
+Arr carry_out(const Arr& a, const Move& mv) {
+  const int n = (int)a.size(), p1 = mv.p1, p2 = mv.p2;
+  Arr o;
+  auto put = [&](int i, bool neg) {
+    Pos t = a[i - 1];
+    if (neg) t.blk = (int16_t)-t.blk;
+    o.push_back(t);
+  };
+  if (mv.sv == 0) {  // del: bitl[, -c(p1:(p2-1))]
+    for (int i = 1; i <= n; ++i)
+      if (!(i >= p1 && i <= p2 - 1)) put(i, false);
+    if (o.size() == 1) o[0].len = a[0].len;  // one column left: colnames(bitl)[1]
+  } else if (mv.sv == 1) {  // dup: cbind(bitl[, 1:p2], bitl[, (p1+1):n])
+    for (int i = 1; i <= p2; ++i) put(i, false);
+    for (int i = p1 + 1; i <= n; ++i) put(i, false);
+    if (p2 - p1 == 1) {
+      if (p1 == 1)
+        o.back().len = o[1].len;
+      else if (p2 == n)
+        o.back().len = o[o.size() - 2].len;
+    }
+  } else {  // inv
+    if (p2 - p1 == 1) return a;
+    if (p1 == 1 && p2 != n) {  // border case 1: the flanks themselves are inverted
+      for (int i = p2; i >= p1; --i) put(i, true);
+      for (int i = p2 + 1; i <= n; ++i) put(i, false);
+      o.back().len = a[o.size() - 1].len;
+    } else if (p1 > 1 && p2 == n) {  // border case 2
+      for (int i = 1; i <= p1 - 1; ++i) put(i, false);
+      for (int i = p2; i >= p1; --i) put(i, true);
+      o[0].len = a[0].len;
+    } else if (p1 == 1 && p2 == n) {  // border case 3
+      for (int i = p2; i >= p1; --i) put(i, true);
+    } else {  // the standard case keeps both flanks
+      for (int i = 1; i <= p1; ++i) put(i, false);
+      for (int i = p2 - 1; i >= p1 + 1; --i) put(i, true);
+      for (int i = p2; i <= n; ++i) put(i, false);
+    }
+    if (p2 - p1 == 2) {
+      for (int i = 0; i < n; ++i) o[i].len = a[i].len;  // colnames(bitl_mut) <- colnames(bitl)
+    } else if (p2 == n) {
+      o[p2 - 1].len = o[p1 - 1].len;
+    }
+  }
+  return o;
+}
+
+inline int64_t cell(const Grid& g, const Arr& a, int y, int p) {
+  const int v = a[p].blk;
+  const int64_t t = g.at(y, std::abs(v) - 1);
+  return v < 0 ? -t : t;
+}
+
+// return_diag_values_new(matrix, fraction = 0.05) (helpers.R:98-113): the values rlang::hash() is fed
+void diag_values(const Grid& g, const Arr& a, std::vector<int64_t>& out) {
+  out.clear();
+  const int64_t nr = g.ny, nc = (int64_t)a.size(), mn = std::min(nr, nc);
+  const int64_t md = (int64_t)r_round0(std::max(5.0, 0.05 * (double)nr));
+  const int64_t last = (nr + 1) * (mn - 1) + 1;
+  auto value = [&](int64_t idx) { return cell(g, a, (int)((idx - 1) % nr), (int)((idx - 1) / nr)); };
+  std::vector<int64_t> clean;
+  for (int64_t o = -md; o <= md; ++o)  // outer() is flattened column-major: offsets outer, diagonal cells inner
+    for (int64_t k = 0; k < mn; ++k) {
+      const int64_t idx = 1 + k * (nr + 1) + o;
+      if (idx > 0 && idx <= last) clean.push_back(idx);
+    }
+  for (int64_t idx : clean) out.push_back(value(idx));
+  for (int64_t idx : clean) {
+    const int64_t j = nr * nc - idx;
+    if (j == 0) continue;  // zero subscript selects nothing
+    if (j < 0 || j > nr * nc) rfail(NW_ERR_ARG, "return_diag_values_new: subscript outside the matrix");
+    out.push_back(value(j));
+  }
+}
+
+struct VecHash {
+  size_t operator()(const std::vector<int64_t>& v) const {
+    uint64_t h = 1469598103934665603ull ^ v.size();
+    for (int64_t t : v) {
+      h ^= (uint64_t)t + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+      h *= 1099511628211ull;
+    }
+    return (size_t)h;
+  }
+};
+
+// is_cluttered (helpers.R:209-235)
+bool is_cluttered(const Grid& g) {
+  const int nr = g.ny, nc = g.nx;
+  if (!(nr > 5 && nc > 5)) return false;
+  int c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+  for (int x = 1; x <= nc - 2; ++x) {
+    c1 += g.at(0, x) != 0;
+    c2 += g.at(nr - 1, x) != 0;
+  }
+  for (int y = 1; y <= nr - 2; ++y) {
+    c3 += g.at(y, 0) != 0;
+    c4 += g.at(y, nc - 1) != 0;
+  }
+  return c1 >= 5 || c2 >= 5 || c3 >= 5 || c4 >= 5;
+}
+
+double round3(double x) {  // round(x, 3) for the non-tie values that occur; identical to the solver's rounding
+  const double y = std::nearbyint(x * 1000.0) / 1000.0;
+  return std::isfinite(y) ? y : x;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// result tables
+// ---------------------------------------------------------------------------------------------------------------
+struct nw_table {
+  // kind 0: table of solve_mutation (eval, mut1, mut1_start, mut1_end, mut1_pos_pm, mut1_len, mut1_len_pm, mut2_len,
+  //         mut2_len_pm, mut3_len, mut3_len_pm);  kind 1: table of format_julia_output (eval, mut1..mutN,
+  //         mut{i}_start, mut{i}_end, mut{i}_len for i = 1..N);  kind 2: format_julia_output's (eval, nmut, mut1 = ref)
+  int kind = 0;
+  int n_mut = 1;
+  struct Row {
+    double eval = 0;
+    int nmoves = 0;
+    std::vector<std::string> mut;  // "" = NA
+    std::vector<double> num;       // NaN = NA; kind 0: 9 values, kind 1: 3 per mutation
+  };
+  std::vector<Row> rows;
+  std::string tsv, mut_max;
+  nw_region_summary summ{};
+  std::vector<nw_candidate> cands;  // pre-pass diagnostics
+};
+
+namespace {
+
+int na_count(const nw_table& t, const nw_table::Row& r) {
+  int k = 0;
+  for (const std::string& m : r.mut) k += m.empty();
+  for (double v : r.num) k += std::isnan(v);
+  (void)t;
+  return k;
+}
+
+void sort_eval_na(nw_table& t) {  // order(-eval, -rowSums(is.na(.))), stable
+  std::vector<int> na(t.rows.size());
+  std::vector<size_t> ord(t.rows.size());
+  for (size_t k = 0; k < t.rows.size(); ++k) {
+    na[k] = na_count(t, t.rows[k]);
+    ord[k] = k;
+  }
+  std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
+    if (t.rows[a].eval != t.rows[b].eval) return t.rows[a].eval > t.rows[b].eval;
+    return na[a] > na[b];
+  });
+  std::vector<nw_table::Row> r2;
+  r2.reserve(ord.size());
+  for (size_t k : ord) r2.push_back(std::move(t.rows[k]));
+  t.rows.swap(r2);
+}
+
+void fmt_num(std::string& s, double v) {
+  if (std::isnan(v)) {
+    s += "NA";
+    return;
+  }
+  char buf[40];
+  for (int prec = 1; prec <= 17; ++prec) {  // shortest representation that round-trips
+    snprintf(buf, sizeof buf, "%.*g", prec, v);
+    if (strtod(buf, nullptr) == v) break;
+  }
+  s += buf;
+}
+
+// save_to_logfile (R/save_logfile.R:17-51) + text form
+void finish_table(nw_table& t) {
+  std::string& s = t.tsv;
+  s.clear();
+  if (t.kind == 0) {
+    s = "eval\tmut1\tmut1_start\tmut1_end\tmut1_pos_pm\tmut1_len\tmut1_len_pm\tmut2_len\tmut2_len_pm\tmut3_len\tmut3_len_pm\n";
+  } else if (t.kind == 2) {
+    s = "eval\tnmut\tmut1\n";
+  } else {
+    s = "eval";
+    for (int i = 1; i <= t.n_mut; ++i) s += "\tmut" + std::to_string(i);
+    for (int i = 1; i <= t.n_mut; ++i)
+      for (const char* suf : {"_start", "_end", "_len"}) s += "\tmut" + std::to_string(i) + suf;
+    s += "\n";
+  }
+  for (const auto& r : t.rows) {
+    fmt_num(s, r.eval);
+    if (t.kind == 2) s += "\t" + std::to_string(r.nmoves);
+    for (const std::string& m : r.mut) s += "\t" + (m.empty() ? std::string("NA") : m);
+    for (double v : r.num) {
+      s += "\t";
+      fmt_num(s, v);
+    }
+    s += "\n";
+  }
+  nw_region_summary& S = t.summ;
+  S.n_rows = (int32_t)t.rows.size();
+  S.n_mut = t.n_mut;
+  for (double& v : S.maxres) v = kNA;
+  S.res_ref = S.res_max = kNA;
+  S.n_res_max = 0;
+  t.mut_max = "ref";
+  if (t.rows.empty()) return;
+  int nref = 0;
+  for (const auto& r : t.rows)
+    if (!r.mut.empty() && r.mut[0] == "ref") {
+      ++nref;
+      S.res_ref = r.eval;
+    }
+  if (nref != 1) S.res_ref = kNA;
+  S.res_max = t.rows[0].eval;
+  double mx = t.rows[0].eval;
+  for (const auto& r : t.rows) mx = std::max(mx, r.eval);
+  // which.max over the max-eval subset of the NA count in mut1..mut3; the position is then used as a row number of
+  // the full table (identical when the table is sorted by eval, which it is on this path)
+  int pos = 0, best = -1, sub = 0;
+  for (const auto& r : t.rows) {
+    if (r.eval != mx) continue;
+    ++S.n_res_max;
+    int k = 0;
+    for (int i = 0; i < std::min<int>(3, (int)r.mut.size()); ++i) k += r.mut[i].empty();
+    if (k > best) {
+      best = k;
+      pos = sub;
+    }
+    ++sub;
+  }
+  const auto& m = t.rows[std::min<size_t>(pos, t.rows.size() - 1)];
+  std::string mm;
+  int nmut = 0;
+  for (int i = 0; i < std::min<int>(3, (int)m.mut.size()); ++i) nmut += !m.mut[i].empty();
+  for (int i = 0; i < nmut; ++i) mm += (i ? "+" : "") + m.mut[i];
+  t.mut_max = mm;
+  if (t.kind == 0) {  // mut1_start, mut1_end, mut1_pos_pm, mut1_len, mut1_len_pm, mut2_len, mut2_len_pm, mut3_len, mut3_len_pm
+    for (int k = 0; k < 5; ++k) S.maxres[k] = m.num[k];
+    S.maxres[8] = m.num[5];
+    S.maxres[9] = m.num[6];
+    S.maxres[13] = m.num[7];
+    S.maxres[14] = m.num[8];
+  } else if (t.kind == 1) {
+    for (int i = 0; i < std::min(3, t.n_mut); ++i) {
+      S.maxres[i * 5 + 0] = m.num[i * 3 + 0];
+      S.maxres[i * 5 + 1] = m.num[i * 3 + 1];
+      S.maxres[i * 5 + 3] = m.num[i * 3 + 2];
+    }
+  }
+}
+
+// turn_mut_max_into_svdf(t, correction = T) (R/juliasolver.R:138-245) on the moves of one trajectory
+struct Sv {
+  double start, end;
+  int kind;  // 0 del, 1 dup, 2 inv
+};
+void correct_coordinates(std::vector<Sv>& v) {
+  const int n = (int)v.size();
+  if (n <= 1) return;
+  std::vector<double> st(n), en(n);
+  for (int i = 0; i < n - 1; ++i) {
+    const double s0 = v[i].start, e0 = v[i].end;
+    for (int k = 0; k < n; ++k) {
+      st[k] = v[k].start;
+      en[k] = v[k].end;
+    }
+    if (v[i].kind == 2) {
+      for (int k = i + 1; k < n; ++k) {
+        const bool cs = st[k] > s0 && st[k] < e0, ce = en[k] > s0 && en[k] < e0;
+        if (ce) v[k].end = e0 - (en[k] - s0);
+        if (cs) v[k].start = e0 - (st[k] - s0);
+      }
+      for (int k = 0; k < n; ++k)
+        if (v[k].start > v[k].end) std::swap(v[k].start, v[k].end);
+    }
+    if (v[i].kind == 0) {
+      for (int k = i + 1; k < n; ++k) {
+        if (st[k] > s0) v[k].start += (e0 - s0);
+        if (en[k] > s0) v[k].end += (e0 - s0);
+      }
+    } else if (v[i].kind == 1) {
+      for (int k = i + 1; k < n; ++k) {
+        if (st[k] > e0) v[k].start -= (e0 - s0);
+        if (en[k] > e0) v[k].end -= (e0 - s0);
+      }
+    }
+  }
+}
+
+nw_table* format_solver_output(const char* tsv, int64_t len, const double* gl, int n_gl) {
+  struct Line {
+    std::vector<std::string> f;
+  };
+  std::vector<Line> lines;
+  {
+    int64_t a = 0;
+    while (a < len) {
+      int64_t b = a;
+      while (b < len && tsv[b] != '\n') ++b;
+      if (b > a) {
+        Line L;
+        int64_t s = a;
+        for (int64_t k = a; k <= b; ++k)
+          if (k == b || tsv[k] == '\t') {
+            L.f.emplace_back(tsv + s, tsv + k);
+            s = k + 1;
+          }
+        lines.push_back(std::move(L));
+      }
+      a = b + 1;
+    }
+  }
+  if (lines.empty()) rfail(NW_ERR_PARSE, "solver report is empty");  // read.table stops: no lines available
+  size_t ncols = 0;
+  for (const Line& L : lines) ncols = std::max(ncols, L.f.size());
+  if (ncols < 2) rfail(NW_ERR_PARSE, "solver report needs at least two columns");
+  const int n_mut = (int)((ncols - 2) / 3);
+  std::unique_ptr<nw_table> T(new nw_table);
+  auto num = [&](const std::string& s) {
+    char* e = nullptr;
+    const double v = strtod(s.c_str(), &e);
+    if (e == s.c_str()) rfail(NW_ERR_PARSE, "solver report: not a number: '" + s + "'");
+    return v;
+  };
+  if (n_mut == 0) {  // data.frame(eval = jout[1], nmut = jout[2], mut1 = 'ref')
+    T->kind = 2;
+    T->n_mut = 1;
+    for (const Line& L : lines) {
+      nw_table::Row r;
+      r.eval = num(L.f[0]);
+      r.nmoves = (int)num(L.f.size() > 1 ? L.f[1] : "0");
+      r.mut = {"ref"};
+      T->rows.push_back(std::move(r));
+    }
+    finish_table(*T);
+    return T.release();
+  }
+  T->kind = 1;
+  T->n_mut = n_mut;
+  for (const Line& L : lines) {
+    nw_table::Row r;
+    r.eval = num(L.f[0]);
+    r.nmoves = (int)num(L.f[1]);
+    r.mut.assign(n_mut, "");
+    r.num.assign((size_t)3 * n_mut, kNA);
+    std::vector<Sv> svs;
+    for (int i = 0; i < n_mut; ++i) {
+      const size_t c = 2 + 3 * (size_t)i;
+      if (c + 2 >= L.f.size()) continue;  // read.table(fill = TRUE): short lines are padded with NA
+      if (L.f[c].empty()) continue;
+      std::string kind = L.f[c];
+      if (kind.compare(0, 5, "move_") == 0) kind = kind.substr(5);
+      const double a = num(L.f[c + 1]), z = num(L.f[c + 2]);
+      char buf[96];
+      snprintf(buf, sizeof buf, "%.15g_%.15g_%s", a, z, kind.c_str());
+      r.mut[i] = buf;
+      const int k = kind == "del" ? 0 : kind == "dup" ? 1 : kind == "inv" ? 2 : -1;
+      if (k < 0) rfail(NW_ERR_PARSE, "solver report: unknown move '" + L.f[c] + "'");
+      svs.push_back(Sv{a, z, k});
+    }
+    if (r.nmoves != 0) {
+      correct_coordinates(svs);
+      for (size_t i = 0; i < svs.size(); ++i) {
+        auto at = [&](double p) {
+          const long long k = (long long)p;  // R truncates a double subscript
+          return (k >= 1 && k <= n_gl) ? gl[k - 1] : kNA;
+        };
+        const double a = at(svs[i].start), z = at(svs[i].end);
+        r.num[i * 3 + 0] = a;
+        r.num[i * 3 + 1] = z;
+        r.num[i * 3 + 2] = z - a;  // NA propagates
+      }
+    }
+    T->rows.push_back(std::move(r));
+  }
+  sort_eval_na(*T);
+  for (auto& r : T->rows)
+    if (r.nmoves == 0) r.mut[0] = "ref";
+  finish_table(*T);
+  return T.release();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the depth-1 pre-pass
+// ---------------------------------------------------------------------------------------------------------------
+struct PrepassOut {
+  std::unique_ptr<nw_table> table;
+  Grid flipped;
+  bool did_flip = false, unsure = false, cluttered = false;
+  std::vector<Move> moves;  // find_sv_opportunities of the flipped matrix
+  int64_t n_cand = 0, n_dp = 0;
+  int maxdepth = 1;
+  int launches = 0;
+};
+
+Grid make_grid(const int64_t* grid, int n_x, int n_y, const int64_t* len_x, const int64_t* len_y) {
+  if (!grid || !len_x || !len_y) rfail(NW_ERR_ARG, "null argument");
+  if (n_x < 2 || n_y < 2) rfail(NW_ERR_ARG, "the gridmatrix needs at least 2 x 2 blocks");
+  if (n_x > 16000 || n_y > 16000) rfail(NW_ERR_ARG, "gridmatrix too large");
+  Grid g;
+  g.nx = n_x;
+  g.ny = n_y;
+  g.v.assign(grid, grid + (size_t)n_x * n_y);
+  g.rn.assign(len_y, len_y + n_y);
+  g.cn.assign(len_x, len_x + n_x);
+  for (int64_t t : g.rn)
+    if (t <= 0) rfail(NW_ERR_RANGE, "non-positive y block length");
+  for (int64_t t : g.cn)
+    if (t <= 0) rfail(NW_ERR_RANGE, "non-positive x block length");
+  return g;
+}
+
+void annotate_row(nw_table::Row& r, const Grid& g, int p1, int p2) {
+  // annotate_res_out_with_positions_lens (helpers.R:412-485), mut1 only.  sum(colnumbers[1:(p-1)]): 1:0 selects element 1
+  auto lead = [&](int p) {
+    double s = 0;
+    if (p >= 2)
+      for (int i = 0; i < p - 1; ++i) s += (double)g.cn[i];
+    else
+      s = (double)g.cn[0];
+    return s;
+  };
+  const double start_mean = r_round0(lead(p1) + (double)g.cn[p1 - 1] / 2), end_mean = r_round0(lead(p2) + (double)g.cn[p2 - 1] / 2);
+  const double start_pm = r_round0((double)g.cn[p1 - 1] / 2), end_pm = r_round0((double)g.cn[p2 - 1] / 2);
+  const double lo = (end_mean - end_pm) - (start_mean + start_pm), hi = (end_mean + end_pm) - (start_mean - start_pm);
+  const double mean = (lo + hi) / 2;
+  r.num[0] = start_mean;
+  r.num[1] = end_mean;
+  r.num[2] = start_pm;
+  r.num[3] = mean;
+  r.num[4] = hi - mean;
+}
+
+PrepassOut run_prepass(nw_ctx* ctx, const Grid& g0, const nw_region_opts& o) {
+  PrepassOut P;
+  P.table.reset(new nw_table);
+  nw_table& T = *P.table;
+  T.kind = 0;
+  T.n_mut = 1;
+  auto add_row = [&](double ev, const std::string& mut1) -> nw_table::Row& {
+    nw_table::Row r;
+    r.eval = ev;
+    r.mut = {mut1};
+    r.num.assign(9, kNA);
+    T.rows.push_back(std::move(r));
+    return T.rows.back();
+  };
+  if (is_cluttered(g0)) {  // explore_mutation_space_v2.R:27-33
+    P.cluttered = true;
+    add_row(0.0, "ref");
+    P.flipped = g0;
+    finish_table(T);
+    return P;
+  }
+  P.flipped = flip_if_needed(g0, P.did_flip, P.unsure);
+  const Grid& g = P.flipped;
+  P.moves = find_sv_opportunities(g);
+  // reduce_depth_if_needed (helpers.R:318-347) with maxdepth_input = 1
+  P.maxdepth = P.moves.size() > 2000 ? 0 : 1;
+  const int n = g.nx;
+  Arr root(n);
+  for (int i = 0; i < n; ++i) root[i] = Pos{(int16_t)(i + 1), g.cn[i]};
+  std::vector<Arr> cand;
+  if (P.maxdepth >= 1)
+    for (const Move& m : P.moves) cand.push_back(carry_out(root, m));
+  P.n_cand = (int64_t)cand.size();
+
+  // ---- problem handed to the DP kernels: x blocks of the flipped matrix plus one virtual block per (block, length)
+  //      pair that a colname repair created ----
+  std::vector<int64_t> lenx(g.cn);
+  std::vector<int> vsrc;  // source block of every virtual block
+  std::map<std::pair<int, int64_t>, int> vmap;
+  std::vector<std::vector<int16_t>> seqs(cand.size() + 1);
+  auto to_seq = [&](const Arr& a, std::vector<int16_t>& s) {
+    s.resize(a.size());
+    for (size_t p = 0; p < a.size(); ++p) {
+      const int b = std::abs(a[p].blk);
+      int id = b;
+      if (a[p].len != g.cn[b - 1]) {
+        auto it = vmap.find({b, a[p].len});
+        if (it == vmap.end()) {
+          lenx.push_back(a[p].len);
+          vsrc.push_back(b);
+          it = vmap.emplace(std::make_pair(b, a[p].len), (int)lenx.size()).first;
+        }
+        id = it->second;
+      }
+      if (id > 32000) rfail(NW_ERR_ARG, "too many blocks");
+      s[p] = (int16_t)(a[p].blk < 0 ? -id : id);
+    }
+  };
+  to_seq(root, seqs[0]);
+  for (size_t k = 0; k < cand.size(); ++k) to_seq(cand[k], seqs[k + 1]);
+  const int nxa = (int)lenx.size();
+  std::vector<int8_t> aln((size_t)nxa * g.ny);
+  for (int x = 0; x < nxa; ++x) {
+    const int src = x < n ? x : vsrc[x - n] - 1;
+    for (int y = 0; y < g.ny; ++y) {
+      const int64_t t = g.at(y, src);
+      aln[(size_t)x * g.ny + y] = (int8_t)(t > 0 ? 1 : t < 0 ? -1 : 0);
+    }
+  }
+  const int L0 = nw::ctx_launches(ctx);
+  // ---- GPU 1: forced score of the reference arrangement (dfsutil: forcecalc = (pair$sv == "ref")) ----
+  int64_t cost = 0, total = 0;
+  double s_ref = 0;
+  {
+    const int64_t off[2] = {0, (int64_t)seqs[0].size()};
+    NWCK(nw_score_batch(ctx, aln.data(), nxa, g.ny, lenx.data(), g.rn.data(), seqs[0].data(), off, 1, 1, o.flags & NW_FLAG_GENERIC_DP,
+                        &cost, &total, &s_ref));
+    if (cost == -2) s_ref = 1.0;  // R/evaltools.R:259-261 (cannot happen with the full corridor)
+  }
+  // ---- GPU 2 + 3: estimate sums and DP of every child ----
+  const size_t nc = cand.size();
+  std::vector<int64_t> off(nc + 2, 0);
+  std::vector<int16_t> flat_dp, flat_blk;
+  for (size_t k = 0; k <= nc; ++k) {  // entry 0 = the reference arrangement (its estimate seeds est_highest)
+    const Arr& a = k ? cand[k - 1] : root;
+    off[k + 1] = off[k] + (int64_t)a.size();
+    for (const Pos& p : a) flat_blk.push_back(p.blk);
+    flat_dp.insert(flat_dp.end(), seqs[k].begin(), seqs[k].end());
+  }
+  std::vector<long long> srow(nc + 1), scol(nc + 1);
+  std::vector<int64_t> ccost(nc + 1, -1), ctotal(nc + 1, 0);
+  std::vector<double> cscore(nc + 1, 0.0);
+  {
+    RCK(cudaSetDevice(nw::ctx_device(ctx)));
+    cudaStream_t st = nw::ctx_stream(ctx);
+    void *d_grid = nullptr, *d_blk = nullptr, *d_off = nullptr, *d_sr = nullptr, *d_sc = nullptr;
+    auto cleanup = [&] {
+      cudaFree(d_grid);
+      cudaFree(d_blk);
+      cudaFree(d_off);
+      cudaFree(d_sr);
+      cudaFree(d_sc);
+    };
+    try {
+      RCK(cudaMalloc(&d_grid, g.v.size() * 8));
+      RCK(cudaMalloc(&d_blk, std::max<size_t>(flat_blk.size(), 1) * 2));
+      RCK(cudaMalloc(&d_off, off.size() * 8));
+      RCK(cudaMalloc(&d_sr, (nc + 1) * 8));
+      RCK(cudaMalloc(&d_sc, (nc + 1) * 8));
+      RCK(cudaMemcpyAsync(d_grid, g.v.data(), g.v.size() * 8, cudaMemcpyHostToDevice, st));
+      RCK(cudaMemcpyAsync(d_blk, flat_blk.data(), flat_blk.size() * 2, cudaMemcpyHostToDevice, st));
+      RCK(cudaMemcpyAsync(d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+      const int nn = (int)(nc + 1);
+      k_est_diag<<<(nn * 32 + 255) / 256, 256, 0, st>>>((const int64_t*)d_grid, g.nx, g.ny, (const int16_t*)d_blk,
+                                                        (const int64_t*)d_off, nn, (long long*)d_sr, (long long*)d_sc);
+      RCK(cudaGetLastError());
+      ++P.launches;
+      RCK(cudaMemcpyAsync(srow.data(), d_sr, (nc + 1) * 8, cudaMemcpyDeviceToHost, st));
+      RCK(cudaMemcpyAsync(scol.data(), d_sc, (nc + 1) * 8, cudaMemcpyDeviceToHost, st));
+      RCK(cudaStreamSynchronize(st));
+    } catch (...) {
+      cleanup();
+      throw;
+    }
+    cleanup();
+  }
+  if (nc > 0) {
+    // children with more than one column; a single remaining column has its own formula (R/evaltools.R:109-114)
+    std::vector<int64_t> off2(1, 0);
+    std::vector<int16_t> flat2;
+    std::vector<size_t> who;
+    for (size_t k = 1; k <= nc; ++k) {
+      if (cand[k - 1].size() < 2) continue;
+      who.push_back(k);
+      flat2.insert(flat2.end(), seqs[k].begin(), seqs[k].end());
+      off2.push_back((int64_t)flat2.size());
+    }
+    if (!who.empty()) {
+      std::vector<int64_t> c2(who.size()), t2(who.size());
+      std::vector<double> s2(who.size());
+      NWCK(nw_score_batch(ctx, aln.data(), nxa, g.ny, lenx.data(), g.rn.data(), flat2.data(), off2.data(), (int64_t)who.size(), 2,
+                          o.flags & NW_FLAG_GENERIC_DP, c2.data(), t2.data(), s2.data()));
+      for (size_t q = 0; q < who.size(); ++q) {
+        ccost[who[q]] = c2[q];
+        ctotal[who[q]] = t2[q];
+        cscore[who[q]] = s2[q];
+      }
+    }
+  }
+  P.launches += nw::ctx_launches(ctx) - L0;
+
+  for (size_t k = 1; k <= nc; ++k) {
+    const Move& m = P.moves[k - 1];
+    T.cands.push_back(nw_candidate{m.p1, m.p2, m.sv, (int32_t)cand[k - 1].size(), srow[k], scol[k], ccost[k], ctotal[k], cscore[k]});
+  }
+  // ---- replay of dfsutil's sequential part (R/dfs_machinery.R:79-246) ----
+  double sum_rn = 0, sum_cn0 = 0;
+  for (int64_t t : g.rn) sum_rn += (double)t;
+  for (int64_t t : g.cn) sum_cn0 += (double)t;
+  const double orig_symm = std::min(sum_rn, sum_cn0) / std::max(sum_rn, sum_cn0);  // calc_symm
+  auto est_of = [&](size_t k, double sum_cn) {
+    return (((double)srow[k] + (double)scol[k]) / (sum_rn + sum_cn)) * 100;
+  };
+  double est_highest = est_of(0, sum_cn0);  // forcecalc: est_highest <<- est
+  struct Rec {
+    int depth;
+    int mv;  // -1 = ref
+    double eval;
+  };
+  std::vector<Rec> recs;
+  recs.push_back(Rec{0, -1, s_ref});
+  std::unordered_map<std::vector<int64_t>, double, VecHash> visited;
+  std::vector<int64_t> dv;
+  diag_values(g, root, dv);
+  visited.emplace(dv, s_ref);
+  if (s_ref >= 0 && P.maxdepth > 0) {
+    for (size_t k = 1; k <= nc; ++k) {
+      const Arr& a = cand[k - 1];
+      diag_values(g, a, dv);
+      auto it = visited.find(dv);
+      if (it != visited.end()) {
+        if (it->second > 1) recs.push_back(Rec{1, (int)k - 1, it->second});
+        continue;
+      }
+      double s;
+      double sum_cn = 0;
+      for (const Pos& p : a) sum_cn += (double)p.len;
+      if (a.size() == 1) {  // dim(mat)[2] == 1: pos_aln / sum(row.names)
+        double pos_aln = 0;
+        for (int y = 0; y < g.ny; ++y) {
+          const int64_t t = cell(g, a, y, 0);
+          if (t > 0) pos_aln += (double)t;
+        }
+        s = round3((pos_aln / sum_rn) * 100);
+      } else {
+        const double symmetry = std::min(sum_rn, sum_cn) / std::max(sum_rn, sum_cn);
+        if (symmetry < orig_symm * 1 && g.ny > 5) {
+          s = 1;
+        } else {
+          const double est = est_of(k, sum_cn);
+          const double thr = g.ny < 10 ? 0.9 : 1.0;
+          if (est < est_highest * thr) {
+            s = 1;
+          } else {
+            if (est > est_highest) est_highest = est;
+            ++P.n_dp;
+            s = ccost[k] == -2 ? 1.0 : cscore[k];  // unreachable terminal cell: R/evaltools.R:259-261
+          }
+        }
+      }
+      if (s > 90) recs.push_back(Rec{1, (int)k - 1, s});
+      visited.emplace(dv, s);
+    }
+  }
+  // ---- sort_new_by_penalised, transform_res_new_to_old, annotate ----
+  const double step_penalty = (o.compression / sum_cn0 * 100) * 1.5;
+  std::vector<size_t> ord(recs.size());
+  std::vector<double> pen(recs.size());
+  for (size_t k = 0; k < recs.size(); ++k) {
+    ord[k] = k;
+    pen[k] = recs[k].eval - recs[k].depth * step_penalty;
+  }
+  std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return pen[a] > pen[b]; });
+  int count = 1;
+  bool stop = false;
+  for (size_t k : ord) {
+    const Rec& rc = recs[k];
+    if (rc.mv < 0) {
+      add_row(rc.eval, "ref");
+    } else {
+      const Move& m = P.moves[rc.mv];
+      add_row(rc.eval, std::to_string(m.p1) + "_" + std::to_string(m.p2) + "_" + kSvName[m.sv]);
+    }
+  }
+  for (size_t q = 0; q < T.rows.size() && !stop; ++q) {
+    ++count;
+    if (count > 2000) {
+      stop = true;
+      break;
+    }
+    const Rec& rc = recs[ord[q]];
+    if (rc.mv < 0) continue;
+    annotate_row(T.rows[q], g0, P.moves[rc.mv].p1, P.moves[rc.mv].p2);
+  }
+  finish_table(T);
+  return P;
+}
+
+void fill_prepass_summary(nw_region_summary& S, const PrepassOut& P) {
+  S.search_depth = P.maxdepth;
+  S.mut_simulated = S.mut_tested = (int64_t)P.table->rows.size();
+  S.flipped = P.did_flip;
+  S.flip_unsure = P.unsure;
+  S.cluttered = P.cluttered;
+  S.prepass_candidates = P.n_cand;
+  S.prepass_dp = P.n_dp;
+  S.gpu_launches = P.launches;
+  if (P.cluttered) {
+    S.search_depth = 0;
+    S.mut_simulated = S.mut_tested = 0;
+  }
+}
+
+int rguard(const std::function<void()>& fn) {
+  try {
+    fn();
+    return NW_OK;
+  } catch (const RErr& e) {
+    nw::set_last_error(e.msg);
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    nw::set_last_error("host out of memory");
+    return NW_ERR_NOMEM;
+  } catch (const std::exception& e) {
+    nw::set_last_error(e.what());
+    return NW_ERR_ARG;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+void nw_region_default_opts(nw_region_opts* o) {
+  if (!o) return;
+  o->depth = 3;
+  o->maxdup = 2;
+  o->init_width = 1000;
+  o->minreport = 0.98;
+  o->compression = 1000;
+  o->flags = 0;
+  o->reserved = 0;
+}
+
+int nw_region_prepass(nw_ctx* ctx, const int64_t* grid, int32_t n_x, int32_t n_y, const int64_t* len_x,
+                      const int64_t* len_y, const nw_region_opts* opts, nw_table** out, nw_region_summary* summary) {
+  if (out) *out = nullptr;
+  return rguard([&] {
+    if (!ctx || !opts || !out) rfail(NW_ERR_ARG, "null argument");
+    const Grid g = make_grid(grid, n_x, n_y, len_x, len_y);
+    PrepassOut P = run_prepass(ctx, g, *opts);
+    fill_prepass_summary(P.table->summ, P);
+    if (summary) *summary = P.table->summ;
+    *out = P.table.release();
+  });
+}
+
+int nw_region_format(const char* tsv, int64_t tsv_len, const double* gridlines_x, int32_t n_gridlines, nw_table** out) {
+  if (out) *out = nullptr;
+  return rguard([&] {
+    if (!tsv || tsv_len < 0 || !out || (n_gridlines > 0 && !gridlines_x)) rfail(NW_ERR_ARG, "null argument");
+    *out = format_solver_output(tsv, tsv_len, gridlines_x, n_gridlines);
+  });
+}
+
+int nw_region_analyse(nw_ctx* ctx, const int64_t* grid, int32_t n_x, int32_t n_y, const int64_t* len_x,
+                      const int64_t* len_y, const double* gridlines_x, int32_t n_gridlines,
+                      const nw_region_opts* opts, nw_table** out, nw_region_summary* summary) {
+  if (out) *out = nullptr;
+  return rguard([&] {
+    if (!ctx || !opts || !out || (n_gridlines > 0 && !gridlines_x)) rfail(NW_ERR_ARG, "null argument");
+    const Grid g0 = make_grid(grid, n_x, n_y, len_x, len_y);
+    PrepassOut P = run_prepass(ctx, g0, *opts);
+    nw_region_summary S{};
+    fill_prepass_summary(S, P);
+    std::unique_ptr<nw_table> T = std::move(P.table);
+    T->summ.n_rows = (int32_t)T->rows.size();
+    double mx = -INFINITY;
+    for (const auto& r : T->rows) mx = std::max(mx, r.eval);
+    if (!P.cluttered && mx < 99.8) {  // wrapper :177
+      S.solver_called = 1;
+      const Grid& g = P.flipped;
+      // berzerk guard (R/juliasolver.R:9-30) on the flipped matrix
+      double width = opts->init_width;
+      {
+        int64_t ndup = 0, longest = std::numeric_limits<int64_t>::min();
+        for (const Move& m : P.moves)
+          if (m.sv == 1) {
+            ++ndup;
+            longest = std::max<int64_t>(longest, m.p2 - m.p1);
+          }
+        const size_t nm = P.moves.size();
+        if (nm > 400 || (nm > 200 && longest > 40 && ndup > 40)) {
+          width = width / 10;
+          S.width_reduced = 1;
+        }
+      }
+      std::vector<int8_t> aln((size_t)g.nx * g.ny);
+      for (int x = 0; x < g.nx; ++x)
+        for (int y = 0; y < g.ny; ++y) {
+          const int64_t t = g.at(y, x);
+          aln[(size_t)x * g.ny + y] = (int8_t)(t > 0 ? 1 : t < 0 ? -1 : 0);
+        }
+      nw_opts so;
+      nw_default_opts(&so);
+      so.maxdepth = opts->depth;
+      so.maxdup = opts->maxdup;
+      so.maxwidth = (int64_t)width;  // the command line carries paste0(width): "100", "1000"
+      so.minreport = opts->minreport;
+      so.maxreport = 1000;  // -R 1000 (R/juliasolver.R:48)
+      so.flags = opts->flags;
+      nw_result* res = nullptr;
+      NWCK(nw_solve(ctx, aln.data(), g.nx, g.ny, g.cn.data(), g.rn.data(), &so, &res));
+      std::unique_ptr<nw_table> J;
+      nw_stats st{};
+      try {
+        const char* data = nullptr;
+        int64_t len = 0;
+        NWCK(nw_result_tsv(res, &data, &len));
+        NWCK(nw_result_stats(res, &st));
+        J.reset(format_solver_output(data, len, gridlines_x, n_gridlines));
+      } catch (...) {
+        nw_result_free(res);
+        throw;
+      }
+      nw_result_free(res);
+      S.gpu_launches += st.kernel_launches;
+      S.search_depth = opts->depth;  // format_julia_output overwrites the log counters (R/juliasolver.R:63-65, :107-111)
+      if (J->kind == 2) {
+        S.mut_simulated = S.mut_tested = 0;
+      } else {
+        S.mut_simulated = S.mut_tested = (int64_t)J->rows.size();
+      }
+      if (!(J->kind == 2 && J->rows.size() == 1)) {  // !all(dim(res_julia) == c(1, 3))
+        bool has_ref = false;
+        for (const auto& r : J->rows) has_ref |= (!r.mut.empty() && r.mut[0] == "ref");
+        if (!has_ref) {
+          double ref_eval = kNA;
+          for (const auto& r : T->rows)
+            if (r.mut[0] == "ref") ref_eval = r.eval;
+          nw_table::Row r;
+          r.eval = ref_eval;
+          r.mut.assign(J->n_mut, "");
+          r.mut[0] = "ref";
+          r.num.assign(J->rows.empty() ? 0 : J->rows[0].num.size(), kNA);
+          J->rows.push_back(std::move(r));
+          sort_eval_na(*J);
+        }
+        T = std::move(J);
+      }
+    }
+    finish_table(*T);
+    const nw_region_summary F = T->summ;  // res_ref, res_max, n_res_max, maxres, shape
+    S.res_ref = F.res_ref;
+    S.res_max = F.res_max;
+    S.n_res_max = F.n_res_max;
+    S.n_rows = F.n_rows;
+    S.n_mut = F.n_mut;
+    memcpy(S.maxres, F.maxres, sizeof S.maxres);
+    T->summ = S;
+    if (summary) *summary = S;
+    *out = T.release();
+  });
+}
+
+int nw_table_summary(const nw_table* t, nw_region_summary* out) {
+  if (!t || !out) {
+    nw::set_last_error("null argument");
+    return NW_ERR_ARG;
+  }
+  *out = t->summ;
+  return NW_OK;
+}
+const char* nw_table_mut_max(const nw_table* t) { return t ? t->mut_max.c_str() : ""; }
+int nw_table_tsv(const nw_table* t, const char** data, int64_t* len) {
+  if (!t || !data || !len) {
+    nw::set_last_error("null argument");
+    return NW_ERR_ARG;
+  }
+  *data = t->tsv.data();
+  *len = (int64_t)t->tsv.size();
+  return NW_OK;
+}
+int64_t nw_table_candidates(const nw_table* t, const nw_candidate** out) {
+  if (!t || !out) return 0;
+  *out = t->cands.data();
+  return (int64_t)t->cands.size();
+}
+int32_t nw_table_rows(const nw_table* t) { return t ? (int32_t)t->rows.size() : 0; }
+void nw_table_free(nw_table* t) { delete t; }
+
+}  // extern "C"

@@ -171,7 +171,9 @@ class Solver:
 
     def score_batch(self, aln, len_x, len_y, seqs, force=False, generic_dp=False):
         """slow_score (solver.jl:329-376) for raw candidate indices.  Returns (score f64, cost_bp, total_bp);
-        cost_bp == -1: early exit (score 0.0, no DP), -2: unreachable (score -inf)."""
+        cost_bp == -1: early exit (score 0.0, no DP), -2: unreachable (score -inf).
+        force: 0/False = slow_score; 1/True = the R twin's forcecalc branch (corridor 1.0, no early exit,
+        R/evaltools.R:203-205); 2 = the R twin without forcecalc (corridor chosen by n_y, R/evaltools.R:193-201)."""
         aln, lx, ly = self._problem(aln, len_x, len_y)
         n = len(seqs)
         off = np.zeros(n + 1, np.int64)
@@ -184,7 +186,7 @@ class Solver:
         total = np.zeros(n, np.int64)
         score = np.zeros(n, np.float64)
         _lib.check(self.L.nw_score_batch(self.h, _p(aln), aln.shape[0], aln.shape[1], _p(lx), _p(ly), _p(flat), _p(off),
-                                         n, 1 if force else 0, _lib.FLAG_GENERIC_DP if generic_dp else 0, _p(cost),
+                                         n, int(force), _lib.FLAG_GENERIC_DP if generic_dp else 0, _p(cost),
                                          _p(total), _p(score)))
         return score, cost, total
 

@@ -58,7 +58,7 @@ int h_score_fast(const int8_t* aln, int n_x, int n_y, const int64_t* len_x, cons
   RegionHost R = build_region(aln, n_x, n_y, len_x, len_y, 4);
   const int Lc = child_len(L, kind, p, q);
   if (!force && early_exit(Lc, n_y)) return -1;
-  BandTable T = build_band(Lc, n_y, force != 0, WINDOW_MAX);
+  BandTable T = build_band(Lc, n_y, force, WINDOW_MAX);
   if (!T.fast_ok) return 0;
   static const int wins[] = {8, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64, 72, 80, 96, 112, 128};
   int W = 0;
@@ -130,7 +130,7 @@ void h_fp(const int16_t* seq, int L, uint32_t* out4) {
 
 // band geometry: cells, fast_ok, max_width
 void h_band(int L, int n_y, int force, int64_t* cells, int* fast_ok, int* max_width, int* contiguous) {
-  BandTable T = build_band(L, n_y, force != 0, WINDOW_MAX);
+  BandTable T = build_band(L, n_y, force, WINDOW_MAX);
   *cells = T.cells;
   *fast_ok = T.fast_ok;
   *max_width = T.max_width;
@@ -142,8 +142,8 @@ int h_band_check(int L, int n_y, int force) {
   std::vector<BandRowHost> r1, r2;
   int64_t c1 = 0, c2 = 0;
   bool k1 = true, k2 = true;
-  band_rows_bruteforce(L, n_y, force != 0, r1, c1, k1);
-  band_rows_fast(L, n_y, corridor_pct(L, force != 0), r2, c2, k2);
+  band_rows_bruteforce(L, n_y, force, r1, c1, k1);
+  band_rows_fast(L, n_y, corridor_pct(L, force, n_y), r2, c2, k2);
   if (c1 != c2 || k1 != k2) return 0;
   if (!k1) return 1;  // non-contiguous rows go to the generic kernel, which uses only (a, b) of contiguous tables
   for (int i = 1; i <= L; ++i)

@@ -1,0 +1,126 @@
+"""GPU parity tests of the region steps (include/nwregion.h): the depth-1 pre-pass and the
+whole solver stage of a region through the C ABI vs the R restatement (oracle/nw_region_oracle.py) on identical
+gridmatrices -- every row of the result table, the log counters and the logfile summary."""
+import os
+
+import numpy as np
+import pytest
+
+import nahrwhals_b200 as nb
+from nahrwhals_b200.sdgrid import random_grid, sdgrid
+from oracle import nw_region_oracle as ro
+from tests.test_region_oracle import _rows_equal, load_testrun, oracle_solver
+
+pytestmark = pytest.mark.gpu
+
+
+def check_prepass(solver, mat, ly, lx, compression=1000, generic=False):
+    O = ro.solve_mutation_depth1(ro.Bitl(mat, ly, lx), compression)
+    P = nb.solve_mutation_depth1(solver, mat, ly, lx, compression=compression, generic_dp=generic)
+    _rows_equal(P.rows, O["res"])
+    if O["log"].get("cluttered_boundaries"):
+        assert P.log["cluttered_boundaries"]
+        return O, P
+    # every depth-1 child, whether or not the reference's sequential filters would have looked at it: the GPU's
+    # estimate sums and DP result vs the R restatement applied to the child matrix carry_out_compressed_sv builds
+    bf = ro.flip_bitl_y_if_needed(ro.Bitl(mat, ly, lx))[0]
+    moves = ro.find_sv_opportunities(bf)
+    assert [c[:3] for c in P.candidates] == moves
+    for c, (p1, p2, sv) in zip(P.candidates, moves):
+        child = ro.carry_out_compressed_sv(bf, p1, p2, sv)
+        assert c[3] == child.ncol
+        if child.ncol < 2:
+            continue
+        st = ro.ScorerState()
+        det = {}
+        s = ro.calc_coarse_grained_aln_score(child, st, forcecalc=False, orig_symm=0.0, detail=det)
+        est = st.est_highest          # with est_highest = 0 before the call this is the child's own estimate
+        assert ((c[4] + c[5]) / (sum(child.rn) + sum(child.cn))) * 100 == est, (p1, p2, sv)
+        if det:
+            assert (c[6], c[7], c[8]) == (det["cost"], det["total"], s), (p1, p2, sv)
+        else:
+            assert c[6] == -2 and s == 1.0, (p1, p2, sv)
+    assert P.log["depth"] == O["log"]["depth"] and P.log["mut_simulated"] == O["log"]["mut_simulated"]
+    assert P.prepass_dp == O["state"].n_eval_calc - 1
+    assert P.gpu_launches >= 2
+    return O, P
+
+
+def check_region(solver, oracle, mat, ly, lx, **kw):
+    gl = np.concatenate([[0], np.cumsum(lx)])
+    O = ro.analyse_region(mat, ly, lx, gl, oracle_solver(oracle), **kw)
+    P = nb.analyse_region(solver, mat, ly, lx, gl, **kw)
+    _rows_equal(P.rows, O["res"])
+    assert P.solver_called == O["julia_called"]
+    assert P.mut_max == O["mut_max"]
+    assert (P.res_max, P.n_res_max) == (O["res_max"], O["n_res_max"])
+    assert P.res_ref == O["res_ref"]
+    for k, v in O["log"].items():
+        assert P.log[k] == v, (k, P.log, O["log"])
+    for k, v in P.maxres.items():
+        assert v == O["maxres"].get(k), (k, P.maxres, O["maxres"])
+    return O, P
+
+
+def test_testrun_readme_row(solver, oracle):
+    """README.md:135-139 through the CUDA path: res_ref 71.378, res_max 99.595, mut_max 4_12_inv+11_18_del."""
+    mat, ly, lx = load_testrun()
+    O, P = check_prepass(solver, mat, ly, lx)
+    assert P.res_ref == 71.378 and P.res_max == 82.114
+    O, P = check_region(solver, oracle, mat, ly, lx, depth=2)
+    assert (P.res_ref, P.res_max, P.mut_max) == (71.378, 99.595, "4_12_inv+11_18_del")
+    O, P = check_region(solver, oracle, mat, ly, lx, depth=3)
+    assert P.res_max == 100.0 and P.solver_called
+
+
+@pytest.mark.parametrize("seed", range(1, 13))
+def test_prepass_sdgrid(solver, seed):
+    fams = [[3, 2], [4, 3, 2], [5, 4, 3], [6, 4, 4, 3]][seed % 4]
+    n_x = 10 + 4 * seed
+    mat, lx, ly, _ = sdgrid(n_x, fams, chain_depth=1 + seed % 3, seed=seed)
+    check_prepass(solver, mat, ly, lx, generic=(seed % 5 == 0))
+    # upside-down y axis: flip_bitl_y_if_needed has to undo it (and the row names flip with the rows)
+    check_prepass(solver, -mat[::-1], ly[::-1], lx, compression=10000)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_prepass_random_grids(solver, seed):
+    """Unstructured grids: repeats touching the first / last block (border cases of carry_out_compressed_sv and its
+    colname repairs -> virtual blocks), short (n_y < 10: full estimate band, threshold 0.9) and lopsided shapes."""
+    shapes = [(6, 5), (9, 8), (14, 9), (12, 20), (25, 25), (33, 30), (40, 12), (8, 30)]
+    n_x, n_y = shapes[seed]
+    mat, lx, ly = random_grid(n_x, n_y, 0.12 if n_x > 20 else 0.25, seed)
+    O, P = check_prepass(solver, mat, ly, lx)
+    if not P.log["cluttered_boundaries"]:
+        assert P.prepass_candidates == len(ro.find_sv_opportunities(ro.flip_bitl_y_if_needed(ro.Bitl(mat, ly, lx))[0]))
+
+
+def test_prepass_cluttered_and_tiny(solver):
+    mat, lx, ly = random_grid(12, 12, 0.05, 3)
+    mat[0, 1:8] = lx[1:8]                       # five or more dots on a border: is_cluttered
+    O, P = check_prepass(solver, mat, ly, lx)
+    assert P.log["cluttered_boundaries"] and P.rows[0]["mut1"] == "ref" and P.rows[0]["eval"] == 0.0
+    m = np.array([[5, 5], [0, 5]], dtype=np.int64) * 1000   # 2 x 2: deletion leaves a single column
+    check_prepass(solver, m, np.array([5000, 5000]), np.array([5000, 5000]))
+    with pytest.raises(Exception):
+        nb.solve_mutation_depth1(solver, m[:1], np.array([5000]), np.array([5000, 5000]))
+
+
+@pytest.mark.parametrize("seed", range(1, 9))
+def test_region_sdgrid(solver, oracle, seed):
+    """The whole solver stage: pre-pass, 99.8 gate, flip, solver, format_julia_output, ref row, summary."""
+    fams = [[3, 2], [4, 3], [4, 3, 2]][seed % 3]
+    mat, lx, ly, _ = sdgrid(12 + 5 * seed, fams, chain_depth=1 + seed % 3, seed=100 + seed)
+    check_region(solver, oracle, mat, ly, lx, depth=3, init_width=200)
+    check_region(solver, oracle, -mat[::-1], ly[::-1], lx, depth=2, minreport=0.9)
+
+
+def test_region_solved_by_prepass(solver, oracle):
+    """A region the depth-1 pre-pass solves (>= 99.8) never reaches the solver."""
+    for seed in range(1, 30):
+        mat, lx, ly, hidden = sdgrid(20, [2], chain_depth=1, seed=seed)
+        O, P = check_region(solver, oracle, mat, ly, lx)
+        if not P.solver_called:
+            assert P.res_max >= 99.8
+            return
+    pytest.fail("no single-move region found")

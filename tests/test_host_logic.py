@@ -177,6 +177,12 @@ def test_library_exports_declared_symbols():
     for s in declared:
         assert getattr(L, s) is not None
     assert b"sm_100a" in L.nw_version()
+    from nahrwhals_b200 import region
+    hdr = open(os.path.join(ROOT, "include", "nwregion.h")).read()
+    declared = set(re.findall(r"\b(nw_(?:region|table)_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(region.SYMBOLS)
+    for s in declared:
+        assert getattr(L, s) is not None
 
 
 def test_read_problem_accepts_r_number_formats(tmp_path):
