@@ -1979,6 +1979,12 @@ void do_solve(nw_ctx* c, const int8_t* aln, int n_x, int n_y, const int64_t* len
 
 // internal hooks for the other translation units of the library (nw_region.cu)
 namespace nw {
+struct ScoreProblem {
+  const int8_t* aln;  // n_x*n_y, x-major
+  int n_x, n_y;
+  const int64_t* len_x;
+  const int64_t* len_y;
+};
 void set_last_error(const std::string& m) { g_last_error = m; }
 int ctx_device(nw_ctx* c) { return c->device; }
 cudaStream_t ctx_stream(nw_ctx* c) { return c->stream; }
@@ -2279,10 +2285,16 @@ int nw_result_edges(const nw_result* r, int32_t* child, int32_t* parent, int32_t
 }
 void nw_result_free(nw_result* r) { delete r; }
 
-int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const int64_t* len_x, const int64_t* len_y,
-                   const int16_t* flat, const int64_t* off, int64_t n, int32_t force, int32_t flags, int64_t* cost_bp,
-                   int64_t* total_bp, double* score) {
-  if (!c || !aln || !len_x || !len_y || !flat || !off || n < 0) {
+}  // extern "C" (reopened below)
+
+// Scores n raw candidate indices that belong to R regions (rid[k] = region of candidate k; nullptr: all region 0)
+// through the banded-DP kernels in ONE bucketed pass.  nw_score_batch is the R == 1 case; the region pre-pass
+// (nw_region.cu) hands in the depth-1 children of a whole batch of regions at once.
+namespace nw {
+int score_batch_regions(nw_ctx* c, const ScoreProblem* probs, int R, const uint16_t* rid, const int16_t* flat,
+                        const int64_t* off, int64_t n, int force, int flags, int64_t* cost_bp, int64_t* total_bp,
+                        double* score) {
+  if (!c || !probs || R < 1 || !flat || !off || n < 0) {
     g_last_error = "null argument";
     return NW_ERR_ARG;
   }
@@ -2294,21 +2306,24 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
     if (force < 0 || force > 2) fail(NW_ERR_ARG, "force must be 0 (slow_score), 1 (forcecalc) or 2 (R twin corridor)");
     cudaStream_t s = c->stream;
     int maxlen = 1;
+    int depth_equiv = 0;  // depth bound for the int32 range: candidates may hold each block up to len/n_x times
     for (int64_t k = 0; k < n; ++k) {
+      const int r = rid ? rid[k] : 0;
+      if (r >= R) fail(NW_ERR_ARG, "candidate region out of range");
+      const int n_x = probs[r].n_x;
       const int64_t l = off[k + 1] - off[k];
       if (l < 1 || l > LMAX) fail(NW_ERR_ARG, "candidate length out of range");
       maxlen = std::max<int>(maxlen, (int)l);
+      while (((int64_t)n_x << depth_equiv) < l) ++depth_equiv;
       for (int64_t t = off[k]; t < off[k + 1]; ++t) {
         const int v = flat[t];
         if (v == 0 || v > n_x || v < -n_x) fail(NW_ERR_ARG, "candidate element out of range");
       }
     }
-    // depth bound for the int32 range: candidates may hold each block up to maxlen/n_x times
-    int depth_equiv = 0;
-    while (((int64_t)n_x << depth_equiv) < maxlen) ++depth_equiv;
     {
-      const ProblemRef P{aln, n_x, n_y, len_x, len_y};
-      setup_regions(c, &P, 1, depth_equiv, force);
+      std::vector<ProblemRef> P(R);
+      for (int r = 0; r < R; ++r) P[r] = ProblemRef{probs[r].aln, probs[r].n_x, probs[r].n_y, probs[r].len_x, probs[r].len_y};
+      setup_regions(c, P.data(), R, depth_equiv, force);
     }
     // candidates as a "frontier" of n parents scored through KIND_ID descriptors
     Level L;
@@ -2330,6 +2345,7 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
       desc[k] = pack_desc((uint32_t)k, 0, 0, KIND_ID);
       newlist[k] = (uint32_t)k;
       nlen[k] = (uint16_t)l;
+      if (rid) nrid[k] = rid[k];
     }
     L.G = (uint32_t)n;
     L.n_new = (uint32_t)n;
@@ -2348,14 +2364,15 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
     {
       ScoreView V = view_of(L);
       V.F.regions = c->d_regions.as<RegionDev>();
-      V.F.rid = nullptr;
-      int* dummy_best = (int*)c->best.ensure(16);
-      CK(cudaMemsetAsync(dummy_best, 0, 8, s));
-      const size_t nbins = (size_t)lcap * NSUB;
+      V.F.rid = R > 1 ? L.nrid.as<uint16_t>() : nullptr;  // every candidate is its own "parent": same region array
+      int* dummy_best = (int*)c->best.ensure((size_t)R * 8 + 16);
+      CK(cudaMemsetAsync(dummy_best, 0, (size_t)R * 8 + 16, s));
+      const size_t nbins = (size_t)R * lcap * NSUB;
+      if (nbins > ((size_t)64 << 20)) fail(NW_ERR_NOMEM, "too many (region, length) buckets in one batch");
       uint32_t* hist = (uint32_t*)c->hist.ensure(nbins * 4, true);
       CK(cudaMemsetAsync(hist, 0, nbins * 4, s));
-      c->launches += launch_len_hist(c->new_len.as<uint16_t>(), nullptr, c->d_regions.as<RegionDev>(), lcap, (uint32_t)n,
-                                     force, hist, s);
+      c->launches += launch_len_hist(c->new_len.as<uint16_t>(), R > 1 ? L.nrid.as<uint16_t>() : nullptr,
+                                     c->d_regions.as<RegionDev>(), lcap, (uint32_t)n, force, hist, s);
       run_scoring(c, V, hist, lcap, L.nrid.as<uint16_t>(), force, flags, dummy_best, nullptr);
     }
     d2h(c, k3.data(), L.k3.p, n * 4);
@@ -2364,13 +2381,28 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
     CK(spin_sync(s));
     CK(cudaGetLastError());
     for (int64_t k = 0; k < n; ++k) {
-      if (cost_bp) cost_bp[k] = cost[k] < 0 ? cost[k] : (int64_t)cost[k] * c->RH[0].gcd;
-      if (total_bp) total_bp[k] = (int64_t)total[k] * c->RH[0].gcd;
+      const int64_t g = c->RH[rid ? rid[k] : 0].gcd;
+      if (cost_bp) cost_bp[k] = cost[k] < 0 ? cost[k] : (int64_t)cost[k] * g;
+      if (total_bp) total_bp[k] = (int64_t)total[k] * g;
       if (score) score[k] = k3[k] < 0 ? -INFINITY : k3_to_score(k3[k]);
     }
   });
   if (rc != NW_OK) cudaGetLastError();
   return rc;
+}
+}  // namespace nw
+
+extern "C" {
+
+int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const int64_t* len_x, const int64_t* len_y,
+                   const int16_t* flat, const int64_t* off, int64_t n, int32_t force, int32_t flags, int64_t* cost_bp,
+                   int64_t* total_bp, double* score) {
+  if (!c || !aln || !len_x || !len_y || !flat || !off || n < 0) {
+    g_last_error = "null argument";
+    return NW_ERR_ARG;
+  }
+  const nw::ScoreProblem P{aln, n_x, n_y, len_x, len_y};
+  return nw::score_batch_regions(c, &P, 1, nullptr, flat, off, n, force, flags, cost_bp, total_bp, score);
 }
 
 int nw_moveset(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, uint8_t* dup_del, uint8_t* invert) {

@@ -29,6 +29,15 @@ void set_last_error(const std::string& m);
 int ctx_device(nw_ctx* c);
 cudaStream_t ctx_stream(nw_ctx* c);
 int ctx_launches(nw_ctx* c);
+struct ScoreProblem {
+  const int8_t* aln;  // n_x*n_y, x-major
+  int n_x, n_y;
+  const int64_t* len_x;
+  const int64_t* len_y;
+};
+int score_batch_regions(nw_ctx* c, const ScoreProblem* probs, int R, const uint16_t* rid, const int16_t* flat,
+                        const int64_t* off, int64_t n, int force, int flags, int64_t* cost_bp, int64_t* total_bp,
+                        double* score);
 }  // namespace nw
 
 namespace {
@@ -54,14 +63,17 @@ struct RErr {
 // ---------------------------------------------------------------------------------------------------------------
 // GPU: estimate pre-filter of every child (calculate_estimated_aln_score, R/evaltools.R:51-71).
 //   matdiag = mat * (|row - col| < ncol * fact);  sum(rowMaxs(matdiag)) + sum(colMaxs(matdiag))
-// One warp per child.  The child matrix is read through its position list: mat[y][p] = sign(blk_p) * grid[y][|blk_p|].
+// One warp per entry (child or reference arrangement) of any region of the batch.  The child matrix is read through its position list: mat[y][p] = sign(blk_p) * grid[y][|blk_p|].
 // fact = 1 when n_y < 10 (|d| < L), else 0.25 (|d| < L/4  <=>  4|d| < L, exact in integers).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_est_diag(const int64_t* __restrict__ grid, int n_x, int n_y,
+__global__ void __launch_bounds__(256) k_est_diag(const int64_t* __restrict__ grid_all, const int4* __restrict__ meta,
                                                   const int16_t* __restrict__ blk, const int64_t* __restrict__ off,
-                                                  int n, long long* __restrict__ sum_rows, long long* __restrict__ sum_cols) {
+                                                  int n, long long* __restrict__ out /* [n][2]: rows, cols */) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= n) return;
+  const int4 mt = meta[w];  // grid offset (lo, hi), n_x, n_y of the entry's region
+  const int64_t* grid = grid_all + (((long long)(unsigned)mt.x) | ((long long)mt.y << 32));
+  const int n_x = mt.z, n_y = mt.w;
   const int16_t* b = blk + off[w];
   const int L = (int)(off[w + 1] - off[w]);
   const int fm = n_y < 10 ? 1 : 4;  // diagonalize_fact 1 (dim(mat)[1] < 10) or 0.25
@@ -104,8 +116,8 @@ __global__ void __launch_bounds__(256) k_est_diag(const int64_t* __restrict__ gr
     sc += __shfl_xor_sync(0xffffffffu, sc, o);
   }
   if (lane == 0) {
-    sum_rows[w] = sr;
-    sum_cols[w] = sc;
+    out[(size_t)w * 2] = sr;
+    out[(size_t)w * 2 + 1] = sc;
   }
 }
 
@@ -587,12 +599,21 @@ nw_table* format_solver_output(const char* tsv, int64_t len, const double* gl, i
 // ---------------------------------------------------------------------------------------------------------------
 struct PrepassOut {
   std::unique_ptr<nw_table> table;
-  Grid flipped;
+  Grid g0, flipped;
   bool did_flip = false, unsure = false, cluttered = false;
   std::vector<Move> moves;  // find_sv_opportunities of the flipped matrix
   int64_t n_cand = 0, n_dp = 0;
   int maxdepth = 1;
   int launches = 0;
+  // --- work of one region between its three phases (host prepare -> GPU batch -> host replay) ---
+  std::vector<Arr> cand;                   // children of the reference arrangement (cand[k-1] <-> entry k)
+  std::vector<std::vector<int16_t>> seqs;  // entry 0 = the reference arrangement; block ids incl. virtual blocks
+  std::vector<int64_t> lenx;               // x lengths incl. one virtual block per (block, length) a colname repair made
+  std::vector<int8_t> aln;                 // sign matrix of those blocks, x-major
+  int nxa = 0;
+  std::vector<long long> srow, scol;       // estimate sums per entry
+  std::vector<int64_t> ccost, ctotal;      // DP per entry (entry 0: forced, full corridor)
+  std::vector<double> cscore;
 };
 
 Grid make_grid(const int64_t* grid, int n_x, int n_y, const int64_t* len_x, const int64_t* len_y) {
@@ -633,46 +654,44 @@ void annotate_row(nw_table::Row& r, const Grid& g, int p1, int p2) {
   r.num[4] = hi - mean;
 }
 
-PrepassOut run_prepass(nw_ctx* ctx, const Grid& g0, const nw_region_opts& o) {
-  PrepassOut P;
+nw_table::Row& add_row(nw_table& T, double ev, const std::string& mut1) {
+  nw_table::Row r;
+  r.eval = ev;
+  r.mut = {mut1};
+  r.num.assign(9, kNA);
+  T.rows.push_back(std::move(r));
+  return T.rows.back();
+}
+
+// Phase 1 (host): clutter test, flip, moves, children, and the problem handed to the DP kernels: the x blocks of the
+// flipped matrix plus one virtual block per (block, length) pair that a colname repair created.
+void prepass_prepare(PrepassOut& P, Grid&& g0in) {
+  P.g0 = std::move(g0in);
   P.table.reset(new nw_table);
   nw_table& T = *P.table;
   T.kind = 0;
   T.n_mut = 1;
-  auto add_row = [&](double ev, const std::string& mut1) -> nw_table::Row& {
-    nw_table::Row r;
-    r.eval = ev;
-    r.mut = {mut1};
-    r.num.assign(9, kNA);
-    T.rows.push_back(std::move(r));
-    return T.rows.back();
-  };
-  if (is_cluttered(g0)) {  // explore_mutation_space_v2.R:27-33
+  if (is_cluttered(P.g0)) {  // explore_mutation_space_v2.R:27-33
     P.cluttered = true;
-    add_row(0.0, "ref");
-    P.flipped = g0;
+    add_row(T, 0.0, "ref");
+    P.flipped = P.g0;
     finish_table(T);
-    return P;
+    return;
   }
-  P.flipped = flip_if_needed(g0, P.did_flip, P.unsure);
+  P.flipped = flip_if_needed(P.g0, P.did_flip, P.unsure);
   const Grid& g = P.flipped;
   P.moves = find_sv_opportunities(g);
-  // reduce_depth_if_needed (helpers.R:318-347) with maxdepth_input = 1
-  P.maxdepth = P.moves.size() > 2000 ? 0 : 1;
+  P.maxdepth = P.moves.size() > 2000 ? 0 : 1;  // reduce_depth_if_needed (helpers.R:318-347), maxdepth_input = 1
   const int n = g.nx;
   Arr root(n);
   for (int i = 0; i < n; ++i) root[i] = Pos{(int16_t)(i + 1), g.cn[i]};
-  std::vector<Arr> cand;
   if (P.maxdepth >= 1)
-    for (const Move& m : P.moves) cand.push_back(carry_out(root, m));
-  P.n_cand = (int64_t)cand.size();
-
-  // ---- problem handed to the DP kernels: x blocks of the flipped matrix plus one virtual block per (block, length)
-  //      pair that a colname repair created ----
-  std::vector<int64_t> lenx(g.cn);
+    for (const Move& m : P.moves) P.cand.push_back(carry_out(root, m));
+  P.n_cand = (int64_t)P.cand.size();
+  P.lenx = g.cn;
   std::vector<int> vsrc;  // source block of every virtual block
   std::map<std::pair<int, int64_t>, int> vmap;
-  std::vector<std::vector<int16_t>> seqs(cand.size() + 1);
+  P.seqs.assign(P.cand.size() + 1, {});
   auto to_seq = [&](const Arr& a, std::vector<int16_t>& s) {
     s.resize(a.size());
     for (size_t p = 0; p < a.size(); ++p) {
@@ -681,9 +700,9 @@ PrepassOut run_prepass(nw_ctx* ctx, const Grid& g0, const nw_region_opts& o) {
       if (a[p].len != g.cn[b - 1]) {
         auto it = vmap.find({b, a[p].len});
         if (it == vmap.end()) {
-          lenx.push_back(a[p].len);
+          P.lenx.push_back(a[p].len);
           vsrc.push_back(b);
-          it = vmap.emplace(std::make_pair(b, a[p].len), (int)lenx.size()).first;
+          it = vmap.emplace(std::make_pair(b, a[p].len), (int)P.lenx.size()).first;
         }
         id = it->second;
       }
@@ -691,111 +710,149 @@ PrepassOut run_prepass(nw_ctx* ctx, const Grid& g0, const nw_region_opts& o) {
       s[p] = (int16_t)(a[p].blk < 0 ? -id : id);
     }
   };
-  to_seq(root, seqs[0]);
-  for (size_t k = 0; k < cand.size(); ++k) to_seq(cand[k], seqs[k + 1]);
-  const int nxa = (int)lenx.size();
-  std::vector<int8_t> aln((size_t)nxa * g.ny);
-  for (int x = 0; x < nxa; ++x) {
+  to_seq(root, P.seqs[0]);
+  for (size_t k = 0; k < P.cand.size(); ++k) to_seq(P.cand[k], P.seqs[k + 1]);
+  P.nxa = (int)P.lenx.size();
+  P.aln.resize((size_t)P.nxa * g.ny);
+  for (int x = 0; x < P.nxa; ++x) {
     const int src = x < n ? x : vsrc[x - n] - 1;
     for (int y = 0; y < g.ny; ++y) {
       const int64_t t = g.at(y, src);
-      aln[(size_t)x * g.ny + y] = (int8_t)(t > 0 ? 1 : t < 0 ? -1 : 0);
+      P.aln[(size_t)x * g.ny + y] = (int8_t)(t > 0 ? 1 : t < 0 ? -1 : 0);
     }
   }
+  const size_t ne = P.cand.size() + 1;
+  P.srow.assign(ne, 0);
+  P.scol.assign(ne, 0);
+  P.ccost.assign(ne, -1);
+  P.ctotal.assign(ne, 0);
+  P.cscore.assign(ne, 0.0);
+}
+
+// Phase 2 (GPU), for a whole batch of regions: ONE estimate launch over every entry of every region, one DP pass over
+// all reference arrangements (forced corridor) and one over all children (R-twin corridor).
+void prepass_gpu(nw_ctx* ctx, std::vector<PrepassOut*>& Ps, int flags, int& launches) {
+  std::vector<PrepassOut*> live;
+  for (PrepassOut* P : Ps)
+    if (!P->cluttered) live.push_back(P);
+  if (live.empty()) return;
+  if (live.size() > 60000) rfail(NW_ERR_ARG, "too many regions in one pre-pass batch");
   const int L0 = nw::ctx_launches(ctx);
-  // ---- GPU 1: forced score of the reference arrangement (dfsutil: forcecalc = (pair$sv == "ref")) ----
-  int64_t cost = 0, total = 0;
-  double s_ref = 0;
+  // ---- estimate sums ----
   {
-    const int64_t off[2] = {0, (int64_t)seqs[0].size()};
-    NWCK(nw_score_batch(ctx, aln.data(), nxa, g.ny, lenx.data(), g.rn.data(), seqs[0].data(), off, 1, 1, o.flags & NW_FLAG_GENERIC_DP,
-                        &cost, &total, &s_ref));
-    if (cost == -2) s_ref = 1.0;  // R/evaltools.R:259-261 (cannot happen with the full corridor)
-  }
-  // ---- GPU 2 + 3: estimate sums and DP of every child ----
-  const size_t nc = cand.size();
-  std::vector<int64_t> off(nc + 2, 0);
-  std::vector<int16_t> flat_dp, flat_blk;
-  for (size_t k = 0; k <= nc; ++k) {  // entry 0 = the reference arrangement (its estimate seeds est_highest)
-    const Arr& a = k ? cand[k - 1] : root;
-    off[k + 1] = off[k] + (int64_t)a.size();
-    for (const Pos& p : a) flat_blk.push_back(p.blk);
-    flat_dp.insert(flat_dp.end(), seqs[k].begin(), seqs[k].end());
-  }
-  std::vector<long long> srow(nc + 1), scol(nc + 1);
-  std::vector<int64_t> ccost(nc + 1, -1), ctotal(nc + 1, 0);
-  std::vector<double> cscore(nc + 1, 0.0);
-  {
-    RCK(cudaSetDevice(nw::ctx_device(ctx)));
-    cudaStream_t st = nw::ctx_stream(ctx);
-    void *d_grid = nullptr, *d_blk = nullptr, *d_off = nullptr, *d_sr = nullptr, *d_sc = nullptr;
-    auto cleanup = [&] {
-      cudaFree(d_grid);
-      cudaFree(d_blk);
-      cudaFree(d_off);
-      cudaFree(d_sr);
-      cudaFree(d_sc);
-    };
-    try {
-      RCK(cudaMalloc(&d_grid, g.v.size() * 8));
-      RCK(cudaMalloc(&d_blk, std::max<size_t>(flat_blk.size(), 1) * 2));
-      RCK(cudaMalloc(&d_off, off.size() * 8));
-      RCK(cudaMalloc(&d_sr, (nc + 1) * 8));
-      RCK(cudaMalloc(&d_sc, (nc + 1) * 8));
-      RCK(cudaMemcpyAsync(d_grid, g.v.data(), g.v.size() * 8, cudaMemcpyHostToDevice, st));
-      RCK(cudaMemcpyAsync(d_blk, flat_blk.data(), flat_blk.size() * 2, cudaMemcpyHostToDevice, st));
-      RCK(cudaMemcpyAsync(d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
-      const int nn = (int)(nc + 1);
-      k_est_diag<<<(nn * 32 + 255) / 256, 256, 0, st>>>((const int64_t*)d_grid, g.nx, g.ny, (const int16_t*)d_blk,
-                                                        (const int64_t*)d_off, nn, (long long*)d_sr, (long long*)d_sc);
-      RCK(cudaGetLastError());
-      ++P.launches;
-      RCK(cudaMemcpyAsync(srow.data(), d_sr, (nc + 1) * 8, cudaMemcpyDeviceToHost, st));
-      RCK(cudaMemcpyAsync(scol.data(), d_sc, (nc + 1) * 8, cudaMemcpyDeviceToHost, st));
-      RCK(cudaStreamSynchronize(st));
-    } catch (...) {
-      cleanup();
-      throw;
-    }
-    cleanup();
-  }
-  if (nc > 0) {
-    // children with more than one column; a single remaining column has its own formula (R/evaltools.R:109-114)
-    std::vector<int64_t> off2(1, 0);
-    std::vector<int16_t> flat2;
-    std::vector<size_t> who;
-    for (size_t k = 1; k <= nc; ++k) {
-      if (cand[k - 1].size() < 2) continue;
-      who.push_back(k);
-      flat2.insert(flat2.end(), seqs[k].begin(), seqs[k].end());
-      off2.push_back((int64_t)flat2.size());
-    }
-    if (!who.empty()) {
-      std::vector<int64_t> c2(who.size()), t2(who.size());
-      std::vector<double> s2(who.size());
-      NWCK(nw_score_batch(ctx, aln.data(), nxa, g.ny, lenx.data(), g.rn.data(), flat2.data(), off2.data(), (int64_t)who.size(), 2,
-                          o.flags & NW_FLAG_GENERIC_DP, c2.data(), t2.data(), s2.data()));
-      for (size_t q = 0; q < who.size(); ++q) {
-        ccost[who[q]] = c2[q];
-        ctotal[who[q]] = t2[q];
-        cscore[who[q]] = s2[q];
+    std::vector<int64_t> grid_all, off(1, 0);
+    std::vector<int16_t> blk;
+    std::vector<int32_t> meta;  // per entry: grid offset (in int64 elements, two int32), n_x, n_y
+    for (PrepassOut* P : live) {
+      const Grid& g = P->flipped;
+      const int64_t go = (int64_t)grid_all.size();
+      grid_all.insert(grid_all.end(), g.v.begin(), g.v.end());
+      Arr root(g.nx);
+      for (int i = 0; i < g.nx; ++i) root[i] = Pos{(int16_t)(i + 1), 0};
+      for (size_t k = 0; k <= P->cand.size(); ++k) {
+        const Arr& a = k ? P->cand[k - 1] : root;
+        for (const Pos& p : a) blk.push_back(p.blk);
+        off.push_back((int64_t)blk.size());
+        meta.push_back((int32_t)(go & 0xffffffffll));
+        meta.push_back((int32_t)(go >> 32));
+        meta.push_back(g.nx);
+        meta.push_back(g.ny);
       }
     }
+    const size_t ne = off.size() - 1;
+    if (ne >= ((size_t)1 << 26)) rfail(NW_ERR_ARG, "too many pre-pass candidates in one batch");
+    std::vector<long long> out(ne * 2);
+    RCK(cudaSetDevice(nw::ctx_device(ctx)));
+    cudaStream_t st = nw::ctx_stream(ctx);
+    void* d = nullptr;
+    auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };  // the int4 metadata needs 16-byte alignment
+    const size_t b_grid = up16(grid_all.size() * 8), b_off = up16(off.size() * 8), b_out = ne * 16, b_meta = meta.size() * 4,
+                 b_blk = up16(blk.size() * 2);
+    RCK(cudaMalloc(&d, b_grid + b_off + b_out + b_meta + b_blk + 64));
+    unsigned char* base = static_cast<unsigned char*>(d);
+    unsigned char *d_grid = base, *d_off = d_grid + b_grid, *d_out = d_off + b_off, *d_meta = d_out + b_out, *d_blk = d_meta + b_meta;
+    try {
+      RCK(cudaMemcpyAsync(d_grid, grid_all.data(), grid_all.size() * 8, cudaMemcpyHostToDevice, st));
+      RCK(cudaMemcpyAsync(d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+      RCK(cudaMemcpyAsync(d_meta, meta.data(), b_meta, cudaMemcpyHostToDevice, st));
+      RCK(cudaMemcpyAsync(d_blk, blk.data(), blk.size() * 2, cudaMemcpyHostToDevice, st));
+      k_est_diag<<<(unsigned)((ne * 32 + 255) / 256), 256, 0, st>>>((const int64_t*)d_grid, (const int4*)d_meta, (const int16_t*)d_blk,
+                                                                     (const int64_t*)d_off, (int)ne, (long long*)d_out);
+      RCK(cudaGetLastError());
+      ++launches;
+      RCK(cudaMemcpyAsync(out.data(), d_out, b_out, cudaMemcpyDeviceToHost, st));
+      RCK(cudaStreamSynchronize(st));
+    } catch (...) {
+      cudaFree(d);
+      throw;
+    }
+    cudaFree(d);
+    size_t e = 0;
+    for (PrepassOut* P : live)
+      for (size_t k = 0; k <= P->cand.size(); ++k, ++e) {
+        P->srow[k] = out[e * 2];
+        P->scol[k] = out[e * 2 + 1];
+      }
   }
-  P.launches += nw::ctx_launches(ctx) - L0;
+  // ---- DP: pass 0 = reference arrangements, forcecalc (dfsutil: forcecalc = (pair$sv == "ref")); pass 1 = children
+  //      with more than one column (a single remaining column has its own formula, R/evaltools.R:109-114) ----
+  std::vector<nw::ScoreProblem> probs(live.size());
+  for (size_t r = 0; r < live.size(); ++r) {
+    PrepassOut* P = live[r];
+    probs[r] = nw::ScoreProblem{P->aln.data(), P->nxa, P->flipped.ny, P->lenx.data(), P->flipped.rn.data()};
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    std::vector<int16_t> flat;
+    std::vector<int64_t> off(1, 0);
+    std::vector<uint16_t> rid;
+    std::vector<std::pair<uint32_t, uint32_t>> who;
+    for (size_t r = 0; r < live.size(); ++r) {
+      PrepassOut* P = live[r];
+      const size_t k0 = pass ? 1 : 0, k1 = pass ? P->cand.size() : 0;
+      for (size_t k = k0; k <= k1; ++k) {
+        if (P->seqs[k].size() < 2) continue;
+        flat.insert(flat.end(), P->seqs[k].begin(), P->seqs[k].end());
+        off.push_back((int64_t)flat.size());
+        rid.push_back((uint16_t)r);
+        who.emplace_back((uint32_t)r, (uint32_t)k);
+      }
+    }
+    if (who.empty()) continue;
+    std::vector<int64_t> c2(who.size()), t2(who.size());
+    std::vector<double> s2(who.size());
+    NWCK(nw::score_batch_regions(ctx, probs.data(), (int)live.size(), rid.data(), flat.data(), off.data(), (int64_t)who.size(),
+                                 pass ? 2 : 1, flags & NW_FLAG_GENERIC_DP, c2.data(), t2.data(), s2.data()));
+    for (size_t q = 0; q < who.size(); ++q) {
+      PrepassOut* P = live[who[q].first];
+      P->ccost[who[q].second] = c2[q];
+      P->ctotal[who[q].second] = t2[q];
+      P->cscore[who[q].second] = s2[q];
+    }
+  }
+  launches += nw::ctx_launches(ctx) - L0;
+}
 
+// Phase 3 (host): replay of dfsutil's sequential part (R/dfs_machinery.R:79-246) over the per-child numbers, then
+// sort_new_by_penalised, transform_res_new_to_old, annotate_res_out_with_positions_lens.
+void prepass_replay(PrepassOut& P, const nw_region_opts& o) {
+  if (P.cluttered) return;
+  nw_table& T = *P.table;
+  const Grid& g = P.flipped;
+  const size_t nc = P.cand.size();
+  Arr root(g.nx);
+  for (int i = 0; i < g.nx; ++i) root[i] = Pos{(int16_t)(i + 1), g.cn[i]};
   for (size_t k = 1; k <= nc; ++k) {
     const Move& m = P.moves[k - 1];
-    T.cands.push_back(nw_candidate{m.p1, m.p2, m.sv, (int32_t)cand[k - 1].size(), srow[k], scol[k], ccost[k], ctotal[k], cscore[k]});
+    T.cands.push_back(nw_candidate{m.p1, m.p2, m.sv, (int32_t)P.cand[k - 1].size(), P.srow[k], P.scol[k], P.ccost[k],
+                                   P.ctotal[k], P.cscore[k]});
   }
-  // ---- replay of dfsutil's sequential part (R/dfs_machinery.R:79-246) ----
+  double s_ref = P.cscore[0];
+  if (P.ccost[0] == -2) s_ref = 1.0;  // R/evaltools.R:259-261 (cannot happen with the full corridor)
   double sum_rn = 0, sum_cn0 = 0;
   for (int64_t t : g.rn) sum_rn += (double)t;
   for (int64_t t : g.cn) sum_cn0 += (double)t;
   const double orig_symm = std::min(sum_rn, sum_cn0) / std::max(sum_rn, sum_cn0);  // calc_symm
-  auto est_of = [&](size_t k, double sum_cn) {
-    return (((double)srow[k] + (double)scol[k]) / (sum_rn + sum_cn)) * 100;
-  };
+  auto est_of = [&](size_t k, double sum_cn) { return (((double)P.srow[k] + (double)P.scol[k]) / (sum_rn + sum_cn)) * 100; };
   double est_highest = est_of(0, sum_cn0);  // forcecalc: est_highest <<- est
   struct Rec {
     int depth;
@@ -810,7 +867,7 @@ PrepassOut run_prepass(nw_ctx* ctx, const Grid& g0, const nw_region_opts& o) {
   visited.emplace(dv, s_ref);
   if (s_ref >= 0 && P.maxdepth > 0) {
     for (size_t k = 1; k <= nc; ++k) {
-      const Arr& a = cand[k - 1];
+      const Arr& a = P.cand[k - 1];
       diag_values(g, a, dv);
       auto it = visited.find(dv);
       if (it != visited.end()) {
@@ -839,7 +896,7 @@ PrepassOut run_prepass(nw_ctx* ctx, const Grid& g0, const nw_region_opts& o) {
           } else {
             if (est > est_highest) est_highest = est;
             ++P.n_dp;
-            s = ccost[k] == -2 ? 1.0 : cscore[k];  // unreachable terminal cell: R/evaltools.R:259-261
+            s = P.ccost[k] == -2 ? 1.0 : P.cscore[k];  // unreachable terminal cell: R/evaltools.R:259-261
           }
         }
       }
@@ -847,7 +904,6 @@ PrepassOut run_prepass(nw_ctx* ctx, const Grid& g0, const nw_region_opts& o) {
       visited.emplace(dv, s);
     }
   }
-  // ---- sort_new_by_penalised, transform_res_new_to_old, annotate ----
   const double step_penalty = (o.compression / sum_cn0 * 100) * 1.5;
   std::vector<size_t> ord(recs.size());
   std::vector<double> pen(recs.size());
@@ -856,29 +912,28 @@ PrepassOut run_prepass(nw_ctx* ctx, const Grid& g0, const nw_region_opts& o) {
     pen[k] = recs[k].eval - recs[k].depth * step_penalty;
   }
   std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return pen[a] > pen[b]; });
-  int count = 1;
-  bool stop = false;
   for (size_t k : ord) {
     const Rec& rc = recs[k];
     if (rc.mv < 0) {
-      add_row(rc.eval, "ref");
+      add_row(T, rc.eval, "ref");
     } else {
       const Move& m = P.moves[rc.mv];
-      add_row(rc.eval, std::to_string(m.p1) + "_" + std::to_string(m.p2) + "_" + kSvName[m.sv]);
+      add_row(T, rc.eval, std::to_string(m.p1) + "_" + std::to_string(m.p2) + "_" + kSvName[m.sv]);
     }
   }
-  for (size_t q = 0; q < T.rows.size() && !stop; ++q) {
+  int count = 1;
+  for (size_t q = 0; q < T.rows.size(); ++q) {
     ++count;
-    if (count > 2000) {
-      stop = true;
-      break;
-    }
+    if (count > 2000) break;  // "Stopping to annotate results to save some time."
     const Rec& rc = recs[ord[q]];
     if (rc.mv < 0) continue;
-    annotate_row(T.rows[q], g0, P.moves[rc.mv].p1, P.moves[rc.mv].p2);
+    annotate_row(T.rows[q], P.g0, P.moves[rc.mv].p1, P.moves[rc.mv].p2);
   }
   finish_table(T);
-  return P;
+  // the work arrays are not needed any more
+  std::vector<Arr>().swap(P.cand);
+  std::vector<std::vector<int16_t>>().swap(P.seqs);
+  std::vector<int8_t>().swap(P.aln);
 }
 
 void fill_prepass_summary(nw_region_summary& S, const PrepassOut& P) {
@@ -896,6 +951,77 @@ void fill_prepass_summary(nw_region_summary& S, const PrepassOut& P) {
   }
 }
 
+// berzerk guard (R/juliasolver.R:9-30) on the flipped matrix
+double guarded_width(const PrepassOut& P, double width, int32_t& reduced) {
+  int64_t ndup = 0, longest = std::numeric_limits<int64_t>::min();
+  for (const Move& m : P.moves)
+    if (m.sv == 1) {
+      ++ndup;
+      longest = std::max<int64_t>(longest, m.p2 - m.p1);
+    }
+  const size_t nm = P.moves.size();
+  reduced = 0;
+  if (nm > 400 || (nm > 200 && longest > 40 && ndup > 40)) {
+    width = width / 10;
+    reduced = 1;
+  }
+  return width;
+}
+
+// R/wrapper_aln_and_analyse.R:180-190: merge of the pre-pass table T and the formatted solver table J
+void merge_tables(std::unique_ptr<nw_table>& T, std::unique_ptr<nw_table>& J) {
+  if (J->kind == 2 && J->rows.size() == 1) return;  // all(dim(res_julia) == c(1, 3)): res stays the pre-pass table
+  bool has_ref = false;
+  for (const auto& r : J->rows) has_ref |= (!r.mut.empty() && r.mut[0] == "ref");
+  if (!has_ref) {
+    double ref_eval = kNA;
+    for (const auto& r : T->rows)
+      if (r.mut[0] == "ref") ref_eval = r.eval;
+    nw_table::Row r;
+    r.eval = ref_eval;
+    r.mut.assign(J->n_mut, "");
+    r.mut[0] = "ref";
+    r.num.assign(J->rows.empty() ? 0 : J->rows[0].num.size(), kNA);
+    J->rows.push_back(std::move(r));
+    sort_eval_na(*J);
+  }
+  T = std::move(J);
+}
+
+void finish_region(std::unique_ptr<nw_table>& T, nw_region_summary& S) {
+  finish_table(*T);
+  const nw_region_summary F = T->summ;  // res_ref, res_max, n_res_max, maxres, shape
+  S.res_ref = F.res_ref;
+  S.res_max = F.res_max;
+  S.n_res_max = F.n_res_max;
+  S.n_rows = F.n_rows;
+  S.n_mut = F.n_mut;
+  memcpy(S.maxres, F.maxres, sizeof S.maxres);
+  T->summ = S;
+}
+
+std::vector<int8_t> sign_matrix(const Grid& g) {
+  std::vector<int8_t> aln((size_t)g.nx * g.ny);
+  for (int x = 0; x < g.nx; ++x)
+    for (int y = 0; y < g.ny; ++y) {
+      const int64_t t = g.at(y, x);
+      aln[(size_t)x * g.ny + y] = (int8_t)(t > 0 ? 1 : t < 0 ? -1 : 0);
+    }
+  return aln;
+}
+
+nw_opts solver_opts(const nw_region_opts& o, double width) {
+  nw_opts so;
+  nw_default_opts(&so);
+  so.maxdepth = o.depth;
+  so.maxdup = o.maxdup;
+  so.maxwidth = (int64_t)width;  // the command line carries paste0(width): "100", "1000"
+  so.minreport = o.minreport;
+  so.maxreport = 1000;  // -R 1000 (R/juliasolver.R:48)
+  so.flags = o.flags;
+  return so;
+}
+
 int rguard(const std::function<void()>& fn) {
   try {
     fn();
@@ -910,6 +1036,80 @@ int rguard(const std::function<void()>& fn) {
     nw::set_last_error(e.what());
     return NW_ERR_ARG;
   }
+}
+
+// The solver stage of n regions: pre-pass of all of them in one GPU batch, then the regions below 99.8 through the
+// forest search (nw_solve_many; regions of one width setting per call), format + merge + summary per region.
+void analyse_many(nw_ctx* ctx, const nw_region_problem* regs, int64_t n, const nw_region_opts& o, nw_table** outs,
+                  nw_region_summary* summaries) {
+  std::vector<PrepassOut> Ps((size_t)n);
+  std::vector<PrepassOut*> ptrs;
+  for (int64_t k = 0; k < n; ++k) {
+    const nw_region_problem& r = regs[k];
+    if (r.n_gridlines > 0 && !r.gridlines_x) rfail(NW_ERR_ARG, "null gridlines");
+    prepass_prepare(Ps[k], make_grid(r.grid, r.n_x, r.n_y, r.len_x, r.len_y));
+    ptrs.push_back(&Ps[k]);
+  }
+  int launches = 0;
+  prepass_gpu(ctx, ptrs, o.flags, launches);
+  std::vector<nw_region_summary> S((size_t)n);
+  std::vector<int64_t> need[2];  // regions that go to the solver, by width setting (plain / reduced by the guard)
+  std::vector<std::vector<int8_t>> alns((size_t)n);
+  for (int64_t k = 0; k < n; ++k) {
+    PrepassOut& P = Ps[k];
+    prepass_replay(P, o);
+    P.launches = k == 0 ? launches : 0;  // the launches are shared by the batch: reported once
+    memset(&S[k], 0, sizeof S[k]);
+    fill_prepass_summary(S[k], P);
+    double mx = -INFINITY;
+    for (const auto& r : P.table->rows) mx = std::max(mx, r.eval);
+    if (!P.cluttered && mx < 99.8) {  // wrapper :177
+      S[k].solver_called = 1;
+      guarded_width(P, o.init_width, S[k].width_reduced);
+      need[S[k].width_reduced].push_back(k);
+      alns[k] = sign_matrix(P.flipped);
+    }
+  }
+  for (int wset = 0; wset < 2; ++wset) {
+    const std::vector<int64_t>& idx = need[wset];
+    if (idx.empty()) continue;
+    const nw_opts so = solver_opts(o, wset ? o.init_width / 10 : o.init_width);
+    std::vector<nw_problem> probs(idx.size());
+    for (size_t q = 0; q < idx.size(); ++q) {
+      const PrepassOut& P = Ps[idx[q]];
+      probs[q] = nw_problem{alns[idx[q]].data(), P.flipped.nx, P.flipped.ny, P.flipped.cn.data(), P.flipped.rn.data()};
+    }
+    std::vector<nw_result*> res(idx.size(), nullptr);
+    if (idx.size() == 1) {
+      NWCK(nw_solve(ctx, probs[0].aln_sign, probs[0].n_x, probs[0].n_y, probs[0].len_x, probs[0].len_y, &so, &res[0]));
+    } else {
+      NWCK(nw_solve_many(ctx, probs.data(), (int64_t)idx.size(), &so, 512, res.data()));
+    }
+    try {
+      for (size_t q = 0; q < idx.size(); ++q) {
+        const int64_t k = idx[q];
+        const char* data = nullptr;
+        int64_t len = 0;
+        nw_stats st{};
+        NWCK(nw_result_tsv(res[q], &data, &len));
+        NWCK(nw_result_stats(res[q], &st));
+        std::unique_ptr<nw_table> J(format_solver_output(data, len, regs[k].gridlines_x, regs[k].n_gridlines));
+        if (idx.size() == 1 || q % 512 == 0) S[k].gpu_launches += st.kernel_launches;  // counters are per pass
+        S[k].search_depth = o.depth;  // format_julia_output overwrites the log counters (R/juliasolver.R:63-65, :107-111)
+        S[k].mut_simulated = S[k].mut_tested = J->kind == 2 ? 0 : (int64_t)J->rows.size();
+        merge_tables(Ps[k].table, J);
+      }
+    } catch (...) {
+      for (nw_result* r : res) nw_result_free(r);
+      throw;
+    }
+    for (nw_result* r : res) nw_result_free(r);
+  }
+  for (int64_t k = 0; k < n; ++k) {
+    finish_region(Ps[k].table, S[k]);
+    if (summaries) summaries[k] = S[k];
+  }
+  for (int64_t k = 0; k < n; ++k) outs[k] = Ps[k].table.release();
 }
 
 }  // namespace
@@ -932,10 +1132,15 @@ int nw_region_prepass(nw_ctx* ctx, const int64_t* grid, int32_t n_x, int32_t n_y
   if (out) *out = nullptr;
   return rguard([&] {
     if (!ctx || !opts || !out) rfail(NW_ERR_ARG, "null argument");
-    const Grid g = make_grid(grid, n_x, n_y, len_x, len_y);
-    PrepassOut P = run_prepass(ctx, g, *opts);
-    fill_prepass_summary(P.table->summ, P);
-    if (summary) *summary = P.table->summ;
+    PrepassOut P;
+    prepass_prepare(P, make_grid(grid, n_x, n_y, len_x, len_y));
+    std::vector<PrepassOut*> one{&P};
+    prepass_gpu(ctx, one, opts->flags, P.launches);
+    prepass_replay(P, *opts);
+    nw_region_summary S = P.table->summ;  // res_ref / res_max / n_res_max / maxres of the pre-pass table
+    fill_prepass_summary(S, P);
+    P.table->summ = S;
+    if (summary) *summary = S;
     *out = P.table.release();
   });
 }
@@ -953,98 +1158,31 @@ int nw_region_analyse(nw_ctx* ctx, const int64_t* grid, int32_t n_x, int32_t n_y
                       const nw_region_opts* opts, nw_table** out, nw_region_summary* summary) {
   if (out) *out = nullptr;
   return rguard([&] {
-    if (!ctx || !opts || !out || (n_gridlines > 0 && !gridlines_x)) rfail(NW_ERR_ARG, "null argument");
-    const Grid g0 = make_grid(grid, n_x, n_y, len_x, len_y);
-    PrepassOut P = run_prepass(ctx, g0, *opts);
-    nw_region_summary S{};
-    fill_prepass_summary(S, P);
-    std::unique_ptr<nw_table> T = std::move(P.table);
-    T->summ.n_rows = (int32_t)T->rows.size();
-    double mx = -INFINITY;
-    for (const auto& r : T->rows) mx = std::max(mx, r.eval);
-    if (!P.cluttered && mx < 99.8) {  // wrapper :177
-      S.solver_called = 1;
-      const Grid& g = P.flipped;
-      // berzerk guard (R/juliasolver.R:9-30) on the flipped matrix
-      double width = opts->init_width;
-      {
-        int64_t ndup = 0, longest = std::numeric_limits<int64_t>::min();
-        for (const Move& m : P.moves)
-          if (m.sv == 1) {
-            ++ndup;
-            longest = std::max<int64_t>(longest, m.p2 - m.p1);
-          }
-        const size_t nm = P.moves.size();
-        if (nm > 400 || (nm > 200 && longest > 40 && ndup > 40)) {
-          width = width / 10;
-          S.width_reduced = 1;
-        }
-      }
-      std::vector<int8_t> aln((size_t)g.nx * g.ny);
-      for (int x = 0; x < g.nx; ++x)
-        for (int y = 0; y < g.ny; ++y) {
-          const int64_t t = g.at(y, x);
-          aln[(size_t)x * g.ny + y] = (int8_t)(t > 0 ? 1 : t < 0 ? -1 : 0);
-        }
-      nw_opts so;
-      nw_default_opts(&so);
-      so.maxdepth = opts->depth;
-      so.maxdup = opts->maxdup;
-      so.maxwidth = (int64_t)width;  // the command line carries paste0(width): "100", "1000"
-      so.minreport = opts->minreport;
-      so.maxreport = 1000;  // -R 1000 (R/juliasolver.R:48)
-      so.flags = opts->flags;
-      nw_result* res = nullptr;
-      NWCK(nw_solve(ctx, aln.data(), g.nx, g.ny, g.cn.data(), g.rn.data(), &so, &res));
-      std::unique_ptr<nw_table> J;
-      nw_stats st{};
+    if (!ctx || !opts || !out) rfail(NW_ERR_ARG, "null argument");
+    const nw_region_problem r{grid, n_x, n_y, len_x, len_y, gridlines_x, n_gridlines};
+    analyse_many(ctx, &r, 1, *opts, out, summary);
+  });
+}
+
+int nw_region_analyse_many(nw_ctx* ctx, const nw_region_problem* regions, int64_t n, const nw_region_opts* opts,
+                           nw_table** outs, nw_region_summary* summaries) {
+  if (outs)
+    for (int64_t k = 0; k < n; ++k) outs[k] = nullptr;
+  return rguard([&] {
+    if (!ctx || !opts || !outs || n < 0 || (n > 0 && !regions)) rfail(NW_ERR_ARG, "null argument");
+    const int64_t PASS = 4096;  // regions per pre-pass batch (the solver batches 512 at a time below that)
+    for (int64_t a = 0; a < n; a += PASS) {
+      const int64_t m = std::min(PASS, n - a);
       try {
-        const char* data = nullptr;
-        int64_t len = 0;
-        NWCK(nw_result_tsv(res, &data, &len));
-        NWCK(nw_result_stats(res, &st));
-        J.reset(format_solver_output(data, len, gridlines_x, n_gridlines));
+        analyse_many(ctx, regions + a, m, *opts, outs + a, summaries ? summaries + a : nullptr);
       } catch (...) {
-        nw_result_free(res);
+        for (int64_t k = 0; k < a; ++k) {
+          nw_table_free(outs[k]);
+          outs[k] = nullptr;
+        }
         throw;
       }
-      nw_result_free(res);
-      S.gpu_launches += st.kernel_launches;
-      S.search_depth = opts->depth;  // format_julia_output overwrites the log counters (R/juliasolver.R:63-65, :107-111)
-      if (J->kind == 2) {
-        S.mut_simulated = S.mut_tested = 0;
-      } else {
-        S.mut_simulated = S.mut_tested = (int64_t)J->rows.size();
-      }
-      if (!(J->kind == 2 && J->rows.size() == 1)) {  // !all(dim(res_julia) == c(1, 3))
-        bool has_ref = false;
-        for (const auto& r : J->rows) has_ref |= (!r.mut.empty() && r.mut[0] == "ref");
-        if (!has_ref) {
-          double ref_eval = kNA;
-          for (const auto& r : T->rows)
-            if (r.mut[0] == "ref") ref_eval = r.eval;
-          nw_table::Row r;
-          r.eval = ref_eval;
-          r.mut.assign(J->n_mut, "");
-          r.mut[0] = "ref";
-          r.num.assign(J->rows.empty() ? 0 : J->rows[0].num.size(), kNA);
-          J->rows.push_back(std::move(r));
-          sort_eval_na(*J);
-        }
-        T = std::move(J);
-      }
     }
-    finish_table(*T);
-    const nw_region_summary F = T->summ;  // res_ref, res_max, n_res_max, maxres, shape
-    S.res_ref = F.res_ref;
-    S.res_max = F.res_max;
-    S.n_res_max = F.n_res_max;
-    S.n_rows = F.n_rows;
-    S.n_mut = F.n_mut;
-    memcpy(S.maxres, F.maxres, sizeof S.maxres);
-    T->summ = S;
-    if (summary) *summary = S;
-    *out = T.release();
   });
 }
 

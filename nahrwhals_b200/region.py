@@ -30,7 +30,12 @@ class NwRegionSummary(C.Structure):
 
 
 SYMBOLS = ["nw_region_default_opts", "nw_region_prepass", "nw_region_format", "nw_region_analyse", "nw_table_summary",
-           "nw_table_mut_max", "nw_table_tsv", "nw_table_rows", "nw_table_free", "nw_table_candidates"]
+           "nw_table_mut_max", "nw_table_tsv", "nw_table_rows", "nw_table_free", "nw_table_candidates", "nw_region_analyse_many"]
+
+
+class NwRegionProblem(C.Structure):
+    _fields_ = [("grid", C.c_void_p), ("n_x", C.c_int32), ("n_y", C.c_int32), ("len_x", C.c_void_p),
+                ("len_y", C.c_void_p), ("gridlines_x", C.c_void_p), ("n_gridlines", C.c_int32)]
 
 
 class NwCandidate(C.Structure):
@@ -54,6 +59,7 @@ def _lib_region():
         L.nw_region_format.argtypes = [C.c_char_p, i64, vp, i32, C.POINTER(vp)]
         L.nw_region_analyse.argtypes = [vp, vp, i32, i32, vp, vp, vp, i32, C.POINTER(NwRegionOpts), C.POINTER(vp),
                                         C.POINTER(NwRegionSummary)]
+        L.nw_region_analyse_many.argtypes = [vp, vp, i64, C.POINTER(NwRegionOpts), vp, vp]
         L.nw_table_summary.argtypes = [vp, C.POINTER(NwRegionSummary)]
         L.nw_table_mut_max.restype = C.c_char_p
         L.nw_table_mut_max.argtypes = [vp]
@@ -174,3 +180,27 @@ def analyse_region(solver, mat, len_y, len_x, gridlines_x, depth=3, maxdup=2, in
     _lib.check(L.nw_region_analyse(solver.h, _p(g), g.shape[1], g.shape[0], _p(lx), _p(ly), _p(gl), len(gl),
                                    C.byref(o), C.byref(h), C.byref(S)))
     return RegionResult(L, h, S)
+
+
+def analyse_regions(solver, regions, depth=3, maxdup=2, init_width=1000, minreport=0.98, compression=1000, timing=None,
+                    **kw):
+    """Regionfile mode: the solver stage of many regions in one call (nw_region_analyse_many).  `regions` is a list of
+    (mat[n_y, n_x], len_y, len_x, gridlines_x).  Returns one RegionResult per region, identical to analyse_region."""
+    import time
+    L = _lib_region()
+    n = len(regions)
+    keep = []
+    probs = (NwRegionProblem * max(n, 1))()
+    for k, (mat, len_y, len_x, gridlines_x) in enumerate(regions):
+        g, ly, lx = _grid(mat, len_y, len_x)
+        gl = np.ascontiguousarray(gridlines_x, dtype=np.float64)
+        keep.append((g, ly, lx, gl))
+        probs[k] = NwRegionProblem(_p(g), g.shape[1], g.shape[0], _p(lx), _p(ly), _p(gl), len(gl))
+    o = _opts(L, depth, maxdup, init_width, minreport, compression, **kw)
+    outs = (C.c_void_p * max(n, 1))()
+    summ = (NwRegionSummary * max(n, 1))()
+    t0 = time.perf_counter()
+    _lib.check(L.nw_region_analyse_many(solver.h, probs, n, C.byref(o), outs, summ))
+    if timing is not None:
+        timing["native_s"] = time.perf_counter() - t0
+    return [RegionResult(L, C.c_void_p(outs[k]), summ[k]) for k in range(n)]

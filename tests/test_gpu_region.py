@@ -124,3 +124,35 @@ def test_region_solved_by_prepass(solver, oracle):
             assert P.res_max >= 99.8
             return
     pytest.fail("no single-move region found")
+
+
+def test_region_batch_equals_single(solver, oracle):
+    """nw_region_analyse_many: the pre-pass of all regions in one GPU batch and the forest search for the regions that
+    need the solver give, region by region, the tables of nw_region_analyse -- and of the R restatement."""
+    regs = []
+    for seed in range(40):
+        n_x = 10 + (seed * 7) % 45
+        fams = [[2], [3, 2], [4, 3], [4, 3, 2], [3, 3, 2, 2]][seed % 5]
+        mat, lx, ly, _ = sdgrid(n_x, fams, chain_depth=1 + seed % 3, seed=500 + seed)
+        if seed % 4 == 3:
+            mat, ly = -mat[::-1], ly[::-1]
+        if seed % 9 == 8:
+            mat, lx, ly = random_grid(9 + seed % 7, 8 + seed % 5, 0.2, seed)
+        regs.append((mat, ly, lx, np.concatenate([[0], np.cumsum(lx)])))
+    kw = dict(depth=3, init_width=150, minreport=0.95)
+    B = nb.analyse_regions(solver, regs, **kw)
+    assert len(B) == len(regs)
+    called = 0
+    for k, (mat, ly, lx, gl) in enumerate(regs):
+        S = nb.analyse_region(solver, mat, ly, lx, gl, **kw)
+        assert B[k].tsv == S.tsv and B[k].mut_max == S.mut_max
+        assert (B[k].res_ref, B[k].res_max, B[k].n_res_max) == (S.res_ref, S.res_max, S.n_res_max)
+        assert B[k].log == S.log and B[k].maxres == S.maxres and B[k].solver_called == S.solver_called
+        assert B[k].candidates == S.candidates
+        called += S.solver_called
+        if k % 5 == 0:
+            O = ro.analyse_region(mat, ly, lx, gl, oracle_solver(oracle), **kw)
+            _rows_equal(B[k].rows, O["res"])
+            assert B[k].mut_max == O["mut_max"]
+    assert 5 < called < len(regs)          # both branches of the 99.8 gate are in the batch
+    assert nb.analyse_regions(solver, []) == []
