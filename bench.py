@@ -256,6 +256,92 @@ def run_regions(args, rank, world, local):
         s_.close()
 
 
+def run_stage(args, rank, world, local):
+    """SURVEY 8f rows 1+3 around the solver: the whole solver STAGE of a region as R/wrapper_aln_and_analyse.R:176-191
+    runs it (R depth-1 pre-pass, 99.8 gate, flip, solver, format_julia_output, merge, logfile summary) for a batch of
+    regions through nw_region_analyse_many on one context per GPU.  Metric: regions/s, wall clock around the C-ABI
+    call, host buffers in, result tables in host memory out.  --impl reference: the R restatement (Python) around the
+    C++ oracle solver, one region per worker process."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from region_batch import make_stage_regions, run_stage_cpu
+    cores = os.cpu_count() or 1
+    desc = ("solver stage of a regionfile batch (R depth-1 pre-pass + solver -d 3 -u 2 -w 1000 -r 0.98 -R 1000 + "
+            "format/merge/logfile summary): %d synthetic SD-flanked regions per GPU, 20-120 blocks")
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        regs = make_stage_regions(max(32, args.regions // 40), seed=0)
+        r, _, dt = run_stage_cpu(regs, cores)
+        print(json.dumps(dict(impl="reference", metric="regions_solved_per_s", value=r, unit="regions/s",
+                              n_gpus=args.gpus, steps=1, warmup=0, ms_per_step=1e3 * dt, higher_is_better=True,
+                              scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                              config=dict(workload=desc % len(regs)),
+                              cpu_baseline=dict(value=r, unit="regions/s", cores=cores, kind="port",
+                                                sample="%d regions, one per worker process" % len(regs)),
+                              e2e=dict(value=r, unit="regions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                              gpu_launches=0)), flush=True)
+        return
+    import torch
+    import nahrwhals_b200 as nb
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    regs = make_stage_regions(args.regions, seed=rank)
+    warm = make_stage_regions(min(args.regions, 1500), seed=1000 + rank)
+    solver = nb.Solver(local)
+    kw = dict(depth=3, maxdup=2, init_width=1000, minreport=0.98)
+    for _ in range(max(1, args.warmup_regions)):
+        nb.analyse_regions(solver, warm, **kw)
+    del warm
+    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler.start()
+    steps = max(1, args.steps)
+    dt = 0.0
+    for _ in range(steps):
+        tm = {}
+        res = nb.analyse_regions(solver, regs, timing=tm, **kw)
+        dt += tm["native_s"]
+    torch.cuda.synchronize()
+    dt /= steps
+    clocks = sampler.stop()
+    n = len(regs)
+    called = sum(1 for R in res if R.solver_called)
+    launches = sum(R.gpu_launches for R in res)
+    cands = sum(R.prepass_candidates for R in res)
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        s = torch.tensor([n, called, launches, cands], dtype=torch.float64, device="cuda")
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        n, called, launches, cands = s.tolist()
+    line = dict(metric="regions_solved_per_s", value=n / dt, unit="regions/s", n_gpus=world, steps=steps,
+                warmup=max(1, args.warmup_regions), ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="int32", data="synthetic",
+                config=dict(workload=(desc % args.regions) + "; one context per GPU, regions shard per GPU, no collective",
+                            solver_called=int(called), prepass_candidates=int(cands),
+                            timed="wall clock around nw_region_analyse_many (host buffers in, result tables out)"),
+                clocks=clocks, e2e=dict(value=n / dt, unit="regions/s", h2d_bytes_per_step=None, d2h_bytes_per_step=None),
+                gpu_launches=int(launches))
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = make_stage_regions(max(32, args.regions // 40), seed=0)
+        r, _, cdt = run_stage_cpu(sample, cores)
+        line["cpu_baseline"] = dict(value=r, unit="regions/s", cores=cores, kind="port",
+                                    sample="%d regions of the same generator, %.1f s, one region per worker process; R "
+                                           "restatement in Python around the C++ oracle solver" % (len(sample), cdt))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    solver.close()
+
+
 def run_frontier(args, rank, world, local):
     """BASELINE.json config 3: ONE deep search sharded over the GPUs (frontier round-robin, per-level all-gather of
     40-byte records over NCCL, deterministic merge on every rank).  Strong scaling: total work is fixed."""
@@ -310,7 +396,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS) + ["regions"])
+    ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS) + ["regions", "stage"])
     ap.add_argument("--regions", type=int, default=6000, help="regions per rank for --workload regions")
     ap.add_argument("--contexts", type=int, default=4, help="solver contexts (streams) per GPU for --workload regions")
     ap.add_argument("--warmup-regions", type=int, default=2, help="untimed warm-up runs for --workload regions")
@@ -327,6 +413,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload == "regions":
         run_regions(args, rank, world, local)
+        return
+    if args.workload == "stage":
+        run_stage(args, rank, world, local)
         return
     if args.impl == "reference":
         run_reference(args, rank, world)

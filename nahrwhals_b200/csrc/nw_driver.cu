@@ -261,6 +261,11 @@ struct nw_ctx {
   void* dist = nullptr;  // active frontier-sharded search (Search*, nw_dist_*)
   void* pinned = nullptr;  // pinned staging area for D2H scalars / histograms (grown on demand)
   size_t pinned_bytes = 0;
+  // staging of the region pre-pass (nw_region.cu): pinned host buffer + device buffer, grown on demand, kept
+  void* rg_pinned = nullptr;
+  size_t rg_pinned_bytes = 0;
+  void* rg_dev = nullptr;
+  size_t rg_dev_bytes = 0;
   DevPool pool;
   int launches = 0;
   int64_t h2d_bytes = 0, d2h_bytes = 0;
@@ -696,6 +701,8 @@ struct Search {
   uint32_t* pinned(size_t bytes) {  // growable pinned staging area
     if (bytes > c->pinned_bytes) {
       if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->rg_pinned) cudaFreeHost(c->rg_pinned);
+  if (c->rg_dev) cudaFree(c->rg_dev);
       c->pinned = nullptr;
       c->pinned_bytes = 0;
       const size_t want = std::max(bytes + bytes / 2, (size_t)512 * 1024);
@@ -1990,6 +1997,30 @@ int ctx_device(nw_ctx* c) { return c->device; }
 cudaStream_t ctx_stream(nw_ctx* c) { return c->stream; }
 void ctx_add_launches(nw_ctx* c, int n) { c->launches += n; }
 int ctx_launches(nw_ctx* c) { return c->launches; }
+// growable staging pair of the region pre-pass; returns cudaSuccess or the allocation error
+cudaError_t ctx_region_staging(nw_ctx* c, size_t bytes, void** host_pinned, void** dev) {
+  if (bytes > c->rg_pinned_bytes) {
+    if (c->rg_pinned) cudaFreeHost(c->rg_pinned);
+    c->rg_pinned = nullptr;
+    c->rg_pinned_bytes = 0;
+    const size_t want = bytes + bytes / 2;
+    cudaError_t e = cudaMallocHost(&c->rg_pinned, want);
+    if (e != cudaSuccess) return e;
+    c->rg_pinned_bytes = want;
+  }
+  if (bytes > c->rg_dev_bytes) {
+    if (c->rg_dev) cudaFree(c->rg_dev);
+    c->rg_dev = nullptr;
+    c->rg_dev_bytes = 0;
+    const size_t want = bytes + bytes / 2;
+    cudaError_t e = cudaMalloc(&c->rg_dev, want);
+    if (e != cudaSuccess) return e;
+    c->rg_dev_bytes = want;
+  }
+  *host_pinned = c->rg_pinned;
+  *dev = c->rg_dev;
+  return cudaSuccess;
+}
 }  // namespace nw
 
 extern "C" {
@@ -2060,6 +2091,8 @@ void nw_ctx_destroy(nw_ctx* c) {
   nw_dist_abort(c);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->rg_pinned) cudaFreeHost(c->rg_pinned);
+  if (c->rg_dev) cudaFree(c->rg_dev);
   for (auto& ev : c->score_events) c->event_pool.push_back(ev);
   for (auto& ev : c->event_pool) {
     cudaEventDestroy(ev.first);

@@ -10,7 +10,13 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <thread>
+#include <chrono>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -29,6 +35,7 @@ void set_last_error(const std::string& m);
 int ctx_device(nw_ctx* c);
 cudaStream_t ctx_stream(nw_ctx* c);
 int ctx_launches(nw_ctx* c);
+cudaError_t ctx_region_staging(nw_ctx* c, size_t bytes, void** host_pinned, void** dev);
 struct ScoreProblem {
   const int8_t* aln;  // n_x*n_y, x-major
   int n_x, n_y;
@@ -290,16 +297,44 @@ void diag_values(const Grid& g, const Arr& a, std::vector<int64_t>& out) {
   }
 }
 
-struct VecHash {
-  size_t operator()(const std::vector<int64_t>& v) const {
-    uint64_t h = 1469598103934665603ull ^ v.size();
-    for (int64_t t : v) {
-      h ^= (uint64_t)t + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
-      h *= 1099511628211ull;
-    }
-    return (size_t)h;
-  }
+// 128-bit hash of the same value sequence without materialising it (the visited set of dfsutil is keyed by
+// rlang::hash of that vector); equal hashes are verified element-wise by the caller.
+struct DiagKey {
+  uint64_t h1, h2, n;
+  bool operator==(const DiagKey& o) const { return h1 == o.h1 && h2 == o.h2 && n == o.n; }
 };
+struct DiagKeyHash {
+  size_t operator()(const DiagKey& k) const { return (size_t)(k.h1 ^ (k.h2 * 0x9e3779b97f4a7c15ull)); }
+};
+DiagKey diag_key(const Grid& g, const Arr& a) {
+  const int64_t nr = g.ny, nc = (int64_t)a.size(), mn = std::min(nr, nc);
+  const int64_t md = (int64_t)r_round0(std::max(5.0, 0.05 * (double)nr));
+  const int64_t last = (nr + 1) * (mn - 1) + 1;
+  DiagKey k{0x243f6a8885a308d3ull, 0x13198a2e03707344ull, 0};
+  auto mix = [&](int64_t v) {
+    k.h1 = (k.h1 ^ (uint64_t)v) * 0x100000001b3ull;
+    k.h1 ^= k.h1 >> 29;
+    k.h2 = (k.h2 + (uint64_t)v + 0x9e3779b97f4a7c15ull) * 0xbf58476d1ce4e5b9ull;
+    k.h2 ^= k.h2 >> 31;
+    ++k.n;
+  };
+  auto value = [&](int64_t idx) { return cell(g, a, (int)((idx - 1) % nr), (int)((idx - 1) / nr)); };
+  for (int pass = 0; pass < 2; ++pass)
+    for (int64_t o = -md; o <= md; ++o)
+      for (int64_t q = 0; q < mn; ++q) {
+        const int64_t idx = 1 + q * (nr + 1) + o;
+        if (!(idx > 0 && idx <= last)) continue;
+        if (pass == 0) {
+          mix(value(idx));
+        } else {
+          const int64_t j = nr * nc - idx;
+          if (j == 0) continue;
+          if (j < 0 || j > nr * nc) rfail(NW_ERR_ARG, "return_diag_values_new: subscript outside the matrix");
+          mix(value(j));
+        }
+      }
+  return k;
+}
 
 // is_cluttered (helpers.R:209-235)
 bool is_cluttered(const Grid& g) {
@@ -340,7 +375,9 @@ struct nw_table {
     std::vector<double> num;       // NaN = NA; kind 0: 9 values, kind 1: 3 per mutation
   };
   std::vector<Row> rows;
-  std::string tsv, mut_max;
+  mutable std::string tsv;  // rendered on first use
+  mutable bool tsv_ready = false;
+  std::string mut_max;
   nw_region_summary summ{};
   std::vector<nw_candidate> cands;  // pre-pass diagnostics
 };
@@ -372,22 +409,23 @@ void sort_eval_na(nw_table& t) {  // order(-eval, -rowSums(is.na(.))), stable
   t.rows.swap(r2);
 }
 
-void fmt_num(std::string& s, double v) {
+void fmt_num(std::string& s, double v) {  // shortest text that reads back as v
   if (std::isnan(v)) {
     s += "NA";
     return;
   }
   char buf[40];
-  for (int prec = 1; prec <= 17; ++prec) {  // shortest representation that round-trips
-    snprintf(buf, sizeof buf, "%.*g", prec, v);
-    if (strtod(buf, nullptr) == v) break;
+  if (v == std::floor(v) && std::fabs(v) < 1e15) {
+    snprintf(buf, sizeof buf, "%lld", (long long)v);
+  } else {
+    snprintf(buf, sizeof buf, "%.15g", v);  // 3-decimal scores and x.5 lengths come out shortest already
+    if (strtod(buf, nullptr) != v) snprintf(buf, sizeof buf, "%.17g", v);
   }
   s += buf;
 }
 
 // save_to_logfile (R/save_logfile.R:17-51) + text form
-void finish_table(nw_table& t) {
-  std::string& s = t.tsv;
+void render_tsv(const nw_table& t, std::string& s) {
   s.clear();
   if (t.kind == 0) {
     s = "eval\tmut1\tmut1_start\tmut1_end\tmut1_pos_pm\tmut1_len\tmut1_len_pm\tmut2_len\tmut2_len_pm\tmut3_len\tmut3_len_pm\n";
@@ -400,16 +438,29 @@ void finish_table(nw_table& t) {
       for (const char* suf : {"_start", "_end", "_len"}) s += "\tmut" + std::to_string(i) + suf;
     s += "\n";
   }
+  s.reserve(s.size() + t.rows.size() * (size_t)(16 + 40 * t.n_mut));
   for (const auto& r : t.rows) {
     fmt_num(s, r.eval);
     if (t.kind == 2) s += "\t" + std::to_string(r.nmoves);
-    for (const std::string& m : r.mut) s += "\t" + (m.empty() ? std::string("NA") : m);
+    for (const std::string& m : r.mut) {
+      s += '\t';
+      if (m.empty())
+        s += "NA";
+      else
+        s += m;
+    }
     for (double v : r.num) {
-      s += "\t";
+      s += '\t';
       fmt_num(s, v);
     }
-    s += "\n";
+    s += '\n';
   }
+}
+
+// the logfile summary of a table (the text form is rendered on demand by nw_table_tsv)
+void finish_table(nw_table& t) {
+  t.tsv.clear();
+  t.tsv_ready = false;
   nw_region_summary& S = t.summ;
   S.n_rows = (int32_t)t.rows.size();
   S.n_mut = t.n_mut;
@@ -501,48 +552,28 @@ void correct_coordinates(std::vector<Sv>& v) {
   }
 }
 
-nw_table* format_solver_output(const char* tsv, int64_t len, const double* gl, int n_gl) {
-  struct Line {
-    std::vector<std::string> f;
-  };
-  std::vector<Line> lines;
-  {
-    int64_t a = 0;
-    while (a < len) {
-      int64_t b = a;
-      while (b < len && tsv[b] != '\n') ++b;
-      if (b > a) {
-        Line L;
-        int64_t s = a;
-        for (int64_t k = a; k <= b; ++k)
-          if (k == b || tsv[k] == '\t') {
-            L.f.emplace_back(tsv + s, tsv + k);
-            s = k + 1;
-          }
-        lines.push_back(std::move(L));
-      }
-      a = b + 1;
-    }
-  }
-  if (lines.empty()) rfail(NW_ERR_PARSE, "solver report is empty");  // read.table stops: no lines available
-  size_t ncols = 0;
-  for (const Line& L : lines) ncols = std::max(ncols, L.f.size());
+// One reported trajectory as format_julia_output sees it: the line's eval, its move count (column V2) and the moves.
+struct TrajIn {
+  double eval;
+  int nmoves;
+  uint32_t mv_off, mv_n;
+};
+
+// Block 1 + 2 + sort of format_julia_output (R/juliasolver.R:68-117) on parsed trajectories.  ncols = the widest line
+// of the report in fields (count.fields): 3 for a 0-move line ("score<TAB>0<TAB>"), 2 + 3m for m moves.
+nw_table* table_from_trajectories(const std::vector<TrajIn>& tr, const std::vector<Sv>& mv, size_t ncols, const double* gl,
+                                  int n_gl) {
+  if (tr.empty()) rfail(NW_ERR_PARSE, "solver report is empty");  // read.table stops: no lines available
   if (ncols < 2) rfail(NW_ERR_PARSE, "solver report needs at least two columns");
   const int n_mut = (int)((ncols - 2) / 3);
   std::unique_ptr<nw_table> T(new nw_table);
-  auto num = [&](const std::string& s) {
-    char* e = nullptr;
-    const double v = strtod(s.c_str(), &e);
-    if (e == s.c_str()) rfail(NW_ERR_PARSE, "solver report: not a number: '" + s + "'");
-    return v;
-  };
   if (n_mut == 0) {  // data.frame(eval = jout[1], nmut = jout[2], mut1 = 'ref')
     T->kind = 2;
     T->n_mut = 1;
-    for (const Line& L : lines) {
+    for (const TrajIn& t : tr) {
       nw_table::Row r;
-      r.eval = num(L.f[0]);
-      r.nmoves = (int)num(L.f.size() > 1 ? L.f[1] : "0");
+      r.eval = t.eval;
+      r.nmoves = t.nmoves;
       r.mut = {"ref"};
       T->rows.push_back(std::move(r));
     }
@@ -551,30 +582,24 @@ nw_table* format_solver_output(const char* tsv, int64_t len, const double* gl, i
   }
   T->kind = 1;
   T->n_mut = n_mut;
-  for (const Line& L : lines) {
+  T->rows.reserve(tr.size() + 1);
+  static const char* const names[3] = {"del", "dup", "inv"};
+  std::vector<Sv> svs;
+  for (const TrajIn& t : tr) {
     nw_table::Row r;
-    r.eval = num(L.f[0]);
-    r.nmoves = (int)num(L.f[1]);
+    r.eval = t.eval;
+    r.nmoves = t.nmoves;
     r.mut.assign(n_mut, "");
     r.num.assign((size_t)3 * n_mut, kNA);
-    std::vector<Sv> svs;
-    for (int i = 0; i < n_mut; ++i) {
-      const size_t c = 2 + 3 * (size_t)i;
-      if (c + 2 >= L.f.size()) continue;  // read.table(fill = TRUE): short lines are padded with NA
-      if (L.f[c].empty()) continue;
-      std::string kind = L.f[c];
-      if (kind.compare(0, 5, "move_") == 0) kind = kind.substr(5);
-      const double a = num(L.f[c + 1]), z = num(L.f[c + 2]);
+    svs.assign(mv.begin() + t.mv_off, mv.begin() + t.mv_off + t.mv_n);
+    for (size_t i = 0; i < svs.size() && (int)i < n_mut; ++i) {
       char buf[96];
-      snprintf(buf, sizeof buf, "%.15g_%.15g_%s", a, z, kind.c_str());
+      snprintf(buf, sizeof buf, "%.15g_%.15g_%s", svs[i].start, svs[i].end, names[svs[i].kind]);  // concat_triplet
       r.mut[i] = buf;
-      const int k = kind == "del" ? 0 : kind == "dup" ? 1 : kind == "inv" ? 2 : -1;
-      if (k < 0) rfail(NW_ERR_PARSE, "solver report: unknown move '" + L.f[c] + "'");
-      svs.push_back(Sv{a, z, k});
     }
     if (r.nmoves != 0) {
-      correct_coordinates(svs);
-      for (size_t i = 0; i < svs.size(); ++i) {
+      correct_coordinates(svs);  // process_row + turn_mut_max_into_svdf
+      for (size_t i = 0; i < svs.size() && (int)i < n_mut; ++i) {
         auto at = [&](double p) {
           const long long k = (long long)p;  // R truncates a double subscript
           return (k >= 1 && k <= n_gl) ? gl[k - 1] : kNA;
@@ -592,6 +617,73 @@ nw_table* format_solver_output(const char* tsv, int64_t len, const double* gl, i
     if (r.nmoves == 0) r.mut[0] = "ref";
   finish_table(*T);
   return T.release();
+}
+
+// the bytes of a solver report (what read.table parses, R/juliasolver.R:58-59)
+nw_table* format_solver_output(const char* tsv, int64_t len, const double* gl, int n_gl) {
+  std::vector<TrajIn> tr;
+  std::vector<Sv> mv;
+  size_t ncols = 0;
+  std::vector<std::pair<int64_t, int64_t>> f;  // [begin, end) of the fields of one line
+  auto num = [&](std::pair<int64_t, int64_t> q) {
+    const std::string t(tsv + q.first, tsv + q.second);
+    char* e = nullptr;
+    const double v = strtod(t.c_str(), &e);
+    if (e == t.c_str()) rfail(NW_ERR_PARSE, "solver report: not a number: '" + t + "'");
+    return v;
+  };
+  int64_t a = 0;
+  while (a < len) {
+    int64_t b = a;
+    while (b < len && tsv[b] != '\n') ++b;
+    if (b > a) {
+      f.clear();
+      int64_t s0 = a;
+      for (int64_t k = a; k <= b; ++k)
+        if (k == b || tsv[k] == '\t') {
+          f.emplace_back(s0, k);
+          s0 = k + 1;
+        }
+      ncols = std::max(ncols, f.size());
+      TrajIn t;
+      t.eval = num(f[0]);
+      t.nmoves = f.size() > 1 ? (int)num(f[1]) : 0;
+      t.mv_off = (uint32_t)mv.size();
+      for (size_t c = 2; c + 2 < f.size(); c += 3) {  // read.table(fill = TRUE): short lines are padded with NA
+        if (f[c].first == f[c].second) break;
+        std::string kind(tsv + f[c].first, tsv + f[c].second);
+        if (kind.compare(0, 5, "move_") == 0) kind = kind.substr(5);
+        const int k = kind == "del" ? 0 : kind == "dup" ? 1 : kind == "inv" ? 2 : -1;
+        if (k < 0) rfail(NW_ERR_PARSE, "solver report: unknown move '" + kind + "'");
+        mv.push_back(Sv{num(f[c + 1]), num(f[c + 2]), k});
+      }
+      t.mv_n = (uint32_t)mv.size() - t.mv_off;
+      tr.push_back(t);
+    }
+    a = b + 1;
+  }
+  return table_from_trajectories(tr, mv, ncols, gl, n_gl);
+}
+
+// the same table straight from a result handle: the trajectories are taken from the result's arrays instead of
+// re-parsing its text.  A reported score is a 3-decimal number printed from Float32 (solver.jl:714, :719), so the
+// double R reads from the text is round(f * 1000) / 1000.
+nw_table* format_solver_result(const nw_result* res, const double* gl, int n_gl) {
+  const int64_t n = nw_result_count(res), nm = nw_result_move_count(res);
+  std::vector<float> sc((size_t)n);
+  std::vector<int32_t> nmv((size_t)n), m3((size_t)nm * 3 + 3);
+  std::vector<int64_t> off((size_t)n);
+  NWCK(nw_result_arrays(res, sc.data(), nmv.data(), off.data(), nullptr, nullptr, nullptr, m3.data()));
+  std::vector<TrajIn> tr((size_t)n);
+  std::vector<Sv> mv((size_t)nm);
+  static const int kmap[3] = {1, 0, 2};  // NW_MOVE_DUP, NW_MOVE_DEL, NW_MOVE_INV -> dup, del, inv
+  for (int64_t k = 0; k < nm; ++k) mv[k] = Sv{(double)m3[k * 3 + 1], (double)m3[k * 3 + 2], kmap[m3[k * 3]]};
+  size_t ncols = 0;
+  for (int64_t k = 0; k < n; ++k) {
+    tr[k] = TrajIn{std::nearbyint((double)sc[k] * 1000.0) / 1000.0, nmv[k], (uint32_t)off[k], (uint32_t)nmv[k]};
+    ncols = std::max<size_t>(ncols, nmv[k] == 0 ? 3 : 2 + 3 * (size_t)nmv[k]);
+  }
+  return table_from_trajectories(tr, mv, ncols, gl, n_gl);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -738,56 +830,63 @@ void prepass_gpu(nw_ctx* ctx, std::vector<PrepassOut*>& Ps, int flags, int& laun
   if (live.empty()) return;
   if (live.size() > 60000) rfail(NW_ERR_ARG, "too many regions in one pre-pass batch");
   const int L0 = nw::ctx_launches(ctx);
-  // ---- estimate sums ----
+  static const bool dbg = getenv("NW_DEBUG_TIMING") != nullptr;
+  auto tnow = [] { return std::chrono::steady_clock::now(); };
+  auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  const auto tp0 = tnow();
+  // ---- estimate sums: inputs are packed straight into the context's pinned staging buffer (one H2D copy) ----
   {
-    std::vector<int64_t> grid_all, off(1, 0);
-    std::vector<int16_t> blk;
-    std::vector<int32_t> meta;  // per entry: grid offset (in int64 elements, two int32), n_x, n_y
+    size_t n_grid = 0, n_blk = 0, ne = 0;
     for (PrepassOut* P : live) {
-      const Grid& g = P->flipped;
-      const int64_t go = (int64_t)grid_all.size();
-      grid_all.insert(grid_all.end(), g.v.begin(), g.v.end());
-      Arr root(g.nx);
-      for (int i = 0; i < g.nx; ++i) root[i] = Pos{(int16_t)(i + 1), 0};
-      for (size_t k = 0; k <= P->cand.size(); ++k) {
-        const Arr& a = k ? P->cand[k - 1] : root;
-        for (const Pos& p : a) blk.push_back(p.blk);
-        off.push_back((int64_t)blk.size());
-        meta.push_back((int32_t)(go & 0xffffffffll));
-        meta.push_back((int32_t)(go >> 32));
-        meta.push_back(g.nx);
-        meta.push_back(g.ny);
-      }
+      n_grid += P->flipped.v.size();
+      n_blk += (size_t)P->flipped.nx;
+      for (const Arr& a : P->cand) n_blk += a.size();
+      ne += P->cand.size() + 1;
     }
-    const size_t ne = off.size() - 1;
     if (ne >= ((size_t)1 << 26)) rfail(NW_ERR_ARG, "too many pre-pass candidates in one batch");
-    std::vector<long long> out(ne * 2);
+    auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };  // the int4 metadata needs 16-byte alignment
+    const size_t o_grid = 0, o_off = o_grid + up16(n_grid * 8), o_meta = o_off + up16((ne + 1) * 8), o_blk = o_meta + ne * 16,
+                 o_out = o_blk + up16(n_blk * 2), total = o_out + ne * 16;
     RCK(cudaSetDevice(nw::ctx_device(ctx)));
     cudaStream_t st = nw::ctx_stream(ctx);
-    void* d = nullptr;
-    auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };  // the int4 metadata needs 16-byte alignment
-    const size_t b_grid = up16(grid_all.size() * 8), b_off = up16(off.size() * 8), b_out = ne * 16, b_meta = meta.size() * 4,
-                 b_blk = up16(blk.size() * 2);
-    RCK(cudaMalloc(&d, b_grid + b_off + b_out + b_meta + b_blk + 64));
-    unsigned char* base = static_cast<unsigned char*>(d);
-    unsigned char *d_grid = base, *d_off = d_grid + b_grid, *d_out = d_off + b_off, *d_meta = d_out + b_out, *d_blk = d_meta + b_meta;
-    try {
-      RCK(cudaMemcpyAsync(d_grid, grid_all.data(), grid_all.size() * 8, cudaMemcpyHostToDevice, st));
-      RCK(cudaMemcpyAsync(d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
-      RCK(cudaMemcpyAsync(d_meta, meta.data(), b_meta, cudaMemcpyHostToDevice, st));
-      RCK(cudaMemcpyAsync(d_blk, blk.data(), blk.size() * 2, cudaMemcpyHostToDevice, st));
-      k_est_diag<<<(unsigned)((ne * 32 + 255) / 256), 256, 0, st>>>((const int64_t*)d_grid, (const int4*)d_meta, (const int16_t*)d_blk,
-                                                                     (const int64_t*)d_off, (int)ne, (long long*)d_out);
-      RCK(cudaGetLastError());
-      ++launches;
-      RCK(cudaMemcpyAsync(out.data(), d_out, b_out, cudaMemcpyDeviceToHost, st));
-      RCK(cudaStreamSynchronize(st));
-    } catch (...) {
-      cudaFree(d);
-      throw;
+    void *hp = nullptr, *dp = nullptr;
+    RCK(nw::ctx_region_staging(ctx, total, &hp, &dp));
+    unsigned char *h = static_cast<unsigned char*>(hp), *d = static_cast<unsigned char*>(dp);
+    int64_t* h_grid = reinterpret_cast<int64_t*>(h + o_grid);
+    int64_t* h_off = reinterpret_cast<int64_t*>(h + o_off);
+    int32_t* h_meta = reinterpret_cast<int32_t*>(h + o_meta);
+    int16_t* h_blk = reinterpret_cast<int16_t*>(h + o_blk);
+    size_t go = 0, bo = 0, e = 0;
+    h_off[0] = 0;
+    for (PrepassOut* P : live) {
+      const Grid& g = P->flipped;
+      memcpy(h_grid + go, g.v.data(), g.v.size() * 8);
+      for (size_t k = 0; k <= P->cand.size(); ++k, ++e) {
+        if (k == 0) {
+          for (int i = 0; i < g.nx; ++i) h_blk[bo++] = (int16_t)(i + 1);
+        } else {
+          for (const Pos& p : P->cand[k - 1]) h_blk[bo++] = p.blk;
+        }
+        h_off[e + 1] = (int64_t)bo;
+        h_meta[e * 4 + 0] = (int32_t)(go & 0xffffffffull);
+        h_meta[e * 4 + 1] = (int32_t)(go >> 32);
+        h_meta[e * 4 + 2] = g.nx;
+        h_meta[e * 4 + 3] = g.ny;
+      }
+      go += g.v.size();
     }
-    cudaFree(d);
-    size_t e = 0;
+    RCK(cudaMemcpyAsync(d, h, o_out, cudaMemcpyHostToDevice, st));
+    k_est_diag<<<(unsigned)((ne * 32 + 255) / 256), 256, 0, st>>>((const int64_t*)(d + o_grid), (const int4*)(d + o_meta),
+                                                                   (const int16_t*)(d + o_blk), (const int64_t*)(d + o_off),
+                                                                   (int)ne, (long long*)(d + o_out));
+    RCK(cudaGetLastError());
+    ++launches;
+    RCK(cudaMemcpyAsync(h + o_out, d + o_out, ne * 16, cudaMemcpyDeviceToHost, st));
+    RCK(cudaStreamSynchronize(st));
+    const long long* out = reinterpret_cast<const long long*>(h + o_out);
+    e = 0;
     for (PrepassOut* P : live)
       for (size_t k = 0; k <= P->cand.size(); ++k, ++e) {
         P->srow[k] = out[e * 2];
@@ -801,7 +900,10 @@ void prepass_gpu(nw_ctx* ctx, std::vector<PrepassOut*>& Ps, int flags, int& laun
     PrepassOut* P = live[r];
     probs[r] = nw::ScoreProblem{P->aln.data(), P->nxa, P->flipped.ny, P->lenx.data(), P->flipped.rn.data()};
   }
+  const auto tp1 = tnow();
+  double tpass[2] = {0, 0};
   for (int pass = 0; pass < 2; ++pass) {
+    const auto tq = tnow();
     std::vector<int16_t> flat;
     std::vector<int64_t> off(1, 0);
     std::vector<uint16_t> rid;
@@ -828,7 +930,9 @@ void prepass_gpu(nw_ctx* ctx, std::vector<PrepassOut*>& Ps, int flags, int& laun
       P->ctotal[who[q].second] = t2[q];
       P->cscore[who[q].second] = s2[q];
     }
+    tpass[pass] = tms(tq, tnow());
   }
+  if (dbg) fprintf(stderr, "[nw_region prepass gpu] estimate %.1f ms, forced ref DP %.1f ms, child DP %.1f ms\n", tms(tp0, tp1), tpass[0], tpass[1]);
   launches += nw::ctx_launches(ctx) - L0;
 }
 
@@ -861,17 +965,23 @@ void prepass_replay(PrepassOut& P, const nw_region_opts& o) {
   };
   std::vector<Rec> recs;
   recs.push_back(Rec{0, -1, s_ref});
-  std::unordered_map<std::vector<int64_t>, double, VecHash> visited;
-  std::vector<int64_t> dv;
-  diag_values(g, root, dv);
-  visited.emplace(dv, s_ref);
+  struct Seen {
+    double eval;
+    size_t entry;  // 0 = the reference arrangement, k = child k
+  };
+  std::unordered_map<DiagKey, Seen, DiagKeyHash> visited;
+  std::vector<int64_t> dv, dv2;
+  visited.emplace(diag_key(g, root), Seen{s_ref, 0});
   if (s_ref >= 0 && P.maxdepth > 0) {
     for (size_t k = 1; k <= nc; ++k) {
       const Arr& a = P.cand[k - 1];
-      diag_values(g, a, dv);
-      auto it = visited.find(dv);
+      const DiagKey key = diag_key(g, a);
+      auto it = visited.find(key);
       if (it != visited.end()) {
-        if (it->second > 1) recs.push_back(Rec{1, (int)k - 1, it->second});
+        diag_values(g, a, dv);  // equal hash: compare the value vectors themselves
+        diag_values(g, it->second.entry ? P.cand[it->second.entry - 1] : root, dv2);
+        if (dv != dv2) rfail(NW_ERR_COLLISION, "pre-pass: two different diagonal bands with one 128-bit hash");
+        if (it->second.eval > 1) recs.push_back(Rec{1, (int)k - 1, it->second.eval});
         continue;
       }
       double s;
@@ -901,7 +1011,7 @@ void prepass_replay(PrepassOut& P, const nw_region_opts& o) {
         }
       }
       if (s > 90) recs.push_back(Rec{1, (int)k - 1, s});
-      visited.emplace(dv, s);
+      visited.emplace(key, Seen{s, k});
     }
   }
   const double step_penalty = (o.compression / sum_cn0 * 100) * 1.5;
@@ -1022,6 +1132,44 @@ nw_opts solver_opts(const nw_region_opts& o, double width) {
   return so;
 }
 
+// Regions are independent on the host side too: the prepare / replay / format phases of a batch run on a few threads.
+void parallel_for(int64_t n, const std::function<void(int64_t)>& fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  const int nt = (int)std::min<int64_t>(std::max<int64_t>(1, n / 8), std::min<unsigned>(hw ? hw : 4, 12));
+  if (nt <= 1) {
+    for (int64_t k = 0; k < n; ++k) fn(k);
+    return;
+  }
+  std::atomic<int64_t> next{0};
+  std::mutex mu;
+  bool failed = false;
+  RErr err{NW_OK, ""};
+  auto work = [&] {
+    for (;;) {
+      const int64_t k = next.fetch_add(1);
+      if (k >= n) return;
+      try {
+        fn(k);
+      } catch (const RErr& e) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!failed) err = e;
+        failed = true;
+        next.store(n);
+      } catch (const std::exception& e) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!failed) err = RErr{NW_ERR_ARG, e.what()};
+        failed = true;
+        next.store(n);
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  if (failed) throw err;
+}
+
 int rguard(const std::function<void()>& fn) {
   try {
     fn();
@@ -1042,22 +1190,30 @@ int rguard(const std::function<void()>& fn) {
 // forest search (nw_solve_many; regions of one width setting per call), format + merge + summary per region.
 void analyse_many(nw_ctx* ctx, const nw_region_problem* regs, int64_t n, const nw_region_opts& o, nw_table** outs,
                   nw_region_summary* summaries) {
+  static const bool dbg = getenv("NW_DEBUG_TIMING") != nullptr;
+  auto tnow = [] { return std::chrono::steady_clock::now(); };
+  auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  const auto t0 = tnow();
   std::vector<PrepassOut> Ps((size_t)n);
   std::vector<PrepassOut*> ptrs;
-  for (int64_t k = 0; k < n; ++k) {
+  parallel_for(n, [&](int64_t k) {
     const nw_region_problem& r = regs[k];
     if (r.n_gridlines > 0 && !r.gridlines_x) rfail(NW_ERR_ARG, "null gridlines");
     prepass_prepare(Ps[k], make_grid(r.grid, r.n_x, r.n_y, r.len_x, r.len_y));
-    ptrs.push_back(&Ps[k]);
-  }
+  });
+  for (int64_t k = 0; k < n; ++k) ptrs.push_back(&Ps[k]);
   int launches = 0;
+  const auto t1 = tnow();
   prepass_gpu(ctx, ptrs, o.flags, launches);
+  const auto t2 = tnow();
   std::vector<nw_region_summary> S((size_t)n);
   std::vector<int64_t> need[2];  // regions that go to the solver, by width setting (plain / reduced by the guard)
   std::vector<std::vector<int8_t>> alns((size_t)n);
+  parallel_for(n, [&](int64_t k) { prepass_replay(Ps[k], o); });
   for (int64_t k = 0; k < n; ++k) {
     PrepassOut& P = Ps[k];
-    prepass_replay(P, o);
     P.launches = k == 0 ? launches : 0;  // the launches are shared by the batch: reported once
     memset(&S[k], 0, sizeof S[k]);
     fill_prepass_summary(S[k], P);
@@ -1067,49 +1223,57 @@ void analyse_many(nw_ctx* ctx, const nw_region_problem* regs, int64_t n, const n
       S[k].solver_called = 1;
       guarded_width(P, o.init_width, S[k].width_reduced);
       need[S[k].width_reduced].push_back(k);
-      alns[k] = sign_matrix(P.flipped);
     }
   }
+  const auto t3 = tnow();
+  double t_solve = 0, t_format = 0;
   for (int wset = 0; wset < 2; ++wset) {
     const std::vector<int64_t>& idx = need[wset];
     if (idx.empty()) continue;
     const nw_opts so = solver_opts(o, wset ? o.init_width / 10 : o.init_width);
     std::vector<nw_problem> probs(idx.size());
+    parallel_for((int64_t)idx.size(), [&](int64_t q) { alns[idx[q]] = sign_matrix(Ps[idx[q]].flipped); });
     for (size_t q = 0; q < idx.size(); ++q) {
       const PrepassOut& P = Ps[idx[q]];
       probs[q] = nw_problem{alns[idx[q]].data(), P.flipped.nx, P.flipped.ny, P.flipped.cn.data(), P.flipped.rn.data()};
     }
     std::vector<nw_result*> res(idx.size(), nullptr);
+    const auto ts0 = tnow();
     if (idx.size() == 1) {
       NWCK(nw_solve(ctx, probs[0].aln_sign, probs[0].n_x, probs[0].n_y, probs[0].len_x, probs[0].len_y, &so, &res[0]));
     } else {
       NWCK(nw_solve_many(ctx, probs.data(), (int64_t)idx.size(), &so, 512, res.data()));
     }
+    const auto ts1 = tnow();
+    t_solve += tms(ts0, ts1);
     try {
-      for (size_t q = 0; q < idx.size(); ++q) {
+      parallel_for((int64_t)idx.size(), [&](int64_t q) {
         const int64_t k = idx[q];
-        const char* data = nullptr;
-        int64_t len = 0;
         nw_stats st{};
-        NWCK(nw_result_tsv(res[q], &data, &len));
         NWCK(nw_result_stats(res[q], &st));
-        std::unique_ptr<nw_table> J(format_solver_output(data, len, regs[k].gridlines_x, regs[k].n_gridlines));
+        std::unique_ptr<nw_table> J(format_solver_result(res[q], regs[k].gridlines_x, regs[k].n_gridlines));
         if (idx.size() == 1 || q % 512 == 0) S[k].gpu_launches += st.kernel_launches;  // counters are per pass
         S[k].search_depth = o.depth;  // format_julia_output overwrites the log counters (R/juliasolver.R:63-65, :107-111)
         S[k].mut_simulated = S[k].mut_tested = J->kind == 2 ? 0 : (int64_t)J->rows.size();
         merge_tables(Ps[k].table, J);
-      }
+      });
     } catch (...) {
       for (nw_result* r : res) nw_result_free(r);
       throw;
     }
     for (nw_result* r : res) nw_result_free(r);
+    t_format += tms(ts1, tnow());
   }
-  for (int64_t k = 0; k < n; ++k) {
+  const auto t4 = tnow();
+  parallel_for(n, [&](int64_t k) {
     finish_region(Ps[k].table, S[k]);
     if (summaries) summaries[k] = S[k];
-  }
+  });
   for (int64_t k = 0; k < n; ++k) outs[k] = Ps[k].table.release();
+  if (dbg)
+    fprintf(stderr, "[nw_region] %lld regions: prepare %.1f ms, prepass gpu %.1f ms, replay %.1f ms, solver %.1f ms (%zu regions), "
+                    "format+merge %.1f ms, finish %.1f ms\n", (long long)n, tms(t0, t1), tms(t1, t2), tms(t2, t3), t_solve,
+            need[0].size() + need[1].size(), t_format, tms(t4, tnow()));
 }
 
 }  // namespace
@@ -1199,6 +1363,10 @@ int nw_table_tsv(const nw_table* t, const char** data, int64_t* len) {
   if (!t || !data || !len) {
     nw::set_last_error("null argument");
     return NW_ERR_ARG;
+  }
+  if (!t->tsv_ready) {
+    render_tsv(*t, t->tsv);
+    t->tsv_ready = true;
   }
   *data = t->tsv.data();
   *len = (int64_t)t->tsv.size();

@@ -30,6 +30,44 @@ def make_regions(n, seed=0):
     return out
 
 
+def make_stage_regions(n, seed=0):
+    """The same generator, but as the wrapper sees a region: (mat[n_y, n_x] signed bp, len_y, len_x, gridlines_x)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(n):
+        n_x = int(rng.integers(20, 121))
+        fams = [int(rng.integers(2, 5)) for _ in range(int(rng.integers(2, 7)))]
+        while sum(fams) > n_x:
+            fams.pop()
+        mat, lx, ly, _ = sdgrid(n_x, fams, seed=1000 + k, chain_depth=int(rng.integers(1, 4)), len_tol=0.3)
+        out.append((mat, ly, lx, np.concatenate([[0], np.cumsum(lx)])))
+    return out
+
+
+def _stage_cpu_one(reg):
+    """One region through the R restatement (pre-pass, gate, flip, C++ oracle solver, format, merge, summary)."""
+    from oracle import nw_region_oracle as ro, oracle_lib
+    mat, ly, lx, gl = reg
+
+    def solver(aln, lx_, ly_, d, u, w, r, R):
+        return oracle_lib.solve(aln, lx_, ly_, maxdepth=d, maxdup=u, maxwidth=int(w), minreport=r, maxreport=R,
+                                full=False).tsv
+    A = ro.analyse_region(mat, ly, lx, gl, solver, depth=3, maxdup=2, init_width=1000, minreport=0.98)
+    return A["mut_max"], A["res_max"], A["julia_called"]
+
+
+def run_stage_cpu(regions, procs):
+    """CPU arm of the region stage: one region per worker process at a time (what R's threads= does)."""
+    import multiprocessing as mp
+    from oracle import oracle_lib
+    oracle_lib.lib()
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = pool.map(_stage_cpu_one, regions, chunksize=1)
+    dt = time.perf_counter() - t0
+    return len(regions) / dt, res, dt
+
+
 def run_gpu(regions, threads, device=0):
     solvers = [nb.Solver(device) for _ in range(threads)]
     for s in solvers:  # warm-up (pool, module load)
