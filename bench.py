@@ -263,14 +263,28 @@ def run_stage(args, rank, world, local):
     call, host buffers in, result tables in host memory out.  --impl reference: the R restatement (Python) around the
     C++ oracle solver, one region per worker process."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
-    from region_batch import make_stage_regions, run_stage_cpu
+    from region_batch import genome_plan, make_genome_regions, make_stage_regions, run_stage_cpu
     cores = os.cpu_count() or 1
-    desc = ("solver stage of a regionfile batch (R depth-1 pre-pass + solver -d 3 -u 2 -w 1000 -r 0.98 -R 1000 + "
-            "format/merge/logfile summary): %d synthetic SD-flanked regions per GPU, 20-120 blocks")
+    genome = args.workload == "genome"
+    if genome:
+        # config 5: a fixed genome-wide window list, LPT-sharded over the GPUs (strong scaling), blacklist on the host
+        from nahrwhals_b200.distributed import shard_regions
+        plan = genome_plan(args.regions, seed=0)
+        shards = shard_regions([c for _, _, c in plan], max(world, 1))
+        desc = ("solver stage of whole-genome mode (synthetic T2T-sized pair: %%d candidate windows of 200 kb / 1 Mb / "
+                "5 Mb -> 10-124 blocks per axis, %d left after the blacklist), R depth-1 pre-pass + solver -d 3 -u 2 "
+                "-w 1000 -r 0.98 -R 1000 + format/merge/logfile summary" % len(plan))
+    else:
+        desc = ("solver stage of a regionfile batch (R depth-1 pre-pass + solver -d 3 -u 2 -w 1000 -r 0.98 -R 1000 + "
+                "format/merge/logfile summary): %d synthetic SD-flanked regions per GPU, 20-120 blocks")
     if args.impl == "reference":
         if rank != 0:
             return
-        regs = make_stage_regions(max(32, args.regions // 40), seed=0)
+        if genome:
+            step = max(1, len(plan) // max(32, args.regions // 40))
+            regs = make_genome_regions(plan, list(range(0, len(plan), step)))
+        else:
+            regs = make_stage_regions(max(32, args.regions // 40), seed=0)
         r, _, dt = run_stage_cpu(regs, cores)
         print(json.dumps(dict(impl="reference", metric="regions_solved_per_s", value=r, unit="regions/s",
                               n_gpus=args.gpus, steps=1, warmup=0, ms_per_step=1e3 * dt, higher_is_better=True,
@@ -288,8 +302,12 @@ def run_stage(args, rank, world, local):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    regs = make_stage_regions(args.regions, seed=rank)
-    warm = make_stage_regions(min(args.regions, 1500), seed=1000 + rank)
+    if genome:
+        regs = make_genome_regions(plan, shards[rank])
+        warm = make_stage_regions(min(len(regs), 1500), seed=1000 + rank)
+    else:
+        regs = make_stage_regions(args.regions, seed=rank)
+        warm = make_stage_regions(min(args.regions, 1500), seed=1000 + rank)
     solver = nb.Solver(local)
     kw = dict(depth=3, maxdup=2, init_width=1000, minreport=0.98)
     for _ in range(max(1, args.warmup_regions)):
@@ -321,15 +339,22 @@ def run_stage(args, rank, world, local):
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
         n, called, launches, cands = s.tolist()
     line = dict(metric="regions_solved_per_s", value=n / dt, unit="regions/s", n_gpus=world, steps=steps,
-                warmup=max(1, args.warmup_regions), ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak",
-                vs_baseline=None, dtype="int32", data="synthetic",
-                config=dict(workload=(desc % args.regions) + "; one context per GPU, regions shard per GPU, no collective",
+                warmup=max(1, args.warmup_regions), ms_per_step=1e3 * dt, higher_is_better=True,
+                scaling="strong" if genome else "weak", vs_baseline=None, dtype="int32", data="synthetic",
+                config=dict(workload=(desc % args.regions) + ("; windows LPT-sharded over the GPUs by estimated work, "
+                                                              "no collective on the data path" if genome else
+                                                              "; one context per GPU, regions shard per GPU, no collective"),
+                            solver_stage_seconds=dt,
                             solver_called=int(called), prepass_candidates=int(cands),
                             timed="wall clock around nw_region_analyse_many (host buffers in, result tables out)"),
                 clocks=clocks, e2e=dict(value=n / dt, unit="regions/s", h2d_bytes_per_step=None, d2h_bytes_per_step=None),
                 gpu_launches=int(launches))
     if rank == 0 and world == 1 and not args.no_cpu:
-        sample = make_stage_regions(max(32, args.regions // 40), seed=0)
+        if genome:
+            step = max(1, len(plan) // max(32, args.regions // 40))
+            sample = make_genome_regions(plan, list(range(0, len(plan), step)))
+        else:
+            sample = make_stage_regions(max(32, args.regions // 40), seed=0)
         r, _, cdt = run_stage_cpu(sample, cores)
         line["cpu_baseline"] = dict(value=r, unit="regions/s", cores=cores, kind="port",
                                     sample="%d regions of the same generator, %.1f s, one region per worker process; R "
@@ -396,7 +421,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS) + ["regions", "stage"])
+    ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS) + ["regions", "stage", "genome"])
     ap.add_argument("--regions", type=int, default=6000, help="regions per rank for --workload regions")
     ap.add_argument("--contexts", type=int, default=4, help="solver contexts (streams) per GPU for --workload regions")
     ap.add_argument("--warmup-regions", type=int, default=2, help="untimed warm-up runs for --workload regions")
@@ -414,7 +439,7 @@ def main():
     if args.workload == "regions":
         run_regions(args, rank, world, local)
         return
-    if args.workload == "stage":
+    if args.workload in ("stage", "genome"):
         run_stage(args, rank, world, local)
         return
     if args.impl == "reference":

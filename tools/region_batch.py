@@ -44,6 +44,40 @@ def make_stage_regions(n, seed=0):
     return out
 
 
+def genome_plan(n, seed=0, blacklist_frac=0.08):
+    """BASELINE.json config 5: the solver stage of whole-genome mode on a synthetic T2T-sized pair.  Window sizes follow
+    scan_for_windows (R/wholegenome.R:24: 200 kb / 1 Mb / 5 Mb) -> gridmatrices of 10-40 / 40-100 / 100-124 blocks per
+    axis (the reference caps a grid at 250 gridlines, R/nahrwhals.R:55); a blacklist (ref_masked_regions) removes a
+    fraction of the windows on the host before the solver stage.  Returns [(index, generator kwargs, cost estimate)] of
+    the windows that survive -- cheap to compute for the whole genome on every rank; the matrices themselves are only
+    built for a rank's own shard (make_genome_regions)."""
+    rng = np.random.default_rng(seed)
+    plan = []
+    for k in range(n):
+        cls = rng.choice(3, p=[0.70, 0.25, 0.05])
+        n_x = int(rng.integers(*((10, 41), (40, 101), (100, 125))[cls]))
+        fams = [int(rng.integers(2, 5)) for _ in range(int(rng.integers(1, (4, 6, 8)[cls])))]
+        while sum(fams) > n_x:
+            fams.pop()
+        depth = int(rng.integers(1, 4))
+        masked = rng.random() < blacklist_frac
+        if masked:
+            continue
+        pairs = sum(m * (m - 1) // 2 for m in fams)
+        cost = float(n_x * n_x) * (1.0 + min(float(pairs) ** 3, 1000.0 * pairs * 2))
+        plan.append((k, dict(n_x=n_x, families=fams, seed=7000 + k, chain_depth=depth, len_tol=0.2), cost))
+    return plan
+
+
+def make_genome_regions(plan, idx):
+    out = []
+    for q in idx:
+        _, kw, _ = plan[q]
+        mat, lx, ly, _ = sdgrid(**kw)
+        out.append((mat, ly, lx, np.concatenate([[0], np.cumsum(lx)])))
+    return out
+
+
 def _stage_cpu_one(reg):
     """One region through the R restatement (pre-pass, gate, flip, C++ oracle solver, format, merge, summary)."""
     from oracle import nw_region_oracle as ro, oracle_lib
