@@ -7,4 +7,5 @@ interface on top of that ABI.  There is no CPU fallback.
 from .solver import (Solver, SolveResult, read_problem, solve_batch, solve_many, solve_files_many, main,  # noqa: F401
                      MOVE_NAMES)  # noqa: F401
 from .region import solve_mutation_depth1, format_julia_output, analyse_region, analyse_regions, RegionResult  # noqa: F401
+from .grid import build_grids, paf_to_gridmatrix, GridResult  # noqa: F401
 from .sdgrid import sdgrid, to_solver_inputs, write_tsvs  # noqa: F401
