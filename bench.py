@@ -367,6 +367,98 @@ def run_stage(args, rank, world, local):
     solver.close()
 
 
+def _grid_cpu_one(p):
+    from oracle import nw_grid_oracle as go
+    try:
+        return go.paf_to_gridmatrix(*p)["mat"].shape
+    except Exception:
+        return None
+
+
+def run_grid(args, rank, world, local):
+    """the gridding step upstream of the solver (make_xy_grid_fast + bressiwrap +
+    gridlist_to_gridmatrix) for a batch of regions through nw_grid_build.  Metric: regions/s, wall clock around the
+    C-ABI call (host alignment arrays in, gridlines + gridmatrices in host memory out).  --impl reference: the R
+    restatement (Python) on all host cores, one region per worker process."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from region_batch import make_stage_regions
+    from nahrwhals_b200.sdgrid import matrix_to_alignments
+    cores = os.cpu_count() or 1
+    desc = "gridding of a regionfile batch: alignments of %d synthetic SD-flanked regions per GPU (20-120 blocks) -> gridlines -> gridmatrix"
+
+    def cpu(pafs):
+        import multiprocessing as mp
+        t0 = time.perf_counter()
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_grid_cpu_one, pafs, chunksize=4)
+        return len(pafs) / (time.perf_counter() - t0), time.perf_counter() - t0
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        pafs = [matrix_to_alignments(m, lx, ly) for m, ly, lx, _ in make_stage_regions(max(64, args.regions // 20), seed=0)]
+        r, dt = cpu(pafs)
+        print(json.dumps(dict(impl="reference", metric="regions_gridded_per_s", value=r, unit="regions/s", n_gpus=args.gpus,
+                              steps=1, warmup=0, ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak",
+                              vs_baseline=None, dtype="f64", data="synthetic", config=dict(workload=desc % len(pafs)),
+                              cpu_baseline=dict(value=r, unit="regions/s", cores=cores, kind="port",
+                                                sample="%d regions, one per worker process" % len(pafs)),
+                              e2e=dict(value=r, unit="regions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                              gpu_launches=0)), flush=True)
+        return
+    import torch
+    import nahrwhals_b200 as nb
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pafs = [matrix_to_alignments(m, lx, ly) for m, ly, lx, _ in make_stage_regions(args.regions, seed=rank)]
+    solver = nb.Solver(local)
+    for _ in range(3):
+        nb.build_grids(solver, pafs[:min(len(pafs), 1000)])
+    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler.start()
+    steps = max(1, args.steps)
+    dt = 0.0
+    for _ in range(steps):
+        tm = {}
+        grids, rcs = nb.build_grids(solver, pafs, timing=tm)
+        dt += tm["native_s"]
+    torch.cuda.synchronize()
+    dt /= steps
+    clocks = sampler.stop()
+    n, ok = len(pafs), sum(1 for r in rcs if r == 0)
+    alns = sum(len(p[0]) for p in pafs)
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        s = torch.tensor([n, ok, alns], dtype=torch.float64, device="cuda")
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        n, ok, alns = s.tolist()
+    line = dict(metric="regions_gridded_per_s", value=n / dt, unit="regions/s", n_gpus=world, steps=steps, warmup=3,
+                ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=(desc % args.regions) + "; regions shard per GPU, no collective", grids_built=int(ok),
+                            alignments=int(alns), timed="wall clock around nw_grid_build (host arrays in, grids out)"),
+                clocks=clocks, e2e=dict(value=n / dt, unit="regions/s", h2d_bytes_per_step=int(alns) * 36,
+                                        d2h_bytes_per_step=None), gpu_launches=3 * steps * max(world, 1))
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = pafs[:max(64, args.regions // 20)]
+        r, cdt = cpu(sample)
+        line["cpu_baseline"] = dict(value=r, unit="regions/s", cores=cores, kind="port",
+                                    sample="%d regions of the same set, %.1f s, one region per worker process; R "
+                                           "restatement in Python" % (len(sample), cdt))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    solver.close()
+
+
 def run_frontier(args, rank, world, local):
     """BASELINE.json config 3: ONE deep search sharded over the GPUs (frontier round-robin, per-level all-gather of
     40-byte records over NCCL, deterministic merge on every rank).  Strong scaling: total work is fixed."""
@@ -421,7 +513,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS) + ["regions", "stage", "genome"])
+    ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS) + ["regions", "stage", "genome", "grid"])
     ap.add_argument("--regions", type=int, default=6000, help="regions per rank for --workload regions")
     ap.add_argument("--contexts", type=int, default=4, help="solver contexts (streams) per GPU for --workload regions")
     ap.add_argument("--warmup-regions", type=int, default=2, help="untimed warm-up runs for --workload regions")
@@ -438,6 +530,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload == "regions":
         run_regions(args, rank, world, local)
+        return
+    if args.workload == "grid":
+        run_grid(args, rank, world, local)
         return
     if args.workload in ("stage", "genome"):
         run_stage(args, rank, world, local)

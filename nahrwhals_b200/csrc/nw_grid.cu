@@ -10,6 +10,7 @@
 // Every double expression uses the explicit round-to-nearest intrinsics so that no FMA is formed.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -277,6 +278,10 @@ __global__ void k_grid_fill(const RegionIn* __restrict__ rin, const int* __restr
   }
 }
 
+__global__ void k_grid_clear(unsigned long long* mats, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) mats[i] = EMPTY_BITS;
+}
 __global__ void k_grid_finish(unsigned long long* mats, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && mats[i] == EMPTY_BITS) mats[i] = 0ull;
@@ -386,10 +391,8 @@ int nw_grid_build(nw_ctx* ctx, const nw_paf* pafs, int64_t n_regions, nw_grid** 
       if (cells > 0) {
         GCK(cudaMalloc(&dmat, (size_t)cells * 8));
         try {
-          // EMPTY pattern: every byte pair differs, so fill with a tiny kernel-free trick: memset cannot write it ->
-          // upload a pattern buffer once per call
-          std::fill(hmat.begin(), hmat.end(), EMPTY_BITS);
-          GCK(cudaMemcpyAsync(dmat, hmat.data(), (size_t)cells * 8, cudaMemcpyHostToDevice, st));
+          k_grid_clear<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(dmat, cells);
+          GCK(cudaGetLastError());
           GCK(cudaMemcpyAsync(d + o_rout, h + o_rout, up16(R * sizeof(RegionOut)), cudaMemcpyHostToDevice, st));
           k_grid_fill<<<(unsigned)((n_aln + 127) / 128), 128, 0, st>>>(
               (const RegionIn*)(d + o_rin), (const int*)(d + o_areg), n_aln, (const double*)(d + o_ts), (const double*)(d + o_te),
@@ -404,7 +407,12 @@ int nw_grid_build(nw_ctx* ctx, const nw_paf* pafs, int64_t n_regions, nw_grid** 
           throw;
         }
       }
-      GCK(cudaMemcpyAsync(h + o_rout, d + o_rout, total - o_rout, cudaMemcpyDeviceToHost, st));
+      {  // status words, and only the used prefix of every region's gridline rows
+        int mx = 2;
+        for (size_t r = 0; r < R; ++r) mx = std::max(mx, std::max(rout[r].n_gx, rout[r].n_gy));
+        GCK(cudaMemcpyAsync(h + o_rout, d + o_rout, up16(R * sizeof(RegionOut)), cudaMemcpyDeviceToHost, st));
+        GCK(cudaMemcpy2DAsync(h + o_gx, (size_t)CAP * 8, d + o_gx, (size_t)CAP * 8, (size_t)mx * 8, 2 * R, cudaMemcpyDeviceToHost, st));
+      }
       GCK(cudaStreamSynchronize(st));
       if (dmat) cudaFree(dmat);
       const double* hgx = reinterpret_cast<const double*>(h + o_gx);

@@ -98,3 +98,16 @@ def random_grid(n_x, n_y, density, seed, len_choices=(1, 2, 3, 5, 8, 13)):
             sign[k * n_y // max(n_x, n_y) if n_y < n_x else k, k if n_y >= n_x else k] = 1
     mat = sign * len_x[None, :]
     return mat.astype(np.int64), len_x.astype(np.int64), len_y.astype(np.int64)
+
+
+def matrix_to_alignments(mat, len_x, len_y):
+    """The alignments a signed gridmatrix stands for, in the reference's paf columns (tstart, tend, qstart, qend):
+    one slope +-1 segment per non-zero cell (reverse strand: qstart > qend).  Input of the gridding step."""
+    ox = np.concatenate([[0], np.cumsum(len_x)]).astype(np.float64)
+    oy = np.concatenate([[0], np.cumsum(len_y)]).astype(np.float64)
+    ys, xs = np.nonzero(mat)
+    pos = mat[ys, xs] > 0
+    ts, te = ox[xs], ox[xs + 1]
+    qs = np.where(pos, oy[ys], oy[ys + 1])
+    qe = np.where(pos, oy[ys + 1], oy[ys])
+    return ts, te, qs, qe
