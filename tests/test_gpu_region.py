@@ -156,3 +156,15 @@ def test_region_batch_equals_single(solver, oracle):
             assert B[k].mut_max == O["mut_max"]
     assert 5 < called < len(regs)          # both branches of the 99.8 gate are in the batch
     assert nb.analyse_regions(solver, []) == []
+
+
+def test_region_golden_fixture_gpu(solver):
+    """nw_table_tsv of the CUDA path, byte for byte against the committed tables of the test run."""
+    from tests.test_region_oracle import GOLD
+    mat, ly, lx = load_testrun()
+    gl = np.concatenate([[0], np.cumsum(lx)])
+    for d in (2, 3):
+        P = nb.analyse_region(solver, mat, ly, lx, gl, depth=d)
+        head, body = open(os.path.join(GOLD, "testrun_region_d%d.tsv" % d)).read().split("\n", 1)
+        assert P.tsv == body
+        assert "mut_max=%s" % P.mut_max in head and "n_res_max=%d " % P.n_res_max in head

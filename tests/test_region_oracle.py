@@ -132,3 +132,18 @@ def test_product_formatter_matches_oracle(oracle, seed):
     assert P.rows == [dict(eval=100.0, nmut=0.0, mut1="ref")] and P.mut_max == "ref"
     with pytest.raises(Exception):
         nb.format_julia_output("", gl)
+
+
+def test_region_golden_fixture(oracle):
+    """The committed region tables of the test run (tests/golden/make_region_fixture.py) still come out of the oracle."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mrf", os.path.join(GOLD, "make_region_fixture.py"))
+    mrf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mrf)
+    mat, ly, lx = load_testrun()
+    gl = np.concatenate([[0], np.cumsum(lx)])
+    for d in (2, 3):
+        A = ro.analyse_region(mat, ly, lx, gl, oracle_solver(oracle), depth=d)
+        gold = open(os.path.join(GOLD, "testrun_region_d%d.tsv" % d)).read().split("\n", 1)
+        assert gold[1] == mrf.render(A["res"])
+        assert "mut_max=%s" % A["mut_max"] in gold[0]
