@@ -2324,9 +2324,12 @@ void nw_result_free(nw_result* r) { delete r; }
 // through the banded-DP kernels in ONE bucketed pass.  nw_score_batch is the R == 1 case; the region pre-pass
 // (nw_region.cu) hands in the depth-1 children of a whole batch of regions at once.
 namespace nw {
+// depth_floor: lower bound of the int32-range depth the region contexts are built for; reuse_regions != 0: the region
+// contexts of the previous call on this context (same problems, depth_floor covering this call) are kept and only the
+// corridor mode is switched -- the pre-pass scores the same regions twice (forced reference row, then the children).
 int score_batch_regions(nw_ctx* c, const ScoreProblem* probs, int R, const uint16_t* rid, const int16_t* flat,
                         const int64_t* off, int64_t n, int force, int flags, int64_t* cost_bp, int64_t* total_bp,
-                        double* score) {
+                        double* score, int depth_floor, int reuse_regions) {
   if (!c || !probs || R < 1 || !flat || !off || n < 0) {
     g_last_error = "null argument";
     return NW_ERR_ARG;
@@ -2339,7 +2342,7 @@ int score_batch_regions(nw_ctx* c, const ScoreProblem* probs, int R, const uint1
     if (force < 0 || force > 2) fail(NW_ERR_ARG, "force must be 0 (slow_score), 1 (forcecalc) or 2 (R twin corridor)");
     cudaStream_t s = c->stream;
     int maxlen = 1;
-    int depth_equiv = 0;  // depth bound for the int32 range: candidates may hold each block up to len/n_x times
+    int depth_equiv = std::max(0, depth_floor);  // depth bound for the int32 range: a block may occur up to len/n_x times
     for (int64_t k = 0; k < n; ++k) {
       const int r = rid ? rid[k] : 0;
       if (r >= R) fail(NW_ERR_ARG, "candidate region out of range");
@@ -2353,7 +2356,14 @@ int score_batch_regions(nw_ctx* c, const ScoreProblem* probs, int R, const uint1
         if (v == 0 || v > n_x || v < -n_x) fail(NW_ERR_ARG, "candidate element out of range");
       }
     }
-    {
+    if (reuse_regions && c->n_regions == R && depth_equiv <= depth_floor) {
+      for (int r = 0; r < R; ++r) {  // same contexts, other corridor tables
+        const int ny = c->RH[r].n_y;
+        BandStore& bs = c->band_cache[ny * 3 + force];
+        if (bs.n_y != ny || bs.force != force) bs.reset(ny, force);
+        c->rbands[r] = &bs;
+      }
+    } else {
       std::vector<ProblemRef> P(R);
       for (int r = 0; r < R; ++r) P[r] = ProblemRef{probs[r].aln, probs[r].n_x, probs[r].n_y, probs[r].len_x, probs[r].len_y};
       setup_regions(c, P.data(), R, depth_equiv, force);
@@ -2435,7 +2445,7 @@ int nw_score_batch(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const
     return NW_ERR_ARG;
   }
   const nw::ScoreProblem P{aln, n_x, n_y, len_x, len_y};
-  return nw::score_batch_regions(c, &P, 1, nullptr, flat, off, n, force, flags, cost_bp, total_bp, score);
+  return nw::score_batch_regions(c, &P, 1, nullptr, flat, off, n, force, flags, cost_bp, total_bp, score, 0, 0);
 }
 
 int nw_moveset(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, uint8_t* dup_del, uint8_t* invert) {

@@ -44,7 +44,7 @@ struct ScoreProblem {
 };
 int score_batch_regions(nw_ctx* c, const ScoreProblem* probs, int R, const uint16_t* rid, const int16_t* flat,
                         const int64_t* off, int64_t n, int force, int flags, int64_t* cost_bp, int64_t* total_bp,
-                        double* score);
+                        double* score, int depth_floor, int reuse_regions);
 }  // namespace nw
 
 namespace {
@@ -902,6 +902,7 @@ void prepass_gpu(nw_ctx* ctx, std::vector<PrepassOut*>& Ps, int flags, int& laun
   }
   const auto tp1 = tnow();
   double tpass[2] = {0, 0};
+  int did_pass0 = 0;  // pass 1 reuses the region contexts pass 0 built (a child holds a block at most twice: depth 1)
   for (int pass = 0; pass < 2; ++pass) {
     const auto tq = tnow();
     std::vector<int16_t> flat;
@@ -923,7 +924,8 @@ void prepass_gpu(nw_ctx* ctx, std::vector<PrepassOut*>& Ps, int flags, int& laun
     std::vector<int64_t> c2(who.size()), t2(who.size());
     std::vector<double> s2(who.size());
     NWCK(nw::score_batch_regions(ctx, probs.data(), (int)live.size(), rid.data(), flat.data(), off.data(), (int64_t)who.size(),
-                                 pass ? 2 : 1, flags & NW_FLAG_GENERIC_DP, c2.data(), t2.data(), s2.data()));
+                                 pass ? 2 : 1, flags & NW_FLAG_GENERIC_DP, c2.data(), t2.data(), s2.data(), 1, pass && did_pass0));
+    if (pass == 0) did_pass0 = 1;
     for (size_t q = 0; q < who.size(); ++q) {
       PrepassOut* P = live[who[q].first];
       P->ccost[who[q].second] = c2[q];
@@ -1133,9 +1135,10 @@ nw_opts solver_opts(const nw_region_opts& o, double width) {
 }
 
 // Regions are independent on the host side too: the prepare / replay / format phases of a batch run on a few threads.
+thread_local int g_host_threads = 12;  // budget of the calling thread (divided among contexts by the _ctxs entry point)
 void parallel_for(int64_t n, const std::function<void(int64_t)>& fn) {
   unsigned hw = std::thread::hardware_concurrency();
-  const int nt = (int)std::min<int64_t>(std::max<int64_t>(1, n / 8), std::min<unsigned>(hw ? hw : 4, 12));
+  const int nt = (int)std::min<int64_t>(std::max<int64_t>(1, n / 8), std::min<unsigned>(hw ? hw : 4, (unsigned)std::max(1, g_host_threads)));
   if (nt <= 1) {
     for (int64_t k = 0; k < n; ++k) fn(k);
     return;
@@ -1346,6 +1349,59 @@ int nw_region_analyse_many(nw_ctx* ctx, const nw_region_problem* regions, int64_
         }
         throw;
       }
+    }
+  });
+}
+
+int nw_region_analyse_many_ctxs(nw_ctx** ctxs, int32_t n_ctx, const nw_region_problem* regions, int64_t n,
+                                const nw_region_opts* opts, int32_t regions_per_batch, nw_table** outs,
+                                nw_region_summary* summaries) {
+  if (outs)
+    for (int64_t k = 0; k < n; ++k) outs[k] = nullptr;
+  return rguard([&] {
+    if (!ctxs || n_ctx < 1 || !opts || !outs || n < 0 || (n > 0 && !regions)) rfail(NW_ERR_ARG, "null argument");
+    for (int t = 0; t < n_ctx; ++t)
+      if (!ctxs[t]) rfail(NW_ERR_ARG, "null context");
+    const int64_t B = regions_per_batch > 0 ? std::min<int64_t>(regions_per_batch, 4096) : 1024;
+    const int64_t nb = (n + B - 1) / B;
+    std::atomic<int64_t> next{0};
+    std::mutex mu;
+    bool failed = false;
+    RErr err{NW_OK, ""};
+    unsigned hw = std::thread::hardware_concurrency();
+    const int per_ctx = std::max(2, (int)(hw ? hw : 8) / n_ctx);
+    auto work = [&](int t) {
+      g_host_threads = per_ctx;
+      for (;;) {
+        const int64_t b = next.fetch_add(1);
+        if (b >= nb) return;
+        const int64_t a = b * B, m = std::min(B, n - a);
+        try {
+          analyse_many(ctxs[t], regions + a, m, *opts, outs + a, summaries ? summaries + a : nullptr);
+        } catch (const RErr& e) {
+          std::lock_guard<std::mutex> lk(mu);
+          if (!failed) err = e;
+          failed = true;
+          next.store(nb);
+        } catch (const std::exception& e) {
+          std::lock_guard<std::mutex> lk(mu);
+          if (!failed) err = RErr{NW_ERR_ARG, e.what()};
+          failed = true;
+          next.store(nb);
+        }
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_ctx; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    g_host_threads = 12;
+    if (failed) {
+      for (int64_t k = 0; k < n; ++k) {
+        nw_table_free(outs[k]);
+        outs[k] = nullptr;
+      }
+      throw err;
     }
   });
 }

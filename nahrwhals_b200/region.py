@@ -30,7 +30,8 @@ class NwRegionSummary(C.Structure):
 
 
 SYMBOLS = ["nw_region_default_opts", "nw_region_prepass", "nw_region_format", "nw_region_analyse", "nw_table_summary",
-           "nw_table_mut_max", "nw_table_tsv", "nw_table_rows", "nw_table_free", "nw_table_candidates", "nw_region_analyse_many"]
+           "nw_table_mut_max", "nw_table_tsv", "nw_table_rows", "nw_table_free", "nw_table_candidates", "nw_region_analyse_many",
+           "nw_region_analyse_many_ctxs"]
 
 
 class NwRegionProblem(C.Structure):
@@ -60,6 +61,7 @@ def _lib_region():
         L.nw_region_analyse.argtypes = [vp, vp, i32, i32, vp, vp, vp, i32, C.POINTER(NwRegionOpts), C.POINTER(vp),
                                         C.POINTER(NwRegionSummary)]
         L.nw_region_analyse_many.argtypes = [vp, vp, i64, C.POINTER(NwRegionOpts), vp, vp]
+        L.nw_region_analyse_many_ctxs.argtypes = [vp, i32, vp, i64, C.POINTER(NwRegionOpts), i32, vp, vp]
         L.nw_table_summary.argtypes = [vp, C.POINTER(NwRegionSummary)]
         L.nw_table_mut_max.restype = C.c_char_p
         L.nw_table_mut_max.argtypes = [vp]
@@ -183,9 +185,10 @@ def analyse_region(solver, mat, len_y, len_x, gridlines_x, depth=3, maxdup=2, in
 
 
 def analyse_regions(solver, regions, depth=3, maxdup=2, init_width=1000, minreport=0.98, compression=1000, timing=None,
-                    **kw):
+                    regions_per_batch=1024, **kw):
     """Regionfile mode: the solver stage of many regions in one call (nw_region_analyse_many).  `regions` is a list of
-    (mat[n_y, n_x], len_y, len_x, gridlines_x).  Returns one RegionResult per region, identical to analyse_region."""
+    (mat[n_y, n_x], len_y, len_x, gridlines_x); `solver` may be a list of Solvers (contexts) that share the batches.
+    Returns one RegionResult per region, identical to analyse_region."""
     import time
     L = _lib_region()
     n = len(regions)
@@ -200,7 +203,11 @@ def analyse_regions(solver, regions, depth=3, maxdup=2, init_width=1000, minrepo
     outs = (C.c_void_p * max(n, 1))()
     summ = (NwRegionSummary * max(n, 1))()
     t0 = time.perf_counter()
-    _lib.check(L.nw_region_analyse_many(solver.h, probs, n, C.byref(o), outs, summ))
+    if isinstance(solver, (list, tuple)):  # several contexts: batches handed out dynamically (nw_region_analyse_many_ctxs)
+        hs = (C.c_void_p * len(solver))(*[s_.h for s_ in solver])
+        _lib.check(L.nw_region_analyse_many_ctxs(hs, len(solver), probs, n, C.byref(o), int(regions_per_batch), outs, summ))
+    else:
+        _lib.check(L.nw_region_analyse_many(solver.h, probs, n, C.byref(o), outs, summ))
     if timing is not None:
         timing["native_s"] = time.perf_counter() - t0
     return [RegionResult(L, C.c_void_p(outs[k]), summ[k]) for k in range(n)]

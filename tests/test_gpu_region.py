@@ -155,6 +155,14 @@ def test_region_batch_equals_single(solver, oracle):
             _rows_equal(B[k].rows, O["res"])
             assert B[k].mut_max == O["mut_max"]
     assert 5 < called < len(regs)          # both branches of the 99.8 gate are in the batch
+    # several contexts sharing the batches (nw_region_analyse_many_ctxs): same tables
+    s2 = nb.Solver(0)
+    try:
+        M = nb.analyse_regions([solver, s2], regs, regions_per_batch=7, **kw)
+    finally:
+        s2.close()
+    for a, b in zip(M, B):
+        assert a.tsv == b.tsv and a.mut_max == b.mut_max and a.log == b.log and a.solver_called == b.solver_called
     assert nb.analyse_regions(solver, []) == []
 
 
