@@ -102,9 +102,12 @@ __global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
 #pragma unroll
   for (int k = 0; k < W; ++k) S[k] = 0;
   int sumup = 0;
-  for (int i = 1; i <= Lc; ++i) {
-    const uint32_t ci = crow[(size_t)(i - 1) * 128 + tid];  // plane row = block * 2 + strand
-    const uint32_t* bw = brow + i * BROW;                    // warp-uniform: broadcast loads
+  // running pointers (one add per row each) instead of re-deriving both addresses from the row number
+  const uint16_t* cp = crow + tid;
+  const uint32_t* bw = brow + BROW;
+  const uint16_t* const cend = cp + (size_t)Lc * 128;
+  for (; cp != cend; cp += 128, bw += BROW) {
+    const uint32_t ci = *cp;  // plane row = block * 2 + strand; bw: warp-uniform broadcast loads
     const uint32_t r0 = bw[0];
     const uint32_t sbw = bw[2];
     const int up = upx[ci];
