@@ -8,6 +8,10 @@
 // Savings form: S = max(up, run) per cell + a predicated diagonal update (see nw_device.h / DESIGN.md).
 #include "nw_kernels.cuh"
 
+#ifndef NW_DP_MINB
+#define NW_DP_MINB 1
+#endif
+
 namespace nw {
 
 // Shared-memory layout per CTA (128 threads = 4 warps):
@@ -16,7 +20,7 @@ namespace nw {
 // plane-row index (block * 2 + strand) that addresses both the match bit-plane and the up cost -- so the row
 // loop never waits on global memory; the warp's band table (one length per warp) is copied next to it.
 template <int W>
-__global__ void __launch_bounds__(128) k_score_fast(ScoreArgs A) {
+__global__ void __launch_bounds__(128, NW_DP_MINB) k_score_fast(ScoreArgs A) {
   constexpr int NWORD = (W + 31) / 32;
   constexpr bool RTREG = (W <= 64);  // rt window in registers (LDS.128) vs predicated scalar LDS per cell
   constexpr int RTW = RTREG ? W : 4;
