@@ -1279,6 +1279,42 @@ void analyse_many(nw_ctx* ctx, const nw_region_problem* regs, int64_t n, const n
             need[0].size() + need[1].size(), t_format, tms(t4, tnow()));
 }
 
+// A batch with per-region status: if the batch as a whole is refused (a gridmatrix that is not 2 x 2 at least, a
+// length outside the int32 DP range, ...) its regions are analysed one by one and only the offending ones fail --
+// the reference drops such a region in its tryCatch (R/nahrwhals.R:204, :274) and carries on.
+void analyse_many_isolated(nw_ctx* ctx, const nw_region_problem* regs, int64_t n, const nw_region_opts& o, nw_table** outs,
+                           nw_region_summary* summaries, int32_t* rcs) {
+  if (!rcs) {
+    analyse_many(ctx, regs, n, o, outs, summaries);
+    return;
+  }
+  try {
+    analyse_many(ctx, regs, n, o, outs, summaries);
+    for (int64_t k = 0; k < n; ++k) rcs[k] = NW_OK;
+    return;
+  } catch (const RErr& e) {
+    if (e.code == NW_ERR_CUDA || e.code == NW_ERR_NOMEM) throw;  // not a property of one region
+    for (int64_t k = 0; k < n; ++k) {
+      nw_table_free(outs[k]);
+      outs[k] = nullptr;
+    }
+    cudaGetLastError();
+  }
+  for (int64_t k = 0; k < n; ++k) {
+    try {
+      analyse_many(ctx, regs + k, 1, o, outs + k, summaries ? summaries + k : nullptr);
+      rcs[k] = NW_OK;
+    } catch (const RErr& e) {
+      if (e.code == NW_ERR_CUDA || e.code == NW_ERR_NOMEM) throw;
+      nw::set_last_error("region " + std::to_string(k) + ": " + e.msg);
+      rcs[k] = e.code;
+      outs[k] = nullptr;
+      if (summaries) memset(&summaries[k], 0, sizeof summaries[k]);
+      cudaGetLastError();
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -1332,7 +1368,7 @@ int nw_region_analyse(nw_ctx* ctx, const int64_t* grid, int32_t n_x, int32_t n_y
 }
 
 int nw_region_analyse_many(nw_ctx* ctx, const nw_region_problem* regions, int64_t n, const nw_region_opts* opts,
-                           nw_table** outs, nw_region_summary* summaries) {
+                           nw_table** outs, nw_region_summary* summaries, int32_t* rcs) {
   if (outs)
     for (int64_t k = 0; k < n; ++k) outs[k] = nullptr;
   return rguard([&] {
@@ -1341,7 +1377,7 @@ int nw_region_analyse_many(nw_ctx* ctx, const nw_region_problem* regions, int64_
     for (int64_t a = 0; a < n; a += PASS) {
       const int64_t m = std::min(PASS, n - a);
       try {
-        analyse_many(ctx, regions + a, m, *opts, outs + a, summaries ? summaries + a : nullptr);
+        analyse_many_isolated(ctx, regions + a, m, *opts, outs + a, summaries ? summaries + a : nullptr, rcs ? rcs + a : nullptr);
       } catch (...) {
         for (int64_t k = 0; k < a; ++k) {
           nw_table_free(outs[k]);
@@ -1355,7 +1391,7 @@ int nw_region_analyse_many(nw_ctx* ctx, const nw_region_problem* regions, int64_
 
 int nw_region_analyse_many_ctxs(nw_ctx** ctxs, int32_t n_ctx, const nw_region_problem* regions, int64_t n,
                                 const nw_region_opts* opts, int32_t regions_per_batch, nw_table** outs,
-                                nw_region_summary* summaries) {
+                                nw_region_summary* summaries, int32_t* rcs) {
   if (outs)
     for (int64_t k = 0; k < n; ++k) outs[k] = nullptr;
   return rguard([&] {
@@ -1377,7 +1413,8 @@ int nw_region_analyse_many_ctxs(nw_ctx** ctxs, int32_t n_ctx, const nw_region_pr
         if (b >= nb) return;
         const int64_t a = b * B, m = std::min(B, n - a);
         try {
-          analyse_many(ctxs[t], regions + a, m, *opts, outs + a, summaries ? summaries + a : nullptr);
+          analyse_many_isolated(ctxs[t], regions + a, m, *opts, outs + a, summaries ? summaries + a : nullptr,
+                                rcs ? rcs + a : nullptr);
         } catch (const RErr& e) {
           std::lock_guard<std::mutex> lk(mu);
           if (!failed) err = e;

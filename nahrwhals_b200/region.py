@@ -60,8 +60,8 @@ def _lib_region():
         L.nw_region_format.argtypes = [C.c_char_p, i64, vp, i32, C.POINTER(vp)]
         L.nw_region_analyse.argtypes = [vp, vp, i32, i32, vp, vp, vp, i32, C.POINTER(NwRegionOpts), C.POINTER(vp),
                                         C.POINTER(NwRegionSummary)]
-        L.nw_region_analyse_many.argtypes = [vp, vp, i64, C.POINTER(NwRegionOpts), vp, vp]
-        L.nw_region_analyse_many_ctxs.argtypes = [vp, i32, vp, i64, C.POINTER(NwRegionOpts), i32, vp, vp]
+        L.nw_region_analyse_many.argtypes = [vp, vp, i64, C.POINTER(NwRegionOpts), vp, vp, vp]
+        L.nw_region_analyse_many_ctxs.argtypes = [vp, i32, vp, i64, C.POINTER(NwRegionOpts), i32, vp, vp, vp]
         L.nw_table_summary.argtypes = [vp, C.POINTER(NwRegionSummary)]
         L.nw_table_mut_max.restype = C.c_char_p
         L.nw_table_mut_max.argtypes = [vp]
@@ -185,10 +185,11 @@ def analyse_region(solver, mat, len_y, len_x, gridlines_x, depth=3, maxdup=2, in
 
 
 def analyse_regions(solver, regions, depth=3, maxdup=2, init_width=1000, minreport=0.98, compression=1000, timing=None,
-                    regions_per_batch=1024, **kw):
+                    regions_per_batch=1024, isolate=False, **kw):
     """Regionfile mode: the solver stage of many regions in one call (nw_region_analyse_many).  `regions` is a list of
     (mat[n_y, n_x], len_y, len_x, gridlines_x); `solver` may be a list of Solvers (contexts) that share the batches.
-    Returns one RegionResult per region, identical to analyse_region."""
+    Returns one RegionResult per region, identical to analyse_region.  isolate=True: a region that cannot be analysed
+    fails alone (None in its place) and (results, rcs) is returned -- the reference drops such regions in a tryCatch."""
     import time
     L = _lib_region()
     n = len(regions)
@@ -202,12 +203,18 @@ def analyse_regions(solver, regions, depth=3, maxdup=2, init_width=1000, minrepo
     o = _opts(L, depth, maxdup, init_width, minreport, compression, **kw)
     outs = (C.c_void_p * max(n, 1))()
     summ = (NwRegionSummary * max(n, 1))()
+    rcs = np.zeros(max(n, 1), np.int32)
+    rcs_p = _p(rcs) if isolate else None
     t0 = time.perf_counter()
     if isinstance(solver, (list, tuple)):  # several contexts: batches handed out dynamically (nw_region_analyse_many_ctxs)
         hs = (C.c_void_p * len(solver))(*[s_.h for s_ in solver])
-        _lib.check(L.nw_region_analyse_many_ctxs(hs, len(solver), probs, n, C.byref(o), int(regions_per_batch), outs, summ))
+        _lib.check(L.nw_region_analyse_many_ctxs(hs, len(solver), probs, n, C.byref(o), int(regions_per_batch), outs, summ,
+                                                 rcs_p))
     else:
-        _lib.check(L.nw_region_analyse_many(solver.h, probs, n, C.byref(o), outs, summ))
+        _lib.check(L.nw_region_analyse_many(solver.h, probs, n, C.byref(o), outs, summ, rcs_p))
     if timing is not None:
         timing["native_s"] = time.perf_counter() - t0
-    return [RegionResult(L, C.c_void_p(outs[k]), summ[k]) for k in range(n)]
+    res = [RegionResult(L, C.c_void_p(outs[k]), summ[k]) if outs[k] else None for k in range(n)]
+    if isolate:
+        return res, rcs[:n].tolist()
+    return res

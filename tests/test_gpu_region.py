@@ -176,3 +176,21 @@ def test_region_golden_fixture_gpu(solver):
         head, body = open(os.path.join(GOLD, "testrun_region_d%d.tsv" % d)).read().split("\n", 1)
         assert P.tsv == body
         assert "mut_max=%s" % P.mut_max in head and "n_res_max=%d " % P.n_res_max in head
+
+
+def test_region_batch_isolates_bad_regions(solver):
+    """A region the stage cannot take (non-positive block length) fails alone when per-region status is requested."""
+    good = []
+    for seed in range(3):
+        mat, lx, ly, _ = sdgrid(16 + 4 * seed, [3, 2], chain_depth=2, seed=900 + seed)
+        good.append((mat, ly, lx, np.concatenate([[0], np.cumsum(lx)])))
+    mat, ly, lx, gl = good[1]
+    bad = (mat, ly, np.where(np.arange(len(lx)) == 2, 0, lx), gl)
+    regs = [good[0], bad, good[2]]
+    res, rcs = nb.analyse_regions(solver, regs, isolate=True)
+    assert rcs[0] == 0 and rcs[2] == 0 and rcs[1] == -5 and res[1] is None
+    for k in (0, 2):
+        S = nb.analyse_region(solver, *regs[k])
+        assert res[k].tsv == S.tsv and res[k].mut_max == S.mut_max
+    with pytest.raises(Exception):
+        nb.analyse_regions(solver, regs)

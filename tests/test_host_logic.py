@@ -216,3 +216,19 @@ def test_no_gpu_fails_loudly():
         pytest.skip("GPU present")
     with pytest.raises(Exception, match="CUDA"):
         nb.Solver(0)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver runs next to ours): one JSON line with the contract's keys, on a
+    small sample so that the CPU suite stays short."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup",
+                          "0", "--cpu-sample", "3000"], capture_output=True, text=True, timeout=300, check=True).stdout
+    line = json.loads(out.strip().split("\n")[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
