@@ -11,6 +11,9 @@
 #ifndef NW_DP_MINB
 #define NW_DP_MINB 1
 #endif
+#ifndef NW_RTREG_MAX
+#define NW_RTREG_MAX 64  // widest window whose rt values are held in registers (LDS.128) instead of read per cell
+#endif
 
 namespace nw {
 
@@ -22,7 +25,7 @@ namespace nw {
 template <int W>
 __global__ void __launch_bounds__(128, NW_DP_MINB) k_score_fast(ScoreArgs A) {
   constexpr int NWORD = (W + 31) / 32;
-  constexpr bool RTREG = (W <= 64);  // rt window in registers (LDS.128) vs predicated scalar LDS per cell
+  constexpr bool RTREG = (W <= NW_RTREG_MAX);  // rt window in registers (LDS.128) vs predicated scalar LDS per cell
   constexpr int RTW = RTREG ? W : 4;
   // uint32 words per band row, everything the row loop needs ready-made (no unpacking on the ALU pipe):
   //   r0 (window start in reversed columns), byte offset of the 16-B aligned rt window, sb | extra << 8, masks
