@@ -255,6 +255,7 @@ struct nw_ctx {
   // dedup table
   DevBuf table;
   uint64_t table_cap = 0;
+  DevBuf table_prev;                 // the table a level outgrew: released when the next one is retired (no host sync)
   // per-level scratch
   DevBuf cnt, off, bsum, slot, owner, is_new, newrank, nrank, new_len, hist, bstart, cursor, work, scratch, flag, pre, sel, keys,
       misc, rslot, newflag, grank, edgebuf, cta_rid, new_rid, best, gather, binflag, binrank, binsum, binrec;
@@ -460,6 +461,7 @@ void table_reserve(nw_ctx* c, uint64_t need_entries) {
   if (want > (1ull << 32)) fail(NW_ERR_NOMEM, "dedup table would exceed 2^32 slots");
   const size_t bytes = want * TBL_WORDS * 8;
   if (c->table_cap == 0) {  // fresh search: reuse the physical buffer when it is large enough
+    c->table_prev.release();
     c->table.ensure(bytes);
     CK(cudaMemsetAsync(c->table.p, 0xFF, bytes, c->stream));
     c->table_cap = want;
@@ -469,7 +471,10 @@ void table_reserve(nw_ctx* c, uint64_t need_entries) {
   nt.ensure(bytes);
   CK(cudaMemsetAsync(nt.p, 0xFF, bytes, c->stream));
   c->launches += launch_rehash(c->table.as<uint64_t>(), c->table_cap, nt.as<uint64_t>(), want - 1, c->stream);
-  CK(spin_sync(c->stream));
+  // the outgrown table is still being read by the rehash: it is kept until the next growth (or the next search)
+  // retires it, by which time the host has synchronised with the stream several times -- no sync here (clearing
+  // the new table on a second stream under the emit kernel was measured as well: no further gain)
+  c->table_prev = std::move(c->table);
   c->table = std::move(nt);
   c->table_cap = want;
 }
@@ -895,17 +900,17 @@ struct Search {
       L.n_new = 0;
       return false;
     }
-    table_reserve(c, (uint64_t)n_ids + G);
     E.off = off;
     E.desc = (uint64_t*)L.desc.ensure((size_t)G * 8);
     E.slot = (uint32_t*)c->slot.ensure((size_t)G * 4, true);
-    E.table = c->table.as<uint64_t>();
-    E.tmask = c->table_cap - 1;
     E.gbase = L.gbase;
     E.pw = c->d_pow.as<U4>();
     E.own_mod = 1;
     E.own_rem = 0;
     E.off_glob = nullptr;
+    table_reserve(c, (uint64_t)n_ids + G);
+    E.table = c->table.as<uint64_t>();
+    E.tmask = c->table_cap - 1;
     c->launches += launch_expand(true, E, s);
     c->launches += launch_hash_insert(E, G, s);
     uint32_t* is_new = (uint32_t*)c->is_new.ensure((size_t)G * 4, true);
