@@ -194,3 +194,20 @@ def test_region_batch_isolates_bad_regions(solver):
         assert res[k].tsv == S.tsv and res[k].mut_max == S.mut_max
     with pytest.raises(Exception):
         nb.analyse_regions(solver, regs)
+
+
+@pytest.mark.parametrize("shape", [(40, 8), (8, 40), (35, 25), (28, 45), (60, 31), (31, 9)])
+def test_prepass_lopsided_uncluttered(solver, shape):
+    """Shapes where the R twin's corridor (chosen by n_y) differs from slow_score's (chosen by the child length), with
+    the borders cleaned so that is_cluttered does not short-circuit the pre-pass."""
+    n_x, n_y = shape
+    mat, lx, ly = random_grid(n_x, n_y, 0.10, 1000 + n_x * 7 + n_y)
+    mat[0, 1:] = 0
+    mat[-1, :-1] = 0
+    mat[1:, 0] = 0
+    mat[:-1, -1] = 0
+    mat[0, 0] = lx[0]
+    mat[-1, -1] = lx[-1]
+    assert not ro.is_cluttered(ro.Bitl(mat, ly, lx))
+    O, P = check_prepass(solver, mat, ly, lx)
+    assert P.prepass_candidates > 0
