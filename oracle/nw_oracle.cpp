@@ -99,7 +99,11 @@ struct ScoreScratch {
 // fill_matrix! :408-426.  Matrices are stored column-major like Julia (i + j*row, 0-based).
 // `force` reproduces the R twin's forcecalc branch (R/evaltools.R:203-205: corridor 1.0, no early exit), the
 // path that yields res_ref (R/wrapper_aln_and_analyse.R:176).  Julia's own scorer always has force == false.
-static ScoreOut slow_score(const Problem& P, const int16_t* index, int L, ScoreScratch& ws, bool force = false) {
+// force: 0 = slow_score as Julia runs it; 1 = the R twin's forcecalc branch (corridor 1.0, no early exit);
+// 2 = the R twin without forcecalc (R/evaltools.R:193-201: no early exit, corridor chosen by dim(mat)[1], which is the
+// y dimension of R's matrix; the predicates are symmetric in (i/row, j/col), so the transposed matrix Julia-style
+// gives the same cell set).
+static ScoreOut slow_score(const Problem& P, const int16_t* index, int L, ScoreScratch& ws, int force = 0) {
   const double inf = std::numeric_limits<double>::infinity();
   ScoreOut out{0.0, std::nan(""), 0.0, 0};
   const int ny = P.n_y;
@@ -136,7 +140,7 @@ static ScoreOut slow_score(const Problem& P, const int16_t* index, int L, ScoreS
     sr += rt[j - 1];
     ws.cumsum_r[j - 1] = sr;  // :350
   }
-  const double pct = force ? 1.0 : determine_corridor_pct(row);  // :359
+  const double pct = force == 1 ? 1.0 : determine_corridor_pct(force == 2 ? col : row);  // :359
   int64_t cells = 1;
   C(1, 1) = std::min(ws.up[0] + rt[0], D(1, 1));  // :362
   for (int i = 2; i <= row; ++i) {                // :388-396
@@ -705,7 +709,7 @@ void nwo_score_batch(const int8_t* aln, int n_x, int n_y, const double* len_x, c
   fill_problem(P, aln, n_x, n_y, len_x, len_y);
   ScoreScratch ws;
   for (int64_t k = 0; k < n; ++k) {
-    ScoreOut so = slow_score(P, flat + off[k], (int)(off[k + 1] - off[k]), ws, force != 0);
+    ScoreOut so = slow_score(P, flat + off[k], (int)(off[k + 1] - off[k]), ws, force);
     score[k] = so.score;
     cost[k] = so.cost;
     total[k] = so.total;

@@ -119,7 +119,8 @@ def solve_files(inmat, inlens, out, **kw):
 
 
 def score_batch(aln, len_x, len_y, seqs, force=False):
-    """seqs: list of int sequences.  Returns (score f64, cost f64 [NaN early exit / inf], total f64, cells)."""
+    """seqs: list of int sequences.  force: 0 slow_score, 1 / True the R twin's forcecalc branch, 2 the R twin's own
+    corridor (chosen by n_y, no early exit).  Returns (score f64, cost f64 [NaN early exit / inf], total f64, cells)."""
     L = lib()
     aln = np.ascontiguousarray(aln, dtype=np.int8)
     n_x, n_y = aln.shape
@@ -136,7 +137,7 @@ def score_batch(aln, len_x, len_y, seqs, force=False):
     cost = np.zeros(n, np.float64)
     total = np.zeros(n, np.float64)
     cells = np.zeros(n, np.int64)
-    L.nwo_score_batch(_p(aln), n_x, n_y, _p(lx), _p(ly), _p(flat), _p(off), n, 1 if force else 0, _p(score), _p(cost),
+    L.nwo_score_batch(_p(aln), n_x, n_y, _p(lx), _p(ly), _p(flat), _p(off), n, int(force), _p(score), _p(cost),
                       _p(total), _p(cells))
     return score, cost, total, cells
 

@@ -211,3 +211,36 @@ def test_prepass_lopsided_uncluttered(solver, shape):
     assert not ro.is_cluttered(ro.Bitl(mat, ly, lx))
     O, P = check_prepass(solver, mat, ly, lx)
     assert P.prepass_candidates > 0
+
+
+@pytest.mark.parametrize("shape", [(20, 9), (30, 30), (64, 64), (100, 70), (150, 150), (140, 31), (45, 160), (8, 60)])
+def test_rtwin_corridor_scores_large_shapes(solver, oracle, shape):
+    """nw_score_batch(force = 2): the R twin's own corridor (chosen by n_y, no early exit) against the C++ restatement
+    at sizes the Python one is too slow for -- random arrangements of every length from n_y / 3 to 2 n_x, through the
+    register-resident kernels and through the generic kernel.  force = 1 (full corridor) on the same arrangements."""
+    n_x, n_y = shape
+    rng = np.random.default_rng(n_x * 1000 + n_y)
+    mat, lx, ly = random_grid(n_x, n_y, 0.08, n_x + n_y)
+    aln = np.ascontiguousarray(np.sign(mat).T.astype(np.int8))
+    seqs = [list(range(1, n_x + 1))]
+    for _ in range(160):
+        L = int(rng.integers(min(max(2, n_y // 3), 2 * n_x), 2 * n_x + 1))
+        start = int(rng.integers(1, n_x + 1))
+        seq = [((start + t - 1) % n_x) + 1 for t in range(L)]          # a run of consecutive blocks ...
+        for _ in range(int(rng.integers(0, 4))):                        # ... with a few inverted stretches
+            a = int(rng.integers(0, L))
+            b = int(rng.integers(a, min(L, a + 12))) + 1
+            seq[a:b] = [-v for v in reversed(seq[a:b])]
+        seqs.append(seq)
+    lxf, lyf = lx.astype(np.float64), ly.astype(np.float64)
+    for force in (2, 1):
+        osc, ocost, otot, _ = oracle.score_batch(aln, lxf, lyf, seqs, force=force)
+        for generic in (False, True):
+            if generic and force == 1 and n_x * n_y > 12000:
+                continue                                                 # the generic kernel on full corridors is slow
+            sc, cost, tot = solver.score_batch(aln, lx, ly, seqs, force=force, generic_dp=generic)
+            want_cost = np.where(np.isinf(ocost), -2, ocost).astype(np.int64)
+            assert np.array_equal(cost, want_cost), (force, generic)
+            assert np.array_equal(tot, otot.astype(np.int64))
+            reach = ~np.isinf(ocost)
+            assert np.array_equal(sc[reach], osc[reach])
