@@ -32,6 +32,7 @@ namespace {
 
 constexpr int CAP = NW_GRID_MAX_LINES;
 constexpr int GT = 256;  // threads per CTA of k_gridlines
+constexpr size_t GRID_BATCH = 8192;  // regions per pass of nw_grid_build
 constexpr unsigned long long EMPTY_BITS = 0x7ff8dead00000001ull;  // a NaN payload no computation produces
 
 enum : int { ST_OK = 0, ST_OVERFLOW = 1, ST_WALK = 2 };
@@ -339,8 +340,13 @@ int nw_grid_build(nw_ctx* ctx, const nw_paf* pafs, int64_t n_regions, nw_grid** 
       live.push_back(k);
       n_aln += p.n;
     }
-    const size_t R = live.size();
-    if (R > 0) {
+    // batches of at most GRID_BATCH regions: the staging area holds 16 KB of gridline buffers per region
+    const std::vector<int64_t> live_all = std::move(live);
+    for (size_t b0 = 0; b0 < live_all.size(); b0 += GRID_BATCH) {
+      live.assign(live_all.begin() + b0, live_all.begin() + std::min(live_all.size(), b0 + GRID_BATCH));
+      n_aln = 0;
+      for (int64_t k : live) n_aln += pafs[k].n;
+      const size_t R = live.size();
       GCK(cudaSetDevice(nw::ctx_device(ctx)));
       cudaStream_t st = nw::ctx_stream(ctx);
       auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };

@@ -116,3 +116,21 @@ def test_gpu_grid_to_region_stage(solver, oracle):
     P = nb.analyse_region(solver, G.mat, G.len_y, G.len_x, G.gridlines_x, depth=3)
     O = ro.analyse_region(G.mat, G.len_y, G.len_x, G.gridlines_x, oracle_solver(oracle), depth=3)
     assert P.mut_max == O["mut_max"] and P.res_max == O["res_max"] and P.res_ref == O["res_ref"]
+
+
+@pytest.mark.gpu
+def test_gpu_grid_many_regions(solver):
+    """More regions than one internal pass holds (8192): results do not depend on the pass a region falls into."""
+    import nahrwhals_b200 as nb
+    rng = np.random.default_rng(3)
+    base = [random_paf(rng, int(rng.integers(1, 6)), span=80) for _ in range(50)]
+    pafs = [base[k % 50] for k in range(8300)]
+    grids, rcs = nb.build_grids(solver, pafs)
+    ref, rref = nb.build_grids(solver, base)
+    for k in range(0, 8300, 83):
+        a, b = grids[k], ref[k % 50]
+        assert rcs[k] == rref[k % 50]
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert np.array_equal(a.mat, b.mat) and a.gridlines_x.tolist() == b.gridlines_x.tolist()
+    assert all((grids[k] is None) == (ref[k % 50] is None) for k in range(8192, 8300))
