@@ -497,9 +497,14 @@ ScoreView view_of(const Level& L) {
 // Only the non-empty bins travel to the host (compacted on the device, in (region, length) order).
 // Work-list layout: kernel class (register window W ascending, generic last) > region > length; every bucket is
 // padded to a warp, every region segment of a register-kernel class to a CTA (a CTA stages one region context).
+// n_new_deferred != nullptr: the caller has not fetched the number of fresh candidates yet (misc[5], written by the
+// scan of the first-discoverer flags); it travels with the bins in the same round trip and is handed back.  Only for
+// launches that take the single-copy path below (one region, few bins) -- saves one host round trip per level.
 void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int lcap, const uint16_t* new_rid_dev, int force,
-                 int flags, int* best_dev, int64_t* cells_out /* [n_regions] or nullptr */) {
+                 int flags, int* best_dev, int64_t* cells_out /* [n_regions] or nullptr */,
+                 uint32_t* n_new_deferred = nullptr) {
   const int R = c->n_regions;
+  uint32_t n_new = Lv.n_new;
   const size_t nbins = (size_t)R * lcap * NSUB;
   const uint32_t nb = (uint32_t)((size_t)R * lcap);
   cudaStream_t st = c->stream;
@@ -516,12 +521,18 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
     BinRec* brec = (BinRec*)c->binrec.ensure((size_t)(nb + 1) * sizeof(BinRec), true);
     c->launches += launch_bins_small(hist_dev, nb, brec, st);
     BinRec* pin = reinterpret_cast<BinRec*>(static_cast<unsigned char*>(c->pinned) + 4096);
+    if (n_new_deferred) d2h(c, c->pinned, c->misc.p, 32);
     d2h(c, pin, brec, (size_t)(nb + 1) * sizeof(BinRec));
     CK(spin_sync(st));
+    if (n_new_deferred) {
+      n_new = reinterpret_cast<const uint32_t*>(c->pinned)[5];
+      *n_new_deferred = n_new;
+    }
     const uint32_t n = pin[0].bin;
     if (!n) return;
     bins.assign(pin + 1, pin + 1 + n);
   } else {
+    if (n_new_deferred) fail(NW_ERR_ARG, "internal: deferred fresh count on the multi-copy bucket path");
     uint32_t* bflag = (uint32_t*)c->binflag.ensure((size_t)nb * 4, true);
     uint32_t* brank = (uint32_t*)c->binrank.ensure((size_t)nb * 4, true);
     uint32_t* bsumn = (uint32_t*)c->binsum.ensure((size_t)nb * 4, true);
@@ -529,7 +540,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
     int32_t* misc = (int32_t*)c->misc.p;
     c->launches += launch_bin_flags(hist_dev, nb, bflag, bsumn, st);
     c->launches += launch_scan(bflag, brank, nb, bsum, (uint32_t*)(misc + 13), st);
-    BinRec* brec = (BinRec*)c->binrec.ensure((size_t)std::min<uint64_t>(nb, (uint64_t)Lv.n_new + 1) * sizeof(BinRec), true);
+    BinRec* brec = (BinRec*)c->binrec.ensure((size_t)std::min<uint64_t>(nb, (uint64_t)n_new + 1) * sizeof(BinRec), true);
     c->launches += launch_bin_compact(bflag, brank, bsumn, nb, brec, st);
     uint32_t* pin = (uint32_t*)c->pinned;
     d2h(c, pin, misc, 64);
@@ -608,13 +619,13 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
     d_cta_rid = (uint16_t*)c->cta_rid.ensure(cta_rid.size() * 2, true);
     h2d(c, d_cta_rid, cta_rid.data(), cta_rid.size() * 2);
   }
-  c->launches += launch_bucket_scatter(c->new_len.as<uint16_t>(), new_rid_dev, c->d_regions.as<RegionDev>(), lcap, Lv.n_new,
+  c->launches += launch_bucket_scatter(c->new_len.as<uint16_t>(), new_rid_dev, c->d_regions.as<RegionDev>(), lcap, n_new,
                                        force, c->bstart.as<uint32_t>(), c->cursor.as<uint32_t>(), c->work.as<uint32_t>(),
                                        st);
   // no sync: cudaMemcpyAsync from pageable memory has consumed the host vectors (bins, cta_rid) when it returns
   if (dbg)
     fprintf(stderr, "[nw scoring] buckets %zu, work %u for %u new, ranges %zu: bucket loop %.2f ms, bands %.2f, layout %.2f, scatter %.2f\n",
-            bk.size(), n_work, Lv.n_new, ranges.size(), tms(T0, T1), tms(T1, T2), tms(T2, T3), tms(T3, tnow()));
+            bk.size(), n_work, n_new, ranges.size(), tms(T0, T1), tms(T1, T2), tms(T2, T3), tms(T3, tnow()));
   ScoreArgs A{};
   A.F = Lv.F;
   A.F.regions = c->d_regions.as<RegionDev>();
@@ -919,21 +930,28 @@ struct Search {
     uint32_t* newrank = (uint32_t*)c->newrank.ensure((size_t)G * 4, true);
     bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(G) * 4, true);
     c->launches += launch_scan(is_new, newrank, G, bsum, (uint32_t*)(misc + 5), s);
-    if (R > 1) gather_async(newrank, L.cstart, G, 0xffffffffu);  // first fresh rank of every region
-    d2h(c, pin_u32(), misc, 32);
-    if (R > 1) d2h(c, pin_u32() + 64, c->gather.p, (size_t)(R + 1) * 4);
-    CK(spin_sync(s));
-    CK(cudaGetLastError());
-    const auto T2 = tnow();
-    const uint32_t n_new = pin_u32()[5];
-    for (int r = 0; r <= R; ++r) {
-      const uint32_t v = R > 1 ? pin_u32()[64 + r] : (r == 0 ? 0u : n_new);
-      L.nstart[r] = v == 0xffffffffu ? n_new : v;
-    }
-    L.n_new = n_new;
-    for (int r = 0; r < R; ++r) rst[r].scored[d - 1] = L.nstart[r + 1] - L.nstart[r];
-    // ids / edges / histogram of (region, child length)
     const int lcap = std::min(std::max(maxlen, L.LS), LMAX) + 1;  // longest possible child of this level, + 1
+    // single search with few (length) bins: the fresh count is fetched together with the DP buckets (one host round
+    // trip less per level); the per-fresh arrays are then sized by the candidate count
+    static const bool no_defer = getenv("NW_NO_DEFER") != nullptr;
+    const bool defer = R == 1 && (size_t)lcap <= BINS_SMALL_LIMIT && !no_defer;
+    uint32_t n_new = G;  // upper bound until known
+    if (!defer) {
+      if (R > 1) gather_async(newrank, L.cstart, G, 0xffffffffu);  // first fresh rank of every region
+      d2h(c, pin_u32(), misc, 32);
+      if (R > 1) d2h(c, pin_u32() + 64, c->gather.p, (size_t)(R + 1) * 4);
+      CK(spin_sync(s));
+      CK(cudaGetLastError());
+      n_new = pin_u32()[5];
+      for (int r = 0; r <= R; ++r) {
+        const uint32_t v = R > 1 ? pin_u32()[64 + r] : (r == 0 ? 0u : n_new);
+        L.nstart[r] = v == 0xffffffffu ? n_new : v;
+      }
+      L.n_new = n_new;
+      for (int r = 0; r < R; ++r) rst[r].scored[d - 1] = L.nstart[r + 1] - L.nstart[r];
+    }
+    const auto T2 = tnow();
+    // ids / edges / histogram of (region, child length)
     const size_t nbins = (size_t)R * lcap * NSUB;
     if (nbins > ((size_t)64 << 20)) fail(NW_ERR_NOMEM, "too many (region, length) buckets in one batch");
     AssignArgs A{};
@@ -971,9 +989,15 @@ struct Search {
     CK(cudaGetLastError());
     const auto T3 = tnow();
     std::vector<int64_t> cells(R, 0);
-    run_scoring(c, ScoreView{frontier_of(L), L.n_new, L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(), L.k3.as<int32_t>(),
-                             L.cost.as<int32_t>(), L.total.as<int32_t>()},
-                A.hist, lcap, L.nrid.as<uint16_t>(), 0, o.flags, c->best.as<int>(), cells.data());
+    run_scoring(c, ScoreView{frontier_of(L), defer ? 0u : L.n_new, L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(),
+                             L.k3.as<int32_t>(), L.cost.as<int32_t>(), L.total.as<int32_t>()},
+                A.hist, lcap, L.nrid.as<uint16_t>(), 0, o.flags, c->best.as<int>(), cells.data(), defer ? &n_new : nullptr);
+    if (defer) {
+      L.nstart[0] = 0;
+      L.nstart[1] = n_new;
+      L.n_new = n_new;
+      rst[0].scored[d - 1] = n_new;
+    }
     for (int r = 0; r < R; ++r) rst[r].cells[d - 1] = cells[r];
     if (dbg) {
       const auto T4 = tnow();
