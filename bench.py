@@ -288,8 +288,8 @@ def run_stage(args, rank, world, local):
         r, _, dt = run_stage_cpu(regs, cores)
         print(json.dumps(dict(impl="reference", metric="regions_solved_per_s", value=r, unit="regions/s",
                               n_gpus=args.gpus, steps=1, warmup=0, ms_per_step=1e3 * dt, higher_is_better=True,
-                              scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                              config=dict(workload=desc % len(regs)),
+                              scaling="strong" if genome else "weak", vs_baseline=None, dtype="f64", data="synthetic",
+                              config=dict(workload=desc % (args.regions if genome else len(regs)), sample_regions=len(regs)),
                               cpu_baseline=dict(value=r, unit="regions/s", cores=cores, kind="port",
                                                 sample="%d regions, one per worker process" % len(regs)),
                               e2e=dict(value=r, unit="regions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
