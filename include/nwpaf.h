@@ -1,0 +1,62 @@
+/* nwpaf.h -- C ABI (libnwsolve.so) of the PAF preparation upstream of the gridding.
+ *
+ * Reference: load_and_prep_paf_for_gridplot_transform (R/tsv_to_bitlocus.R:15-110) turns the chunked minimap2
+ * alignments of a region into the table make_xy_grid_fast reads:
+ *     strand swap (qstart > qend for '-' alignments), compress_paf_fnct(second_run = T) (R/compress_paf.R:173-406:
+ *     merge_paf_entries_intraloop finds the pairs of alignments where one ends where the other starts -- an all-pairs
+ *     test per target-axis chunk --, the best partner per row / column is kept, merge_rows stitches them),
+ *     alen > minlen, rounding to the compression grid, enforce_slope_one (:258-275).
+ * The all-pairs test runs on the GPU (one thread per ordered pair of alignments, every chunk both touch, the chunk's
+ * own tolerance); the selection and the sequential stitching of merge_rows run on the host in the reference's order.
+ * A table is passed column-wise as doubles; strand is +1 / -1.  The qname / tname strings influence no number
+ * downstream and are not carried.  No CPU fallback.
+ */
+#ifndef NWPAF_H
+#define NWPAF_H
+
+#include <stdint.h>
+
+#include "nwsolve.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nw_paf_cols {
+  const double* qlen;
+  const double* qstart;
+  const double* qend;
+  const double* strand; /* +1 or -1 */
+  const double* tlen;
+  const double* tstart;
+  const double* tend;
+  const double* nmatch;
+  const double* alen;
+  const double* mapq;
+  int64_t n;
+} nw_paf_cols;
+
+typedef struct nw_paf_table nw_paf_table;
+
+/* Replaces compress_paf_fnct(inpaf_df = paf, save_outpaf = F, second_run, inparam_chunklen, inparam_compression,
+ * n_quadrants_per_axis) (R/compress_paf.R:173-406).  n_quadrants <= 0: the reference's choice (2 below 50 kb, else 10). */
+int nw_paf_compress(nw_ctx* ctx, const nw_paf_cols* in, int32_t second_run, double chunklen, double compression,
+                    int32_t n_quadrants, nw_paf_table** out);
+
+/* Replaces load_and_prep_paf_for_gridplot_transform(inpaf, minlen, compression, inparam_chunklen) from the parsed
+ * table on (R/tsv_to_bitlocus.R:38-82); `in` holds the PAF columns as minimap2 writes them (qstart < qend). */
+int nw_paf_prepare(nw_ctx* ctx, const nw_paf_cols* in, double minlen, double compression, double chunklen,
+                   nw_paf_table** out);
+
+int64_t nw_paf_rows(const nw_paf_table* t);
+/* any pointer may be NULL; arrays of nw_paf_rows() doubles */
+int nw_paf_columns(const nw_paf_table* t, double* qlen, double* qstart, double* qend, double* strand, double* tlen,
+                   double* tstart, double* tend, double* nmatch, double* alen, double* mapq);
+/* pairs the all-pairs test found (before selection) and kernels launched: diagnostics */
+int nw_paf_stats(const nw_paf_table* t, int64_t* pairs_found, int32_t* gpu_launches);
+void nw_paf_free(nw_paf_table* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NWPAF_H */

@@ -177,7 +177,12 @@ def test_library_exports_declared_symbols():
     for s in declared:
         assert getattr(L, s) is not None
     assert b"sm_100a" in L.nw_version()
-    from nahrwhals_b200 import grid, region
+    from nahrwhals_b200 import grid, paf, region
+    hdr = open(os.path.join(ROOT, "include", "nwpaf.h")).read()
+    declared = set(re.findall(r"\b(nw_paf_[a-z_0-9]+)\s*\(", hdr)) - {"nw_paf_cols", "nw_paf_table"}
+    assert declared == set(paf.SYMBOLS)
+    for s in declared:
+        assert getattr(L, s) is not None
     hdr = open(os.path.join(ROOT, "include", "nwgrid.h")).read()
     declared = set(re.findall(r"\b(nw_grid_[a-z_0-9]+)\s*\(", hdr))
     assert declared == set(grid.SYMBOLS)

@@ -1,0 +1,104 @@
+"""PAF preparation: the R restatement on the CPU, and the GPU path (include/nwpaf.h) against it."""
+import numpy as np
+import pytest
+
+from oracle import nw_paf_oracle as po
+
+
+def chunked_paf(rng, n_segments=6, chunk=10000, jitter=0, span=400000, drop=0.0, extra=0):
+    """Alignments as chunked minimap2 reports them: every true segment cut into chunk-long pieces (optionally with a few
+    bp of jitter at the cuts, dropped pieces and unrelated short hits)."""
+    rows = []
+    for _ in range(n_segments):
+        length = min(chunk * int(rng.integers(1, 9)) + int(rng.integers(0, chunk)), span // 2)
+        t0 = int(rng.integers(0, span - length))
+        q0 = int(rng.integers(0, span - length))
+        strand = 1 if rng.random() < 0.6 else -1
+        for k in range(0, length, chunk):
+            ln = min(chunk, length - k)
+            if rng.random() < drop:
+                continue
+            j0 = int(rng.integers(-jitter, jitter + 1)) if jitter else 0
+            j1 = int(rng.integers(-jitter, jitter + 1)) if jitter else 0
+            ts, te = t0 + k + j0, t0 + k + ln + j1
+            if strand > 0:
+                qs, qe = q0 + k + j0, q0 + k + ln + j1
+            else:
+                qs, qe = q0 + length - k - ln - j1, q0 + length - k - j0
+            if te - ts < 50 or qe - qs < 50:
+                continue
+            rows.append((chunk, qs, qe, strand, span, ts, te, te - ts - int(rng.integers(0, 30)), te - ts, 60))
+    for _ in range(extra):
+        ln = int(rng.integers(200, 3000))
+        t0, q0 = int(rng.integers(0, span - ln)), int(rng.integers(0, span - ln))
+        rows.append((chunk, q0, q0 + ln, 1 if rng.random() < 0.5 else -1, span, t0, t0 + ln, ln - 5, ln, 30))
+    order = rng.permutation(len(rows))
+    a = np.array([rows[k] for k in order], dtype=np.float64).reshape(-1, 10)
+    return {k: a[:, i].copy() for i, k in enumerate(po.COLS)}
+
+
+def test_oracle_stitches_chunks():
+    """Chunks of one alignment are stitched back (forward and reverse strand), unrelated alignments are left alone."""
+    rng = np.random.default_rng(0)
+    p = chunked_paf(rng, n_segments=1, chunk=10000)
+    out = po.compress_paf_fnct(po.swap_minus(p), second_run=True, chunklen=10000, compression=1000)
+    assert len(out["tstart"]) == 1
+    assert out["tend"][0] - out["tstart"][0] == p["alen"].sum() == out["alen"][0]
+    # the full preparation ends with slope-one alignments on the compression grid
+    p = chunked_paf(np.random.default_rng(3), n_segments=5, jitter=3, extra=4)
+    out = po.load_and_prep_paf(p, minlen=2000, compression=1000)
+    assert len(out["tstart"]) >= 3
+    assert np.all(np.abs(out["tend"] - out["tstart"]) == np.abs(out["qend"] - out["qstart"]))
+    assert np.all(out["tstart"] % 1000 == 0) and np.all(out["qstart"] % 1000 == 0)
+    neg = out["strand"] < 0
+    assert np.all(out["qstart"][neg] > out["qend"][neg]) and np.all(out["qstart"][~neg] < out["qend"][~neg])
+
+
+def _same(P, O):
+    for k in po.COLS:
+        assert np.array_equal(P[k], O[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(12))
+def test_gpu_paf_matches_oracle(solver, seed):
+    import nahrwhals_b200 as nb
+    rng = np.random.default_rng(100 + seed)
+    p = chunked_paf(rng, n_segments=int(rng.integers(1, 14)), chunk=int(rng.choice([5000, 10000])),
+                    jitter=int(rng.choice([0, 0, 2, 30, 400])), span=int(rng.choice([40000, 300000, 900000])),
+                    drop=float(rng.choice([0.0, 0.1])), extra=int(rng.integers(0, 12)))
+    chunklen = float(p["qlen"][0]) if len(p["qlen"]) else 10000.0
+    for second_run, compression in ((True, 1000.0), (False, 1000.0), (True, 10000.0)):
+        O = po.compress_paf_fnct(po.swap_minus(p), second_run=second_run, chunklen=chunklen, compression=compression)
+        P = nb.compress_paf(solver, po.swap_minus(p), second_run=second_run, chunklen=chunklen, compression=compression)
+        _same(P, O)
+    for minlen, compression in ((500.0, 1000.0), (3000.0, 5000.0)):
+        O = po.load_and_prep_paf(p, minlen, compression, chunklen)
+        P = nb.load_and_prep_paf(solver, p, minlen, compression, chunklen)
+        _same(P, O)
+    # quadrant count given explicitly (R/make_whole_genome_list.R:105 passes 10)
+    O = po.compress_paf_fnct(po.swap_minus(p), second_run=False, chunklen=chunklen, n_quadrants_per_axis=10)
+    P = nb.compress_paf(solver, po.swap_minus(p), second_run=False, chunklen=chunklen, n_quadrants_per_axis=10)
+    _same(P, O)
+
+
+@pytest.mark.gpu
+def test_gpu_paf_edge_cases_and_chain(solver):
+    """Empty / single-row tables, bad input, and the whole native chain PAF -> grid -> region stage."""
+    import nahrwhals_b200 as nb
+    empty = {k: np.zeros(0) for k in po.COLS}
+    assert len(nb.load_and_prep_paf(solver, empty, 100, 1000)["tstart"]) == 0
+    one = chunked_paf(np.random.default_rng(1), n_segments=1, chunk=100000)
+    one = {k: v[:1] for k, v in one.items()}
+    _same(nb.compress_paf(solver, one, second_run=True), po.compress_paf_fnct(one, second_run=True, compression=1000.0))
+    bad = dict(one)
+    bad["strand"] = np.array([0.0])
+    with pytest.raises(Exception):
+        nb.compress_paf(solver, bad)
+    p = chunked_paf(np.random.default_rng(9), n_segments=7, jitter=2, span=200000)
+    T = nb.load_and_prep_paf(solver, p, 1000, 1000)
+    assert T["_gpu_launches"] >= 1 and T["_pairs_found"] > 0
+    G = nb.paf_to_gridmatrix(solver, T["tstart"], T["tend"], T["qstart"], T["qend"])
+    assert G.mat.shape[0] >= 2 and G.mat.shape[1] >= 2
+    R = nb.analyse_region(solver, G.mat, G.len_y, G.len_x, G.gridlines_x, depth=2)
+    assert R.res_ref is not None and R.res_max >= R.res_ref
