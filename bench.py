@@ -465,6 +465,101 @@ def run_grid(args, rank, world, local):
     solver.close()
 
 
+def _paf_tables(n, seed, n_segments=260):
+    """Chunked PAF tables of a few thousand alignments each (a 4 Mb region cut into 10 kb chunks, repeats, short hits)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_paf import chunked_paf
+    return [chunked_paf(np.random.default_rng(seed * 100000 + k), n_segments=n_segments, chunk=10000, jitter=3, span=4000000,
+                        drop=0.02, extra=300) for k in range(n)]
+
+
+def _paf_cpu_one(p):
+    from oracle import nw_paf_oracle as po
+    return len(po.load_and_prep_paf(p, 1000.0, 1000.0, 10000.0)["tstart"])
+
+
+def run_paf(args, rank, world, local):
+    """PAF preparation (strand swap, compress_paf_fnct(second_run), minlen filter, rounding,
+    enforce_slope_one) of chunked alignment tables through nw_paf_prepare.  Metric: alignments/s (input rows), wall clock
+    around the C-ABI calls, host columns in, prepared table in host memory out.  --impl reference: the R restatement
+    (numpy) on all host cores, one table per worker process."""
+    cores = os.cpu_count() or 1
+    n_tab = max(8, args.regions // 200)
+    desc = "PAF preparation of %d chunked alignment tables per GPU (~2 400 alignments each: 4 Mb region, 10 kb chunks)"
+
+    def cpu(tabs):
+        import multiprocessing as mp
+        t0 = time.perf_counter()
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_paf_cpu_one, tabs, chunksize=1)
+        dt = time.perf_counter() - t0
+        return sum(len(t["tstart"]) for t in tabs) / dt, dt
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        tabs = _paf_tables(max(cores, n_tab // 2), 0)
+        r, dt = cpu(tabs)
+        print(json.dumps(dict(impl="reference", metric="paf_alignments_prepared_per_s", value=r, unit="alignments/s",
+                              n_gpus=args.gpus, steps=1, warmup=0, ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak",
+                              vs_baseline=None, dtype="f64", data="synthetic", config=dict(workload=desc % len(tabs)),
+                              cpu_baseline=dict(value=r, unit="alignments/s", cores=cores, kind="port",
+                                                sample="%d tables, one per worker process" % len(tabs)),
+                              e2e=dict(value=r, unit="alignments/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                              gpu_launches=0)), flush=True)
+        return
+    import torch
+    import nahrwhals_b200 as nb
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tabs = _paf_tables(n_tab, rank)
+    solver = nb.Solver(local)
+    for t in tabs[:3]:
+        nb.load_and_prep_paf(solver, t, 1000.0, 1000.0, 10000.0)
+    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler.start()
+    steps = max(1, args.steps)
+    t0 = time.perf_counter()
+    launches = 0
+    for _ in range(steps):
+        for t in tabs:
+            launches += nb.load_and_prep_paf(solver, t, 1000.0, 1000.0, 10000.0)["_gpu_launches"]
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    clocks = sampler.stop()
+    rows = sum(len(t["tstart"]) for t in tabs)
+    if dist is not None:
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        ss = torch.tensor([rows, launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ss, op=dist.ReduceOp.SUM)
+        rows, launches = ss.tolist()
+    line = dict(metric="paf_alignments_prepared_per_s", value=rows / dt, unit="alignments/s", n_gpus=world, steps=steps,
+                warmup=3, ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic", config=dict(workload=(desc % n_tab) + "; tables shard per GPU, no collective",
+                                             timed="wall clock around nw_paf_prepare through the Python mirror"),
+                clocks=clocks, e2e=dict(value=rows / dt, unit="alignments/s", h2d_bytes_per_step=int(rows) * 56,
+                                        d2h_bytes_per_step=None), gpu_launches=int(launches))
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = tabs[:max(cores, n_tab // 2)]
+        r, cdt = cpu(sample)
+        line["cpu_baseline"] = dict(value=r, unit="alignments/s", cores=cores, kind="port",
+                                    sample="%d tables of the same set, %.1f s, one table per worker process; R restatement "
+                                           "in numpy" % (len(sample), cdt))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    solver.close()
+
+
 def run_frontier(args, rank, world, local):
     """BASELINE.json config 3: ONE deep search sharded over the GPUs (frontier round-robin, per-level all-gather of
     40-byte records over NCCL, deterministic merge on every rank).  Strong scaling: total work is fixed."""
@@ -519,7 +614,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS) + ["regions", "stage", "genome", "grid"])
+    ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS) + ["regions", "stage", "genome", "grid", "paf"])
     ap.add_argument("--regions", type=int, default=6000, help="regions per rank for --workload regions")
     ap.add_argument("--contexts", type=int, default=4, help="solver contexts (streams) per GPU for --workload regions")
     ap.add_argument("--warmup-regions", type=int, default=2, help="untimed warm-up runs for --workload regions")
@@ -539,6 +634,9 @@ def main():
         return
     if args.workload == "grid":
         run_grid(args, rank, world, local)
+        return
+    if args.workload == "paf":
+        run_paf(args, rank, world, local)
         return
     if args.workload in ("stage", "genome"):
         run_stage(args, rank, world, local)
