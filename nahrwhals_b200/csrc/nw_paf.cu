@@ -15,9 +15,11 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <set>
 #include <string>
 #include <vector>
 
+#include "../../include/nwbitlocus.h"
 #include "../../include/nwpaf.h"
 
 struct nw_ctx;
@@ -316,6 +318,27 @@ Table enforce_slope_one(const Table& p) {  // R/tsv_to_bitlocus.R:258-275
   return take(o, keep);
 }
 
+// load_and_prep_paf_for_gridplot_transform from the parsed table on (R/tsv_to_bitlocus.R:38-82)
+Table prepare(nw_ctx* ctx, Table p, double minlen, double compression, double chunklen, CompressStats& stats) {
+  if (!(compression > 0)) pfail(NW_ERR_ARG, "compression must be positive");
+  swap_minus(p);
+  p = compress(ctx, p, true, chunklen, compression, 0, stats);
+  {
+    std::vector<size_t> keep;
+    for (size_t k = 0; k < p.n(); ++k)
+      if (p.c[ALEN][k] > minlen) keep.push_back(k);
+    p = take(p, keep);
+  }
+  if (p.n() > 0) {
+    for (int col : {QSTART, QEND, TSTART, TEND})
+      for (double& v : p.c[col]) v = std::nearbyint(v / compression) * compression;  // round(x / compression, 0) * compression
+    swap_minus(p);
+    p = enforce_slope_one(p);
+    swap_minus(p);
+  }
+  return p;
+}
+
 }  // namespace
 
 struct nw_paf_table {
@@ -360,25 +383,8 @@ int nw_paf_prepare(nw_ctx* ctx, const nw_paf_cols* in, double minlen, double com
   if (out) *out = nullptr;
   return pguard([&] {
     if (!ctx || !out) pfail(NW_ERR_ARG, "null argument");
-    if (!(compression > 0)) pfail(NW_ERR_ARG, "compression must be positive");
     std::unique_ptr<nw_paf_table> T(new nw_paf_table);
-    Table p = from_cols(in);
-    swap_minus(p);
-    p = compress(ctx, p, true, chunklen, compression, 0, T->stats);
-    {
-      std::vector<size_t> keep;
-      for (size_t k = 0; k < p.n(); ++k)
-        if (p.c[ALEN][k] > minlen) keep.push_back(k);
-      p = take(p, keep);
-    }
-    if (p.n() > 0) {
-      for (int col : {QSTART, QEND, TSTART, TEND})
-        for (double& v : p.c[col]) v = std::nearbyint(v / compression) * compression;  // round(x / compression, 0) * compression
-      swap_minus(p);
-      p = enforce_slope_one(p);
-      swap_minus(p);
-    }
-    T->t = std::move(p);
+    T->t = prepare(ctx, from_cols(in), minlen, compression, chunklen, T->stats);
     *out = T.release();
   });
 }
@@ -399,5 +405,245 @@ int nw_paf_stats(const nw_paf_table* t, int64_t* pairs_found, int32_t* gpu_launc
   return NW_OK;
 }
 void nw_paf_free(nw_paf_table* t) { delete t; }
+
+}  // extern "C"
+
+// =====================================================================================================
+// wrapper_paf_to_bitlocus (R/tsv_to_bitlocus.R:151-241): prepare -> checks -> grid -> checks, coarser on rejection
+// =====================================================================================================
+namespace {
+
+// update_params (R/tsv_to_bitlocus.R:111-129): both minlen and compression become the returned value
+double update_params(double minlen) {
+  const double next_power_of_10 = std::pow(10.0, std::floor(std::log10(minlen)) + 1.0);
+  double new_val = minlen >= next_power_of_10 ? next_power_of_10 * 2 : minlen * 2;
+  if (new_val >= next_power_of_10) new_val = next_power_of_10;
+  return new_val;
+}
+
+// is_cluttered_paf (R/explore_mutation_space_v2_helpers.R:231-256); the fourth term of seems_simplistic repeats qstart
+bool is_cluttered_paf(const Table& p, int limit = 5) {
+  const size_t n = p.n();
+  if (n == 0) return false;
+  auto count_eq = [&](int col, double v) {
+    int c = 0;
+    for (double x : p.c[col]) c += x == v ? 1 : 0;
+    return c;
+  };
+  auto n_unique = [&](int col) { return std::set<double>(p.c[col].begin(), p.c[col].end()).size(); };
+  const double max_qend = *std::max_element(p.c[QEND].begin(), p.c[QEND].end());
+  const double max_tend = *std::max_element(p.c[TEND].begin(), p.c[TEND].end());
+  const int clutter[4] = {count_eq(QSTART, 0.0), count_eq(QEND, max_qend), count_eq(TSTART, 0.0), count_eq(TEND, max_tend)};
+  const double half = (double)n / 2.0;
+  const bool seems_simplistic = (double)n_unique(QSTART) < half || (double)n_unique(TSTART) < half || (double)n_unique(QEND) < half;
+  bool any = false;
+  for (int c : clutter) any = any || c >= limit;
+  return any && seems_simplistic;
+}
+
+// nrow(find_sv_opportunities(mat)) (R/find_sv_opportunities.R:12-98): unique (p1, p2, orientation) over the rows with
+// two or more non-zero cells; same-orientation pairs count twice (del + dup), adjacent inverted pairs are dropped
+int64_t count_sv_opportunities(const std::vector<double>& mat, int ny, int nx) {
+  std::set<std::pair<std::pair<int, int>, int>> seen;
+  std::vector<int> nz;
+  for (int y = 0; y < ny; ++y) {
+    nz.clear();
+    for (int x = 0; x < nx; ++x)
+      if (mat[(size_t)y * nx + x] != 0) nz.push_back(x);
+    for (size_t a = 0; a < nz.size(); ++a)
+      for (size_t b = a + 1; b < nz.size(); ++b) {
+        const int ori = ((mat[(size_t)y * nx + nz[a]] > 0) == (mat[(size_t)y * nx + nz[b]] > 0)) ? 1 : -1;
+        seen.insert({{nz[a], nz[b]}, ori});
+      }
+  }
+  int64_t n = 0;
+  for (const auto& k : seen) {
+    if (k.second == 1)
+      n += 2;
+    else if (k.first.second - k.first.first != 1)
+      n += 1;
+  }
+  return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+void nw_bitlocus_default_params(nw_bitlocus_params* p) {
+  if (!p) return;
+  p->minlen = 10000;  // "default" of a 0.5 - 5 Mb region (nw_bitlocus_auto_params)
+  p->compression = 10000;
+  p->chunklen = 10000;
+  p->max_n_alns = 150;
+  p->max_size_col_plus_rows = 250;
+  p->max_pairs = 2000;
+  p->max_passes = 64;
+}
+
+// determine_chunklen / determine_compression (R/wrapper_aln_and_analyse.R:269-307): the value of the first cutoff that
+// is >= the interval length (which.min over dists[dists > 0]); at or beyond the last cutoff which.min of all-Inf is 1
+static double first_cutoff_value(double interval_len, const double* cutoffs, const double* values, int n) {
+  for (int k = 0; k < n; ++k) {
+    const double d = cutoffs[k] - interval_len;
+    if (d > 0) return values[k];
+    if (d == 0) return k + 1 < n ? values[k] : values[0];  // the zero is filtered out: the index shifts by one
+  }
+  return values[0];
+}
+void nw_bitlocus_auto_params(double start_x, double end_x, nw_bitlocus_params* p) {
+  if (!p) return;
+  const double len = end_x - start_x;
+  static const double chunk_cut[6] = {10000, 500000, 1000000, 2000000, 5000000, 1e10};
+  static const double chunk_val[6] = {100, 1000, 10000, 10000, 10000, 50000};
+  static const double comp_cut[4] = {50000, 500000, 5000000, 1e10};
+  static const double comp_val[4] = {100, 1000, 10000, 20000};
+  p->chunklen = first_cutoff_value(len, chunk_cut, chunk_val, 6);
+  p->minlen = p->compression = first_cutoff_value(len, comp_cut, comp_val, 4);
+}
+
+int nw_bitlocus_build(nw_ctx* ctx, const nw_paf_cols* pafs, int64_t n_regions, const nw_bitlocus_params* params,
+                      nw_grid** grids, nw_paf_table** tables, nw_bitlocus_info* infos, int32_t* rcs) {
+  if (grids)
+    for (int64_t k = 0; k < n_regions; ++k) grids[k] = nullptr;
+  if (tables)
+    for (int64_t k = 0; k < n_regions; ++k) tables[k] = nullptr;
+  std::vector<nw_grid*> pass_grids;  // grids of the pass in flight (freed if the pass throws)
+  const int rc = pguard([&] {
+    if (!ctx || !params || !grids || n_regions < 0 || (n_regions > 0 && !pafs)) pfail(NW_ERR_ARG, "null argument");
+    if (!(params->minlen > 0) || !(params->compression > 0) || !std::isfinite(params->minlen) ||
+        !std::isfinite(params->compression))
+      pfail(NW_ERR_ARG, "minlen and compression must be positive");
+    const int max_passes = params->max_passes > 0 ? params->max_passes : 64;
+    struct Region {
+      double minlen, compression;
+      nw_bitlocus_info info;
+      std::unique_ptr<nw_paf_table> tab;
+      int32_t rc = NW_OK;
+    };
+    std::vector<Region> R((size_t)n_regions);
+    std::vector<int64_t> pending;
+    for (int64_t k = 0; k < n_regions; ++k) {
+      R[k].minlen = params->minlen;
+      R[k].compression = params->compression;
+      R[k].info = nw_bitlocus_info{params->minlen, params->compression, 0, 0, 0, -1};
+      pending.push_back(k);
+    }
+    auto coarser = [&](Region& r, std::vector<int64_t>& next, int64_t k) {
+      r.minlen = r.compression = update_params(r.minlen);
+      r.tab.reset();
+      if (r.info.passes >= max_passes) {
+        r.rc = NW_ERR_RANGE;
+        nw::set_last_error("wrapper_paf_to_bitlocus: no acceptable grid within max_passes");
+      } else {
+        next.push_back(k);
+      }
+    };
+    while (!pending.empty()) {
+      std::vector<int64_t> next, togrid;
+      for (int64_t k : pending) {
+        Region& r = R[k];
+        r.info.passes += 1;
+        r.info.minlen = r.minlen;
+        r.info.compression = r.compression;
+        r.tab.reset(new nw_paf_table);
+        try {
+          r.tab->t = prepare(ctx, from_cols(&pafs[k]), r.minlen, r.compression, params->chunklen, r.tab->stats);
+        } catch (const PErr& e) {
+          if (e.code == NW_ERR_CUDA) throw;
+          r.rc = e.code;
+          nw::set_last_error(e.msg);
+          r.tab.reset();
+          continue;
+        }
+        const size_t n = r.tab->t.n();
+        r.info.n_alns = (int32_t)n;
+        if ((int64_t)n > (int64_t)params->max_n_alns) {  // :171-176
+          coarser(r, next, k);
+          continue;
+        }
+        if (n == 0) {  // make_xy_grid_fast stops on an empty table
+          r.rc = NW_ERR_ARG;
+          nw::set_last_error("no alignment longer than minlen");
+          r.tab.reset();
+          continue;
+        }
+        if (is_cluttered_paf(r.tab->t)) {  // :179-182: return() -- no grid
+          r.info.cluttered = 1;
+          r.tab.reset();
+          continue;
+        }
+        togrid.push_back(k);
+      }
+      if (!togrid.empty()) {
+        std::vector<nw_paf> gp(togrid.size());
+        for (size_t q = 0; q < togrid.size(); ++q) {
+          const Table& t = R[togrid[q]].tab->t;
+          gp[q] = nw_paf{t.c[TSTART].data(), t.c[TEND].data(), t.c[QSTART].data(), t.c[QEND].data(), (int64_t)t.n()};
+        }
+        pass_grids.assign(togrid.size(), nullptr);
+        std::vector<int32_t> grc(togrid.size(), NW_OK);
+        const int brc = nw_grid_build(ctx, gp.data(), (int64_t)gp.size(), pass_grids.data(), grc.data());
+        if (brc != NW_OK) pfail(brc, std::string("nw_grid_build: ") + nw_last_error());
+        for (size_t q = 0; q < togrid.size(); ++q) {
+          const int64_t k = togrid[q];
+          Region& r = R[k];
+          nw_grid*& g = pass_grids[q];
+          if (grc[q] == NW_ERR_RANGE && r.info.n_alns <= NW_GRID_MAX_ALNS &&
+              params->max_size_col_plus_rows <= NW_GRID_MAX_LINES) {
+            coarser(r, next, k);  // more than NW_GRID_MAX_LINES gridlines on an axis: certainly above the limit of :192
+            continue;
+          }
+          if (grc[q] != NW_OK) {
+            r.rc = grc[q];
+            r.tab.reset();
+            continue;
+          }
+          int32_t nx = 0, ny = 0, cv = 0, gen = 0;
+          nw_grid_dims(g, &nx, &ny, &cv, &gen);
+          if ((int64_t)nx + 1 + ny + 1 > (int64_t)params->max_size_col_plus_rows) {  // :192-197
+            nw_grid_free(g);
+            g = nullptr;
+            coarser(r, next, k);
+            continue;
+          }
+          std::vector<double> mat((size_t)nx * ny), lx((size_t)nx), ly((size_t)ny);
+          nw_grid_matrix(g, mat.data(), lx.data(), ly.data());
+          r.info.n_pairs = (int32_t)std::min<int64_t>(count_sv_opportunities(mat, ny, nx), INT32_MAX);
+          if (r.info.n_pairs > params->max_pairs) {  // :215-222
+            nw_grid_free(g);
+            g = nullptr;
+            coarser(r, next, k);
+            continue;
+          }
+          grids[k] = g;
+          g = nullptr;
+        }
+        pass_grids.clear();
+      }
+      pending.swap(next);
+    }
+    for (int64_t k = 0; k < n_regions; ++k) {
+      if (rcs) rcs[k] = R[k].rc;
+      if (infos) infos[k] = R[k].info;
+      if (tables && grids[k]) tables[k] = R[k].tab.release();
+    }
+  });
+  if (rc != NW_OK) {
+    for (nw_grid* g : pass_grids)
+      if (g) nw_grid_free(g);
+    if (grids)
+      for (int64_t k = 0; k < n_regions; ++k) {
+        if (grids[k]) nw_grid_free(grids[k]);
+        grids[k] = nullptr;
+      }
+    if (tables)
+      for (int64_t k = 0; k < n_regions; ++k) {
+        delete tables[k];
+        tables[k] = nullptr;
+      }
+  }
+  return rc;
+}
 
 }  // extern "C"
