@@ -465,6 +465,105 @@ def run_grid(args, rank, world, local):
     solver.close()
 
 
+def _bitlocus_cpu_one(p):
+    from oracle import nw_bitlocus_oracle as bo
+    try:
+        return bo.wrapper_paf_to_bitlocus(p, 1000.0, 1000.0)["status"]
+    except Exception:
+        return None
+
+
+def run_bitlocus(args, rank, world, local):
+    """SURVEY 8f rows 4 + 2 joined: wrapper_paf_to_bitlocus (PAF preparation, limits, gridding, SV-pair limit, coarser
+    retries) for a regionfile batch through nw_bitlocus_build.  Metric: regions/s, wall clock around the C-ABI call
+    (host PAF columns in, prepared tables + grids in host memory out).  --impl reference: the R restatement (Python) on
+    all host cores, one region per worker process."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from region_batch import make_stage_regions
+    from nahrwhals_b200.sdgrid import matrix_to_chunked_paf
+    cores = os.cpu_count() or 1
+    n_reg = max(16, args.regions // 4)
+    desc = ("wrapper_paf_to_bitlocus of a regionfile batch: chunked (10 kb) alignment tables of %d synthetic SD-flanked "
+            "regions per GPU (20-120 blocks) -> prepared PAF -> gridlines -> gridmatrix, minlen = compression = 1000, "
+            "max_n_alns 150, max_size_col_plus_rows 250")
+
+    def cpu(pafs):
+        import multiprocessing as mp
+        t0 = time.perf_counter()
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_bitlocus_cpu_one, pafs, chunksize=2)
+        return len(pafs) / (time.perf_counter() - t0), time.perf_counter() - t0
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        pafs = [matrix_to_chunked_paf(m, lx, ly) for m, ly, lx, _ in make_stage_regions(max(64, n_reg // 20), seed=0)]
+        r, dt = cpu(pafs)
+        print(json.dumps(dict(impl="reference", metric="regions_to_bitlocus_per_s", value=r, unit="regions/s",
+                              n_gpus=args.gpus, steps=1, warmup=0, ms_per_step=1e3 * dt, higher_is_better=True,
+                              scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                              config=dict(workload=desc % len(pafs)),
+                              cpu_baseline=dict(value=r, unit="regions/s", cores=cores, kind="port",
+                                                sample="%d regions, one per worker process" % len(pafs)),
+                              e2e=dict(value=r, unit="regions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                              gpu_launches=0)), flush=True)
+        return
+    import torch
+    import nahrwhals_b200 as nb
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pafs = [matrix_to_chunked_paf(m, lx, ly) for m, ly, lx, _ in make_stage_regions(n_reg, seed=rank)]
+    solver = nb.Solver(local)
+    for k in range(3):  # steady state: the context's staging buffers have seen a batch of this size
+        nb.paf_to_bitlocus(solver, pafs if k == 0 else pafs[:min(len(pafs), 200)], 1000.0, 1000.0)
+    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler.start()
+    steps = max(1, args.steps)
+    dt = 0.0
+    for _ in range(steps):
+        tm = {}
+        res = nb.paf_to_bitlocus(solver, pafs, 1000.0, 1000.0, timing=tm)
+        dt += tm["native_s"]
+    torch.cuda.synchronize()
+    dt /= steps
+    clocks = sampler.stop()
+    n, ok = len(pafs), sum(1 for r in res if r.status == "ok")
+    alns = sum(len(p["tstart"]) for p in pafs)
+    passes = sum(r.passes for r in res)
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        s = torch.tensor([n, ok, alns, passes], dtype=torch.float64, device="cuda")
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        n, ok, alns, passes = s.tolist()
+    max_passes = max(r.passes for r in res)
+    line = dict(metric="regions_to_bitlocus_per_s", value=n / dt, unit="regions/s", n_gpus=world, steps=steps, warmup=3,
+                ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=(desc % n_reg) + "; regions shard per GPU, no collective", accepted=int(ok),
+                            alignments_in=int(alns), passes=int(passes),
+                            timed="wall clock around nw_bitlocus_build (host PAF columns in, tables + grids out)"),
+                clocks=clocks, e2e=dict(value=n / dt, unit="regions/s", h2d_bytes_per_step=int(alns) * 56,
+                                        d2h_bytes_per_step=None), gpu_launches=4 * max_passes * steps * max(world, 1))
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = pafs[:max(32, n_reg // 20)]
+        r, cdt = cpu(sample)
+        line["cpu_baseline"] = dict(value=r, unit="regions/s", cores=cores, kind="port",
+                                    sample="%d regions of the same set, %.1f s, one region per worker process; R "
+                                           "restatement in Python" % (len(sample), cdt))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    solver.close()
+
+
 def _paf_tables(n, seed, n_segments=260):
     """Chunked PAF tables of a few thousand alignments each (a 4 Mb region cut into 10 kb chunks, repeats, short hits)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -516,8 +615,8 @@ def run_paf(args, rank, world, local):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     tabs = _paf_tables(n_tab, rank)
     solver = nb.Solver(local)
-    for t in tabs[:3]:
-        nb.load_and_prep_paf(solver, t, 1000.0, 1000.0, 10000.0)
+    for _ in range(3):
+        nb.load_and_prep_pafs(solver, tabs, 1000.0, 1000.0, 10000.0)
     sampler = ClockSampler(local)
     torch.cuda.synchronize()
     if dist is not None:
@@ -527,8 +626,8 @@ def run_paf(args, rank, world, local):
     t0 = time.perf_counter()
     launches = 0
     for _ in range(steps):
-        for t in tabs:
-            launches += nb.load_and_prep_paf(solver, t, 1000.0, 1000.0, 10000.0)["_gpu_launches"]
+        got, _ = nb.load_and_prep_pafs(solver, tabs, 1000.0, 1000.0, 10000.0)
+        launches += max(t["_gpu_launches"] for t in got)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
     clocks = sampler.stop()
@@ -543,7 +642,7 @@ def run_paf(args, rank, world, local):
     line = dict(metric="paf_alignments_prepared_per_s", value=rows / dt, unit="alignments/s", n_gpus=world, steps=steps,
                 warmup=3, ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                 data="synthetic", config=dict(workload=(desc % n_tab) + "; tables shard per GPU, no collective",
-                                             timed="wall clock around nw_paf_prepare through the Python mirror"),
+                                             timed="wall clock around nw_paf_prepare_many (one all-pairs launch per batch) through the Python mirror"),
                 clocks=clocks, e2e=dict(value=rows / dt, unit="alignments/s", h2d_bytes_per_step=int(rows) * 56,
                                         d2h_bytes_per_step=None), gpu_launches=int(launches))
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -614,7 +713,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS) + ["regions", "stage", "genome", "grid", "paf"])
+    ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS) + ["regions", "stage", "genome", "grid", "paf", "bitlocus"])
     ap.add_argument("--regions", type=int, default=6000, help="regions per rank for --workload regions")
     ap.add_argument("--contexts", type=int, default=4, help="solver contexts (streams) per GPU for --workload regions")
     ap.add_argument("--warmup-regions", type=int, default=2, help="untimed warm-up runs for --workload regions")
@@ -634,6 +733,9 @@ def main():
         return
     if args.workload == "grid":
         run_grid(args, rank, world, local)
+        return
+    if args.workload == "bitlocus":
+        run_bitlocus(args, rank, world, local)
         return
     if args.workload == "paf":
         run_paf(args, rank, world, local)

@@ -48,6 +48,12 @@ int nw_paf_compress(nw_ctx* ctx, const nw_paf_cols* in, int32_t second_run, doub
 int nw_paf_prepare(nw_ctx* ctx, const nw_paf_cols* in, double minlen, double compression, double chunklen,
                    nw_paf_table** out);
 
+/* nw_paf_prepare for a batch of tables (the regions of a regionfile): the all-pairs tests of all tables run in ONE
+ * kernel launch (one upload, one download).  rcs[k] (may be NULL) is the status of table k (NW_ERR_ARG for a malformed
+ * table; outs[k] is NULL then); the call returns the first CUDA / argument error of the batch itself. */
+int nw_paf_prepare_many(nw_ctx* ctx, const nw_paf_cols* ins, int64_t n_tables, double minlen, double compression,
+                        double chunklen, nw_paf_table** outs, int32_t* rcs);
+
 int64_t nw_paf_rows(const nw_paf_table* t);
 /* any pointer may be NULL; arrays of nw_paf_rows() doubles */
 int nw_paf_columns(const nw_paf_table* t, double* qlen, double* qstart, double* qend, double* strand, double* tlen,

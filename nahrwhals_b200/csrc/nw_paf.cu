@@ -10,6 +10,12 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -27,6 +33,7 @@ namespace nw {
 void set_last_error(const std::string& m);
 int ctx_device(nw_ctx* c);
 cudaStream_t ctx_stream(nw_ctx* c);
+cudaError_t ctx_region_staging(nw_ctx* c, size_t bytes, void** host_pinned, void** dev);
 }  // namespace nw
 
 namespace {
@@ -42,28 +49,93 @@ struct PErr {
     if (e_ != cudaSuccess) pfail(NW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+// tables are independent on the host side: the pre / post phases of a batch run on a few threads.  fn must not throw
+// anything but PErr; the first error is rethrown on the calling thread.
+void paf_parallel_for(int64_t n, const std::function<void(int64_t)>& fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  const int nt = (int)std::min<int64_t>(std::max<int64_t>(1, n / 2), std::min<unsigned>(hw ? hw : 4, 8u));
+  if (nt <= 1) {
+    for (int64_t k = 0; k < n; ++k) fn(k);
+    return;
+  }
+  std::atomic<int64_t> next{0};
+  std::mutex mu;
+  bool failed = false;
+  PErr err{NW_OK, ""};
+  auto work = [&] {
+    for (;;) {
+      const int64_t k = next.fetch_add(1);
+      if (k >= n) return;
+      try {
+        fn(k);
+      } catch (const PErr& e) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!failed) err = e;
+        failed = true;
+        next.store(n);
+      } catch (const std::exception& e) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!failed) err = PErr{NW_ERR_NOMEM, e.what()};
+        failed = true;
+        next.store(n);
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  if (failed) throw err;
+}
+double paf_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 struct PairRec {
-  int32_t col, step, row, pad;
+  int32_t col, step, row, tab;
 };
 
-// one thread per ordered pair (i = row: the alignment that ends, j = col: the alignment that starts)
-__global__ void k_paf_pairs(const double* __restrict__ ts, const double* __restrict__ te, const double* __restrict__ qs,
-                            const double* __restrict__ qe, const double* __restrict__ strand, const double* __restrict__ alen,
-                            const unsigned long long* __restrict__ mask, const double* __restrict__ tol, int n,
-                            PairRec* __restrict__ out, unsigned long long cap, unsigned long long* __restrict__ count) {
-  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// one thread per ordered pair (i = row: the alignment that ends, j = col: the alignment that starts) of one table of a
+// batch; the column arrays of all tables are concatenated, a CTA works on one table (tables start at CTA boundaries)
+struct PafTab {
+  uint32_t off;      // first element of the table in the concatenated columns
+  uint32_t n;        // alignments
+  uint32_t tol_off;  // first tolerance (one per chunk)
+  uint32_t blk0;     // first CTA of the table
+  uint32_t out_off;  // first record of the table's output segment
+  uint32_t out_cap;  // records the segment holds
+};
+__global__ void __launch_bounds__(256) k_paf_pairs(const PafTab* __restrict__ tabs, int n_tabs, const double* __restrict__ ts,
+                                                   const double* __restrict__ te, const double* __restrict__ qs,
+                                                   const double* __restrict__ qe, const double* __restrict__ strand,
+                                                   const double* __restrict__ alen, const unsigned long long* __restrict__ mask,
+                                                   const double* __restrict__ tol, PairRec* __restrict__ out,
+                                                   unsigned int* __restrict__ count /* [n_tabs] */) {
+  __shared__ PafTab T;
+  __shared__ int s_tab;
+  if (threadIdx.x == 0) {  // last table with blk0 <= blockIdx.x
+    int lo = 0, hi = n_tabs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (tabs[mid].blk0 <= blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    T = tabs[lo];
+    s_tab = lo;
+  }
+  __syncthreads();
+  const int n = (int)T.n;
+  const long long w = (long long)(blockIdx.x - T.blk0) * blockDim.x + threadIdx.x;
   if (w >= (long long)n * n) return;
   const int j = (int)(w / n), i = (int)(w % n);  // column-major like which(, arr.ind = T): consecutive threads share j
-  unsigned long long common = mask[i] & mask[j];
-  if (!common || strand[i] != strand[j]) return;
-  const double dt = fabs(te[i] - ts[j]), dq = fabs(qe[i] - qs[j]);
+  const size_t gi = (size_t)T.off + i, gj = (size_t)T.off + j;
+  unsigned long long common = mask[gi] & mask[gj];
+  if (!common || strand[gi] != strand[gj]) return;
+  const double dt = fabs(te[gi] - ts[gj]), dq = fabs(qe[gi] - qs[gj]);
   while (common) {
     const int s = __ffsll((long long)common) - 1;
     common &= common - 1;
-    const double t = tol[s];
-    if (dt < t && dq < t && (!(t > 100) || (alen[i] > t && alen[j] > t))) {
-      const unsigned long long k = atomicAdd(count, 1ull);
-      if (k < cap) out[k] = PairRec{j, s, i, 0};
+    const double t = tol[T.tol_off + s];
+    if (dt < t && dq < t && (!(t > 100) || (alen[gi] > t && alen[gj] > t))) {
+      const unsigned int k = atomicAdd(&count[s_tab], 1u);  // the table's own cursor and output segment
+      if (k < T.out_cap) out[(size_t)T.out_off + k] = PairRec{j, s, i, s_tab};
       return;  // later chunks only repeat the pair (unique() drops the repeats)
     }
   }
@@ -153,25 +225,42 @@ struct CompressStats {
   int launches = 0;
 };
 
-// compress_paf_fnct(inpaf_df = , save_outpaf = F, qname = NULL)
-Table compress(nw_ctx* ctx, const Table& in, bool second_run, double chunklen, double compression, int n_quadrants,
-               CompressStats& stats) {
-  Table p = take(in, stable_order(in.c[QSTART]));
+// compress_paf_fnct(inpaf_df = , save_outpaf = F, qname = NULL) in three phases, so that the all-pairs tests of many
+// tables share one upload, one launch and one download: host (sorting, chunk masks, tolerances) -> GPU -> host
+// (selection, merge_rows)
+struct CompressJob {
+  bool second_run = true;
+  double chunklen = 10000, compression = 1000;
+  int n_quadrants = 0;
+  Table p, shortt;
+  int n = 0, nsteps = 0;
+  std::vector<unsigned long long> mask;
+  std::vector<double> tol;
+  bool need_gpu = false;
+  std::vector<PairRec> recs;
+  CompressStats stats;
+};
+
+void compress_pre(CompressJob& J, const Table& in) {
+  J.need_gpu = false;
+  J.recs.clear();
+  J.shortt = Table();
+  J.p = take(in, stable_order(in.c[QSTART]));
+  Table& p = J.p;
   const size_t n0 = p.n();
-  if (n0 <= 1) return p;
+  if (n0 <= 1) return;
   p = take(p, stable_order(p.c[TSTART]));
   const double range_t = *std::max_element(p.c[TEND].begin(), p.c[TEND].end());
-  const double minlen_for_merge = n0 < 15000 ? 0.0 : chunklen * 0.9;
-  int nq = n_quadrants > 0 ? n_quadrants : (range_t < 50000 ? 2 : 10);
+  const double minlen_for_merge = n0 < 15000 ? 0.0 : J.chunklen * 0.9;
+  const int nq = J.n_quadrants > 0 ? J.n_quadrants : (range_t < 50000 ? 2 : 10);
   if (nq > 64) pfail(NW_ERR_ARG, "at most 64 quadrants per axis");
-  Table shortt;
   {
     std::vector<size_t> a, b;
     for (size_t k = 0; k < p.n(); ++k) (p.c[ALEN][k] <= minlen_for_merge ? a : b).push_back(k);
-    shortt = take(p, a);
+    J.shortt = take(p, a);
     p = take(p, b);
   }
-  const int n = (int)p.n();
+  const int n = J.n = (int)p.n();
   std::vector<double> tsteps(nq);
   {
     const double by = nq > 1 ? (range_t - 1) / (nq - 1) : 0.0;  // seq(1, range, length.out = nq): from + k * by
@@ -179,14 +268,14 @@ Table compress(nw_ctx* ctx, const Table& in, bool second_run, double chunklen, d
   }
   double tstepsize = nq > 1 ? tsteps[1] - tsteps[0] : NAN;
   if (nq == 1) tstepsize = 1e10;
-  const int nsteps = nq - 1;
-  auto append_short = [&](Table& t) {
-    for (int k = 0; k < 10; ++k) t.c[k].insert(t.c[k].end(), shortt.c[k].begin(), shortt.c[k].end());
-  };
-  if (n < 2 || nsteps < 1) return p;  // no chunk can hold two alignments: rowpairs stays empty (short rows are dropped too)
+  const int nsteps = J.nsteps = nq - 1;
+  if (n < 2 || nsteps < 1) {  // no chunk can hold two alignments: rowpairs stays empty (short rows are dropped too)
+    J.shortt = Table();
+    return;
+  }
   // chunk membership and per-chunk tolerance
-  std::vector<unsigned long long> mask(n, 0ull);
-  std::vector<double> tol(std::max(nsteps, 1), 0.0);
+  J.mask.assign(n, 0ull);
+  J.tol.assign(std::max(nsteps, 1), 0.0);
   bool any = false;
   for (int s = 0; s < nsteps; ++s) {
     const double lo = tsteps[s], hi = tsteps[s] + tstepsize;
@@ -195,71 +284,133 @@ Table compress(nw_ctx* ctx, const Table& in, bool second_run, double chunklen, d
     for (int k = 0; k < n; ++k) {
       const double a = p.c[TSTART][k], b = p.c[TEND][k];
       if ((a >= lo && a <= hi) || (b >= lo && b <= hi)) {
-        mask[k] |= 1ull << s;
+        J.mask[k] |= 1ull << s;
         ++cnt;
         minq = std::min(minq, p.c[QLEN][k]);
       }
     }
     if (cnt > 1) {
-      tol[s] = second_run ? std::min(0.5 * compression, minq * 0.9) : 0.05 * chunklen;
+      J.tol[s] = J.second_run ? std::min(0.5 * J.compression, minq * 0.9) : 0.05 * J.chunklen;
       any = true;
     } else {
-      for (int k = 0; k < n; ++k) mask[k] &= ~(1ull << s);  // nrow(inpaf_q) <= 1: the chunk is skipped
+      for (int k = 0; k < n; ++k) J.mask[k] &= ~(1ull << s);  // nrow(inpaf_q) <= 1: the chunk is skipped
     }
   }
-  if (!any) return p;
-  // ---- GPU: all ordered pairs ----
-  std::vector<PairRec> recs;
-  {
-    PCK(cudaSetDevice(nw::ctx_device(ctx)));
-    cudaStream_t st = nw::ctx_stream(ctx);
-    const size_t nb = (size_t)n * 8;
-    unsigned char* d = nullptr;
-    unsigned long long cap = std::max<unsigned long long>(4096, (unsigned long long)n * 8);
-    for (;;) {
-      const size_t total = 7 * nb + (size_t)nsteps * 8 + 16 + cap * sizeof(PairRec);
-      PCK(cudaMalloc(&d, total));
-      try {
-        double* dts = (double*)d;
-        double *dte = dts + n, *dqs = dte + n, *dqe = dqs + n, *dst = dqe + n, *dal = dst + n;
-        unsigned long long* dmask = (unsigned long long*)(dal + n);
-        double* dtol = (double*)(dmask + n);
-        unsigned long long* dcount = (unsigned long long*)(dtol + nsteps);
-        PairRec* dout = (PairRec*)(dcount + 2);
-        PCK(cudaMemcpyAsync(dts, p.c[TSTART].data(), nb, cudaMemcpyHostToDevice, st));
-        PCK(cudaMemcpyAsync(dte, p.c[TEND].data(), nb, cudaMemcpyHostToDevice, st));
-        PCK(cudaMemcpyAsync(dqs, p.c[QSTART].data(), nb, cudaMemcpyHostToDevice, st));
-        PCK(cudaMemcpyAsync(dqe, p.c[QEND].data(), nb, cudaMemcpyHostToDevice, st));
-        PCK(cudaMemcpyAsync(dst, p.c[STRAND].data(), nb, cudaMemcpyHostToDevice, st));
-        PCK(cudaMemcpyAsync(dal, p.c[ALEN].data(), nb, cudaMemcpyHostToDevice, st));
-        PCK(cudaMemcpyAsync(dmask, mask.data(), nb, cudaMemcpyHostToDevice, st));
-        PCK(cudaMemcpyAsync(dtol, tol.data(), (size_t)nsteps * 8, cudaMemcpyHostToDevice, st));
-        PCK(cudaMemsetAsync(dcount, 0, 16, st));
-        const long long work = (long long)n * n;
-        k_paf_pairs<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(dts, dte, dqs, dqe, dst, dal, dmask, dtol, n, dout, cap, dcount);
-        PCK(cudaGetLastError());
-        ++stats.launches;
-        unsigned long long found = 0;
-        PCK(cudaMemcpyAsync(&found, dcount, 8, cudaMemcpyDeviceToHost, st));
-        PCK(cudaStreamSynchronize(st));
-        if (found <= cap) {
-          recs.resize((size_t)found);
-          if (found) PCK(cudaMemcpy(recs.data(), dout, (size_t)found * sizeof(PairRec), cudaMemcpyDeviceToHost));
-          cudaFree(d);
-          d = nullptr;
-          break;
-        }
-        cap = found + found / 8;
-      } catch (...) {
-        cudaFree(d);
-        throw;
+  if (!any) {
+    J.shortt = Table();
+    return;
+  }
+  J.need_gpu = true;
+}
+
+// ---- GPU: all ordered pairs of every job that needs them, one launch per sub-batch ----
+constexpr size_t PAF_BATCH_ALNS = 1u << 20;     // alignments per launch (56 B each in the staging buffer)
+constexpr size_t PAF_BATCH_BLOCKS = 1u << 30;   // CTAs per launch
+
+void compress_gpu_batch(nw_ctx* ctx, CompressJob** jobs, size_t nj, int& launches) {
+  PCK(cudaSetDevice(nw::ctx_device(ctx)));
+  cudaStream_t st = nw::ctx_stream(ctx);
+  size_t N = 0, NT = 0, blocks = 0;
+  std::vector<PafTab> tabs(nj);
+  std::vector<size_t> cap(nj);
+  for (size_t t = 0; t < nj; ++t) {
+    const CompressJob& J = *jobs[t];
+    tabs[t] = PafTab{(uint32_t)N, (uint32_t)J.n, (uint32_t)NT, (uint32_t)blocks, 0u, 0u};
+    N += (size_t)J.n;
+    NT += (size_t)J.nsteps;
+    blocks += ((size_t)J.n * J.n + 255) / 256;
+    cap[t] = 2 * (size_t)J.n + 64;  // chunks of one alignment pair up with their neighbours: ~n pairs
+  }
+  auto al16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  const size_t o_tabs = 0, o_cols = al16(nj * sizeof(PafTab)), o_tol = o_cols + 7 * N * 8, o_cnt = al16(o_tol + NT * 8),
+               o_out = al16(o_cnt + nj * 4);
+  for (;;) {
+    size_t ncap = 0;
+    for (size_t t = 0; t < nj; ++t) {
+      tabs[t].out_off = (uint32_t)ncap;
+      tabs[t].out_cap = (uint32_t)cap[t];
+      ncap += cap[t];
+    }
+    if (ncap > 0xffffffffull) pfail(NW_ERR_RANGE, "PAF batch too large");
+    const size_t total = o_out + ncap * sizeof(PairRec);
+    void *hp = nullptr, *dp = nullptr;
+    PCK(nw::ctx_region_staging(ctx, total, &hp, &dp));
+    unsigned char* h = (unsigned char*)hp;
+    unsigned char* d = (unsigned char*)dp;
+    memcpy(h + o_tabs, tabs.data(), nj * sizeof(PafTab));
+    static const int colsel[6] = {TSTART, TEND, QSTART, QEND, STRAND, ALEN};
+    paf_parallel_for((int64_t)nj, [&](int64_t t) {
+      const CompressJob& J = *jobs[t];
+      for (int c = 0; c < 6; ++c) memcpy(h + o_cols + ((size_t)c * N + tabs[t].off) * 8, J.p.c[colsel[c]].data(), (size_t)J.n * 8);
+      memcpy(h + o_cols + ((size_t)6 * N + tabs[t].off) * 8, J.mask.data(), (size_t)J.n * 8);
+      memcpy(h + o_tol + (size_t)tabs[t].tol_off * 8, J.tol.data(), (size_t)J.nsteps * 8);
+    });
+    memset(h + o_cnt, 0, o_out - o_cnt);
+    PCK(cudaMemcpyAsync(d, h, o_out, cudaMemcpyHostToDevice, st));
+    const double* dc = (const double*)(d + o_cols);
+    k_paf_pairs<<<(unsigned)blocks, 256, 0, st>>>((const PafTab*)(d + o_tabs), (int)nj, dc, dc + N, dc + 2 * N, dc + 3 * N,
+                                                  dc + 4 * N, dc + 5 * N, (const unsigned long long*)(dc + 6 * N),
+                                                  (const double*)(d + o_tol), (PairRec*)(d + o_out),
+                                                  (unsigned int*)(d + o_cnt));
+    PCK(cudaGetLastError());
+    ++launches;
+    PCK(cudaMemcpyAsync(h + o_cnt, d + o_cnt, nj * 4, cudaMemcpyDeviceToHost, st));
+    PCK(cudaStreamSynchronize(st));
+    const unsigned int* found = (const unsigned int*)(h + o_cnt);
+    bool overflow = false;
+    size_t last = 0;  // records up to the end of the last non-empty segment are fetched
+    for (size_t t = 0; t < nj; ++t) {
+      if (found[t] > cap[t]) {
+        cap[t] = (size_t)found[t] + found[t] / 8;
+        overflow = true;
       }
-      cudaFree(d);
-      d = nullptr;
+      if (found[t]) last = (size_t)tabs[t].out_off + std::min<size_t>(found[t], tabs[t].out_cap);
     }
+    if (overflow) continue;  // rare: a segment was too small -- again with the exact sizes
+    if (last) {
+      PCK(cudaMemcpyAsync(h + o_out, d + o_out, last * sizeof(PairRec), cudaMemcpyDeviceToHost, st));
+      PCK(cudaStreamSynchronize(st));
+      const PairRec* r = (const PairRec*)(h + o_out);
+      paf_parallel_for((int64_t)nj, [&](int64_t t) {
+        jobs[t]->recs.assign(r + tabs[t].out_off, r + tabs[t].out_off + found[t]);
+      });
+    }
+    return;
   }
-  stats.pairs_found = (int64_t)recs.size();
-  if (recs.empty()) return p;
+}
+
+void compress_gpu(nw_ctx* ctx, const std::vector<CompressJob*>& all) {
+  std::vector<CompressJob*> need;
+  for (CompressJob* J : all)
+    if (J->need_gpu) need.push_back(J);
+  size_t a = 0;
+  while (a < need.size()) {
+    size_t b = a, N = 0, blocks = 0;
+    while (b < need.size()) {
+      const size_t n = (size_t)need[b]->n, bl = (n * n + 255) / 256;
+      if (b > a && (N + n > PAF_BATCH_ALNS || blocks + bl > PAF_BATCH_BLOCKS)) break;
+      N += n;
+      blocks += bl;
+      ++b;
+    }
+    if (N > 0xffffffffull || blocks > 0x7fffffffull) pfail(NW_ERR_RANGE, "PAF table too large");
+    int launches = 0;
+    compress_gpu_batch(ctx, need.data() + a, b - a, launches);
+    for (size_t t = a; t < b; ++t) need[t]->stats.launches += launches;  // launches the table took part in
+    a = b;
+  }
+}
+
+Table compress_post(CompressJob& J) {
+  if (!J.need_gpu) return std::move(J.p);
+  Table& p = J.p;
+  const double chunklen = J.chunklen;
+  auto append_short = [&](Table& t) {
+    for (int k = 0; k < 10; ++k) t.c[k].insert(t.c[k].end(), J.shortt.c[k].begin(), J.shortt.c[k].end());
+  };
+  std::vector<PairRec>& recs = J.recs;
+  J.stats.pairs_found = (int64_t)recs.size();
+  if (recs.empty()) return std::move(p);
   // rowpairs[order(col), ] (stable over chunk order, then column-major inside a chunk), unique(): the kernel reports a
   // pair once, with its first chunk, so the reference's order is (col, first chunk, row)
   std::sort(recs.begin(), recs.end(), [](const PairRec& a, const PairRec& b) {
@@ -279,19 +430,14 @@ Table compress(nw_ctx* ctx, const Table& in, bool second_run, double chunklen, d
   }
   // group_by(row) %>% top_n(1, combined_matchlen) %>% group_by(col) %>% top_n(1, combined_matchlen): ties are kept
   {
-    std::map<int, double> best;
-    for (const RP& r : rp) {
-      auto it = best.find(r.row);
-      if (it == best.end() || r.ml > it->second) best[r.row] = r.ml;
-    }
+    const double none = -INFINITY;
+    std::vector<double> best(p.n(), none);
+    for (const RP& r : rp) best[r.row] = std::max(best[r.row], r.ml);
     std::vector<RP> k1;
     for (const RP& r : rp)
       if (r.ml == best[r.row]) k1.push_back(r);
-    best.clear();
-    for (const RP& r : k1) {
-      auto it = best.find(r.col);
-      if (it == best.end() || r.ml > it->second) best[r.col] = r.ml;
-    }
+    std::fill(best.begin(), best.end(), none);
+    for (const RP& r : k1) best[r.col] = std::max(best[r.col], r.ml);
     rp.clear();
     for (const RP& r : k1)
       if (r.ml == best[r.col]) rp.push_back(r);
@@ -302,7 +448,21 @@ Table compress(nw_ctx* ctx, const Table& in, bool second_run, double chunklen, d
     p = merge_rows(p, pairs);
   }
   append_short(p);
-  return p;
+  return std::move(p);
+}
+
+Table compress(nw_ctx* ctx, const Table& in, bool second_run, double chunklen, double compression, int n_quadrants,
+               CompressStats& stats) {
+  CompressJob J;
+  J.second_run = second_run;
+  J.chunklen = chunklen;
+  J.compression = compression;
+  J.n_quadrants = n_quadrants;
+  compress_pre(J, in);
+  compress_gpu(ctx, {&J});
+  Table out = compress_post(J);
+  stats = J.stats;
+  return out;
 }
 
 Table enforce_slope_one(const Table& p) {  // R/tsv_to_bitlocus.R:258-275
@@ -318,11 +478,27 @@ Table enforce_slope_one(const Table& p) {  // R/tsv_to_bitlocus.R:258-275
   return take(o, keep);
 }
 
-// load_and_prep_paf_for_gridplot_transform from the parsed table on (R/tsv_to_bitlocus.R:38-82)
-Table prepare(nw_ctx* ctx, Table p, double minlen, double compression, double chunklen, CompressStats& stats) {
+// load_and_prep_paf_for_gridplot_transform from the parsed table on (R/tsv_to_bitlocus.R:38-82), in the phases of
+// compress: prepare_pre (host) -> compress_gpu (one launch for all jobs of a batch) -> prepare_post (host)
+struct PrepJob {
+  CompressJob cj;
+  double minlen = 0, compression = 0;
+};
+void prepare_pre(PrepJob& J, Table p, double minlen, double compression, double chunklen) {
   if (!(compression > 0)) pfail(NW_ERR_ARG, "compression must be positive");
+  J.minlen = minlen;
+  J.compression = compression;
+  J.cj = CompressJob();
+  J.cj.second_run = true;
+  J.cj.chunklen = chunklen;
+  J.cj.compression = compression;
   swap_minus(p);
-  p = compress(ctx, p, true, chunklen, compression, 0, stats);
+  compress_pre(J.cj, p);
+}
+Table prepare_post(PrepJob& J, CompressStats& stats) {
+  Table p = compress_post(J.cj);
+  stats = J.cj.stats;
+  const double minlen = J.minlen, compression = J.compression;
   {
     std::vector<size_t> keep;
     for (size_t k = 0; k < p.n(); ++k)
@@ -337,6 +513,12 @@ Table prepare(nw_ctx* ctx, Table p, double minlen, double compression, double ch
     swap_minus(p);
   }
   return p;
+}
+Table prepare(nw_ctx* ctx, Table p, double minlen, double compression, double chunklen, CompressStats& stats) {
+  PrepJob J;
+  prepare_pre(J, std::move(p), minlen, compression, chunklen);
+  compress_gpu(ctx, {&J.cj});
+  return prepare_post(J, stats);
 }
 
 }  // namespace
@@ -387,6 +569,56 @@ int nw_paf_prepare(nw_ctx* ctx, const nw_paf_cols* in, double minlen, double com
     T->t = prepare(ctx, from_cols(in), minlen, compression, chunklen, T->stats);
     *out = T.release();
   });
+}
+
+int nw_paf_prepare_many(nw_ctx* ctx, const nw_paf_cols* ins, int64_t n_tables, double minlen, double compression,
+                        double chunklen, nw_paf_table** outs, int32_t* rcs) {
+  if (outs)
+    for (int64_t k = 0; k < n_tables; ++k) outs[k] = nullptr;
+  const int rc = pguard([&] {
+    if (!ctx || !outs || n_tables < 0 || (n_tables > 0 && !ins)) pfail(NW_ERR_ARG, "null argument");
+    static const bool dbg = getenv("NW_DEBUG_TIMING") != nullptr;
+    const double t0 = paf_now();
+    std::vector<PrepJob> jobs((size_t)n_tables);
+    std::vector<int32_t> st((size_t)n_tables, NW_OK);
+    std::vector<std::string> msg((size_t)n_tables);
+    paf_parallel_for(n_tables, [&](int64_t k) {
+      try {
+        prepare_pre(jobs[k], from_cols(&ins[k]), minlen, compression, chunklen);
+      } catch (const PErr& e) {
+        st[k] = e.code;
+        msg[k] = e.msg;
+      }
+    });
+    std::vector<CompressJob*> run;
+    for (int64_t k = 0; k < n_tables; ++k) {
+      if (st[k] == NW_OK)
+        run.push_back(&jobs[k].cj);
+      else
+        nw::set_last_error(msg[k]);
+    }
+    const double t1 = paf_now();
+    compress_gpu(ctx, run);
+    const double t2 = paf_now();
+    std::vector<std::unique_ptr<nw_paf_table>> res((size_t)n_tables);
+    paf_parallel_for(n_tables, [&](int64_t k) {
+      if (st[k] != NW_OK) return;
+      res[k].reset(new nw_paf_table);
+      res[k]->t = prepare_post(jobs[k], res[k]->stats);
+    });
+    for (int64_t k = 0; k < n_tables; ++k) outs[k] = res[k].release();
+    if (dbg)
+      fprintf(stderr, "[nw_paf_prepare_many] %lld tables: pre %.2f ms, gpu %.2f ms, post %.2f ms\n", (long long)n_tables,
+              1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (paf_now() - t2));
+    if (rcs)
+      for (int64_t k = 0; k < n_tables; ++k) rcs[k] = st[k];
+  });
+  if (rc != NW_OK && outs)
+    for (int64_t k = 0; k < n_tables; ++k) {
+      delete outs[k];
+      outs[k] = nullptr;
+    }
+  return rc;
 }
 
 int64_t nw_paf_rows(const nw_paf_table* t) { return t ? (int64_t)t->t.n() : 0; }
@@ -515,6 +747,7 @@ int nw_bitlocus_build(nw_ctx* ctx, const nw_paf_cols* pafs, int64_t n_regions, c
         !std::isfinite(params->compression))
       pfail(NW_ERR_ARG, "minlen and compression must be positive");
     const int max_passes = params->max_passes > 0 ? params->max_passes : 64;
+    static const bool dbg = getenv("NW_DEBUG_TIMING") != nullptr;
     struct Region {
       double minlen, compression;
       nw_bitlocus_info info;
@@ -539,23 +772,46 @@ int nw_bitlocus_build(nw_ctx* ctx, const nw_paf_cols* pafs, int64_t n_regions, c
         next.push_back(k);
       }
     };
+    std::vector<PrepJob> jobs((size_t)n_regions);
     while (!pending.empty()) {
-      std::vector<int64_t> next, togrid;
-      for (int64_t k : pending) {
+      std::vector<int64_t> next, togrid, prepared;
+      std::vector<CompressJob*> run;
+      std::vector<std::string> msg(pending.size());
+      const double t0 = paf_now();
+      paf_parallel_for((int64_t)pending.size(), [&](int64_t q) {  // host part of the preparation, tables in parallel
+        const int64_t k = pending[q];
         Region& r = R[k];
         r.info.passes += 1;
         r.info.minlen = r.minlen;
         r.info.compression = r.compression;
-        r.tab.reset(new nw_paf_table);
         try {
-          r.tab->t = prepare(ctx, from_cols(&pafs[k]), r.minlen, r.compression, params->chunklen, r.tab->stats);
+          prepare_pre(jobs[k], from_cols(&pafs[k]), r.minlen, r.compression, params->chunklen);
         } catch (const PErr& e) {
-          if (e.code == NW_ERR_CUDA) throw;
           r.rc = e.code;
-          nw::set_last_error(e.msg);
-          r.tab.reset();
-          continue;
+          msg[q] = e.msg;
         }
+      });
+      for (size_t q = 0; q < pending.size(); ++q) {
+        const int64_t k = pending[q];
+        if (R[k].rc == NW_OK) {
+          run.push_back(&jobs[k].cj);
+          prepared.push_back(k);
+        } else {
+          nw::set_last_error(msg[q]);
+        }
+      }
+      const double t1 = paf_now();
+      compress_gpu(ctx, run);  // one all-pairs launch for the whole pass
+      const double t2 = paf_now();
+      paf_parallel_for((int64_t)prepared.size(), [&](int64_t q) {
+        const int64_t k = prepared[q];
+        R[k].tab.reset(new nw_paf_table);
+        R[k].tab->t = prepare_post(jobs[k], R[k].tab->stats);
+        jobs[k] = PrepJob();
+      });
+      const double t3 = paf_now();
+      for (int64_t k : prepared) {
+        Region& r = R[k];
         const size_t n = r.tab->t.n();
         r.info.n_alns = (int32_t)n;
         if ((int64_t)n > (int64_t)params->max_n_alns) {  // :171-176
@@ -575,6 +831,8 @@ int nw_bitlocus_build(nw_ctx* ctx, const nw_paf_cols* pafs, int64_t n_regions, c
         }
         togrid.push_back(k);
       }
+      const double t4 = paf_now();
+      double t5 = t4;
       if (!togrid.empty()) {
         std::vector<nw_paf> gp(togrid.size());
         for (size_t q = 0; q < togrid.size(); ++q) {
@@ -585,6 +843,7 @@ int nw_bitlocus_build(nw_ctx* ctx, const nw_paf_cols* pafs, int64_t n_regions, c
         std::vector<int32_t> grc(togrid.size(), NW_OK);
         const int brc = nw_grid_build(ctx, gp.data(), (int64_t)gp.size(), pass_grids.data(), grc.data());
         if (brc != NW_OK) pfail(brc, std::string("nw_grid_build: ") + nw_last_error());
+        t5 = paf_now();
         for (size_t q = 0; q < togrid.size(); ++q) {
           const int64_t k = togrid[q];
           Region& r = R[k];
@@ -621,6 +880,10 @@ int nw_bitlocus_build(nw_ctx* ctx, const nw_paf_cols* pafs, int64_t n_regions, c
         }
         pass_grids.clear();
       }
+      if (dbg)
+        fprintf(stderr, "[nw_bitlocus_build] pass of %zu regions: paf pre %.2f ms, gpu %.2f ms, post %.2f ms, checks %.2f ms, "
+                        "grid %.2f ms, matrices + pairs %.2f ms\n", pending.size(), 1e3 * (t1 - t0), 1e3 * (t2 - t1),
+                1e3 * (t3 - t2), 1e3 * (t4 - t3), 1e3 * (t5 - t4), 1e3 * (paf_now() - t5));
       pending.swap(next);
     }
     for (int64_t k = 0; k < n_regions; ++k) {

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 
-SYMBOLS = ["nw_paf_compress", "nw_paf_prepare", "nw_paf_rows", "nw_paf_columns", "nw_paf_stats", "nw_paf_free"]
+SYMBOLS = ["nw_paf_compress", "nw_paf_prepare", "nw_paf_prepare_many", "nw_paf_rows", "nw_paf_columns", "nw_paf_stats", "nw_paf_free"]
 COLS = ("qlen", "qstart", "qend", "strand", "tlen", "tstart", "tend", "nmatch", "alen", "mapq")
 
 
@@ -29,6 +29,7 @@ def _lib_paf():
         vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
         L.nw_paf_compress.argtypes = [vp, C.POINTER(NwPafCols), i32, f64, f64, i32, C.POINTER(vp)]
         L.nw_paf_prepare.argtypes = [vp, C.POINTER(NwPafCols), f64, f64, f64, C.POINTER(vp)]
+        L.nw_paf_prepare_many.argtypes = [vp, vp, i64, f64, f64, f64, vp, vp]
         L.nw_paf_rows.restype = i64
         L.nw_paf_rows.argtypes = [vp]
         L.nw_paf_columns.argtypes = [vp] * 11
@@ -79,3 +80,24 @@ def load_and_prep_paf(solver, paf, minlen, compression, chunklen=10000.0):
     h = C.c_void_p()
     _lib.check(L.nw_paf_prepare(solver.h, C.byref(c), float(minlen), float(compression), float(chunklen), C.byref(h)))
     return _table(L, h)
+
+
+def load_and_prep_pafs(solver, pafs, minlen, compression, chunklen=10000.0, timing=None):
+    """load_and_prep_paf for a batch of tables (one kernel launch for the all-pairs tests of all of them).
+    Returns (tables, rcs); tables[k] is None for a malformed table."""
+    import time
+    L = _lib_paf()
+    n = len(pafs)
+    keep = []
+    arr = (NwPafCols * max(n, 1))()
+    for k, p in enumerate(pafs):
+        c, a = _cols(p)
+        keep.append(a)
+        arr[k] = c
+    outs = (C.c_void_p * max(n, 1))()
+    rcs = np.zeros(max(n, 1), np.int32)
+    t0 = time.perf_counter()
+    _lib.check(L.nw_paf_prepare_many(solver.h, arr, n, float(minlen), float(compression), float(chunklen), outs, _p(rcs)))
+    if timing is not None:
+        timing["native_s"] = time.perf_counter() - t0
+    return [_table(L, C.c_void_p(outs[k])) if outs[k] else None for k in range(n)], rcs[:n].tolist()

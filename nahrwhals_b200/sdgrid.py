@@ -111,3 +111,22 @@ def matrix_to_alignments(mat, len_x, len_y):
     qs = np.where(pos, oy[ys], oy[ys + 1])
     qe = np.where(pos, oy[ys + 1], oy[ys])
     return ts, te, qs, qe
+
+
+def matrix_to_chunked_paf(mat, len_x, len_y, chunk=10000):
+    """The PAF table chunked minimap2 would report for a signed gridmatrix (input of the PAF preparation): every
+    non-zero cell is one slope +-1 alignment cut into chunk-long pieces, columns as minimap2 writes them
+    (qstart < qend, strand +1 / -1).  Returns the dict of columns nahrwhals_b200.paf expects."""
+    ts, te, qs, qe = matrix_to_alignments(mat, len_x, len_y)
+    span = float(max(np.sum(len_x), np.sum(len_y)))
+    rows = []
+    for a in range(len(ts)):
+        length = te[a] - ts[a]
+        neg = qs[a] > qe[a]
+        for k in np.arange(0, length, chunk):
+            ln = min(chunk, length - k)
+            q0, q1 = (qs[a] - k - ln, qs[a] - k) if neg else (qs[a] + k, qs[a] + k + ln)
+            rows.append((chunk, q0, q1, -1.0 if neg else 1.0, span, ts[a] + k, ts[a] + k + ln, ln - 3, ln, 60))
+    arr = np.array(rows, dtype=np.float64).reshape(-1, 10)
+    cols = ("qlen", "qstart", "qend", "strand", "tlen", "tstart", "tend", "nmatch", "alen", "mapq")
+    return {k: arr[:, i].copy() for i, k in enumerate(cols)}

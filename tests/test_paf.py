@@ -102,3 +102,49 @@ def test_gpu_paf_edge_cases_and_chain(solver):
     assert G.mat.shape[0] >= 2 and G.mat.shape[1] >= 2
     R = nb.analyse_region(solver, G.mat, G.len_y, G.len_x, G.gridlines_x, depth=2)
     assert R.res_ref is not None and R.res_max >= R.res_ref
+
+
+@pytest.mark.gpu
+def test_gpu_paf_batch_matches_oracle(solver):
+    """nw_paf_prepare_many: tables of very different sizes (incl. empty, single-row and a malformed one) in one launch."""
+    import nahrwhals_b200 as nb
+    rng = np.random.default_rng(77)
+    tabs = [chunked_paf(rng, n_segments=int(rng.integers(1, 40)), chunk=int(rng.choice([5000, 10000])),
+                        jitter=int(rng.choice([0, 2, 30])), span=int(rng.choice([40000, 300000, 2000000])),
+                        drop=float(rng.choice([0.0, 0.1])), extra=int(rng.integers(0, 12))) for _ in range(40)]
+    tabs.insert(3, {k: np.zeros(0) for k in po.COLS})
+    tabs.insert(9, {k: v[:1] for k, v in tabs[0].items()})
+    bad = {k: v.copy() for k, v in tabs[1].items()}
+    bad["strand"][0] = 0.0
+    tabs.insert(5, bad)
+    for minlen, compression in ((500.0, 1000.0), (3000.0, 5000.0)):
+        got, rcs = nb.load_and_prep_pafs(solver, tabs, minlen, compression, 10000.0)
+        for k, (t, rc) in enumerate(zip(got, rcs)):
+            if k == 5:
+                assert t is None and rc == -1
+                continue
+            assert rc == 0
+            _same(t, po.load_and_prep_paf(tabs[k], minlen, compression, 10000.0))
+        assert max(t["_gpu_launches"] for t in got if t is not None) == 1
+
+
+@pytest.mark.gpu
+def test_gpu_paf_pair_segment_overflow(solver):
+    """Far more pairs than alignments (40 near-identical short alignments: every ordered pair qualifies): the table's
+    output segment overflows and the launch is repeated with the exact size."""
+    import nahrwhals_b200 as nb
+    n = 40
+    rng = np.random.default_rng(4)
+    j = rng.integers(0, 5, size=(n, 4)).astype(np.float64)
+    p = dict(qlen=np.full(n, 1000.0), qstart=1000.0 + j[:, 0], qend=1010.0 + j[:, 1], strand=np.ones(n),
+             tlen=np.full(n, 1e6), tstart=2000.0 + j[:, 2], tend=2010.0 + j[:, 3], nmatch=np.full(n, 150.0),
+             alen=np.full(n, 10.0), mapq=np.full(n, 60.0))
+    O = po.compress_paf_fnct(p, second_run=False, chunklen=1000.0, compression=1000.0)
+    P = nb.compress_paf(solver, p, second_run=False, chunklen=1000.0, compression=1000.0)
+    assert P["_pairs_found"] > 2 * n + 64 and P["_gpu_launches"] == 2
+    _same(P, O)
+    other = chunked_paf(np.random.default_rng(2), n_segments=5)
+    got, rcs = nb.load_and_prep_pafs(solver, [other, p, other], 5.0, 10.0, 1000.0)
+    assert rcs == [0, 0, 0]
+    for t, src in zip(got, (other, p, other)):
+        _same(t, po.load_and_prep_paf(src, 5.0, 10.0, 1000.0))
