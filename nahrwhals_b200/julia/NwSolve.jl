@@ -136,4 +136,47 @@ function build_grid(ctx::Context, tstart::Vector{Float64}, tend::Vector{Float64}
     (gridlines_x = gx, gridlines_y = gy, mat = collect(transpose(m)), len_x = lx, len_y = ly, converged = cv[] != 0)
 end
 
+# ---- wrapper_paf_to_bitlocus (include/nwbitlocus.h): parsed PAF table -> accepted grid, with the reference's retry loop
+struct NwPafCols                   # struct nw_paf_cols
+    qlen::Ptr{Float64}; qstart::Ptr{Float64}; qend::Ptr{Float64}; strand::Ptr{Float64}; tlen::Ptr{Float64}
+    tstart::Ptr{Float64}; tend::Ptr{Float64}; nmatch::Ptr{Float64}; alen::Ptr{Float64}; mapq::Ptr{Float64}
+    n::Int64
+end
+struct NwBitlocusParams            # struct nw_bitlocus_params
+    minlen::Float64; compression::Float64; chunklen::Float64
+    max_n_alns::Int32; max_size_col_plus_rows::Int32; max_pairs::Int32; max_passes::Int32
+end
+struct NwBitlocusInfo              # struct nw_bitlocus_info
+    minlen::Float64; compression::Float64
+    passes::Int32; cluttered::Int32; n_alns::Int32; n_pairs::Int32
+end
+
+"paf: NamedTuple / Dict of Float64 vectors qlen, qstart, qend, strand (+1 / -1), tlen, tstart, tend, nmatch, alen, mapq.
+Returns nothing for a cluttered PAF (as the reference does), else (gridlines_x, gridlines_y, mat, len_x, len_y, minlen,
+compression, passes)."
+function paf_to_bitlocus(ctx::Context, paf; minlen::Float64, compression::Float64, chunklen::Float64 = 10000.0,
+                         max_n_alns::Integer = 150, max_size_col_plus_rows::Integer = 250)
+    cols = [Vector{Float64}(paf[k]) for k in (:qlen, :qstart, :qend, :strand, :tlen, :tstart, :tend, :nmatch, :alen, :mapq)]
+    g = Ref{Ptr{Cvoid}}(C_NULL); rc = Ref{Int32}(0)
+    info = Ref(NwBitlocusInfo(0.0, 0.0, 0, 0, 0, -1))
+    GC.@preserve cols begin
+        c = Ref(NwPafCols(map(pointer, cols)..., length(cols[1])))
+        prm = Ref(NwBitlocusParams(minlen, compression, chunklen, max_n_alns, max_size_col_plus_rows, 2000, 64))
+        check(ccall((:nw_bitlocus_build, LIB), Cint,
+                    (Ptr{Cvoid}, Ref{NwPafCols}, Int64, Ref{NwBitlocusParams}, Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Ref{NwBitlocusInfo}, Ref{Int32}),
+                    ctx.h, c, 1, prm, g, C_NULL, info, rc))
+    end
+    rc[] == 0 || error("wrapper_paf_to_bitlocus failed with status $(rc[])")
+    info[].cluttered != 0 && return nothing
+    nx = Ref{Int32}(0); ny = Ref{Int32}(0); cv = Ref{Int32}(0); gen = Ref{Int32}(0)
+    check(ccall((:nw_grid_dims, LIB), Cint, (Ptr{Cvoid}, Ref{Int32}, Ref{Int32}, Ref{Int32}, Ref{Int32}), g[], nx, ny, cv, gen))
+    gx = Vector{Float64}(undef, nx[] + 1); gy = Vector{Float64}(undef, ny[] + 1)
+    check(ccall((:nw_grid_lines, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), g[], gx, gy))
+    m = Matrix{Float64}(undef, nx[], ny[]); lx = Vector{Float64}(undef, nx[]); ly = Vector{Float64}(undef, ny[])
+    check(ccall((:nw_grid_matrix, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), g[], m, lx, ly))
+    ccall((:nw_grid_free, LIB), Cvoid, (Ptr{Cvoid},), g[])
+    (gridlines_x = gx, gridlines_y = gy, mat = collect(transpose(m)), len_x = lx, len_y = ly,
+     minlen = info[].minlen, compression = info[].compression, passes = Int(info[].passes))
+end
+
 end # module

@@ -84,6 +84,39 @@ def test_oracle_loop_branches():
     assert bo.wrapper_paf_to_bitlocus(p, 1000.0, 1000.0, max_n_alns=0, max_passes=3)["status"] in ("passes", "empty")
 
 
+def _testrun():
+    import os
+    import nahrwhals_b200 as nb
+    from nahrwhals_b200.sdgrid import matrix_to_chunked_paf
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    _, lx, ly = nb.read_problem(os.path.join(g, "testrun_grid_mut.tsv"), os.path.join(g, "testrun_grid_mut_lens.tsv"))
+    mat = np.loadtxt(os.path.join(g, "testrun_grid_mut.tsv"), dtype=np.float64, ndmin=2)
+    ap = nb.auto_params(1700000, 3300000)        # the bundled test run: chr1_partial:1700000-3300000
+    return mat, lx, ly, ap, matrix_to_chunked_paf(mat, lx, ly, int(ap["chunklen"]))
+
+
+def test_oracle_testrun_chunks_give_back_the_testrun_gridmatrix():
+    """The test run's alignments, chunked as the pipeline chunks them, through the restated wrapper_paf_to_bitlocus with
+    the reference's default parameters: 153 chunks -> 6 alignments -> the 11 x 19 gridmatrix of the reference's figure."""
+    mat, lx, ly, ap, chunks = _testrun()
+    assert ap == dict(chunklen=10000.0, minlen=10000.0, compression=10000.0)
+    O = bo.wrapper_paf_to_bitlocus(chunks, ap["minlen"], ap["compression"], ap["chunklen"])
+    assert (O["status"], O["passes"], O["n_alns"]) == ("ok", 1, 6)
+    assert np.array_equal(O["grid"]["mat"], mat) and np.array_equal(O["grid"]["len_x"], lx)
+    assert np.array_equal(O["grid"]["len_y"], ly)
+
+
+@pytest.mark.gpu
+def test_gpu_testrun_chunks_give_back_the_testrun_gridmatrix(solver):
+    import nahrwhals_b200 as nb
+    mat, lx, ly, ap, chunks = _testrun()
+    B = nb.paf_to_bitlocus(solver, [chunks], ap["minlen"], ap["compression"], ap["chunklen"])[0]
+    assert (B.status, B.passes, B.n_alns) == ("ok", 1, 6)
+    assert np.array_equal(B.grid.mat, mat) and np.array_equal(B.grid.len_x, lx) and np.array_equal(B.grid.len_y, ly)
+    R = nb.analyse_region(solver, B.grid.mat, B.grid.len_y, B.grid.len_x, B.grid.gridlines_x, depth=2)
+    assert (R.res_ref, R.res_max, R.mut_max) == (71.378, 99.595, "4_12_inv+11_18_del")   # README.md:135-139
+
+
 def _check(B, O):
     want = {"ok": "ok", "cluttered": "cluttered", "empty": "failed", "passes": "failed"}[O["status"]]
     assert B.status == want, (B.status, O["status"])
