@@ -54,6 +54,19 @@ int nw_paf_prepare(nw_ctx* ctx, const nw_paf_cols* in, double minlen, double com
 int nw_paf_prepare_many(nw_ctx* ctx, const nw_paf_cols* ins, int64_t n_tables, double minlen, double compression,
                         double chunklen, nw_paf_table** outs, int32_t* rcs);
 
+/* Replaces compress_paf_fnct(inpaf_link = inpaf, outpaf_link = outpaf, inparam_chunklen = chunklen)
+ * (R/compress_paf.R:173-406 with save_outpaf = T: the "melt" step after the chunked minimap2 run,
+ * R/seqbuilder_functions.R:107): read.table + unique(), strand swap, merge (first run: tolerance 0.05 * chunklen),
+ * merged rows get the rebuilt qname of merge_rows (:49-59), write.table (numbers as R prints them; a table in which
+ * rows were merged has the 12 PAF columns only, nmatch / alen as doubles).  The output file is written to a temporary
+ * name and renamed.  n_quadrants <= 0: the reference's choice. */
+int nw_paf_compress_file(nw_ctx* ctx, const char* inpaf_path, const char* outpaf_path, double chunklen, int32_t n_quadrants,
+                         int64_t* rows_in, int64_t* rows_out);
+
+/* read.table(inpaf) of load_and_prep_paf_for_gridplot_transform (R/tsv_to_bitlocus.R:17-31): the numeric columns of a
+ * PAF file (12 columns + optional tags) as a table; strand '+' / '-' becomes +1 / -1.  Host only. */
+int nw_paf_read_file(const char* path, nw_paf_table** out);
+
 int64_t nw_paf_rows(const nw_paf_table* t);
 /* any pointer may be NULL; arrays of nw_paf_rows() doubles */
 int nw_paf_columns(const nw_paf_table* t, double* qlen, double* qstart, double* qend, double* strand, double* tlen,

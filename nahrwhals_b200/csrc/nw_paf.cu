@@ -14,6 +14,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
+#include <sstream>
+#include <unordered_set>
 #include <mutex>
 #include <thread>
 #include <cmath>
@@ -142,14 +145,14 @@ __global__ void __launch_bounds__(256) k_paf_pairs(const PafTab* __restrict__ ta
 }
 
 struct Table {
-  std::vector<double> c[10];  // qlen qstart qend strand tlen tstart tend nmatch alen mapq
+  std::vector<double> c[11];  // qlen qstart qend strand tlen tstart tend nmatch alen mapq + the row of the input table
   size_t n() const { return c[0].size(); }
 };
-enum { QLEN = 0, QSTART, QEND, STRAND, TLEN, TSTART, TEND, NMATCH, ALEN, MAPQ };
+enum { QLEN = 0, QSTART, QEND, STRAND, TLEN, TSTART, TEND, NMATCH, ALEN, MAPQ, ROWID, NCOL };
 
 Table take(const Table& t, const std::vector<size_t>& idx) {
   Table o;
-  for (int k = 0; k < 10; ++k) {
+  for (int k = 0; k < NCOL; ++k) {
     o.c[k].resize(idx.size());
     for (size_t q = 0; q < idx.size(); ++q) o.c[k][q] = t.c[k][idx[q]];
   }
@@ -167,6 +170,8 @@ Table from_cols(const nw_paf_cols* in) {
   }
   for (double v : t.c[STRAND])
     if (v != 1.0 && v != -1.0) pfail(NW_ERR_ARG, "strand must be +1 or -1");
+  t.c[ROWID].resize((size_t)in->n);
+  for (size_t k = 0; k < t.c[ROWID].size(); ++k) t.c[ROWID][k] = (double)k;
   return t;
 }
 void swap_minus(Table& t) {  // transform(paf, qend = ifelse(strand == '-', qstart, qend), qstart = ifelse(..., qend, qstart))
@@ -180,8 +185,58 @@ std::vector<size_t> stable_order(const std::vector<double>& key) {
   return o;
 }
 
+// as.character() / paste0() / write.table() of an R double: the fewest significant digits (at most 15) that reproduce
+// the value at 15 digits, fixed notation unless scientific is narrower (R: formatReal + scientific(), scipen = 0)
+std::string r_format_double(double v) {
+  if (v == 0) return "0";
+  if (!std::isfinite(v)) return std::isnan(v) ? "NA" : (v > 0 ? "Inf" : "-Inf");
+  char ref[64], buf[64];
+  snprintf(ref, sizeof ref, "%.14e", v);
+  const double target = strtod(ref, nullptr);
+  int nsig = 15;
+  for (int d = 1; d <= 15; ++d) {
+    snprintf(buf, sizeof buf, "%.*e", d - 1, v);
+    if (strtod(buf, nullptr) == target) {
+      nsig = d;
+      break;
+    }
+  }
+  snprintf(buf, sizeof buf, "%.*e", nsig - 1, v);
+  const char* e = strchr(buf, 'e');
+  const int kp = atoi(e + 1);
+  const int neg = v < 0 ? 1 : 0;
+  const int rgt = std::max(0, nsig - kp - 1);
+  const int left = kp >= 0 ? kp + 1 : 1;
+  const int wF = neg + left + (rgt > 0 ? rgt + 1 : 0);
+  const int wE = neg + (nsig > 1 ? nsig + 1 : 1) + (std::abs(kp) >= 100 ? 5 : 4);
+  if (wF <= wE) {
+    snprintf(buf, sizeof buf, "%.*f", rgt, v);
+    return buf;
+  }
+  std::string mant(buf, e - buf);
+  char ex[16];
+  snprintf(ex, sizeof ex, "e%c%02d", kp < 0 ? '-' : '+', std::abs(kp));
+  return mant + ex;
+}
+// a value of a column read.table typed integer prints as an integer, of a double column like a double
+std::string r_format(double v, bool integer_typed) {
+  if (integer_typed) {
+    char buf[32];
+    snprintf(buf, sizeof buf, "%lld", (long long)v);
+    return buf;
+  }
+  return r_format_double(v);
+}
+
+// the names merge_rows rewrites (R/compress_paf.R:49-59, :86-97): aligned with the rows of the table
+struct MergeNames {
+  std::vector<std::string> qname;
+  bool reduced = false;     // reduced_qnames
+  bool q_integer = true;    // the qstart / qend columns are integer typed (formatting of the rebuilt name)
+};
+
 // merge_rows (R/compress_paf.R:13-138); pairs are (row, col), 0-based here
-Table merge_rows(const Table& p, const std::vector<std::pair<int, int>>& pairs) {
+Table merge_rows(const Table& p, const std::vector<std::pair<int, int>>& pairs, MergeNames* names = nullptr) {
   Table o = p;
   std::vector<double>&qs = o.c[QSTART], &qe = o.c[QEND], &ts = o.c[TSTART], &te = o.c[TEND], &nm = o.c[NMATCH], &al = o.c[ALEN];
   const std::vector<double>& st = o.c[STRAND];
@@ -190,6 +245,12 @@ Table merge_rows(const Table& p, const std::vector<std::pair<int, int>>& pairs) 
     const int bu = nl1;
     if (st[nl1] > 0) {
       const double q1 = qs[nl1], q2 = qs[nl2], e1 = qe[nl1], e2 = qe[nl2], t1 = ts[nl1], t2 = ts[nl2], f1 = te[nl1], f2 = te[nl2];
+      if (names && !names->reduced) {  // paste0(sub("_[^_]*$", "", qname1), "_", qstart1, "-", qend2 - 1)
+        std::string base = names->qname[nl1];
+        const size_t us = base.rfind('_');
+        if (us != std::string::npos) base.erase(us);
+        names->qname[bu] = base + "_" + r_format(q1, names->q_integer) + "-" + r_format_double(e2 - 1);
+      }
       qe[bu] = std::max(e1, e2);
       qs[bu] = std::min(q1, q2);
       te[bu] = std::max(f1, f2);
@@ -200,6 +261,10 @@ Table merge_rows(const Table& p, const std::vector<std::pair<int, int>>& pairs) 
         nl2 = bu;
       }
       const double q1 = qs[nl1], q2 = qs[nl2], e1 = qe[nl1], e2 = qe[nl2], t1 = ts[nl1], t2 = ts[nl2], f1 = te[nl1], f2 = te[nl2];
+      if (names) {  // :97 overrides the rebuilt name: qnames[nl1_bu] <- qname1
+        const std::string q = names->qname[nl1];
+        names->qname[bu] = q;
+      }
       qe[bu] = std::min(e1, e2);
       qs[bu] = std::max(q1, q2);
       te[bu] = std::max(f1, f2);
@@ -216,6 +281,11 @@ Table merge_rows(const Table& p, const std::vector<std::pair<int, int>>& pairs) 
     if (is_col[k]) continue;
     const double ratio = std::fabs(te[k] - ts[k]) / std::fabs(qe[k] - qs[k]);
     if (ratio >= 0.5 && ratio <= 2) keep.push_back(k);  // dplyr::between; NaN fails both comparisons
+  }
+  if (names) {
+    std::vector<std::string> kept;
+    for (size_t k : keep) kept.push_back(names->qname[k]);
+    names->qname.swap(kept);
   }
   return take(o, keep);
 }
@@ -239,6 +309,11 @@ struct CompressJob {
   bool need_gpu = false;
   std::vector<PairRec> recs;
   CompressStats stats;
+  // file mode: the qname strings of the input rows (indexed by ROWID); out: names of the result rows, merged = merge_rows ran
+  const std::vector<std::string>* in_qname = nullptr;
+  bool q_integer = true;
+  std::vector<std::string> out_qname;
+  bool merged = false;
 };
 
 void compress_pre(CompressJob& J, const Table& in) {
@@ -406,7 +481,7 @@ Table compress_post(CompressJob& J) {
   Table& p = J.p;
   const double chunklen = J.chunklen;
   auto append_short = [&](Table& t) {
-    for (int k = 0; k < 10; ++k) t.c[k].insert(t.c[k].end(), J.shortt.c[k].begin(), J.shortt.c[k].end());
+    for (int k = 0; k < NCOL; ++k) t.c[k].insert(t.c[k].end(), J.shortt.c[k].begin(), J.shortt.c[k].end());
   };
   std::vector<PairRec>& recs = J.recs;
   J.stats.pairs_found = (int64_t)recs.size();
@@ -445,7 +520,17 @@ Table compress_post(CompressJob& J) {
   if (!rp.empty()) {
     std::vector<std::pair<int, int>> pairs;
     for (const RP& r : rp) pairs.emplace_back(r.row, r.col);
-    p = merge_rows(p, pairs);
+    if (J.in_qname) {
+      MergeNames nm;
+      nm.q_integer = J.q_integer;
+      for (size_t k = 0; k < p.n(); ++k) nm.qname.push_back((*J.in_qname)[(size_t)p.c[ROWID][k]]);
+      p = merge_rows(p, pairs, &nm);
+      J.out_qname.swap(nm.qname);
+      for (size_t k = 0; k < J.shortt.n(); ++k) J.out_qname.push_back((*J.in_qname)[(size_t)J.shortt.c[ROWID][k]]);
+    } else {
+      p = merge_rows(p, pairs);
+    }
+    J.merged = true;
   }
   append_short(p);
   return std::move(p);
@@ -637,6 +722,135 @@ int nw_paf_stats(const nw_paf_table* t, int64_t* pairs_found, int32_t* gpu_launc
   return NW_OK;
 }
 void nw_paf_free(nw_paf_table* t) { delete t; }
+
+}  // extern "C"
+
+// =====================================================================================================
+// PAF files: read.table(inpaf) and compress_paf_fnct(inpaf_link, outpaf_link) (save_outpaf = T)
+// =====================================================================================================
+namespace {
+
+struct PafFile {
+  Table t;                                  // numeric columns (+ ROWID = row of this struct's string vectors)
+  std::vector<std::string> qname, tname, extra;  // extra: columns 13.. joined by tabs (carried through, never parsed)
+  bool integer_typed[10];                   // read.table types a column integer if every value is an integer
+};
+
+// read.table(path, sep = "\t") of a PAF: 12 columns (qname qlen qstart qend strand tname tlen tstart tend nmatch alen
+// mapq) + optional tags; dedupe = unique(inpaf) (first occurrences, compared as text)
+PafFile read_paf_file(const char* path, bool dedupe) {
+  if (!path) pfail(NW_ERR_ARG, "null path");
+  std::ifstream f(path);
+  if (!f) pfail(NW_ERR_IO, std::string("cannot open ") + path);
+  PafFile P;
+  for (bool& b : P.integer_typed) b = true;
+  std::unordered_set<std::string> seen;
+  std::string line;
+  size_t lineno = 0;
+  static const int numcol[12] = {-1, QLEN, QSTART, QEND, -2, -3, TLEN, TSTART, TEND, NMATCH, ALEN, MAPQ};
+  while (std::getline(f, line)) {
+    ++lineno;
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.empty()) continue;  // blank.lines.skip = TRUE
+    if (dedupe && !seen.insert(line).second) continue;
+    std::vector<std::string> fld;
+    size_t a = 0;
+    for (int k = 0; k < 12; ++k) {
+      const size_t b = line.find('\t', a);
+      if (b == std::string::npos && k < 11) pfail(NW_ERR_PARSE, std::string(path) + ": line " + std::to_string(lineno) + " has fewer than 12 columns");
+      fld.push_back(line.substr(a, b == std::string::npos ? std::string::npos : b - a));
+      a = b == std::string::npos ? line.size() : b + 1;
+    }
+    const size_t row = P.qname.size();
+    P.qname.push_back(fld[0]);
+    P.tname.push_back(fld[5]);
+    P.extra.push_back(a < line.size() ? line.substr(a) : std::string());
+    for (int k = 0; k < 12; ++k) {
+      if (numcol[k] == -1 || numcol[k] == -3) continue;
+      if (numcol[k] == -2) {
+        if (fld[k] != "+" && fld[k] != "-") pfail(NW_ERR_PARSE, std::string(path) + ": line " + std::to_string(lineno) + ": strand must be + or -");
+        P.t.c[STRAND].push_back(fld[k] == "+" ? 1.0 : -1.0);
+        continue;
+      }
+      char* end = nullptr;
+      const double v = strtod(fld[k].c_str(), &end);
+      if (end == fld[k].c_str() || *end != 0 || !std::isfinite(v))
+        pfail(NW_ERR_PARSE, std::string(path) + ": line " + std::to_string(lineno) + ": column " + std::to_string(k + 1) + " is not a number");
+      P.t.c[numcol[k]].push_back(v);
+      if (v != std::floor(v) || std::fabs(v) > 2147483647.0 || fld[k].find_first_of(".eE") != std::string::npos)
+        P.integer_typed[numcol[k]] = false;
+    }
+    P.t.c[ROWID].push_back((double)row);
+  }
+  return P;
+}
+
+// write.table(inpaf, quote = F, col.names = F, row.names = F, sep = "\t") after the final strand swap
+void write_paf_file(const char* path, const Table& t, const std::vector<std::string>& qname, const PafFile& src, bool merged) {
+  const std::string tmp = std::string(path) + ".tmp";
+  {
+    std::ofstream o(tmp);
+    if (!o) pfail(NW_ERR_IO, std::string("cannot write ") + tmp);
+    bool it[10];
+    for (int k = 0; k < 10; ++k) it[k] = src.integer_typed[k];
+    if (merged) it[NMATCH] = it[ALEN] = false;  // merge_rows: as.numeric(paffile$nmatch), as.numeric(paffile$alen)
+    for (size_t k = 0; k < t.n(); ++k) {
+      const size_t row = (size_t)t.c[ROWID][k];
+      const bool neg = t.c[STRAND][k] < 0;
+      const double qs = neg ? t.c[QEND][k] : t.c[QSTART][k], qe = neg ? t.c[QSTART][k] : t.c[QEND][k];
+      o << qname[k] << '\t' << r_format(t.c[QLEN][k], it[QLEN]) << '\t' << r_format(qs, it[QSTART] && it[QEND]) << '\t'
+        << r_format(qe, it[QSTART] && it[QEND]) << '\t' << (neg ? '-' : '+') << '\t' << src.tname[row] << '\t'
+        << r_format(t.c[TLEN][k], it[TLEN]) << '\t' << r_format(t.c[TSTART][k], it[TSTART]) << '\t'
+        << r_format(t.c[TEND][k], it[TEND]) << '\t' << r_format(t.c[NMATCH][k], it[NMATCH]) << '\t'
+        << r_format(t.c[ALEN][k], it[ALEN]) << '\t' << r_format(t.c[MAPQ][k], it[MAPQ]);
+      if (!merged && !src.extra[row].empty()) o << '\t' << src.extra[row];  // merge_rows rebuilds the 12 columns only
+      o << '\n';
+    }
+    o.flush();
+    if (!o) pfail(NW_ERR_IO, std::string("cannot write ") + tmp);
+  }
+  if (rename(tmp.c_str(), path) != 0) pfail(NW_ERR_IO, std::string("cannot rename to ") + path);
+}
+
+}  // namespace
+
+extern "C" {
+
+int nw_paf_read_file(const char* path, nw_paf_table** out) {
+  if (out) *out = nullptr;
+  return pguard([&] {
+    if (!out) pfail(NW_ERR_ARG, "null argument");
+    PafFile P = read_paf_file(path, false);
+    std::unique_ptr<nw_paf_table> T(new nw_paf_table);
+    T->t = std::move(P.t);
+    *out = T.release();
+  });
+}
+
+int nw_paf_compress_file(nw_ctx* ctx, const char* inpaf_path, const char* outpaf_path, double chunklen, int32_t n_quadrants,
+                         int64_t* rows_in, int64_t* rows_out) {
+  return pguard([&] {
+    if (!ctx || !outpaf_path) pfail(NW_ERR_ARG, "null argument");
+    PafFile P = read_paf_file(inpaf_path, true);  // read.table + unique()
+    if (rows_in) *rows_in = (int64_t)P.t.n();
+    swap_minus(P.t);  // :196-200
+    CompressJob J;
+    J.second_run = false;
+    J.chunklen = chunklen;
+    J.n_quadrants = n_quadrants;
+    J.in_qname = &P.qname;
+    J.q_integer = P.integer_typed[QSTART] && P.integer_typed[QEND];
+    compress_pre(J, P.t);
+    compress_gpu(ctx, {&J});
+    Table out = compress_post(J);
+    if (!J.merged) {
+      J.out_qname.clear();
+      for (size_t k = 0; k < out.n(); ++k) J.out_qname.push_back(P.qname[(size_t)out.c[ROWID][k]]);
+    }
+    write_paf_file(outpaf_path, out, J.out_qname, P, J.merged);
+    if (rows_out) *rows_out = (int64_t)out.n();
+  });
+}
 
 }  // extern "C"
 

@@ -11,7 +11,8 @@ import numpy as np
 
 from . import _lib
 
-SYMBOLS = ["nw_paf_compress", "nw_paf_prepare", "nw_paf_prepare_many", "nw_paf_rows", "nw_paf_columns", "nw_paf_stats", "nw_paf_free"]
+SYMBOLS = ["nw_paf_compress", "nw_paf_prepare", "nw_paf_prepare_many", "nw_paf_compress_file", "nw_paf_read_file",
+           "nw_paf_rows", "nw_paf_columns", "nw_paf_stats", "nw_paf_free"]
 COLS = ("qlen", "qstart", "qend", "strand", "tlen", "tstart", "tend", "nmatch", "alen", "mapq")
 
 
@@ -30,6 +31,8 @@ def _lib_paf():
         L.nw_paf_compress.argtypes = [vp, C.POINTER(NwPafCols), i32, f64, f64, i32, C.POINTER(vp)]
         L.nw_paf_prepare.argtypes = [vp, C.POINTER(NwPafCols), f64, f64, f64, C.POINTER(vp)]
         L.nw_paf_prepare_many.argtypes = [vp, vp, i64, f64, f64, f64, vp, vp]
+        L.nw_paf_compress_file.argtypes = [vp, C.c_char_p, C.c_char_p, f64, i32, C.POINTER(i64), C.POINTER(i64)]
+        L.nw_paf_read_file.argtypes = [C.c_char_p, C.POINTER(vp)]
         L.nw_paf_rows.restype = i64
         L.nw_paf_rows.argtypes = [vp]
         L.nw_paf_columns.argtypes = [vp] * 11
@@ -101,3 +104,22 @@ def load_and_prep_pafs(solver, pafs, minlen, compression, chunklen=10000.0, timi
     if timing is not None:
         timing["native_s"] = time.perf_counter() - t0
     return [_table(L, C.c_void_p(outs[k])) if outs[k] else None for k in range(n)], rcs[:n].tolist()
+
+
+def compress_paf_file(solver, inpaf_link, outpaf_link, chunklen=10000.0, n_quadrants_per_axis=None):
+    """compress_paf_fnct(inpaf_link, outpaf_link, inparam_chunklen = chunklen) (R/seqbuilder_functions.R:107): PAF file in,
+    "molten" PAF file out.  Returns (rows read after unique(), rows written)."""
+    L = _lib_paf()
+    a, b = C.c_int64(), C.c_int64()
+    _lib.check(L.nw_paf_compress_file(solver.h, str(inpaf_link).encode(), str(outpaf_link).encode(), float(chunklen),
+                                      int(n_quadrants_per_axis or 0), C.byref(a), C.byref(b)))
+    return int(a.value), int(b.value)
+
+
+def read_paf(path):
+    """read.table(inpaf) of load_and_prep_paf_for_gridplot_transform: the numeric columns of a PAF file as a table."""
+    L = _lib_paf()
+    h = C.c_void_p()
+    _lib.check(L.nw_paf_read_file(str(path).encode(), C.byref(h)))
+    t = _table(L, h)
+    return {k: t[k] for k in COLS}

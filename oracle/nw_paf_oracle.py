@@ -4,7 +4,9 @@ TEST INFRASTRUCTURE ONLY (imported by tests/ and bench.py's cpu_baseline leg, ne
 
     load_and_prep_paf_for_gridplot_transform   R/tsv_to_bitlocus.R:15-110   (strand swap, compress, minlen filter,
                                                rounding to the compression grid, enforce_slope_one :258-275)
-    compress_paf_fnct                          R/compress_paf.R:173-406    (inpaf_df path, save_outpaf = F)
+    compress_paf_fnct                          R/compress_paf.R:173-406    (inpaf_df path, save_outpaf = F; and the file
+                                               path inpaf_link -> outpaf_link of R/seqbuilder_functions.R:107:
+                                               compress_paf_file, with R's number formatting restated)
     merge_paf_entries_intraloop                R/merge_paf_entries_intraloop.R:14-79
     merge_rows                                 R/compress_paf.R:13-138
 
@@ -48,8 +50,9 @@ def merge_paf_entries_intraloop(p, names, second_run, chunklen, compression):
     return [(int(names[r]), int(names[c])) for r, c in pairs]
 
 
-def merge_rows(p, pairs):
-    """R/compress_paf.R:13-138 (reduced_qnames irrelevant: names are not carried).  pairs: list of (row, col), 1-based."""
+def merge_rows(p, pairs, names=None, reduced_qnames=False, q_integer=True):
+    """R/compress_paf.R:13-138.  pairs: list of (row, col), 1-based.  names (file mode): list of qname strings aligned
+    with the rows, rewritten in place as :49-59 / :86-97 do and filtered like the rows."""
     qs, qe = p["qstart"].astype(np.float64).copy(), p["qend"].astype(np.float64).copy()
     ts, te = p["tstart"].astype(np.float64).copy(), p["tend"].astype(np.float64).copy()
     nm, al = p["nmatch"].astype(np.float64).copy(), p["alen"].astype(np.float64).copy()
@@ -59,6 +62,9 @@ def merge_rows(p, pairs):
         if st[nl1] > 0:
             q1, q2, e1, e2 = qs[nl1], qs[nl2], qe[nl1], qe[nl2]
             t1, t2, f1, f2 = ts[nl1], ts[nl2], te[nl1], te[nl2]
+            if names is not None and not reduced_qnames:
+                import re
+                names[bu] = re.sub(r"_[^_]*$", "", names[nl1]) + "_" + r_format(q1, q_integer) + "-" + r_format_double(e2 - 1)
             qe[bu], qs[bu] = max(e1, e2), min(q1, q2)
             te[bu], ts[bu] = max(f1, f2), min(t1, t2)
         else:
@@ -66,6 +72,8 @@ def merge_rows(p, pairs):
                 nl1, nl2 = nl2, bu
             q1, q2, e1, e2 = qs[nl1], qs[nl2], qe[nl1], qe[nl2]
             t1, t2, f1, f2 = ts[nl1], ts[nl2], te[nl1], te[nl2]
+            if names is not None:
+                names[bu] = names[nl1]                     # :97 overrides the rebuilt name with qname1
             qe[bu], qs[bu] = min(e1, e2), max(q1, q2)
             te[bu], ts[bu] = max(f1, f2), min(t1, t2)
         nm[bu] = nm[nl1] + nm[nl2]
@@ -78,11 +86,15 @@ def merge_rows(p, pairs):
     with np.errstate(divide="ignore", invalid="ignore"):
         ratio = np.abs(out["tend"] - out["tstart"]) / np.abs(out["qend"] - out["qstart"])
     ok = (ratio >= 0.5) & (ratio <= 2)                    # dplyr::between; NaN (0 / 0) rows are treated as dropped
+    if names is not None:
+        kept = [names[i] for i in np.nonzero(keep)[0]]
+        names[:] = [nm for nm, good in zip(kept, ok) if good]
     return take(out, ok)
 
 
-def compress_paf_fnct(p, second_run=False, chunklen=10000.0, compression=None, n_quadrants_per_axis=None):
-    """R/compress_paf.R:173-406 with inpaf_df, save_outpaf = F, qname = NULL."""
+def compress_paf_fnct(p, second_run=False, chunklen=10000.0, compression=None, n_quadrants_per_axis=None, file_mode=None):
+    """R/compress_paf.R:173-406 with inpaf_df, save_outpaf = F, qname = NULL.  file_mode (compress_paf_file): a dict with
+    'qname' (names by the '_row' column of p) and 'q_integer'; receives 'merged' and 'out_qname'."""
     p = {k: np.asarray(v, dtype=np.float64) for k, v in p.items()}
     p = take(p, np.argsort(p["qstart"], kind="stable"))
     n = len(p["qstart"])
@@ -129,7 +141,13 @@ def compress_paf_fnct(p, second_run=False, chunklen=10000.0, compression=None, n
     k2 = [k for k in range(len(rowpairs)) if ml[k] == best[rowpairs[k][1]]]
     rowpairs = [rowpairs[k] for k in k2]
     if rowpairs:
-        p = merge_rows(p, rowpairs)
+        if file_mode is not None:
+            names = [file_mode["qname"][int(r)] for r in p["_row"]]
+            p = merge_rows(p, rowpairs, names=names, q_integer=file_mode["q_integer"])
+            file_mode["merged"] = True
+            file_mode["out_qname"] = names + [file_mode["qname"][int(r)] for r in short["_row"]]
+        else:
+            p = merge_rows(p, rowpairs)
     return {k: np.concatenate([p[k], short[k]]) for k in p}
 
 
@@ -158,3 +176,93 @@ def load_and_prep_paf(p, minlen, compression, chunklen=10000.0):
     p = enforce_slope_one(p)
     p = swap_minus(p)
     return p
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# file mode: compress_paf_fnct(inpaf_link, outpaf_link) with save_outpaf = T (R/compress_paf.R:184-216, :386-401),
+# the call of R/seqbuilder_functions.R:107
+# ---------------------------------------------------------------------------------------------------------------
+def r_format_double(v):
+    """as.character() / write.table() of an R double: fewest significant digits (<= 15) reproducing the value at 15
+    digits; fixed notation unless scientific is narrower (formatReal, scipen = 0)."""
+    v = float(v)
+    if v == 0:
+        return "0"
+    target = float("%.14e" % v)
+    nsig = 15
+    for d in range(1, 16):
+        if float("%.*e" % (d - 1, v)) == target:
+            nsig = d
+            break
+    mant, ex = ("%.*e" % (nsig - 1, v)).split("e")
+    kp = int(ex)
+    neg = 1 if v < 0 else 0
+    rgt = max(0, nsig - kp - 1)
+    left = kp + 1 if kp >= 0 else 1
+    w_fixed = neg + left + (rgt + 1 if rgt > 0 else 0)
+    w_sci = neg + (nsig + 1 if nsig > 1 else 1) + (5 if abs(kp) >= 100 else 4)
+    if w_fixed <= w_sci:
+        return "%.*f" % (rgt, v)
+    return "%se%s%02d" % (mant, "-" if kp < 0 else "+", abs(kp))
+
+
+def r_format(v, integer_typed):
+    return str(int(v)) if integer_typed else r_format_double(v)
+
+
+NUMCOLS = ("qlen", "qstart", "qend", "tlen", "tstart", "tend", "nmatch", "alen", "mapq")
+
+
+def read_paf_file(path, dedupe=False):
+    """read.table(path, sep = '\\t') [+ unique()] -> (table with '_row', qname, tname, extra, integer_typed)."""
+    seen, rows, qname, tname, extra = set(), [], [], [], []
+    ityp = {k: True for k in NUMCOLS}
+    for line in open(path).read().split("\n"):
+        line = line.rstrip("\r")
+        if not line:
+            continue
+        if dedupe:
+            if line in seen:
+                continue
+            seen.add(line)
+        f = line.split("\t")
+        assert len(f) >= 12, "fewer than 12 columns"
+        qname.append(f[0])
+        tname.append(f[5])
+        extra.append("\t".join(f[12:]))
+        num = dict(zip(("qlen", "qstart", "qend"), f[1:4]))
+        num.update(zip(("tlen", "tstart", "tend", "nmatch", "alen", "mapq"), f[6:12]))
+        for k, txt in num.items():
+            v = float(txt)
+            if v != int(v) or abs(v) > 2147483647 or any(c in txt for c in ".eE"):
+                ityp[k] = False
+        rows.append([float(num["qlen"]), float(num["qstart"]), float(num["qend"]), 1.0 if f[4] == "+" else -1.0,
+                     float(num["tlen"]), float(num["tstart"]), float(num["tend"]), float(num["nmatch"]), float(num["alen"]),
+                     float(num["mapq"]), float(len(rows))])
+    a = np.array(rows, dtype=np.float64).reshape(-1, 11)
+    p = {k: a[:, i].copy() for i, k in enumerate(COLS + ("_row",))}
+    return p, qname, tname, extra, ityp
+
+
+def compress_paf_file(in_path, out_path, chunklen, n_quadrants_per_axis=None):
+    p, qname, tname, extra, ityp = read_paf_file(in_path, dedupe=True)
+    p = swap_minus(p)
+    fm = dict(qname=qname, q_integer=ityp["qstart"] and ityp["qend"], merged=False, out_qname=None)
+    out = compress_paf_fnct(p, second_run=False, chunklen=chunklen, n_quadrants_per_axis=n_quadrants_per_axis, file_mode=fm)
+    names = fm["out_qname"] if fm["merged"] else [qname[int(r)] for r in out["_row"]]
+    if fm["merged"]:
+        ityp = dict(ityp, nmatch=False, alen=False)
+    out = swap_minus(out)
+    qi = fm["q_integer"]
+    with open(out_path, "w") as f:
+        for k in range(len(out["qstart"])):
+            r = int(out["_row"][k])
+            cells = [names[k], r_format(out["qlen"][k], ityp["qlen"]), r_format(out["qstart"][k], qi), r_format(out["qend"][k], qi),
+                     "+" if out["strand"][k] > 0 else "-", tname[r], r_format(out["tlen"][k], ityp["tlen"]),
+                     r_format(out["tstart"][k], ityp["tstart"]), r_format(out["tend"][k], ityp["tend"]),
+                     r_format(out["nmatch"][k], ityp["nmatch"]), r_format(out["alen"][k], ityp["alen"]),
+                     r_format(out["mapq"][k], ityp["mapq"])]
+            if not fm["merged"] and extra[r]:
+                cells.append(extra[r])
+            f.write("\t".join(cells) + "\n")
+    return len(qname), len(names)

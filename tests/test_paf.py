@@ -148,3 +148,94 @@ def test_gpu_paf_pair_segment_overflow(solver):
     assert rcs == [0, 0, 0]
     for t, src in zip(got, (other, p, other)):
         _same(t, po.load_and_prep_paf(src, 5.0, 10.0, 1000.0))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# file mode: compress_paf_fnct(inpaf_link, outpaf_link) -- R/seqbuilder_functions.R:107
+# ---------------------------------------------------------------------------------------------------------------
+def write_chunk_paf(path, p, tags=False, dup_lines=0):
+    """A PAF file as correct_paf leaves it: qname = <seq>_<start>-<end> of the chunk, 12 columns (optionally tags)."""
+    lines = []
+    for k in range(len(p["qstart"])):
+        qn = "chr1_partial_%d-%d" % (int(p["qstart"][k]), int(p["qend"][k]) - 1)
+        f = [qn, int(p["qlen"][k]), int(p["qstart"][k]), int(p["qend"][k]), "+" if p["strand"][k] > 0 else "-", "chr1_t",
+             int(p["tlen"][k]), int(p["tstart"][k]), int(p["tend"][k]), int(p["nmatch"][k]), int(p["alen"][k]), int(p["mapq"][k])]
+        if tags:
+            f += ["tp:A:P", "cm:i:%d" % (k % 7)]
+        lines.append("\t".join(str(v) for v in f))
+    lines += lines[:dup_lines]                                # exact duplicates: unique() drops them
+    open(path, "w").write("\n".join(lines) + "\n")
+
+
+def test_r_number_formatting():
+    """as.character / write.table of doubles as R prints them (15 significant digits, scientific when narrower)."""
+    for v, want in [(100000, "1e+05"), (123456, "123456"), (1e6, "1e+06"), (1200000, "1200000"), (12000000, "1.2e+07"),
+                    (0.5, "0.5"), (1e-4, "1e-04"), (0.0001234, "0.0001234"), (99999, "99999"), (0.1 + 0.2, "0.3"),
+                    (1 / 3, "0.333333333333333"), (1e15, "1e+15"), (123456789012, "123456789012"), (-100000, "-1e+05"),
+                    (3e5, "3e+05"), (150.0, "150"), (0, "0")]:
+        assert po.r_format_double(v) == want, v
+    assert po.r_format(100000.0, True) == "100000"
+
+
+def test_read_paf_file_c_abi(tmp_path):
+    """nw_paf_read_file is host-only: a PAF with tags, against the restatement's reader; malformed files fail."""
+    import nahrwhals_b200 as nb
+    p = chunked_paf(np.random.default_rng(3), n_segments=4, jitter=2)
+    f = tmp_path / "in.paf"
+    write_chunk_paf(f, p, tags=True)
+    got = nb.read_paf(f)
+    want = po.read_paf_file(str(f))[0]
+    for k in po.COLS:
+        assert np.array_equal(got[k], want[k]) and np.array_equal(got[k], p[k]), k
+    (tmp_path / "bad.paf").write_text("a\t1\t2\n")
+    with pytest.raises(Exception):
+        nb.read_paf(tmp_path / "bad.paf")
+    with pytest.raises(Exception):
+        nb.read_paf(tmp_path / "missing.paf")
+
+
+def test_oracle_file_mode_names(tmp_path):
+    """Chunks of a forward alignment melt into one row whose qname is rebuilt from the first chunk's start and the last
+    chunk's end (R/compress_paf.R:49-59), with R's double formatting of `qend2 - 1`."""
+    n = 12
+    p = dict(qlen=np.full(n, 10000.0), qstart=10000.0 * np.arange(n), qend=10000.0 * (np.arange(n) + 1), strand=np.ones(n),
+             tlen=np.full(n, 5e6), tstart=500000 + 10000.0 * np.arange(n), tend=500000 + 10000.0 * (np.arange(n) + 1),
+             nmatch=np.full(n, 9990.0), alen=np.full(n, 10000.0), mapq=np.full(n, 60.0))
+    write_chunk_paf(tmp_path / "in.paf", p, dup_lines=3)
+    nin, nout = po.compress_paf_file(str(tmp_path / "in.paf"), str(tmp_path / "out.paf"), 10000.0)
+    assert (nin, nout) == (n, 1)
+    f = (tmp_path / "out.paf").read_text().strip().split("\t")
+    assert f[0] == "chr1_partial_0-119999" and f[2:4] == ["0", "120000"] and f[7:9] == ["500000", "620000"]
+    assert f[9:11] == ["119880", "120000"] and len(f) == 12     # nmatch / alen are doubles after the merge: 120000 stays fixed
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(8))
+def test_gpu_paf_file_mode_matches_oracle(solver, tmp_path, seed):
+    import nahrwhals_b200 as nb
+    rng = np.random.default_rng(500 + seed)
+    if seed == 0:     # one long forward alignment whose merged nmatch / alen / name hit R's scientific notation
+        n = 10
+        p = dict(qlen=np.full(n, 10000.0), qstart=1.0 + 10000.0 * np.arange(n), qend=1.0 + 10000.0 * (np.arange(n) + 1),
+                 strand=np.ones(n), tlen=np.full(n, 5e6), tstart=500000 + 10000.0 * np.arange(n),
+                 tend=500000 + 10000.0 * (np.arange(n) + 1), nmatch=np.full(n, 10000.0), alen=np.full(n, 10000.0),
+                 mapq=np.full(n, 60.0))
+    else:
+        p = chunked_paf(rng, n_segments=int(rng.integers(1, 12)), chunk=10000, jitter=int(rng.choice([0, 2, 30])),
+                        span=int(rng.choice([40000, 300000, 900000])), drop=float(rng.choice([0.0, 0.1])),
+                        extra=int(rng.integers(0, 6)))
+        if seed == 1:
+            p = {k: v[:1] for k, v in p.items()}
+    fin, fo, fg = tmp_path / "in.paf", tmp_path / "oracle.paf", tmp_path / "gpu.paf"
+    write_chunk_paf(fin, p, tags=(seed % 3 == 2), dup_lines=seed % 4)
+    want = po.compress_paf_file(str(fin), str(fo), 10000.0)
+    got = nb.compress_paf_file(solver, fin, fg, 10000.0)
+    assert got == want
+    assert fg.read_text() == fo.read_text()
+    if seed == 0:
+        assert "1e+05" in fg.read_text()
+    # the molten file is what load_and_prep_paf_for_gridplot_transform reads next
+    T = nb.read_paf(fg)
+    O = po.read_paf_file(str(fo))[0]
+    for k in po.COLS:
+        assert np.array_equal(T[k], O[k]), k
