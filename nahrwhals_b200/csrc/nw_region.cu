@@ -8,6 +8,10 @@
 // (visited-hash, running est_highest, > 90 filter) is then replayed on the host over the per-child numbers in the
 // reference's order.  No CPU fallback: without a device nw_region_prepass / nw_region_analyse fail.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/file.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -607,5 +611,107 @@ int64_t nw_table_candidates(const nw_table* t, const nw_candidate** out) {
 }
 int32_t nw_table_rows(const nw_table* t) { return t ? (int32_t)t->rows.size() : 0; }
 void nw_table_free(nw_table* t) { delete t; }
+
+// ---- save_to_logfile (R/save_logfile.R:112-232): the row of nahrwhals_res.tsv ----
+static const char* kLogHeader =
+    "seqname\tstart\tend\tsample\ty_seqname\ty_start\ty_end\twidth_orig\txpad\tres_ref\tres_max\tn_res_max\tmut_max\t"
+    "mut_simulated\tmut_tested\tsearch_depth\tgrid_compression\texceeds_x\texceeds_y\tgrid_inconsistency\tflip_unsure\t"
+    "cluttered_boundaries\tmut1_start\tmut1_end\tmut1_pos_pm\tmut1_len\tmut1_len_pm\tmut2_start\tmut2_end\tmut2_pos_pm\t"
+    "mut2_len\tmut2_len_pm\tmut3_start\tmut3_end\tmut3_pos_pm\tmut3_len\tmut3_len_pm";
+const char* nw_region_logrow_header(void) { return kLogHeader; }
+
+// a double as write.table / as.character print it under options(scipen = 999): the fewest significant digits (<= 15)
+// that reproduce the value at 15 digits, fixed notation
+static std::string r_fixed15(double v) {
+  if (std::isnan(v)) return "NA";
+  if (std::isinf(v)) return v > 0 ? "Inf" : "-Inf";
+  if (v == 0) return "0";
+  char ref[64], buf[400];
+  snprintf(ref, sizeof ref, "%.14e", v);
+  const double target = strtod(ref, nullptr);
+  int nsig = 15;
+  for (int d = 1; d <= 15; ++d) {
+    snprintf(buf, sizeof buf, "%.*e", d - 1, v);
+    if (strtod(buf, nullptr) == target) {
+      nsig = d;
+      break;
+    }
+  }
+  snprintf(buf, sizeof buf, "%.*e", nsig - 1, v);
+  const int kp = atoi(strchr(buf, 'e') + 1);
+  snprintf(buf, sizeof buf, "%.*f", std::max(0, nsig - kp - 1), strtod(buf, nullptr));
+  return buf;
+}
+
+int nw_region_logrow(const nw_region_summary* s, const char* mut_max, const nw_log_meta* m, char* buf, int64_t cap,
+                     int64_t* len) {
+  if (!s || !m || !len || (cap > 0 && !buf)) {
+    nw::set_last_error("null argument");
+    return NW_ERR_ARG;
+  }
+  auto txt = [](const char* t) { return std::string(t ? t : "NA"); };
+  auto num = [](const char* t) { return t ? strtod(t, nullptr) : std::numeric_limits<double>::quiet_NaN(); };
+  auto lgl = [](int32_t v) { return std::string(v < 0 ? "NA" : (v ? "TRUE" : "FALSE")); };
+  const double start = num(m->start), end = num(m->end);
+  std::vector<std::string> f = {txt(m->chr), txt(m->start), txt(m->end), txt(m->samplename), txt(m->y_seqname), txt(m->y_start),
+                                txt(m->y_end), r_fixed15(end - start), txt(m->xpad), r_fixed15(s->res_ref), r_fixed15(s->res_max),
+                                std::to_string((long long)s->n_res_max), txt(mut_max && *mut_max ? mut_max : nullptr),
+                                std::to_string((long long)s->mut_simulated), std::to_string((long long)s->mut_tested),
+                                std::to_string(s->search_depth), r_fixed15(std::isnan(m->compression) ? 0.0 : m->compression),
+                                lgl(m->exceeds_x), lgl(m->exceeds_y), lgl(m->grid_inconsistency), lgl(s->flip_unsure),
+                                lgl(s->cluttered)};
+  for (int k = 0; k < 3; ++k) {
+    f.push_back(r_fixed15(s->maxres[5 * k] + start));  // as.character(as.numeric(maxres$mutK_start) + as.numeric(log$start))
+    f.push_back(r_fixed15(s->maxres[5 * k + 1] + start));
+    for (int q = 2; q < 5; ++q) f.push_back(r_fixed15(s->maxres[5 * k + q]));
+  }
+  std::string row;
+  for (size_t k = 0; k < f.size(); ++k) {
+    if (k) row += '\t';
+    row += f[k];
+  }
+  *len = (int64_t)row.size();
+  if ((int64_t)row.size() + 1 > cap) {
+    nw::set_last_error("nw_region_logrow: buffer too small");
+    return NW_ERR_RANGE;
+  }
+  memcpy(buf, row.c_str(), row.size() + 1);
+  return NW_OK;
+}
+
+int nw_region_log_append(const char* logfile, const char* row) {
+  if (!logfile || !row) {
+    nw::set_last_error("null argument");
+    return NW_ERR_ARG;
+  }
+  const int fd = open(logfile, O_WRONLY | O_CREAT | O_APPEND, 0644);
+  if (fd < 0) {
+    nw::set_last_error(std::string("cannot open ") + logfile);
+    return NW_ERR_IO;
+  }
+  int rc = NW_OK;
+  if (flock(fd, LOCK_EX) != 0) {
+    rc = NW_ERR_IO;
+  } else {
+    struct stat st;
+    std::string out;
+    if (fstat(fd, &st) == 0 && st.st_size == 0) out = std::string(kLogHeader) + "\n";
+    out += row;
+    out += '\n';
+    size_t off = 0;
+    while (off < out.size()) {
+      const ssize_t w = write(fd, out.data() + off, out.size() - off);
+      if (w <= 0) {
+        rc = NW_ERR_IO;
+        break;
+      }
+      off += (size_t)w;
+    }
+    flock(fd, LOCK_UN);
+  }
+  close(fd);
+  if (rc != NW_OK) nw::set_last_error(std::string("cannot write ") + logfile);
+  return rc;
+}
 
 }  // extern "C"

@@ -29,9 +29,16 @@ class NwRegionSummary(C.Structure):
                 ("gpu_launches", C.c_int32), ("reserved", C.c_int32)]
 
 
+class NwLogMeta(C.Structure):
+    _fields_ = [("chr", C.c_char_p), ("start", C.c_char_p), ("end", C.c_char_p), ("samplename", C.c_char_p),
+                ("y_seqname", C.c_char_p), ("y_start", C.c_char_p), ("y_end", C.c_char_p), ("xpad", C.c_char_p),
+                ("compression", C.c_double), ("exceeds_x", C.c_int32), ("exceeds_y", C.c_int32),
+                ("grid_inconsistency", C.c_int32)]
+
+
 SYMBOLS = ["nw_region_default_opts", "nw_region_prepass", "nw_region_format", "nw_region_analyse", "nw_table_summary",
            "nw_table_mut_max", "nw_table_tsv", "nw_table_rows", "nw_table_free", "nw_table_candidates", "nw_region_analyse_many",
-           "nw_region_analyse_many_ctxs"]
+           "nw_region_analyse_many_ctxs", "nw_region_logrow_header", "nw_region_logrow", "nw_region_log_append"]
 
 
 class NwRegionProblem(C.Structure):
@@ -71,6 +78,10 @@ def _lib_region():
         L.nw_table_free.argtypes = [vp]
         L.nw_table_candidates.restype = i64
         L.nw_table_candidates.argtypes = [vp, C.POINTER(C.POINTER(NwCandidate))]
+        L.nw_region_logrow_header.restype = C.c_char_p
+        L.nw_region_logrow.argtypes = [C.POINTER(NwRegionSummary), C.c_char_p, C.POINTER(NwLogMeta), C.c_char_p, i64,
+                                       C.POINTER(i64)]
+        L.nw_region_log_append.argtypes = [C.c_char_p, C.c_char_p]
         _bound = True
     return L
 
@@ -125,6 +136,22 @@ class RegionResult:
         self.prepass_candidates = int(S.prepass_candidates)
         self.prepass_dp = int(S.prepass_dp)
         self.gpu_launches = int(S.gpu_launches)
+        self._summary = S
+
+    def logfile_row(self, chr, start, end, samplename, y_seqname=None, y_start=None, y_end=None, xpad="1", compression=None,
+                    exceeds_x=False, exceeds_y=False, grid_inconsistency=False):
+        """The row save_to_logfile appends to nahrwhals_res.tsv for this region (R/save_logfile.R:112-232).  chr / start /
+        end / xpad are the CHARACTER values log_collection holds (pass them as R would print them)."""
+        L = _lib_region()
+        enc = lambda v: None if v is None else str(v).encode()  # noqa: E731
+        lg = lambda v: -1 if v is None else int(bool(v))  # noqa: E731
+        m = NwLogMeta(enc(chr), enc(start), enc(end), enc(samplename), enc(y_seqname), enc(y_start), enc(y_end), enc(xpad),
+                      float("nan") if compression is None else float(compression), lg(exceeds_x), lg(exceeds_y),
+                      lg(grid_inconsistency))
+        buf = C.create_string_buffer(4096)
+        n = C.c_int64()
+        _lib.check(L.nw_region_logrow(C.byref(self._summary), self.mut_max.encode(), C.byref(m), buf, 4096, C.byref(n)))
+        return buf.value.decode()
 
 
 def _grid(mat, len_y, len_x):
@@ -218,3 +245,12 @@ def analyse_regions(solver, regions, depth=3, maxdup=2, init_width=1000, minrepo
     if isolate:
         return res, rcs[:n].tolist()
     return res
+
+
+def logfile_header():
+    return _lib_region().nw_region_logrow_header().decode()
+
+
+def append_logfile(logfile, row):
+    """Appends a logfile_row() to nahrwhals_res.tsv under an exclusive lock (header first if the file is empty)."""
+    _lib.check(_lib_region().nw_region_log_append(str(logfile).encode(), row.encode()))

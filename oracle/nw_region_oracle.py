@@ -599,3 +599,53 @@ def analyse_region(mat, len_y, len_x, gridlines_x, solver, depth=3, maxdup=2, in
         res = merge_results(res, fj)
     summ = logfile_summary(res)
     return dict(res=res, log=log, julia_called=julia_called, **summ)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# save_to_logfile: the row of nahrwhals_res.tsv (R/save_logfile.R:112-232)
+# ---------------------------------------------------------------------------------------------------------------
+LOG_COLUMNS = ["seqname", "start", "end", "sample", "y_seqname", "y_start", "y_end", "width_orig", "xpad", "res_ref", "res_max",
+               "n_res_max", "mut_max", "mut_simulated", "mut_tested", "search_depth", "grid_compression", "exceeds_x",
+               "exceeds_y", "grid_inconsistency", "flip_unsure", "cluttered_boundaries"] + \
+              ["mut%d_%s" % (i, s) for i in (1, 2, 3) for s in ("start", "end", "pos_pm", "len", "len_pm")]
+
+
+def r_fixed15(v):
+    """A double as write.table prints it under options(scipen = 999): <= 15 significant digits, fixed notation."""
+    if v is NA or v != v:
+        return "NA"
+    v = float(v)
+    if v == 0:
+        return "0"
+    target = float("%.14e" % v)
+    nsig = 15
+    for d in range(1, 16):
+        if float("%.*e" % (d - 1, v)) == target:
+            nsig = d
+            break
+    txt = "%.*e" % (nsig - 1, v)
+    kp = int(txt.split("e")[1])
+    return "%.*f" % (max(0, nsig - kp - 1), float(txt))
+
+
+def logfile_row(summ, log):
+    """summ: logfile_summary(); log: the log_collection entries (chr / start / end / samplename / xpad as the CHARACTER
+    values of R/wrapper_aln_and_analyse.R:13-24, y_* or None, mut_simulated, mut_tested, depth, compression or None,
+    exceeds_x, exceeds_y, grid_inconsistency, flip_unsure, cluttered_boundaries)."""
+    txt = lambda v: "NA" if v is None else str(v)                      # noqa: E731
+    lgl = lambda v: "NA" if v is None else ("TRUE" if v else "FALSE")  # noqa: E731
+    start, end = float(log["start"]), float(log["end"])
+    mr = summ["maxres"]
+    num = lambda k: mr[k] if (k in mr and mr[k] is not NA and mr[k] is not None) else float("nan")  # noqa: E731
+    comp = log.get("compression")
+    f = [txt(log["chr"]), txt(log["start"]), txt(log["end"]), txt(log["samplename"]), txt(log.get("y_seqname")),
+         txt(log.get("y_start")), txt(log.get("y_end")), r_fixed15(end - start), txt(log["xpad"]), r_fixed15(summ["res_ref"]),
+         r_fixed15(summ["res_max"]), str(int(summ["n_res_max"])), summ["mut_max"], str(int(log["mut_simulated"])),
+         str(int(log["mut_tested"])), str(int(log["depth"])), r_fixed15(0 if comp is None else comp), lgl(log["exceeds_x"]),
+         lgl(log["exceeds_y"]), lgl(log["grid_inconsistency"]), lgl(log["flip_unsure"]), lgl(log["cluttered_boundaries"])]
+    for i in (1, 2, 3):
+        f.append(r_fixed15(num("mut%d_start" % i) + start))
+        f.append(r_fixed15(num("mut%d_end" % i) + start))
+        for s_ in ("pos_pm", "len", "len_pm"):
+            f.append(r_fixed15(num("mut%d_%s" % (i, s_))))
+    return "\t".join(f)
