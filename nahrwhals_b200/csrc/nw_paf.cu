@@ -105,41 +105,76 @@ struct PafTab {
   uint32_t blk0;     // first CTA of the table
   uint32_t out_off;  // first record of the table's output segment
   uint32_t out_cap;  // records the segment holds
+  uint32_t shift;    // n < 256: a CTA covers 256 >> shift columns x (1 << shift) rows, 1 << shift >= n
+  uint32_t strips;   // n >= 256: a CTA covers 256 rows of one column, `strips` CTAs per column
 };
-__global__ void __launch_bounds__(256) k_paf_pairs(const PafTab* __restrict__ tabs, int n_tabs, const double* __restrict__ ts,
-                                                   const double* __restrict__ te, const double* __restrict__ qs,
-                                                   const double* __restrict__ qe, const double* __restrict__ strand,
-                                                   const double* __restrict__ alen, const unsigned long long* __restrict__ mask,
-                                                   const double* __restrict__ tol, PairRec* __restrict__ out,
-                                                   unsigned int* __restrict__ count /* [n_tabs] */) {
-  __shared__ PafTab T;
-  __shared__ int s_tab;
-  if (threadIdx.x == 0) {  // last table with blk0 <= blockIdx.x
+// CTAs a table needs (no per-thread division: the pair of a thread follows from its CTA's column / row origin)
+inline void paf_tab_layout(uint32_t n, uint32_t& shift, uint32_t& strips, size_t& blocks) {
+  if (n >= 256) {
+    shift = 0;
+    strips = (n + 255) / 256;
+    blocks = (size_t)n * strips;
+  } else {
+    shift = 1;
+    while ((1u << shift) < n) ++shift;
+    strips = 0;
+    const uint32_t cols = 256u >> shift;
+    blocks = (n + cols - 1) / cols;
+  }
+}
+// A CTA works through a contiguous range of 256-pair tiles: it finds the table of its first tile by a binary search over
+// the tables' first tiles ONCE and walks forward from there (a search per tile cost more than the tile's pairs).
+__global__ void __launch_bounds__(256) k_paf_pairs(const PafTab* __restrict__ tabs, int n_tabs, uint32_t n_tiles,
+                                                   const double* __restrict__ ts, const double* __restrict__ te,
+                                                   const double* __restrict__ qs, const double* __restrict__ qe,
+                                                   const double* __restrict__ strand, const double* __restrict__ alen,
+                                                   const unsigned long long* __restrict__ mask, const double* __restrict__ tol,
+                                                   PairRec* __restrict__ out, unsigned int* __restrict__ count /* [n_tabs] */) {
+  const uint32_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+  uint32_t b = blockIdx.x * per_cta;
+  const uint32_t bend = min(b + per_cta, n_tiles);
+  if (b >= bend) return;
+  int tab;
+  {  // last table with blk0 <= b (uniform over the CTA: broadcast loads)
     int lo = 0, hi = n_tabs - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (tabs[mid].blk0 <= blockIdx.x) lo = mid; else hi = mid - 1;
+      if (tabs[mid].blk0 <= b) lo = mid; else hi = mid - 1;
     }
-    T = tabs[lo];
-    s_tab = lo;
+    tab = lo;
   }
-  __syncthreads();
-  const int n = (int)T.n;
-  const long long w = (long long)(blockIdx.x - T.blk0) * blockDim.x + threadIdx.x;
-  if (w >= (long long)n * n) return;
-  const int j = (int)(w / n), i = (int)(w % n);  // column-major like which(, arr.ind = T): consecutive threads share j
-  const size_t gi = (size_t)T.off + i, gj = (size_t)T.off + j;
-  unsigned long long common = mask[gi] & mask[gj];
-  if (!common || strand[gi] != strand[gj]) return;
-  const double dt = fabs(te[gi] - ts[gj]), dq = fabs(qe[gi] - qs[gj]);
-  while (common) {
-    const int s = __ffsll((long long)common) - 1;
-    common &= common - 1;
-    const double t = tol[T.tol_off + s];
-    if (dt < t && dq < t && (!(t > 100) || (alen[gi] > t && alen[gj] > t))) {
-      const unsigned int k = atomicAdd(&count[s_tab], 1u);  // the table's own cursor and output segment
-      if (k < T.out_cap) out[(size_t)T.out_off + k] = PairRec{j, s, i, s_tab};
-      return;  // later chunks only repeat the pair (unique() drops the repeats)
+  PafTab T = tabs[tab];
+  uint32_t next0 = tab + 1 < n_tabs ? tabs[tab + 1].blk0 : 0xffffffffu;
+  for (; b < bend; ++b) {
+    while (b >= next0) {
+      ++tab;
+      T = tabs[tab];
+      next0 = tab + 1 < n_tabs ? tabs[tab + 1].blk0 : 0xffffffffu;
+    }
+    const uint32_t n = T.n, lb = b - T.blk0;
+    // i = row: the alignment that ends, j = col: the alignment that starts; consecutive threads share j
+    uint32_t i, j;
+    if (T.strips) {
+      j = lb / T.strips;
+      i = (lb - j * T.strips) * 256u + threadIdx.x;
+    } else {
+      j = lb * (256u >> T.shift) + (threadIdx.x >> T.shift);
+      i = threadIdx.x & ((1u << T.shift) - 1u);
+    }
+    if (i >= n || j >= n) continue;
+    const size_t gi = (size_t)T.off + i, gj = (size_t)T.off + j;
+    unsigned long long common = mask[gi] & mask[gj];
+    if (!common || strand[gi] != strand[gj]) continue;
+    const double dt = fabs(te[gi] - ts[gj]), dq = fabs(qe[gi] - qs[gj]);
+    while (common) {
+      const int s = __ffsll((long long)common) - 1;
+      common &= common - 1;
+      const double t = tol[T.tol_off + s];
+      if (dt < t && dq < t && (!(t > 100) || (alen[gi] > t && alen[gj] > t))) {
+        const unsigned int k = atomicAdd(&count[tab], 1u);  // the table's own cursor and output segment
+        if (k < T.out_cap) out[(size_t)T.out_off + k] = PairRec{(int32_t)j, s, (int32_t)i, tab};
+        break;  // later chunks only repeat the pair (unique() drops the repeats)
+      }
     }
   }
 }
@@ -390,10 +425,13 @@ void compress_gpu_batch(nw_ctx* ctx, CompressJob** jobs, size_t nj, int& launche
   std::vector<size_t> cap(nj);
   for (size_t t = 0; t < nj; ++t) {
     const CompressJob& J = *jobs[t];
-    tabs[t] = PafTab{(uint32_t)N, (uint32_t)J.n, (uint32_t)NT, (uint32_t)blocks, 0u, 0u};
+    uint32_t shift = 0, strips = 0;
+    size_t nb = 0;
+    paf_tab_layout((uint32_t)J.n, shift, strips, nb);
+    tabs[t] = PafTab{(uint32_t)N, (uint32_t)J.n, (uint32_t)NT, (uint32_t)blocks, 0u, 0u, shift, strips};
     N += (size_t)J.n;
     NT += (size_t)J.nsteps;
-    blocks += ((size_t)J.n * J.n + 255) / 256;
+    blocks += nb;
     cap[t] = 2 * (size_t)J.n + 64;  // chunks of one alignment pair up with their neighbours: ~n pairs
   }
   auto al16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
@@ -423,7 +461,8 @@ void compress_gpu_batch(nw_ctx* ctx, CompressJob** jobs, size_t nj, int& launche
     memset(h + o_cnt, 0, o_out - o_cnt);
     PCK(cudaMemcpyAsync(d, h, o_out, cudaMemcpyHostToDevice, st));
     const double* dc = (const double*)(d + o_cols);
-    k_paf_pairs<<<(unsigned)blocks, 256, 0, st>>>((const PafTab*)(d + o_tabs), (int)nj, dc, dc + N, dc + 2 * N, dc + 3 * N,
+    const unsigned grid = (unsigned)std::min<size_t>(blocks, (size_t)148 * 32);  // 148 SMs x 8 resident CTAs x 4 waves
+    k_paf_pairs<<<grid, 256, 0, st>>>((const PafTab*)(d + o_tabs), (int)nj, (uint32_t)blocks, dc, dc + N, dc + 2 * N, dc + 3 * N,
                                                   dc + 4 * N, dc + 5 * N, (const unsigned long long*)(dc + 6 * N),
                                                   (const double*)(d + o_tol), (PairRec*)(d + o_out),
                                                   (unsigned int*)(d + o_cnt));
@@ -462,7 +501,10 @@ void compress_gpu(nw_ctx* ctx, const std::vector<CompressJob*>& all) {
   while (a < need.size()) {
     size_t b = a, N = 0, blocks = 0;
     while (b < need.size()) {
-      const size_t n = (size_t)need[b]->n, bl = (n * n + 255) / 256;
+      const size_t n = (size_t)need[b]->n;
+      uint32_t sh_ = 0, st_ = 0;
+      size_t bl = 0;
+      paf_tab_layout((uint32_t)n, sh_, st_, bl);
       if (b > a && (N + n > PAF_BATCH_ALNS || blocks + bl > PAF_BATCH_BLOCKS)) break;
       N += n;
       blocks += bl;
