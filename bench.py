@@ -564,6 +564,127 @@ def run_bitlocus(args, rank, world, local):
     solver.close()
 
 
+def _pipeline_cpu_one(job):
+    from oracle import oracle_lib
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from tests.test_pipeline import oracle_row
+    p, m = job
+    try:
+        return oracle_row(oracle_lib, p, m, 3, 1000.0, 1000.0, 10000.0) is not None
+    except Exception:
+        return None
+
+
+def run_pipeline(args, rank, world, local):
+    """Regionfile mode from the alignments on, all native (nahrwhals_b200.pipeline.run_regions): chunked PAF tables ->
+    wrapper_paf_to_bitlocus -> solver stage (-d 3) -> rows of nahrwhals_res.tsv.  Metric: regions/s, wall clock around
+    run_regions (host PAF columns in, result rows out).  --impl reference: the chain of the R restatements around the C++
+    oracle solver on all host cores, one region per worker process."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from region_batch import make_stage_regions
+    from nahrwhals_b200.sdgrid import matrix_to_chunked_paf
+    cores = os.cpu_count() or 1
+    n_reg = max(16, args.regions // 4)
+    desc = ("regionfile mode from the alignments on: chunked (10 kb) alignment tables of %d synthetic SD-flanked regions per "
+            "GPU (20-120 blocks) -> wrapper_paf_to_bitlocus -> R depth-1 pre-pass + solver -d 3 -u 2 -w 1000 -r 0.98 -R 1000 + "
+            "format / merge -> rows of nahrwhals_res.tsv")
+
+    def make(n, seed):
+        regs = make_stage_regions(n, seed=seed)
+        pafs = [matrix_to_chunked_paf(m, lx, ly) for m, ly, lx, _ in regs]
+        metas = [dict(chr="chr%d" % (1 + k % 22), start=str(1000000 + 1000 * k), end=str(1000000 + 1000 * k + int(lx.sum())),
+                      samplename="x_y") for k, (m, ly, lx, _) in enumerate(regs)]
+        return pafs, metas
+
+    def cpu(pafs, metas):
+        import multiprocessing as mp
+        t0 = time.perf_counter()
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_pipeline_cpu_one, list(zip(pafs, metas)), chunksize=1)
+        return len(pafs) / (time.perf_counter() - t0), time.perf_counter() - t0
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        pafs, metas = make(max(64, n_reg // 20), 0)
+        r, dt = cpu(pafs, metas)
+        print(json.dumps(dict(impl="reference", metric="regions_alignments_to_result_row_per_s", value=r, unit="regions/s",
+                              n_gpus=args.gpus, steps=1, warmup=0, ms_per_step=1e3 * dt, higher_is_better=True,
+                              scaling="weak", vs_baseline=None, dtype="int32", data="synthetic",
+                              config=dict(workload=desc % len(pafs)),
+                              cpu_baseline=dict(value=r, unit="regions/s", cores=cores, kind="port",
+                                                sample="%d regions, one per worker process" % len(pafs)),
+                              e2e=dict(value=r, unit="regions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                              gpu_launches=0)), flush=True)
+        return
+    import torch
+    import nahrwhals_b200 as nb
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pafs, metas = make(n_reg, rank)
+    solver = nb.Solver(local)
+    kw = dict(depth=3, minlen=1000.0, compression=1000.0, chunklen=10000.0)
+    for k in range(3):
+        nb.run_regions_native(solver, pafs if k == 0 else pafs[:200], metas if k == 0 else metas[:200], 1000.0, 1000.0,
+                              10000.0, depth=3)
+    nb.run_regions(solver, pafs[:200], metas[:200], **kw)
+    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler.start()
+    steps = max(1, args.steps)
+    dt = 0.0
+    for _ in range(steps):
+        tn = {}
+        rows, st_ = nb.run_regions_native(solver, pafs, metas, 1000.0, 1000.0, 10000.0, depth=3, timing=tn)
+        dt += tn["native_s"]
+    torch.cuda.synchronize()
+    dt /= steps
+    clocks = sampler.stop()
+    # the same through the per-step Python mirror (three batched calls + Python objects per region): reported, not the metric
+    tm = {}
+    t0 = time.perf_counter()
+    rows_py, det = nb.run_regions(solver, pafs, metas, timing=tm, **kw)
+    tm["total_s"] = time.perf_counter() - t0
+    assert rows_py == rows, "pipeline: the one-call form and the Python-routed form disagree"
+    n, ok = len(pafs), sum(1 for r in rows if r is not None)
+    called = sum(1 for _, r in det if r is not None and r.solver_called)
+    launches = sum(r.gpu_launches for _, r in det if r is not None)
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        s_ = torch.tensor([n, ok, called], dtype=torch.float64, device="cuda")
+        dist.all_reduce(s_, op=dist.ReduceOp.SUM)
+        n, ok, called = s_.tolist()
+    line = dict(metric="regions_alignments_to_result_row_per_s", value=n / dt, unit="regions/s", n_gpus=world, steps=steps,
+                warmup=3, ms_per_step=1e3 * dt, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32",
+                data="synthetic",
+                config=dict(workload=(desc % n_reg) + "; regions shard per GPU, no collective", rows=int(ok),
+                            solver_called=int(called),
+                            python_routed_ms=dict(total=1e3 * tm["total_s"], bitlocus=1e3 * tm["bitlocus_s"],
+                                                  stage=1e3 * tm["stage_s"], rows=1e3 * tm["rows_s"]),
+                            timed="wall clock around nw_regions_run (host PAF columns in, result rows in host memory out)"),
+                clocks=clocks, e2e=dict(value=n / dt, unit="regions/s",
+                                        h2d_bytes_per_step=int(sum(len(p["tstart"]) for p in pafs)) * 56,
+                                        d2h_bytes_per_step=None), gpu_launches=int(max(launches, 1)) * steps)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        k = max(32, n_reg // 20)
+        r, cdt = cpu(pafs[:k], metas[:k])
+        line["cpu_baseline"] = dict(value=r, unit="regions/s", cores=cores, kind="port",
+                                    sample="%d regions of the same set, %.1f s, one region per worker process; R "
+                                           "restatements in Python around the C++ oracle solver" % (k, cdt))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    solver.close()
+
+
 def _paf_tables(n, seed, n_segments=260):
     """Chunked PAF tables of a few thousand alignments each (a 4 Mb region cut into 10 kb chunks, repeats, short hits)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -713,7 +834,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS) + ["regions", "stage", "genome", "grid", "paf", "bitlocus"])
+    ap.add_argument("--workload", default="s64", choices=sorted(WORKLOADS) + ["regions", "stage", "genome", "grid", "paf", "bitlocus", "pipeline"])
     ap.add_argument("--regions", type=int, default=6000, help="regions per rank for --workload regions")
     ap.add_argument("--contexts", type=int, default=4, help="solver contexts (streams) per GPU for --workload regions")
     ap.add_argument("--warmup-regions", type=int, default=2, help="untimed warm-up runs for --workload regions")
@@ -736,6 +857,9 @@ def main():
         return
     if args.workload == "bitlocus":
         run_bitlocus(args, rank, world, local)
+        return
+    if args.workload == "pipeline":
+        run_pipeline(args, rank, world, local)
         return
     if args.workload == "paf":
         run_paf(args, rank, world, local)

@@ -335,8 +335,11 @@ def reduce_depth_if_needed(b, maxdepth):
 
 
 def dfs(b, maxdepth, st):
-    """R/dfs_machinery.R:16-246 for maxdepth in {0, 1}.  Returns rows (hash key, depth, mut_path, eval)."""
-    bitl, _, _ = flip_bitl_y_if_needed(b)
+    """R/dfs_machinery.R:16-246 for maxdepth in {0, 1}.  Returns rows (hash key, depth, mut_path, eval).
+    st.flip_unsure receives the side effect of flip_bitl_y_if_needed on log_collection (R/flip_bitl_y_if_needed.R:56-58)."""
+    bitl, _, unsure = flip_bitl_y_if_needed(b)
+    if unsure:
+        st.flip_unsure = True
     orig_symm = calc_symm(bitl)
     visited = {}
     ref_hash = return_diag_values_new(carry_out_compressed_sv(bitl, 1, 1, "ref"))
@@ -420,6 +423,8 @@ def solve_mutation_depth1(b, compression=1000):
         res.append(dict(eval=float(ev), mut1=(parts[1] if len(parts) > 1 else "ref")))
     res, _ = annotate_positions(res, b)
     log.update(depth=maxdepth, mut_simulated=len(rows), mut_tested=len(rows))
+    if getattr(st, "flip_unsure", False):
+        log["flip_unsure"] = True
     return dict(res=res, log=log, state=st)
 
 
@@ -590,7 +595,7 @@ def analyse_region(mat, len_y, len_x, gridlines_x, solver, depth=3, maxdup=2, in
     if max(r["eval"] for r in res) < 99.8:
         julia_called = True
         bf, flipped, unsure = flip_bitl_y_if_needed(b)
-        log["flip_unsure"] = unsure
+        log["flip_unsure"] = unsure or log.get("flip_unsure", False)   # the flag is only ever set, never cleared
         width = berzerk_width(bf, init_width)
         aln = np.sign(bf.m).T.astype(np.int8)
         tsv = solver(aln, np.array(bf.cn), np.array(bf.rn), depth, maxdup, width, minreport, 1000)

@@ -194,6 +194,12 @@ def test_library_exports_declared_symbols():
     assert declared == set(bitlocus.SYMBOLS)
     for s in declared:
         assert getattr(L, s) is not None
+    from nahrwhals_b200 import pipeline
+    hdr = open(os.path.join(ROOT, "include", "nwpipeline.h")).read()
+    declared = set(re.findall(r"\b(nw_regions_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(pipeline.SYMBOLS)
+    for s in declared:
+        assert getattr(L, s) is not None
     hdr = open(os.path.join(ROOT, "include", "nwregion.h")).read()
     declared = set(re.findall(r"\b(nw_(?:region|table)_[a-z_0-9]+)\s*\(", hdr))
     assert declared == set(region.SYMBOLS)
