@@ -65,6 +65,8 @@ class ClockSampler:
     def start(self):
         if int(os.environ.get("RANK", "0")) != 0:  # one sampler per job: nvidia-smi polling competes with the ranks
             return
+        if os.environ.get("NW_BENCH_NO_SAMPLER"):  # diagnostics only: a line without clocks is not a valid bench line
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", self.idx, "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
@@ -625,22 +627,31 @@ def run_pipeline(args, rank, world, local):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pafs, metas = make(n_reg, rank)
     solver = nb.Solver(local)
+    solver2 = nb.Solver(local)  # second context on the same GPU: host phases of one batch overlap device phases of the other
+    ctxs = [solver, solver2]
     kw = dict(depth=3, minlen=1000.0, compression=1000.0, chunklen=10000.0)
     for k in range(3):
-        nb.run_regions_native(solver, pafs if k == 0 else pafs[:200], metas if k == 0 else metas[:200], 1000.0, 1000.0,
-                              10000.0, depth=3)
+        nb.run_regions_native(ctxs, pafs if k == 0 else pafs[:600], metas if k == 0 else metas[:600], 1000.0, 1000.0,
+                              10000.0, depth=3, regions_per_batch=256)
+    one = {}
+    nb.run_regions_native(solver, pafs, metas, 1000.0, 1000.0, 10000.0, depth=3)
+    nb.run_regions_native(solver, pafs, metas, 1000.0, 1000.0, 10000.0, depth=3, timing=one)
     nb.run_regions(solver, pafs[:200], metas[:200], **kw)
     sampler = ClockSampler(local)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     sampler.start()
+    # last warm-up step with the sampler already attached (nvidia-smi's start-up stalls CUDA calls of the first step it meets)
+    nb.run_regions_native(ctxs, pafs, metas, 1000.0, 1000.0, 10000.0, depth=3, regions_per_batch=256)
     steps = max(1, args.steps)
     dt = 0.0
+    step_ms = []
     for _ in range(steps):
         tn = {}
-        rows, st_ = nb.run_regions_native(solver, pafs, metas, 1000.0, 1000.0, 10000.0, depth=3, timing=tn)
+        rows, st_ = nb.run_regions_native(ctxs, pafs, metas, 1000.0, 1000.0, 10000.0, depth=3, timing=tn, regions_per_batch=256)
         dt += tn["native_s"]
+        step_ms.append(round(1e3 * tn["native_s"], 2))
     torch.cuda.synchronize()
     dt /= steps
     clocks = sampler.stop()
@@ -667,7 +678,9 @@ def run_pipeline(args, rank, world, local):
                             solver_called=int(called),
                             python_routed_ms=dict(total=1e3 * tm["total_s"], bitlocus=1e3 * tm["bitlocus_s"],
                                                   stage=1e3 * tm["stage_s"], rows=1e3 * tm["rows_s"]),
-                            timed="wall clock around nw_regions_run (host PAF columns in, result rows in host memory out)"),
+                            one_context_ms=1e3 * one["native_s"], step_ms=step_ms,
+                            timed="wall clock around nw_regions_run_ctxs, two contexts on the GPU sharing batches of 256 regions "
+                                  "(host PAF columns in, result rows in host memory out)"),
                 clocks=clocks, e2e=dict(value=n / dt, unit="regions/s",
                                         h2d_bytes_per_step=int(sum(len(p["tstart"]) for p in pafs)) * 56,
                                         d2h_bytes_per_step=None), gpu_launches=int(max(launches, 1)) * steps)
@@ -682,6 +695,7 @@ def run_pipeline(args, rank, world, local):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    solver2.close()
     solver.close()
 
 

@@ -33,6 +33,13 @@ int nw_regions_run(nw_ctx* ctx, const nw_paf_cols* pafs, const nw_log_meta* meta
                    const nw_bitlocus_params* bp, const nw_region_opts* ropts, const char* logfile, char** rows,
                    int64_t* rows_len, int64_t* row_off, int32_t* status);
 
+/* The same over n_ctx contexts (one host thread + CUDA stream each; on one GPU -- the host phases of one batch overlap
+ * the device phases of another -- or on several GPUs): batches of regions_per_batch (<= 0: 512) regions are handed out
+ * dynamically; rows come back (and reach the logfile) in region order.  Results identical to nw_regions_run. */
+int nw_regions_run_ctxs(nw_ctx** ctxs, int32_t n_ctx, const nw_paf_cols* pafs, const nw_log_meta* metas, int64_t n,
+                        const nw_bitlocus_params* bp, const nw_region_opts* ropts, int32_t regions_per_batch,
+                        const char* logfile, char** rows, int64_t* rows_len, int64_t* row_off, int32_t* status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,9 @@
 // nw_pipeline.cu -- regionfile mode from the alignments on (include/nwpipeline.h): a composition of the library's own C
 // entry points (nw_bitlocus_build -> nw_region_analyse_many -> nw_region_logrow), written against the public headers only.
+#include <atomic>
 #include <cmath>
+#include <mutex>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -12,6 +15,7 @@
 namespace nw {
 void set_last_error(const std::string& m);
 }
+extern "C" const char* nw_last_error(void);
 
 extern "C" int nw_regions_run(nw_ctx* ctx, const nw_paf_cols* pafs, const nw_log_meta* metas, int64_t n,
                               const nw_bitlocus_params* bp, const nw_region_opts* ropts, const char* logfile, char** rows,
@@ -142,6 +146,96 @@ extern "C" int nw_regions_run(nw_ctx* ctx, const nw_paf_cols* pafs, const nw_log
   }
   if (row_off) row_off[n] = (int64_t)text.size();
   cleanup();
+  char* out = (char*)malloc(text.size() + 1);
+  if (!out) {
+    nw::set_last_error("host out of memory");
+    return NW_ERR_NOMEM;
+  }
+  memcpy(out, text.c_str(), text.size() + 1);
+  *rows = out;
+  *rows_len = (int64_t)text.size();
+  return NW_OK;
+}
+
+extern "C" int nw_regions_run_ctxs(nw_ctx** ctxs, int32_t n_ctx, const nw_paf_cols* pafs, const nw_log_meta* metas, int64_t n,
+                                   const nw_bitlocus_params* bp, const nw_region_opts* ropts, int32_t regions_per_batch,
+                                   const char* logfile, char** rows, int64_t* rows_len, int64_t* row_off, int32_t* status) {
+  if (rows) *rows = nullptr;
+  if (rows_len) *rows_len = 0;
+  if (!ctxs || n_ctx < 1 || !rows || !rows_len || n < 0) {
+    nw::set_last_error("null argument");
+    return NW_ERR_ARG;
+  }
+  for (int t = 0; t < n_ctx; ++t)
+    if (!ctxs[t]) {
+      nw::set_last_error("null context");
+      return NW_ERR_ARG;
+    }
+  const int64_t per = regions_per_batch > 0 ? regions_per_batch : 512;
+  const int64_t nb = (n + per - 1) / per;
+  if (n_ctx == 1 || nb <= 1) return nw_regions_run(ctxs[0], pafs, metas, n, bp, ropts, logfile, rows, rows_len, row_off, status);
+  struct Batch {
+    char* text = nullptr;
+    int64_t len = 0;
+    std::vector<int64_t> off;
+  };
+  std::vector<Batch> B((size_t)nb);
+  std::vector<int32_t> st((size_t)n, NW_OK);
+  std::atomic<int64_t> next{0};
+  std::mutex mu;
+  int first_rc = NW_OK;
+  std::string first_msg;
+  auto work = [&](int t) {
+    for (;;) {
+      const int64_t b = next.fetch_add(1);
+      if (b >= nb) return;
+      const int64_t a = b * per, m = std::min<int64_t>(per, n - a);
+      B[b].off.assign((size_t)m + 1, 0);
+      const int rc = nw_regions_run(ctxs[t], pafs + a, metas + a, m, bp, ropts, nullptr, &B[b].text, &B[b].len, B[b].off.data(),
+                                    st.data() + a);
+      if (rc != NW_OK) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (first_rc == NW_OK) {
+          first_rc = rc;
+          first_msg = nw_last_error();  // thread-local: carried to the caller's thread below
+        }
+        next.store(nb);
+        return;
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_ctx; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+  auto release = [&] {
+    for (Batch& b : B) free(b.text);
+  };
+  if (first_rc != NW_OK) {
+    release();
+    nw::set_last_error(first_msg);
+    return first_rc;
+  }
+  std::string text;
+  for (int64_t b = 0; b < nb; ++b) {
+    const int64_t a = b * per;
+    if (row_off)
+      for (size_t q = 0; q + 1 < B[b].off.size(); ++q) row_off[a + (int64_t)q] = (int64_t)text.size() + B[b].off[q];
+    if (B[b].text) text.append(B[b].text, (size_t)B[b].len);
+  }
+  if (row_off) row_off[n] = (int64_t)text.size();
+  release();
+  if (status) memcpy(status, st.data(), (size_t)n * sizeof(int32_t));
+  if (logfile) {  // in region order, one locked append per row (as the one-context form does)
+    size_t p0 = 0;
+    while (p0 < text.size()) {
+      const size_t e = text.find('\n', p0);
+      const std::string line = text.substr(p0, e - p0);
+      const int a = nw_region_log_append(logfile, line.c_str());
+      if (a != NW_OK) return a;
+      p0 = e + 1;
+    }
+  }
   char* out = (char*)malloc(text.size() + 1);
   if (!out) {
     nw::set_last_error("host out of memory");

@@ -17,7 +17,7 @@ from .bitlocus import NwBitlocusParams, _lib_bitlocus, auto_params, paf_to_bitlo
 from .paf import NwPafCols, _cols
 from .region import (NwLogMeta, NwRegionSummary, _lib_region, _opts, analyse_regions, append_logfile)
 
-SYMBOLS = ["nw_regions_run"]
+SYMBOLS = ["nw_regions_run", "nw_regions_run_ctxs"]
 
 
 def _empty_row(meta, depth, cluttered):
@@ -106,15 +106,20 @@ def _meta(m, keep):
 
 
 def run_regions_native(solver, pafs, metas, minlen, compression, chunklen=10000.0, depth=3, maxdup=2, init_width=1000,
-                       minreport=0.98, max_n_alns=150, max_size_col_plus_rows=250, logfile=None, timing=None):
+                       minreport=0.98, max_n_alns=150, max_size_col_plus_rows=250, logfile=None, timing=None,
+                       regions_per_batch=512):
     """run_regions as ONE call of the C ABI (nw_regions_run, include/nwpipeline.h): all regions share minlen / compression /
-    chunklen.  Returns (rows, status): rows[k] the region's line of nahrwhals_res.tsv or None, status[k] 0 / 1 (cluttered
-    PAF: the empty row) / negative (dropped)."""
+    chunklen.  `solver` may be a list of Solvers (contexts, on one GPU or several) that share the batches
+    (nw_regions_run_ctxs).  Returns (rows, status): rows[k] the region's line of nahrwhals_res.tsv or None, status[k]
+    0 / 1 (cluttered PAF: the empty row) / negative (dropped)."""
     import time
     L = _lib_bitlocus()
     _lib_region()
     L.nw_regions_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(NwBitlocusParams), C.c_void_p,
                                  C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]
+    L.nw_regions_run_ctxs.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(NwBitlocusParams),
+                                      C.c_void_p, C.c_int32, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p,
+                                      C.c_void_p]
     L.nw_free.argtypes = [C.c_void_p]
     n = len(pafs)
     keep = []
@@ -132,8 +137,15 @@ def run_regions_native(solver, pafs, metas, minlen, compression, chunklen=10000.
     off = np.zeros(n + 1, np.int64)
     st = np.zeros(max(n, 1), np.int32)
     t0 = time.perf_counter()
-    _lib.check(L.nw_regions_run(solver.h, cols, ms, n, C.byref(bp), C.byref(ro), None if logfile is None else str(logfile).encode(),
-                                C.byref(text), C.byref(tlen), off.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p)))
+    lf = None if logfile is None else str(logfile).encode()
+    if isinstance(solver, (list, tuple)):
+        hs = (C.c_void_p * len(solver))(*[s_.h for s_ in solver])
+        _lib.check(L.nw_regions_run_ctxs(hs, len(solver), cols, ms, n, C.byref(bp), C.byref(ro), int(regions_per_batch), lf,
+                                         C.byref(text), C.byref(tlen), off.ctypes.data_as(C.c_void_p),
+                                         st.ctypes.data_as(C.c_void_p)))
+    else:
+        _lib.check(L.nw_regions_run(solver.h, cols, ms, n, C.byref(bp), C.byref(ro), lf, C.byref(text), C.byref(tlen),
+                                    off.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p)))
     if timing is not None:
         timing["native_s"] = time.perf_counter() - t0
     try:

@@ -72,6 +72,15 @@ def test_gpu_pipeline_matches_oracle_chain(solver, oracle, tmp_path):
     for (b, _), r, s_ in zip(det, rows, st):
         assert (s_ == 1) == (b.status == "cluttered") and (s_ < 0) == (r is None)
     assert st[-1] < 0 and st[3] == 1
+    # two contexts sharing batches of three regions
+    s2 = nb.Solver(0)
+    try:
+        f3 = tmp_path / "res3.tsv"
+        rows3, st3 = nb.run_regions_native([solver, s2], pafs, metas, 1000.0, 1000.0, 10000.0, depth=2, logfile=f3,
+                                           regions_per_batch=3)
+        assert rows3 == want and st3 == st and f3.read_text() == f.read_text()
+    finally:
+        s2.close()
 
 
 @pytest.mark.gpu
