@@ -63,6 +63,15 @@ int nw_paf_prepare_many(nw_ctx* ctx, const nw_paf_cols* ins, int64_t n_tables, d
 int nw_paf_compress_file(nw_ctx* ctx, const char* inpaf_path, const char* outpaf_path, double chunklen, int32_t n_quadrants,
                          int64_t* rows_in, int64_t* rows_out);
 
+/* Replaces the loop of whole-genome mode's all-vs-all melt (R/make_whole_genome_list.R:80-106): read.table, the chunk
+ * suffix "_<start>-<end>" stripped from qname, strand swap, and for every query sequence in unique(paf$qname) order
+ * compress_paf_fnct(inpaf_df = paf, outpaf_link, inparam_chunklen, n_quadrants_per_axis, qname = q): that sequence's
+ * rows melted with reduced_qnames (a merged row keeps qname1) and APPENDED to outpaf_path (append = TRUE in the
+ * reference; the file is not truncated).  The all-pairs tests of all query sequences run in one kernel launch.
+ * The reference passes n_quadrants = 10. */
+int nw_paf_compress_file_by_qname(nw_ctx* ctx, const char* inpaf_path, const char* outpaf_path, double chunklen,
+                                  int32_t n_quadrants, int64_t* rows_in, int64_t* rows_out);
+
 /* read.table(inpaf) of load_and_prep_paf_for_gridplot_transform (R/tsv_to_bitlocus.R:17-31): the numeric columns of a
  * PAF file (12 columns + optional tags) as a table; strand '+' / '-' becomes +1 / -1.  Host only. */
 int nw_paf_read_file(const char* path, nw_paf_table** out);

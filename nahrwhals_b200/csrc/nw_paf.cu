@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cctype>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -347,6 +348,7 @@ struct CompressJob {
   // file mode: the qname strings of the input rows (indexed by ROWID); out: names of the result rows, merged = merge_rows ran
   const std::vector<std::string>* in_qname = nullptr;
   bool q_integer = true;
+  bool reduced_qnames = false;
   std::vector<std::string> out_qname;
   bool merged = false;
 };
@@ -565,6 +567,7 @@ Table compress_post(CompressJob& J) {
     if (J.in_qname) {
       MergeNames nm;
       nm.q_integer = J.q_integer;
+      nm.reduced = J.reduced_qnames;
       for (size_t k = 0; k < p.n(); ++k) nm.qname.push_back((*J.in_qname)[(size_t)p.c[ROWID][k]]);
       p = merge_rows(p, pairs, &nm);
       J.out_qname.swap(nm.qname);
@@ -828,10 +831,11 @@ PafFile read_paf_file(const char* path, bool dedupe) {
 }
 
 // write.table(inpaf, quote = F, col.names = F, row.names = F, sep = "\t") after the final strand swap
-void write_paf_file(const char* path, const Table& t, const std::vector<std::string>& qname, const PafFile& src, bool merged) {
-  const std::string tmp = std::string(path) + ".tmp";
+void write_paf_file(const char* path, const Table& t, const std::vector<std::string>& qname, const PafFile& src, bool merged,
+                    bool append = false) {
+  const std::string tmp = append ? std::string(path) : std::string(path) + ".tmp";
   {
-    std::ofstream o(tmp);
+    std::ofstream o(tmp, append ? std::ios::app : std::ios::trunc);
     if (!o) pfail(NW_ERR_IO, std::string("cannot write ") + tmp);
     bool it[10];
     for (int k = 0; k < 10; ++k) it[k] = src.integer_typed[k];
@@ -851,7 +855,7 @@ void write_paf_file(const char* path, const Table& t, const std::vector<std::str
     o.flush();
     if (!o) pfail(NW_ERR_IO, std::string("cannot write ") + tmp);
   }
-  if (rename(tmp.c_str(), path) != 0) pfail(NW_ERR_IO, std::string("cannot rename to ") + path);
+  if (!append && rename(tmp.c_str(), path) != 0) pfail(NW_ERR_IO, std::string("cannot rename to ") + path);
 }
 
 }  // namespace
@@ -891,6 +895,63 @@ int nw_paf_compress_file(nw_ctx* ctx, const char* inpaf_path, const char* outpaf
     }
     write_paf_file(outpaf_path, out, J.out_qname, P, J.merged);
     if (rows_out) *rows_out = (int64_t)out.n();
+  });
+}
+
+int nw_paf_compress_file_by_qname(nw_ctx* ctx, const char* inpaf_path, const char* outpaf_path, double chunklen,
+                                  int32_t n_quadrants, int64_t* rows_in, int64_t* rows_out) {
+  return pguard([&] {
+    if (!ctx || !outpaf_path) pfail(NW_ERR_ARG, "null argument");
+    PafFile P = read_paf_file(inpaf_path, false);
+    if (rows_in) *rows_in = (int64_t)P.t.n();
+    // paf$V1 = sub("_[0-9]+-[0-9]+$", "", paf$V1) (R/make_whole_genome_list.R:81)
+    for (std::string& q : P.qname) {
+      size_t e = q.size(), d2 = e;
+      while (d2 > 0 && isdigit((unsigned char)q[d2 - 1])) --d2;
+      if (d2 == e || d2 == 0 || q[d2 - 1] != '-') continue;
+      size_t d1 = d2 - 1;
+      while (d1 > 0 && isdigit((unsigned char)q[d1 - 1])) --d1;
+      if (d1 == d2 - 1 || d1 == 0 || q[d1 - 1] != '_') continue;
+      q.erase(d1 - 1);
+    }
+    swap_minus(P.t);  // :97-101
+    // one table per query sequence, in the order of unique(paf$qname)
+    std::vector<std::string> order;
+    std::map<std::string, std::vector<size_t>> rows_of;
+    for (size_t k = 0; k < P.t.n(); ++k) {
+      auto it = rows_of.find(P.qname[k]);
+      if (it == rows_of.end()) {
+        order.push_back(P.qname[k]);
+        it = rows_of.emplace(P.qname[k], std::vector<size_t>()).first;
+      }
+      it->second.push_back(k);
+    }
+    std::vector<CompressJob> jobs(order.size());
+    std::vector<CompressJob*> run;
+    for (size_t g = 0; g < order.size(); ++g) {
+      CompressJob& J = jobs[g];
+      J.second_run = false;
+      J.chunklen = chunklen;
+      J.n_quadrants = n_quadrants;
+      J.in_qname = &P.qname;
+      J.q_integer = P.integer_typed[QSTART] && P.integer_typed[QEND];
+      J.reduced_qnames = true;  // merge_rows(inpaf, rowpairs_singular, !is.null(qname))
+      compress_pre(J, take(P.t, rows_of[order[g]]));
+      run.push_back(&J);
+    }
+    compress_gpu(ctx, run);  // the all-pairs tests of every query sequence in one launch
+    int64_t total = 0;
+    for (size_t g = 0; g < order.size(); ++g) {
+      CompressJob& J = jobs[g];
+      Table out = compress_post(J);
+      if (!J.merged) {
+        J.out_qname.clear();
+        for (size_t k = 0; k < out.n(); ++k) J.out_qname.push_back(P.qname[(size_t)out.c[ROWID][k]]);
+      }
+      write_paf_file(outpaf_path, out, J.out_qname, P, J.merged, true);  // append = !is.null(qname)
+      total += (int64_t)out.n();
+    }
+    if (rows_out) *rows_out = total;
   });
 }
 

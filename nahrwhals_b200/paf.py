@@ -11,7 +11,8 @@ import numpy as np
 
 from . import _lib
 
-SYMBOLS = ["nw_paf_compress", "nw_paf_prepare", "nw_paf_prepare_many", "nw_paf_compress_file", "nw_paf_read_file",
+SYMBOLS = ["nw_paf_compress", "nw_paf_prepare", "nw_paf_prepare_many", "nw_paf_compress_file", "nw_paf_compress_file_by_qname",
+           "nw_paf_read_file",
            "nw_paf_rows", "nw_paf_columns", "nw_paf_stats", "nw_paf_free"]
 COLS = ("qlen", "qstart", "qend", "strand", "tlen", "tstart", "tend", "nmatch", "alen", "mapq")
 
@@ -32,6 +33,7 @@ def _lib_paf():
         L.nw_paf_prepare.argtypes = [vp, C.POINTER(NwPafCols), f64, f64, f64, C.POINTER(vp)]
         L.nw_paf_prepare_many.argtypes = [vp, vp, i64, f64, f64, f64, vp, vp]
         L.nw_paf_compress_file.argtypes = [vp, C.c_char_p, C.c_char_p, f64, i32, C.POINTER(i64), C.POINTER(i64)]
+        L.nw_paf_compress_file_by_qname.argtypes = [vp, C.c_char_p, C.c_char_p, f64, i32, C.POINTER(i64), C.POINTER(i64)]
         L.nw_paf_read_file.argtypes = [C.c_char_p, C.POINTER(vp)]
         L.nw_paf_rows.restype = i64
         L.nw_paf_rows.argtypes = [vp]
@@ -123,3 +125,13 @@ def read_paf(path):
     _lib.check(L.nw_paf_read_file(str(path).encode(), C.byref(h)))
     t = _table(L, h)
     return {k: t[k] for k in COLS}
+
+
+def compress_paf_file_by_qname(solver, inpaf_link, outpaf_link, chunklen=10000.0, n_quadrants_per_axis=10):
+    """The all-vs-all melt of whole-genome mode (R/make_whole_genome_list.R:80-106): every query sequence of the chunked PAF
+    melted on its own and appended to outpaf_link.  Returns (rows read, rows written)."""
+    L = _lib_paf()
+    a, b = C.c_int64(), C.c_int64()
+    _lib.check(L.nw_paf_compress_file_by_qname(solver.h, str(inpaf_link).encode(), str(outpaf_link).encode(), float(chunklen),
+                                               int(n_quadrants_per_axis or 0), C.byref(a), C.byref(b)))
+    return int(a.value), int(b.value)

@@ -143,7 +143,8 @@ def compress_paf_fnct(p, second_run=False, chunklen=10000.0, compression=None, n
     if rowpairs:
         if file_mode is not None:
             names = [file_mode["qname"][int(r)] for r in p["_row"]]
-            p = merge_rows(p, rowpairs, names=names, q_integer=file_mode["q_integer"])
+            p = merge_rows(p, rowpairs, names=names, reduced_qnames=file_mode.get("reduced", False),
+                           q_integer=file_mode["q_integer"])
             file_mode["merged"] = True
             file_mode["out_qname"] = names + [file_mode["qname"][int(r)] for r in short["_row"]]
         else:
@@ -244,25 +245,50 @@ def read_paf_file(path, dedupe=False):
     return p, qname, tname, extra, ityp
 
 
+def _write_rows(f, out, names, tname, extra, ityp, merged, qi):
+    """write.table(inpaf, quote = F, col.names = F, row.names = F, sep = '\\t') after the final strand swap."""
+    if merged:
+        ityp = dict(ityp, nmatch=False, alen=False)
+    out = swap_minus(out)
+    for k in range(len(out["qstart"])):
+        r = int(out["_row"][k])
+        cells = [names[k], r_format(out["qlen"][k], ityp["qlen"]), r_format(out["qstart"][k], qi), r_format(out["qend"][k], qi),
+                 "+" if out["strand"][k] > 0 else "-", tname[r], r_format(out["tlen"][k], ityp["tlen"]),
+                 r_format(out["tstart"][k], ityp["tstart"]), r_format(out["tend"][k], ityp["tend"]),
+                 r_format(out["nmatch"][k], ityp["nmatch"]), r_format(out["alen"][k], ityp["alen"]),
+                 r_format(out["mapq"][k], ityp["mapq"])]
+        if not merged and extra[r]:
+            cells.append(extra[r])
+        f.write("\t".join(cells) + "\n")
+
+
 def compress_paf_file(in_path, out_path, chunklen, n_quadrants_per_axis=None):
     p, qname, tname, extra, ityp = read_paf_file(in_path, dedupe=True)
     p = swap_minus(p)
     fm = dict(qname=qname, q_integer=ityp["qstart"] and ityp["qend"], merged=False, out_qname=None)
     out = compress_paf_fnct(p, second_run=False, chunklen=chunklen, n_quadrants_per_axis=n_quadrants_per_axis, file_mode=fm)
     names = fm["out_qname"] if fm["merged"] else [qname[int(r)] for r in out["_row"]]
-    if fm["merged"]:
-        ityp = dict(ityp, nmatch=False, alen=False)
-    out = swap_minus(out)
-    qi = fm["q_integer"]
     with open(out_path, "w") as f:
-        for k in range(len(out["qstart"])):
-            r = int(out["_row"][k])
-            cells = [names[k], r_format(out["qlen"][k], ityp["qlen"]), r_format(out["qstart"][k], qi), r_format(out["qend"][k], qi),
-                     "+" if out["strand"][k] > 0 else "-", tname[r], r_format(out["tlen"][k], ityp["tlen"]),
-                     r_format(out["tstart"][k], ityp["tstart"]), r_format(out["tend"][k], ityp["tend"]),
-                     r_format(out["nmatch"][k], ityp["nmatch"]), r_format(out["alen"][k], ityp["alen"]),
-                     r_format(out["mapq"][k], ityp["mapq"])]
-            if not fm["merged"] and extra[r]:
-                cells.append(extra[r])
-            f.write("\t".join(cells) + "\n")
+        _write_rows(f, out, names, tname, extra, ityp, fm["merged"], fm["q_integer"])
     return len(qname), len(names)
+
+
+def compress_paf_file_by_qname(in_path, out_path, chunklen, n_quadrants_per_axis=10):
+    """The loop of R/make_whole_genome_list.R:80-106: chunk suffix stripped from qname, strand swap, then per query sequence
+    compress_paf_fnct(inpaf_df = paf, outpaf_link, qname = q) -- reduced_qnames, appended to the output file."""
+    import re
+    p, qname, tname, extra, ityp = read_paf_file(in_path, dedupe=False)
+    qname = [re.sub(r"_[0-9]+-[0-9]+$", "", q) for q in qname]
+    p = swap_minus(p)
+    order = list(dict.fromkeys(qname))
+    total = 0
+    with open(out_path, "a") as f:
+        for q in order:
+            sel = np.array([k for k in range(len(qname)) if qname[k] == q], dtype=np.int64)
+            fm = dict(qname=qname, q_integer=ityp["qstart"] and ityp["qend"], merged=False, out_qname=None, reduced=True)
+            out = compress_paf_fnct(take(p, sel), second_run=False, chunklen=chunklen, n_quadrants_per_axis=n_quadrants_per_axis,
+                                    file_mode=fm)
+            names = fm["out_qname"] if fm["merged"] else [qname[int(r)] for r in out["_row"]]
+            _write_rows(f, out, names, tname, extra, ityp, fm["merged"], fm["q_integer"])
+            total += len(names)
+    return len(qname), total

@@ -239,3 +239,52 @@ def test_gpu_paf_file_mode_matches_oracle(solver, tmp_path, seed):
     O = po.read_paf_file(str(fo))[0]
     for k in po.COLS:
         assert np.array_equal(T[k], O[k]), k
+
+
+def write_multi_qname_paf(path, tables, names):
+    """A chunked all-vs-all PAF: several query sequences, chunk qnames <seq>_<start>-<end>, rows interleaved."""
+    lines = []
+    for p, nm in zip(tables, names):
+        for k in range(len(p["qstart"])):
+            f = ["%s_%d-%d" % (nm, int(p["qstart"][k]), int(p["qend"][k]) - 1), int(p["qlen"][k]), int(p["qstart"][k]),
+                 int(p["qend"][k]), "+" if p["strand"][k] > 0 else "-", "chr%d" % (1 + k % 2), int(p["tlen"][k]),
+                 int(p["tstart"][k]), int(p["tend"][k]), int(p["nmatch"][k]), int(p["alen"][k]), int(p["mapq"][k])]
+            lines.append("\t".join(str(v) for v in f))
+    order = np.random.default_rng(len(lines)).permutation(len(lines))
+    open(path, "w").write("\n".join(lines[k] for k in order) + "\n")
+
+
+def test_oracle_qname_mode(tmp_path):
+    """Per query sequence: rows of other sequences never merge, names lose the chunk suffix and stay reduced, output appended."""
+    n = 6
+    mk = lambda off: dict(qlen=np.full(n, 10000.0), qstart=10000.0 * np.arange(n), qend=10000.0 * (np.arange(n) + 1),  # noqa: E731
+                          strand=np.ones(n), tlen=np.full(n, 5e6), tstart=off + 10000.0 * np.arange(n),
+                          tend=off + 10000.0 * (np.arange(n) + 1), nmatch=np.full(n, 9990.0), alen=np.full(n, 10000.0),
+                          mapq=np.full(n, 60.0))
+    write_multi_qname_paf(tmp_path / "in.paf", [mk(100000), mk(100000)], ["ctgA", "ctg_B"])   # identical coordinates
+    (tmp_path / "out.paf").write_text("previous line\n")
+    nin, nout = po.compress_paf_file_by_qname(str(tmp_path / "in.paf"), str(tmp_path / "out.paf"), 10000.0)
+    lines = (tmp_path / "out.paf").read_text().strip().split("\n")
+    assert (nin, nout) == (12, 2) and lines[0] == "previous line" and len(lines) == 3
+    assert sorted(ln.split("\t")[0] for ln in lines[1:]) == ["ctgA", "ctg_B"]
+    assert all(ln.split("\t")[2:4] == ["0", "60000"] for ln in lines[1:])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(4))
+def test_gpu_paf_qname_mode_matches_oracle(solver, tmp_path, seed):
+    import nahrwhals_b200 as nb
+    rng = np.random.default_rng(900 + seed)
+    tabs = [chunked_paf(rng, n_segments=int(rng.integers(1, 10)), chunk=10000, jitter=int(rng.choice([0, 2, 30])),
+                        span=int(rng.choice([300000, 900000])), drop=float(rng.choice([0.0, 0.1])),
+                        extra=int(rng.integers(0, 5))) for _ in range(int(rng.integers(1, 7)))]
+    if seed == 1:
+        tabs.append({k: v[:1] for k, v in tabs[0].items()})            # a query sequence with one alignment
+    names = ["h1tg%06dl" % k if k % 2 else "contig_%d" % k for k in range(len(tabs))]
+    fin, fo, fg = tmp_path / "in.paf", tmp_path / "oracle.paf", tmp_path / "gpu.paf"
+    write_multi_qname_paf(fin, tabs, names)
+    want = po.compress_paf_file_by_qname(str(fin), str(fo), 10000.0, 10)
+    got = nb.compress_paf_file_by_qname(solver, fin, fg, 10000.0, 10)
+    assert got == want and fg.read_text() == fo.read_text()
+    assert nb.compress_paf_file_by_qname(solver, fin, fg, 10000.0, 10) == want       # appended, not truncated
+    assert fg.read_text() == fo.read_text() * 2
