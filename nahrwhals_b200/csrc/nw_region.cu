@@ -153,7 +153,7 @@ nw_table* format_solver_result(const nw_result* res, const double* gl, int n_gl)
 void prepass_gpu(nw_ctx* ctx, std::vector<PrepassOut*>& Ps, int flags, int& launches) {
   std::vector<PrepassOut*> live;
   for (PrepassOut* P : Ps)
-    if (!P->cluttered) live.push_back(P);
+    if (!P->cluttered && !P->trivial) live.push_back(P);
   if (live.empty()) return;
   if (live.size() > 60000) rfail(NW_ERR_ARG, "too many regions in one pre-pass batch");
   const int L0 = nw::ctx_launches(ctx);

@@ -580,6 +580,7 @@ struct PrepassOut {
   std::unique_ptr<nw_table> table;
   Grid g0, flipped;
   bool did_flip = false, unsure = false, cluttered = false;
+  bool trivial = false;  // 1 x 1 gridmatrix: calc_coarse_grained_aln_score returns 100, there is nothing to search
   std::vector<Move> moves;  // find_sv_opportunities of the flipped matrix
   int64_t n_cand = 0, n_dp = 0;
   int maxdepth = 1;
@@ -597,7 +598,10 @@ struct PrepassOut {
 
 Grid make_grid(const int64_t* grid, int n_x, int n_y, const int64_t* len_x, const int64_t* len_y) {
   if (!grid || !len_x || !len_y) rfail(NW_ERR_ARG, "null argument");
-  if (n_x < 2 || n_y < 2) rfail(NW_ERR_ARG, "the gridmatrix needs at least 2 x 2 blocks");
+  // 1 x 1 (one clean alignment: the region carries no SD) is the reference's "report 100%" case (R/evaltools.R:100-101);
+  // a single row or column with several blocks is not reproduced (R drops such matrices to vectors inside
+  // carry_out_compressed_sv, R/seqmodder.R, and the outcome depends on cbind's recycling)
+  if ((n_x < 2 || n_y < 2) && !(n_x == 1 && n_y == 1)) rfail(NW_ERR_ARG, "the gridmatrix needs at least 2 x 2 blocks (or 1 x 1)");
   if (n_x > 16000 || n_y > 16000) rfail(NW_ERR_ARG, "gridmatrix too large");
   Grid g;
   g.nx = n_x;
@@ -657,6 +661,18 @@ void prepass_prepare(PrepassOut& P, Grid&& g0in) {
     finish_table(T);
     return;
   }
+  if (P.g0.nx == 1 && P.g0.ny == 1) {  // dfs: ref node only, eval 100 (R/evaltools.R:100-101); no SV opportunities
+    P.trivial = true;
+    P.flipped = P.g0;
+    if (P.flipped.v[0] < 0) {  // flip_bitl_y_if_needed: one row, negative -> -bitl (:68-69)
+      P.flipped.v[0] = -P.flipped.v[0];
+      P.did_flip = true;
+    }
+    P.maxdepth = 1;
+    add_row(T, 100.0, "ref");
+    finish_table(T);
+    return;
+  }
   P.flipped = flip_if_needed(P.g0, P.did_flip, P.unsure);
   const Grid& g = P.flipped;
   P.moves = find_sv_opportunities(g);
@@ -711,7 +727,7 @@ void prepass_prepare(PrepassOut& P, Grid&& g0in) {
 // Phase 3 (host): replay of dfsutil's sequential part (R/dfs_machinery.R:79-246) over the per-child numbers, then
 // sort_new_by_penalised, transform_res_new_to_old, annotate_res_out_with_positions_lens.
 void prepass_replay(PrepassOut& P, const nw_region_opts& o) {
-  if (P.cluttered) return;
+  if (P.cluttered || P.trivial) return;
   nw_table& T = *P.table;
   const Grid& g = P.flipped;
   const size_t nc = P.cand.size();

@@ -51,7 +51,7 @@ int hr_region(const int64_t* grid, int nx, int ny, const int64_t* lx, const int6
     nw_region_opts o{depth, maxdup, init_width, minreport, compression, 0, 0};
     PrepassOut P;
     prepass_prepare(P, make_grid(grid, nx, ny, lx, ly));
-    if (!P.cluttered) {
+    if (!P.cluttered && !P.trivial) {
       if (n_entries != (int64_t)P.cand.size() + 1) return 3;
       for (int64_t k = 0; k < n_entries; ++k) {
         P.srow[k] = srow[k];

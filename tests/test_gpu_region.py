@@ -244,3 +244,22 @@ def test_rtwin_corridor_scores_large_shapes(solver, oracle, shape):
             assert np.array_equal(tot, otot.astype(np.int64))
             reach = ~np.isinf(ocost)
             assert np.array_equal(sc[reach], osc[reach])
+
+
+@pytest.mark.gpu
+def test_single_block_region(solver):
+    """1 x 1 gridmatrix (one clean alignment): 'ref' at 100 %, no solver; alone and inside a batch."""
+    import nahrwhals_b200 as nb
+    one = (np.array([[-300000]]), np.array([300000]), np.array([300000]), np.array([0.0, 300000.0]))
+    R = nb.analyse_region(solver, *one, depth=3)
+    assert (R.res_ref, R.res_max, R.n_res_max, R.mut_max, R.solver_called) == (100.0, 100.0, 1, "ref", False)
+    assert R.rows == [dict(eval=100.0, mut1="ref", mut1_start=None, mut1_end=None, mut1_pos_pm=None, mut1_len=None,
+                           mut1_len_pm=None, mut2_len=None, mut2_len_pm=None, mut3_len=None, mut3_len_pm=None)]
+    from nahrwhals_b200.sdgrid import sdgrid
+    mat, lx, ly, _ = sdgrid(16, [3, 2], chain_depth=2, seed=5)
+    other = (mat, ly, lx, np.concatenate([[0], np.cumsum(lx)]))
+    out = nb.analyse_regions(solver, [other, one, other], depth=2)
+    assert out[1].rows == R.rows and out[0].rows == out[2].rows == nb.analyse_region(solver, *other, depth=2).rows
+    with pytest.raises(Exception):
+        nb.analyse_region(solver, np.array([[5000, 0, 3000]]), np.array([5000]), np.array([5000, 2000, 3000]),
+                          np.array([0.0, 5000, 7000, 10000]))

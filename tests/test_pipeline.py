@@ -54,6 +54,8 @@ def test_empty_row_matches_oracle():
 def test_gpu_pipeline_matches_oracle_chain(solver, oracle, tmp_path):
     import nahrwhals_b200 as nb
     pafs = [sd_paf(s, n_blocks=int(12 + 4 * (s % 4))) for s in range(8)]        # seed 3 is a cluttered PAF
+    from nahrwhals_b200.sdgrid import matrix_to_chunked_paf
+    pafs.insert(5, matrix_to_chunked_paf(np.array([[250000]]), np.array([250000]), np.array([250000])))  # one clean alignment
     pafs.append({k: np.zeros(0) for k in pafs[0]})                                # no alignment: dropped
     metas = [dict(chr="chr%d" % (k + 1), start=str(100000 * k), end=str(100000 * k + 400000), samplename="x_y")
              for k in range(len(pafs))]
@@ -61,7 +63,8 @@ def test_gpu_pipeline_matches_oracle_chain(solver, oracle, tmp_path):
     rows, det = nb.run_regions(solver, pafs, metas, depth=2, minlen=1000.0, compression=1000.0, chunklen=10000.0, logfile=f)
     want = [oracle_row(oracle, p, m, 2, 1000.0, 1000.0, 10000.0) for p, m in zip(pafs, metas)]
     assert rows == want
-    assert rows[-1] is None and sum(r is not None for r in rows) == 8
+    assert rows[-1] is None and sum(r is not None for r in rows) == 9
+    assert rows[5].split("\t")[9:13] == ["100", "100", "1", "ref"]     # a 1 x 1 gridmatrix: 100 % in reference state
     assert any(b.status == "cluttered" for b, _ in det) and any(r is not None and r.solver_called for _, r in det)
     lines = f.read_text().split("\n")
     assert lines[0] == "\t".join(ro.LOG_COLUMNS) and lines[1:-1] == [r for r in rows if r is not None]

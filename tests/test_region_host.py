@@ -164,3 +164,16 @@ def test_host_flow_random_regions(HR, oracle, seed):
     n_x, n_y = [(6, 5), (9, 8), (14, 9), (12, 14), (16, 12)][seed % 5]
     mat, lx, ly = random_grid(n_x, n_y, 0.25, seed)
     check_region_host(HR, oracle, mat, ly, lx, depth=2, init_width=100)
+
+
+def test_host_flow_single_block(HR, oracle):
+    """A region with one clean alignment grids to a 1 x 1 matrix: the reference reports 100 % for 'ref' and never calls the
+    solver (R/evaltools.R:100-101); a single row or column with several blocks stays rejected (see nw_region_host.h)."""
+    for v in (250000, -250000):
+        mat = np.array([[v]], dtype=np.int64)
+        O, S = check_region_host(HR, oracle, mat, np.array([250000]), np.array([250000]), depth=3)
+        assert (S.res_ref, S.res_max, S.n_res_max, O["mut_max"]) == (100.0, 100.0, 1, "ref") and not S.solver_called
+        assert (S.search_depth, S.mut_simulated) == (1, 1)
+    numbers = tuple(np.zeros(1, t) for t in (np.int64, np.int64, np.int64, np.int64, np.float64))
+    rc = run_host(HR, np.array([[5000, 0, 3000]]), [5000], [5000, 2000, 3000], [0, 5000, 7000, 10000], {}, numbers, None)[0]
+    assert rc == -1
