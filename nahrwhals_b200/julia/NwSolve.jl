@@ -179,4 +179,38 @@ function paf_to_bitlocus(ctx::Context, paf; minlen::Float64, compression::Float6
      minlen = info[].minlen, compression = info[].compression, passes = Int(info[].passes))
 end
 
+# ---- regionfile mode from the alignments on, one call (include/nwpipeline.h)
+struct NwLogMeta                   # struct nw_log_meta
+    chr::Cstring; start::Cstring; stop::Cstring; samplename::Cstring
+    y_seqname::Cstring; y_start::Cstring; y_end::Cstring; xpad::Cstring
+    compression::Float64
+    exceeds_x::Int32; exceeds_y::Int32; grid_inconsistency::Int32
+end
+
+"pafs: vector of PAF tables (as in paf_to_bitlocus); metas: vector of NamedTuples (chr, start, stop, samplename[, xpad]) of
+strings.  Returns the rows of nahrwhals_res.tsv (nothing for a dropped region); logfile: also appended there."
+function run_regions(ctx::Context, pafs::Vector, metas::Vector; minlen::Float64, compression::Float64,
+                     chunklen::Float64 = 10000.0, depth::Integer = 3, maxdup::Integer = 2, init_width::Float64 = 1000.0,
+                     minreport::Float64 = 0.98, logfile::Union{Nothing,String} = nothing)
+    n = length(pafs)
+    cols = [[Vector{Float64}(p[k]) for k in (:qlen, :qstart, :qend, :strand, :tlen, :tstart, :tend, :nmatch, :alen, :mapq)] for p in pafs]
+    strs = [[String(m.chr), String(m.start), String(m.stop), String(m.samplename), String(get(m, :xpad, "1"))] for m in metas]
+    text = Ref{Ptr{UInt8}}(C_NULL); len = Ref{Int64}(0)
+    off = Vector{Int64}(undef, n + 1); st = Vector{Int32}(undef, max(n, 1))
+    GC.@preserve cols strs begin
+        pc = [NwPafCols(map(pointer, c)..., length(c[1])) for c in cols]
+        pm = [NwLogMeta(pointer(s[1]), pointer(s[2]), pointer(s[3]), pointer(s[4]), C_NULL, C_NULL, C_NULL, pointer(s[5]),
+                        NaN, 0, 0, 0) for s in strs]
+        bp = Ref(NwBitlocusParams(minlen, compression, chunklen, 150, 250, 2000, 64))
+        ro = Ref(NwRegionOpts(depth, maxdup, init_width, minreport, compression, 0, 0))
+        check(ccall((:nw_regions_run, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{NwPafCols}, Ptr{NwLogMeta}, Int64, Ref{NwBitlocusParams}, Ref{NwRegionOpts}, Cstring,
+                     Ref{Ptr{UInt8}}, Ref{Int64}, Ptr{Int64}, Ptr{Int32}),
+                    ctx.h, pc, pm, n, bp, ro, logfile === nothing ? C_NULL : logfile, text, len, off, st))
+    end
+    blob = unsafe_string(text[], len[])
+    ccall((:nw_free, LIB), Cvoid, (Ptr{Cvoid},), text[])
+    [st[k] >= 0 ? chomp(blob[off[k]+1:off[k+1]]) : nothing for k in 1:n]
+end
+
 end # module
