@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(128, NW_DP_MINB) k_score_fast(ScoreArgs A) {
   constexpr bool RTREG = (W <= NW_RTREG_MAX);  // rt window in registers (LDS.128) vs predicated scalar LDS per cell
   constexpr int RTW = RTREG ? W : 4;
   // uint32 words per band row, everything the row loop needs ready-made (no unpacking on the ALU pipe):
-  //   r0 (window start in reversed columns), byte offset of the 16-B aligned rt window, sb | extra << 8, masks
+  //   r0 (window start in reversed columns), byte offset of the 16-B aligned rt window, sb, masks
   constexpr int BROW = 3 + NWORD;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128, NW_DP_MINB) k_score_fast(ScoreArgs A) {
       brow[i * BROW] = (uint32_t)r0;
       // rt of the window columns: 4 shifted copies of rt_rev make the window start 16-B aligned for LDS.128
       brow[i * BROW + 1] = (uint32_t)(((r0 & 3) * rt_stride + (r0 & ~3)) * 4);
-      brow[i * BROW + 2] = (uint32_t)min(sb, 2) | ((uint32_t)max(sb - 2, 0) << 8);
+      brow[i * BROW + 2] = (uint32_t)sb;  // 0 / 1 / 2 = the row step's shift; > 2: sb - 2 single shifts first, then step<2>
 #pragma unroll
       for (int t = 0; t < NWORD; ++t) brow[i * BROW + 3 + t] = mk_t[(size_t)i * 4 + t];
     }
@@ -135,24 +135,25 @@ __global__ void __launch_bounds__(128, NW_DP_MINB) k_score_fast(ScoreArgs A) {
         rtr[4 * g + 3] = v.w;
       }
     }
-    if (sbw >> 8) {  // rare: window moved by more than two columns (first rows of steep corridors)
-      for (int e = sbw >> 8; e > 0; --e) dp_row_shift1<W>(S);
-    }
-    const int sb = sbw & 3;
+    // the common shifts first: one compare + branch each, no unpacking of the band word
     if (RTREG) {
-      if (sb == 0)
-        dp_row_step<W, 0>(S, m, up, rtr);
-      else if (sb == 1)
+      if (sbw == 1) {
         dp_row_step<W, 1>(S, m, up, rtr);
-      else
+      } else if (sbw == 0) {
+        dp_row_step<W, 0>(S, m, up, rtr);
+      } else {
+        for (int e = (int)sbw - 2; e > 0; --e) dp_row_shift1<W>(S);  // rare: first rows of steep corridors
         dp_row_step<W, 2>(S, m, up, rtr);
+      }
     } else {
-      if (sb == 0)
-        dp_row_step<W, 0>(S, m, up, rtw);
-      else if (sb == 1)
+      if (sbw == 1) {
         dp_row_step<W, 1>(S, m, up, rtw);
-      else
+      } else if (sbw == 0) {
+        dp_row_step<W, 0>(S, m, up, rtw);
+      } else {
+        for (int e = (int)sbw - 2; e > 0; --e) dp_row_shift1<W>(S);
         dp_row_step<W, 2>(S, m, up, rtw);
+      }
     }
   }
   const int total = sumup + sum_rt;
