@@ -1054,6 +1054,20 @@ struct Search {
     uint32_t* sel = (uint32_t*)c->sel.ensure((size_t)std::max<uint32_t>(nvalid, 1) * 4, true);
     if (o.maxwidth < 0) {
       c->launches += launch_compact_ranks(flag, pre, n, sel, s);  // region-major already (candidates follow parents)
+    } else if (R == 1 && o.maxwidth >= 1 && (int64_t)nvalid > o.maxwidth && nvalid > 2048 && !getenv("NW_NO_TOPK")) {
+      // beam search of one region: the width-th best score from a histogram, only the winners are sorted
+      const uint32_t wsel = (uint32_t)o.maxwidth;
+      uint32_t npad = 2048;
+      while (npad < wsel) npad <<= 1;
+      uint64_t* keys = (uint64_t*)c->keys.ensure((size_t)npad * 8, true);
+      uint32_t* hist = (uint32_t*)c->hist.ensure((size_t)100008 * 4, true);
+      // flag is consumed (the valid flags are no longer needed), pre becomes the tie ranks
+      c->launches += launch_topk_keys(Lr.k3.as<int32_t>(), n, wsel, hist, hist + 100001, flag, pre, bsum, (uint32_t*)(misc + 7),
+                                      keys, npad, s);
+      uint32_t* seg = (uint32_t*)c->gather.ensure((size_t)(3 * R + 3) * 4, true);
+      const uint32_t pack[3] = {0u, wsel, 0u};
+      h2d(c, seg, pack, sizeof pack);
+      c->launches += launch_take_sorted(keys, wsel, seg, seg + 1, seg + 2, sel, s);
     } else if (nvalid) {
       uint64_t npad = 2048;
       while (npad < nvalid) npad <<= 1;

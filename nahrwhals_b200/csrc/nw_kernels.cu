@@ -981,6 +981,76 @@ __global__ void k_keys_to_sel(const uint64_t* keys, uint32_t n, uint32_t* sel) {
   if (t < n) sel[t] = (uint32_t)(keys[t] & 0xffffffffu);
 }
 
+__global__ void k_k3_hist(const int32_t* k3, uint32_t n, int k3_floor, uint32_t* hist);
+// ---- top-w of one region without sorting everything: the w-th best k3 from a histogram, then only the w winners are
+// sorted.  The stable order of solver.jl:669-672 is (score descending, discovery rank ascending), so the frontier is
+// every candidate above the threshold score plus the first `quota` candidates (in discovery order) that tie with it.
+constexpr int TOPK_CH = 98;  // bins per thread of the single-CTA threshold search (1024 x 98 >= 100001)
+// thr[0] = threshold k3, thr[1] = quota of the tie bin, thr[2] = candidates above the threshold, thr[3] = 0 (append cursor)
+__global__ void __launch_bounds__(1024) k_topk_threshold(const uint32_t* __restrict__ hist, uint32_t w, uint32_t* __restrict__ thr) {
+  __shared__ uint32_t sh[33];
+  const int t = threadIdx.x;
+  const int hi = 100000 - t * TOPK_CH;  // this thread's bins, descending: hi .. max(hi - TOPK_CH + 1, 0)
+  uint32_t sum = 0;
+  for (int b = hi; b > hi - TOPK_CH && b >= 0; --b) sum += hist[b];
+  uint32_t total;
+  const uint32_t before = block_excl_scan(sum, sh, total);
+  if (before < w && w <= before + sum) {
+    uint32_t cum = before;
+    for (int b = hi; b > hi - TOPK_CH && b >= 0; --b) {
+      const uint32_t h = hist[b];
+      if (cum + h >= w) {
+        thr[0] = (uint32_t)b;
+        thr[1] = w - cum;
+        thr[2] = cum;
+        thr[3] = 0;
+        break;
+      }
+      cum += h;
+    }
+  }
+}
+__global__ void k_topk_tie_flags(const int32_t* __restrict__ k3, uint32_t n, const uint32_t* __restrict__ thr,
+                                 uint32_t* __restrict__ flag) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) flag[r] = k3[r] == (int32_t)thr[0] ? 1u : 0u;
+}
+// keys of the w winners (same key as k_make_keys, region 0) + padding up to npad; winners above the threshold are
+// appended in any order (the sort orders them), the ties take their discovery rank inside the tie bin
+__global__ void k_topk_keys(const int32_t* __restrict__ k3, uint32_t n, uint32_t* __restrict__ thr,
+                            const uint32_t* __restrict__ tie_rank, uint32_t w, uint64_t* __restrict__ keys, uint32_t npad) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < npad - w) keys[w + r] = ~0ull;
+  if (r >= n) return;
+  const int32_t v = k3[r], T = (int32_t)thr[0];
+  if (v < T) return;
+  uint32_t pos;
+  if (v > T) {
+    pos = atomicAdd(&thr[3], 1u);
+  } else {
+    if (tie_rank[r] >= thr[1]) return;
+    pos = thr[2] + tie_rank[r];
+  }
+  keys[pos] = ((uint64_t)(uint32_t)(100000 - v) << 31) | r;
+}
+// keys[0..npad) <- the w best of k3[0..n) in frontier order (ascending key), npad a power of two >= max(w, 2048);
+// needs more than w valid candidates.  hist: 100001 words, thr: 4 words, flag / tie_rank: n words
+int launch_topk_keys(const int32_t* k3, uint32_t n, uint32_t w, uint32_t* hist, uint32_t* thr, uint32_t* flag, uint32_t* tie_rank,
+                     uint32_t* bsum_scratch, uint32_t* total_out, uint64_t* keys, uint32_t npad, cudaStream_t st) {
+  int l = 0;
+  cudaMemsetAsync(hist, 0, (size_t)100001 * 4, st);
+  k_k3_hist<<<(n + 255) / 256, 256, 0, st>>>(k3, n, 0, hist);
+  k_topk_threshold<<<1, 1024, 0, st>>>(hist, w, thr);
+  k_topk_tie_flags<<<(n + 255) / 256, 256, 0, st>>>(k3, n, thr, flag);
+  l += 3;
+  l += launch_scan(flag, tie_rank, n, bsum_scratch, total_out, st);
+  const uint32_t cover = n > npad ? n : npad;
+  k_topk_keys<<<(cover + 255) / 256, 256, 0, st>>>(k3, n, thr, tie_rank, w, keys, npad);
+  ++l;
+  l += launch_sort_u64(keys, npad, st);
+  return l;
+}
+
 int launch_valid_flags(const int32_t* k3, uint32_t n, uint32_t* flag, cudaStream_t st) {
   if (!n) return 0;
   k_valid_flags<<<(n + 255) / 256, 256, 0, st>>>(k3, n, flag);

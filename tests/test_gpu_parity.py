@@ -127,6 +127,10 @@ CASES = [
     ("sd64_d2", dict(n_x=64, families=[10, 9, 8, 8, 7], seed=1, chain_depth=3), dict(maxdepth=2, maxdup=2)),
     ("sd150_w100", dict(n_x=150, families=[6, 5, 4, 4, 3], seed=7, chain_depth=4),
      dict(maxdepth=4, maxdup=2, maxwidth=100)),
+    # beam of 1 000 out of >100 000 candidates per level (the bench's S150 workload): histogram threshold selection
+    ("sd150_w1000", dict(n_x=150, families=[6, 5, 4, 4, 3], seed=7, chain_depth=4),
+     dict(maxdepth=4, maxdup=2, maxwidth=1000)),
+    ("sd64_w300", dict(n_x=64, families=[6, 5, 5, 4], seed=3, chain_depth=3), dict(maxdepth=3, maxdup=2, maxwidth=300)),
     ("sd30_dup0", dict(n_x=30, families=[4, 4, 3], seed=5, chain_depth=2), dict(maxdepth=3, maxdup=0, maxwidth=1000)),
     ("sd30_dup3_w7", dict(n_x=30, families=[5, 4], seed=6, chain_depth=3), dict(maxdepth=5, maxdup=3, maxwidth=7)),
 ]
