@@ -33,6 +33,14 @@ int nw_regions_run(nw_ctx* ctx, const nw_paf_cols* pafs, const nw_log_meta* meta
                    const nw_bitlocus_params* bp, const nw_region_opts* ropts, const char* logfile, char** rows,
                    int64_t* rows_len, int64_t* row_off, int32_t* status);
 
+/* nw_regions_run_ctxs with the alignments read from PAF files (12 columns + optional tags, as minimap2 / the melt step
+ * write them): paf_paths[k] is read like the read.table(inpaf) of load_and_prep_paf_for_gridplot_transform
+ * (R/tsv_to_bitlocus.R:17).  A region whose file cannot be read or parsed is dropped (status[k] = NW_ERR_IO /
+ * NW_ERR_PARSE), the others run. */
+int nw_regions_run_files(nw_ctx** ctxs, int32_t n_ctx, const char* const* paf_paths, const nw_log_meta* metas, int64_t n,
+                         const nw_bitlocus_params* bp, const nw_region_opts* ropts, int32_t regions_per_batch,
+                         const char* logfile, char** rows, int64_t* rows_len, int64_t* row_off, int32_t* status);
+
 /* The same over n_ctx contexts (one host thread + CUDA stream each; on one GPU -- the host phases of one batch overlap
  * the device phases of another -- or on several GPUs): batches of regions_per_batch (<= 0: 512) regions are handed out
  * dynamically; rows come back (and reach the logfile) in region order.  Results identical to nw_regions_run. */

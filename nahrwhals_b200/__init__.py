@@ -10,6 +10,6 @@ from .region import solve_mutation_depth1, format_julia_output, analyse_region, 
 from .grid import build_grids, paf_to_gridmatrix, GridResult  # noqa: F401
 from . import bitlocus, grid, paf, region  # noqa: F401
 from .bitlocus import paf_to_bitlocus, auto_params  # noqa: F401
-from .pipeline import run_regions, run_regions_native  # noqa: F401
+from .pipeline import run_regions, run_regions_native, run_region_files  # noqa: F401
 from .paf import compress_paf, load_and_prep_paf, load_and_prep_pafs, compress_paf_file, compress_paf_file_by_qname, read_paf  # noqa: F401
 from .sdgrid import sdgrid, to_solver_inputs, write_tsvs, matrix_to_alignments  # noqa: F401

@@ -246,3 +246,63 @@ extern "C" int nw_regions_run_ctxs(nw_ctx** ctxs, int32_t n_ctx, const nw_paf_co
   *rows_len = (int64_t)text.size();
   return NW_OK;
 }
+
+extern "C" int nw_regions_run_files(nw_ctx** ctxs, int32_t n_ctx, const char* const* paf_paths, const nw_log_meta* metas,
+                                    int64_t n, const nw_bitlocus_params* bp, const nw_region_opts* ropts,
+                                    int32_t regions_per_batch, const char* logfile, char** rows, int64_t* rows_len,
+                                    int64_t* row_off, int32_t* status) {
+  if (rows) *rows = nullptr;
+  if (rows_len) *rows_len = 0;
+  if (!ctxs || n_ctx < 1 || !rows || !rows_len || n < 0 || (n > 0 && (!paf_paths || !metas))) {
+    nw::set_last_error("null argument");
+    return NW_ERR_ARG;
+  }
+  // read.table(inpaf) of every region; the regions that could be read run as one batch
+  struct Tab {
+    std::vector<double> c[10];
+  };
+  std::vector<Tab> tabs((size_t)n);
+  std::vector<int32_t> st((size_t)n, NW_OK);
+  std::vector<int64_t> idx;
+  std::vector<nw_paf_cols> cols;
+  std::vector<nw_log_meta> ms;
+  for (int64_t k = 0; k < n; ++k) {
+    nw_paf_table* t = nullptr;
+    const int rc = nw_paf_read_file(paf_paths[k], &t);
+    if (rc != NW_OK) {
+      st[k] = rc;
+      continue;
+    }
+    const size_t m = (size_t)nw_paf_rows(t);
+    Tab& T = tabs[k];
+    for (auto& v : T.c) v.resize(m);
+    nw_paf_columns(t, T.c[0].data(), T.c[1].data(), T.c[2].data(), T.c[3].data(), T.c[4].data(), T.c[5].data(), T.c[6].data(),
+                   T.c[7].data(), T.c[8].data(), T.c[9].data());
+    nw_paf_free(t);
+    idx.push_back(k);
+    cols.push_back(nw_paf_cols{T.c[0].data(), T.c[1].data(), T.c[2].data(), T.c[3].data(), T.c[4].data(), T.c[5].data(),
+                               T.c[6].data(), T.c[7].data(), T.c[8].data(), T.c[9].data(), (int64_t)m});
+    ms.push_back(metas[k]);
+  }
+  const int64_t m = (int64_t)idx.size();
+  std::vector<int64_t> off((size_t)m + 1, 0);
+  std::vector<int32_t> sub((size_t)std::max<int64_t>(m, 1), NW_OK);
+  char* text = nullptr;
+  int64_t len = 0;
+  const int rc = nw_regions_run_ctxs(ctxs, n_ctx, cols.data(), ms.data(), m, bp, ropts, regions_per_batch, logfile, &text, &len,
+                                     off.data(), sub.data());
+  if (rc != NW_OK) return rc;
+  for (int64_t q = 0; q < m; ++q) st[idx[q]] = sub[q];
+  if (row_off) {  // the dropped regions own an empty range
+    int64_t q = 0;
+    for (int64_t k = 0; k < n; ++k) {
+      row_off[k] = off[q];
+      if (q < m && idx[q] == k) ++q;
+    }
+    row_off[n] = off[m];
+  }
+  if (status) memcpy(status, st.data(), (size_t)n * sizeof(int32_t));
+  *rows = text;
+  *rows_len = len;
+  return NW_OK;
+}

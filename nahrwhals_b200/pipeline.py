@@ -17,7 +17,7 @@ from .bitlocus import NwBitlocusParams, _lib_bitlocus, auto_params, paf_to_bitlo
 from .paf import NwPafCols, _cols
 from .region import (NwLogMeta, NwRegionSummary, _lib_region, _opts, analyse_regions, append_logfile)
 
-SYMBOLS = ["nw_regions_run", "nw_regions_run_ctxs"]
+SYMBOLS = ["nw_regions_run", "nw_regions_run_ctxs", "nw_regions_run_files"]
 
 
 def _empty_row(meta, depth, cluttered):
@@ -148,6 +148,41 @@ def run_regions_native(solver, pafs, metas, minlen, compression, chunklen=10000.
                                     off.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p)))
     if timing is not None:
         timing["native_s"] = time.perf_counter() - t0
+    try:
+        blob = C.string_at(text, tlen.value).decode()
+    finally:
+        L.nw_free(text)
+    rows = [blob[off[k]:off[k + 1]].rstrip("\n") if st[k] >= 0 else None for k in range(n)]
+    return rows, st[:n].tolist()
+
+
+def run_region_files(solver, paf_paths, metas, minlen, compression, chunklen=10000.0, depth=3, maxdup=2, init_width=1000,
+                     minreport=0.98, max_n_alns=150, max_size_col_plus_rows=250, logfile=None, regions_per_batch=512):
+    """run_regions_native with every region's alignments read from its PAF file (nw_regions_run_files): the regionfile mode
+    of the reference from the files minimap2 / the melt step left behind to the rows of nahrwhals_res.tsv."""
+    L = _lib_bitlocus()
+    _lib_region()
+    L.nw_regions_run_files.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(NwBitlocusParams),
+                                       C.c_void_p, C.c_int32, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p,
+                                       C.c_void_p]
+    L.nw_free.argtypes = [C.c_void_p]
+    solvers = list(solver) if isinstance(solver, (list, tuple)) else [solver]
+    n = len(paf_paths)
+    keep = []
+    paths = (C.c_char_p * max(n, 1))(*[str(p).encode() for p in paf_paths])
+    ms = (NwLogMeta * max(n, 1))()
+    for k in range(n):
+        ms[k] = _meta(metas[k], keep)
+    bp = NwBitlocusParams(float(minlen), float(compression), float(chunklen), int(max_n_alns), int(max_size_col_plus_rows),
+                          2000, 64)
+    ro = _opts(L, depth, maxdup, init_width, minreport, compression)
+    hs = (C.c_void_p * len(solvers))(*[s_.h for s_ in solvers])
+    text, tlen = C.c_void_p(), C.c_int64()
+    off = np.zeros(n + 1, np.int64)
+    st = np.zeros(max(n, 1), np.int32)
+    _lib.check(L.nw_regions_run_files(hs, len(solvers), paths, ms, n, C.byref(bp), C.byref(ro), int(regions_per_batch),
+                                      None if logfile is None else str(logfile).encode(), C.byref(text), C.byref(tlen),
+                                      off.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p)))
     try:
         blob = C.string_at(text, tlen.value).decode()
     finally:

@@ -82,6 +82,16 @@ def test_gpu_pipeline_matches_oracle_chain(solver, oracle, tmp_path):
         rows3, st3 = nb.run_regions_native([solver, s2], pafs, metas, 1000.0, 1000.0, 10000.0, depth=2, logfile=f3,
                                            regions_per_batch=3)
         assert rows3 == want and st3 == st and f3.read_text() == f.read_text()
+        # and from PAF files (one per region; a missing file drops its region only)
+        from tests.test_paf import write_chunk_paf
+        paths = []
+        for k, p in enumerate(pafs):
+            paths.append(tmp_path / ("r%d.paf" % k))
+            write_chunk_paf(paths[-1], p, tags=bool(k % 2))
+        paths[2] = tmp_path / "missing.paf"
+        rows4, st4 = nb.run_region_files([solver, s2], paths, metas, 1000.0, 1000.0, 10000.0, depth=2, regions_per_batch=4)
+        assert st4[2] == -2 and rows4[2] is None
+        assert [r for k, r in enumerate(rows4) if k != 2] == [r for k, r in enumerate(want) if k != 2]
     finally:
         s2.close()
 
