@@ -90,3 +90,30 @@ def test_gpu_readme_row_as_logfile_row(solver, oracle):
     assert got == ro.logfile_row(A, log)
     assert got.startswith("chr1_partial\t1700000\t3300000\tFasta_x_Fasta_y\tNA\tNA\tNA\t1600000\t1\t71.378\t99.595\t")
     assert "\t4_12_inv+11_18_del\t" in got
+
+
+def _append_worker(args):
+    path, tag, n = args
+    from nahrwhals_b200 import region
+    for k in range(n):
+        region.append_logfile(path, "%s\t%d\t%s" % (tag, k, "x" * 3000))     # longer than a pipe buffer's atomic write
+    return n
+
+
+def test_log_append_concurrent_processes(tmp_path):
+    """The reference's PSOCK workers append to one nahrwhals_res.tsv under filelock (R/save_logfile.R:197-221): several
+    processes appending at once give one header and whole rows only."""
+    import multiprocessing as mp
+    from nahrwhals_b200 import region
+    f = str(tmp_path / "nahrwhals_res.tsv")
+    with mp.get_context("fork").Pool(6) as pool:
+        done = pool.map(_append_worker, [(f, "w%d" % w, 40) for w in range(6)])
+    assert sum(done) == 240
+    lines = open(f).read().split("\n")
+    assert lines[0] == region.logfile_header() and lines[-1] == "" and len(lines) == 242
+    seen = {}
+    for ln in lines[1:-1]:
+        tag, k, pad = ln.split("\t")
+        assert pad == "x" * 3000
+        seen.setdefault(tag, []).append(int(k))
+    assert sorted(seen) == ["w%d" % w for w in range(6)] and all(v == list(range(40)) for v in seen.values())
