@@ -117,3 +117,25 @@ def test_log_append_concurrent_processes(tmp_path):
         assert pad == "x" * 3000
         seen.setdefault(tag, []).append(int(k))
     assert sorted(seen) == ["w%d" % w for w in range(6)] and all(v == list(range(40)) for v in seen.values())
+
+
+def test_r_fixed15_c_abi_matches_restatement():
+    """The C side's number formatter (through nw_region_logrow, host only) vs the restatement's on random doubles."""
+    import ctypes as C
+    from nahrwhals_b200 import region
+    L = region._lib_region()
+    rng = np.random.default_rng(5)
+    vals = list(rng.integers(0, 10 ** 9, 300).astype(float)) + list(np.round(rng.random(300) * 100, 3)) + \
+        list(rng.random(300) * 10.0 ** rng.integers(-6, 12, 300)) + [0.0, 1e5, 1e15, 123456789012345.0, 99.9995, 1e-7, 2.5e-5]
+    for v in vals:
+        S = region.NwRegionSummary()
+        S.res_ref = float(v)
+        S.res_max = float("nan")
+        for k in range(15):
+            S.maxres[k] = float("nan")
+        m = region.NwLogMeta(b"c", b"0", b"0", b"s", None, None, None, b"1", float("nan"), 0, 0, 0)
+        buf = C.create_string_buffer(4096)
+        n = C.c_int64()
+        assert L.nw_region_logrow(C.byref(S), b"ref", C.byref(m), buf, 4096, C.byref(n)) == 0
+        f = buf.value.decode().split("\t")
+        assert f[9] == ro.r_fixed15(v) and f[10] == "NA", (v, f[9], ro.r_fixed15(v))
