@@ -992,7 +992,12 @@ __global__ void __launch_bounds__(1024) k_topk_threshold(const uint32_t* __restr
   const int t = threadIdx.x;
   const int hi = 100000 - t * TOPK_CH;  // this thread's bins, descending: hi .. max(hi - TOPK_CH + 1, 0)
   uint32_t sum = 0;
-  for (int b = hi; b > hi - TOPK_CH && b >= 0; --b) sum += hist[b];
+#pragma unroll 14
+  for (int i = 0; i < TOPK_CH; ++i) {  // branch-free so that the 98 independent loads overlap
+    const int b = hi - i;
+    const uint32_t h = hist[b > 0 ? b : 0];
+    sum += b >= 0 ? h : 0u;
+  }
   uint32_t total;
   const uint32_t before = block_excl_scan(sum, sh, total);
   if (before < w && w <= before + sum) {
