@@ -110,7 +110,7 @@ class ClockSampler:
 def cpu_sample(aln, lx, ly, flags, max_scored, threads):
     """Oracle (CPU restatement of solver.jl) on a bounded sample of the workload: the first `max_scored` unique
     candidates of the same search, one independent replica per host thread (what R's threads= does for regions).
-    Returns (candidates/s over all threads, seconds)."""
+    Returns (candidates/s over all threads, seconds, candidates scored, DP cells evaluated)."""
     from oracle import oracle_lib
     oracle_lib.lib()
     kw = dict(maxdepth=flags["maxdepth"], maxdup=flags["maxdup"], maxwidth=flags["maxwidth"],
@@ -128,7 +128,17 @@ def cpu_sample(aln, lx, ly, flags, max_scored, threads):
         t.join()
     dt = time.perf_counter() - t0
     scored = sum(int(r.scored.sum()) for r in res)
-    return scored / dt, dt, scored
+    cells = sum(int(r.cells.sum()) for r in res)
+    return scored / dt, dt, scored, cells
+
+
+def full_search_cells_note(workload):
+    """DP cells per scored candidate of the WHOLE search (oracle fixture of this workload), to put beside the sample's."""
+    try:
+        fx = json.load(open(os.path.join(ROOT, "tests", "golden", "fullsize_%s.json" % workload)))
+        return " vs %.0f over the whole search (oracle, tests/golden/fullsize_%s.json)" % (fx["cells_per_scored"], workload)
+    except Exception:
+        return ""
 
 
 def run_reference(args, rank, world):
@@ -139,14 +149,16 @@ def run_reference(args, rank, world):
     sample_n = args.cpu_sample
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_sample(aln, lx, ly, flags, max(1000, sample_n // 20), cores)
-    tot_scored, tot_t = 0, 0.0
+    tot_scored, tot_t, tot_cells = 0, 0.0, 0
     for _ in range(args.steps):
-        v, dt, sc = cpu_sample(aln, lx, ly, flags, sample_n, cores)
+        v, dt, sc, ce = cpu_sample(aln, lx, ly, flags, sample_n, cores)
         tot_scored += sc
         tot_t += dt
+        tot_cells += ce
     value = tot_scored / tot_t
     sample = ("first %d unique candidates of the same search per replica, %d independent replicas (one per host "
-              "thread), C++ restatement of solver.jl (oracle/nw_oracle.cpp, -O2)" % (sample_n, cores))
+              "thread), C++ restatement of solver.jl (oracle/nw_oracle.cpp, -O2); %.0f DP cells per scored candidate in "
+              "the sample%s" % (sample_n, cores, tot_cells / max(tot_scored, 1), full_search_cells_note(args.workload)))
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * tot_t / args.steps, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64", data="synthetic",
@@ -794,49 +806,134 @@ def run_paf(args, rank, world, local):
     solver.close()
 
 
-def run_frontier(args, rank, world, local):
-    """BASELINE.json config 3: ONE deep search sharded over the GPUs (frontier round-robin, per-level all-gather of
-    40-byte records over NCCL, deterministic merge on every rank).  Strong scaling: total work is fixed."""
-    import torch
-    import torch.distributed as dist
-    import nahrwhals_b200 as nb
+def frontier_section(solver, dist, torch, rank, world, workload, steps, warmup):
+    """BASELINE.json config 3 (and the exhaustive S150 search): ONE deep search over all ranks -- replicated expansion /
+    dedup / selection, the banded DP of every level divided between the ranks, one NCCL all-gather of the score arrays
+    per level issued by libnwsolve on its own stream (nw_solve_sharded).  Strong scaling: total work is fixed.
+    Returns a dict (identical on every rank): device ms per search (CUDA events on each rank's stream, max over
+    ranks), end-to-end ms from host buffers (wall, max over ranks), and the same search on ONE GPU of the same box."""
     from nahrwhals_b200.distributed import solve_sharded
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    aln, lx, ly, flags, desc = make_workload(args.workload, 1)
-    solver = nb.Solver(local)
-    for _ in range(max(3, args.warmup)):
-        R = solve_sharded(solver, aln, lx, ly, **flags)
-    sampler = ClockSampler(local)
-    torch.cuda.synchronize()
-    dist.barrier()
-    sampler.start()
-    tot, scored, launches = 0.0, 0, 0
-    for _ in range(args.steps):
+    aln, lx, ly, flags, desc = make_workload(workload, 1)
+    ref = solver.solve(aln, lx, ly, **flags)
+    R = solve_sharded(solver, aln, lx, ly, **flags)
+    same = R.tsv == ref.tsv and R.scored == ref.scored and R.generated == ref.generated and R.cells == ref.cells
+    for _ in range(max(3, warmup)):
+        solve_sharded(solver, aln, lx, ly, **flags)
+    dev, e2e, dp, launches = 0.0, 0.0, 0.0, 0
+    for _ in range(steps):
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
         R = solve_sharded(solver, aln, lx, ly, **flags)
-        torch.cuda.synchronize()
-        tot += time.perf_counter() - t0
-        scored += sum(R.scored)
+        e2e += time.perf_counter() - t0
+        dev += R.stats.total_ms
+        dp += R.stats.score_ms
         launches += R.stats.kernel_launches
-    clocks = sampler.stop()
-    t = torch.tensor([tot], dtype=torch.float64, device="cuda")
+    one_dev, one_e2e, one_dp = 0.0, 0.0, 0.0
+    for _ in range(max(3, warmup)):
+        solver.solve(aln, lx, ly, **flags)
+    for _ in range(steps):
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        Q = solver.solve(aln, lx, ly, **flags)
+        one_e2e += time.perf_counter() - t0
+        one_dev += Q.stats.total_ms
+        one_dp += Q.stats.score_ms
+    t = torch.tensor([dev, 1e3 * e2e, dp, one_dev, 1e3 * one_e2e, one_dp, 0.0 if same else 1.0], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    tot = float(t.item())
-    s = torch.tensor([launches], dtype=torch.float64, device="cuda")
-    dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    dev, e2e, dp, one_dev, one_e2e, one_dp, bad = (t / steps).tolist()
+    ln = torch.tensor([launches], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+    scored = sum(ref.scored)
+    return dict(workload=desc, ranks=world, scaling="strong", scored_per_search=scored,
+                identical_to_single_gpu=(bad == 0.0), ms_per_search=dev, ms_per_search_e2e=e2e,
+                cand_per_s=scored / (dev * 1e-3), dp_ms_per_search_max_rank=dp,
+                ms_1gpu_same_box=one_dev, ms_1gpu_same_box_e2e=one_e2e, dp_ms_1gpu=one_dp,
+                speedup_vs_1gpu=one_dev / dev if dev > 0 else None,
+                launches_per_search_all_ranks=ln.item() / steps,
+                exchange="one ncclAllGather group (k3, cost, total; 12 B per fresh candidate) per BFS level on the "
+                         "library's stream",
+                timing="CUDA events on every rank's stream around the whole search, max over ranks, mean of %d "
+                       "searches; e2e = wall clock around nw_solve_sharded from host buffers" % steps)
+
+
+def regions_section(solvers, dist, torch, rank, world, total_regions, per_pass):
+    """BASELINE.json config 4: ONE regionfile batch of `total_regions` synthetic SD-flanked regions (20-120 blocks),
+    LPT-sharded over the ranks by estimated work (nahrwhals_b200.distributed.shard_regions), every rank solving its
+    shard through nw_solve_many_ctxs; no collective on the data path.  Strong scaling: total work is fixed.  Also the
+    whole batch on ONE GPU of the same box (rank 0 alone)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from region_batch import FLAGS, make_regions
+    import nahrwhals_b200 as nb
+    from nahrwhals_b200.distributed import estimate_region_cost, shard_regions
+    # every rank builds a slice of the batch, then everybody gets everything (generation is untimed set-up)
+    regs_all = make_regions(total_regions, seed=0, only=range(rank, total_regions, world))
+    parts = [None] * world
+    dist.all_gather_object(parts, regs_all)
+    regs = [None] * total_regions
+    for r in range(world):
+        for k, reg in zip(range(r, total_regions, world), parts[r]):
+            regs[k] = reg
+    del parts
+    costs = [estimate_region_cost(a, FLAGS["maxdepth"], FLAGS["maxwidth"]) for a, _, _ in regs]
+    mine = shard_regions(costs, world)[rank]
+    my = [regs[k] for k in mine]
+    warm = make_regions(min(1500, total_regions), seed=1000 + rank)
+    for _ in range(2):
+        nb.solve_many(solvers, warm, regions_per_pass=per_pass, **FLAGS)
+    del warm
+
+    def timed(batch):
+        torch.cuda.synchronize()
+        dist.barrier()
+        tm = {}
+        t0 = time.perf_counter()
+        res = nb.solve_many(solvers, batch, regions_per_pass=per_pass, timing=tm, **FLAGS) if batch else []
+        return time.perf_counter() - t0, tm.get("native_s", 0.0), sum(sum(R.scored) for R in res)
+    nb.solve_many(solvers, my, regions_per_pass=per_pass, **FLAGS)  # shapes of the timed batch warm (corridor tables)
+    wall, native, scored = timed(my)
+    one_wall, one_native, one_scored = timed(regs if rank == 0 else [])
+    t = torch.tensor([wall, native, one_wall, one_native], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall, native, one_wall, one_native = t.tolist()
+    sc = torch.tensor([scored, one_scored, len(my) ** 2], dtype=torch.float64, device="cuda")
+    dist.all_reduce(sc, op=dist.ReduceOp.SUM)
+    return dict(workload="regionfile batch of %d synthetic SD-flanked regions (20-120 blocks, 2-6 repeat families), "
+                         "-d 3 -u 2 -w 1000 -r 0.98 -R 1000, LPT-sharded over %d GPUs by estimated work, %d regions "
+                         "searched together per pass, %d contexts per GPU" % (total_regions, world, per_pass, len(solvers)),
+                total_regions=total_regions, ranks=world, scaling="strong",
+                regions_per_s=total_regions / native, regions_per_s_python=total_regions / wall,
+                candidates_scored=sc[0].item(), seconds=native,
+                regions_per_s_1gpu_same_box=total_regions / one_native if one_native > 0 else None,
+                speedup_vs_1gpu=one_native / native if native > 0 else None,
+                timing="wall clock around nw_solve_many_ctxs on every rank (host buffers in, reports in host memory out), "
+                       "max over ranks; 1 GPU = rank 0 alone on the whole batch")
+
+
+def run_frontier(args, rank, world, local):
+    """`--mode frontier`: only the sharded single search of BASELINE config 3 (the default N > 1 run reports it under
+    config.frontier next to the headline line)."""
+    import torch
+    import torch.distributed as dist
+    import nahrwhals_b200 as nb
+    from nahrwhals_b200.distributed import init_sharded
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    solver = nb.Solver(local)
+    init_sharded(solver)
+    sampler = ClockSampler(local)
+    sampler.start()
+    F = frontier_section(solver, dist, torch, rank, world, args.workload, args.steps, args.warmup)
+    clocks = sampler.stop()
     if rank == 0:
-        v = scored / tot
-        print(json.dumps(dict(metric=METRIC, value=v, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
-                              ms_per_step=1e3 * tot / args.steps, higher_is_better=True, scaling="strong",
-                              vs_baseline=None, dtype="int32", data="synthetic",
-                              config=dict(workload=desc + "; ONE search, frontier sharded over %d GPUs, per-level "
-                                                          "all-gather (NCCL)" % world, timing="wall clock, max over ranks"),
-                              clocks=clocks, e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=int(R.stats.h2d_bytes),
-                                                      d2h_bytes_per_step=int(R.stats.d2h_bytes)),
-                              gpu_launches=int(s.item()))), flush=True)
+        print(json.dumps(dict(metric=METRIC, value=F["cand_per_s"], unit=UNIT, n_gpus=world, steps=args.steps,
+                              warmup=max(3, args.warmup), ms_per_step=F["ms_per_search"], higher_is_better=True,
+                              scaling="strong", vs_baseline=None, dtype="int32", data="synthetic",
+                              config=dict(workload=F["workload"] + "; ONE search over %d GPUs" % world, frontier=F),
+                              clocks=clocks, e2e=dict(value=F["scored_per_search"] / (F["ms_per_search_e2e"] * 1e-3), unit=UNIT,
+                                                      h2d_bytes_per_step=None, d2h_bytes_per_step=None),
+                              gpu_launches=int(F["launches_per_search_all_ranks"] * args.steps))), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     solver.close()
@@ -857,8 +954,11 @@ def main():
     ap.add_argument("--mode", default="regions", choices=["regions", "frontier"],
                     help="N > 1: 'regions' = one independent search per GPU (default, weak scaling); 'frontier' = ONE "
                          "search sharded over the GPUs with a per-level all-gather (strong scaling, config 3)")
-    ap.add_argument("--cpu-sample", type=int, default=150000, help="unique candidates per CPU replica (bounded sample)")
+    ap.add_argument("--cpu-sample", type=int, default=600000, help="unique candidates per CPU replica (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-multi", action="store_true", help="N > 1: skip the frontier-sharded and sharded-regionfile sections")
+    ap.add_argument("--total-regions", type=int, default=10000,
+                    help="N > 1: regions of the ONE regionfile batch that is LPT-sharded over the GPUs (BASELINE config 4)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -1011,14 +1111,31 @@ def main():
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_all / args.steps,
                          d2h_bytes_per_step=d2h_all / args.steps, ms_per_step=1e3 * e2e_t / args.steps),
                 gpu_launches=int(launches_all), roofline=roofline, wall_s_timed=wall1)
+    if world > 1 and not args.no_multi:
+        # the two multi-GPU designs north_star names, measured in the same invocation (the headline value above stays
+        # the per-GPU replica figure so that the driver's efficiency arithmetic over N keeps its meaning)
+        from nahrwhals_b200.distributed import init_sharded
+        init_sharded(solver)
+        msteps = max(5, min(args.steps, 20))
+        line["config"]["frontier"] = frontier_section(solver, dist, torch, rank, world, "s150", msteps, args.warmup)
+        line["config"]["frontier_exhaustive"] = frontier_section(solver, dist, torch, rank, world, "s150d3", max(3, msteps // 4), 1)
+        nctx = max(1, min(args.contexts, (os.cpu_count() or 8) // max(world, 1)))
+        more = [nb.Solver(local) for _ in range(nctx - 1)]
+        line["config"]["regions"] = regions_section([solver] + more, dist, torch, rank, world, args.total_regions,
+                                                    args.regions_per_pass)
+        for s_ in more:
+            s_.close()
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v, dt, sc = cpu_sample(aln, lx, ly, flags, args.cpu_sample, cores)
+        v, dt, sc, ce = cpu_sample(aln, lx, ly, flags, args.cpu_sample, cores)
         line["cpu_baseline"] = dict(
             value=v, unit=UNIT, cores=cores, kind="port",
             sample="first %d unique candidates of the same search per replica, %d independent replicas (one per host "
-                   "thread), %.1f s; C++ restatement of solver.jl (the reference itself needs julia, absent here)" %
-                   (args.cpu_sample, cores, dt))
+                   "thread), %.1f s; %.0f DP cells per scored candidate in the sample vs %.0f over the whole search on "
+                   "the GPU; C++ restatement of solver.jl (the reference itself needs julia, absent here)" %
+                   (args.cpu_sample, cores, dt, ce / max(sc, 1), cells / max(scored, 1)),
+            cells_per_candidate=dict(sample=ce / max(sc, 1), full_search=cells / max(scored, 1)),
+            cells_per_s=ce / dt)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:

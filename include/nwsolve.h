@@ -167,37 +167,35 @@ int nw_solve_files_many(nw_ctx** ctxs, int32_t n_ctx, const char* const* inmat, 
                         int32_t* rcs);
 
 /* ---- one deep search sharded over `world` ranks (config 3 of BASELINE.json) -------------------------
- * One context per rank, the same problem and options on every rank.  The frontier is replicated; rank r expands the
- * parents whose frontier slot is congruent to r modulo world, dedups and scores its own candidates, and contributes
- * one NW_DIST_RECORD_BYTES record per locally-first candidate to a per-level all-gather that the CALLER performs
- * (torch.distributed / NCCL in nahrwhals_b200/distributed.py; any transport works).  Every rank then runs the same
- * deterministic merge (min global discovery position per fingerprint = the serial first-discoverer rule of
- * solver.jl:535; ids in global discovery order; stable top-width), so results are bit-identical to nw_solve.
+ * The reference's level loop (solver.jl:667-684) is serial and its cost is the scorer (slow_score, :329-426, called
+ * once per new index at :536).  Every rank runs the SAME deterministic expansion, dedup, id assignment and frontier
+ * selection (replicated: no exchange, identical state everywhere); the banded DP of a level's fresh candidates is
+ * divided between the ranks by contiguous ranges of discovery rank, and ONE all-gather per level over the score
+ * arrays (12 bytes per fresh candidate, in place, on the context's stream, no host synchronisation) completes them.
+ * Results -- every id, score, edge and the report -- are bit-identical to nw_solve on every rank.
  *
- *   nw_dist_begin
- *   do { nw_dist_expand(&n);  all-gather n -> counts[];  nw_dist_pack(send);  all-gather send -> all (padded to
- *        stride = max(counts) records per rank);  nw_dist_merge(all, counts, stride, &more); } while (more);
- *   nw_dist_report_begin(needed, n_ids+16)          -- needed: caller-owned device bytes, identical on all ranks
- *   for pass = 1 .. maxdepth+1: nw_dist_report_mark(needed, pass);  all-reduce MAX over needed
- *   nw_dist_report_edges(needed, &ne); all-gather ne; nw_dist_report_pack(send); all-gather (NW_DIST_EDGE_BYTES each)
- *   nw_dist_finish(needed, all_edges, counts, stride, &result)      -- every rank builds the same result
- * All pointers named dev_* / needed are DEVICE pointers on the context's GPU; every call returns with the
- * context's stream idle, so the caller only has to order its own collectives. */
-#define NW_DIST_RECORD_BYTES 40
-#define NW_DIST_EDGE_BYTES 16
-int nw_dist_begin(nw_ctx* ctx, const int8_t* aln_sign, int32_t n_x, int32_t n_y, const int64_t* len_x,
-                  const int64_t* len_y, const nw_opts* opts, int32_t rank, int32_t world);
-int nw_dist_expand(nw_ctx* ctx, int64_t* n_records);
-int nw_dist_pack(nw_ctx* ctx, void* dev_out);
-int nw_dist_merge(nw_ctx* ctx, const void* dev_all, const int64_t* counts, int64_t stride_records, int32_t* more);
-int64_t nw_dist_n_ids(nw_ctx* ctx);
-int nw_dist_report_begin(nw_ctx* ctx, void* needed_dev, int64_t nbytes);
-int nw_dist_report_mark(nw_ctx* ctx, void* needed_dev, int32_t pass);
-int nw_dist_report_edges(nw_ctx* ctx, const void* needed_dev, int64_t* n_edges);
-int nw_dist_report_pack(nw_ctx* ctx, void* dev_out);
-int nw_dist_finish(nw_ctx* ctx, const void* needed_dev, const void* dev_edges_all, const int64_t* counts,
-                   int64_t stride_edges, nw_result** out);
-void nw_dist_abort(nw_ctx* ctx);
+ * Multi-process (one rank per GPU, e.g. under torchrun / mpirun): rank 0 calls nw_dist_unique_id and hands the
+ * NW_DIST_ID_BYTES bytes to the other ranks by any means (torch.distributed broadcast, MPI_Bcast, a file); every rank
+ * then calls nw_dist_init (collective: ncclCommInitRank on the context's device) once, and nw_solve_sharded
+ * (collective: the same problem and options on every rank) per search.  NCCL is bound at run time (libnccl.so.2);
+ * without it these calls fail with NW_ERR_CUDA and nw_last_error() says why.  A rank that fails inside a collective
+ * search leaves its peers waiting in NCCL -- run sharded jobs under the launcher's timeout.
+ * nw_stats of a sharded search: counters are those of the whole search (cells summed over the ranks); times,
+ * launches and byte counts are this rank's. */
+#define NW_DIST_ID_BYTES 128
+int nw_dist_unique_id(void* id_out /* NW_DIST_ID_BYTES */);
+int nw_dist_init(nw_ctx* ctx, const void* id /* NW_DIST_ID_BYTES */, int32_t rank, int32_t world);
+int nw_dist_info(nw_ctx* ctx, int32_t* rank, int32_t* world); /* 0 / 1 without a communicator */
+void nw_dist_shutdown(nw_ctx* ctx);
+int nw_solve_sharded(nw_ctx* ctx, const int8_t* aln_sign, int32_t n_x, int32_t n_y, const int64_t* len_x,
+                     const int64_t* len_y, const nw_opts* opts, nw_result** out);
+/* The same inside ONE process: ctxs[r] is rank r (one host thread each).  The contexts may sit on different GPUs
+ * (the exchange is a set of peer copies over NVLink) or share a GPU (how the parity tests emulate several ranks on one
+ * device).  outs[r] receives rank r's result (all identical); on error no result is returned.  This is what
+ * `nwsolve --devices 0,1,...` runs for a single search, so the file + command-line boundary R uses
+ * (R/juliasolver.R:34-53) reaches several GPUs without a launcher. */
+int nw_solve_sharded_ctxs(nw_ctx** ctxs, int32_t world, const int8_t* aln_sign, int32_t n_x, int32_t n_y,
+                          const int64_t* len_x, const int64_t* len_y, const nw_opts* opts, nw_result** outs);
 
 /* Roofline denominators measured on this device with dependency-free micro-kernels:
  * out[0] VIADDMNMX, out[1] IADD3, out[2] VIADDMNMX+IMAD interleaved -- thread-instructions per second;

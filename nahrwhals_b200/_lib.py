@@ -20,8 +20,7 @@ class NwStats(C.Structure):
                 ("score_launches", C.c_int32), ("host_ms", C.c_float * 4)]
 
 
-DIST_RECORD_BYTES = 40
-DIST_EDGE_BYTES = 16
+DIST_ID_BYTES = 128
 FLAG_GENERIC_DP = 1
 FLAG_NO_TRAJ = 2
 FLAG_PAIR_EXPAND = 4
@@ -33,9 +32,8 @@ SYMBOLS = ["nw_default_opts", "nw_last_error", "nw_version", "nw_ctx_create", "n
            "nw_solve_files", "nw_result_count", "nw_result_get", "nw_result_cost", "nw_result_arrays", "nw_result_move_count",
            "nw_result_tsv", "nw_result_stats",
            "nw_result_ids", "nw_result_edge_count", "nw_result_edges", "nw_result_free", "nw_score_batch",
-           "nw_moveset", "nw_bench_peaks", "nw_read_problem", "nw_free", "nw_dist_begin", "nw_dist_expand",
-           "nw_dist_pack", "nw_dist_merge", "nw_dist_n_ids", "nw_dist_report_begin", "nw_dist_report_mark",
-           "nw_dist_report_edges", "nw_dist_report_pack", "nw_dist_finish", "nw_dist_abort", "nw_solve_batch", "nw_solve_many",
+           "nw_moveset", "nw_bench_peaks", "nw_read_problem", "nw_free", "nw_dist_unique_id", "nw_dist_init",
+           "nw_dist_info", "nw_dist_shutdown", "nw_solve_sharded", "nw_solve_sharded_ctxs", "nw_solve_batch", "nw_solve_many",
            "nw_solve_many_ctxs", "nw_solve_files_many", "nw_results_sizes", "nw_results_gather"]
 
 _lib = None
@@ -77,18 +75,12 @@ def load():
     L.nw_read_problem.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32),
                                   C.POINTER(vp), C.POINTER(vp)]
     L.nw_free.argtypes = [vp]
-    L.nw_dist_begin.argtypes = [vp, vp, i32, i32, vp, vp, C.POINTER(NwOpts), i32, i32]
-    L.nw_dist_expand.argtypes = [vp, C.POINTER(i64)]
-    L.nw_dist_pack.argtypes = [vp, vp]
-    L.nw_dist_merge.argtypes = [vp, vp, vp, i64, C.POINTER(i32)]
-    L.nw_dist_n_ids.restype = i64
-    L.nw_dist_n_ids.argtypes = [vp]
-    L.nw_dist_report_begin.argtypes = [vp, vp, i64]
-    L.nw_dist_report_mark.argtypes = [vp, vp, i32]
-    L.nw_dist_report_edges.argtypes = [vp, vp, C.POINTER(i64)]
-    L.nw_dist_report_pack.argtypes = [vp, vp]
-    L.nw_dist_finish.argtypes = [vp, vp, vp, vp, i64, C.POINTER(vp)]
-    L.nw_dist_abort.argtypes = [vp]
+    L.nw_dist_unique_id.argtypes = [vp]
+    L.nw_dist_init.argtypes = [vp, vp, i32, i32]
+    L.nw_dist_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    L.nw_dist_shutdown.argtypes = [vp]
+    L.nw_solve_sharded.argtypes = [vp, vp, i32, i32, vp, vp, C.POINTER(NwOpts), C.POINTER(vp)]
+    L.nw_solve_sharded_ctxs.argtypes = [vp, i32, vp, i32, i32, vp, vp, C.POINTER(NwOpts), vp]
     L.nw_solve_batch.argtypes = [vp, i32, vp, i64, C.POINTER(NwOpts), vp, vp]
     L.nw_solve_many.argtypes = [vp, vp, i64, C.POINTER(NwOpts), i32, vp]
     L.nw_results_sizes.argtypes = [vp, i64, vp, vp, vp]

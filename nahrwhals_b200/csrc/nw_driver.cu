@@ -21,6 +21,7 @@
 
 #include "../../include/nwsolve.h"
 #include "nw_band.h"
+#include "nw_exchange.h"
 #include "nw_host.h"
 #include "nw_kernels.cuh"
 #include "nw_launch.h"
@@ -259,7 +260,7 @@ struct nw_ctx {
   // per-level scratch
   DevBuf cnt, off, bsum, slot, owner, is_new, newrank, nrank, new_len, hist, bstart, cursor, work, scratch, flag, pre, sel, keys,
       misc, rslot, newflag, grank, edgebuf, cta_rid, new_rid, best, gather, binflag, binrank, binsum, binrec;
-  void* dist = nullptr;  // active frontier-sharded search (Search*, nw_dist_*)
+  nw::Exchange* xch = nullptr;  // NCCL communicator of the frontier-sharded search (nw_dist_init), owned by the context
   void* pinned = nullptr;  // pinned staging area for D2H scalars / histograms (grown on demand)
   size_t pinned_bytes = 0;
   // staging of the region pre-pass (nw_region.cu): pinned host buffer + device buffer, grown on demand, kept
@@ -318,10 +319,6 @@ struct Level {
   DevBuf desc, cand_id, newlist, k3, cost, total, nrid;  // nrid: region of every fresh id (uint16)
   // region boundaries (R+1 entries each): parents, candidate positions, new ranks of every region at this level
   std::vector<uint32_t> fstart, cstart, nstart;
-  // frontier-sharded search only: G counts this rank's candidates, G_all all ranks'; k3/cost/total are the merged
-  // (replicated) per-id arrays, l_* the rank-local ones of the candidates this rank scored
-  uint32_t G_all = 0, n_local_new = 0;
-  DevBuf off_loc, off_glob, desc_new, gid_at, l_k3, l_cost, l_total;
   FrontierDev frontier() const {
     FrontierDev F;
     F.P = P;
@@ -502,7 +499,7 @@ ScoreView view_of(const Level& L) {
 // launches that take the single-copy path below (one region, few bins) -- saves one host round trip per level.
 void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int lcap, const uint16_t* new_rid_dev, int force,
                  int flags, int* best_dev, int64_t* cells_out /* [n_regions] or nullptr */,
-                 uint32_t* n_new_deferred = nullptr) {
+                 uint32_t* n_new_deferred = nullptr, OwnRange own = OwnRange{1, 0, nullptr}) {
   const int R = c->n_regions;
   uint32_t n_new = Lv.n_new;
   const size_t nbins = (size_t)R * lcap * NSUB;
@@ -620,8 +617,8 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
     h2d(c, d_cta_rid, cta_rid.data(), cta_rid.size() * 2);
   }
   c->launches += launch_bucket_scatter(c->new_len.as<uint16_t>(), new_rid_dev, c->d_regions.as<RegionDev>(), lcap, n_new,
-                                       force, c->bstart.as<uint32_t>(), c->cursor.as<uint32_t>(), c->work.as<uint32_t>(),
-                                       st);
+                                       force, own, c->bstart.as<uint32_t>(), c->cursor.as<uint32_t>(),
+                                       c->work.as<uint32_t>(), st);
   // no sync: cudaMemcpyAsync from pageable memory has consumed the host vectors (bins, cta_rid) when it returns
   if (dbg)
     fprintf(stderr, "[nw scoring] buckets %zu, work %u for %u new, ranges %zu: bucket loop %.2f ms, bands %.2f, layout %.2f, scatter %.2f\n",
@@ -695,13 +692,10 @@ struct Search {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> lev;
 
-  int rank = 0, world = 1;      // frontier sharding (nw_dist_*); world == 1 is the plain single-GPU search
-  ExpandArgs curE{};            // expansion arguments of the level in flight (sharded search)
-  int cur_level = 0;
-  bool dist_more = false;
-  int dist_k3_min = 0;
-  int dist_maxlen = 0;
-  uint32_t dist_edges = 0;
+  // frontier sharding (nw_solve_sharded*): every rank runs the same search, the DP of a level is divided by new-rank
+  // ranges and completed by one all-gather (nw_exchange.h).  xch == nullptr is the plain single-GPU search.
+  Exchange* xch = nullptr;
+  int rank = 0, world = 1;
   uint32_t edge_cap_hint = 0, id_cap_hint = 0;
   int level_maxlen = 0;  // longest duplication child of the level in flight
   explicit Search(nw_ctx* ctx, const nw_opts& opts) : c(ctx), o(opts) {}
@@ -712,6 +706,14 @@ struct Search {
   }
 
   uint32_t* pin_u32() { return reinterpret_cast<uint32_t*>(c->pinned); }
+  template <typename F>
+  void xcall(F&& f) {  // transport errors of the sharded search surface like CUDA errors
+    try {
+      f();
+    } catch (const ExchangeError& e) {
+      fail(NW_ERR_CUDA, "sharded search exchange: " + e.msg);
+    }
+  }
 
   FrontierDev frontier_of(const Level& L) const {
     FrontierDev F = L.frontier();
@@ -916,9 +918,6 @@ struct Search {
     E.slot = (uint32_t*)c->slot.ensure((size_t)G * 4, true);
     E.gbase = L.gbase;
     E.pw = c->d_pow.as<U4>();
-    E.own_mod = 1;
-    E.own_rem = 0;
-    E.off_glob = nullptr;
     table_reserve(c, (uint64_t)n_ids + G);
     E.table = c->table.as<uint64_t>();
     E.tmask = c->table_cap - 1;
@@ -975,13 +974,17 @@ struct Search {
     A.G = G;
     A.id_base = L.id_base;
     A.force = 0;
+    const OwnRange own{world, rank, (const uint32_t*)(misc + 5)};
+    A.own = own;
     A.cand_id = (int32_t*)L.cand_id.ensure((size_t)G * 4);
     A.newlist = (uint32_t*)L.newlist.ensure((size_t)std::max<uint32_t>(n_new, 1) * 4);
     A.new_len = (uint16_t*)c->new_len.ensure((size_t)std::max<uint32_t>(n_new, 1) * 2, true);
     A.new_rid = (uint16_t*)L.nrid.ensure((size_t)std::max<uint32_t>(n_new, 1) * 2);
-    A.k3 = (int32_t*)L.k3.ensure((size_t)std::max<uint32_t>(n_new, 1) * 4);
-    A.cost = (int32_t*)L.cost.ensure((size_t)std::max<uint32_t>(n_new, 1) * 4);
-    A.total = (int32_t*)L.total.ensure((size_t)std::max<uint32_t>(n_new, 1) * 4);
+    // sharded search: the score arrays are exchanged in place as `world` segments of own_chunk items
+    const size_t n_score = world > 1 ? (size_t)own_chunk(n_new, world) * world : std::max<uint32_t>(n_new, 1);
+    A.k3 = (int32_t*)L.k3.ensure(n_score * 4);
+    A.cost = (int32_t*)L.cost.ensure(n_score * 4);
+    A.total = (int32_t*)L.total.ensure(n_score * 4);
     A.hist = (uint32_t*)c->hist.ensure(nbins * 4, true);
     CK(cudaMemsetAsync(A.hist, 0, nbins * 4, s));
     c->launches += launch_assign(A, s);
@@ -991,7 +994,12 @@ struct Search {
     std::vector<int64_t> cells(R, 0);
     run_scoring(c, ScoreView{frontier_of(L), defer ? 0u : L.n_new, L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(),
                              L.k3.as<int32_t>(), L.cost.as<int32_t>(), L.total.as<int32_t>()},
-                A.hist, lcap, L.nrid.as<uint16_t>(), 0, o.flags, c->best.as<int>(), cells.data(), defer ? &n_new : nullptr);
+                A.hist, lcap, L.nrid.as<uint16_t>(), 0, o.flags, c->best.as<int>(), cells.data(), defer ? &n_new : nullptr, own);
+    if (xch && n_new) {
+      // the one exchange step of a level: every rank's share of the DP results, in place, on the search's stream
+      xcall([&] { xch->allgather3(L.k3.as<int32_t>(), L.cost.as<int32_t>(), L.total.as<int32_t>(), own_chunk(n_new, world), s); });
+      c->launches += launch_max_k3(L.k3.as<int32_t>(), n_new, c->best.as<int>(), s);
+    }
     if (defer) {
       L.nstart[0] = 0;
       L.nstart[1] = n_new;
@@ -1095,8 +1103,8 @@ struct Search {
     MaterialiseArgs M{};
     M.F = frontier_of(Lr);
     M.sel = sel;
-    M.newlist = world > 1 ? nullptr : Lr.newlist.as<uint32_t>();  // sharded: descriptors of the merged new ids
-    M.desc = world > 1 ? Lr.desc_new.as<uint64_t>() : Lr.desc.as<uint64_t>();
+    M.newlist = Lr.newlist.as<uint32_t>();
+    M.desc = Lr.desc.as<uint64_t>();
     M.id_base = Lr.id_base;
     M.maxdup = o.maxdup;
     M.nx_max = c->nx_max;
@@ -1142,6 +1150,12 @@ struct Search {
     st.n_levels = n_levels;
     st.n_ids = n_ids;
     st.kernel_launches = c->launches;
+    if (xch) {  // DP cells are counted where they are evaluated: sum the ranks' shares (R == 1 in a sharded search)
+      int64_t v[16];
+      for (int l = 0; l < 16; ++l) v[l] = rst[0].cells[l];
+      xcall([&] { xch->allreduce_sum(v, 16, s); });
+      for (int l = 0; l < 16; ++l) rst[0].cells[l] = v[l];
+    }
     for (int r = 0; r < R; ++r) {
       best_k3[r] = best[r];
       nw_stats& q = rst[r];
@@ -1187,237 +1201,6 @@ struct Search {
     CK(spin_sync(s));
     CK(cudaGetLastError());
     finish_stats(n_levels);
-  }
-
-  // =================================================================================================
-  // frontier-sharded search: the level loop of run() cut at the point where ranks exchange records
-  // =================================================================================================
-  void dist_begin() {
-    cudaStream_t s = c->stream;
-    CK(cudaEventCreate(&ev0));
-    CK(cudaEventCreate(&ev1));
-    CK(cudaEventRecord(ev0, s));
-    init_root();
-    cur_level = 1;
-    dist_more = o.maxdepth >= 1;
-    st.n_levels = 0;
-  }
-
-  // expand this rank's share of level cur_level; returns the number of records it contributes to the exchange
-  int64_t dist_expand() {
-    cudaStream_t s = c->stream;
-    const int d = cur_level;
-    Level& L = lv[d];
-    int32_t* misc = (int32_t*)c->misc.p;
-    rst[0].frontier[d - 1] = L.P;
-    st.n_levels = d;
-    L.G = L.G_all = L.n_local_new = L.n_new = 0;
-    L.gbase = gtotal;
-    L.id_base = n_ids + 1;
-    L.cstart.assign(2, 0);
-    L.nstart.assign(2, 0);
-    curE = ExpandArgs{};
-    if (L.P == 0) return 0;
-    ExpandArgs E{};
-    E.F = frontier_of(L);
-    E.nx_max = c->nx_max;
-    E.cnt = (uint32_t*)c->cnt.ensure((size_t)L.P * 4, true);
-    E.maxlen = misc + 2;
-    E.own_mod = 1;
-    E.force_pairs = (o.flags & NW_FLAG_PAIR_EXPAND) ? 1 : 0;
-    CK(cudaMemsetAsync(misc + 2, 0, 4, s));
-    c->launches += launch_expand(false, E, s);  // every rank counts every parent: global offsets need no collective
-    uint32_t* off_glob = (uint32_t*)L.off_glob.ensure((size_t)L.P * 4);
-    uint32_t* off_loc = (uint32_t*)L.off_loc.ensure((size_t)L.P * 4);
-    uint32_t* own_cnt = (uint32_t*)c->off.ensure((size_t)L.P * 4, true);
-    uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items((uint64_t)L.P) * 4, true);
-    c->launches += launch_scan(E.cnt, off_glob, (uint64_t)L.P, bsum, (uint32_t*)(misc + 4), s);
-    c->launches += launch_mask_counts(E.cnt, (uint32_t)L.P, world, rank, own_cnt, s);
-    c->launches += launch_scan(own_cnt, off_loc, (uint64_t)L.P, bsum, (uint32_t*)(misc + 7), s);
-    d2h(c, pin_u32(), misc, 32);
-    CK(spin_sync(s));
-    CK(cudaGetLastError());
-    const uint32_t G_all = pin_u32()[4], G = pin_u32()[7];
-    const int maxlen = (int)pin_u32()[2];
-    dist_maxlen = maxlen;
-    if (maxlen > LMAX) fail(NW_ERR_RANGE, "a child index exceeds the supported length");
-    if ((uint64_t)gtotal + G_all >= 0xfffffff0ull || G_all >= 0x7ffffff0u) fail(NW_ERR_NOMEM, "more than 2^32 candidates");
-    L.G = G;
-    L.G_all = G_all;
-    rst[0].generated[d - 1] = G_all;
-    if (G_all == 0) return 0;
-    table_reserve(c, (uint64_t)n_ids + G_all);  // room for every rank's records: no rehash during the merge
-    E.off = off_loc;
-    E.off_glob = off_glob;
-    E.own_mod = world;
-    E.own_rem = rank;
-    E.desc = (uint64_t*)L.desc.ensure((size_t)std::max<uint32_t>(G, 1) * 8);
-    E.slot = (uint32_t*)c->slot.ensure((size_t)std::max<uint32_t>(G, 1) * 4, true);
-    E.table = c->table.as<uint64_t>();
-    E.tmask = c->table_cap - 1;
-    E.gbase = L.gbase;
-    E.pw = c->d_pow.as<U4>();
-    curE = E;
-    if (G == 0) return 0;
-    c->launches += launch_expand(true, E, s);
-    c->launches += launch_hash_insert(E, G, s);
-    uint32_t* is_new = (uint32_t*)c->is_new.ensure((size_t)G * 4, true);
-    uint32_t* owner = (uint32_t*)c->owner.ensure((size_t)G * 4, true);
-    c->launches += launch_resolve(E, G, is_new, owner, s);
-    uint32_t* newrank = (uint32_t*)c->newrank.ensure((size_t)G * 4, true);
-    bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(G) * 4, true);
-    c->launches += launch_scan(is_new, newrank, G, bsum, (uint32_t*)(misc + 5), s);
-    d2h(c, pin_u32(), misc, 32);
-    CK(spin_sync(s));
-    CK(cudaGetLastError());
-    const uint32_t n_loc = pin_u32()[5];
-    L.n_local_new = n_loc;
-    AssignArgs A{};
-    A.LT.n_levels = 0;
-    A.slot = E.slot;
-    A.table = E.table;
-    A.owner = owner;
-    A.is_new = is_new;
-    A.newrank = newrank;
-    A.desc = E.desc;
-    A.front_len = L.flen.as<int32_t>();
-    A.front_rid = nullptr;
-    A.regions = c->d_regions.as<RegionDev>();
-    const int lcap = std::min(std::max(maxlen, L.LS), LMAX) + 1;
-    const size_t nbins = (size_t)lcap * NSUB;
-    A.lcap = lcap;
-    A.gbase = L.gbase;
-    A.G = G;
-    A.id_base = 0;
-    A.force = 0;
-    A.skip_ids = 1;
-    A.cand_id = nullptr;
-    A.newlist = (uint32_t*)L.newlist.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
-    A.new_len = (uint16_t*)c->new_len.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 2, true);
-    A.new_rid = (uint16_t*)L.nrid.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 2);
-    A.k3 = (int32_t*)L.l_k3.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
-    A.cost = (int32_t*)L.l_cost.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
-    A.total = (int32_t*)L.l_total.ensure((size_t)std::max<uint32_t>(n_loc, 1) * 4);
-    A.hist = (uint32_t*)c->hist.ensure(nbins * 4, true);
-    CK(cudaMemsetAsync(A.hist, 0, nbins * 4, s));
-    c->launches += launch_assign(A, s);
-    CK(cudaGetLastError());
-    int64_t cells = 0;
-    ScoreView V{frontier_of(L), n_loc, L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(), L.l_k3.as<int32_t>(),
-                L.l_cost.as<int32_t>(), L.l_total.as<int32_t>()};
-    int* dummy_best = (int*)c->flag.ensure(16, true);  // best is taken from the merged records
-    CK(cudaMemsetAsync(dummy_best, 0, 8, s));
-    run_scoring(c, V, A.hist, lcap, L.nrid.as<uint16_t>(), 0, o.flags, dummy_best, &cells);
-    rst[0].cells[d - 1] = cells;  // cells evaluated by THIS rank (includes candidates another rank discovered first)
-    CK(spin_sync(s));
-    return n_loc;
-  }
-
-  void dist_pack(void* out) {
-    Level& L = lv[cur_level];
-    if (!L.n_local_new) return;
-    c->launches += launch_dist_pack(curE, L.newlist.as<uint32_t>(), L.n_local_new, L.l_k3.as<int32_t>(),
-                                    L.l_cost.as<int32_t>(), L.l_total.as<int32_t>(), out, c->stream);
-    CK(spin_sync(c->stream));
-    CK(cudaGetLastError());
-  }
-
-  // all: world segments of `stride` records each, segment r holding counts[r] records.  Identical on every rank.
-  void dist_merge(const void* all, const int64_t* counts, int64_t stride) {
-    cudaStream_t s = c->stream;
-    const int d = cur_level;
-    const int D = std::min(o.maxdepth, MAX_LEVELS - 1);
-    int32_t* misc = (int32_t*)c->misc.p;
-    {
-      Level& L = lv[d];
-      const DistRec* rec = (const DistRec*)all;
-      uint32_t n_new = 0;
-      if (L.G_all) {
-        uint32_t* rslot = (uint32_t*)c->rslot.ensure((size_t)std::max<int64_t>(world * stride, 1) * 4, true);
-        for (int r = 0; r < world; ++r)
-          c->launches += launch_dist_merge_insert(rec + (size_t)r * stride, (uint32_t)counts[r], c->table.as<uint64_t>(),
-                                                  c->table_cap - 1, rslot + (size_t)r * stride, s);
-        uint32_t* newflag = (uint32_t*)c->newflag.ensure((size_t)L.G_all * 4, true);
-        uint32_t* grank = (uint32_t*)c->grank.ensure((size_t)L.G_all * 4, true);
-        CK(cudaMemsetAsync(newflag, 0, (size_t)L.G_all * 4, s));
-        for (int r = 0; r < world; ++r)
-          c->launches += launch_dist_merge_flag(rec + (size_t)r * stride, (uint32_t)counts[r], rslot + (size_t)r * stride,
-                                                c->table.as<uint64_t>(), L.gbase, newflag, s);
-        uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.G_all) * 4, true);
-        c->launches += launch_scan(newflag, grank, L.G_all, bsum, (uint32_t*)(misc + 5), s);
-        d2h(c, pin_u32(), misc, 32);
-        CK(spin_sync(s));
-        n_new = pin_u32()[5];
-        L.n_new = n_new;
-        const size_t nn = std::max<uint32_t>(n_new, 1);
-        L.k3.ensure(nn * 4);
-        L.cost.ensure(nn * 4);
-        L.total.ensure(nn * 4);
-        L.desc_new.ensure(nn * 8);
-        L.gid_at.ensure((size_t)L.G_all * 4);
-        CK(cudaMemsetAsync(L.gid_at.p, 0, (size_t)L.G_all * 4, s));
-        for (int r = 0; r < world; ++r)
-          c->launches += launch_dist_scatter(rec + (size_t)r * stride, (uint32_t)counts[r], rslot + (size_t)r * stride,
-                                             c->table.as<uint64_t>(), L.gbase, grank, L.id_base, L.k3.as<int32_t>(),
-                                             L.cost.as<int32_t>(), L.total.as<int32_t>(), L.desc_new.as<uint64_t>(),
-                                             L.gid_at.as<int32_t>(), c->best.as<int>(), s);
-        if (L.G) {  // ids of the indices this rank's candidates produced (provenance edges)
-          LevelTable LT{};
-          LT.n_levels = d + 1;
-          for (int l = 0; l <= d; ++l) {
-            LT.gbase[l] = lv[l].gbase;
-            LT.cand_id[l] = l == 0 ? lv[0].cand_id.as<int32_t>() : lv[l].gid_at.as<int32_t>();
-          }
-          LT.gbase[d + 1] = L.gbase + L.G_all;
-          c->launches += launch_dist_cand_id(curE.slot, c->table.as<uint64_t>(), LT, L.G,
-                                             (int32_t*)L.cand_id.ensure((size_t)L.G * 4), s);
-        }
-      }
-      rst[0].scored[d - 1] = n_new;
-      L.cstart = {0u, L.G};
-      L.nstart = {0u, n_new};
-      gtotal += L.G_all;
-      n_ids += (int32_t)n_new;
-      level_maxlen = dist_maxlen;
-    }
-    bool more = false;
-    if (d < D) {
-      select_next(d);
-      more = lv[d].n_new > 0 && lv[d + 1].P > 0;
-    }
-    CK(spin_sync(s));
-    CK(cudaGetLastError());
-    lv[d].fblob.release();
-    if (!more) {
-      pad_levels(D);
-      CK(cudaEventRecord(ev1, s));
-      CK(spin_sync(s));
-      finish_stats(D);
-    }
-    dist_more = more;
-    cur_level = d + 1;
-  }
-
-  void dist_report_begin(uint8_t* needed) {
-    int k3_star;
-    int64_t quota;
-    report_thresholds(dist_k3_min, k3_star, quota);
-    extract_good(needed, dist_k3_min, k3_star, quota);
-    CK(spin_sync(c->stream));
-    CK(cudaGetLastError());
-  }
-  void dist_finish(const uint8_t* needed, const void* all, const int64_t* counts, int64_t stride, nw_result* R) {
-    std::vector<EdgeRec> edges;
-    for (int r = 0; r < world; ++r) {
-      if (!counts[r]) continue;
-      const size_t at = edges.size();
-      edges.resize(at + (size_t)counts[r]);
-      d2h(c, edges.data() + at, (const EdgeRec*)all + (size_t)r * stride, (size_t)counts[r] * sizeof(EdgeRec));
-    }
-    CK(spin_sync(c->stream));
-    build_nodes(needed, edges);
-    build_local_ids();
-    enumerate(R, 0, dist_k3_min);
   }
 
   // ---- report: get_good_trajectories (solver.jl:727-745) ----
@@ -1498,9 +1281,7 @@ struct Search {
       for (int l = 1; l < nl; ++l) {
         const Level& L = lv[l];
         c->launches += launch_edge_append(L.cand_id.as<int32_t>(), L.desc.as<uint64_t>(), L.fid.as<int32_t>(), L.G, needed,
-                                          nrank, l, o.maxdepth, L.gbase, world > 1 ? L.off_loc.as<uint32_t>() : nullptr,
-                                          world > 1 ? L.off_glob.as<uint32_t>() : nullptr, buf, cap,
-                                          (uint32_t*)(misc + 8), s);
+                                          nrank, l, o.maxdepth, L.gbase, buf, cap, (uint32_t*)(misc + 8), s);
       }
       d2h(c, pin_u32(), misc, 64);
       CK(spin_sync(s));
@@ -1986,8 +1767,9 @@ void check_opts(const nw_opts* o) {
 
 // Searches R regions together through one pipeline instance (R == 1: the plain single search).  out[r] receives
 // region r's report and statistics; timings / launch counts / byte counts are those of the whole batch.
-void do_solve_many(nw_ctx* c, const ProblemRef* probs, int R, const nw_opts* o, nw_result** out) {
+void do_solve_many(nw_ctx* c, const ProblemRef* probs, int R, const nw_opts* o, nw_result** out, Exchange* xch = nullptr) {
   CK(cudaSetDevice(c->device));
+  if (xch && R != 1) fail(NW_ERR_ARG, "a sharded search holds one region");
   c->launches = 0;
   c->h2d_bytes = c->d2h_bytes = 0;
   collect_score_time(c, nullptr, nullptr);
@@ -1998,6 +1780,11 @@ void do_solve_many(nw_ctx* c, const ProblemRef* probs, int R, const nw_opts* o, 
   const auto t0 = now();
   setup_regions(c, probs, R, o->maxdepth, NW_BAND_JULIA);
   Search S(c, *o);
+  if (xch && xch->world() > 1) {
+    S.xch = xch;
+    S.rank = xch->rank();
+    S.world = xch->world();
+  }
   const auto t1 = now();
   S.run();
   const auto t2 = now();
@@ -2136,8 +1923,9 @@ int nw_ctx_create(int device, nw_ctx** out) {
 void nw_ctx_destroy(nw_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  nw_dist_abort(c);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  delete c->xch;
+  c->xch = nullptr;
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->rg_pinned) cudaFreeHost(c->rg_pinned);
   if (c->rg_dev) cudaFree(c->rg_dev);
@@ -2643,152 +2431,63 @@ int nw_solve_batch(nw_ctx** ctxs, int32_t n_ctx, const nw_problem* probs, int64_
 }
 
 // ---------------------------------------------------------------------------------------------------
-// frontier-sharded single search: see include/nwsolve.h for the protocol
+// frontier-sharded single search (BASELINE config 3): see include/nwsolve.h
 // ---------------------------------------------------------------------------------------------------
-static Search* dist_of(nw_ctx* c) {
-  if (!c || !c->dist) fail(NW_ERR_ARG, "no sharded search in progress (call nw_dist_begin first)");
-  return static_cast<Search*>(c->dist);
+int nw_dist_unique_id(void* id128) {
+  if (!id128) return NW_ERR_ARG;
+  return guard([&] {
+    try {
+      nccl_unique_id(id128);
+    } catch (const ExchangeError& e) {
+      fail(NW_ERR_CUDA, e.msg);
+    }
+  });
 }
-void nw_dist_abort(nw_ctx* c) {
-  if (!c || !c->dist) return;
-  PoolScope pool_scope(c);
-  cudaSetDevice(c->device);
-  delete static_cast<Search*>(c->dist);
-  c->dist = nullptr;
-}
-int nw_dist_begin(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const int64_t* len_x, const int64_t* len_y,
-                  const nw_opts* o, int32_t rank, int32_t world) {
-  if (!c || !aln || !len_x || !len_y) {
+int nw_dist_init(nw_ctx* c, const void* id128, int32_t rank, int32_t world) {
+  if (!c || !id128) {
     g_last_error = "null argument";
     return NW_ERR_ARG;
   }
-  nw_dist_abort(c);
+  return guard([&] {
+    if (world < 1 || rank < 0 || rank >= world) fail(NW_ERR_ARG, "bad rank/world");
+    CK(cudaSetDevice(c->device));
+    delete c->xch;
+    c->xch = nullptr;
+    try {
+      c->xch = nccl_exchange_create(id128, rank, world);
+    } catch (const ExchangeError& e) {
+      fail(NW_ERR_CUDA, e.msg);
+    }
+  });
+}
+void nw_dist_shutdown(nw_ctx* c) {
+  if (!c || !c->xch) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  delete c->xch;
+  c->xch = nullptr;
+}
+int nw_dist_info(nw_ctx* c, int32_t* rank, int32_t* world) {
+  if (!c) return NW_ERR_ARG;
+  if (rank) *rank = c->xch ? c->xch->rank() : 0;
+  if (world) *world = c->xch ? c->xch->world() : 1;
+  return NW_OK;
+}
+int nw_solve_sharded(nw_ctx* c, const int8_t* aln, int32_t n_x, int32_t n_y, const int64_t* len_x, const int64_t* len_y,
+                     const nw_opts* o, nw_result** out) {
+  if (!c || !aln || !len_x || !len_y || !out) {
+    g_last_error = "null argument";
+    return NW_ERR_ARG;
+  }
+  *out = nullptr;
+  nw_result* R = new nw_result();
   PoolScope pool_scope(c);
   const int rc = guard([&] {
     check_opts(o);
-    if (world < 1 || rank < 0 || rank >= world) fail(NW_ERR_ARG, "bad rank/world");
-    CK(cudaSetDevice(c->device));
-    c->launches = 0;
-    c->h2d_bytes = c->d2h_bytes = 0;
-    collect_score_time(c, nullptr, nullptr);
-    {
-      const ProblemRef P{aln, n_x, n_y, len_x, len_y};
-      setup_regions(c, &P, 1, o->maxdepth, NW_BAND_JULIA);
-    }
-    Search* S = new Search(c, *o);
-    c->dist = S;
-    S->rank = rank;
-    S->world = world;
-    S->dist_begin();
+    if (!c->xch) fail(NW_ERR_ARG, "nw_solve_sharded: the context has no communicator (call nw_dist_init first)");
+    const ProblemRef P{aln, n_x, n_y, len_x, len_y};
+    do_solve_many(c, &P, 1, o, &R, c->xch);
   });
-  if (rc != NW_OK) {
-    cudaGetLastError();
-    nw_dist_abort(c);
-  }
-  return rc;
-}
-int nw_dist_expand(nw_ctx* c, int64_t* n_records) {
-  PoolScope pool_scope(c);
-  const int rc = guard([&] {
-    Search* S = dist_of(c);
-    CK(cudaSetDevice(c->device));
-    if (!S->dist_more) fail(NW_ERR_ARG, "the sharded search has no further level");
-    const int64_t n = S->dist_expand();
-    if (n_records) *n_records = n;
-  });
-  if (rc != NW_OK) cudaGetLastError();
-  return rc;
-}
-int nw_dist_pack(nw_ctx* c, void* dev_out) {
-  PoolScope pool_scope(c);
-  const int rc = guard([&] {
-    Search* S = dist_of(c);
-    CK(cudaSetDevice(c->device));
-    S->dist_pack(dev_out);
-  });
-  if (rc != NW_OK) cudaGetLastError();
-  return rc;
-}
-int nw_dist_merge(nw_ctx* c, const void* dev_all, const int64_t* counts, int64_t stride_records, int32_t* more) {
-  PoolScope pool_scope(c);
-  const int rc = guard([&] {
-    Search* S = dist_of(c);
-    CK(cudaSetDevice(c->device));
-    if (!counts) fail(NW_ERR_ARG, "counts is null");
-    S->dist_merge(dev_all, counts, stride_records);
-    if (more) *more = S->dist_more ? 1 : 0;
-  });
-  if (rc != NW_OK) cudaGetLastError();
-  return rc;
-}
-int64_t nw_dist_n_ids(nw_ctx* c) { return (c && c->dist) ? (int64_t) static_cast<Search*>(c->dist)->n_ids : -1; }
-int nw_dist_report_begin(nw_ctx* c, void* needed_dev, int64_t nbytes) {
-  PoolScope pool_scope(c);
-  const int rc = guard([&] {
-    Search* S = dist_of(c);
-    CK(cudaSetDevice(c->device));
-    if (!needed_dev || nbytes < (int64_t)S->n_ids + 16) fail(NW_ERR_ARG, "needed buffer must hold n_ids + 16 bytes");
-    collect_score_time(c, &S->rst[0].score_ms, &S->rst[0].score_launches);
-    S->dist_report_begin((uint8_t*)needed_dev);
-  });
-  if (rc != NW_OK) cudaGetLastError();
-  return rc;
-}
-int nw_dist_report_mark(nw_ctx* c, void* needed_dev, int32_t pass) {
-  PoolScope pool_scope(c);
-  const int rc = guard([&] {
-    Search* S = dist_of(c);
-    CK(cudaSetDevice(c->device));
-    S->extract_mark((uint8_t*)needed_dev, pass);
-    CK(spin_sync(c->stream));
-    CK(cudaGetLastError());
-  });
-  if (rc != NW_OK) cudaGetLastError();
-  return rc;
-}
-int nw_dist_report_edges(nw_ctx* c, const void* needed_dev, int64_t* n_edges) {
-  PoolScope pool_scope(c);
-  const int rc = guard([&] {
-    Search* S = dist_of(c);
-    CK(cudaSetDevice(c->device));
-    const uint32_t n = S->extract_edges((uint8_t*)needed_dev);
-    S->dist_edges = n;
-    if (n_edges) *n_edges = n;
-  });
-  if (rc != NW_OK) cudaGetLastError();
-  return rc;
-}
-int nw_dist_report_pack(nw_ctx* c, void* dev_out) {
-  PoolScope pool_scope(c);
-  const int rc = guard([&] {
-    Search* S = dist_of(c);
-    CK(cudaSetDevice(c->device));
-    if (S->dist_edges) {
-      CK(cudaMemcpyAsync(dev_out, c->edgebuf.p, (size_t)S->dist_edges * sizeof(EdgeRec), cudaMemcpyDeviceToDevice,
-                         c->stream));
-      CK(spin_sync(c->stream));
-    }
-  });
-  if (rc != NW_OK) cudaGetLastError();
-  return rc;
-}
-int nw_dist_finish(nw_ctx* c, const void* needed_dev, const void* dev_edges_all, const int64_t* counts,
-                   int64_t stride_edges, nw_result** out) {
-  if (!out) return NW_ERR_ARG;
-  *out = nullptr;
-  PoolScope pool_scope(c);
-  nw_result* R = new nw_result();
-  const int rc = guard([&] {
-    Search* S = dist_of(c);
-    CK(cudaSetDevice(c->device));
-    if (!counts) fail(NW_ERR_ARG, "counts is null");
-    S->dist_finish((const uint8_t*)needed_dev, dev_edges_all, counts, stride_edges, R);
-    S->rst[0].kernel_launches = c->launches;
-    S->rst[0].h2d_bytes = c->h2d_bytes;
-    S->rst[0].d2h_bytes = c->d2h_bytes;
-    R->stats = S->rst[0];
-  });
-  nw_dist_abort(c);
   if (rc != NW_OK) {
     delete R;
     cudaGetLastError();
@@ -2796,6 +2495,76 @@ int nw_dist_finish(nw_ctx* c, const void* needed_dev, const void* dev_edges_all,
   }
   *out = R;
   return NW_OK;
+}
+int nw_solve_sharded_ctxs(nw_ctx** ctxs, int32_t world, const int8_t* aln, int32_t n_x, int32_t n_y, const int64_t* len_x,
+                          const int64_t* len_y, const nw_opts* o, nw_result** outs) {
+  if (!ctxs || world < 1 || !aln || !len_x || !len_y || !o || !outs) {
+    g_last_error = "null argument";
+    return NW_ERR_ARG;
+  }
+  for (int r = 0; r < world; ++r) {
+    outs[r] = nullptr;
+    if (!ctxs[r]) {
+      g_last_error = "null context";
+      return NW_ERR_ARG;
+    }
+    for (int q = 0; q < r; ++q)
+      if (ctxs[q] == ctxs[r]) {
+        g_last_error = "nw_solve_sharded_ctxs: every rank needs its own context";
+        return NW_ERR_ARG;
+      }
+  }
+  // direct peer copies between the ranks' devices (NVLink) where the contexts sit on different GPUs
+  for (int r = 0; r < world; ++r)
+    for (int q = 0; q < world; ++q)
+      if (ctxs[r]->device != ctxs[q]->device) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, ctxs[r]->device, ctxs[q]->device);
+        if (can) {
+          cudaSetDevice(ctxs[r]->device);
+          cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+          cudaGetLastError();  // already enabled is fine
+        }
+      }
+  std::shared_ptr<LocalGroup> grp = local_group_create(world);
+  std::vector<int> rcs(world, NW_OK);
+  std::vector<std::string> msgs(world);
+  std::vector<nw_result*> res(world, nullptr);
+  auto worker = [&](int r) {
+    nw_ctx* c = ctxs[r];
+    PoolScope pool_scope(c);
+    std::unique_ptr<Exchange> x(local_exchange_create(grp, r, c->device));
+    res[r] = new nw_result();
+    rcs[r] = guard([&] {
+      check_opts(o);
+      const ProblemRef P{aln, n_x, n_y, len_x, len_y};
+      nw_result* R = res[r];
+      do_solve_many(c, &P, 1, o, &R, x.get());
+    });
+    if (rcs[r] != NW_OK) {
+      msgs[r] = g_last_error;
+      x->abort();  // the other ranks stop at their next exchange instead of waiting for this one
+      cudaGetLastError();
+    }
+  };
+  std::vector<std::thread> th;
+  for (int r = 1; r < world; ++r) th.emplace_back(worker, r);
+  worker(0);
+  for (auto& t : th) t.join();
+  int rc = NW_OK;
+  for (int r = 0; r < world && rc == NW_OK; ++r)
+    if (rcs[r] != NW_OK) {
+      rc = rcs[r];
+      g_last_error = "rank " + std::to_string(r) + ": " + msgs[r];
+    }
+  for (int r = 0; r < world; ++r) {
+    if (rc == NW_OK) {
+      outs[r] = res[r];
+    } else {
+      delete res[r];
+    }
+  }
+  return rc;
 }
 
 int nw_bench_peaks(nw_ctx* c, double out[4]) {

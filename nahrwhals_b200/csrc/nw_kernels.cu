@@ -111,7 +111,6 @@ __global__ void __launch_bounds__(128) k_expand_pairs(ExpandArgs A) {
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t s_warp_tot[4];
   const int parent = blockIdx.x;
-  if (EMIT && A.own_mod > 1 && parent % A.own_mod != A.own_rem) return;  // another rank expands this parent
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = A.F.len[parent];
   const int LS = A.F.LS;
@@ -261,7 +260,6 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
   __shared__ uint32_t s_tot;
   __shared__ int s_maxlen;
   const int parent = blockIdx.x;
-  if (EMIT && A.own_mod > 1 && parent % A.own_mod != A.own_rem) return;  // another rank expands this parent
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = A.F.len[parent];
   const int LS = A.F.LS;
@@ -401,7 +399,7 @@ __global__ void __launch_bounds__(256) k_hash_insert(ExpandArgs A, uint32_t G) {
     f.v[0] &= 0xffu;
     f.v[1] = f.v[2] = f.v[3] = 0;
   }
-  A.slot[pos] = table_insert(A.table, A.tmask, fp_key0(f), fp_key1(f), (uint64_t)cand_gpos(A, pos, ps));
+  A.slot[pos] = table_insert(A.table, A.tmask, fp_key0(f), fp_key1(f), (uint64_t)A.gbase + pos);
 }
 int launch_hash_insert(const ExpandArgs& A, uint32_t G, cudaStream_t st) {
   if (G == 0) return 0;
@@ -535,8 +533,7 @@ uint64_t scan_scratch_items(uint64_t n) { return (n + SCAN_B - 1) / SCAN_B + 1; 
 // =====================================================================================================
 // resolve / assign: which candidate is the first discoverer of its index (solver.jl:535-561)
 // =====================================================================================================
-// four candidates per thread: four independent random table reads in flight; the descriptor is only needed for the
-// global position of a sharded search
+// four candidates per thread: four independent random table reads in flight
 __global__ void __launch_bounds__(256) k_resolve(ExpandArgs A, uint32_t G, uint32_t* is_new, uint32_t* owner) {
   const uint32_t pos0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
   if (pos0 >= G) return;
@@ -547,15 +544,14 @@ __global__ void __launch_bounds__(256) k_resolve(ExpandArgs A, uint32_t G, uint3
 #pragma unroll
     for (int q = 0; q < 4; ++q) o[q] = (uint32_t)__ldg(&A.table[(uint64_t)s4[q] * TBL_WORDS + 2]);  // the random reads
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      g[q] = A.off_glob ? cand_gpos(A, pos0 + q, desc_parent(A.desc[pos0 + q])) : A.gbase + pos0 + q;
+    for (int q = 0; q < 4; ++q) g[q] = A.gbase + pos0 + q;
     *reinterpret_cast<uint4*>(owner + pos0) = make_uint4(o[0], o[1], o[2], o[3]);
     *reinterpret_cast<uint4*>(is_new + pos0) =
         make_uint4(o[0] == g[0] ? 1u : 0u, o[1] == g[1] ? 1u : 0u, o[2] == g[2] ? 1u : 0u, o[3] == g[3] ? 1u : 0u);
     return;
   }
   for (uint32_t pos = pos0; pos < G; ++pos) {
-    const uint32_t g = A.off_glob ? cand_gpos(A, pos, desc_parent(A.desc[pos])) : A.gbase + pos;
+    const uint32_t g = A.gbase + pos;
     const uint32_t o = (uint32_t)A.table[(uint64_t)A.slot[pos] * TBL_WORDS + 2];
     owner[pos] = o;
     is_new[pos] = o == g ? 1u : 0u;
@@ -574,7 +570,7 @@ __device__ __forceinline__ int assign_one(const AssignArgs& A, uint32_t pos, uin
                                           uint64_t d) {
   int key = -1;  // histogram key (region, child length, sub-counter) of candidates that need a DP; -1 = none
   if (fresh) {
-    if (!A.skip_ids) A.cand_id[pos] = A.id_base + (int32_t)r;
+    A.cand_id[pos] = A.id_base + (int32_t)r;
     A.newlist[r] = pos;
     const uint32_t ps = desc_parent(d);
     const int len = child_len(A.front_len[ps], desc_kind(d), desc_i(d), desc_j(d));
@@ -585,10 +581,10 @@ __device__ __forceinline__ int assign_one(const AssignArgs& A, uint32_t pos, uin
       A.k3[r] = 0;
       A.cost[r] = -1;
       A.total[r] = 0;
-    } else {
+    } else if (owns(A.own, r)) {  // sharded search: another rank scores the rest (exchange after the DP)
       key = bucket_key(rid, A.lcap, len, r);
     }
-  } else if (!A.skip_ids) {
+  } else {
     A.cand_id[pos] = own >= A.gbase ? A.id_base + (int32_t)A.newrank[own - A.gbase] : owner_id(A.LT, own);
   }
   return key;
@@ -639,7 +635,8 @@ int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* is_new, uint32_t* 
 constexpr int SCAT_SLOTS = 64;
 __global__ void __launch_bounds__(1024) k_bucket_scatter(const uint16_t* new_len, const uint16_t* new_rid,
                                                          const RegionDev* regions, int lcap, uint32_t n_new, int force,
-                                                         const uint32_t* bstart, uint32_t* cursor, uint32_t* work) {
+                                                         OwnRange own, const uint32_t* bstart, uint32_t* cursor,
+                                                         uint32_t* work) {
   __shared__ int s_key[SCAT_SLOTS];
   __shared__ uint32_t s_cnt[SCAT_SLOTS], s_base[SCAT_SLOTS];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -650,7 +647,7 @@ __global__ void __launch_bounds__(1024) k_bucket_scatter(const uint16_t* new_len
   __syncthreads();
   const uint32_t r = blockIdx.x * blockDim.x + tid;
   int key = -1;
-  if (r < n_new) {
+  if (r < n_new && owns(own, r)) {
     const int len = new_len[r], rid = new_rid[r];
     if (force || !early_exit(len, regions[rid].n_y)) key = bucket_key(rid, lcap, len, r);
   }
@@ -680,10 +677,23 @@ __global__ void __launch_bounds__(1024) k_bucket_scatter(const uint16_t* new_len
   if (key >= 0) work[bstart[key] + wbase + mine] = r;
 }
 int launch_bucket_scatter(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap,
-                          uint32_t n_new, int force, const uint32_t* bstart, uint32_t* cursor, uint32_t* work,
-                          cudaStream_t st) {
+                          uint32_t n_new, int force, const OwnRange& own, const uint32_t* bstart, uint32_t* cursor,
+                          uint32_t* work, cudaStream_t st) {
   if (n_new == 0) return 0;
-  k_bucket_scatter<<<(n_new + 1023) / 1024, 1024, 0, st>>>(new_len, new_rid, regions, lcap, n_new, force, bstart, cursor, work);
+  k_bucket_scatter<<<(n_new + 1023) / 1024, 1024, 0, st>>>(new_len, new_rid, regions, lcap, n_new, force, own, bstart, cursor,
+                                                          work);
+  return 1;
+}
+// best score of a level over ALL fresh candidates (sharded search: the DP kernels only saw this rank's share)
+__global__ void k_max_k3(const int32_t* k3, uint32_t n, int* best) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  int b = r < n ? k3[r] : 0;
+  for (int o = 16; o; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+  if ((threadIdx.x & 31) == 0 && b > 0) atomicMax(best, b);
+}
+int launch_max_k3(const int32_t* k3, uint32_t n, int* best, cudaStream_t st) {
+  if (!n) return 0;
+  k_max_k3<<<(n + 255) / 256, 256, 0, st>>>(k3, n, best);
   return 1;
 }
 
@@ -1220,8 +1230,7 @@ __global__ void k_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* 
   flag[pos] = (v && lvl + v <= maxdepth + 2) ? 1u : 0u;
 }
 __global__ void k_edge_compact(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
-                               const uint32_t* flag, const uint32_t* pre, uint32_t gbase, const uint32_t* off_loc,
-                               const uint32_t* off_glob, EdgeRec* out) {
+                               const uint32_t* flag, const uint32_t* pre, uint32_t gbase, EdgeRec* out) {
   const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= G || !flag[pos]) return;
   const uint64_t d = desc[pos];
@@ -1230,7 +1239,7 @@ __global__ void k_edge_compact(const int32_t* cand_id, const uint64_t* desc, con
   e.child = cand_id[pos];
   e.parent = front_id[ps];
   e.move = (uint32_t)desc_kind(d) | ((uint32_t)desc_i(d) << 2) | ((uint32_t)desc_j(d) << 17);
-  e.gpos = off_glob ? gbase + off_glob[ps] + (pos - off_loc[ps]) : gbase + pos;
+  e.gpos = gbase + pos;
   out[pre[pos]] = e;
 }
 __global__ void k_id_flags(const uint8_t* needed, int32_t id_base, uint32_t n, uint32_t* flag) {
@@ -1264,8 +1273,7 @@ __device__ __forceinline__ uint32_t warp_append(bool take, uint32_t* counter) {
 // needed flags; -1 = parent not needed), so the host builds its graph without any search
 __global__ void k_edge_append(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
                               const uint8_t* needed, const uint32_t* nrank, int lvl, int maxdepth, uint32_t gbase,
-                              const uint32_t* off_loc, const uint32_t* off_glob, EdgeRec* out, uint32_t cap,
-                              uint32_t* counter) {
+                              EdgeRec* out, uint32_t cap, uint32_t* counter) {
   const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
   bool take = false;
   int32_t child = 0;
@@ -1283,7 +1291,7 @@ __global__ void k_edge_append(const int32_t* cand_id, const uint64_t* desc, cons
   e.child = (int32_t)nrank[child];
   e.parent = needed[pid] ? (int32_t)nrank[pid] : -1;
   e.move = (uint32_t)desc_kind(d) | ((uint32_t)desc_i(d) << 2) | ((uint32_t)desc_j(d) << 17);
-  e.gpos = off_glob ? gbase + off_glob[ps] + (pos - off_loc[ps]) : gbase + pos;
+  e.gpos = gbase + pos;
   out[at] = e;
 }
 // record of every needed id of a level, written at its node index (ascending id order, no sort on the host)
@@ -1316,12 +1324,11 @@ __global__ void k_id_append(const int32_t* k3, const int32_t* cost, const int32_
   out[at] = o;
 }
 int launch_edge_append(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
-                       const uint8_t* needed, const uint32_t* nrank, int lvl, int maxdepth, uint32_t gbase,
-                       const uint32_t* off_loc, const uint32_t* off_glob, void* out, uint32_t cap, uint32_t* counter,
-                       cudaStream_t st) {
+                       const uint8_t* needed, const uint32_t* nrank, int lvl, int maxdepth, uint32_t gbase, void* out,
+                       uint32_t cap, uint32_t* counter, cudaStream_t st) {
   if (!G) return 0;
-  k_edge_append<<<(G + 255) / 256, 256, 0, st>>>(cand_id, desc, front_id, G, needed, nrank, lvl, maxdepth, gbase, off_loc,
-                                                off_glob, (EdgeRec*)out, cap, counter);
+  k_edge_append<<<(G + 255) / 256, 256, 0, st>>>(cand_id, desc, front_id, G, needed, nrank, lvl, maxdepth, gbase,
+                                                (EdgeRec*)out, cap, counter);
   return 1;
 }
 int launch_id_write(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,
@@ -1405,11 +1412,9 @@ int launch_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* needed,
   return 1;
 }
 int launch_edge_compact(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
-                        const uint32_t* flag, const uint32_t* pre, uint32_t gbase, const uint32_t* off_loc,
-                        const uint32_t* off_glob, void* out, cudaStream_t st) {
+                        const uint32_t* flag, const uint32_t* pre, uint32_t gbase, void* out, cudaStream_t st) {
   if (!G) return 0;
-  k_edge_compact<<<(G + 255) / 256, 256, 0, st>>>(cand_id, desc, front_id, G, flag, pre, gbase, off_loc, off_glob,
-                                                 (EdgeRec*)out);
+  k_edge_compact<<<(G + 255) / 256, 256, 0, st>>>(cand_id, desc, front_id, G, flag, pre, gbase, (EdgeRec*)out);
   return 1;
 }
 int launch_id_flags(const uint8_t* needed, int32_t id_base, uint32_t n, uint32_t* flag, cudaStream_t st) {
@@ -1456,100 +1461,6 @@ int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t
                        unsigned int* mismatches, cudaStream_t st) {
   if (!G) return 0;
   k_verify_dups<<<(G + 255) / 256, 256, 0, st>>>(A, V, is_new, owner, G, mismatches);
-  return 1;
-}
-
-// =====================================================================================================
-// frontier-sharded search (one deep search over several ranks).  Each rank expands the parents it owns,
-// dedups locally, scores its locally-first candidates and contributes one DistRec per such candidate to a per-level
-// all-gather.  Every rank then runs the same merge: min discovery position per fingerprint over all ranks decides
-// the owner (exactly the serial first-discoverer rule of solver.jl:535), ids follow global discovery order.
-// =====================================================================================================
-__global__ void k_mask_counts(const uint32_t* cnt, uint32_t P, int own_mod, int own_rem, uint32_t* out) {
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < P) out[s] = ((int)(s % (uint32_t)own_mod) == own_rem) ? cnt[s] : 0u;
-}
-__global__ void k_dist_pack(ExpandArgs A, const uint32_t* newlist, uint32_t n_new, const int32_t* k3, const int32_t* cost,
-                            const int32_t* total, DistRec* out) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_new) return;
-  const uint32_t pos = newlist[r];
-  const uint64_t s = A.slot[pos];
-  DistRec o;
-  o.k0 = A.table[s * TBL_WORDS];
-  o.k1 = A.table[s * TBL_WORDS + 1];
-  o.desc = A.desc[pos];
-  o.gpos = cand_gpos(A, pos, desc_parent(o.desc));
-  o.k3 = k3[r];
-  o.cost = cost[r];
-  o.total = total[r];
-  out[r] = o;
-}
-__global__ void k_dist_merge_insert(const DistRec* rec, uint32_t n, uint64_t* table, uint64_t mask, uint32_t* slot) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  slot[i] = table_insert(table, mask, rec[i].k0, rec[i].k1, (uint64_t)rec[i].gpos);
-}
-__global__ void k_dist_merge_flag(const DistRec* rec, uint32_t n, const uint32_t* slot, const uint64_t* table,
-                                  uint32_t gbase, uint32_t* newflag) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (table[(uint64_t)slot[i] * TBL_WORDS + 2] == (uint64_t)rec[i].gpos) newflag[rec[i].gpos - gbase] = 1u;
-}
-__global__ void k_dist_scatter(const DistRec* rec, uint32_t n, const uint32_t* slot, const uint64_t* table, uint32_t gbase,
-                               const uint32_t* grank, int32_t id_base, int32_t* k3, int32_t* cost, int32_t* total,
-                               uint64_t* desc_new, int32_t* gid_at, int* best_k3) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const DistRec o = rec[i];
-  if (table[(uint64_t)slot[i] * TBL_WORDS + 2] != (uint64_t)o.gpos) return;  // a smaller position owns this index
-  const uint32_t r = grank[o.gpos - gbase];
-  k3[r] = o.k3;
-  cost[r] = o.cost;
-  total[r] = o.total;
-  desc_new[r] = o.desc;
-  gid_at[o.gpos - gbase] = id_base + (int32_t)r;
-  if (o.k3 > 0) atomicMax(best_k3, o.k3);
-}
-__global__ void k_dist_cand_id(const uint32_t* slot, const uint64_t* table, LevelTable LT, uint32_t G, int32_t* cand_id) {
-  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= G) return;
-  cand_id[pos] = owner_id(LT, (uint32_t)table[(uint64_t)slot[pos] * TBL_WORDS + 2]);
-}
-int launch_mask_counts(const uint32_t* cnt, uint32_t P, int own_mod, int own_rem, uint32_t* out, cudaStream_t st) {
-  if (!P) return 0;
-  k_mask_counts<<<(P + 255) / 256, 256, 0, st>>>(cnt, P, own_mod, own_rem, out);
-  return 1;
-}
-int launch_dist_pack(const ExpandArgs& A, const uint32_t* newlist, uint32_t n_new, const int32_t* k3, const int32_t* cost,
-                     const int32_t* total, void* out, cudaStream_t st) {
-  if (!n_new) return 0;
-  k_dist_pack<<<(n_new + 255) / 256, 256, 0, st>>>(A, newlist, n_new, k3, cost, total, (DistRec*)out);
-  return 1;
-}
-int launch_dist_merge_insert(const void* rec, uint32_t n, uint64_t* table, uint64_t mask, uint32_t* slot, cudaStream_t st) {
-  if (!n) return 0;
-  k_dist_merge_insert<<<(n + 255) / 256, 256, 0, st>>>((const DistRec*)rec, n, table, mask, slot);
-  return 1;
-}
-int launch_dist_merge_flag(const void* rec, uint32_t n, const uint32_t* slot, const uint64_t* table, uint32_t gbase,
-                           uint32_t* newflag, cudaStream_t st) {
-  if (!n) return 0;
-  k_dist_merge_flag<<<(n + 255) / 256, 256, 0, st>>>((const DistRec*)rec, n, slot, table, gbase, newflag);
-  return 1;
-}
-int launch_dist_scatter(const void* rec, uint32_t n, const uint32_t* slot, const uint64_t* table, uint32_t gbase,
-                        const uint32_t* grank, int32_t id_base, int32_t* k3, int32_t* cost, int32_t* total,
-                        uint64_t* desc_new, int32_t* gid_at, int* best_k3, cudaStream_t st) {
-  if (!n) return 0;
-  k_dist_scatter<<<(n + 255) / 256, 256, 0, st>>>((const DistRec*)rec, n, slot, table, gbase, grank, id_base, k3, cost,
-                                                 total, desc_new, gid_at, best_k3);
-  return 1;
-}
-int launch_dist_cand_id(const uint32_t* slot, const uint64_t* table, const LevelTable& LT, uint32_t G, int32_t* cand_id,
-                        cudaStream_t st) {
-  if (!G) return 0;
-  k_dist_cand_id<<<(G + 255) / 256, 256, 0, st>>>(slot, table, LT, G, cand_id);
   return 1;
 }
 

@@ -80,17 +80,25 @@ struct ExpandArgs {
   uint64_t tmask;
   uint32_t gbase;
   const U4* pw;
-  // frontier sharding (single deep search over several ranks): this rank owns parents with slot % own_mod == own_rem;
-  // `off` then holds offsets into the rank-local candidate arrays and off_glob the offsets in global discovery order.
-  int own_mod, own_rem;
-  const uint32_t* off_glob;  // nullptr: local == global
   int force_pairs;           // NW_FLAG_PAIR_EXPAND
   int weak_fp;               // NW_FLAG_DEBUG_WEAK_FP (tests only)
 };
 
-// global discovery position of the candidate stored at local position `pos` (parent slot ps)
-__device__ __forceinline__ uint32_t cand_gpos(const ExpandArgs& A, uint32_t pos, uint32_t ps) {
-  return A.off_glob ? A.gbase + A.off_glob[ps] + (pos - A.off[ps]) : A.gbase + pos;
+// Frontier-sharded search (one deep search over `world` ranks): expansion, dedup and selection are
+// replicated (deterministic, identical on every rank); only the banded DP -- the dominant cost -- is divided: rank r
+// scores the fresh candidates whose new-rank lies in [r * chunk, (r + 1) * chunk), chunk = own_chunk(n_new, world),
+// and one all-gather per level over the k3 / cost / total arrays (in place, `chunk` items per rank) completes them.
+// n_dev points at the level's fresh-candidate count in device memory (the host may not know it yet at launch time).
+struct OwnRange {
+  int world, rank;
+  const uint32_t* n_dev;
+};
+__host__ __device__ inline uint32_t own_chunk(uint32_t n, int world) {
+  const uint32_t c = (((n + (uint32_t)world - 1u) / (uint32_t)world) + 3u) & ~3u;  // multiple of 4: 16-B aligned segments
+  return c < 4u ? 4u : c;
+}
+__device__ __forceinline__ bool owns(const OwnRange& o, uint32_t r) {
+  return o.world <= 1 || r / own_chunk(*o.n_dev, o.world) == (uint32_t)o.rank;
 }
 
 // Everything needed to re-materialise the index a candidate of any finished level stands for (dedup verifier)
@@ -101,14 +109,6 @@ struct VerifyTable {
   const unsigned char* blob[MAX_LEVELS];
   uint32_t pstride[MAX_LEVELS];
   const int32_t* len[MAX_LEVELS];
-};
-
-// record exchanged between ranks for every locally-first candidate of a level (40 bytes)
-struct DistRec {
-  uint64_t k0, k1;  // fingerprint
-  uint64_t desc;    // (global parent slot, i, j, kind)
-  uint32_t gpos;    // global discovery position
-  int32_t k3, cost, total;
 };
 
 struct ScoreArgs {
@@ -146,7 +146,7 @@ struct AssignArgs {
   int lcap;                   // bins per region = lcap * NSUB
   uint16_t* new_rid;          // [n_new] out: region of every fresh candidate
   int force;
-  int skip_ids;     // sharded search: ids are assigned after the cross-rank merge
+  OwnRange own;     // sharded search: only this rank's share of the fresh candidates enters the DP histogram
   int32_t* cand_id;   // [G] out
   uint32_t* newlist;  // [n_new] out: rank -> pos
   uint16_t* new_len;  // [n_new] out: child length

@@ -30,8 +30,9 @@ int launch_bin_compact(const uint32_t* flag, const uint32_t* rank, const uint32_
 int launch_bucket_fill(const BinRec* ent, uint32_t n, const uint32_t* hist, uint32_t* bstart, uint32_t* cursor,
                        cudaStream_t st);
 int launch_bucket_scatter(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap,
-                          uint32_t n_new, int force, const uint32_t* bstart, uint32_t* cursor, uint32_t* work,
-                          cudaStream_t st);
+                          uint32_t n_new, int force, const OwnRange& own, const uint32_t* bstart, uint32_t* cursor,
+                          uint32_t* work, cudaStream_t st);
+int launch_max_k3(const int32_t* k3, uint32_t n, int* best, cudaStream_t st);
 int generic_threads();
 int launch_score_generic(const ScoreArgs& A, cudaStream_t st);
 int launch_valid_flags(const int32_t* k3, uint32_t n, uint32_t* flag, cudaStream_t st);
@@ -55,9 +56,8 @@ int launch_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, int k3_min
 int launch_tie_flags(const int32_t* k3, uint32_t n, int k3_star, uint32_t* flag, cudaStream_t st);
 int launch_k3_hist(const int32_t* k3, uint32_t n, int k3_floor, uint32_t* hist, cudaStream_t st);
 int launch_edge_append(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
-                       const uint8_t* needed, const uint32_t* nrank, int lvl, int maxdepth, uint32_t gbase,
-                       const uint32_t* off_loc, const uint32_t* off_glob, void* out, uint32_t cap, uint32_t* counter,
-                       cudaStream_t st);
+                       const uint8_t* needed, const uint32_t* nrank, int lvl, int maxdepth, uint32_t gbase, void* out,
+                       uint32_t cap, uint32_t* counter, cudaStream_t st);
 int launch_id_write(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,
                     const uint8_t* needed, const uint32_t* nrank, void* out, cudaStream_t st);
 int launch_needed_flags(const uint8_t* needed, uint32_t n, uint32_t* flag, cudaStream_t st);
@@ -68,19 +68,7 @@ int launch_mark_parents(const int32_t* cand_id, const uint64_t* desc, const int3
 int launch_edge_flags(const int32_t* cand_id, uint32_t G, const uint8_t* needed, uint32_t* flag, int lvl, int maxdepth,
                       cudaStream_t st);
 int launch_edge_compact(const int32_t* cand_id, const uint64_t* desc, const int32_t* front_id, uint32_t G,
-                        const uint32_t* flag, const uint32_t* pre, uint32_t gbase, const uint32_t* off_loc,
-                        const uint32_t* off_glob, void* out, cudaStream_t st);
-int launch_mask_counts(const uint32_t* cnt, uint32_t P, int own_mod, int own_rem, uint32_t* out, cudaStream_t st);
-int launch_dist_pack(const ExpandArgs& A, const uint32_t* newlist, uint32_t n_new, const int32_t* k3, const int32_t* cost,
-                     const int32_t* total, void* out, cudaStream_t st);
-int launch_dist_merge_insert(const void* rec, uint32_t n, uint64_t* table, uint64_t mask, uint32_t* slot, cudaStream_t st);
-int launch_dist_merge_flag(const void* rec, uint32_t n, const uint32_t* slot, const uint64_t* table, uint32_t gbase,
-                           uint32_t* newflag, cudaStream_t st);
-int launch_dist_scatter(const void* rec, uint32_t n, const uint32_t* slot, const uint64_t* table, uint32_t gbase,
-                        const uint32_t* grank, int32_t id_base, int32_t* k3, int32_t* cost, int32_t* total,
-                        uint64_t* desc_new, int32_t* gid_at, int* best_k3, cudaStream_t st);
-int launch_dist_cand_id(const uint32_t* slot, const uint64_t* table, const LevelTable& LT, uint32_t G, int32_t* cand_id,
-                        cudaStream_t st);
+                        const uint32_t* flag, const uint32_t* pre, uint32_t gbase, void* out, cudaStream_t st);
 int launch_id_flags(const uint8_t* needed, int32_t id_base, uint32_t n, uint32_t* flag, cudaStream_t st);
 int launch_id_compact(const int32_t* k3, const int32_t* cost, const int32_t* total, int32_t id_base, uint32_t n,
                       const uint32_t* flag, const uint32_t* pre, void* out, cudaStream_t st);

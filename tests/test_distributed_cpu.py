@@ -1,5 +1,6 @@
-"""CPU tests of the multi-rank host logic (gloo, world_size 2): region sharding and the padded variable-length
-all-gather used by the sharded search.  The CUDA merge itself is covered by the GPU tests (emulated ranks)."""
+"""CPU tests of the multi-rank host logic (gloo, world_size 2): region sharding (LPT), the hand-over of the
+communicator id that precedes a sharded search, and the ownership arithmetic of the per-level score exchange.  The
+sharded search itself is covered by the GPU tests (ranks emulated on one device, tests/test_gpu_parity.py)."""
 import os
 import socket
 
@@ -9,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from nahrwhals_b200.distributed import all_gather_varlen, estimate_region_cost, pad_gather_layout, shard_regions
+from nahrwhals_b200.distributed import broadcast_id, estimate_region_cost, own_chunk, own_range, shard_regions
 from nahrwhals_b200.sdgrid import sdgrid, to_solver_inputs
 
 
@@ -31,9 +32,19 @@ def test_region_cost_monotone():
     assert estimate_region_cost(big, 3, maxwidth=10) < estimate_region_cost(big, 3)
 
 
-def test_pad_layout():
-    assert pad_gather_layout([3, 0, 5]) == (5, [0, 5, 10])
-    assert pad_gather_layout([0, 0]) == (0, [0, 0])
+def test_own_ranges_partition_every_level():
+    """Host mirror of own_chunk / owns (csrc/nw_kernels.cuh): the ranks' ranges are disjoint, cover every fresh
+    candidate, and the exchanged segments are 16-byte aligned."""
+    for world in (1, 2, 3, 4, 8):
+        for n in (0, 1, 3, 4, 5, 127, 128, 1000, 65537, 10722271):
+            chunk = own_chunk(n, world)
+            assert chunk % 4 == 0 and chunk >= 4 and chunk * world >= n
+            seen = 0
+            for r in range(world):
+                lo, hi = own_range(n, world, r)
+                assert lo == min(r * chunk, n) and hi == min((r + 1) * chunk, n) and lo <= hi
+                seen += hi - lo
+            assert seen == n
 
 
 def _worker(rank, world, port, q):
@@ -41,28 +52,28 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        item = 40
-        count = 3 + 2 * rank  # ragged: rank 0 sends 3 records, rank 1 sends 5
-        local = torch.arange(count * item, dtype=torch.int64).to(torch.uint8) + rank * 100
-        out, counts, stride = all_gather_varlen(dist, local, count, item)
-        ok = counts == [3, 5] and stride == 5 and out.numel() == world * stride * item
-        for r in range(world):
-            exp = (torch.arange(counts[r] * item, dtype=torch.int64).to(torch.uint8) + r * 100)
-            ok = ok and torch.equal(out[r * stride * item: r * stride * item + counts[r] * item], exp)
-        # empty contribution from every rank
-        out2, counts2, stride2 = all_gather_varlen(dist, torch.zeros(0, dtype=torch.uint8), 0, item)
-        ok = ok and counts2 == [0, 0] and stride2 == 1
-        # needed-flags reduction used between marking passes
-        need = torch.zeros(8, dtype=torch.uint8)
-        need[rank] = rank + 1
-        dist.all_reduce(need, op=dist.ReduceOp.MAX)
-        ok = ok and need.tolist() == [1, 2, 0, 0, 0, 0, 0, 0]
+        ident = bytes((7 * k + 3) % 256 for k in range(128)) if rank == 0 else None
+        got = broadcast_id(dist, ident, 0)
+        ok = got == bytes((7 * k + 3) % 256 for k in range(128))
+        # every rank derives the same shard of a regionfile without talking to the others
+        costs = [float((k * 37) % 11 + 1) for k in range(40)]
+        mine = shard_regions(costs, world)[rank]
+        allp = [None] * world
+        dist.all_gather_object(allp, mine)
+        ok = ok and sorted(k for p in allp for k in p) == list(range(40)) and allp == shard_regions(costs, world)
+        # the source rank must supply a full id
+        if rank == 0:
+            try:
+                broadcast_id(dist, b"short", 0)
+                ok = False
+            except ValueError:
+                pass
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
 
 
-def test_varlen_allgather_gloo_world2():
+def test_id_broadcast_and_sharding_gloo_world2():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]

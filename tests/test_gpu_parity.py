@@ -178,10 +178,12 @@ def test_roundtrip_property_full_size(solver):
 
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_search_emulated(oracle, world):
-    """Frontier-sharded single search with the ranks emulated on one GPU: every rank must reproduce the
-    single-GPU / oracle result bit for bit (ids, counts, TSV), for a beam search and an exhaustive one."""
+    """Frontier-sharded single search (nw_solve_sharded_ctxs) with the ranks emulated on one GPU: every rank
+    must reproduce the single-GPU / oracle result bit for bit (every id, score, edge, counter, TSV), for a beam search
+    and an exhaustive one, and the DP work must really be divided (cells are summed over the ranks)."""
     import nahrwhals_b200 as nb
-    from nahrwhals_b200.distributed import solve_sharded_emulated
+    from nahrwhals_b200.distributed import solve_sharded_local
+    from tests.util import assert_search_equal
     solvers = [nb.Solver(0) for _ in range(world)]
     try:
         for gen, flags in [(dict(n_x=40, families=[5, 4, 3, 2], seed=12, chain_depth=3), dict(maxdepth=4, maxdup=2, maxwidth=50)),
@@ -191,12 +193,11 @@ def test_sharded_search_emulated(oracle, world):
             aln = to_solver_inputs(mat)
             kw = dict(minreport=0.98, maxreport=1000, **flags)
             O = oracle.solve(aln, lx, ly, **kw)
-            res = solve_sharded_emulated(solvers, aln, lx, ly, **kw)
+            res = solve_sharded_local(solvers, aln, lx, ly, keep_ids=True, **kw)
+            assert len(res) == world
             for R in res:
-                assert R.tsv == O.tsv
-                assert R.generated == [int(v) for v in O.generated]
-                assert R.scored == [int(v) for v in O.scored]
-                assert int(R.stats.n_ids) == O.n_ids and R.stats.best == O.best
+                assert_search_equal(R, O)
+                assert R.stats.score_launches >= 1
     finally:
         for s in solvers:
             s.close()
@@ -431,7 +432,7 @@ def test_full_size_properties_bench_workload(solver, oracle):
     sys.path.insert(0, ROOT)
     from bench import make_workload
     from oracle.nw_oracle_py import apply_move
-    from nahrwhals_b200.distributed import solve_sharded_emulated
+    from nahrwhals_b200.distributed import solve_sharded_local
     import nahrwhals_b200 as nb
     aln, lx, ly, flags, _ = make_workload("s64", 1)
     A = solver.solve(aln, lx, ly, keep_ids=True, verify_dedup=True, **flags)
@@ -453,11 +454,11 @@ def test_full_size_properties_bench_workload(solver, oracle):
     del C
     extra = nb.Solver(0)
     try:
-        S = solve_sharded_emulated([solver, extra], aln, lx, ly, **flags)
+        S = solve_sharded_local([solver, extra], aln, lx, ly, **flags)
     finally:
         extra.close()
     for R in S:
-        assert R.tsv == A.tsv and R.generated == A.generated and R.scored == A.scored
+        assert R.tsv == A.tsv and R.generated == A.generated and R.scored == A.scored and R.cells == A.cells
     # round trip of the report through the CPU oracle
     n_x = aln.shape[0]
     root = tuple(range(1, n_x + 1))

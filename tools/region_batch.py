@@ -17,15 +17,21 @@ from nahrwhals_b200.sdgrid import sdgrid, to_solver_inputs  # noqa: E402
 FLAGS = dict(maxdepth=3, maxdup=2, maxwidth=1000, minreport=0.98, maxreport=1000)
 
 
-def make_regions(n, seed=0):
+def make_regions(n, seed=0, only=None):
+    """only: build just these region indices of the n-region set (the random stream is consumed for all of them, so a
+    region is the same whoever builds it)."""
     rng = np.random.default_rng(seed)
+    want = None if only is None else set(only)
     out = []
     for k in range(n):
         n_x = int(rng.integers(20, 121))
         fams = [int(rng.integers(2, 5)) for _ in range(int(rng.integers(2, 7)))]
         while sum(fams) > n_x:
             fams.pop()
-        mat, lx, ly, _ = sdgrid(n_x, fams, seed=1000 + k, chain_depth=int(rng.integers(1, 4)), len_tol=0.3)
+        depth = int(rng.integers(1, 4))
+        if want is not None and k not in want:
+            continue
+        mat, lx, ly, _ = sdgrid(n_x, fams, seed=1000 + k, chain_depth=depth, len_tol=0.3)
         out.append((to_solver_inputs(mat), lx, ly))
     return out
 
