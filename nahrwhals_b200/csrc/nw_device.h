@@ -116,6 +116,8 @@ NW_HD U4 seq_fingerprint(const int16_t* s, int L, const U4* pw, uint32_t rid1) {
 
 NW_HD uint64_t fp_key0(const U4& f) { return (uint64_t)f.v[0] | ((uint64_t)f.v[1] << 32); }
 NW_HD uint64_t fp_key1(const U4& f) { return (uint64_t)f.v[2] | ((uint64_t)f.v[3] << 32); }
+// the 32 key bits stored next to the position in the second table word: base 2 (31 bits) and the top bit of base 3
+NW_HD uint32_t fp_key_hi32(const U4& f) { return f.v[2] | ((f.v[3] & 0x40000000u) << 1); }
 NW_HD uint64_t fp_slot_hash(uint64_t k0, uint64_t k1) {
   uint64_t h = k0 * 0x9E3779B97F4A7C15ull ^ (k1 + 0xD6E8FEB86659FD93ull);
   h ^= h >> 32;

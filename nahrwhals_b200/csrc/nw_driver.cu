@@ -242,6 +242,8 @@ struct BandStore {  // one context's device mirror of the tables of one (n_y, fo
 struct nw_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;        // the root's own DP runs here, beside level 1 (nothing waits for it until the report)
+  cudaEvent_t side_go = nullptr, side_done = nullptr;
   std::vector<U4> h_pow;
   DevBuf d_pow;
   // regions of the current search (regionfile mode runs many independent regions through one pipeline)
@@ -259,7 +261,7 @@ struct nw_ctx {
   DevBuf table_prev;                 // the table a level outgrew: released when the next one is retired (no host sync)
   // per-level scratch
   DevBuf cnt, off, bsum, slot, owner, is_new, newrank, nrank, new_len, hist, bstart, cursor, work, scratch, flag, pre, sel, keys,
-      misc, rslot, newflag, grank, edgebuf, cta_rid, new_rid, best, gather, binflag, binrank, binsum, binrec;
+      misc, edgebuf, cta_rid, new_rid, best, gather, binflag, binrank, binsum, binrec, rootwork;
   nw::Exchange* xch = nullptr;  // NCCL communicator of the frontier-sharded search (nw_dist_init), owned by the context
   void* pinned = nullptr;  // pinned staging area for D2H scalars / histograms (grown on demand)
   size_t pinned_bytes = 0;
@@ -564,8 +566,37 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
     if (!(flags & NW_FLAG_GENERIC_DP) && T.fast_ok) cls = score_fast_window(T.max_width);
     if (cls && score_fast_smem(cls, c->ctx_max, L) > 200 * 1024) cls = 0;  // tiles would not fit: generic kernel
     bk[k] = Bucket{r, L, cls, bins[k].n, bins[k].bin};
-    cls_count[cls_key(cls) + 1]++;
     if (cells_out) cells_out[r] += (int64_t)bins[k].n * T.cells;
+  }
+  {
+    // A register-window class that would not fill the device on its own is folded into the next wider class that is
+    // present: a wider window only carries idle columns (masks and band rows are per length, the region context is
+    // padded for WINDOW_MAX), while a launch of its own costs the whole single-thread latency of a DP (~70-100 us at 150
+    // blocks) again.  S150: windows 60 and 64 become one launch per level.
+    static const bool no_merge = getenv("NW_NO_CLASS_MERGE") != nullptr;
+    std::map<int, uint64_t> cta_of;  // fast classes present -> work slots
+    for (const Bucket& b : bk)
+      if (b.cls) cta_of[b.cls] += (b.n + 31) & ~31u;
+    std::map<int, int> into;
+    if (!no_merge)
+      for (auto it = cta_of.begin(); it != cta_of.end(); ++it) {
+        auto nx = std::next(it);
+        if (nx == cta_of.end()) break;
+        if ((it->second + 127) / 128 < 4 * 148) {
+          into[it->first] = nx->first;
+          nx->second += it->second;
+        }
+      }
+    for (Bucket& b : bk) {
+      int cls = b.cls;
+      while (cls && into.count(cls)) {
+        const int up = into[cls];
+        if (score_fast_smem(up, c->ctx_max, b.L) > 200 * 1024) break;
+        cls = up;
+      }
+      b.cls = cls;
+      cls_count[cls_key(cls) + 1]++;
+    }
   }
   const auto T1 = tnow();
   {
@@ -724,8 +755,6 @@ struct Search {
   uint32_t* pinned(size_t bytes) {  // growable pinned staging area
     if (bytes > c->pinned_bytes) {
       if (c->pinned) cudaFreeHost(c->pinned);
-  if (c->rg_pinned) cudaFreeHost(c->rg_pinned);
-  if (c->rg_dev) cudaFree(c->rg_dev);
       c->pinned = nullptr;
       c->pinned_bytes = 0;
       const size_t want = std::max(bytes + bytes / 2, (size_t)512 * 1024);
@@ -815,6 +844,8 @@ struct Search {
     CK(spin_sync(s));
     // score the roots (solver.jl:599) -- a root's score never updates `best` (:606): dummy best array
     const int lcap = c->nx_max + 1;
+    root_pending = false;
+    if (R == 1 && score_root_aside(L0, L1)) return;  // one region: the root's DP runs beside level 1 (collected by run())
     {
       const size_t nbins = (size_t)R * lcap * NSUB;
       uint32_t* hist = (uint32_t*)c->hist.ensure(nbins * 4, true);
@@ -827,6 +858,12 @@ struct Search {
       CK(cudaMemsetAsync(dummy_best, 0, (size_t)(R + 1) * 4, s));
       run_scoring(c, view, hist, lcap, L0.nrid.as<uint16_t>(), 0, o.flags, dummy_best, nullptr);
     }
+    collect_roots();
+  }
+  void collect_roots() {
+    cudaStream_t s = c->stream;
+    Level& L0 = lv[0];
+    std::vector<int32_t> k3i(R), ci(R), ti(R);
     d2h(c, k3i.data(), L0.k3.p, (size_t)R * 4);
     d2h(c, ci.data(), L0.cost.p, (size_t)R * 4);
     d2h(c, ti.data(), L0.total.p, (size_t)R * 4);
@@ -836,6 +873,56 @@ struct Search {
       root_cost[r] = ci[r];
       root_total[r] = ti[r];
     }
+  }
+  // One region: the root is a single candidate, and one DP of a 150-block index is ~70 us of pure latency that nothing
+  // in the search depends on (the root's score enters the report only).  Its launch goes to the context's side stream
+  // behind the uploads; run() joins it before the report.  Returns false when the root needs the generic kernel.
+  bool root_pending = false;
+  bool score_root_aside(Level& L0, Level& L1) {
+    cudaStream_t s = c->stream;
+    const int L = c->RH[0].n_x;
+    if (early_exit(L, c->RH[0].n_y)) return false;  // settled without a DP (k3 0, cost -1: the arrays' initial values)
+    const BandTable& T = c->rbands[0]->get(L);
+    if (!T.contiguous) fail(NW_ERR_RANGE, "corridor rows are not intervals for this shape (unsupported)");
+    int cls = 0;
+    if (!(o.flags & NW_FLAG_GENERIC_DP) && T.fast_ok) cls = score_fast_window(T.max_width);
+    if (!cls || score_fast_smem(cls, c->ctx_max, L) > 200 * 1024) return false;
+    if (c->rbands[0]->upload(c, s)) CK(spin_sync(s));
+    refresh_region_bands(c);
+    uint32_t work[32];
+    work[0] = 0;
+    for (int k = 1; k < 32; ++k) work[k] = WORK_PAD;
+    h2d(c, c->rootwork.ensure(sizeof work + 16), work, sizeof work);
+    int* dummy_best = reinterpret_cast<int*>(c->rootwork.as<unsigned char>() + sizeof work);
+    CK(cudaMemsetAsync(dummy_best, 0, 8, s));
+    CK(cudaEventRecord(c->side_go, s));
+    CK(cudaStreamWaitEvent(c->side, c->side_go, 0));
+    ScoreArgs A{};
+    A.F = frontier_of(L1);
+    A.ctx_max = c->ctx_max;
+    A.ny_max = c->ny_max;
+    A.newlist = L0.newlist.as<uint32_t>();
+    A.desc = L0.desc.as<uint64_t>();
+    A.k3 = L0.k3.as<int32_t>();
+    A.cost = L0.cost.as<int32_t>();
+    A.total = L0.total.as<int32_t>();
+    A.best_k3 = dummy_best;
+    A.work = c->rootwork.as<uint32_t>();
+    A.n_work = 32;
+    A.lmax = L;
+    A.cta_rid = nullptr;
+    if (launch_score_fast(cls, A, c->side) < 0) fail(NW_ERR_CUDA, "no register-DP kernel for window " + std::to_string(cls));
+    c->launches += 1;
+    CK(cudaEventRecord(c->side_done, c->side));
+    CK(cudaGetLastError());
+    root_pending = true;
+    return true;
+  }
+  void join_root() {
+    if (!root_pending) return;
+    CK(cudaStreamWaitEvent(c->stream, c->side_done, 0));
+    root_pending = false;
+    collect_roots();
   }
 
   // NW_FLAG_VERIFY_DEDUP: element-wise comparison of every merged candidate of level d with its owner
@@ -1189,7 +1276,9 @@ struct Search {
       n_levels = d;
       if (d < D) select_next(d);
       CK(cudaEventRecord(b, s));
-      // the frontier blob of level d is no longer needed once level d+1 is materialised (ids are kept)
+      // the frontier blob of level d is no longer needed once level d+1 is materialised (ids are kept); the root's own
+      // DP on the side stream reads level 1's blob: whatever reuses that memory is ordered behind it (no host wait)
+      if (d == 1 && root_pending) CK(cudaStreamWaitEvent(s, c->side_done, 0));
       if (!(o.flags & NW_FLAG_VERIFY_DEDUP)) lv[d].fblob.release();  // the verifier re-reads old frontiers
       if (d < D && (!any || lv[d + 1].P == 0)) {
         n_levels = D;  // solver.jl keeps looping over empty frontiers; nothing more can be generated
@@ -1197,6 +1286,7 @@ struct Search {
       }
     }
     pad_levels(D);
+    join_root();
     CK(cudaEventRecord(ev1, s));
     CK(spin_sync(s));
     CK(cudaGetLastError());
@@ -1906,6 +1996,9 @@ int nw_ctx_create(int device, nw_ctx** out) {
     PoolScope pool_scope(c);
     try {
       CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&c->side_go, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&c->side_done, cudaEventDisableTiming));
       CK(cudaMallocHost(&c->pinned, PINNED_BYTES));
       c->pinned_bytes = PINNED_BYTES;
       c->h_pow = build_pow_table();
@@ -1924,6 +2017,10 @@ void nw_ctx_destroy(nw_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->side) cudaStreamSynchronize(c->side);
+  if (c->side_go) cudaEventDestroy(c->side_go);
+  if (c->side_done) cudaEventDestroy(c->side_done);
+  if (c->side) cudaStreamDestroy(c->side);
   delete c->xch;
   c->xch = nullptr;
   if (c->pinned) cudaFreeHost(c->pinned);
@@ -2464,6 +2561,10 @@ void nw_dist_shutdown(nw_ctx* c) {
   if (!c || !c->xch) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->side) cudaStreamSynchronize(c->side);
+  if (c->side_go) cudaEventDestroy(c->side_go);
+  if (c->side_done) cudaEventDestroy(c->side_done);
+  if (c->side) cudaStreamDestroy(c->side);
   delete c->xch;
   c->xch = nullptr;
 }

@@ -44,28 +44,30 @@ __device__ __forceinline__ void cas128(uint64_t* addr, uint64_t cl, uint64_t ch,
       : "memory");
 }
 
-// Insert (k0,k1) with discovery position gpos; returns the slot.  Slot = {k0, k1, min gpos, pad}, all-ones = empty.
-// Reads come first: a slot's key never changes once set and its position only decreases, so a stale read can only
-// cause a redundant atomic, never a wrong result.  Duplicates of an index discovered earlier need no atomic at all.
-__device__ __forceinline__ uint32_t table_insert(uint64_t* T, uint64_t mask, uint64_t k0, uint64_t k1, uint64_t gpos) {
-  uint64_t s = fp_slot_hash(k0, k1) & mask;
+// Insert the key (k0, kh) with discovery position gpos; returns the slot.  Slot = {k0, kh << 32 | min gpos}, all-ones =
+// empty.  Reads come first: a slot's key never changes once set and its position only decreases, so a duplicate of an
+// index discovered earlier needs no atomic at all, and a stale read can only cause a redundant compare-and-swap.
+__device__ __forceinline__ uint32_t table_insert(uint64_t* T, uint64_t mask, uint64_t k0, uint32_t kh, uint32_t gpos) {
+  uint64_t s = fp_slot_hash(k0, kh) & mask;
+  const uint64_t mine = ((uint64_t)kh << 32) | gpos;
   while (true) {
     uint64_t* e = T + s * TBL_WORDS;
-    // key and position of the slot arrive with one 32-byte sector (two loads in flight together)
-    const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(e));
-    const uint64_t v = __ldcg(reinterpret_cast<const unsigned long long*>(e + 2));
+    const ulonglong2 cur = __ldcg(reinterpret_cast<const ulonglong2*>(e));  // key and position arrive together
     uint64_t o0 = cur.x, o1 = cur.y;
-    if (o0 == TBL_EMPTY && o1 == TBL_EMPTY) {
-      cas128(e, TBL_EMPTY, TBL_EMPTY, k0, k1, o0, o1);
-      if ((o0 == TBL_EMPTY && o1 == TBL_EMPTY) || (o0 == k0 && o1 == k1)) {
-        // claimed now (by this thread or, a moment ago, by a sibling with the same key): the position read above
-        // is stale, so the minimum is sent unconditionally -- result unused, i.e. a fire-and-forget reduction
-        atomicMin(reinterpret_cast<unsigned long long*>(e + 2), (unsigned long long)gpos);
-        return (uint32_t)s;
+    if ((o0 == TBL_EMPTY) != (o1 == TBL_EMPTY)) continue;  // a 16-byte read torn by a concurrent claim: read again
+    if (o0 == TBL_EMPTY) {
+      cas128(e, TBL_EMPTY, TBL_EMPTY, k0, mine, o0, o1);
+      if (o0 == TBL_EMPTY && o1 == TBL_EMPTY) return (uint32_t)s;  // claimed
+    }
+    if (o0 == k0 && (uint32_t)(o1 >> 32) == kh) {
+      // same index: keep the smaller discovery position (the first discoverer of solver.jl:535 in serial order)
+      while ((uint32_t)o1 > gpos) {
+        uint64_t n0, n1;
+        cas128(e, o0, o1, k0, mine, n0, n1);
+        if (n0 == o0 && n1 == o1) break;
+        o0 = n0;
+        o1 = n1;
       }
-    } else if (o0 == k0 && o1 == k1) {
-      // a key never changes and a position only decreases: no atomic when the stored position is already smaller
-      if (v > gpos) atomicMin(reinterpret_cast<unsigned long long*>(e + 2), (unsigned long long)gpos);
       return (uint32_t)s;
     }
     s = (s + 1) & mask;
@@ -76,7 +78,8 @@ __global__ void k_table_rehash(const uint64_t* oldT, uint64_t old_cap, uint64_t*
   for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < old_cap; s += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t k0 = oldT[s * TBL_WORDS];
     if (k0 == TBL_EMPTY) continue;
-    table_insert(newT, new_mask, k0, oldT[s * TBL_WORDS + 1], oldT[s * TBL_WORDS + 2]);
+    const uint64_t w1 = oldT[s * TBL_WORDS + 1];
+    table_insert(newT, new_mask, k0, (uint32_t)(w1 >> 32), (uint32_t)w1);
   }
 }
 
@@ -87,7 +90,7 @@ __global__ void k_insert_roots(const unsigned char* blob, uint32_t pstride, cons
   if (r >= n_regions) return;
   const int16_t* seq = reinterpret_cast<const int16_t*>(blob + (size_t)r * pstride);
   const U4 f = seq_fingerprint(seq, len[r], pw, regions[r].rid1);
-  table_insert(table, tmask, fp_key0(f), fp_key1(f), (uint64_t)r);
+  table_insert(table, tmask, fp_key0(f), fp_key_hi32(f), (uint32_t)r);
 }
 
 // =====================================================================================================
@@ -359,14 +362,15 @@ static void launch_expand_rows(bool emit, const ExpandArgs& A, cudaStream_t st) 
 int launch_expand(bool emit, const ExpandArgs& A, cudaStream_t st) {
   if (A.F.P <= 0) return 0;
   const int LW = (A.F.LS + 31) / 32;
-  const int LWT = LW <= 1 ? 1 : LW <= 2 ? 2 : LW <= 4 ? 4 : LW <= 8 ? 8 : LW <= 16 ? 16 : 0;
+  const int LWT = LW <= 1 ? 1 : LW <= 2 ? 2 : LW <= 4 ? 4 : LW <= 8 ? 8 : LW <= 16 ? 16 : LW <= 32 ? 32 : 0;
   if (LWT && !A.force_pairs && expand_rows_smem(A.F.LS, A.nx_max, LWT) <= 160 * 1024) {
     switch (LWT) {
       case 1: launch_expand_rows<1>(emit, A, st); break;
       case 2: launch_expand_rows<2>(emit, A, st); break;
       case 4: launch_expand_rows<4>(emit, A, st); break;
       case 8: launch_expand_rows<8>(emit, A, st); break;
-      default: launch_expand_rows<16>(emit, A, st); break;
+      case 16: launch_expand_rows<16>(emit, A, st); break;
+      default: launch_expand_rows<32>(emit, A, st); break;
     }
     return 1;
   }
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(256) k_hash_insert(ExpandArgs A, uint32_t G) {
     f.v[0] &= 0xffu;
     f.v[1] = f.v[2] = f.v[3] = 0;
   }
-  A.slot[pos] = table_insert(A.table, A.tmask, fp_key0(f), fp_key1(f), (uint64_t)A.gbase + pos);
+  A.slot[pos] = table_insert(A.table, A.tmask, fp_key0(f), fp_key_hi32(f), A.gbase + pos);
 }
 int launch_hash_insert(const ExpandArgs& A, uint32_t G, cudaStream_t st) {
   if (G == 0) return 0;
@@ -542,7 +546,7 @@ __global__ void __launch_bounds__(256) k_resolve(ExpandArgs A, uint32_t G, uint3
     const uint32_t s4[4] = {sl.x, sl.y, sl.z, sl.w};
     uint32_t o[4], g[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) o[q] = (uint32_t)__ldg(&A.table[(uint64_t)s4[q] * TBL_WORDS + 2]);  // the random reads
+    for (int q = 0; q < 4; ++q) o[q] = (uint32_t)__ldg(&A.table[(uint64_t)s4[q] * TBL_WORDS + 1]);  // the random reads
 #pragma unroll
     for (int q = 0; q < 4; ++q) g[q] = A.gbase + pos0 + q;
     *reinterpret_cast<uint4*>(owner + pos0) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -552,7 +556,7 @@ __global__ void __launch_bounds__(256) k_resolve(ExpandArgs A, uint32_t G, uint3
   }
   for (uint32_t pos = pos0; pos < G; ++pos) {
     const uint32_t g = A.gbase + pos;
-    const uint32_t o = (uint32_t)A.table[(uint64_t)A.slot[pos] * TBL_WORDS + 2];
+    const uint32_t o = (uint32_t)A.table[(uint64_t)A.slot[pos] * TBL_WORDS + 1];
     owner[pos] = o;
     is_new[pos] = o == g ? 1u : 0u;
   }
@@ -1519,6 +1523,8 @@ void init_kernel_attrs() {
   cudaFuncSetAttribute(k_expand<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   cudaFuncSetAttribute(k_expand<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   cudaFuncSetAttribute(k_expand<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_expand<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  cudaFuncSetAttribute(k_expand<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   cudaFuncSetAttribute(k_expand<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   cudaFuncSetAttribute(k_expand<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   cudaFuncSetAttribute(k_expand<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);

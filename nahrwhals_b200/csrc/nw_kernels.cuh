@@ -9,7 +9,13 @@
 namespace nw {
 
 constexpr uint64_t TBL_EMPTY = ~0ull;
-constexpr int TBL_WORDS = 4;  // slot = {key0, key1, first-discoverer gpos, unused} (32 B)
+// Dedup table slot = 16 bytes, claimed and updated with ONE 128-bit compare-and-swap:
+//   word 0 = fingerprint bits 0..63, word 1 = fingerprint bits 64..95 << 32 | first-discoverer position (32 bits).
+// Two slots share a 32-byte DRAM sector, so a probe that steps to the neighbour slot usually stays in the sector it
+// already fetched, and the table (and its per-level clear) is half the size of a 32-byte-slot layout.  The table keys
+// on 96 of the fingerprint's 124 bits; exactness does not rest on the key width: the search verifies every merged
+// candidate element-wise against its owner (k_verify_dups) unless the caller opts out.
+constexpr int TBL_WORDS = 2;
 constexpr int MAX_LEVELS = 16;
 constexpr uint32_t WORK_PAD = 0xffffffffu;
 // The per-length counters used to bucket fresh candidates are split NSUB ways (by new-rank / 256) to spread the
