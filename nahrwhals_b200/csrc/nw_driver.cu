@@ -647,7 +647,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
     d_cta_rid = (uint16_t*)c->cta_rid.ensure(cta_rid.size() * 2, true);
     h2d(c, d_cta_rid, cta_rid.data(), cta_rid.size() * 2);
   }
-  c->launches += launch_bucket_scatter(c->new_len.as<uint16_t>(), new_rid_dev, c->d_regions.as<RegionDev>(), lcap, n_new,
+  c->launches += launch_bucket_scatter(c->new_len.as<uint16_t>(), R > 1 ? new_rid_dev : nullptr, c->d_regions.as<RegionDev>(), lcap, n_new,
                                        force, own, c->bstart.as<uint32_t>(), c->cursor.as<uint32_t>(),
                                        c->work.as<uint32_t>(), st);
   // no sync: cudaMemcpyAsync from pageable memory has consumed the host vectors (bins, cta_rid) when it returns
@@ -1010,12 +1010,16 @@ struct Search {
     E.tmask = c->table_cap - 1;
     c->launches += launch_expand(true, E, s);
     c->launches += launch_hash_insert(E, G, s);
-    uint32_t* is_new = (uint32_t*)c->is_new.ensure((size_t)G * 4, true);
+    // first-discoverer flags as a bit mask + exclusive scan of the words' popcounts (new-rank of any candidate)
+    const uint32_t nwords = (G + 31) / 32;
+    const uint32_t nwords4 = (nwords + 3u) & ~3u;  // the scan reads its input as 16-byte vectors
+    uint32_t* is_new = (uint32_t*)c->is_new.ensure((size_t)nwords4 * 8 + 16, true);  // [mask words | word counts]
+    uint32_t* wcount = is_new + nwords4;
     uint32_t* owner = (uint32_t*)c->owner.ensure((size_t)G * 4, true);
-    c->launches += launch_resolve(E, G, is_new, owner, s);
-    uint32_t* newrank = (uint32_t*)c->newrank.ensure((size_t)G * 4, true);
-    bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(G) * 4, true);
-    c->launches += launch_scan(is_new, newrank, G, bsum, (uint32_t*)(misc + 5), s);
+    c->launches += launch_resolve(E, G, is_new, wcount, owner, s);
+    uint32_t* newrank = (uint32_t*)c->newrank.ensure((size_t)nwords * 4 + 16, true);  // word prefixes
+    bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(nwords) * 4, true);
+    c->launches += launch_scan(wcount, newrank, nwords, bsum, (uint32_t*)(misc + 5), s);
     const int lcap = std::min(std::max(maxlen, L.LS), LMAX) + 1;  // longest possible child of this level, + 1
     // single search with few (length) bins: the fresh count is fetched together with the DP buckets (one host round
     // trip less per level); the per-fresh arrays are then sized by the candidate count
@@ -1023,7 +1027,12 @@ struct Search {
     const bool defer = R == 1 && (size_t)lcap <= BINS_SMALL_LIMIT && !no_defer;
     uint32_t n_new = G;  // upper bound until known
     if (!defer) {
-      if (R > 1) gather_async(newrank, L.cstart, G, 0xffffffffu);  // first fresh rank of every region
+      if (R > 1) {  // first fresh rank of every region
+        const uint32_t n = (uint32_t)L.cstart.size();
+        uint32_t* g = (uint32_t*)c->gather.ensure((size_t)n * 8, true);
+        h2d(c, g + n, L.cstart.data(), (size_t)n * 4);
+        c->launches += launch_gather_rank(is_new, newrank, g + n, n, G, 0xffffffffu, g, s);
+      }
       d2h(c, pin_u32(), misc, 32);
       if (R > 1) d2h(c, pin_u32() + 64, c->gather.p, (size_t)(R + 1) * 4);
       CK(spin_sync(s));
@@ -1050,8 +1059,8 @@ struct Search {
     A.slot = E.slot;
     A.table = E.table;
     A.owner = owner;
-    A.is_new = is_new;
-    A.newrank = newrank;
+    A.fresh_mask = is_new;
+    A.wprefix = newrank;
     A.desc = E.desc;
     A.front_len = L.flen.as<int32_t>();
     A.front_rid = R > 1 ? L.frid.as<uint16_t>() : nullptr;

@@ -537,28 +537,36 @@ uint64_t scan_scratch_items(uint64_t n) { return (n + SCAN_B - 1) / SCAN_B + 1; 
 // =====================================================================================================
 // resolve / assign: which candidate is the first discoverer of its index (solver.jl:535-561)
 // =====================================================================================================
-// four candidates per thread: four independent random table reads in flight
-__global__ void __launch_bounds__(256) k_resolve(ExpandArgs A, uint32_t G, uint32_t* is_new, uint32_t* owner) {
+// four candidates per thread: four independent random table reads in flight.  A warp covers 128 consecutive
+// candidates = four words of the first-discoverer bit mask, assembled from the lanes' nibbles by three shuffles.
+__global__ void __launch_bounds__(256) k_resolve(ExpandArgs A, uint32_t G, uint32_t* fresh_mask, uint32_t* wcount,
+                                                 uint32_t* owner) {
   const uint32_t pos0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-  if (pos0 >= G) return;
+  uint32_t nib = 0;
   if (pos0 + 3 < G) {
     const uint4 sl = *reinterpret_cast<const uint4*>(A.slot + pos0);
     const uint32_t s4[4] = {sl.x, sl.y, sl.z, sl.w};
-    uint32_t o[4], g[4];
+    uint32_t o[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) o[q] = (uint32_t)__ldg(&A.table[(uint64_t)s4[q] * TBL_WORDS + 1]);  // the random reads
-#pragma unroll
-    for (int q = 0; q < 4; ++q) g[q] = A.gbase + pos0 + q;
     *reinterpret_cast<uint4*>(owner + pos0) = make_uint4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<uint4*>(is_new + pos0) =
-        make_uint4(o[0] == g[0] ? 1u : 0u, o[1] == g[1] ? 1u : 0u, o[2] == g[2] ? 1u : 0u, o[3] == g[3] ? 1u : 0u);
-    return;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) nib |= (o[q] == A.gbase + pos0 + q ? 1u : 0u) << q;
+  } else {
+    for (uint32_t q = 0; q < 4 && pos0 + q < G; ++q) {
+      const uint32_t o = (uint32_t)A.table[(uint64_t)A.slot[pos0 + q] * TBL_WORDS + 1];
+      owner[pos0 + q] = o;
+      nib |= (o == A.gbase + pos0 + q ? 1u : 0u) << q;
+    }
   }
-  for (uint32_t pos = pos0; pos < G; ++pos) {
-    const uint32_t g = A.gbase + pos;
-    const uint32_t o = (uint32_t)A.table[(uint64_t)A.slot[pos] * TBL_WORDS + 1];
-    owner[pos] = o;
-    is_new[pos] = o == g ? 1u : 0u;
+  const int lane = threadIdx.x & 31;
+  uint32_t w = nib << (4 * (lane & 7));
+  w |= __shfl_xor_sync(0xffffffffu, w, 1);
+  w |= __shfl_xor_sync(0xffffffffu, w, 2);
+  w |= __shfl_xor_sync(0xffffffffu, w, 4);
+  if ((lane & 7) == 0 && pos0 < G) {
+    fresh_mask[pos0 >> 5] = w;
+    wcount[pos0 >> 5] = (uint32_t)__popc(w);
   }
 }
 
@@ -570,15 +578,17 @@ __device__ __forceinline__ int32_t owner_id(const LevelTable& LT, uint32_t g) {
 
 // Four consecutive candidates per thread: the per-candidate records arrive as 16-byte vectors and the four dependent
 // chains (parent length / region, owner's id) are in flight together -- the kernel is bound by memory latency.
+// Returns the child length of a fresh candidate of this rank that needs a DP (its histogram key), else -1.
 __device__ __forceinline__ int assign_one(const AssignArgs& A, uint32_t pos, uint32_t fresh, uint32_t r, uint32_t own,
-                                          uint64_t d) {
-  int key = -1;  // histogram key (region, child length, sub-counter) of candidates that need a DP; -1 = none
+                                          uint64_t d, int& rid_out) {
+  int len_key = -1;
   if (fresh) {
     A.cand_id[pos] = A.id_base + (int32_t)r;
     A.newlist[r] = pos;
     const uint32_t ps = desc_parent(d);
     const int len = child_len(A.front_len[ps], desc_kind(d), desc_i(d), desc_j(d));
     const int rid = A.front_rid ? (int)A.front_rid[ps] : 0;
+    rid_out = rid;
     A.new_len[r] = (uint16_t)len;
     A.new_rid[r] = (uint16_t)rid;
     if (!A.force && early_exit(len, A.regions[rid].n_y)) {  // solver.jl:332-334 -> score 0.0, no DP
@@ -586,50 +596,100 @@ __device__ __forceinline__ int assign_one(const AssignArgs& A, uint32_t pos, uin
       A.cost[r] = -1;
       A.total[r] = 0;
     } else if (owns(A.own, r)) {  // sharded search: another rank scores the rest (exchange after the DP)
-      key = bucket_key(rid, A.lcap, len, r);
+      len_key = len;
     }
   } else {
-    A.cand_id[pos] = own >= A.gbase ? A.id_base + (int32_t)A.newrank[own - A.gbase] : owner_id(A.LT, own);
+    A.cand_id[pos] = own >= A.gbase ? A.id_base + (int32_t)mask_rank(A.fresh_mask, A.wprefix, own - A.gbase) : owner_id(A.LT, own);
   }
-  return key;
+  return len_key;
 }
+// ONE = a single region: the (length, sub-counter) histogram of the CTA is built with shared-memory atomics and flushed
+// once per non-empty bin (the fresh ranks of a CTA's 1024 candidates span at most two sub-counters); several regions:
+// warp-aggregated global atomics keyed by (region, length, sub-counter).
+template <bool ONE>
 __global__ void __launch_bounds__(256) k_assign(AssignArgs A) {
+  extern __shared__ uint32_t s_hist[];  // ONE: [2][lcap]
   const uint32_t pos0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-  int key[4] = {-1, -1, -1, -1};
-  if (pos0 + 3 < A.G) {
-    const uint4 fr = *reinterpret_cast<const uint4*>(A.is_new + pos0);
-    const uint4 rk = *reinterpret_cast<const uint4*>(A.newrank + pos0);
-    const uint4 ow = *reinterpret_cast<const uint4*>(A.owner + pos0);
-    const ulonglong2 d01 = *reinterpret_cast<const ulonglong2*>(A.desc + pos0);
-    const ulonglong2 d23 = *reinterpret_cast<const ulonglong2*>(A.desc + pos0 + 2);
-    key[0] = assign_one(A, pos0, fr.x, rk.x, ow.x, d01.x);
-    key[1] = assign_one(A, pos0 + 1, fr.y, rk.y, ow.y, d01.y);
-    key[2] = assign_one(A, pos0 + 2, fr.z, rk.z, ow.z, d23.x);
-    key[3] = assign_one(A, pos0 + 3, fr.w, rk.w, ow.w, d23.y);
+  uint32_t r_cta = 0;
+  if (ONE) {
+    for (int b = threadIdx.x; b < 2 * A.lcap; b += blockDim.x) s_hist[b] = 0;
+    r_cta = A.wprefix[(blockIdx.x * blockDim.x * 4u) >> 5];  // rank of the CTA's first candidate
+    __syncthreads();
+  }
+  int len[4] = {-1, -1, -1, -1}, rid[4] = {0, 0, 0, 0};
+  uint32_t rk[4] = {0, 0, 0, 0};
+  if (pos0 < A.G) {
+    const uint32_t m = A.fresh_mask[pos0 >> 5], base = A.wprefix[pos0 >> 5], bit = pos0 & 31;
+    if (pos0 + 3 < A.G) {
+      const uint4 ow = *reinterpret_cast<const uint4*>(A.owner + pos0);
+      const ulonglong2 d01 = *reinterpret_cast<const ulonglong2*>(A.desc + pos0);
+      const ulonglong2 d23 = *reinterpret_cast<const ulonglong2*>(A.desc + pos0 + 2);
+      const uint32_t o4[4] = {ow.x, ow.y, ow.z, ow.w};
+      const uint64_t d4[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        rk[q] = base + __popc(m & ((1u << (bit + q)) - 1u));
+        len[q] = assign_one(A, pos0 + q, (m >> (bit + q)) & 1u, rk[q], o4[q], d4[q], rid[q]);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t pos = pos0 + q;
+        if (pos >= A.G) break;
+        rk[q] = base + __popc(m & ((1u << (bit + q)) - 1u));
+        len[q] = assign_one(A, pos, (m >> (bit + q)) & 1u, rk[q], A.owner[pos], A.desc[pos], rid[q]);
+      }
+    }
+  }
+  if (ONE) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (len[q] >= 0) atomicAdd(&s_hist[(((rk[q] >> 10) != (r_cta >> 10)) ? A.lcap : 0) + len[q]], 1u);
+    __syncthreads();
+    for (int b = threadIdx.x; b < 2 * A.lcap; b += blockDim.x) {
+      const uint32_t n = s_hist[b];
+      if (n) {
+        const int l = b < A.lcap ? b : b - A.lcap;
+        const uint32_t rr = b < A.lcap ? r_cta : r_cta + 1024u;  // any rank of that sub-counter's 1024-block
+        atomicAdd(&A.hist[bucket_key(0, A.lcap, l, rr)], n);
+      }
+    }
   } else {
+    // warp-aggregated histogram (all 32 lanes converge here)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const uint32_t pos = pos0 + q;
-      if (pos < A.G) key[q] = assign_one(A, pos, A.is_new[pos], A.newrank[pos], A.owner[pos], A.desc[pos]);
+      const int key = len[q] >= 0 ? bucket_key(rid[q], A.lcap, len[q], rk[q]) : -1;
+      const uint32_t peers = __match_any_sync(0xffffffffu, key);
+      if (key >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&A.hist[key], (uint32_t)__popc(peers));
     }
-  }
-  // warp-aggregated histogram (all 32 lanes converge here)
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint32_t peers = __match_any_sync(0xffffffffu, key[q]);
-    if (key[q] >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&A.hist[key[q]], (uint32_t)__popc(peers));
   }
 }
 
 int launch_assign(const AssignArgs& A, cudaStream_t st) {
   if (A.G == 0) return 0;
   const uint32_t threads = (A.G + 3) / 4;
-  k_assign<<<(threads + 255) / 256, 256, 0, st>>>(A);
+  if (!A.front_rid && (size_t)A.lcap * 8 <= 40 * 1024)
+    k_assign<true><<<(threads + 255) / 256, 256, (size_t)A.lcap * 8, st>>>(A);
+  else
+    k_assign<false><<<(threads + 255) / 256, 256, 0, st>>>(A);
   return 1;
 }
-int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* is_new, uint32_t* owner, cudaStream_t st) {
+int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* fresh_mask, uint32_t* wcount, uint32_t* owner,
+                   cudaStream_t st) {
   if (G == 0) return 0;
-  k_resolve<<<((G + 3) / 4 + 255) / 256, 256, 0, st>>>(A, G, is_new, owner);
+  k_resolve<<<((G + 3) / 4 + 255) / 256, 256, 0, st>>>(A, G, fresh_mask, wcount, owner);
+  return 1;
+}
+// new-rank of the candidates at positions idx[i] (idx[i] < limit, else fill): region boundaries of a forest level
+__global__ void k_gather_rank(const uint32_t* mask, const uint32_t* wprefix, const uint32_t* idx, uint32_t n, uint32_t limit,
+                              uint32_t fill, uint32_t* dst) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = idx[i] < limit ? mask_rank(mask, wprefix, idx[i]) : fill;
+}
+int launch_gather_rank(const uint32_t* mask, const uint32_t* wprefix, const uint32_t* idx, uint32_t n, uint32_t limit,
+                       uint32_t fill, uint32_t* dst, cudaStream_t st) {
+  if (!n) return 0;
+  k_gather_rank<<<(n + 255) / 256, 256, 0, st>>>(mask, wprefix, idx, n, limit, fill, dst);
   return 1;
 }
 
@@ -652,7 +712,7 @@ __global__ void __launch_bounds__(1024) k_bucket_scatter(const uint16_t* new_len
   const uint32_t r = blockIdx.x * blockDim.x + tid;
   int key = -1;
   if (r < n_new && owns(own, r)) {
-    const int len = new_len[r], rid = new_rid[r];
+    const int len = new_len[r], rid = new_rid ? new_rid[r] : 0;
     if (force || !early_exit(len, regions[rid].n_y)) key = bucket_key(rid, lcap, len, r);
   }
   const uint32_t peers = __match_any_sync(0xffffffffu, key);
@@ -680,12 +740,43 @@ __global__ void __launch_bounds__(1024) k_bucket_scatter(const uint16_t* new_len
   wbase = __shfl_sync(0xffffffffu, wbase, leader);
   if (key >= 0) work[bstart[key] + wbase + mine] = r;
 }
+// a single region: the CTA's 1024 consecutive new-ranks share one sub-counter; a shared-memory counter per length hands
+// every candidate its place inside the CTA's share of the bucket, one global cursor atomic per (CTA, non-empty length)
+__global__ void __launch_bounds__(1024) k_bucket_scatter_one(const uint16_t* new_len, const RegionDev* regions, int lcap,
+                                                             uint32_t n_new, int force, OwnRange own, const uint32_t* bstart,
+                                                             uint32_t* cursor, uint32_t* work) {
+  extern __shared__ uint32_t s_cb[];  // [lcap] counts, then [lcap] bases
+  uint32_t* s_cnt = s_cb;
+  uint32_t* s_base = s_cb + lcap;
+  for (int b = threadIdx.x; b < lcap; b += blockDim.x) s_cnt[b] = 0;
+  __syncthreads();
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  int len = -1;
+  uint32_t local = 0;
+  if (r < n_new && owns(own, r)) {
+    const int l = new_len[r];
+    if (force || !early_exit(l, regions[0].n_y)) {
+      len = l;
+      local = atomicAdd(&s_cnt[l], 1u);
+    }
+  }
+  __syncthreads();
+  const uint32_t r_cta = blockIdx.x * blockDim.x;
+  for (int b = threadIdx.x; b < lcap; b += blockDim.x)
+    if (s_cnt[b]) s_base[b] = atomicAdd(&cursor[bucket_key(0, lcap, b, r_cta)], s_cnt[b]);
+  __syncthreads();
+  if (len >= 0) work[bstart[bucket_key(0, lcap, len, r_cta)] + s_base[len] + local] = r;
+}
 int launch_bucket_scatter(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap,
                           uint32_t n_new, int force, const OwnRange& own, const uint32_t* bstart, uint32_t* cursor,
                           uint32_t* work, cudaStream_t st) {
   if (n_new == 0) return 0;
-  k_bucket_scatter<<<(n_new + 1023) / 1024, 1024, 0, st>>>(new_len, new_rid, regions, lcap, n_new, force, own, bstart, cursor,
-                                                          work);
+  if (!new_rid && (size_t)lcap * 8 <= 40 * 1024)
+    k_bucket_scatter_one<<<(n_new + 1023) / 1024, 1024, (size_t)lcap * 8, st>>>(new_len, regions, lcap, n_new, force, own,
+                                                                                bstart, cursor, work);
+  else
+    k_bucket_scatter<<<(n_new + 1023) / 1024, 1024, 0, st>>>(new_len, new_rid, regions, lcap, n_new, force, own, bstart,
+                                                            cursor, work);
   return 1;
 }
 // best score of a level over ALL fresh candidates (sharded search: the DP kernels only saw this rank's share)
@@ -1438,10 +1529,10 @@ int launch_id_compact(const int32_t* k3, const int32_t* cost, const int32_t* tot
 // element by element with that index, both re-materialised through their index maps.  Equal sequences always have
 // equal fingerprints, so a clean run proves the dedup of this search exact (solver.jl:535 semantics).
 // =====================================================================================================
-__global__ void k_verify_dups(ExpandArgs A, VerifyTable V, const uint32_t* is_new, const uint32_t* owner, uint32_t G,
+__global__ void k_verify_dups(ExpandArgs A, VerifyTable V, const uint32_t* fresh_mask, const uint32_t* owner, uint32_t G,
                               unsigned int* mismatches) {
   const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= G || is_new[pos]) return;
+  if (pos >= G || mask_bit(fresh_mask, pos)) return;
   const uint64_t d = A.desc[pos];
   const uint32_t ps = desc_parent(d);
   const int16_t* seq = reinterpret_cast<const int16_t*>(A.F.blob + (size_t)ps * A.F.pstride);
@@ -1461,10 +1552,10 @@ __global__ void k_verify_dups(ExpandArgs A, VerifyTable V, const uint32_t* is_ne
   for (int t = 1; same && t <= Lc; ++t) same = child_elem(seq, kind, p, q, t) == child_elem(oseq, okind, op, oq, t);
   if (!same) atomicAdd(mismatches, 1u);
 }
-int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t* is_new, const uint32_t* owner, uint32_t G,
+int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t* fresh_mask, const uint32_t* owner, uint32_t G,
                        unsigned int* mismatches, cudaStream_t st) {
   if (!G) return 0;
-  k_verify_dups<<<(G + 255) / 256, 256, 0, st>>>(A, V, is_new, owner, G, mismatches);
+  k_verify_dups<<<(G + 255) / 256, 256, 0, st>>>(A, V, fresh_mask, owner, G, mismatches);
   return 1;
 }
 

@@ -23,7 +23,7 @@ constexpr uint32_t WORK_PAD = 0xffffffffu;
 constexpr int NSUB = 8;
 // bins are (region, child length, sub-counter); lcap = (longest child length of the level) + 1
 __host__ __device__ inline int bucket_key(int rid, int lcap, int len, uint32_t new_rank) {
-  return (rid * lcap + len) * NSUB + (int)((new_rank >> 8) & (NSUB - 1));
+  return (rid * lcap + len) * NSUB + (int)((new_rank >> 10) & (NSUB - 1));
 }
 
 // Per-region read-only context in device memory.  [planes | upx | rt_rev] is one contiguous, 16-B aligned
@@ -141,8 +141,11 @@ struct AssignArgs {
   const uint32_t* slot;
   const uint64_t* table;
   const uint32_t* owner;    // first-discoverer position of each candidate's index (k_resolve)
-  const uint32_t* is_new;
-  const uint32_t* newrank;  // exclusive scan of is_new
+  // first-discoverer flags as a bit mask (bit pos & 31 of word pos >> 5) and the exclusive scan of the words' popcounts:
+  // the new-rank of ANY candidate of the level is wprefix[w] + popc(mask[w] & below(pos)), read from two arrays that
+  // stay L2-resident (1/16 of a byte-per-flag + 4-byte-per-rank layout) -- duplicates look their owner's rank up there
+  const uint32_t* fresh_mask;
+  const uint32_t* wprefix;
   const uint64_t* desc;
   const int32_t* front_len;
   uint32_t gbase, G;
@@ -195,6 +198,13 @@ __host__ __device__ inline int edge_j(const EdgeRec& e) { return (int)((e.move >
 struct IdRec {
   int32_t id, k3, cost, total;
 };
+__device__ __forceinline__ uint32_t mask_rank(const uint32_t* mask, const uint32_t* wprefix, uint32_t pos) {
+  return wprefix[pos >> 5] + __popc(mask[pos >> 5] & ((1u << (pos & 31)) - 1u));
+}
+__device__ __forceinline__ bool mask_bit(const uint32_t* mask, uint32_t pos) { return (mask[pos >> 5] >> (pos & 31)) & 1u; }
+// sub-counter of a fresh candidate's (region, length) bin: a function of its new-rank only, constant over 1024
+// consecutive ranks (one CTA of the bucket scatter)
+__host__ __device__ inline int bucket_sub(uint32_t new_rank) { return (int)((new_rank >> 10) & (NSUB - 1)); }
 // ---- launchers (return the number of kernels launched) ----
 int launch_score_fast(int W, const ScoreArgs& A, cudaStream_t st);
 bool score_fast_supports(int width);  // true if some compiled window >= width

@@ -16,9 +16,12 @@ int launch_hash_insert(const ExpandArgs& A, uint32_t G, cudaStream_t st);
 int launch_scan(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* bsum_scratch, uint32_t* total_out,
                 cudaStream_t st);
 uint64_t scan_scratch_items(uint64_t n);
-int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* is_new, uint32_t* owner, cudaStream_t st);
+int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* fresh_mask, uint32_t* wcount, uint32_t* owner,
+                   cudaStream_t st);
+int launch_gather_rank(const uint32_t* mask, const uint32_t* wprefix, const uint32_t* idx, uint32_t n, uint32_t limit,
+                       uint32_t fill, uint32_t* dst, cudaStream_t st);
 int launch_assign(const AssignArgs& A, cudaStream_t st);
-int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t* is_new, const uint32_t* owner, uint32_t G,
+int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t* fresh_mask, const uint32_t* owner, uint32_t G,
                        unsigned int* mismatches, cudaStream_t st);
 int launch_len_hist(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap, uint32_t n,
                     int force, uint32_t* hist, cudaStream_t st);
