@@ -25,7 +25,7 @@ extern "C" {
 #define NW_ERR_CUDA (-4)   /* CUDA runtime error or no device */
 #define NW_ERR_RANGE (-5)  /* lengths not integral / exceed the int32 DP range */
 #define NW_ERR_NOMEM (-6)  /* search does not fit device memory */
-#define NW_ERR_COLLISION (-7) /* NW_FLAG_VERIFY_DEDUP found two different indices with one fingerprint */
+#define NW_ERR_COLLISION (-7) /* the dedup verifier found two different indices under one key, also with other hash bases */
 
 #define NW_MOVE_DUP 0 /* MoveKind, solver.jl:34 */
 #define NW_MOVE_DEL 1
@@ -48,9 +48,16 @@ typedef struct nw_opts {
 #define NW_FLAG_GENERIC_DP 1 /* force the generic (non register-resident) DP kernel; parity cross-check */
 #define NW_FLAG_NO_TRAJ 2    /* skip trajectory enumeration (benchmarking the search itself) */
 #define NW_FLAG_PAIR_EXPAND 4 /* force the pair-testing expansion kernel (fallback for huge indices; parity cross-check) */
-#define NW_FLAG_VERIFY_DEDUP 8 /* compare every deduplicated candidate element-wise with the index it was merged into:
-                                  turns the 124-bit fingerprint dedup into a verified exact one (NW_ERR_COLLISION) */
+#define NW_FLAG_VERIFY_DEDUP 8 /* accepted for compatibility: verification is the default (see NW_FLAG_NO_VERIFY) */
 #define NW_FLAG_DEBUG_WEAK_FP 16 /* TESTS ONLY: truncate fingerprints to 8 bits so that collisions occur */
+/* Dedup exactness.  The reference dedups on the whole Vector{Int16} (solver.jl:81, :535).  Here a candidate is keyed in
+ * the dedup table by 96 bits of a 124-bit polynomial fingerprint, and EVERY candidate that was merged into an already
+ * known index is then compared with that index element by element on the device (both re-materialised through their
+ * index maps).  A search whose comparison finds a difference is repeated with other hash bases (up to twice) and
+ * fails with NW_ERR_COLLISION if that does not help, so a returned result is exact, not probabilistic.
+ * NW_FLAG_NO_VERIFY skips the comparison (benchmarking the fingerprint-only path: two different indices would then be
+ * merged silently with probability <= (4094 / 2^31)^3 per pair of distinct indices of a search). */
+#define NW_FLAG_NO_VERIFY 32
 
 typedef struct nw_stats {
   int32_t n_levels;

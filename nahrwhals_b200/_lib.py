@@ -26,6 +26,7 @@ FLAG_NO_TRAJ = 2
 FLAG_PAIR_EXPAND = 4
 FLAG_VERIFY_DEDUP = 8
 FLAG_DEBUG_WEAK_FP = 16
+FLAG_NO_VERIFY = 32
 
 # every symbol include/nwsolve.h declares (tests check that the library exports exactly these)
 SYMBOLS = ["nw_default_opts", "nw_last_error", "nw_version", "nw_ctx_create", "nw_ctx_destroy", "nw_solve",

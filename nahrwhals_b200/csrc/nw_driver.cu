@@ -244,8 +244,10 @@ struct nw_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;        // the root's own DP runs here, beside level 1 (nothing waits for it until the report)
   cudaEvent_t side_go = nullptr, side_done = nullptr;
+  cudaEvent_t ver_go = nullptr, ver_done = nullptr;  // dedup verifier of a level, on the side stream beside the level's DP
   std::vector<U4> h_pow;
   DevBuf d_pow;
+  uint64_t fp_reseed = 0;  // hash bases in use (bumped when a search's dedup verifier reports a collision)
   // regions of the current search (regionfile mode runs many independent regions through one pipeline)
   std::vector<RegionHost> RH;
   std::vector<RegionDev> RD;          // host copies; d_regions is the device array the kernels index by region id
@@ -261,7 +263,7 @@ struct nw_ctx {
   DevBuf table_prev;                 // the table a level outgrew: released when the next one is retired (no host sync)
   // per-level scratch
   DevBuf cnt, off, bsum, slot, owner, is_new, newrank, nrank, new_len, hist, bstart, cursor, work, scratch, flag, pre, sel, keys,
-      misc, edgebuf, cta_rid, new_rid, best, gather, binflag, binrank, binsum, binrec, rootwork;
+      misc, edgebuf, cta_rid, new_rid, best, gather, binflag, binrank, binsum, binrec, rootwork, rflag;
   nw::Exchange* xch = nullptr;  // NCCL communicator of the frontier-sharded search (nw_dist_init), owned by the context
   void* pinned = nullptr;  // pinned staging area for D2H scalars / histograms (grown on demand)
   size_t pinned_bytes = 0;
@@ -720,7 +722,7 @@ struct Search {
   std::vector<int> root_k3, root_cost, root_total, best_k3;  // per region
   std::vector<nw_stats> rst;                                   // per region
   nw_stats st{};                                               // whole batch (timing, launches)
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_ver = nullptr;
   std::vector<cudaEvent_t> lev;
 
   // frontier sharding (nw_solve_sharded*): every rank runs the same search, the DP of a level is divided by new-rank
@@ -733,6 +735,7 @@ struct Search {
   ~Search() {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (ev_ver) cudaEventDestroy(ev_ver);
     for (auto e : lev) cudaEventDestroy(e);
   }
 
@@ -925,9 +928,10 @@ struct Search {
     collect_roots();
   }
 
-  // NW_FLAG_VERIFY_DEDUP: element-wise comparison of every merged candidate of level d with its owner
-  void verify_level(int d, const ExpandArgs& E, const uint32_t* is_new, const uint32_t* owner, uint32_t G) {
-    cudaStream_t s = c->stream;
+  // dedup verifier: element-wise comparison of every merged candidate of level d with its owner.  No host wait: the
+  // mismatch counter (misc[12], cleared by init_root) is read once when the search ends (check_dedup).
+  bool verify() const { return !(o.flags & NW_FLAG_NO_VERIFY); }
+  void verify_level(int d, const ExpandArgs& E, const uint32_t* fresh_mask, const uint32_t* owner, uint32_t G) {
     int32_t* misc = (int32_t*)c->misc.p;
     VerifyTable V{};
     V.n_levels = d + 1;
@@ -940,14 +944,43 @@ struct Search {
       V.len[l] = fl.flen.as<int32_t>();
     }
     V.gbase[d + 1] = lv[d].gbase + G;
-    CK(cudaMemsetAsync(misc + 12, 0, 4, s));
-    c->launches += launch_verify_dups(E, V, is_new, owner, G, (unsigned int*)(misc + 12), s);
-    d2h(c, pin_u32(), misc, 64);
-    CK(spin_sync(s));
-    CK(cudaGetLastError());
+    // beside the rest of the level (id assignment, bucketing, DP) on the side stream: the verifier is bound by memory
+    // latency, the DP by the integer pipe.  It reads the level's descriptors, the first-discoverer mask and the owner
+    // positions; the next level waits for it before it overwrites the latter two (verify_join).
+    // (ver_go was recorded when the mask was complete; this launch is issued after the level's DP so that the DP is
+    // already running when the verifier reaches the device)
+    CK(cudaStreamWaitEvent(c->side, c->ver_go, 0));
+    c->launches += launch_verify_dups(E, V, fresh_mask, owner, G, (unsigned int*)(misc + 12), c->side);
+    CK(cudaEventRecord(c->ver_done, c->side));
+    if (!ev_ver) CK(cudaEventCreate(&ev_ver));
+    CK(cudaEventRecord(ev_ver, c->side));  // timed twin of ver_done: the device time of the search includes the verifier
+    ver_pending = true;
+  }
+  bool ver_pending = false;
+  void verify_join() {  // orders the main stream behind the verifier in flight (no host wait)
+    if (!ver_pending) return;
+    CK(cudaStreamWaitEvent(c->stream, c->ver_done, 0));
+    ver_pending = false;
+  }
+  // Called once per search, after the report has been extracted: the verifier of the last level runs on the side stream
+  // beside the report's kernels and host work.  A search is only handed out when this passes; its device time is the
+  // later of the two streams' ends.
+  void check_dedup() {
+    if (!verify()) return;
+    verify_join();
+    d2h(c, pin_u32(), c->misc.p, 64);
+    CK(spin_sync(c->stream));
+    if (ev_ver && ev0) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ev0, ev_ver) == cudaSuccess && ms > st.total_ms) {
+        st.total_ms = ms;
+        for (auto& q : rst) q.total_ms = ms;
+      }
+      cudaGetLastError();
+    }
     if (pin_u32()[12])
-      fail(NW_ERR_COLLISION, std::to_string(pin_u32()[12]) + " candidates of level " + std::to_string(d) +
-                                 " were merged into a different index (fingerprint collision)");
+      fail(NW_ERR_COLLISION, std::to_string(pin_u32()[12]) + " groups of merged candidates differ from the index they were "
+                             "merged into (fingerprint collision)");
   }
 
   // one BFS level: expand lv[d]'s frontier (all regions together).  Returns false when nothing new was found.
@@ -1011,6 +1044,7 @@ struct Search {
     c->launches += launch_expand(true, E, s);
     c->launches += launch_hash_insert(E, G, s);
     // first-discoverer flags as a bit mask + exclusive scan of the words' popcounts (new-rank of any candidate)
+    verify_join();
     const uint32_t nwords = (G + 31) / 32;
     const uint32_t nwords4 = (nwords + 3u) & ~3u;  // the scan reads its input as 16-byte vectors
     uint32_t* is_new = (uint32_t*)c->is_new.ensure((size_t)nwords4 * 8 + 16, true);  // [mask words | word counts]
@@ -1020,6 +1054,7 @@ struct Search {
     uint32_t* newrank = (uint32_t*)c->newrank.ensure((size_t)nwords * 4 + 16, true);  // word prefixes
     bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(nwords) * 4, true);
     c->launches += launch_scan(wcount, newrank, nwords, bsum, (uint32_t*)(misc + 5), s);
+    if (verify()) CK(cudaEventRecord(c->ver_go, s));  // everything the verifier reads is complete here
     const int lcap = std::min(std::max(maxlen, L.LS), LMAX) + 1;  // longest possible child of this level, + 1
     // single search with few (length) bins: the fresh count is fetched together with the DP buckets (one host round
     // trip less per level); the per-fresh arrays are then sized by the candidate count
@@ -1084,13 +1119,13 @@ struct Search {
     A.hist = (uint32_t*)c->hist.ensure(nbins * 4, true);
     CK(cudaMemsetAsync(A.hist, 0, nbins * 4, s));
     c->launches += launch_assign(A, s);
-    if (o.flags & NW_FLAG_VERIFY_DEDUP) verify_level(d, E, is_new, owner, G);
     CK(cudaGetLastError());
     const auto T3 = tnow();
     std::vector<int64_t> cells(R, 0);
     run_scoring(c, ScoreView{frontier_of(L), defer ? 0u : L.n_new, L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(),
                              L.k3.as<int32_t>(), L.cost.as<int32_t>(), L.total.as<int32_t>()},
                 A.hist, lcap, L.nrid.as<uint16_t>(), 0, o.flags, c->best.as<int>(), cells.data(), defer ? &n_new : nullptr, own);
+    if (verify()) verify_level(d, E, is_new, owner, G);
     if (xch && n_new) {
       // the one exchange step of a level: every rank's share of the DP results, in place, on the search's stream
       xcall([&] { xch->allgather3(L.k3.as<int32_t>(), L.cost.as<int32_t>(), L.total.as<int32_t>(), own_chunk(n_new, world), s); });
@@ -1288,7 +1323,7 @@ struct Search {
       // the frontier blob of level d is no longer needed once level d+1 is materialised (ids are kept); the root's own
       // DP on the side stream reads level 1's blob: whatever reuses that memory is ordered behind it (no host wait)
       if (d == 1 && root_pending) CK(cudaStreamWaitEvent(s, c->side_done, 0));
-      if (!(o.flags & NW_FLAG_VERIFY_DEDUP)) lv[d].fblob.release();  // the verifier re-reads old frontiers
+      if (!verify()) lv[d].fblob.release();  // the verifier re-reads the sequences of old frontiers
       if (d < D && (!any || lv[d + 1].P == 0)) {
         n_levels = D;  // solver.jl keeps looping over empty frontiers; nothing more can be generated
         break;
@@ -1335,7 +1370,8 @@ struct Search {
       uint32_t* tie_rank = nullptr;
       uint32_t q = 0xffffffffu;
       if (k3_star >= 0) {  // rank of every id tied at k3_star, in id order (levels ascend with id)
-        uint32_t* tflag = (uint32_t*)c->is_new.ensure((size_t)L.n_new * 4, true);
+        // (not is_new / owner: the last level's dedup verifier may still be reading them on the side stream)
+        uint32_t* tflag = (uint32_t*)c->rflag.ensure((size_t)L.n_new * 4, true);
         tie_rank = (uint32_t*)c->newrank.ensure((size_t)L.n_new * 4, true);
         uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(L.n_new) * 4, true);
         c->launches += launch_tie_flags(L.k3.as<int32_t>(), L.n_new, k3_star, tflag, s);
@@ -1368,7 +1404,7 @@ struct Search {
     const int nl = (int)lv.size();
     const uint32_t nflag = (uint32_t)n_ids + 1;
     CK(cudaMemsetAsync(needed + 1, 1, (size_t)R, s));  // the roots are always nodes (index r for region r)
-    uint32_t* nflags = (uint32_t*)c->is_new.ensure((size_t)nflag * 4, true);
+    uint32_t* nflags = (uint32_t*)c->rflag.ensure((size_t)nflag * 4, true);
     uint32_t* nrank = (uint32_t*)c->nrank.ensure((size_t)nflag * 4, true);
     uint32_t* bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(nflag) * 4, true);
     c->launches += launch_needed_flags(needed, nflag, nflags, s);
@@ -1878,19 +1914,40 @@ void do_solve_many(nw_ctx* c, const ProblemRef* probs, int R, const nw_opts* o, 
   };
   const auto t0 = now();
   setup_regions(c, probs, R, o->maxdepth, NW_BAND_JULIA);
-  Search S(c, *o);
-  if (xch && xch->world() > 1) {
-    S.xch = xch;
-    S.rank = xch->rank();
-    S.world = xch->world();
-  }
+  std::unique_ptr<Search> Sp;
   const auto t1 = now();
-  S.run();
-  const auto t2 = now();
+  auto t2 = t1;
   float score_ms = 0;
   int score_launches = 0;
-  collect_score_time(c, &score_ms, &score_launches);
-  if (!(o->flags & NW_FLAG_NO_TRAJ)) S.report_many(out);
+  for (int attempt = 0;; ++attempt) {
+    Sp.reset(new Search(c, *o));
+    if (xch && xch->world() > 1) {
+      Sp->xch = xch;
+      Sp->rank = xch->rank();
+      Sp->world = xch->world();
+    }
+    try {
+      Sp->run();
+      t2 = now();
+      collect_score_time(c, &score_ms, &score_launches);
+      if (!(o->flags & NW_FLAG_NO_TRAJ)) Sp->report_many(out);
+      Sp->check_dedup();
+      break;
+    } catch (const Err& e) {
+      // two different indices under one table key (found by the element-wise verifier): other hash bases, same search.
+      // Every rank of a sharded search sees the same collision (the dedup is replicated), so they all come here.
+      if (e.code != NW_ERR_COLLISION || attempt >= 2 || (o->flags & NW_FLAG_DEBUG_WEAK_FP)) throw;
+      Sp.reset();
+      for (int r = 0; r < R; ++r) *out[r] = nw_result();
+      c->fp_reseed += 1;
+      c->h_pow = build_pow_table(c->fp_reseed);
+      h2d(c, c->d_pow.p, c->h_pow.data(), c->h_pow.size() * sizeof(U4));
+      CK(spin_sync(c->stream));
+      if (c->side) CK(cudaStreamSynchronize(c->side));
+      collect_score_time(c, nullptr, nullptr);
+    }
+  }
+  Search& S = *Sp;
   const auto t3 = now();
   if (o->keep_ids) S.dump_ids(out);
   const auto t4 = now();
@@ -2004,10 +2061,18 @@ int nw_ctx_create(int device, nw_ctx** out) {
     c->device = device;
     PoolScope pool_scope(c);
     try {
-      CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-      CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+      {
+        // the side stream ranks below the main one: its kernels (one root DP, the dedup verifier) fill what the critical
+        // path leaves free -- the verifier of the last level runs under the report's short kernels and host phases
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, lo));
+      }
       CK(cudaEventCreateWithFlags(&c->side_go, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&c->side_done, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&c->ver_go, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&c->ver_done, cudaEventDisableTiming));
       CK(cudaMallocHost(&c->pinned, PINNED_BYTES));
       c->pinned_bytes = PINNED_BYTES;
       c->h_pow = build_pow_table();
@@ -2029,6 +2094,8 @@ void nw_ctx_destroy(nw_ctx* c) {
   if (c->side) cudaStreamSynchronize(c->side);
   if (c->side_go) cudaEventDestroy(c->side_go);
   if (c->side_done) cudaEventDestroy(c->side_done);
+  if (c->ver_go) cudaEventDestroy(c->ver_go);
+  if (c->ver_done) cudaEventDestroy(c->ver_done);
   if (c->side) cudaStreamDestroy(c->side);
   delete c->xch;
   c->xch = nullptr;
@@ -2570,10 +2637,6 @@ void nw_dist_shutdown(nw_ctx* c) {
   if (!c || !c->xch) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  if (c->side) cudaStreamSynchronize(c->side);
-  if (c->side_go) cudaEventDestroy(c->side_go);
-  if (c->side_done) cudaEventDestroy(c->side_done);
-  if (c->side) cudaStreamDestroy(c->side);
   delete c->xch;
   c->xch = nullptr;
 }

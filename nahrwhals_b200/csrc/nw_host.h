@@ -112,9 +112,11 @@ inline uint32_t powmod(uint32_t b, uint64_t e) {
   }
   return r;
 }
-inline std::vector<U4> build_pow_table() {
+inline std::vector<U4> build_pow_table(uint64_t reseed = 0) {
   std::vector<U4> pw(2 * FP_EMAX + 1);
-  uint64_t s = 0x9E3779B97F4A7C15ull;  // splitmix64, fixed seed -> reproducible fingerprints
+  // splitmix64, fixed seed -> reproducible fingerprints; `reseed` > 0 picks other bases (a search whose dedup verifier
+  // found two different indices under one key is repeated with new bases)
+  uint64_t s = 0x9E3779B97F4A7C15ull + reseed * 0xD1B54A32D192ED03ull;
   for (int k = 0; k < 4; ++k) {
     uint32_t B;
     do {

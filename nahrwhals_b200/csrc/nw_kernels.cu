@@ -1529,28 +1529,100 @@ int launch_id_compact(const int32_t* k3, const int32_t* cost, const int32_t* tot
 // element by element with that index, both re-materialised through their index maps.  Equal sequences always have
 // equal fingerprints, so a clean run proves the dedup of this search exact (solver.jl:535 semantics).
 // =====================================================================================================
-__global__ void k_verify_dups(ExpandArgs A, VerifyTable V, const uint32_t* fresh_mask, const uint32_t* owner, uint32_t G,
-                              unsigned int* mismatches) {
+// Branch-free index map of a move (the same form the DP kernel stages children with): element t (1-based) of the child
+// is sgn * seq[src - 1] with src = t > lo ? t + shift : t, mirrored and negated inside an inversion window (lo, hi).
+struct MoveMap {
+  const int16_t* seq;
+  int lo, hi, shift, pq;  // pq = p + q (inversion mirror)
+};
+__device__ __forceinline__ MoveMap move_map(const int16_t* seq, int kind, int p, int q) {
+  MoveMap m;
+  m.seq = seq;
+  m.lo = kind == KIND_DEL ? p - 1 : (kind == KIND_DUP ? q : (kind == KIND_INV ? p : 0x7fffffff));
+  m.hi = kind == KIND_INV ? q : 0;  // hi <= lo: no inversion window
+  m.shift = kind == KIND_DUP ? p - q : (kind == KIND_DEL ? q - p : 0);
+  m.pq = p + q;
+  return m;
+}
+__device__ __forceinline__ int map_elem(const MoveMap& m, int t) {
+  const bool flip = t > m.lo && t < m.hi;
+  int src = t > m.lo ? t + m.shift : t;
+  src = flip ? m.pq - t : src;
+  const int v = m.seq[src - 1];
+  return flip ? -v : v;
+}
+// A warp takes 32 consecutive candidates; every lane prepares the two index maps of its own candidate (its move over its
+// parent, the owner's move over the owner's parent -- one random read of the owner's descriptor), then the merged
+// candidates of the warp are compared four at a time by groups of 8 lanes striding over the elements (coalesced reads of
+// the parent sequences in the frontier blobs, L2-resident at these sizes).  No host synchronisation: mismatches
+// accumulate in a device counter that the search reads once, at its end.  Measured alternatives (profiles/README.md):
+// one thread per merged candidate with run-wise word compares is slower (6.5 active lanes per instruction).
+__global__ void __launch_bounds__(256) k_verify_dups(ExpandArgs A, VerifyTable V, const uint32_t* fresh_mask, const uint32_t* owner,
+                                                     uint32_t G, unsigned int* mismatches) {
   const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= G || mask_bit(fresh_mask, pos)) return;
-  const uint64_t d = A.desc[pos];
-  const uint32_t ps = desc_parent(d);
-  const int16_t* seq = reinterpret_cast<const int16_t*>(A.F.blob + (size_t)ps * A.F.pstride);
-  const int kind = desc_kind(d), p = desc_i(d), q = desc_j(d);
-  const int Lc = child_len(A.F.len[ps], kind, p, q);
-  // locate the owner: level, position inside the level, descriptor, parent sequence
-  const uint32_t g = owner[pos];
-  int l = 0;
-  while (l + 1 < V.n_levels && g >= V.gbase[l + 1]) ++l;
-  const uint32_t opos = g - V.gbase[l];
-  const uint64_t od = V.desc[l][opos];
-  const uint32_t ops = desc_parent(od);
-  const int16_t* oseq = reinterpret_cast<const int16_t*>(V.blob[l] + (size_t)ops * V.pstride[l]);
-  const int okind = desc_kind(od), op = desc_i(od), oq = desc_j(od);
-  const int oL = child_len(V.len[l][ops], okind, op, oq);
-  bool same = oL == Lc;
-  for (int t = 1; same && t <= Lc; ++t) same = child_elem(seq, kind, p, q, t) == child_elem(oseq, okind, op, oq, t);
-  if (!same) atomicAdd(mismatches, 1u);
+  const int lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
+  const uint32_t base = pos - lane;
+  const uint32_t word = base < G ? fresh_mask[base >> 5] : 0xffffffffu;
+  const uint32_t valid = base + 32u <= G ? 0xffffffffu : (G > base ? ((1u << (G - base)) - 1u) : 0u);
+  uint32_t todo = ~word & valid;  // merged candidates of this warp (warp-uniform)
+  if (!todo) return;
+  MoveMap ma{nullptr, 0, 0, 0, 0}, mb{nullptr, 0, 0, 0, 0};
+  int Lc = 0, oL = -1;
+  if ((todo >> lane) & 1u) {
+    const uint64_t d = A.desc[pos];
+    const uint32_t ps = desc_parent(d);
+    ma = move_map(reinterpret_cast<const int16_t*>(A.F.blob + (size_t)ps * A.F.pstride), desc_kind(d), desc_i(d), desc_j(d));
+    Lc = child_len(A.F.len[ps], desc_kind(d), desc_i(d), desc_j(d));
+    const uint32_t g = owner[pos];
+    int l = 0;
+    while (l + 1 < V.n_levels && g >= V.gbase[l + 1]) ++l;
+    const uint64_t od = V.desc[l][g - V.gbase[l]];
+    const uint32_t ops = desc_parent(od);
+    mb = move_map(reinterpret_cast<const int16_t*>(V.blob[l] + (size_t)ops * V.pstride[l]), desc_kind(od), desc_i(od), desc_j(od));
+    oL = child_len(V.len[l][ops], desc_kind(od), desc_i(od), desc_j(od));
+  }
+  unsigned int bad = 0;
+  while (todo) {  // four merged candidates per round: group g takes the g-th set bit
+    uint32_t rest = todo;
+    int src = -1;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int bit = rest ? __ffs(rest) - 1 : -1;
+      if (g == grp) src = bit;
+      if (rest) rest &= rest - 1;
+    }
+    todo = rest;
+    const int from = src < 0 ? lane : src;  // idle groups shadow themselves (no comparison below)
+    MoveMap a, b;
+    a.seq = reinterpret_cast<const int16_t*>(__shfl_sync(0xffffffffu, (unsigned long long)ma.seq, from));
+    a.lo = __shfl_sync(0xffffffffu, ma.lo, from);
+    a.hi = __shfl_sync(0xffffffffu, ma.hi, from);
+    a.shift = __shfl_sync(0xffffffffu, ma.shift, from);
+    a.pq = __shfl_sync(0xffffffffu, ma.pq, from);
+    b.seq = reinterpret_cast<const int16_t*>(__shfl_sync(0xffffffffu, (unsigned long long)mb.seq, from));
+    b.lo = __shfl_sync(0xffffffffu, mb.lo, from);
+    b.hi = __shfl_sync(0xffffffffu, mb.hi, from);
+    b.shift = __shfl_sync(0xffffffffu, mb.shift, from);
+    b.pq = __shfl_sync(0xffffffffu, mb.pq, from);
+    const int n = __shfl_sync(0xffffffffu, Lc, from), no = __shfl_sync(0xffffffffu, oL, from);
+    if (src < 0) continue;
+    bool diff = n != no;
+    if (!diff)
+      for (int t0 = 1 + gl; t0 <= n; t0 += 32) {  // four elements per lane and step: eight loads in flight together
+        int va[4], vb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + 8 * u;
+          const int tc = t <= n ? t : 1;  // past the end: re-read element 1 (equal on both sides or already different)
+          va[u] = map_elem(a, tc);
+          vb[u] = map_elem(b, tc);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) diff |= va[u] != vb[u];
+      }
+    if (diff) bad = 1;
+  }
+  if (bad) atomicAdd(mismatches, 1u);  // any non-zero count condemns the search
 }
 int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t* fresh_mask, const uint32_t* owner, uint32_t G,
                        unsigned int* mismatches, cudaStream_t st) {

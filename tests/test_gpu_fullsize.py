@@ -65,9 +65,9 @@ def test_s64_exhaustive_depth3_matches_oracle_fixture(solver):
     check_against_fixture(solver, "s64")
 
 
-def test_s64_exhaustive_verified_dedup(solver):
-    """The same search with the element-wise dedup verifier on: identical results, no collision."""
-    check_against_fixture(solver, "s64", verify_dedup=True)
+def test_s64_exhaustive_unverified_dedup(solver):
+    """The same search with the element-wise dedup verifier switched off (NW_FLAG_NO_VERIFY): identical results."""
+    check_against_fixture(solver, "s64", verify_dedup=False)
 
 
 def test_genome_sample_matches_oracle_fixture(solver):

@@ -228,22 +228,25 @@ def test_solve_batch_regions(oracle):
 
 
 def test_dedup_verifier(solver, oracle):
-    """NW_FLAG_VERIFY_DEDUP re-materialises every merged candidate and compares it element-wise with its owner: a
-    clean run proves the fingerprint dedup exact.  With fingerprints truncated to 8 bits (test-only flag) collisions
-    are certain and the verifier must report NW_ERR_COLLISION instead of returning a wrong search."""
+    """By default every merged candidate is re-materialised and compared element-wise with its owner (include/nwsolve.h,
+    "Dedup exactness"): a returned search is exact.  With fingerprints truncated to 8 bits (test-only flag) collisions
+    are certain and the search must fail with NW_ERR_COLLISION instead of returning a wrong result."""
     from nahrwhals_b200._lib import NwError
     mat, lx, ly, _ = sdgrid(n_x=64, families=[6, 5, 5, 4], seed=1, chain_depth=3)
     aln = to_solver_inputs(mat)
     kw = dict(maxdepth=3, maxdup=2, minreport=0.98, maxreport=1000)
     O = oracle.solve(aln, lx, ly, **kw)
-    G = solver.solve(aln, lx, ly, keep_ids=True, verify_dedup=True, **kw)
+    G = solver.solve(aln, lx, ly, keep_ids=True, **kw)
     assert_search_equal(G, O)
     with pytest.raises(NwError) as e:
-        solver.solve(aln, lx, ly, verify_dedup=True, debug_weak_fp=True, **kw)
+        solver.solve(aln, lx, ly, debug_weak_fp=True, **kw)
     assert e.value.code == -7 and "collision" in str(e.value)
     # without the verifier the truncated fingerprints silently merge different indices (fewer unique ids)
-    W = solver.solve(aln, lx, ly, debug_weak_fp=True, **kw)
+    W = solver.solve(aln, lx, ly, debug_weak_fp=True, verify_dedup=False, **kw)
     assert sum(W.scored) < int(O.scored.sum())
+    # the fingerprint-only path (NW_FLAG_NO_VERIFY) gives the same search when nothing collides
+    U = solver.solve(aln, lx, ly, keep_ids=True, verify_dedup=False, **kw)
+    assert_search_equal(U, O)
     # and the context is still usable afterwards
     G2 = solver.solve(aln, lx, ly, **kw)
     assert G2.tsv == O.tsv
@@ -435,7 +438,7 @@ def test_full_size_properties_bench_workload(solver, oracle):
     from nahrwhals_b200.distributed import solve_sharded_local
     import nahrwhals_b200 as nb
     aln, lx, ly, flags, _ = make_workload("s64", 1)
-    A = solver.solve(aln, lx, ly, keep_ids=True, verify_dedup=True, **flags)
+    A = solver.solve(aln, lx, ly, keep_ids=True, **flags)
     assert sum(A.generated) > 1.5e7 and sum(A.scored) > 1.0e7  # really the full-size workload
     assert A.stats.n_ids == 1 + sum(A.scored)
     B = solver.solve(aln, lx, ly, keep_ids=True, generic_dp=True, **flags)

@@ -12,8 +12,8 @@ from bench import make_workload  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "s64"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 aln, lx, ly, flags, desc = make_workload(name, 1)
-if os.environ.get("NW_PROFILE_VERIFY"):   # cost of the element-wise dedup verifier
-    flags = dict(flags, verify_dedup=True)
+if os.environ.get("NW_PROFILE_NO_VERIFY"):   # fingerprint-only dedup: what the element-wise verifier costs
+    flags = dict(flags, verify_dedup=False)
 s = nb.Solver(0)
 for r in range(reps):
     t0 = time.perf_counter()
