@@ -879,6 +879,9 @@ def regions_section(solvers, dist, torch, rank, world, total_regions, per_pass):
     costs = [estimate_region_cost(a, FLAGS["maxdepth"], FLAGS["maxwidth"]) for a, _, _ in regs]
     mine = shard_regions(costs, world)[rank]
     my = [regs[k] for k in mine]
+    # a pass per context and round: strong scaling leaves every rank total / world regions, and passes of the single-GPU
+    # size would leave most contexts of an 8-GPU run without a second pass to overlap with
+    per_pass = max(64, min(per_pass, -(-len(my) // (2 * len(solvers)))))
     warm = make_regions(min(1500, total_regions), seed=1000 + rank)
     for _ in range(2):
         nb.solve_many(solvers, warm, regions_per_pass=per_pass, **FLAGS)
@@ -889,7 +892,8 @@ def regions_section(solvers, dist, torch, rank, world, total_regions, per_pass):
         dist.barrier()
         tm = {}
         t0 = time.perf_counter()
-        res = nb.solve_many(solvers, batch, regions_per_pass=per_pass, timing=tm, **FLAGS) if batch else []
+        pp = per_pass if batch is my else max(per_pass, 512)
+        res = nb.solve_many(solvers, batch, regions_per_pass=pp, timing=tm, **FLAGS) if batch else []
         return time.perf_counter() - t0, tm.get("native_s", 0.0), sum(sum(R.scored) for R in res)
     nb.solve_many(solvers, my, regions_per_pass=per_pass, **FLAGS)  # shapes of the timed batch warm (corridor tables)
     wall, native, scored = timed(my)
@@ -1048,6 +1052,21 @@ def main():
         h2d += R.stats.h2d_bytes
         d2h += R.stats.d2h_bytes
     clocks = sampler.stop()
+    # ---- the same search with the element-wise dedup verifier switched off (NW_FLAG_NO_VERIFY): reported, not the metric.
+    # The product default verifies every merged candidate against its owner (exact dedup, as the reference's Dict).
+    nv_ms, nv_e2e = 0.0, 0.0
+    nsteps_nv = max(2, min(args.steps, 5))
+    for _ in range(2):
+        solver.solve(aln, lx, ly, verify_dedup=False, **flags)
+    for _ in range(nsteps_nv):
+        l2_flush()
+        barrier()
+        t1 = time.perf_counter()
+        R2 = solver.solve(np.array(aln), np.array(lx), np.array(ly), verify_dedup=False, **flags)
+        nv_e2e += time.perf_counter() - t1
+        nv_ms += R2.stats.total_ms
+    nv_ms /= nsteps_nv
+    nv_e2e = 1e3 * nv_e2e / nsteps_nv
 
     print("[bench rank %d] device ms/step %.3f, e2e ms/step %.3f, scored/step %d" %
           (rank, dev_ms / args.steps, 1e3 * e2e_t / args.steps, scored // args.steps), file=sys.stderr, flush=True)
@@ -1106,6 +1125,9 @@ def main():
                 data="synthetic",
                 config=dict(workload=desc + ("; one such region per GPU (%d independent regions, no collective on the data path)" % world if world > 1 else ""),
                             scored_per_step=scored_all / args.steps, l2="flushed between timed steps (256 MiB write)",
+                            dedup="exact (default): every merged candidate compared element-wise with its owner on the device",
+                            fingerprint_only_dedup=dict(ms_per_step=nv_ms, e2e_ms_per_step=nv_e2e,
+                                                        note="NW_FLAG_NO_VERIFY, this rank; not the metric"),
                             dp_share_of_step=(score_ms / (dev_ms if dist is None else max(dev_ms, 1e-9)))),
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_all / args.steps,

@@ -81,6 +81,8 @@ void nw_default_opts(nw_opts* o);
 const char* nw_last_error(void);
 const char* nw_version(void);
 
+/* CUDA devices visible to the process (0 when there is none or the driver is missing). */
+int nw_device_count(void);
 /* One context per (process, GPU).  device < 0 picks LOCAL_RANK % device_count. */
 int nw_ctx_create(int device, nw_ctx** out);
 void nw_ctx_destroy(nw_ctx* ctx);
@@ -203,6 +205,9 @@ int nw_solve_sharded(nw_ctx* ctx, const int8_t* aln_sign, int32_t n_x, int32_t n
  * (R/juliasolver.R:34-53) reaches several GPUs without a launcher. */
 int nw_solve_sharded_ctxs(nw_ctx** ctxs, int32_t world, const int8_t* aln_sign, int32_t n_x, int32_t n_y,
                           const int64_t* len_x, const int64_t* len_y, const nw_opts* opts, nw_result** outs);
+/* File form (main() of solver.jl, :755-812, over several GPUs): TSVs in, rank 0's report out, complete or not at all. */
+int nw_solve_files_sharded(nw_ctx** ctxs, int32_t world, const char* inmat_path, const char* inlens_path,
+                           const char* out_path, const nw_opts* opts, nw_stats* stats_or_null);
 
 /* Roofline denominators measured on this device with dependency-free micro-kernels:
  * out[0] VIADDMNMX, out[1] IADD3, out[2] VIADDMNMX+IMAD interleaved -- thread-instructions per second;

@@ -34,7 +34,7 @@ SYMBOLS = ["nw_default_opts", "nw_last_error", "nw_version", "nw_ctx_create", "n
            "nw_result_tsv", "nw_result_stats",
            "nw_result_ids", "nw_result_edge_count", "nw_result_edges", "nw_result_free", "nw_score_batch",
            "nw_moveset", "nw_bench_peaks", "nw_read_problem", "nw_free", "nw_dist_unique_id", "nw_dist_init",
-           "nw_dist_info", "nw_dist_shutdown", "nw_solve_sharded", "nw_solve_sharded_ctxs", "nw_solve_batch", "nw_solve_many",
+           "nw_dist_info", "nw_dist_shutdown", "nw_solve_sharded", "nw_solve_sharded_ctxs", "nw_solve_files_sharded", "nw_device_count", "nw_solve_batch", "nw_solve_many",
            "nw_solve_many_ctxs", "nw_solve_files_many", "nw_results_sizes", "nw_results_gather"]
 
 _lib = None

@@ -930,7 +930,10 @@ struct Search {
 
   // dedup verifier: element-wise comparison of every merged candidate of level d with its owner.  No host wait: the
   // mismatch counter (misc[12], cleared by init_root) is read once when the search ends (check_dedup).
-  bool verify() const { return !(o.flags & NW_FLAG_NO_VERIFY); }
+  bool verify() const {
+    static const bool env_off = getenv("NW_NO_VERIFY") != nullptr;  // diagnostics: what the verifier costs in a whole run
+    return !(o.flags & NW_FLAG_NO_VERIFY) && !env_off;
+  }
   void verify_level(int d, const ExpandArgs& E, const uint32_t* fresh_mask, const uint32_t* owner, uint32_t G) {
     int32_t* misc = (int32_t*)c->misc.p;
     VerifyTable V{};
@@ -2030,6 +2033,15 @@ const char* nw_last_error(void) { return g_last_error.c_str(); }
 
 const char* nw_version(void) { return "nwsolve-b200 0.1 (sm_100a)"; }
 
+int nw_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
 int nw_ctx_create(int device, nw_ctx** out) {
   if (!out) return NW_ERR_ARG;
   *out = nullptr;
@@ -2501,6 +2513,36 @@ int nw_solve_many_ctxs(nw_ctx** ctxs, int32_t n_ctx, const nw_problem* probs, in
   int per = max_regions_per_pass > 0 ? max_regions_per_pass : 256;
   per = std::min(per, 4096);
   const int64_t n_pass = (n + per - 1) / per;
+  // Longest-processing-time order when several contexts share the batch: regions are sorted by estimated work (cells of
+  // the gridmatrix x off-diagonal alignments, the source of moves) before they are cut into passes, so that the heavy
+  // passes are handed out first and the contexts / GPUs finish together (the reference starts regions in file order
+  // from a PSOCK pool, R/nahrwhals.R:171-215).  Results go back to the caller's order.
+  std::vector<int64_t> order;
+  std::vector<nw_problem> sorted;
+  if (n_ctx > 1 && n_pass > 1) {
+    std::vector<double> cost((size_t)n, 0.0);
+    for (int64_t k = 0; k < n; ++k) {
+      const nw_problem& q = probs[k];
+      if (!q.aln_sign || q.n_x < 1 || q.n_y < 1) continue;
+      int64_t nnz = 0;
+      const int64_t cells = (int64_t)q.n_x * q.n_y;
+      for (int64_t t = 0; t < cells; ++t) nnz += q.aln_sign[t] != 0;
+      const int64_t extra = std::max<int64_t>(0, nnz - std::min(q.n_x, q.n_y));
+      cost[k] = (double)cells * (1.0 + (double)extra);
+    }
+    order.resize((size_t)n);
+    for (int64_t k = 0; k < n; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return cost[a] > cost[b]; });
+    sorted.resize((size_t)n);
+    for (int64_t k = 0; k < n; ++k) sorted[k] = probs[order[k]];
+    probs = sorted.data();
+  }
+  std::vector<nw_result*> outs_sorted;
+  nw_result** outs_caller = outs;
+  if (!order.empty()) {
+    outs_sorted.assign((size_t)n, nullptr);
+    outs = outs_sorted.data();
+  }
   std::atomic<int64_t> next{0};
   std::atomic<int> first_err{NW_OK};
   std::mutex err_mu;
@@ -2555,6 +2597,8 @@ int nw_solve_many_ctxs(nw_ctx** ctxs, int32_t n_ctx, const nw_problem* probs, in
       outs[k] = nullptr;
     }
   }
+  if (!order.empty())
+    for (int64_t k = 0; k < n; ++k) outs_caller[order[k]] = outs[k];
   return rc;
 }
 
@@ -2737,6 +2781,26 @@ int nw_solve_sharded_ctxs(nw_ctx** ctxs, int32_t world, const int8_t* aln, int32
       delete res[r];
     }
   }
+  return rc;
+}
+
+int nw_solve_files_sharded(nw_ctx** ctxs, int32_t world, const char* inmat, const char* inlens, const char* outp,
+                           const nw_opts* o, nw_stats* stats) {
+  if (!ctxs || world < 1 || !inmat || !inlens || !outp || !o) {
+    g_last_error = "null argument";
+    return NW_ERR_ARG;
+  }
+  ProblemHost P;
+  int rc = guard([&] { P = read_problem(inmat, inlens); });
+  if (rc != NW_OK) return rc;
+  std::vector<nw_result*> res((size_t)world, nullptr);
+  nw_opts oo = *o;
+  rc = nw_solve_sharded_ctxs(ctxs, world, P.aln.data(), P.n_x, P.n_y, P.len_x.data(), P.len_y.data(), &oo, res.data());
+  if (rc == NW_OK) {
+    rc = guard([&] { write_file_atomic(outp, res[0]->tsv); });
+    if (rc == NW_OK && stats) *stats = res[0]->stats;
+  }
+  for (nw_result* r : res) delete r;
   return rc;
 }
 

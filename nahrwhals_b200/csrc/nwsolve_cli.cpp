@@ -1,6 +1,11 @@
 // nwsolve -- command-line twin of `julia solver.jl` (argument table: solver.jl:756-791 in the reference).
 //   nwsolve [-d D] [-u U] [-w W] [-O O] [-r r] [-R R] compressed_alignment compressed_lengths out_path
-//   nwsolve [flags] --batch list.tsv [--contexts K] [--regions-per-pass N]
+//   nwsolve [flags] --batch list.tsv [--contexts K] [--regions-per-pass N] [--devices 0,1,...|all]
+//   nwsolve [flags] --devices 0,1,...|all compressed_alignment compressed_lengths out_path
+// --devices spreads the work over several GPUs of the machine from this one process (no launcher): a batch hands its
+// passes to `--contexts` contexts on every listed device (regions are independent, R/nahrwhals.R:171-172: no collective);
+// a single search is sharded over one context per listed device (nw_solve_sharded_ctxs: replicated expansion, the DP of
+// every level divided between the devices, one exchange per level).  A device may be listed twice (two ranks on it).
 // --batch is the regionfile / whole-genome form (R/nahrwhals.R:171-215, :240-290 run one solver process per region):
 // every line of list.tsv is "compressed_alignment<TAB>compressed_lengths<TAB>out_path"; all regions are searched by
 // one process through nw_solve_files_many (forest search).  A region that fails leaves no out_path and a message.
@@ -20,11 +25,35 @@ static void usage() {
           "usage: nwsolve [--maxdepth|-d D] [--maxdup|-u U] [--maxwidth|-w W] [--maxoffset|-O O]\n"
           "               [--minreport|-r r] [--maxreport|-R R] [--device N] [--stats]\n"
           "               compressed_alignment compressed_lengths out_path\n"
-          "       nwsolve [flags] --batch list.tsv [--contexts K] [--regions-per-pass N]\n"
-          "               (list.tsv: compressed_alignment<TAB>compressed_lengths<TAB>out_path per line)\n");
+          "       nwsolve [flags] --batch list.tsv [--contexts K] [--regions-per-pass N] [--devices 0,1,...|all]\n"
+          "               (list.tsv: compressed_alignment<TAB>compressed_lengths<TAB>out_path per line)\n"
+          "       nwsolve [flags] --devices 0,1,...|all compressed_alignment compressed_lengths out_path\n"
+          "               (one search sharded over the listed GPUs)\n");
 }
 
-static int run_batch(const char* list, const nw_opts& o, int device, int contexts, int per_pass, bool stats) {
+// "0,1,3" or "all" -> device indices (empty on a malformed list)
+static std::vector<int> parse_devices(const char* spec) {
+  std::vector<int> out;
+  if (!strcmp(spec, "all")) {
+    const int n = nw_device_count();
+    for (int k = 0; k < n; ++k) out.push_back(k);
+    return out;
+  }
+  const char* p = spec;
+  while (*p) {
+    char* end = nullptr;
+    const long v = strtol(p, &end, 10);
+    if (end == p || v < 0 || v > 1023) return {};
+    out.push_back((int)v);
+    p = end;
+    if (*p == ',') ++p;
+    else if (*p) return {};
+  }
+  return out;
+}
+
+static int run_batch(const char* list, const nw_opts& o, const std::vector<int>& devices, int contexts, int per_pass,
+                     bool stats) {
   FILE* f = fopen(list, "rb");
   if (!f) {
     fprintf(stderr, "nwsolve: cannot open %s\n", list);
@@ -57,15 +86,16 @@ static int run_batch(const char* list, const nw_opts& o, int device, int context
   }
   const int64_t n = (int64_t)a.size();
   std::vector<nw_ctx*> ctxs;
-  for (int k = 0; k < contexts; ++k) {
-    nw_ctx* x = nullptr;
-    if (nw_ctx_create(device, &x) != NW_OK) {
-      fprintf(stderr, "nwsolve: %s\n", nw_last_error());
-      for (nw_ctx* y : ctxs) nw_ctx_destroy(y);
-      return 1;
+  for (int k = 0; k < contexts; ++k)
+    for (int device : devices) {  // device-major order inside a round: the first contexts to ask for work sit on different GPUs
+      nw_ctx* x = nullptr;
+      if (nw_ctx_create(device, &x) != NW_OK) {
+        fprintf(stderr, "nwsolve: %s\n", nw_last_error());
+        for (nw_ctx* y : ctxs) nw_ctx_destroy(y);
+        return 1;
+      }
+      ctxs.push_back(x);
     }
-    ctxs.push_back(x);
-  }
   std::vector<const char*> pa(n), pb(n), pc(n);
   for (int64_t k = 0; k < n; ++k) {
     pa[k] = a[k].c_str();
@@ -82,7 +112,9 @@ static int run_batch(const char* list, const nw_opts& o, int device, int context
       fprintf(stderr, "nwsolve: region %lld (%s) failed with code %d\n", (long long)k, pa[k], rcs[k]);
     }
   if (rc != NW_OK) fprintf(stderr, "nwsolve: %s\n", nw_last_error());
-  if (stats) fprintf(stderr, "nwsolve: %lld regions, %lld failed\n", (long long)n, (long long)bad);
+  if (stats)
+    fprintf(stderr, "nwsolve: %lld regions, %lld failed, %zu contexts on %zu device(s)\n", (long long)n, (long long)bad,
+            ctxs.size(), devices.size());
   for (nw_ctx* y : ctxs) nw_ctx_destroy(y);
   return bad ? 1 : 0;
 }
@@ -91,6 +123,7 @@ int main(int argc, char** argv) {
   nw_opts o;
   nw_default_opts(&o);
   int device = -1;
+  std::vector<int> devices;
   bool stats = false;
   const char* batch = nullptr;
   int contexts = 3, per_pass = 512;
@@ -111,6 +144,13 @@ int main(int argc, char** argv) {
     else if (s == "-r" || s == "--minreport") o.minreport = strtod(val("-r"), nullptr);
     else if (s == "-R" || s == "--maxreport") o.maxreport = (int64_t)strtod(val("-R"), nullptr);
     else if (s == "--device") device = atoi(val("--device"));
+    else if (s == "--devices") {
+      devices = parse_devices(val("--devices"));
+      if (devices.empty()) {
+        fprintf(stderr, "nwsolve: --devices needs a comma-separated list of GPU indices or 'all'\n");
+        return 2;
+      }
+    }
     else if (s == "--stats") stats = true;
     else if (s == "--batch") batch = val("--batch");
     else if (s == "--contexts") contexts = atoi(val("--contexts"));
@@ -129,12 +169,33 @@ int main(int argc, char** argv) {
       usage();
       return 2;
     }
-    return run_batch(batch, o, device, contexts, per_pass, stats);
+    if (devices.empty()) devices.push_back(device);
+    return run_batch(batch, o, devices, contexts, per_pass, stats);
   }
   if (pos.size() != 3) {
     usage();
     return 2;
   }
+  if (devices.size() > 1) {  // one search over several GPUs
+    std::vector<nw_ctx*> ctxs;
+    for (int dv : devices) {
+      nw_ctx* x = nullptr;
+      if (nw_ctx_create(dv, &x) != NW_OK) {
+        fprintf(stderr, "nwsolve: %s\n", nw_last_error());
+        for (nw_ctx* y : ctxs) nw_ctx_destroy(y);
+        return 1;
+      }
+      ctxs.push_back(x);
+    }
+    nw_stats st;
+    const int rc = nw_solve_files_sharded(ctxs.data(), (int32_t)ctxs.size(), pos[0], pos[1], pos[2], &o, &st);
+    if (rc != NW_OK) fprintf(stderr, "nwsolve: %s\n", nw_last_error());
+    else if (stats)
+      fprintf(stderr, "nwsolve: levels=%d best=%.3f device_ms=%.3f ranks=%zu\n", st.n_levels, st.best, st.total_ms, ctxs.size());
+    for (nw_ctx* y : ctxs) nw_ctx_destroy(y);
+    return rc == NW_OK ? 0 : 1;
+  }
+  if (devices.size() == 1) device = devices[0];
   nw_ctx* ctx = nullptr;
   int rc = nw_ctx_create(device, &ctx);
   if (rc != NW_OK) {

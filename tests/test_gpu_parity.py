@@ -504,3 +504,44 @@ def test_forest_equals_single_searches_at_bench_shapes(solver):
         for f in ("scores", "n_moves", "cost_bp", "total_bp", "index_id"):
             assert np.array_equal(getattr(M, f), getattr(one, f)), (k, f)
         assert np.array_equal(M.moves3, one.moves3), k
+
+
+@pytest.mark.gpu
+def test_cli_devices_batch_and_sharded_search(oracle, tmp_path):
+    """`nwsolve --devices` (the file + command-line boundary of R/juliasolver.R:34-53 over several GPUs, one process, no
+    launcher): a regionfile batch spread over the listed devices and ONE search sharded over them must write the
+    oracle's bytes.  With a single visible GPU the list names device 0 twice (two ranks / context sets on one device)."""
+    import nahrwhals_b200 as nb
+    ndev = nb._lib.load().nw_device_count()
+    devs = "0,1" if ndev >= 2 else "0,0"
+    cli = os.path.join(ROOT, "nahrwhals_b200", "csrc", "nwsolve")
+    kw = dict(maxdepth=3, maxdup=2, maxwidth=200, minreport=0.95, maxreport=100)
+    flags = ["-d", "3", "-u", "2", "-w", "200", "-r", "0.95", "-R", "100"]
+    rng = np.random.default_rng(11)
+    triples, want = [], []
+    for k in range(12):
+        n_x = int(rng.integers(10, 60))
+        mat, lx, ly, _ = sdgrid(n_x, [4, 3, 2], seed=70 + k, chain_depth=int(rng.integers(1, 4)), len_tol=0.3)
+        a, b, c = (str(tmp_path / ("d%d_%s.tsv" % (k, s))) for s in ("mat", "lens", "out"))
+        write_tsvs(mat, lx, ly, a, b)
+        triples.append((a, b, c))
+        ref = str(tmp_path / ("d%d_ref.tsv" % k))
+        assert oracle.solve_files(a, b, ref, **kw) == 0
+        want.append(open(ref, "rb").read())
+    lst = tmp_path / "dlist.tsv"
+    with open(lst, "w") as f:
+        for t in triples:
+            f.write("\t".join(t) + "\n")
+    assert subprocess.call([cli] + flags + ["--batch", str(lst), "--devices", devs, "--contexts", "2",
+                                            "--regions-per-pass", "2"]) == 0
+    for (a, b, c), w in zip(triples, want):
+        assert open(c, "rb").read() == w
+        os.remove(c)
+    # one search over the listed devices
+    for (a, b, c), w in list(zip(triples, want))[:4]:
+        assert subprocess.call([cli] + flags + ["--devices", devs, a, b, c]) == 0
+        assert open(c, "rb").read() == w
+    # a malformed device list is refused before anything runs
+    assert subprocess.call([cli] + flags + ["--devices", "0;1", triples[0][0], triples[0][1], str(tmp_path / "x.tsv")],
+                           stderr=subprocess.DEVNULL) == 2
+    assert not os.path.exists(tmp_path / "x.tsv")
