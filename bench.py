@@ -1105,10 +1105,9 @@ def main():
         per_search = score_launches / max(args.steps, 1)
         if args.workload == "s64" and per_search > 0:
             traffic = tj["dram_bytes_per_launch"] / per_search
-            traffic_note = ("dram__bytes_read+write of the level-3 launch (%d B, ncu --set full, profiles/"
-                            "r1_ncu_summary_s64.md) spread over the %d DP launches of a search; algorithmic bytes of "
-                            "that launch: %d" % (tj["dram_bytes_per_launch"], per_search,
-                                                 tj["algorithmic_bytes_per_launch"]))
+            traffic_note = ("FROM CAPTURE, not measured by this run: dram__bytes_read+write of the level-3 DP launch (%d B, "
+                            "%s) spread over the %d DP launches of a search; algorithmic bytes of that launch: %d" %
+                            (tj["dram_bytes_per_launch"], tj["source"], per_search, tj["algorithmic_bytes_per_launch"]))
     except Exception:
         pass
     roofline = dict(bound="int_alu", kernel="k_score_fast<W> (banded DP)", achieved=ach, peak=peak, unit="Tintop/s",
@@ -1141,7 +1140,8 @@ def main():
         msteps = max(5, min(args.steps, 20))
         line["config"]["frontier"] = frontier_section(solver, dist, torch, rank, world, "s150", msteps, args.warmup)
         line["config"]["frontier_exhaustive"] = frontier_section(solver, dist, torch, rank, world, "s150d3", max(3, msteps // 4), 1)
-        nctx = max(1, min(args.contexts, (os.cpu_count() or 8) // max(world, 1)))
+        # contexts per GPU: each is a host thread feeding launches plus short parallel host phases; two cores per context
+        nctx = max(1, min(args.contexts, (os.cpu_count() or 8) // (2 * max(world, 1))))
         more = [nb.Solver(local) for _ in range(nctx - 1)]
         line["config"]["regions"] = regions_section([solver] + more, dist, torch, rank, world, args.total_regions,
                                                     args.regions_per_pass)

@@ -58,6 +58,8 @@ typedef struct nw_opts {
  * NW_FLAG_NO_VERIFY skips the comparison (benchmarking the fingerprint-only path: two different indices would then be
  * merged silently with probability <= (4094 / 2^31)^3 per pair of distinct indices of a search). */
 #define NW_FLAG_NO_VERIFY 32
+#define NW_FLAG_DEBUG_WEAK_FP_ONCE 64 /* TESTS ONLY: as NW_FLAG_DEBUG_WEAK_FP, but only with the initial hash bases, so that
+                                         the repeat of the search with other bases can be observed to succeed */
 
 typedef struct nw_stats {
   int32_t n_levels;

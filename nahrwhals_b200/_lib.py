@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libnwsolve.so")
+LIB_PATH = os.environ.get("NWSOLVE_LIB") or os.path.join(HERE, "csrc", "libnwsolve.so")  # NWSOLVE_LIB: another build of the same library
 
 
 class NwOpts(C.Structure):
@@ -27,6 +27,7 @@ FLAG_PAIR_EXPAND = 4
 FLAG_VERIFY_DEDUP = 8
 FLAG_DEBUG_WEAK_FP = 16
 FLAG_NO_VERIFY = 32
+FLAG_DEBUG_WEAK_FP_ONCE = 64
 
 # every symbol include/nwsolve.h declares (tests check that the library exports exactly these)
 SYMBOLS = ["nw_default_opts", "nw_last_error", "nw_version", "nw_ctx_create", "nw_ctx_destroy", "nw_solve",

@@ -29,6 +29,7 @@
 using namespace nw;
 
 static thread_local std::string g_last_error;
+static std::atomic<int> g_live_ctxs{0};  // contexts alive in this process: they share the process's host cores
 struct nw_ctx;
 
 namespace {
@@ -729,6 +730,7 @@ struct Search {
   // ranges and completed by one all-gather (nw_exchange.h).  xch == nullptr is the plain single-GPU search.
   Exchange* xch = nullptr;
   int rank = 0, world = 1;
+  uint64_t fp_reseed0 = 0;  // hash bases of the first attempt of this call (NW_FLAG_DEBUG_WEAK_FP_ONCE)
   uint32_t edge_cap_hint = 0, id_cap_hint = 0;
   int level_maxlen = 0;  // longest duplication child of the level in flight
   explicit Search(nw_ctx* ctx, const nw_opts& opts) : c(ctx), o(opts) {}
@@ -839,8 +841,8 @@ struct Search {
     // dedup table
     c->table_cap = 0;  // logical capacity; the physical buffer is kept across solves
     table_reserve(c, (uint64_t)(1 << 15) + 4 * (uint64_t)R);
-    c->launches += launch_insert_roots(L1.fblob.as<unsigned char>(), L1.pstride, L1.flen.as<int32_t>(), R, c->d_pow.as<U4>(),
-                                       c->d_regions.as<RegionDev>(), c->table.as<uint64_t>(), c->table_cap - 1, s);
+    c->launches += launch_insert_roots(L1.fblob.as<unsigned char>(), L1.pstride, L1.LS, L1.flen.as<int32_t>(), R,
+                                       c->table.as<uint64_t>(), c->table_cap - 1, s);
     int32_t* misc = (int32_t*)c->misc.ensure(256);
     CK(cudaMemsetAsync(misc, 0, 256, s));
     CK(cudaMemsetAsync(c->best.ensure((size_t)(R + 1) * 4), 0, (size_t)(R + 1) * 4, s));
@@ -953,7 +955,14 @@ struct Search {
     // (ver_go was recorded when the mask was complete; this launch is issued after the level's DP so that the DP is
     // already running when the verifier reaches the device)
     CK(cudaStreamWaitEvent(c->side, c->ver_go, 0));
-    c->launches += launch_verify_dups(E, V, fresh_mask, owner, G, (unsigned int*)(misc + 12), c->side);
+    // sharded search: every rank checks its slice of the level's candidates; the counts are summed in check_dedup
+    uint32_t first = 0, end = G;
+    if (world > 1) {
+      const uint64_t per = ((uint64_t)G + world - 1) / world;
+      first = (uint32_t)std::min<uint64_t>(G, (per * rank) & ~31ull);
+      end = rank + 1 == world ? G : (uint32_t)std::min<uint64_t>(G, (per * (rank + 1)) & ~31ull);
+    }
+    c->launches += launch_verify_dups(E, V, fresh_mask, owner, first, end, (unsigned int*)(misc + 12), c->side);
     CK(cudaEventRecord(c->ver_done, c->side));
     if (!ev_ver) CK(cudaEventCreate(&ev_ver));
     CK(cudaEventRecord(ev_ver, c->side));  // timed twin of ver_done: the device time of the search includes the verifier
@@ -981,8 +990,10 @@ struct Search {
       }
       cudaGetLastError();
     }
-    if (pin_u32()[12])
-      fail(NW_ERR_COLLISION, std::to_string(pin_u32()[12]) + " groups of merged candidates differ from the index they were "
+    int64_t bad = pin_u32()[12];
+    if (xch) xcall([&] { xch->allreduce_sum(&bad, 1, c->stream); });  // every rank reaches the same verdict
+    if (bad)
+      fail(NW_ERR_COLLISION, std::to_string(bad) + " groups of merged candidates differ from the index they were "
                              "merged into (fingerprint collision)");
   }
 
@@ -1007,7 +1018,7 @@ struct Search {
     E.cnt = (uint32_t*)c->cnt.ensure((size_t)L.P * 4, true);
     E.maxlen = misc + 2;
     E.force_pairs = (o.flags & NW_FLAG_PAIR_EXPAND) ? 1 : 0;
-    E.weak_fp = (o.flags & NW_FLAG_DEBUG_WEAK_FP) ? 1 : 0;
+    E.weak_fp = ((o.flags & NW_FLAG_DEBUG_WEAK_FP) || ((o.flags & NW_FLAG_DEBUG_WEAK_FP_ONCE) && c->fp_reseed == fp_reseed0)) ? 1 : 0;
     CK(cudaMemsetAsync(misc + 2, 0, 4, s));
     c->launches += launch_expand(false, E, s);
     uint32_t* off = (uint32_t*)c->off.ensure((size_t)L.P * 4, true);
@@ -1746,7 +1757,7 @@ struct Search {
     build_nodes(needed, he);
     const auto T4 = tnow();
     {  // regions are independent (disjoint nodes, own result object): enumerate them on a few host threads
-      const int nt = std::max(1, std::min({8, (int)std::thread::hardware_concurrency(), R / 32}));
+      const int nt = std::max(1, std::min({8, host_cores() / std::max(1, g_live_ctxs.load()), R / 32}));
       std::atomic<int> next{0};
       std::exception_ptr err;
       std::mutex err_mu;
@@ -1922,8 +1933,10 @@ void do_solve_many(nw_ctx* c, const ProblemRef* probs, int R, const nw_opts* o, 
   auto t2 = t1;
   float score_ms = 0;
   int score_launches = 0;
+  const uint64_t reseed0 = c->fp_reseed;
   for (int attempt = 0;; ++attempt) {
     Sp.reset(new Search(c, *o));
+    Sp->fp_reseed0 = reseed0;
     if (xch && xch->world() > 1) {
       Sp->xch = xch;
       Sp->rank = xch->rank();
@@ -2070,6 +2083,7 @@ int nw_ctx_create(int device, nw_ctx** out) {
       }
     }
     nw_ctx* c = new nw_ctx();
+    g_live_ctxs.fetch_add(1);
     c->device = device;
     PoolScope pool_scope(c);
     try {
@@ -2101,6 +2115,7 @@ int nw_ctx_create(int device, nw_ctx** out) {
 
 void nw_ctx_destroy(nw_ctx* c) {
   if (!c) return;
+  g_live_ctxs.fetch_sub(1);
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->side) cudaStreamSynchronize(c->side);

@@ -10,7 +10,9 @@
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "nw_device.h"
@@ -20,6 +22,26 @@ namespace nw {
 constexpr int LMAX = FP_EMAX - 2;  // longest index (child) the search supports
 constexpr int WINDOW_MAX = 128;    // widest register window compiled in nw_score_fast.cu
 constexpr int RT_PAD = 160;        // zero padding of rt_rev beyond NYP (>= WINDOW_MAX + 4)
+
+// Host cores this PROCESS may count on for its short parallel phases (report enumeration, region prepare / replay /
+// format, PAF pre / post): the machine's hardware threads divided by the ranks a launcher started on this node
+// (torchrun / mpirun export LOCAL_WORLD_SIZE / OMPI_COMM_WORLD_LOCAL_SIZE), NW_HOST_THREADS overrides.  Eight ranks with
+// several contexts each would otherwise start hundreds of threads on a 32-core host.
+inline int host_cores() {
+  static const int n = [] {
+    if (const char* e = getenv("NW_HOST_THREADS")) return std::max(1, atoi(e));
+    unsigned hw = std::thread::hardware_concurrency();
+    int cores = hw ? (int)hw : 4;
+    for (const char* name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "SLURM_NTASKS_PER_NODE"})
+      if (const char* e = getenv(name)) {
+        const int w = atoi(e);
+        if (w > 1) cores = std::max(1, cores / w);
+        break;
+      }
+    return cores;
+  }();
+  return n;
+}
 
 struct HostError : std::runtime_error {
   int code;

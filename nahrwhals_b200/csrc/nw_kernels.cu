@@ -83,13 +83,14 @@ __global__ void k_table_rehash(const uint64_t* oldT, uint64_t old_cap, uint64_t*
   }
 }
 
-// insert the roots (region r: global position r) -- solver.jl:596-604
-__global__ void k_insert_roots(const unsigned char* blob, uint32_t pstride, const int32_t* len, int n_regions, const U4* pw,
-                               const RegionDev* regions, uint64_t* table, uint64_t tmask) {
+// insert the roots (region r: global position r) -- solver.jl:596-604.  The root's fingerprint is the last entry of the
+// prefix table F' the host wrote into its frontier blob (fill_blob), so this is one table insertion per region.
+__global__ void k_insert_roots(const unsigned char* blob, uint32_t pstride, int LS, const int32_t* len, int n_regions,
+                               uint64_t* table, uint64_t tmask) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_regions) return;
-  const int16_t* seq = reinterpret_cast<const int16_t*>(blob + (size_t)r * pstride);
-  const U4 f = seq_fingerprint(seq, len[r], pw, regions[r].rid1);
+  const U4* Ft = reinterpret_cast<const U4*>(blob + (size_t)r * pstride + (size_t)LS * 2);
+  const U4 f = Ft[len[r]];
   table_insert(table, tmask, fp_key0(f), fp_key_hi32(f), (uint32_t)r);
 }
 
@@ -1558,8 +1559,8 @@ __device__ __forceinline__ int map_elem(const MoveMap& m, int t) {
 // accumulate in a device counter that the search reads once, at its end.  Measured alternatives (profiles/README.md):
 // one thread per merged candidate with run-wise word compares is slower (6.5 active lanes per instruction).
 __global__ void __launch_bounds__(256) k_verify_dups(ExpandArgs A, VerifyTable V, const uint32_t* fresh_mask, const uint32_t* owner,
-                                                     uint32_t G, unsigned int* mismatches) {
-  const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+                                                     uint32_t first, uint32_t G, unsigned int* mismatches) {
+  const uint32_t pos = first + blockIdx.x * blockDim.x + threadIdx.x;  // first: multiple of 32; G: end of this launch's range
   const int lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
   const uint32_t base = pos - lane;
   const uint32_t word = base < G ? fresh_mask[base >> 5] : 0xffffffffu;
@@ -1624,10 +1625,11 @@ __global__ void __launch_bounds__(256) k_verify_dups(ExpandArgs A, VerifyTable V
   }
   if (bad) atomicAdd(mismatches, 1u);  // any non-zero count condemns the search
 }
-int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t* fresh_mask, const uint32_t* owner, uint32_t G,
-                       unsigned int* mismatches, cudaStream_t st) {
-  if (!G) return 0;
-  k_verify_dups<<<(G + 255) / 256, 256, 0, st>>>(A, V, fresh_mask, owner, G, mismatches);
+// verifies the candidates at positions [first, end) of the level (first a multiple of 32)
+int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t* fresh_mask, const uint32_t* owner, uint32_t first,
+                       uint32_t end, unsigned int* mismatches, cudaStream_t st) {
+  if (end <= first) return 0;
+  k_verify_dups<<<(end - first + 255) / 256, 256, 0, st>>>(A, V, fresh_mask, owner, first, end, mismatches);
   return 1;
 }
 
@@ -1704,9 +1706,9 @@ int launch_moveset(const RegionDev* regions_dev, int n_regions, int nx_max, cuda
   k_moveset<<<dim3((unsigned)((n + 255) / 256), (unsigned)n_regions), 256, 0, st>>>(regions_dev);
   return 1;
 }
-int launch_insert_roots(const unsigned char* blob, uint32_t pstride, const int32_t* len, int n_regions, const U4* pw,
-                        const RegionDev* regions, uint64_t* table, uint64_t tmask, cudaStream_t st) {
-  k_insert_roots<<<(n_regions + 127) / 128, 128, 0, st>>>(blob, pstride, len, n_regions, pw, regions, table, tmask);
+int launch_insert_roots(const unsigned char* blob, uint32_t pstride, int LS, const int32_t* len, int n_regions,
+                        uint64_t* table, uint64_t tmask, cudaStream_t st) {
+  k_insert_roots<<<(n_regions + 127) / 128, 128, 0, st>>>(blob, pstride, LS, len, n_regions, table, tmask);
   return 1;
 }
 int launch_rehash(const uint64_t* oldT, uint64_t old_cap, uint64_t* newT, uint64_t new_mask, cudaStream_t st) {

@@ -8,8 +8,8 @@ namespace nw {
 double launch_int_peak(int mode, int* out, int iters, cudaStream_t st);
 void init_kernel_attrs();  // once per device
 int launch_moveset(const RegionDev* regions_dev, int n_regions, int nx_max, cudaStream_t st);
-int launch_insert_roots(const unsigned char* blob, uint32_t pstride, const int32_t* len, int n_regions, const U4* pw,
-                        const RegionDev* regions, uint64_t* table, uint64_t tmask, cudaStream_t st);
+int launch_insert_roots(const unsigned char* blob, uint32_t pstride, int LS, const int32_t* len, int n_regions,
+                        uint64_t* table, uint64_t tmask, cudaStream_t st);
 int launch_rehash(const uint64_t* oldT, uint64_t old_cap, uint64_t* newT, uint64_t new_mask, cudaStream_t st);
 int launch_expand(bool emit, const ExpandArgs& A, cudaStream_t st);
 int launch_hash_insert(const ExpandArgs& A, uint32_t G, cudaStream_t st);
@@ -21,8 +21,8 @@ int launch_resolve(const ExpandArgs& A, uint32_t G, uint32_t* fresh_mask, uint32
 int launch_gather_rank(const uint32_t* mask, const uint32_t* wprefix, const uint32_t* idx, uint32_t n, uint32_t limit,
                        uint32_t fill, uint32_t* dst, cudaStream_t st);
 int launch_assign(const AssignArgs& A, cudaStream_t st);
-int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t* fresh_mask, const uint32_t* owner, uint32_t G,
-                       unsigned int* mismatches, cudaStream_t st);
+int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t* fresh_mask, const uint32_t* owner, uint32_t first,
+                       uint32_t end, unsigned int* mismatches, cudaStream_t st);
 int launch_len_hist(const uint16_t* new_len, const uint16_t* new_rid, const RegionDev* regions, int lcap, uint32_t n,
                     int force, uint32_t* hist, cudaStream_t st);
 constexpr uint32_t BINS_SMALL_LIMIT = 8192;  // launch_bins_small handles up to this many (region, length) bins

@@ -29,6 +29,7 @@
 #include <string>
 #include <vector>
 
+#include "nw_host.h"
 #include "../../include/nwbitlocus.h"
 #include "../../include/nwpaf.h"
 
@@ -56,8 +57,8 @@ struct PErr {
 // tables are independent on the host side: the pre / post phases of a batch run on a few threads.  fn must not throw
 // anything but PErr; the first error is rethrown on the calling thread.
 void paf_parallel_for(int64_t n, const std::function<void(int64_t)>& fn) {
-  unsigned hw = std::thread::hardware_concurrency();
-  const int nt = (int)std::min<int64_t>(std::max<int64_t>(1, n / 2), std::min<unsigned>(hw ? hw : 4, 8u));
+  const unsigned hw = (unsigned)nw::host_cores();
+  const int nt = (int)std::min<int64_t>(std::max<int64_t>(1, n / 2), std::min<unsigned>(hw, 8u));
   if (nt <= 1) {
     for (int64_t k = 0; k < n; ++k) fn(k);
     return;

@@ -31,6 +31,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "nw_host.h"
 #include "../../include/nwregion.h"
 
 struct nw_ctx;
@@ -280,8 +281,8 @@ nw_opts solver_opts(const nw_region_opts& o, double width) {
 // Regions are independent on the host side too: the prepare / replay / format phases of a batch run on a few threads.
 thread_local int g_host_threads = 12;  // budget of the calling thread (divided among contexts by the _ctxs entry point)
 void parallel_for(int64_t n, const std::function<void(int64_t)>& fn) {
-  unsigned hw = std::thread::hardware_concurrency();
-  const int nt = (int)std::min<int64_t>(std::max<int64_t>(1, n / 8), std::min<unsigned>(hw ? hw : 4, (unsigned)std::max(1, g_host_threads)));
+  const unsigned hw = (unsigned)nw::host_cores();
+  const int nt = (int)std::min<int64_t>(std::max<int64_t>(1, n / 8), std::min<unsigned>(hw, (unsigned)std::max(1, g_host_threads)));
   if (nt <= 1) {
     for (int64_t k = 0; k < n; ++k) fn(k);
     return;
@@ -543,8 +544,7 @@ int nw_region_analyse_many_ctxs(nw_ctx** ctxs, int32_t n_ctx, const nw_region_pr
     std::mutex mu;
     bool failed = false;
     RErr err{NW_OK, ""};
-    unsigned hw = std::thread::hardware_concurrency();
-    const int per_ctx = std::max(2, (int)(hw ? hw : 8) / n_ctx);
+    const int per_ctx = std::max(1, nw::host_cores() / n_ctx);
     auto work = [&](int t) {
       g_host_threads = per_ctx;
       for (;;) {

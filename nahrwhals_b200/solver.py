@@ -94,7 +94,7 @@ class Solver:
 
     def _opts(self, maxdepth=3, maxdup=3, maxwidth=None, minreport=0.95, maxreport=None, keep_ids=False,
               generic_dp=False, no_traj=False, pair_expand=False, verify_dedup=True, debug_weak_fp=False,
-              maxoffset=4):
+              debug_weak_fp_once=False, maxoffset=4):
         o = _lib.NwOpts()
         self.L.nw_default_opts(C.byref(o))
         o.maxdepth, o.maxdup = int(maxdepth), int(maxdup)
@@ -104,7 +104,8 @@ class Solver:
         o.keep_ids = 1 if keep_ids else 0
         o.flags = ((_lib.FLAG_GENERIC_DP if generic_dp else 0) | (_lib.FLAG_NO_TRAJ if no_traj else 0) |
                    (_lib.FLAG_PAIR_EXPAND if pair_expand else 0) | (0 if verify_dedup else _lib.FLAG_NO_VERIFY) |
-                   (_lib.FLAG_DEBUG_WEAK_FP if debug_weak_fp else 0))
+                   (_lib.FLAG_DEBUG_WEAK_FP if debug_weak_fp else 0) |
+                   (_lib.FLAG_DEBUG_WEAK_FP_ONCE if debug_weak_fp_once else 0))
         return o
 
     @staticmethod

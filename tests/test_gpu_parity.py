@@ -244,6 +244,10 @@ def test_dedup_verifier(solver, oracle):
     # without the verifier the truncated fingerprints silently merge different indices (fewer unique ids)
     W = solver.solve(aln, lx, ly, debug_weak_fp=True, verify_dedup=False, **kw)
     assert sum(W.scored) < int(O.scored.sum())
+    # a collision is cured by repeating the search with other hash bases: weak fingerprints on the first attempt only
+    # -> the verifier rejects it, the second attempt (other bases, full fingerprints) is the oracle's search
+    T = solver.solve(aln, lx, ly, keep_ids=True, debug_weak_fp_once=True, **kw)
+    assert_search_equal(T, O)
     # the fingerprint-only path (NW_FLAG_NO_VERIFY) gives the same search when nothing collides
     U = solver.solve(aln, lx, ly, keep_ids=True, verify_dedup=False, **kw)
     assert_search_equal(U, O)
