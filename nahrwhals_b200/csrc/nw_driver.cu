@@ -685,7 +685,17 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
     }
     CK(cudaEventRecord(ev.first, st));
     if (r.cls) {
-      const int l = launch_score_fast(r.cls, A, st);
+      // Form of the register DP for this launch.  The cooperative form (four lanes per candidate) has a quarter of the
+      // dependent chain per row, so a launch too small to fill the device finishes sooner (the latency of ONE thread's DP
+      // is the floor of the thread form); it executes ~2.7x the instructions per cell, so everything larger stays with
+      // one thread per candidate (measured on S150 / S64: profiles/README.md).  NW_DP_COOP=0 / 1 forces one form.
+      static const int coop_mode = getenv("NW_DP_COOP") ? atoi(getenv("NW_DP_COOP")) : -1;
+      static const int coop_max_ctas = getenv("NW_DP_COOP_MAX_CTAS") ? atoi(getenv("NW_DP_COOP_MAX_CTAS")) : 48;
+      const int cw = score_coop_window(r.cls);
+      bool coop = cw && score_coop_smem(cw, c->ctx_max, r.lmax) <= 200 * 1024;
+      if (coop && coop_mode == 0) coop = false;
+      if (coop && coop_mode < 0) coop = (int)(A.n_work / 128) < coop_max_ctas;
+      const int l = coop ? launch_score_coop(cw, A, st) : launch_score_fast(r.cls, A, st);
       if (l < 0) fail(NW_ERR_CUDA, "no register-DP kernel for window " + std::to_string(r.cls));
       c->launches += l;
     } else {
@@ -916,7 +926,14 @@ struct Search {
     A.n_work = 32;
     A.lmax = L;
     A.cta_rid = nullptr;
-    if (launch_score_fast(cls, A, c->side) < 0) fail(NW_ERR_CUDA, "no register-DP kernel for window " + std::to_string(cls));
+    {
+      // one candidate: the cooperative form has a quarter of the latency (NW_DP_COOP=0 keeps the thread form)
+      static const int coop_mode = getenv("NW_DP_COOP") ? atoi(getenv("NW_DP_COOP")) : -1;
+      const int cw = score_coop_window(cls);
+      const bool coop = coop_mode != 0 && cw && score_coop_smem(cw, c->ctx_max, L) <= 200 * 1024;
+      if ((coop ? launch_score_coop(cw, A, c->side) : launch_score_fast(cls, A, c->side)) < 0)
+        fail(NW_ERR_CUDA, "no register-DP kernel for window " + std::to_string(cls));
+    }
     c->launches += 1;
     CK(cudaEventRecord(c->side_done, c->side));
     CK(cudaGetLastError());

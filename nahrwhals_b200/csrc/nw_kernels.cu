@@ -1530,106 +1530,168 @@ int launch_id_compact(const int32_t* k3, const int32_t* cost, const int32_t* tot
 // element by element with that index, both re-materialised through their index maps.  Equal sequences always have
 // equal fingerprints, so a clean run proves the dedup of this search exact (solver.jl:535 semantics).
 // =====================================================================================================
-// Branch-free index map of a move (the same form the DP kernel stages children with): element t (1-based) of the child
-// is sgn * seq[src - 1] with src = t > lo ? t + shift : t, mirrored and negated inside an inversion window (lo, hi).
-struct MoveMap {
-  const int16_t* seq;
-  int lo, hi, shift, pq;  // pq = p + q (inversion mirror)
+// Element t (1-based) of a child through the index map of its move over the parent sequence `seq`:
+//   dup / del / identity:  seq[t - 1 + (t > lo ? shift : 0)]          (lo = q / p-1 / never, shift = p-q / q-p / 0)
+//   inversion:             lo < t < hi ? -seq[lo + hi - t - 1] : seq[t - 1]           (lo = p, hi = q)
+// (apply_duplication / apply_deletion / apply_inversion, solver.jl:244-278).
+struct VerItem {            // 32 bytes in shared memory, one per merged candidate of the CTA
+  uint32_t psA, psB;        // parent slots (A in this level's frontier, B in the frontier of level lvB)
+  uint32_t lvB_n;           // owner's level | child length << 8
+  uint32_t loA_hiA;         // lo | hi << 16   (hi = 0: no inversion window)
+  int32_t shA;              // shift of the non-inversion map
+  uint32_t loB_hiB;
+  int32_t shB;
+  uint32_t pad;
 };
-__device__ __forceinline__ MoveMap move_map(const int16_t* seq, int kind, int p, int q) {
-  MoveMap m;
-  m.seq = seq;
-  m.lo = kind == KIND_DEL ? p - 1 : (kind == KIND_DUP ? q : (kind == KIND_INV ? p : 0x7fffffff));
-  m.hi = kind == KIND_INV ? q : 0;  // hi <= lo: no inversion window
-  m.shift = kind == KIND_DUP ? p - q : (kind == KIND_DEL ? q - p : 0);
-  m.pq = p + q;
-  return m;
+__device__ __forceinline__ void move_params(int L, int kind, int p, int q, uint32_t& lo_hi, int32_t& sh) {
+  int lo = kind == KIND_DEL ? p - 1 : (kind == KIND_DUP ? q : (kind == KIND_INV ? p : 0x7fff));
+  int hi = kind == KIND_INV ? q : 0;
+  sh = kind == KIND_DUP ? p - q : (kind == KIND_DEL ? q - p : 0);
+  lo_hi = (uint32_t)lo | ((uint32_t)hi << 16);
 }
-__device__ __forceinline__ int map_elem(const MoveMap& m, int t) {
-  const bool flip = t > m.lo && t < m.hi;
-  int src = t > m.lo ? t + m.shift : t;
-  src = flip ? m.pq - t : src;
-  const int v = m.seq[src - 1];
-  return flip ? -v : v;
+template <bool INV>
+__device__ __forceinline__ int ver_elem(const int16_t* seq, int lo, int hi, int sh, int t) {
+  if (INV) {
+    const bool flip = t > lo && t < hi;
+    const int v = seq[(unsigned)(flip ? lo + hi - t - 1 : t - 1)];
+    return flip ? -v : v;
+  }
+  return seq[(unsigned)(t - 1 + (t > lo ? sh : 0))];
 }
-// A warp takes 32 consecutive candidates; every lane prepares the two index maps of its own candidate (its move over its
-// parent, the owner's move over the owner's parent -- one random read of the owner's descriptor), then the merged
-// candidates of the warp are compared four at a time by groups of 8 lanes striding over the elements (coalesced reads of
-// the parent sequences in the frontier blobs, L2-resident at these sizes).  No host synchronisation: mismatches
-// accumulate in a device counter that the search reads once, at its end.  Measured alternatives (profiles/README.md):
-// one thread per merged candidate with run-wise word compares is slower (6.5 active lanes per instruction).
+template <bool INVA, bool INVB>
+__device__ __forceinline__ bool ver_compare(const int16_t* sa, int loA, int hiA, int shA, const int16_t* sb, int loB, int hiB,
+                                            int shB, int n, int gl) {
+  bool diff = false;
+  int t = 1 + gl;
+  for (; t + 8 <= n; t += 16) {  // two elements per lane and step: four loads in flight
+    const int a0 = ver_elem<INVA>(sa, loA, hiA, shA, t), b0 = ver_elem<INVB>(sb, loB, hiB, shB, t);
+    const int a1 = ver_elem<INVA>(sa, loA, hiA, shA, t + 8), b1 = ver_elem<INVB>(sb, loB, hiB, shB, t + 8);
+    diff |= (a0 != b0) | (a1 != b1);
+  }
+  if (t <= n) diff |= ver_elem<INVA>(sa, loA, hiA, shA, t) != ver_elem<INVB>(sb, loB, hiB, shB, t);
+  return diff;
+}
+// Element-wise dedup verifier.  A CTA takes 1024 consecutive candidates.  Phase 1 (4 candidates per thread): every merged
+// candidate reads its own move and -- one random read -- its owner's, and leaves a 32-byte item in shared memory, filed
+// under its class: no inversion on either side / on one side (filed with that side as B: equality is symmetric) / on
+// both.  Phase 2: groups of 8 lanes take one item each and stride over the elements (coalesced reads of the parent
+// sequences in the frontier blobs, L2-resident at these sizes).  The items are walked in (class, length) order -- a
+// counting sort in shared memory --, so the four groups of a warp run the same specialised loop the same number of times:
+// no per-element kind tests and next to no divergence between the groups.
+// No host synchronisation: mismatches accumulate in a device counter that the search reads once, at its end.
+constexpr int VER_CAND = 1024;
+constexpr int VER_LBINS = 32;            // length bins of 8 elements (longer children share the last bin)
+constexpr int VER_BINS = 3 * VER_LBINS;  // (class, length bin)
 __global__ void __launch_bounds__(256) k_verify_dups(ExpandArgs A, VerifyTable V, const uint32_t* fresh_mask, const uint32_t* owner,
                                                      uint32_t first, uint32_t G, unsigned int* mismatches) {
-  const uint32_t pos = first + blockIdx.x * blockDim.x + threadIdx.x;  // first: multiple of 32; G: end of this launch's range
-  const int lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
-  const uint32_t base = pos - lane;
-  const uint32_t word = base < G ? fresh_mask[base >> 5] : 0xffffffffu;
-  const uint32_t valid = base + 32u <= G ? 0xffffffffu : (G > base ? ((1u << (G - base)) - 1u) : 0u);
-  uint32_t todo = ~word & valid;  // merged candidates of this warp (warp-uniform)
-  if (!todo) return;
-  MoveMap ma{nullptr, 0, 0, 0, 0}, mb{nullptr, 0, 0, 0, 0};
-  int Lc = 0, oL = -1;
-  if ((todo >> lane) & 1u) {
-    const uint64_t d = A.desc[pos];
-    const uint32_t ps = desc_parent(d);
-    ma = move_map(reinterpret_cast<const int16_t*>(A.F.blob + (size_t)ps * A.F.pstride), desc_kind(d), desc_i(d), desc_j(d));
-    Lc = child_len(A.F.len[ps], desc_kind(d), desc_i(d), desc_j(d));
-    const uint32_t g = owner[pos];
-    int l = 0;
-    while (l + 1 < V.n_levels && g >= V.gbase[l + 1]) ++l;
-    const uint64_t od = V.desc[l][g - V.gbase[l]];
-    const uint32_t ops = desc_parent(od);
-    mb = move_map(reinterpret_cast<const int16_t*>(V.blob[l] + (size_t)ops * V.pstride[l]), desc_kind(od), desc_i(od), desc_j(od));
-    oL = child_len(V.len[l][ops], desc_kind(od), desc_i(od), desc_j(od));
-  }
-  unsigned int bad = 0;
-  while (todo) {  // four merged candidates per round: group g takes the g-th set bit
-    uint32_t rest = todo;
-    int src = -1;
+  __shared__ __align__(16) VerItem s_item[VER_CAND];
+  __shared__ uint16_t s_order[VER_CAND];
+  __shared__ uint32_t s_bin[VER_BINS + 1];  // items per (class, length bin); [VER_BINS] = items filed
+  __shared__ uint32_t s_base[VER_BINS];
+  const int tid = threadIdx.x;
+  if (tid <= VER_BINS) s_bin[tid] = 0;
+  __syncthreads();
+  bool bad = false;
+  int my_slot[4] = {-1, -1, -1, -1}, my_key[4] = {0, 0, 0, 0};
+  const uint32_t pos0 = first + blockIdx.x * (uint32_t)VER_CAND + (uint32_t)tid * 4u;  // first: multiple of 32
+  if (pos0 < G) {
+    const uint32_t word = fresh_mask[pos0 >> 5] >> (pos0 & 31);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int bit = rest ? __ffs(rest) - 1 : -1;
-      if (g == grp) src = bit;
-      if (rest) rest &= rest - 1;
-    }
-    todo = rest;
-    const int from = src < 0 ? lane : src;  // idle groups shadow themselves (no comparison below)
-    MoveMap a, b;
-    a.seq = reinterpret_cast<const int16_t*>(__shfl_sync(0xffffffffu, (unsigned long long)ma.seq, from));
-    a.lo = __shfl_sync(0xffffffffu, ma.lo, from);
-    a.hi = __shfl_sync(0xffffffffu, ma.hi, from);
-    a.shift = __shfl_sync(0xffffffffu, ma.shift, from);
-    a.pq = __shfl_sync(0xffffffffu, ma.pq, from);
-    b.seq = reinterpret_cast<const int16_t*>(__shfl_sync(0xffffffffu, (unsigned long long)mb.seq, from));
-    b.lo = __shfl_sync(0xffffffffu, mb.lo, from);
-    b.hi = __shfl_sync(0xffffffffu, mb.hi, from);
-    b.shift = __shfl_sync(0xffffffffu, mb.shift, from);
-    b.pq = __shfl_sync(0xffffffffu, mb.pq, from);
-    const int n = __shfl_sync(0xffffffffu, Lc, from), no = __shfl_sync(0xffffffffu, oL, from);
-    if (src < 0) continue;
-    bool diff = n != no;
-    if (!diff)
-      for (int t0 = 1 + gl; t0 <= n; t0 += 32) {  // four elements per lane and step: eight loads in flight together
-        int va[4], vb[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int t = t0 + 8 * u;
-          const int tc = t <= n ? t : 1;  // past the end: re-read element 1 (equal on both sides or already different)
-          va[u] = map_elem(a, tc);
-          vb[u] = map_elem(b, tc);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) diff |= va[u] != vb[u];
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t pos = pos0 + u;
+      if (pos >= G || ((word >> u) & 1u)) continue;
+      const uint64_t d = A.desc[pos];
+      const uint32_t ps = desc_parent(d);
+      const int L = A.F.len[ps];
+      const int kind = desc_kind(d), p = desc_i(d), q = desc_j(d);
+      const int n = child_len(L, kind, p, q);
+      const uint32_t g = owner[pos];
+      int l = 0;
+      while (l + 1 < V.n_levels && g >= V.gbase[l + 1]) ++l;
+      const uint64_t od = V.desc[l][g - V.gbase[l]];
+      const uint32_t ops = desc_parent(od);
+      const int Lo = V.len[l][ops];
+      const int okind = desc_kind(od), op = desc_i(od), oq = desc_j(od);
+      if (n != child_len(Lo, okind, op, oq)) {
+        bad = true;
+        continue;
       }
-    if (diff) bad = 1;
+      VerItem it;
+      uint32_t lhA, lhB;
+      int32_t shA, shB;
+      move_params(L, kind, p, q, lhA, shA);
+      move_params(Lo, okind, op, oq, lhB, shB);
+      // parent A lives in this level's frontier (level index V.n_levels - 1), parent B in level l's; store both as
+      // (level, slot) so that the two sides can be swapped
+      const int lvA = V.n_levels - 1;
+      const bool invA = kind == KIND_INV, invB = okind == KIND_INV;
+      const bool swap = invA && !invB;  // a single inversion is filed as side B
+      it.psA = swap ? ops : ps;
+      it.psB = swap ? ps : ops;
+      const int cls = (invA ? 1 : 0) + (invB ? 1 : 0);
+      it.lvB_n = (uint32_t)(swap ? lvA : l) | ((uint32_t)(swap ? l : lvA) << 4) | ((uint32_t)n << 8) | ((uint32_t)cls << 24);
+      it.loA_hiA = swap ? lhB : lhA;
+      it.shA = swap ? shB : shA;
+      it.loB_hiB = swap ? lhA : lhB;
+      it.shB = swap ? shA : shB;
+      it.pad = 0;
+      const uint32_t slot = atomicAdd(&s_bin[VER_BINS], 1u);
+      s_item[slot] = it;
+      // key = class, then length in steps of 8 elements (one stride of a lane group): neighbours in the processing order
+      // run the same loop the same number of times
+      const int key = cls * VER_LBINS + min(VER_LBINS - 1, n >> 3);
+      atomicAdd(&s_bin[key], 1u);
+      my_slot[u] = (int)slot;
+      my_key[u] = key;
+    }
   }
-  if (bad) atomicAdd(mismatches, 1u);  // any non-zero count condemns the search
+  __syncthreads();
+  if (tid < 32) {  // exclusive scan of the bins (one warp, VER_BINS <= 96)
+    uint32_t carry = 0;
+    for (int b0 = 0; b0 < VER_BINS; b0 += 32) {
+      const int b = b0 + tid;
+      const uint32_t v = b < VER_BINS ? s_bin[b] : 0u;
+      uint32_t inc = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (tid >= o) inc += t;
+      }
+      if (b < VER_BINS) {
+        s_base[b] = carry + inc - v;
+        s_bin[b] = 0;  // becomes the placement cursor
+      }
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (my_slot[u] >= 0) s_order[s_base[my_key[u]] + atomicAdd(&s_bin[my_key[u]], 1u)] = (uint16_t)my_slot[u];
+  __syncthreads();
+  const int grp = tid >> 3, gl = tid & 7;  // 32 groups of 8 lanes
+  const uint32_t n_items = s_bin[VER_BINS];
+  for (uint32_t i = grp; i < n_items; i += 32) {
+    const VerItem it = s_item[s_order[i]];
+    const int lvB = (int)(it.lvB_n & 15u), lvA = (int)((it.lvB_n >> 4) & 15u), n = (int)((it.lvB_n >> 8) & 0xffffu);
+    const int cls = (int)(it.lvB_n >> 24);
+    // level 0 of the table is the root pseudo-level: its "frontier" is level 1's (V.blob[0] is set accordingly)
+    const int16_t* sa = reinterpret_cast<const int16_t*>(V.blob[lvA] + (size_t)it.psA * V.pstride[lvA]);
+    const int16_t* sb = reinterpret_cast<const int16_t*>(V.blob[lvB] + (size_t)it.psB * V.pstride[lvB]);
+    const int loA = (int)(it.loA_hiA & 0xffffu), hiA = (int)(it.loA_hiA >> 16);
+    const int loB = (int)(it.loB_hiB & 0xffffu), hiB = (int)(it.loB_hiB >> 16);
+    bool diff;
+    if (cls == 0) diff = ver_compare<false, false>(sa, loA, hiA, it.shA, sb, loB, hiB, it.shB, n, gl);
+    else if (cls == 1) diff = ver_compare<false, true>(sa, loA, hiA, it.shA, sb, loB, hiB, it.shB, n, gl);
+    else diff = ver_compare<true, true>(sa, loA, hiA, it.shA, sb, loB, hiB, it.shB, n, gl);
+    bad |= diff;
+  }
+  if (__syncthreads_or(bad ? 1 : 0) && tid == 0) atomicAdd(mismatches, 1u);  // any non-zero count condemns the search
 }
 // verifies the candidates at positions [first, end) of the level (first a multiple of 32)
 int launch_verify_dups(const ExpandArgs& A, const VerifyTable& V, const uint32_t* fresh_mask, const uint32_t* owner, uint32_t first,
                        uint32_t end, unsigned int* mismatches, cudaStream_t st) {
   if (end <= first) return 0;
-  k_verify_dups<<<(end - first + 255) / 256, 256, 0, st>>>(A, V, fresh_mask, owner, first, end, mismatches);
+  k_verify_dups<<<(end - first + VER_CAND - 1) / VER_CAND, 256, 0, st>>>(A, V, fresh_mask, owner, first, end, mismatches);
   return 1;
 }
 
@@ -1678,6 +1740,7 @@ double launch_int_peak(int mode, int* out, int iters, cudaStream_t st) {
 // Opt-in dynamic shared memory limits are per (device, function) state: they are raised ONCE per device here, never
 // per launch (a per-launch cudaFuncSetAttribute races between contexts running on different host threads).
 void init_score_fast_attrs();
+void init_score_coop_attrs();
 void init_kernel_attrs() {
   int dev = 0, optin = 0;
   cudaGetDevice(&dev);
@@ -1699,6 +1762,7 @@ void init_kernel_attrs() {
   cudaFuncSetAttribute(k_expand_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   cudaFuncSetAttribute(k_materialise, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   init_score_fast_attrs();
+  init_score_coop_attrs();
 }
 
 int launch_moveset(const RegionDev* regions_dev, int n_regions, int nx_max, cudaStream_t st) {

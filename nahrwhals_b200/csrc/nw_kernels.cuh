@@ -210,6 +210,10 @@ int launch_score_fast(int W, const ScoreArgs& A, cudaStream_t st);
 bool score_fast_supports(int width);  // true if some compiled window >= width
 int score_fast_window(int width);     // smallest compiled window >= width (0 if none)
 size_t score_fast_smem(int W, uint32_t ctx_bytes, int lmax);  // dynamic shared memory of one CTA
+// warp-cooperative form (nw_score_coop.cu): four lanes per candidate, CTA = 32 work slots
+int launch_score_coop(int W, const ScoreArgs& A, cudaStream_t st);
+int score_coop_window(int width);  // smallest compiled cooperative window >= width (0 if none)
+size_t score_coop_smem(int W, uint32_t ctx_bytes, int lmax);
 
 // ---- small device helpers ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
