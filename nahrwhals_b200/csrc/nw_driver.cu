@@ -1232,18 +1232,29 @@ struct Search {
       uint64_t* keys = (uint64_t*)c->keys.ensure((size_t)npad * 8, true);
       uint32_t* hist = (uint32_t*)c->hist.ensure((size_t)100008 * 4, true);
       // flag is consumed (the valid flags are no longer needed), pre becomes the tie ranks
+      bsum = (uint32_t*)c->bsum.ensure(std::max<uint64_t>(scan_scratch_items(n), 128) * 4, true);
       c->launches += launch_topk_keys(Lr.k3.as<int32_t>(), n, wsel, hist, hist + 100001, flag, pre, bsum, (uint32_t*)(misc + 7),
                                       keys, npad, s);
-      uint32_t* seg = (uint32_t*)c->gather.ensure((size_t)(3 * R + 3) * 4, true);
-      const uint32_t pack[3] = {0u, wsel, 0u};
-      h2d(c, seg, pack, sizeof pack);
-      c->launches += launch_take_sorted(keys, wsel, seg, seg + 1, seg + 2, sel, s);
+      if (rank_select_fits(wsel)) {  // the winners in frontier order by counting (no sort network, no padding)
+        c->launches += launch_rank_select(keys, wsel, sel, s);
+      } else {
+        c->launches += launch_sort_u64(keys, npad, s);
+        uint32_t* seg = (uint32_t*)c->gather.ensure((size_t)(3 * R + 3) * 4, true);
+        const uint32_t pack[3] = {0u, wsel, 0u};
+        h2d(c, seg, pack, sizeof pack);
+        c->launches += launch_take_sorted(keys, wsel, seg, seg + 1, seg + 2, sel, s);
+      }
     } else if (nvalid) {
       uint64_t npad = 2048;
       while (npad < nvalid) npad <<= 1;
       uint64_t* keys = (uint64_t*)c->keys.ensure(npad * 8, true);
       c->launches += launch_make_keys(Lr.k3.as<int32_t>(), R > 1 ? Lr.nrid.as<uint16_t>() : nullptr, flag, pre, n, keys, nvalid,
                                       npad, s);
+      if (R == 1 && rank_select_fits(nvalid) && (int64_t)take[0] == (int64_t)nvalid) {
+        // one region keeping every valid child (small levels): order by counting, straight into sel
+        c->launches += launch_rank_select(keys, nvalid, sel, s);
+        goto selected;
+      }
       c->launches += launch_sort_u64(keys, npad, s);
       // sorted keys are region-major: region r occupies [vstart[r], vstart[r+1]); keep its first take[r]
       uint32_t* seg = (uint32_t*)c->gather.ensure((size_t)(3 * R + 3) * 4, true);
@@ -1257,6 +1268,7 @@ struct Search {
       c->launches += launch_take_sorted(keys, nvalid, seg, seg + R, seg + 2 * (size_t)R, sel, s);
       // no sync: the pageable source of the H2D above is consumed when cudaMemcpyAsync returns
     }
+  selected:
     if (P2 == 0) return;
     int maxlen = std::max(level_maxlen, c->nx_max);
     maxlen = std::max(maxlen, Lr.LS);  // inversions keep the parent's length

@@ -1144,21 +1144,107 @@ __global__ void k_topk_keys(const int32_t* __restrict__ k3, uint32_t n, uint32_t
   }
   keys[pos] = ((uint64_t)(uint32_t)(100000 - v) << 31) | r;
 }
-// keys[0..npad) <- the w best of k3[0..n) in frontier order (ascending key), npad a power of two >= max(w, 2048);
-// needs more than w valid candidates.  hist: 100001 words, thr: 4 words, flag / tie_rank: n words
+// The same threshold search over many CTAs: CTA b sums the 1024 bins [100000 - 1024 b - 1023, 100000 - 1024 b]; the CTA
+// that finishes last walks the 98 block sums from the best score down, then the 1024 bins of the block in which the
+// running count crosses w.  thr[4] counts finished CTAs and bsum[] holds the block sums (both zeroed by the caller).
+constexpr int TOPK_BLOCKS = 98;  // 98 x 1024 >= 100001
+__global__ void __launch_bounds__(256) k_topk_threshold_mc(const uint32_t* __restrict__ hist, uint32_t w, uint32_t* __restrict__ thr,
+                                                           uint32_t* __restrict__ bsum) {
+  __shared__ uint32_t sh[33];
+  __shared__ int s_last;
+  const int t = threadIdx.x;
+  auto block_sum = [&](int b, uint32_t (&v)[4]) {  // thread t holds bins hi - 4t .. hi - 4t - 3 of block b (descending)
+    const int hi = 100000 - b * 1024 - t * 4;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int bin = hi - i;
+      v[i] = bin >= 0 ? hist[bin] : 0u;
+      sum += v[i];
+    }
+    return sum;
+  };
+  uint32_t v[4];
+  uint32_t total;
+  const uint32_t mine = block_sum(blockIdx.x, v);
+  block_excl_scan(mine, sh, total);
+  if (t == 0) {
+    bsum[blockIdx.x] = total;
+    __threadfence();
+    s_last = atomicAdd(&thr[4], 1u) == (uint32_t)gridDim.x - 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  __shared__ uint32_t s_blk, s_before;
+  if (t == 0) {
+    uint32_t cum = 0;
+    int b = 0;
+    for (; b < (int)gridDim.x; ++b) {
+      const uint32_t x = __ldcg(&bsum[b]);
+      if (cum + x >= w) break;
+      cum += x;
+    }
+    s_blk = (uint32_t)b;
+    s_before = cum;
+  }
+  __syncthreads();
+  if (s_blk >= gridDim.x) return;  // fewer than w candidates: the caller never asks for that
+  const uint32_t sum = block_sum((int)s_blk, v);
+  const uint32_t before = s_before + block_excl_scan(sum, sh, total);
+  if (before < w && w <= before + sum) {
+    uint32_t cum = before;
+    const int hi = 100000 - (int)s_blk * 1024 - t * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (cum + v[i] >= w) {
+        thr[0] = (uint32_t)(hi - i);
+        thr[1] = w - cum;
+        thr[2] = cum;
+        thr[3] = 0;
+        break;
+      }
+      cum += v[i];
+    }
+  }
+}
+// Order of up to RANK_MAX unique keys by counting: every thread finds how many keys are smaller than its own (all keys in
+// shared memory) and writes its payload (the low 31 bits: the discovery rank) at that place -- a sort of the beam's few
+// winners without the 66 barrier-separated steps of a single-CTA bitonic network.
+constexpr uint32_t RANK_MAX = 4096;
+__global__ void __launch_bounds__(256) k_rank_select(const uint64_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ sel) {
+  extern __shared__ uint64_t s_keys[];
+  for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) s_keys[j] = keys[j];
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = s_keys[i];
+  uint32_t rank = 0;
+#pragma unroll 8
+  for (uint32_t j = 0; j < n; ++j) rank += s_keys[j] < k ? 1u : 0u;
+  sel[rank] = (uint32_t)(k & 0x7fffffffu);
+}
+int launch_rank_select(const uint64_t* keys, uint32_t n, uint32_t* sel, cudaStream_t st) {
+  if (!n) return 0;
+  k_rank_select<<<(n + 255) / 256, 256, (size_t)n * 8, st>>>(keys, n, sel);
+  return 1;
+}
+bool rank_select_fits(uint64_t n) { return n <= RANK_MAX; }
+
+// keys[0..w) <- the w best of k3[0..n) (unordered; ascending key == frontier order), keys[w..npad) padding; needs more than
+// w valid candidates.  hist: 100008 words (the last 7 are thr), flag / tie_rank: n words
 int launch_topk_keys(const int32_t* k3, uint32_t n, uint32_t w, uint32_t* hist, uint32_t* thr, uint32_t* flag, uint32_t* tie_rank,
                      uint32_t* bsum_scratch, uint32_t* total_out, uint64_t* keys, uint32_t npad, cudaStream_t st) {
   int l = 0;
-  cudaMemsetAsync(hist, 0, (size_t)100001 * 4, st);
+  cudaMemsetAsync(hist, 0, (size_t)100008 * 4, st);
   k_k3_hist<<<(n + 255) / 256, 256, 0, st>>>(k3, n, 0, hist);
-  k_topk_threshold<<<1, 1024, 0, st>>>(hist, w, thr);
+  k_topk_threshold_mc<<<TOPK_BLOCKS, 256, 0, st>>>(hist, w, thr, bsum_scratch);
   k_topk_tie_flags<<<(n + 255) / 256, 256, 0, st>>>(k3, n, thr, flag);
   l += 3;
   l += launch_scan(flag, tie_rank, n, bsum_scratch, total_out, st);
   const uint32_t cover = n > npad ? n : npad;
   k_topk_keys<<<(cover + 255) / 256, 256, 0, st>>>(k3, n, thr, tie_rank, w, keys, npad);
   ++l;
-  l += launch_sort_u64(keys, npad, st);
   return l;
 }
 

@@ -52,6 +52,8 @@ int launch_set_needed(const int32_t* gids, uint32_t n, uint8_t* needed, cudaStre
 int launch_sort_u64(uint64_t* keys, uint64_t npad, cudaStream_t st);
 int launch_topk_keys(const int32_t* k3, uint32_t n, uint32_t w, uint32_t* hist, uint32_t* thr, uint32_t* flag, uint32_t* tie_rank,
                      uint32_t* bsum_scratch, uint32_t* total_out, uint64_t* keys, uint32_t npad, cudaStream_t st);
+int launch_rank_select(const uint64_t* keys, uint32_t n, uint32_t* sel, cudaStream_t st);
+bool rank_select_fits(uint64_t n);
 int launch_keys_to_sel(const uint64_t* keys, uint32_t n, uint32_t* sel, cudaStream_t st);
 int launch_materialise(const MaterialiseArgs& A, cudaStream_t st);
 int launch_good_flags(const int32_t* k3, uint32_t n, int32_t id_base, int k3_min, int k3_star, uint32_t quota,
