@@ -986,6 +986,9 @@ struct Search {
     ver_pending = true;
   }
   bool ver_pending = false;
+  // issue point of the verifier: right behind the scan (it then fills the gaps of id assignment, the bucket round trip and
+  // the scatter, and waits out the DP) or behind the DP launch
+  bool verify_early = getenv("NW_VERIFY_LATE") == nullptr;
   void verify_join() {  // orders the main stream behind the verifier in flight (no host wait)
     if (!ver_pending) return;
     CK(cudaStreamWaitEvent(c->stream, c->ver_done, 0));
@@ -1085,7 +1088,10 @@ struct Search {
     uint32_t* newrank = (uint32_t*)c->newrank.ensure((size_t)nwords * 4 + 16, true);  // word prefixes
     bsum = (uint32_t*)c->bsum.ensure(scan_scratch_items(nwords) * 4, true);
     c->launches += launch_scan(wcount, newrank, nwords, bsum, (uint32_t*)(misc + 5), s);
-    if (verify()) CK(cudaEventRecord(c->ver_go, s));  // everything the verifier reads is complete here
+    if (verify()) {  // everything the verifier reads is complete here
+      CK(cudaEventRecord(c->ver_go, s));
+      if (verify_early) verify_level(d, E, is_new, owner, G);
+    }
     const int lcap = std::min(std::max(maxlen, L.LS), LMAX) + 1;  // longest possible child of this level, + 1
     // single search with few (length) bins: the fresh count is fetched together with the DP buckets (one host round
     // trip less per level); the per-fresh arrays are then sized by the candidate count
@@ -1156,7 +1162,7 @@ struct Search {
     run_scoring(c, ScoreView{frontier_of(L), defer ? 0u : L.n_new, L.newlist.as<uint32_t>(), L.desc.as<uint64_t>(),
                              L.k3.as<int32_t>(), L.cost.as<int32_t>(), L.total.as<int32_t>()},
                 A.hist, lcap, L.nrid.as<uint16_t>(), 0, o.flags, c->best.as<int>(), cells.data(), defer ? &n_new : nullptr, own);
-    if (verify()) verify_level(d, E, is_new, owner, G);
+    if (verify() && !verify_early) verify_level(d, E, is_new, owner, G);
     if (xch && n_new) {
       // the one exchange step of a level: every rank's share of the DP results, in place, on the search's stream
       xcall([&] { xch->allgather3(L.k3.as<int32_t>(), L.cost.as<int32_t>(), L.total.as<int32_t>(), own_chunk(n_new, world), s); });
