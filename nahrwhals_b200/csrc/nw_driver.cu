@@ -2563,10 +2563,12 @@ int nw_solve_many_ctxs(nw_ctx** ctxs, int32_t n_ctx, const nw_problem* probs, in
   int per = max_regions_per_pass > 0 ? max_regions_per_pass : 256;
   per = std::min(per, 4096);
   const int64_t n_pass = (n + per - 1) / per;
-  // Longest-processing-time order when several contexts share the batch: regions are sorted by estimated work (cells of
-  // the gridmatrix x off-diagonal alignments, the source of moves) before they are cut into passes, so that the heavy
-  // passes are handed out first and the contexts / GPUs finish together (the reference starts regions in file order
-  // from a PSOCK pool, R/nahrwhals.R:171-215).  Results go back to the caller's order.
+  // Passes of equal estimated work when several contexts share the batch: regions are sorted by estimated work (cells of
+  // the gridmatrix x off-diagonal alignments, the source of moves) and dealt round-robin into the passes -- the
+  // longest-processing-time rule applied to the passes --, so every pass is the same mix of heavy and light regions:
+  // contexts / GPUs finish together, and every pass needs the same buffer sizes (a pass far heavier than the ones a
+  // context's memory pool has seen costs a cudaMalloc, which stalls every context on the device).  The reference starts
+  // regions in file order from a PSOCK pool (R/nahrwhals.R:171-215).  Results go back to the caller's order.
   std::vector<int64_t> order;
   std::vector<nw_problem> sorted;
   if (n_ctx > 1 && n_pass > 1) {
@@ -2580,9 +2582,31 @@ int nw_solve_many_ctxs(nw_ctx** ctxs, int32_t n_ctx, const nw_problem* probs, in
       const int64_t extra = std::max<int64_t>(0, nnz - std::min(q.n_x, q.n_y));
       cost[k] = (double)cells * (1.0 + (double)extra);
     }
-    order.resize((size_t)n);
-    for (int64_t k = 0; k < n; ++k) order[k] = k;
-    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return cost[a] > cost[b]; });
+    std::vector<int64_t> by_cost((size_t)n);
+    for (int64_t k = 0; k < n; ++k) by_cost[k] = k;
+    std::stable_sort(by_cost.begin(), by_cost.end(), [&](int64_t a, int64_t b) { return cost[a] > cost[b]; });
+    // pass p takes the regions at sorted positions p, p + n_pass, p + 2 n_pass, ...; passes are contiguous runs of `per`
+    order.assign((size_t)n, 0);
+    int64_t at = 0;
+    for (int64_t pass = 0; pass < n_pass; ++pass) {
+      const int64_t m = std::min<int64_t>(per, n - pass * per);
+      for (int64_t j = 0, src = pass; j < m; ++j, src += n_pass) {
+        // the last passes may run out of their stride: fall back to the unused tail in order
+        order[at++] = src < n ? by_cost[src] : -1;
+      }
+    }
+    {  // repair the (rare) holes left by a short last pass
+      std::vector<char> used((size_t)n, 0);
+      for (int64_t k = 0; k < n; ++k)
+        if (order[k] >= 0) used[order[k]] = 1;
+      int64_t spare = 0;
+      for (int64_t k = 0; k < n; ++k)
+        if (order[k] < 0) {
+          while (used[by_cost[spare]]) ++spare;
+          order[k] = by_cost[spare];
+          used[by_cost[spare]] = 1;
+        }
+    }
     sorted.resize((size_t)n);
     for (int64_t k = 0; k < n; ++k) sorted[k] = probs[order[k]];
     probs = sorted.data();
