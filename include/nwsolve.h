@@ -49,6 +49,9 @@ typedef struct nw_opts {
 #define NW_FLAG_NO_TRAJ 2    /* skip trajectory enumeration (benchmarking the search itself) */
 #define NW_FLAG_PAIR_EXPAND 4 /* force the pair-testing expansion kernel (fallback for huge indices; parity cross-check) */
 #define NW_FLAG_VERIFY_DEDUP 8 /* accepted for compatibility: verification is the default (see NW_FLAG_NO_VERIFY) */
+#define NW_FLAG_DP32 128 /* keep every DP launch on the 32-bit register kernel (k_score_fast); without it a (region,
+                            child length) bucket whose totals fit 15 bits runs on the packed 16-bit kernel (k_score_pair,
+                            two candidates per thread).  Results are identical; parity cross-check */
 #define NW_FLAG_DEBUG_WEAK_FP 16 /* TESTS ONLY: truncate fingerprints to 8 bits so that collisions occur */
 /* Dedup exactness.  The reference dedups on the whole Vector{Int16} (solver.jl:81, :535).  Here a candidate is keyed in
  * the dedup table by 96 bits of a 124-bit polynomial fingerprint, and EVERY candidate that was merged into an already

@@ -28,6 +28,7 @@ FLAG_VERIFY_DEDUP = 8
 FLAG_DEBUG_WEAK_FP = 16
 FLAG_NO_VERIFY = 32
 FLAG_DEBUG_WEAK_FP_ONCE = 64
+FLAG_DP32 = 128
 
 # every symbol include/nwsolve.h declares (tests check that the library exports exactly these)
 SYMBOLS = ["nw_default_opts", "nw_last_error", "nw_version", "nw_ctx_create", "nw_ctx_destroy", "nw_solve",

@@ -200,12 +200,63 @@ NW_HD void dp_row_step(int (&S)[W], const uint32_t* m, int up, const RT& rtw) {
 }
 
 // pure shift by one column (no matches), used to decompose SB > 2
-template <int W>
-NW_HD void dp_row_shift1(int (&S)[W]) {
+template <int W, typename T>
+NW_HD void dp_row_shift1(T (&S)[W]) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int k = W - 1; k >= 1; --k) S[k] = S[k - 1];
+}
+
+// ---------------------------------------------------------------- packed row step: two candidates per register
+// The same recurrence on two candidates of one child length at once, one in each 16-bit half of a register, with the
+// packed DPX instruction (VIADDMNMX.S16x2: per-half max(a + b, c)).  Valid when every candidate's total is below
+// PAIR_TOTAL_MAX units: every intermediate (a savings value, or savings + rt + up of a path prefix) is bounded by the
+// total, so no half ever overflows into its neighbour.
+// The diagonal update cannot be predicated per half, so the match bit is folded into the addend instead:
+//     addend_half = rt | (match ? 0 : 0x8000)          (= rt - 32768 when the cell does not match)
+// a masked candidate lands in [-32768, -1] and loses every max against the savings (>= 0) it competes with, also
+// after `up` is added (dv + rt + up <= total < 32768).  Mq[g] holds the match bits of window cells 16g .. 16g+15:
+// candidate A's in bits 0..15, candidate B's in bits 16..31, so `Mq[g] << (15 - c)` (an IMAD.SHL on the FMA pipe)
+// brings both bits of cell 16g + c to the sign positions and ONE LOP3 builds the addend: three ALU-pipe
+// instructions per cell PAIR against two per cell in dp_row_step.
+constexpr int PAIR_TOTAL_MAX = 32767;
+constexpr uint32_t PAIR_NEG = 0x80008000u;  // (-32768, -32768)
+
+NW_HD uint32_t viaddmax2(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+  return __viaddmax_s16x2(a, b, c);
+#else
+  uint32_t out = 0;
+  for (int h = 0; h < 2; ++h) {
+    const int16_t x = (int16_t)(uint16_t)(((a >> (16 * h)) + (b >> (16 * h))) & 0xffffu);  // wrapping 16-bit add
+    const int16_t y = (int16_t)(uint16_t)((c >> (16 * h)) & 0xffffu);
+    out |= (uint32_t)(uint16_t)(x > y ? x : y) << (16 * h);
+  }
+  return out;
+#endif
+}
+
+template <int W, int SB, typename RT>
+NW_HD void dp_row_step2(uint32_t (&S)[W], const uint32_t* Mq, uint32_t up2, const RT& rt2) {
+  uint32_t runp = PAIR_NEG;
+  uint32_t saved = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = W - 1; k >= 0; --k) {
+    const int us = (k - SB >= 0) ? (k - SB) : 0;
+    const int ds = k - SB + 1;
+    const uint32_t upv = S[us];
+    if (ds >= 0 && ds <= W - 1) {
+      const uint32_t dv = (SB == 0) ? saved : S[ds];
+      const uint32_t v = Mq[k >> 4] << (15 - (k & 15));
+      const uint32_t a2 = (uint32_t)rt2[k] | (~v & PAIR_NEG);
+      runp = viaddmax2(dv, a2, runp);
+    }
+    if (SB == 0) saved = S[k];
+    S[k] = viaddmax2(runp, up2, upv);
+  }
 }
 
 }  // namespace nw

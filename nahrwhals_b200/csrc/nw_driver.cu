@@ -554,13 +554,19 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
     CK(spin_sync(st));
   }
   struct Bucket {
-    int rid, L, cls;  // cls: window W (fast) or 0 (generic)
+    int rid, L, cls;  // cls: window W (32-bit register kernel), W | CLS_PAIR (packed register kernel) or 0 (generic)
     uint32_t n, bin;
+  };
+  constexpr int CLS_PAIR = 0x1000;
+  // NW_DP_PAIR=0 keeps every bucket on the 32-bit register kernel (experiments, A/B parity tests)
+  static const bool pair_on = !getenv("NW_DP_PAIR") || atoi(getenv("NW_DP_PAIR")) != 0;
+  auto cls_smem = [&](int cls, int L) {
+    return (cls & CLS_PAIR) ? score_pair_smem(cls & ~CLS_PAIR, c->ctx_max, L) : score_fast_smem(cls, c->ctx_max, L);
   };
   std::vector<Bucket> bk(bins.size());
   std::vector<uint32_t> cls_count;  // counting sort by kernel class: register windows ascending, generic (0) last
-  auto cls_key = [](int cls) { return cls ? (uint32_t)cls : 1025u; };
-  cls_count.assign(1027, 0);
+  auto cls_key = [](int cls) { return cls ? (uint32_t)cls : 0x2001u; };
+  cls_count.assign(0x2003, 0);
   for (size_t k = 0; k < bins.size(); ++k) {
     const int r = (int)(bins[k].bin / (uint32_t)lcap), L = (int)(bins[k].bin % (uint32_t)lcap);
     const BandTable& T = c->rbands[r]->get(L);
@@ -568,6 +574,8 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
     int cls = 0;
     if (!(flags & NW_FLAG_GENERIC_DP) && T.fast_ok) cls = score_fast_window(T.max_width);
     if (cls && score_fast_smem(cls, c->ctx_max, L) > 200 * 1024) cls = 0;  // tiles would not fit: generic kernel
+    // packed form (two candidates per thread, 16-bit halves): every total of the bucket must fit 15 bits
+    if (cls && pair_on && !(flags & NW_FLAG_DP32) && pair_range_ok(c->RH[r], L) && score_pair_smem(cls, c->ctx_max, L) <= 200 * 1024) cls |= CLS_PAIR;
     bk[k] = Bucket{r, L, cls, bins[k].n, bins[k].bin};
     if (cells_out) cells_out[r] += (int64_t)bins[k].n * T.cells;
   }
@@ -585,7 +593,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
       for (auto it = cta_of.begin(); it != cta_of.end(); ++it) {
         auto nx = std::next(it);
         if (nx == cta_of.end()) break;
-        if ((it->second + 127) / 128 < 4 * 148) {
+        if (((it->first ^ nx->first) & CLS_PAIR) == 0 && (it->second + 127) / 128 < 4 * 148) {
           into[it->first] = nx->first;
           nx->second += it->second;
         }
@@ -594,7 +602,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
       int cls = b.cls;
       while (cls && into.count(cls)) {
         const int up = into[cls];
-        if (score_fast_smem(up, c->ctx_max, b.L) > 200 * 1024) break;
+        if (cls_smem(up, b.L) > 200 * 1024) break;
         cls = up;
       }
       b.cls = cls;
@@ -627,8 +635,9 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
     if (new_class || (b.cls && b.rid != prev_rid)) pos = (pos + 127) & ~127u;  // CTA boundary
     if (new_class) ranges.push_back(Range{b.cls, pos, pos, 0});
     prev_rid = b.rid;
-    bins[idx].n = pos;  // the sub-counters of one length share one contiguous, 32-padded bucket (k_bucket_fill)
-    pos += (b.n + 31) & ~31u;
+    bins[idx].n = pos;  // the sub-counters of one length share one contiguous, warp-padded bucket (k_bucket_fill)
+    const uint32_t pad = (b.cls & CLS_PAIR) ? 63u : 31u;  // a warp of the packed kernel owns 64 slots of one length
+    pos += (b.n + pad) & ~pad;
     ranges.back().end = pos;
     ranges.back().lmax = std::max(ranges.back().lmax, b.L);
     if (R > 1) {
@@ -691,12 +700,14 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
       // one thread per candidate (measured on S150 / S64: profiles/README.md).  NW_DP_COOP=0 / 1 forces one form.
       static const int coop_mode = getenv("NW_DP_COOP") ? atoi(getenv("NW_DP_COOP")) : -1;
       static const int coop_max_ctas = getenv("NW_DP_COOP_MAX_CTAS") ? atoi(getenv("NW_DP_COOP_MAX_CTAS")) : 48;
-      const int cw = score_coop_window(r.cls);
+      const int win = r.cls & ~CLS_PAIR;
+      const int cw = score_coop_window(win);
       bool coop = cw && score_coop_smem(cw, c->ctx_max, r.lmax) <= 200 * 1024;
       if (coop && coop_mode == 0) coop = false;
       if (coop && coop_mode < 0) coop = (int)(A.n_work / 128) < coop_max_ctas;
-      const int l = coop ? launch_score_coop(cw, A, st) : launch_score_fast(r.cls, A, st);
-      if (l < 0) fail(NW_ERR_CUDA, "no register-DP kernel for window " + std::to_string(r.cls));
+      const int l = coop ? launch_score_coop(cw, A, st)
+                         : ((r.cls & CLS_PAIR) ? launch_score_pair(win, A, st) : launch_score_fast(win, A, st));
+      if (l < 0) fail(NW_ERR_CUDA, "no register-DP kernel for window " + std::to_string(win));
       c->launches += l;
     } else {
       const size_t sc = (size_t)2 * (c->ny_max + 2) * generic_threads() * 4;

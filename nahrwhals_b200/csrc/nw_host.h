@@ -52,6 +52,7 @@ struct RegionHost {
   int n_x = 0, n_y = 0, NYP = 0, PW = 0, PWS = 0, MW = 0;
   int64_t gcd = 1;
   int64_t sum_rt = 0, sum_up = 0;  // units
+  int64_t max_up = 0;              // longest x block in units
   std::vector<unsigned char> ctx;  // [planes | upx (per plane row: index x*2+strand) | rt_rev x 4 shifted copies]
   uint32_t off_upx = 0, off_rtrev = 0;
   int rt_copy_stride = 0;
@@ -82,7 +83,10 @@ inline RegionHost build_region(const int8_t* aln, int n_x, int n_y, const int64_
     g = std::gcd(g, len_y[y]);
   }
   R.gcd = g;
-  for (int x = 0; x < n_x; ++x) R.sum_up += len_x[x] / g;
+  for (int x = 0; x < n_x; ++x) {
+    R.sum_up += len_x[x] / g;
+    R.max_up = std::max<int64_t>(R.max_up, len_x[x] / g);
+  }
   for (int y = 0; y < n_y; ++y) R.sum_rt += len_y[y] / g;
   // a child can at most double per level (a duplication copies a segment): bound the int32 DP range
   const double worst = (double)R.sum_up * std::pow(2.0, std::max(0, maxdepth)) + (double)R.sum_rt;
@@ -122,6 +126,12 @@ inline RegionHost build_region(const int8_t* aln, int n_x, int n_y, const int64_
       rr[(size_t)c * R.rt_copy_stride + t] = (j >= 1 && j <= n_y) ? R.rt[j] : 0;
     }
   return R;
+}
+
+// Packed 16-bit DP (dp_row_step2 / k_score_pair): a child of Lc blocks has total <= sum_rt + Lc * max_up; when that
+// bound fits 15 bits no half-register of the packed row step can overflow (nw_device.h).
+inline bool pair_range_ok(const RegionHost& R, int Lc) {
+  return R.sum_rt + (int64_t)Lc * R.max_up <= (int64_t)PAIR_TOTAL_MAX;
 }
 
 // ---- fingerprint power tables: pw[e + FP_EMAX] = B_k^e mod p for four fixed (seeded) bases ----

@@ -1827,6 +1827,7 @@ double launch_int_peak(int mode, int* out, int iters, cudaStream_t st) {
 // per launch (a per-launch cudaFuncSetAttribute races between contexts running on different host threads).
 void init_score_fast_attrs();
 void init_score_coop_attrs();
+void init_score_pair_attrs();
 void init_kernel_attrs() {
   int dev = 0, optin = 0;
   cudaGetDevice(&dev);
@@ -1849,6 +1850,7 @@ void init_kernel_attrs() {
   cudaFuncSetAttribute(k_materialise, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   init_score_fast_attrs();
   init_score_coop_attrs();
+  init_score_pair_attrs();
 }
 
 int launch_moveset(const RegionDev* regions_dev, int n_regions, int nx_max, cudaStream_t st) {

@@ -210,6 +210,10 @@ int launch_score_fast(int W, const ScoreArgs& A, cudaStream_t st);
 bool score_fast_supports(int width);  // true if some compiled window >= width
 int score_fast_window(int width);     // smallest compiled window >= width (0 if none)
 size_t score_fast_smem(int W, uint32_t ctx_bytes, int lmax);  // dynamic shared memory of one CTA
+// packed form (nw_score_pair.cu): two candidates of one length per thread in the 16-bit halves of the DP registers;
+// CTA = 64 threads = 128 work slots, buckets padded to 64 slots; only for totals below PAIR_TOTAL_MAX units
+int launch_score_pair(int W, const ScoreArgs& A, cudaStream_t st);
+size_t score_pair_smem(int W, uint32_t ctx_bytes, int lmax);
 // warp-cooperative form (nw_score_coop.cu): four lanes per candidate, CTA = 32 work slots
 int launch_score_coop(int W, const ScoreArgs& A, cudaStream_t st);
 int score_coop_window(int width);  // smallest compiled cooperative window >= width (0 if none)

@@ -1,0 +1,224 @@
+// nw_score_pair.cu -- register-resident banded DP (slow_score, solver.jl:329-426), TWO candidates per thread.
+//
+// Same recurrence, window and band tables as k_score_fast (nw_score_fast.cu), but every register of the DP row holds
+// the savings of two candidates of one child length, one per 16-bit half, and the row step runs on the packed DPX
+// instruction (VIADDMNMX.S16x2): dp_row_step2, nw_device.h.  Per window cell PAIR the ALU pipe sees one LOP3 (the
+// match bit of either candidate folded into the addend) and two packed DPX instructions -- 1.5 per cell against 2 in
+// the one-candidate form -- and the per-row overhead (band row, window shift, rt window) is paid once for two
+// candidates.  The host routes a (region, length) bucket here only when every total fits 15 bits
+// (pair_range_ok, nw_host.h); everything else keeps the 32-bit kernel.
+//
+// CTA = 64 threads = 128 work slots (the same slot -> CTA -> region mapping as k_score_fast, so the work list and
+// cta_rid need no second layout); a warp owns 64 consecutive slots of ONE length (the host pads the buckets of a
+// packed launch to 64): lane l scores slots l and 32 + l.
+#include "nw_kernels.cuh"
+
+#ifndef NW_PAIR_MINB
+#define NW_PAIR_MINB 1
+#endif
+
+namespace nw {
+
+constexpr int PAIR_THREADS = 64;
+
+// Shared-memory layout per CTA:
+//   [ region context (TMA bulk copy; rt_rev packed in place) | child rows uint32 [Lmax][64] | band rows uint32 [2][Lmax+1][3+NWORD] ]
+template <int W>
+__global__ void __launch_bounds__(PAIR_THREADS, NW_PAIR_MINB) k_score_pair(ScoreArgs A) {
+  constexpr int NWORD = (W + 31) / 32;
+  constexpr int BROW = 3 + NWORD;
+  constexpr bool RTREG = (W <= 64);  // rt window in registers (LDS.128) vs one LDS per cell (wide windows: register budget)
+  constexpr int RTW = RTREG ? W : 4;
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const RegionDev& R = A.F.regions[A.cta_rid ? (int)A.cta_rid[blockIdx.x] : 0];
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, R.ctx_bytes);
+    tma_bulk_g2s(smem, R.ctx, R.ctx_bytes, &bar);
+  }
+  const uint32_t* planes = reinterpret_cast<const uint32_t*>(smem);
+  const int32_t* upx = reinterpret_cast<const int32_t*>(smem + R.off_upx);
+  uint32_t* rtrev = reinterpret_cast<uint32_t*>(smem + R.off_rtrev);
+  const int Lmax = A.lmax;
+  uint32_t* crow = reinterpret_cast<uint32_t*>(smem + A.ctx_max);
+  uint32_t* brow = reinterpret_cast<uint32_t*>(smem + A.ctx_max + (size_t)Lmax * PAIR_THREADS * 4) + (size_t)warp * (Lmax + 1) * BROW;
+
+  const uint32_t w0 = blockIdx.x * 128u + warp * 64u + lane;
+  uint32_t rA = w0 < A.n_work ? A.work[w0] : WORK_PAD;
+  uint32_t rB = w0 + 32u < A.n_work ? A.work[w0 + 32u] : WORK_PAD;
+  const uint32_t actA = __ballot_sync(0xffffffffu, rA != WORK_PAD);
+  // slots fill from the front of a 64-padded bucket: an idle first half means the whole 64-slot group is padding.
+  // The warps of a CTA do not meet again after this point (only __syncwarp below), so an idle warp may leave.
+  const bool warp_idle = actA == 0;
+  const bool mineA = rA != WORK_PAD, mineB = rB != WORK_PAD;
+  if (!warp_idle) {
+    const uint32_t rlead = __shfl_sync(0xffffffffu, rA, __ffs(actA) - 1);
+    if (!mineA) rA = rlead;  // idle halves shadow a real candidate of the same length (results are not written)
+    if (!mineB) rB = rA;
+  }
+  int Lc = 0;
+  if (!warp_idle) {
+    const uint64_t dA = A.desc[A.newlist[rA]], dB = A.desc[A.newlist[rB]];
+    const uint64_t dd[2] = {dA, dB};
+    Lc = child_len(A.F.len[desc_parent(dA)], desc_kind(dA), desc_i(dA), desc_j(dA));  // warp-uniform (buckets)
+    // ---- stage both child sequences (index map over the parent, branch-free): plane row = block * 2 + strand ----
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint64_t d = dd[h];
+      const uint32_t ps = desc_parent(d);
+      const int kind = desc_kind(d), p = desc_i(d), q = desc_j(d);
+      const int16_t* seq = reinterpret_cast<const int16_t*>(A.F.blob + (size_t)ps * A.F.pstride);
+      const int lo = kind == KIND_DEL ? p - 1 : (kind == KIND_DUP ? q : (kind == KIND_INV ? p : Lc));
+      const int hi = kind == KIND_INV ? q : 0x7fffffff;
+      const int shift = kind == KIND_DUP ? p - q : (kind == KIND_DEL ? q - p : 0);
+      uint16_t* cr = reinterpret_cast<uint16_t*>(crow) + tid * 2 + h;
+#pragma unroll 4
+      for (int t = 1; t <= Lc; ++t) {
+        int src = t > lo ? t + shift : t;
+        const bool flip = kind == KIND_INV && t > lo && t < hi;
+        src = flip ? p + q - t : src;
+        const int v = seq[src - 1];
+        const int a = v < 0 ? -v : v;
+        cr[(size_t)(t - 1) * (PAIR_THREADS * 2)] = (uint16_t)(a * 2 + ((v < 0) != flip ? 1 : 0));
+      }
+    }
+    // ---- stage the warp's band rows ----
+    const int boff = R.band_off[Lc];
+    const int16_t* eb_t = R.band_eb + boff;
+    const uint8_t* sb_t = R.band_sb + boff;
+    const uint32_t* mk_t = R.band_mask + (size_t)boff * 4;
+    const int NYP1 = R.NYP - 1;
+    const int rt_stride = R.rt_copy_stride;
+    for (int i = 1 + lane; i <= Lc; i += 32) {
+      const int r0 = NYP1 - (int)eb_t[i];
+      brow[i * BROW] = (uint32_t)r0;
+      brow[i * BROW + 1] = (uint32_t)(((r0 & 3) * rt_stride + (r0 & ~3)) * 4);
+      brow[i * BROW + 2] = (uint32_t)sb_t[i];
+#pragma unroll
+      for (int t = 0; t < NWORD; ++t) brow[i * BROW + 3 + t] = mk_t[(size_t)i * 4 + t];
+    }
+  }
+  const int PWS = R.PWS;
+  const int sum_rt = R.sum_rt;
+  const int n_rt = R.rt_copy_stride * 4;
+  mbar_wait(&bar, 0);
+  // rt of both halves: rt | rt << 16, in place over the four shifted copies (every rt < 2^15 on this path)
+  for (int t = tid; t < n_rt; t += PAIR_THREADS) rtrev[t] *= 0x10001u;
+  __syncthreads();
+  if (warp_idle) return;
+
+  uint32_t S[W];
+#pragma unroll
+  for (int k = 0; k < W; ++k) S[k] = 0;
+  uint32_t sumup2 = 0;
+  const uint32_t* cp = crow + tid;
+  const uint32_t* bw = brow + BROW;
+  const uint32_t* const cend = cp + (size_t)Lc * PAIR_THREADS;
+  for (; cp != cend; cp += PAIR_THREADS, bw += BROW) {
+    const uint32_t ci2 = *cp;
+    const uint32_t ciA = ci2 & 0xffffu, ciB = ci2 >> 16;
+    const uint32_t r0 = bw[0];
+    const uint32_t sbw = bw[2];
+    const uint32_t up2 = (uint32_t)upx[ciA] + ((uint32_t)upx[ciB] << 16);
+    sumup2 += up2;
+    const uint32_t* plA = planes + ciA * PWS + (r0 >> 5);
+    const uint32_t* plB = planes + ciB * PWS + (r0 >> 5);
+    uint32_t Mq[2 * NWORD];
+#pragma unroll
+    for (int t = 0; t < NWORD; ++t) {
+      const uint32_t mk = bw[3 + t];
+      const uint32_t mA = __funnelshift_r(plA[t], plA[t + 1], r0) & mk;  // shift = r0 mod 32
+      const uint32_t mB = __funnelshift_r(plB[t], plB[t + 1], r0) & mk;
+      Mq[2 * t] = __byte_perm(mA, mB, 0x5410);      // cells 32t .. 32t+15: A in the low half, B in the high half
+      Mq[2 * t + 1] = __byte_perm(mA, mB, 0x7632);  // cells 32t+16 .. 32t+31
+    }
+    const uint32_t* rtw = reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(rtrev) + bw[1]);
+    uint32_t rtr[RTW];
+    if (RTREG) {
+#pragma unroll
+      for (int g = 0; g < RTW / 4; ++g) {
+        const uint4 v = *reinterpret_cast<const uint4*>(rtw + 4 * g);
+        rtr[4 * g] = v.x;
+        rtr[4 * g + 1] = v.y;
+        rtr[4 * g + 2] = v.z;
+        rtr[4 * g + 3] = v.w;
+      }
+      if (sbw == 1) {
+        dp_row_step2<W, 1>(S, Mq, up2, rtr);
+      } else if (sbw == 0) {
+        dp_row_step2<W, 0>(S, Mq, up2, rtr);
+      } else {
+        for (int e = (int)sbw - 2; e > 0; --e) dp_row_shift1<W>(S);  // rare: first rows of steep corridors
+        dp_row_step2<W, 2>(S, Mq, up2, rtr);
+      }
+    } else {
+      if (sbw == 1) {
+        dp_row_step2<W, 1>(S, Mq, up2, rtw);
+      } else if (sbw == 0) {
+        dp_row_step2<W, 0>(S, Mq, up2, rtw);
+      } else {
+        for (int e = (int)sbw - 2; e > 0; --e) dp_row_shift1<W>(S);
+        dp_row_step2<W, 2>(S, Mq, up2, rtw);
+      }
+    }
+  }
+  const int totalA = (int)(sumup2 & 0xffffu) + sum_rt, totalB = (int)(sumup2 >> 16) + sum_rt;
+  const int costA = totalA - (int)(S[0] & 0xffffu), costB = totalB - (int)(S[0] >> 16);
+  const int kA = score_k3(costA, totalA), kB = score_k3(costB, totalB);
+  if (mineA) {
+    A.total[rA] = totalA;
+    A.cost[rA] = costA;
+    A.k3[rA] = kA;
+  }
+  if (mineB) {
+    A.total[rB] = totalB;
+    A.cost[rB] = costB;
+    A.k3[rB] = kB;
+  }
+  int b = max(kA, kB);  // warp max -> one atomic (shadow halves carry a duplicate of a real value)
+  for (int o = 16; o; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+  int* best_slot = A.best_k3 + (A.cta_rid ? (int)A.cta_rid[blockIdx.x] : 0);
+  if (lane == 0 && b > 0) atomicMax(best_slot, b);
+}
+
+size_t score_pair_smem(int W, uint32_t ctx_bytes, int lmax) {
+  const int nword = (W + 31) / 32;
+  return (size_t)ctx_bytes + (size_t)lmax * PAIR_THREADS * 4 + (size_t)2 * (lmax + 1) * (3 + nword) * 4;
+}
+
+template <int W>
+static int launch_w(const ScoreArgs& A, cudaStream_t st) {
+  const size_t sm = score_pair_smem(W, A.ctx_max, A.lmax);
+  k_score_pair<W><<<(A.n_work + 127) / 128, PAIR_THREADS, sm, st>>>(A);
+  return 1;
+}
+
+#define NW_PAIR_WINDOWS(X) X(8) X(12) X(16) X(20) X(24) X(28) X(32) X(36) X(40) X(44) X(48) X(52) X(56) X(60) X(64) X(72) X(80) X(96) X(112) X(128)
+
+void init_score_pair_attrs() {
+  int dev = 0, optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const int mx = optin - 2048;  // the limit covers static + dynamic shared memory of a block
+#define X(Wv) cudaFuncSetAttribute(k_score_pair<Wv>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  NW_PAIR_WINDOWS(X)
+#undef X
+}
+
+int launch_score_pair(int W, const ScoreArgs& A, cudaStream_t st) {
+  if (A.n_work == 0) return 0;
+  switch (W) {
+#define X(Wv) \
+  case Wv:    \
+    return launch_w<Wv>(A, st);
+    NW_PAIR_WINDOWS(X)
+#undef X
+    default:
+      return -1;
+  }
+}
+
+}  // namespace nw

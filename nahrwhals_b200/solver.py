@@ -94,7 +94,7 @@ class Solver:
 
     def _opts(self, maxdepth=3, maxdup=3, maxwidth=None, minreport=0.95, maxreport=None, keep_ids=False,
               generic_dp=False, no_traj=False, pair_expand=False, verify_dedup=True, debug_weak_fp=False,
-              debug_weak_fp_once=False, maxoffset=4):
+              debug_weak_fp_once=False, maxoffset=4, dp32=False):
         o = _lib.NwOpts()
         self.L.nw_default_opts(C.byref(o))
         o.maxdepth, o.maxdup = int(maxdepth), int(maxdup)
@@ -105,7 +105,7 @@ class Solver:
         o.flags = ((_lib.FLAG_GENERIC_DP if generic_dp else 0) | (_lib.FLAG_NO_TRAJ if no_traj else 0) |
                    (_lib.FLAG_PAIR_EXPAND if pair_expand else 0) | (0 if verify_dedup else _lib.FLAG_NO_VERIFY) |
                    (_lib.FLAG_DEBUG_WEAK_FP if debug_weak_fp else 0) |
-                   (_lib.FLAG_DEBUG_WEAK_FP_ONCE if debug_weak_fp_once else 0))
+                   (_lib.FLAG_DEBUG_WEAK_FP_ONCE if debug_weak_fp_once else 0) | (_lib.FLAG_DP32 if dp32 else 0))
         return o
 
     @staticmethod
@@ -170,7 +170,7 @@ class Solver:
                                          C.byref(o), C.byref(st)))
         return st
 
-    def score_batch(self, aln, len_x, len_y, seqs, force=False, generic_dp=False):
+    def score_batch(self, aln, len_x, len_y, seqs, force=False, generic_dp=False, dp32=False):
         """slow_score (solver.jl:329-376) for raw candidate indices.  Returns (score f64, cost_bp, total_bp);
         cost_bp == -1: early exit (score 0.0, no DP), -2: unreachable (score -inf).
         force: 0/False = slow_score; 1/True = the R twin's forcecalc branch (corridor 1.0, no early exit,
@@ -187,7 +187,8 @@ class Solver:
         total = np.zeros(n, np.int64)
         score = np.zeros(n, np.float64)
         _lib.check(self.L.nw_score_batch(self.h, _p(aln), aln.shape[0], aln.shape[1], _p(lx), _p(ly), _p(flat), _p(off),
-                                         n, int(force), _lib.FLAG_GENERIC_DP if generic_dp else 0, _p(cost),
+                                         n, int(force), (_lib.FLAG_GENERIC_DP if generic_dp else 0) | (_lib.FLAG_DP32 if dp32 else 0),
+                                         _p(cost),
                                          _p(total), _p(score)))
         return score, cost, total
 

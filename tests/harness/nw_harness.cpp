@@ -49,6 +49,57 @@ static int run_fast(const RegionHost& R, const BandTable& T, const int16_t* pare
   return S[0];
 }
 
+
+// packed form (two candidates of one child length per register, dp_row_step2): the code k_score_pair runs per row
+template <int W>
+static void run_pair(const RegionHost& R, const BandTable& T, const int16_t* parent, const int* kind, const int* p,
+                     const int* q, int Lc, int* s_out, int* sumup_out) {
+  constexpr int NWORD = (W + 31) / 32;
+  uint32_t S[W];
+  for (int k = 0; k < W; ++k) S[k] = 0;
+  uint32_t sumup2 = 0;
+  const uint32_t* planes = R.planes();
+  const int32_t* upx = R.upx();
+  const int32_t* rtrev = R.rtrev();
+  for (int i = 1; i <= Lc; ++i) {
+    uint32_t m[2][NWORD];
+    uint32_t up2 = 0;
+    const int r0 = R.NYP - 1 - T.eb[i];
+    for (int h = 0; h < 2; ++h) {
+      const int c = child_elem(parent, kind[h], p[h], q[h], i);
+      const int x = c < 0 ? -c : c;
+      up2 |= (uint32_t)upx[2 * x] << (16 * h);
+      const uint32_t* pl = planes + (size_t)(x * 2 + (c < 0 ? 1 : 0)) * R.PWS + (r0 >> 5);
+      const int sh = r0 & 31;
+      for (int t = 0; t < NWORD; ++t) {
+        const uint64_t two = (uint64_t)pl[t] | ((uint64_t)pl[t + 1] << 32);
+        m[h][t] = (uint32_t)(two >> sh) & T.mask[(size_t)i * 4 + t];
+      }
+    }
+    sumup2 += up2;
+    uint32_t Mq[2 * NWORD];
+    for (int t = 0; t < NWORD; ++t) {
+      Mq[2 * t] = (m[0][t] & 0xffffu) | (m[1][t] << 16);
+      Mq[2 * t + 1] = (m[0][t] >> 16) | (m[1][t] & 0xffff0000u);
+    }
+    const int* rtw = rtrev + (size_t)(r0 & 3) * R.rt_copy_stride + (r0 & ~3);
+    uint32_t rt2[W];
+    for (int k = 0; k < W; ++k) rt2[k] = (uint32_t)rtw[k] * 0x10001u;
+    int sb = T.sb[i];
+    while (sb > 2) {
+      dp_row_shift1<W>(S);
+      --sb;
+    }
+    if (sb == 0) dp_row_step2<W, 0>(S, Mq, up2, rt2);
+    else if (sb == 1) dp_row_step2<W, 1>(S, Mq, up2, rt2);
+    else dp_row_step2<W, 2>(S, Mq, up2, rt2);
+  }
+  for (int h = 0; h < 2; ++h) {
+    s_out[h] = (int)((S[0] >> (16 * h)) & 0xffffu);
+    sumup_out[h] = (int)((sumup2 >> (16 * h)) & 0xffffu);
+  }
+}
+
 extern "C" {
 
 // Scores child(parent, kind, p, q) with the register-DP code path.  Returns 1 if the fast path applies
@@ -95,6 +146,58 @@ int h_score_fast(const int8_t* aln, int n_x, int n_y, const int64_t* len_x, cons
   *cost_bp = (total - s) * R.gcd;
   *total_bp = total * R.gcd;
   *window = W;
+  return 1;
+}
+
+
+// Scores child(parent, move A) and child(parent, move B) -- two children of ONE length -- with the packed row step.
+// Returns 1 if the packed path applies (cost / total of both in bp written), 0 if it does not (geometry needs the
+// generic kernel, unequal lengths, or a total outside the 16-bit range), -1 on early exit.
+int h_score_pair(const int8_t* aln, int n_x, int n_y, const int64_t* len_x, const int64_t* len_y, const int16_t* parent,
+                 int L, const int* kind, const int* p, const int* q, int force, int64_t* cost_bp, int64_t* total_bp) {
+  RegionHost R = build_region(aln, n_x, n_y, len_x, len_y, 4);
+  const int Lc = child_len(L, kind[0], p[0], q[0]);
+  if (Lc != child_len(L, kind[1], p[1], q[1])) return 0;
+  if (!force && early_exit(Lc, n_y)) return -1;
+  BandTable T = build_band(Lc, n_y, force, WINDOW_MAX);
+  if (!T.fast_ok) return 0;
+  if (!pair_range_ok(R, Lc)) return 0;
+  static const int wins[] = {8, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64, 72, 80, 96, 112, 128};
+  int W = 0;
+  for (int w : wins)
+    if (w >= T.max_width) {
+      W = w;
+      break;
+    }
+  if (!W) return 0;
+  int s[2], sumup[2];
+  switch (W) {
+    case 8: run_pair<8>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 12: run_pair<12>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 16: run_pair<16>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 20: run_pair<20>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 24: run_pair<24>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 28: run_pair<28>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 32: run_pair<32>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 36: run_pair<36>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 40: run_pair<40>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 44: run_pair<44>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 48: run_pair<48>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 52: run_pair<52>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 56: run_pair<56>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 60: run_pair<60>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 64: run_pair<64>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 72: run_pair<72>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 80: run_pair<80>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 96: run_pair<96>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    case 112: run_pair<112>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+    default: run_pair<128>(R, T, parent, kind, p, q, Lc, s, sumup); break;
+  }
+  for (int h = 0; h < 2; ++h) {
+    const int64_t total = (int64_t)sumup[h] + R.sum_rt;
+    cost_bp[h] = (total - s[h]) * R.gcd;
+    total_bp[h] = total * R.gcd;
+  }
   return 1;
 }
 

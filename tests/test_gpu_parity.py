@@ -112,11 +112,38 @@ def test_score_batch_random(solver, oracle, shape):
     for force in (False, True):
         osc, ocost, ototal, _ = oracle.score_batch(aln, lx, ly, seqs, force=force)
         ocost_i = np.where(np.isnan(ocost), -1.0, np.where(np.isinf(ocost), -2.0, ocost)).astype(np.int64)
-        for generic in (False, True):
-            sc, cost, total = solver.score_batch(aln, lx, ly, seqs, force=force, generic_dp=generic)
-            assert np.array_equal(cost, ocost_i), (shape, force, generic)
+        # the three DP kernels: packed 16-bit register form (default when the totals fit 15 bits), 32-bit register form, generic
+        for generic, dp32 in ((False, False), (False, True), (True, False)):
+            sc, cost, total = solver.score_batch(aln, lx, ly, seqs, force=force, generic_dp=generic, dp32=dp32)
+            assert np.array_equal(cost, ocost_i), (shape, force, generic, dp32)
             assert np.array_equal(total, ototal.astype(np.int64))
             assert np.array_equal(sc, osc)  # Float64 scores incl. -inf, exact
+
+
+def test_score_batch_packed_range_boundary(solver, oracle):
+    """Packed 16-bit DP (k_score_pair) at the edge of its range: the same gridmatrix with block lengths scaled so that the
+    totals of the candidates straddle 2^15 units -- the short children run packed, the long ones on the 32-bit kernel,
+    in one call -- and with the largest scale that still fits.  Costs / totals / scores exact vs the oracle."""
+    rng = np.random.default_rng(77)
+    mat, lx, ly, _ = sdgrid(48, [6, 5, 4, 3], seed=9, chain_depth=2)
+    aln = to_solver_inputs(mat)
+    n_x = aln.shape[0]
+    seqs = _random_candidates(rng, n_x, 500)
+    base_lx, base_ly = lx // np.gcd.reduce(np.concatenate([lx, ly])), ly // np.gcd.reduce(np.concatenate([lx, ly]))
+    for target in (20000, 32767, 40000, 70000):
+        # scale so that sum(ly) + 48 * max(lx) ~ target units; +1 on one block keeps the gcd at 1
+        f = max(1, int(target / float(base_ly.sum() + n_x * base_lx.max())))
+        lx2, ly2 = base_lx * f, base_ly * f
+        lx2 = lx2.copy()
+        lx2[0] += 1
+        for force in (False, True):
+            osc, ocost, ototal, _ = oracle.score_batch(aln, lx2, ly2, seqs, force=force)
+            ocost_i = np.where(np.isnan(ocost), -1.0, np.where(np.isinf(ocost), -2.0, ocost)).astype(np.int64)
+            for dp32 in (False, True):
+                sc, cost, total = solver.score_batch(aln, lx2, ly2, seqs, force=force, dp32=dp32)
+                assert np.array_equal(cost, ocost_i), (target, force, dp32)
+                assert np.array_equal(total, ototal.astype(np.int64))
+                assert np.array_equal(sc, osc)
 
 
 CASES = [
@@ -149,6 +176,9 @@ def test_search_parity(solver, oracle, case):
     if case[0] in ("sd40_w50", "sd30_dup3_w7"):  # fallback expansion kernel must agree too
         G2 = solver.solve(aln, lx, ly, keep_ids=True, pair_expand=True, **kw)
         assert_search_equal(G2, O)
+    if case[0] in ("sd64_exh", "sd150_w1000", "sd30_dup3_w7"):  # the default ran the packed 16-bit DP: 32-bit form must agree
+        G3 = solver.solve(aln, lx, ly, keep_ids=True, dp32=True, **kw)
+        assert_search_equal(G3, O)
 
 
 def test_search_small_and_degenerate(solver, oracle):

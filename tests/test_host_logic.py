@@ -156,6 +156,77 @@ def test_register_dp_matches_oracle(H, oracle):
     assert nfast > 1000 and len(windows) >= 8
 
 
+def test_packed_register_dp_matches_oracle(H, oracle):
+    """dp_row_step2 (two candidates of one child length in the 16-bit halves of a register, the code k_score_pair runs
+    per row) vs the oracle's Float64 DP, bit-exact cost/total for both halves; totals close to the 15-bit limit
+    included, and shapes beyond it rejected by pair_range_ok."""
+    rng = np.random.default_rng(11)
+    npair = 0
+    nreject = 0
+    windows = set()
+    for trial in range(260):
+        n_x = int(rng.integers(3, 90))
+        n_y = int(rng.integers(1, 90))
+        if trial % 3 == 0:
+            m, lx, ly = random_grid(n_x, n_y, 0.08, trial)
+        else:
+            fams = [int(rng.integers(2, 6)) for _ in range(int(rng.integers(1, 5)))]
+            if sum(fams) > n_x:
+                continue
+            m, lx, ly, _ = sdgrid(n_x, fams, seed=trial, chain_depth=int(rng.integers(0, 4)))
+        if trial % 5 == 4:  # scale the units so that totals approach (and sometimes exceed) the 15-bit range
+            f = int(rng.integers(2, 30))
+            lx, ly = lx * f, ly * f
+            lx[0] += 1000 * int(lx[0] // 1000 == lx[0] / 1000)  # keep the gcd small
+        aln = to_solver_inputs(m)
+        n_x = aln.shape[0]
+        par = list(range(1, n_x + 1))
+        for _ in range(int(rng.integers(0, 3))):
+            L = len(par)
+            if L < 3:
+                break
+            a = int(rng.integers(1, L))
+            b = int(rng.integers(a + 1, L + 1))
+            k = int(rng.integers(0, 3))
+            if k == 0 and L + (b - a) > 3 * n_x:
+                continue
+            par = _child(H, par, k, a, b)
+        L = len(par)
+        if L < 4:
+            continue
+        parr = np.ascontiguousarray(par, np.int16)
+        for _ in range(8):
+            # two moves with the same child length: same kind and same q - p for dup / del, anything for inv / id
+            k = int(rng.integers(0, 4))
+            if k in (0, 1):
+                d = int(rng.integers(1, L))
+                pa = int(rng.integers(1, L - d + 1))
+                pb = int(rng.integers(1, L - d + 1))
+                moves = [(k, pa, pa + d), (k, pb, pb + d)]
+            else:
+                moves = []
+                for _ in range(2):
+                    a = int(rng.integers(1, L))
+                    moves.append((int(rng.choice([2, 3])), a, int(rng.integers(a + 1, L + 1))))
+            seqs = [_child(H, par, *mv) for mv in moves]
+            kind = np.array([mv[0] for mv in moves], np.int32)
+            pp = np.array([mv[1] for mv in moves], np.int32)
+            qq = np.array([mv[2] for mv in moves], np.int32)
+            for force in (0, 1):
+                cost = np.zeros(2, np.int64)
+                tot = np.zeros(2, np.int64)
+                rc = H.h_score_pair(_p(aln), aln.shape[0], aln.shape[1], _p(lx), _p(ly), _p(parr), L, _p(kind), _p(pp),
+                                    _p(qq), force, _p(cost), _p(tot))
+                if rc != 1:
+                    nreject += rc == 0
+                    continue
+                _, co, to, _ = oracle.score_batch(aln, lx, ly, seqs, force=bool(force))
+                npair += 1
+                assert cost.tolist() == [int(v) for v in co], (trial, moves, force)
+                assert tot.tolist() == [int(v) for v in to]
+    assert npair > 1500 and nreject > 0
+
+
 def test_score_string_all_values(H, oracle):
     """The product's TSV score formatter vs a generic shortest-round-trip Float32 printer, all 100001 values."""
     buf = C.create_string_buffer(64)

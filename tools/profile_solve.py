@@ -14,6 +14,8 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 aln, lx, ly, flags, desc = make_workload(name, 1)
 if os.environ.get("NW_PROFILE_NO_VERIFY"):   # fingerprint-only dedup: what the element-wise verifier costs
     flags = dict(flags, verify_dedup=False)
+if os.environ.get("NW_PROFILE_DP32"):        # 32-bit register DP everywhere: what the packed 16-bit form buys
+    flags = dict(flags, dp32=True)
 s = nb.Solver(0)
 for r in range(reps):
     t0 = time.perf_counter()
