@@ -20,13 +20,43 @@
 namespace nw {
 
 constexpr int PAIR_THREADS = 64;
+constexpr int PAIR_BROW = 8;  // uint32 per staged band row: {r0, plane word offset, rt byte offset, sb, mask[0..3]} = two LDS.128
 
-// Shared-memory layout per CTA:
-//   [ region context (TMA bulk copy; rt_rev packed in place) | child rows uint32 [Lmax][64] | band rows uint32 [2][Lmax+1][3+NWORD] ]
+// one candidate's index map over its parent (apply_* of solver.jl:244-278, never materialised)
+struct PairMap {
+  const int16_t* seq;
+  int lo, hi, shift, pq;
+  // child[t] = sgn(t) * seq[src(t)]:  dup: t<=q ? t : t-q+p ; del: t<p ? t : t+q-p ; inv: p<t<q ? p+q-t (negated) : t
+  __device__ __forceinline__ void init(const ScoreArgs& A, uint64_t d, int Lc) {
+    const uint32_t ps = desc_parent(d);
+    const int kind = desc_kind(d), p = desc_i(d), q = desc_j(d);
+    seq = reinterpret_cast<const int16_t*>(A.F.blob + (size_t)ps * A.F.pstride);
+    lo = kind == KIND_DEL ? p - 1 : (kind == KIND_DUP ? q : (kind == KIND_INV ? p : Lc));
+    hi = kind == KIND_INV ? q : 0;  // inversion window is (lo, hi); empty for the other kinds
+    shift = kind == KIND_DUP ? p - q : (kind == KIND_DEL ? q - p : 0);
+    pq = p + q;
+  }
+  // signed element t (1-based) of the child
+  __device__ __forceinline__ int elem(int t) const {
+    const bool seg2 = t > lo;
+    int src = seg2 ? t + shift : t;
+    const bool flip = seg2 && t < hi;
+    src = flip ? pq - t : src;
+    const int v = seq[src - 1];
+    return flip ? -v : v;
+  }
+};
+// plane row of a signed block id: block * 2 + strand (addresses both the match bit-plane and the up cost)
+__device__ __forceinline__ uint32_t plane_row(int c) { return (uint32_t)(c < 0 ? -c : c) * 2u + ((uint32_t)c >> 31); }
+
+// Shared-memory layout per CTA:  [ region context (TMA bulk copy; rt_rev packed in place) | band rows uint32 [2][Lmax+2][8] ]
+// The child sequences are NOT staged: a row's two block ids are read through the index maps two rows ahead (one LDG
+// each, L1-resident parents) and its match words / up costs one row ahead, so the only dependent chain of a row is
+// the DPX chain itself and a CTA needs no per-candidate tile (S150: 84 KB -> 33 KB of shared memory per CTA).
 template <int W>
 __global__ void __launch_bounds__(PAIR_THREADS, NW_PAIR_MINB) k_score_pair(ScoreArgs A) {
   constexpr int NWORD = (W + 31) / 32;
-  constexpr int BROW = 3 + NWORD;
+  constexpr int BROW = PAIR_BROW;
   constexpr bool RTREG = (W <= 64);  // rt window in registers (LDS.128) vs one LDS per cell (wide windows: register budget)
   constexpr int RTW = RTREG ? W : 4;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -43,62 +73,41 @@ __global__ void __launch_bounds__(PAIR_THREADS, NW_PAIR_MINB) k_score_pair(Score
   const int32_t* upx = reinterpret_cast<const int32_t*>(smem + R.off_upx);
   uint32_t* rtrev = reinterpret_cast<uint32_t*>(smem + R.off_rtrev);
   const int Lmax = A.lmax;
-  uint32_t* crow = reinterpret_cast<uint32_t*>(smem + A.ctx_max);
-  uint32_t* brow = reinterpret_cast<uint32_t*>(smem + A.ctx_max + (size_t)Lmax * PAIR_THREADS * 4) + (size_t)warp * (Lmax + 1) * BROW;
+  uint32_t* brow = reinterpret_cast<uint32_t*>(smem + A.ctx_max) + (size_t)warp * (Lmax + 2) * BROW;
 
   const uint32_t w0 = blockIdx.x * 128u + warp * 64u + lane;
   uint32_t rA = w0 < A.n_work ? A.work[w0] : WORK_PAD;
   uint32_t rB = w0 + 32u < A.n_work ? A.work[w0 + 32u] : WORK_PAD;
   const uint32_t actA = __ballot_sync(0xffffffffu, rA != WORK_PAD);
-  // slots fill from the front of a 64-padded bucket: an idle first half means the whole 64-slot group is padding.
-  // The warps of a CTA do not meet again after this point (only __syncwarp below), so an idle warp may leave.
+  // slots fill from the front of a 64-padded bucket: an idle first half means the whole 64-slot group is padding
   const bool warp_idle = actA == 0;
   const bool mineA = rA != WORK_PAD, mineB = rB != WORK_PAD;
+  int Lc = 0;
+  PairMap mapA, mapB;
   if (!warp_idle) {
     const uint32_t rlead = __shfl_sync(0xffffffffu, rA, __ffs(actA) - 1);
     if (!mineA) rA = rlead;  // idle halves shadow a real candidate of the same length (results are not written)
     if (!mineB) rB = rA;
-  }
-  int Lc = 0;
-  if (!warp_idle) {
     const uint64_t dA = A.desc[A.newlist[rA]], dB = A.desc[A.newlist[rB]];
-    const uint64_t dd[2] = {dA, dB};
     Lc = child_len(A.F.len[desc_parent(dA)], desc_kind(dA), desc_i(dA), desc_j(dA));  // warp-uniform (buckets)
-    // ---- stage both child sequences (index map over the parent, branch-free): plane row = block * 2 + strand ----
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const uint64_t d = dd[h];
-      const uint32_t ps = desc_parent(d);
-      const int kind = desc_kind(d), p = desc_i(d), q = desc_j(d);
-      const int16_t* seq = reinterpret_cast<const int16_t*>(A.F.blob + (size_t)ps * A.F.pstride);
-      const int lo = kind == KIND_DEL ? p - 1 : (kind == KIND_DUP ? q : (kind == KIND_INV ? p : Lc));
-      const int hi = kind == KIND_INV ? q : 0x7fffffff;
-      const int shift = kind == KIND_DUP ? p - q : (kind == KIND_DEL ? q - p : 0);
-      uint16_t* cr = reinterpret_cast<uint16_t*>(crow) + tid * 2 + h;
-#pragma unroll 4
-      for (int t = 1; t <= Lc; ++t) {
-        int src = t > lo ? t + shift : t;
-        const bool flip = kind == KIND_INV && t > lo && t < hi;
-        src = flip ? p + q - t : src;
-        const int v = seq[src - 1];
-        const int a = v < 0 ? -v : v;
-        cr[(size_t)(t - 1) * (PAIR_THREADS * 2)] = (uint16_t)(a * 2 + ((v < 0) != flip ? 1 : 0));
-      }
-    }
-    // ---- stage the warp's band rows ----
+    mapA.init(A, dA, Lc);
+    mapB.init(A, dB, Lc);
+    // ---- stage the warp's band rows (row Lc + 1 = zeros: the look-ahead of the last row reads it) ----
     const int boff = R.band_off[Lc];
     const int16_t* eb_t = R.band_eb + boff;
     const uint8_t* sb_t = R.band_sb + boff;
-    const uint32_t* mk_t = R.band_mask + (size_t)boff * 4;
+    const uint4* mk_t = reinterpret_cast<const uint4*>(R.band_mask + (size_t)boff * 4);
     const int NYP1 = R.NYP - 1;
     const int rt_stride = R.rt_copy_stride;
-    for (int i = 1 + lane; i <= Lc; i += 32) {
-      const int r0 = NYP1 - (int)eb_t[i];
-      brow[i * BROW] = (uint32_t)r0;
-      brow[i * BROW + 1] = (uint32_t)(((r0 & 3) * rt_stride + (r0 & ~3)) * 4);
-      brow[i * BROW + 2] = (uint32_t)sb_t[i];
-#pragma unroll
-      for (int t = 0; t < NWORD; ++t) brow[i * BROW + 3 + t] = mk_t[(size_t)i * 4 + t];
+    for (int i = 1 + lane; i <= Lc + 1; i += 32) {
+      uint4 g = make_uint4(0u, 0u, 0u, 0u), mk = g;
+      if (i <= Lc) {
+        const int r0 = NYP1 - (int)eb_t[i];
+        g = make_uint4((uint32_t)r0, (uint32_t)(r0 >> 5), (uint32_t)(((r0 & 3) * rt_stride + (r0 & ~3)) * 4), (uint32_t)sb_t[i]);
+        mk = mk_t[i];
+      }
+      *reinterpret_cast<uint4*>(brow + i * BROW) = g;
+      *reinterpret_cast<uint4*>(brow + i * BROW + 4) = mk;
     }
   }
   const int PWS = R.PWS;
@@ -110,32 +119,40 @@ __global__ void __launch_bounds__(PAIR_THREADS, NW_PAIR_MINB) k_score_pair(Score
   __syncthreads();
   if (warp_idle) return;
 
+  // match words (both candidates interleaved by 16-cell groups) and packed up cost of one row
+  auto row_inputs = [&](const uint32_t* bw, int cA, int cB, uint32_t (&Mq)[2 * NWORD], uint32_t& up2) {
+    const uint4 g = *reinterpret_cast<const uint4*>(bw);
+    const uint4 mk4 = *reinterpret_cast<const uint4*>(bw + 4);
+    const uint32_t mk[4] = {mk4.x, mk4.y, mk4.z, mk4.w};
+    const uint32_t ciA = plane_row(cA), ciB = plane_row(cB);
+    up2 = (uint32_t)upx[ciA] + ((uint32_t)upx[ciB] << 16);
+    const uint32_t* plA = planes + ciA * PWS + g.y;
+    const uint32_t* plB = planes + ciB * PWS + g.y;
+#pragma unroll
+    for (int t = 0; t < NWORD; ++t) {
+      const uint32_t mA = __funnelshift_r(plA[t], plA[t + 1], g.x) & mk[t];  // shift = r0 mod 32
+      const uint32_t mB = __funnelshift_r(plB[t], plB[t + 1], g.x) & mk[t];
+      Mq[2 * t] = __byte_perm(mA, mB, 0x5410);      // cells 32t .. 32t+15: A in the low half, B in the high half
+      Mq[2 * t + 1] = __byte_perm(mA, mB, 0x7632);  // cells 32t+16 .. 32t+31
+    }
+    return make_uint2(g.z, g.w);  // rt byte offset, sb
+  };
+
   uint32_t S[W];
 #pragma unroll
   for (int k = 0; k < W; ++k) S[k] = 0;
   uint32_t sumup2 = 0;
-  const uint32_t* cp = crow + tid;
-  const uint32_t* bw = brow + BROW;
-  const uint32_t* const cend = cp + (size_t)Lc * PAIR_THREADS;
-  for (; cp != cend; cp += PAIR_THREADS, bw += BROW) {
-    const uint32_t ci2 = *cp;
-    const uint32_t ciA = ci2 & 0xffffu, ciB = ci2 >> 16;
-    const uint32_t r0 = bw[0];
-    const uint32_t sbw = bw[2];
-    const uint32_t up2 = (uint32_t)upx[ciA] + ((uint32_t)upx[ciB] << 16);
-    sumup2 += up2;
-    const uint32_t* plA = planes + ciA * PWS + (r0 >> 5);
-    const uint32_t* plB = planes + ciB * PWS + (r0 >> 5);
-    uint32_t Mq[2 * NWORD];
-#pragma unroll
-    for (int t = 0; t < NWORD; ++t) {
-      const uint32_t mk = bw[3 + t];
-      const uint32_t mA = __funnelshift_r(plA[t], plA[t + 1], r0) & mk;  // shift = r0 mod 32
-      const uint32_t mB = __funnelshift_r(plB[t], plB[t + 1], r0) & mk;
-      Mq[2 * t] = __byte_perm(mA, mB, 0x5410);      // cells 32t .. 32t+15: A in the low half, B in the high half
-      Mq[2 * t + 1] = __byte_perm(mA, mB, 0x7632);  // cells 32t+16 .. 32t+31
-    }
-    const uint32_t* rtw = reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(rtrev) + bw[1]);
+  const uint32_t* bw = brow + BROW;  // band row of the current DP row
+  // software pipeline: elements two rows ahead, match words / up one row ahead
+  int cA1 = mapA.elem(1), cB1 = mapB.elem(1);
+  int cA2 = mapA.elem(min(2, Lc)), cB2 = mapB.elem(min(2, Lc));
+  uint32_t Mq[2 * NWORD], up2;
+  uint2 geo = row_inputs(bw, cA1, cB1, Mq, up2);
+  for (int t = 1; t <= Lc; ++t, bw += BROW) {
+    const int tn = min(t + 2, Lc);
+    const int cA3 = mapA.elem(tn), cB3 = mapB.elem(tn);  // LDG, consumed in the next iteration
+    const uint32_t* rtw = reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(rtrev) + geo.x);
+    const uint32_t sbw = geo.y;
     uint32_t rtr[RTW];
     if (RTREG) {
 #pragma unroll
@@ -146,6 +163,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, NW_PAIR_MINB) k_score_pair(Score
         rtr[4 * g + 2] = v.z;
         rtr[4 * g + 3] = v.w;
       }
+    }
+    uint32_t Mq_n[2 * NWORD], up2_n;
+    const uint2 geo_n = row_inputs(bw + BROW, cA2, cB2, Mq_n, up2_n);  // row t + 1 (row Lc + 1: zeros, unused)
+    sumup2 += up2;
+    if (RTREG) {
       if (sbw == 1) {
         dp_row_step2<W, 1>(S, Mq, up2, rtr);
       } else if (sbw == 0) {
@@ -164,6 +186,12 @@ __global__ void __launch_bounds__(PAIR_THREADS, NW_PAIR_MINB) k_score_pair(Score
         dp_row_step2<W, 2>(S, Mq, up2, rtw);
       }
     }
+#pragma unroll
+    for (int k = 0; k < 2 * NWORD; ++k) Mq[k] = Mq_n[k];
+    up2 = up2_n;
+    geo = geo_n;
+    cA2 = cA3;
+    cB2 = cB3;
   }
   const int totalA = (int)(sumup2 & 0xffffu) + sum_rt, totalB = (int)(sumup2 >> 16) + sum_rt;
   const int costA = totalA - (int)(S[0] & 0xffffu), costB = totalB - (int)(S[0] >> 16);
@@ -185,8 +213,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, NW_PAIR_MINB) k_score_pair(Score
 }
 
 size_t score_pair_smem(int W, uint32_t ctx_bytes, int lmax) {
-  const int nword = (W + 31) / 32;
-  return (size_t)ctx_bytes + (size_t)lmax * PAIR_THREADS * 4 + (size_t)2 * (lmax + 1) * (3 + nword) * 4;
+  (void)W;
+  return (size_t)ctx_bytes + (size_t)2 * (lmax + 2) * PAIR_BROW * 4;
 }
 
 template <int W>
