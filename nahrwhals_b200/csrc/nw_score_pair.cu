@@ -36,18 +36,22 @@ struct PairMap {
     shift = kind == KIND_DUP ? p - q : (kind == KIND_DEL ? q - p : 0);
     pq = p + q;
   }
-  // signed element t (1-based) of the child
-  __device__ __forceinline__ int elem(int t) const {
+  // element t (1-based) of the child as (parent element, negate?): the sign flip of an inverted segment is applied by
+  // the consumer one row later, so nothing waits for the load in the iteration that issues it
+  __device__ __forceinline__ void elem(int t, int& v, uint32_t& neg) const {
     const bool seg2 = t > lo;
     int src = seg2 ? t + shift : t;
     const bool flip = seg2 && t < hi;
     src = flip ? pq - t : src;
-    const int v = seq[src - 1];
-    return flip ? -v : v;
+    neg = flip ? 1u : 0u;
+    v = seq[src - 1];
   }
 };
-// plane row of a signed block id: block * 2 + strand (addresses both the match bit-plane and the up cost)
-__device__ __forceinline__ uint32_t plane_row(int c) { return (uint32_t)(c < 0 ? -c : c) * 2u + ((uint32_t)c >> 31); }
+// plane row of a block id: block * 2 + strand (addresses both the match bit-plane and the up cost)
+__device__ __forceinline__ uint32_t plane_row(int v, uint32_t neg) {
+  const uint32_t a = (uint32_t)(v < 0 ? -v : v);
+  return __funnelshift_l((uint32_t)v, a, 1) ^ neg;  // |v| * 2 + sign bit, strand flipped inside an inversion
+}
 
 // Shared-memory layout per CTA:  [ region context (TMA bulk copy; rt_rev packed in place) | band rows uint32 [2][Lmax+2][8] ]
 // The child sequences are NOT staged: a row's two block ids are read through the index maps two rows ahead (one LDG
@@ -119,23 +123,39 @@ __global__ void __launch_bounds__(PAIR_THREADS, NW_PAIR_MINB) k_score_pair(Score
   __syncthreads();
   if (warp_idle) return;
 
-  // match words (both candidates interleaved by 16-cell groups) and packed up cost of one row
-  auto row_inputs = [&](const uint32_t* bw, int cA, int cB, uint32_t (&Mq)[2 * NWORD], uint32_t& up2) {
-    const uint4 g = *reinterpret_cast<const uint4*>(bw);
-    const uint4 mk4 = *reinterpret_cast<const uint4*>(bw + 4);
-    const uint32_t mk[4] = {mk4.x, mk4.y, mk4.z, mk4.w};
-    const uint32_t ciA = plane_row(cA), ciB = plane_row(cB);
-    up2 = (uint32_t)upx[ciA] + ((uint32_t)upx[ciB] << 16);
-    const uint32_t* plA = planes + ciA * PWS + g.y;
-    const uint32_t* plB = planes + ciB * PWS + g.y;
+  // Row inputs in two halves so that the loads of row t + 1 are in flight during the DP step of row t:
+  // issue = band row (two LDS.128), plane words and up costs of both candidates; finish = match words of both
+  // candidates interleaved by 16-cell groups, packed up cost, (rt byte offset, sb) of the row.
+  struct RowLoads {
+    uint4 g, mk4;
+    uint32_t pa[NWORD + 1], pb[NWORD + 1];
+    uint32_t ua, ub;
+  };
+  auto issue = [&](const uint32_t* bw, int vA, uint32_t nA, int vB, uint32_t nB, RowLoads& L) {
+    L.g = *reinterpret_cast<const uint4*>(bw);
+    L.mk4 = *reinterpret_cast<const uint4*>(bw + 4);
+    const uint32_t ciA = plane_row(vA, nA), ciB = plane_row(vB, nB);
+    L.ua = (uint32_t)upx[ciA];
+    L.ub = (uint32_t)upx[ciB];
+    const uint32_t* plA = planes + ciA * PWS + L.g.y;
+    const uint32_t* plB = planes + ciB * PWS + L.g.y;
+#pragma unroll
+    for (int t = 0; t <= NWORD; ++t) {
+      L.pa[t] = plA[t];
+      L.pb[t] = plB[t];
+    }
+  };
+  auto finish = [&](const RowLoads& L, uint32_t (&Mq)[2 * NWORD], uint32_t& up2) {
+    const uint32_t mk[4] = {L.mk4.x, L.mk4.y, L.mk4.z, L.mk4.w};
+    up2 = L.ua + (L.ub << 16);
 #pragma unroll
     for (int t = 0; t < NWORD; ++t) {
-      const uint32_t mA = __funnelshift_r(plA[t], plA[t + 1], g.x) & mk[t];  // shift = r0 mod 32
-      const uint32_t mB = __funnelshift_r(plB[t], plB[t + 1], g.x) & mk[t];
+      const uint32_t mA = __funnelshift_r(L.pa[t], L.pa[t + 1], L.g.x) & mk[t];  // shift = r0 mod 32
+      const uint32_t mB = __funnelshift_r(L.pb[t], L.pb[t + 1], L.g.x) & mk[t];
       Mq[2 * t] = __byte_perm(mA, mB, 0x5410);      // cells 32t .. 32t+15: A in the low half, B in the high half
       Mq[2 * t + 1] = __byte_perm(mA, mB, 0x7632);  // cells 32t+16 .. 32t+31
     }
-    return make_uint2(g.z, g.w);  // rt byte offset, sb
+    return make_uint2(L.g.z, L.g.w);  // rt byte offset, sb
   };
 
   uint32_t S[W];
@@ -143,14 +163,21 @@ __global__ void __launch_bounds__(PAIR_THREADS, NW_PAIR_MINB) k_score_pair(Score
   for (int k = 0; k < W; ++k) S[k] = 0;
   uint32_t sumup2 = 0;
   const uint32_t* bw = brow + BROW;  // band row of the current DP row
-  // software pipeline: elements two rows ahead, match words / up one row ahead
-  int cA1 = mapA.elem(1), cB1 = mapB.elem(1);
-  int cA2 = mapA.elem(min(2, Lc)), cB2 = mapB.elem(min(2, Lc));
+  // software pipeline: elements two rows ahead (LDG), plane words / up / band row one row ahead (LDS)
+  int vA, vB, vA2, vB2;
+  uint32_t nA, nB, nA2, nB2;
+  mapA.elem(1, vA, nA);
+  mapB.elem(1, vB, nB);
+  mapA.elem(min(2, Lc), vA2, nA2);
+  mapB.elem(min(2, Lc), vB2, nB2);
   uint32_t Mq[2 * NWORD], up2;
-  uint2 geo = row_inputs(bw, cA1, cB1, Mq, up2);
+  uint2 geo;
+  {
+    RowLoads L0;
+    issue(bw, vA, nA, vB, nB, L0);
+    geo = finish(L0, Mq, up2);
+  }
   for (int t = 1; t <= Lc; ++t, bw += BROW) {
-    const int tn = min(t + 2, Lc);
-    const int cA3 = mapA.elem(tn), cB3 = mapB.elem(tn);  // LDG, consumed in the next iteration
     const uint32_t* rtw = reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(rtrev) + geo.x);
     const uint32_t sbw = geo.y;
     uint32_t rtr[RTW];
@@ -164,8 +191,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, NW_PAIR_MINB) k_score_pair(Score
         rtr[4 * g + 3] = v.w;
       }
     }
-    uint32_t Mq_n[2 * NWORD], up2_n;
-    const uint2 geo_n = row_inputs(bw + BROW, cA2, cB2, Mq_n, up2_n);  // row t + 1 (row Lc + 1: zeros, unused)
+    const int tn = min(t + 2, Lc);
+    int vA3, vB3;
+    uint32_t nA3, nB3;
+    mapA.elem(tn, vA3, nA3);  // LDG, consumed in the next iteration
+    mapB.elem(tn, vB3, nB3);
+    RowLoads Ln;
+    issue(bw + BROW, vA2, nA2, vB2, nB2, Ln);  // row t + 1 (row Lc + 1: zeros, unused)
     sumup2 += up2;
     if (RTREG) {
       if (sbw == 1) {
@@ -186,12 +218,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, NW_PAIR_MINB) k_score_pair(Score
         dp_row_step2<W, 2>(S, Mq, up2, rtw);
       }
     }
-#pragma unroll
-    for (int k = 0; k < 2 * NWORD; ++k) Mq[k] = Mq_n[k];
-    up2 = up2_n;
-    geo = geo_n;
-    cA2 = cA3;
-    cB2 = cB3;
+    geo = finish(Ln, Mq, up2);
+    vA2 = vA3;
+    vB2 = vB3;
+    nA2 = nA3;
+    nB2 = nB3;
   }
   const int totalA = (int)(sumup2 & 0xffffu) + sum_rt, totalB = (int)(sumup2 >> 16) + sum_rt;
   const int costA = totalA - (int)(S[0] & 0xffffu), costB = totalB - (int)(S[0] >> 16);
