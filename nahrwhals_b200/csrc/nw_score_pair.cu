@@ -13,13 +13,11 @@
 // packed launch to 64): lane l scores slots l and 32 + l.
 #include "nw_kernels.cuh"
 
-#ifndef NW_PAIR_MINB
-#define NW_PAIR_MINB 1
-#endif
-
 namespace nw {
 
 constexpr int PAIR_THREADS = 64;
+// CTAs per SM the register allocation has to leave room for (64 threads each): 128 registers up to W = 28, 168 up to 40
+constexpr int pair_min_ctas(int W) { return W <= 28 ? 8 : (W <= 40 ? 6 : 4); }
 constexpr int PAIR_BROW = 8;  // uint32 per staged band row: {r0, plane word offset, rt byte offset, sb, mask[0..3]} = two LDS.128
 
 // one candidate's index map over its parent (apply_* of solver.jl:244-278, never materialised)
@@ -58,7 +56,7 @@ __device__ __forceinline__ uint32_t plane_row(int v, uint32_t neg) {
 // each, L1-resident parents) and its match words / up costs one row ahead, so the only dependent chain of a row is
 // the DPX chain itself and a CTA needs no per-candidate tile (S150: 84 KB -> 33 KB of shared memory per CTA).
 template <int W>
-__global__ void __launch_bounds__(PAIR_THREADS, NW_PAIR_MINB) k_score_pair(ScoreArgs A) {
+__global__ void __launch_bounds__(PAIR_THREADS, pair_min_ctas(W)) k_score_pair(ScoreArgs A) {
   constexpr int NWORD = (W + 31) / 32;
   constexpr int BROW = PAIR_BROW;
   constexpr bool RTREG = (W <= 64);  // rt window in registers (LDS.128) vs one LDS per cell (wide windows: register budget)
