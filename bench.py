@@ -1092,7 +1092,7 @@ def main():
     value = scored_all / (dev_ms * 1e-3)
     e2e_value = scored_all / e2e_t
 
-    # ---- roofline of the dominant kernel (banded DP, k_score_fast<W>): integer ALU bound ----
+    # ---- roofline of the dominant kernel (banded DP, k_score_pair<W> / k_score_fast<W>): integer ALU bound ----
     # algorithmic int-ops = 5 per band cell (3 adds + 2 mins); duration = CUDA events around every DP launch
     intops = 5.0 * cells
     ach = intops / (score_ms * 1e-3) / 1e12 if score_ms > 0 else 0.0
@@ -1119,12 +1119,18 @@ def main():
                             (tj["dram_bytes_per_launch"], tj["source"], per_search, tj["algorithmic_bytes_per_launch"]))
     except Exception:
         pass
-    roofline = dict(bound="int_alu", kernel="k_score_fast<W> (banded DP)", achieved=ach, peak=peak, unit="Tintop/s",
+    roofline = dict(bound="int_alu",
+                    kernel="k_score_pair<W> (banded DP, two candidates per thread on packed 16-bit DPX; k_score_fast<W> "
+                           "when a total exceeds 15 bits, k_score_coop<W> for launches under 48 CTAs)",
+                    achieved=ach, peak=peak, unit="Tintop/s",
                     frac=(ach / peak if peak else None), traffic=traffic, traffic_note=traffic_note,
                     launches=score_launches, avg_launch_ms=(score_ms / score_launches if score_launches else None),
                     peak_basis="measured on this GPU (nw_bench_peaks): VIADDMNMX %.2f, IADD3 %.2f, VIADDMNMX+IMAD %.2f "
                                "T thread-instr/s" % (peaks["viaddmnmx_ips"] / 1e12, peaks["iadd3_ips"] / 1e12,
                                                      peaks["mixed_ips"] / 1e12),
+                    peak_note="the denominator is the 32-bit figure round 1 was measured against (2 int-ops per VIADDMNMX "
+                              "thread-instruction); VIADDMNMX.S16x2 issues at the same rate (tools/ubench/dpx_rates: 18.45 T/s) "
+                              "and carries two 16-bit lanes, i.e. 2 x this peak for a kernel made of packed instructions only",
                     hbm=dict(bound="hbm", achieved=hbm_ach, peak=hbm_peak, unit="GB/s",
                              frac=hbm_ach / hbm_peak if hbm_peak else None, peak_source=hbm_src,
                              copy_measured_gbs=peaks["copy_Bps"] / 1e9))

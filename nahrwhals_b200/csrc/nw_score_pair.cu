@@ -43,6 +43,7 @@ struct PairMap {
     src = flip ? pq - t : src;
     neg = flip ? 1u : 0u;
     v = seq[src - 1];
+    asm("" : "+r"(v));  // sign-extend in the load (LDG.S16), not in a PRMT at the consumer one iteration later
   }
 };
 // plane row of a block id: block * 2 + strand (addresses both the match bit-plane and the up cost)
