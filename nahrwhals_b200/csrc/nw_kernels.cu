@@ -292,13 +292,24 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
     atomicOr(&occ[((size_t)(v < 0 ? 1 : 0) * (n_x + 1) + b) * LWT + (t >> 5)], 1u << (t & 31));
   }
   __syncthreads();
-  // ---- pass 1: candidate count of every row ----
+  // ---- pass 1: candidate count of every row (the masks of a thread's first row stay in registers for pass 2) ----
   int maxlen = 0;
+  uint32_t ddm0[LWT], ivm0[LWT];
+  uint32_t cnt0 = 0;
   for (int i = tid + 1; i <= L; i += blockDim.x) {
     uint32_t ddm[LWT], ivm[LWT];
     int top;
-    rowcnt[i - 1] = row_masks<LWT>(R, n_x, seq, occ, i, dupok, ddm, ivm, top);
+    const uint32_t cnt = row_masks<LWT>(R, n_x, seq, occ, i, dupok, ddm, ivm, top);
+    rowcnt[i - 1] = cnt;
     if (dupok && top >= 0) maxlen = max(maxlen, L + (top + 1 - i));
+    if (EMIT && i == tid + 1) {
+      cnt0 = cnt;
+#pragma unroll
+      for (int x = 0; x < LWT; ++x) {
+        ddm0[x] = ddm[x];
+        ivm0[x] = ivm[x];
+      }
+    }
   }
   if (!EMIT && maxlen > 0) atomicMax(&s_maxlen, maxlen);
   __syncthreads();
@@ -330,8 +341,17 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
   const uint32_t base = A.off[parent];
   for (int i = tid + 1; i <= L; i += blockDim.x) {
     uint32_t ddm[LWT], ivm[LWT];
-    int top;
-    if (row_masks<LWT>(R, n_x, seq, occ, i, dupok, ddm, ivm, top) == 0) continue;
+    if (i == tid + 1) {
+      if (cnt0 == 0) continue;
+#pragma unroll
+      for (int x = 0; x < LWT; ++x) {
+        ddm[x] = ddm0[x];
+        ivm[x] = ivm0[x];
+      }
+    } else {  // indices longer than the CTA: the further rows of a thread are recomputed
+      int top;
+      if (row_masks<LWT>(R, n_x, seq, occ, i, dupok, ddm, ivm, top) == 0) continue;
+    }
     uint32_t pos = base + rowcnt[i - 1];
 #pragma unroll
     for (int x = 0; x < LWT; ++x) {

@@ -17,7 +17,13 @@ namespace nw {
 
 constexpr int PAIR_THREADS = 64;
 // CTAs per SM the register allocation has to leave room for (64 threads each): 128 registers up to W = 28, 168 up to 40
-constexpr int pair_min_ctas(int W) { return W <= 28 ? 8 : (W <= 40 ? 6 : 4); }
+#ifndef NW_PAIR_RTREG_MAX
+#define NW_PAIR_RTREG_MAX 64  // widest window whose packed rt values are held in registers (LDS.128) instead of read per cell
+#endif
+#ifndef NW_PAIR_MINB_WIDE
+#define NW_PAIR_MINB_WIDE 4
+#endif
+constexpr int pair_min_ctas(int W) { return W <= 28 ? 8 : (W <= 40 ? 6 : (W <= 64 ? NW_PAIR_MINB_WIDE : 4)); }
 constexpr int PAIR_BROW = 8;  // uint32 per staged band row: {r0, plane word offset, rt byte offset, sb, mask[0..3]} = two LDS.128
 
 // one candidate's index map over its parent (apply_* of solver.jl:244-278, never materialised)
@@ -43,7 +49,6 @@ struct PairMap {
     src = flip ? pq - t : src;
     neg = flip ? 1u : 0u;
     v = seq[src - 1];
-    asm("" : "+r"(v));  // sign-extend in the load (LDG.S16), not in a PRMT at the consumer one iteration later
   }
 };
 // plane row of a block id: block * 2 + strand (addresses both the match bit-plane and the up cost)
@@ -60,7 +65,7 @@ template <int W>
 __global__ void __launch_bounds__(PAIR_THREADS, pair_min_ctas(W)) k_score_pair(ScoreArgs A) {
   constexpr int NWORD = (W + 31) / 32;
   constexpr int BROW = PAIR_BROW;
-  constexpr bool RTREG = (W <= 64);  // rt window in registers (LDS.128) vs one LDS per cell (wide windows: register budget)
+  constexpr bool RTREG = (W <= NW_PAIR_RTREG_MAX);  // rt window in registers (LDS.128) vs one LDS per cell (wide windows: register budget)
   constexpr int RTW = RTREG ? W : 4;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
