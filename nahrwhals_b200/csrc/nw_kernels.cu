@@ -208,27 +208,30 @@ __host__ __device__ inline size_t expand_rows_smem(int LS, int n_x, int LW) {
   return (((size_t)LS * 2 + 15) & ~(size_t)15) + (size_t)2 * (n_x + 1) * LW * 4 + (size_t)LS * 4;
 }
 
-template <int LWT>
-__device__ __forceinline__ uint32_t row_masks(const RegionDev& R, int nx_max, const int16_t* seq, const uint32_t* occ, int i,
+// LWT = mask words of the launch (longest parent of the level), LWA <= LWT = mask words of THIS parent's size class:
+// the loops over mask words and the occupancy layout `occ[(strand * (n_x + 1) + block) * LWA + word]` follow the parent
+// (a 20-block region searched together with 120-block ones pays for 1 word per block, not 16); words >= LWA stay 0.
+template <int LWT, int LWA>
+__device__ __forceinline__ uint32_t row_masks(const RegionDev& R, int n_x, const int16_t* seq, const uint32_t* occ, int i,
                                               int dupok, uint32_t (&ddm)[LWT], uint32_t (&ivm)[LWT], int& top) {
-  const int n_x = nx_max, MW = R.MW;
+  const int MW = R.MW;
   const int a = seq[i - 1];
   const int aa = a < 0 ? -a : a, sa = a < 0 ? 1 : 0;
 #pragma unroll
   for (int x = 0; x < LWT; ++x) ddm[x] = ivm[x] = 0;
   top = -1;
   if (!__ldg(&R.ms_any[aa])) return 0;
-  const uint32_t* same = occ + (size_t)sa * (n_x + 1) * LWT;
-  const uint32_t* oppo = occ + (size_t)(1 - sa) * (n_x + 1) * LWT;
+  const uint32_t* same = occ + (size_t)sa * (n_x + 1) * LWA;
+  const uint32_t* oppo = occ + (size_t)(1 - sa) * (n_x + 1) * LWA;
   for (int w = 0; w < MW; ++w) {
     uint32_t bits = __ldg(&R.ms_dd[(size_t)aa * MW + w]);  // dup_del table true (solver.jl:184)
     while (bits) {
       const int b = w * 32 + __ffs(bits) - 1;
       bits &= bits - 1;
 #pragma unroll
-      for (int x = 0; x < LWT; ++x) {
-        ddm[x] |= same[(size_t)b * LWT + x];  // not flipped: dup/del
-        ivm[x] |= oppo[(size_t)b * LWT + x];  // flipped:     inversion   (:187-188)
+      for (int x = 0; x < LWA; ++x) {
+        ddm[x] |= same[(size_t)b * LWA + x];  // not flipped: dup/del
+        ivm[x] |= oppo[(size_t)b * LWA + x];  // flipped:     inversion   (:187-188)
       }
     }
     bits = __ldg(&R.ms_inv[(size_t)aa * MW + w]);  // invert table true (:185)
@@ -236,15 +239,15 @@ __device__ __forceinline__ uint32_t row_masks(const RegionDev& R, int nx_max, co
       const int b = w * 32 + __ffs(bits) - 1;
       bits &= bits - 1;
 #pragma unroll
-      for (int x = 0; x < LWT; ++x) {
-        ivm[x] |= same[(size_t)b * LWT + x];
-        ddm[x] |= oppo[(size_t)b * LWT + x];
+      for (int x = 0; x < LWA; ++x) {
+        ivm[x] |= same[(size_t)b * LWA + x];
+        ddm[x] |= oppo[(size_t)b * LWA + x];
       }
     }
   }
   uint32_t n = 0;
 #pragma unroll
-  for (int x = 0; x < LWT; ++x) {  // keep positions j > i only: bit index t = j-1 >= i
+  for (int x = 0; x < LWA; ++x) {  // keep positions j > i only: bit index t = j-1 >= i
     const int lo = x * 32;
     uint32_t keep = 0xffffffffu;
     if (lo + 32 <= i) keep = 0;
@@ -257,61 +260,47 @@ __device__ __forceinline__ uint32_t row_masks(const RegionDev& R, int nx_max, co
   return n;
 }
 
-template <bool EMIT, int LWT>
-__global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint32_t s_tot;
-  __shared__ int s_maxlen;
-  const int parent = blockIdx.x;
+// One parent, mask words of its own size class (LWA <= LWT): see row_masks.
+template <bool EMIT, int LWT, int LWA>
+__device__ __forceinline__ void expand_parent(const ExpandArgs& A, unsigned char* smem, uint64_t* bar, uint32_t* s_tot,
+                                              int* s_maxlen, int parent, int L) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int L = A.F.len[parent];
   const int LS = A.F.LS;
   const int dupok = A.F.dupok[parent];
   const RegionDev& R = A.F.regions[region_index(A.F, parent)];
-  const int n_x = A.nx_max;  // layout of the occurrence masks (>= this region's n_x)
+  const int n_x = R.n_x;  // layout of the occurrence masks: this region's blocks, this parent's mask words
   int16_t* seq = reinterpret_cast<int16_t*>(smem);
   uint32_t* occ = reinterpret_cast<uint32_t*>(smem + (((size_t)LS * 2 + 15) & ~(size_t)15));
-  uint32_t* rowcnt = occ + (size_t)2 * (n_x + 1) * LWT;
-  const uint32_t blob_bytes = (uint32_t)LS * 2;
-  if (tid == 0) {
-    mbar_init(&bar, 1);
-    s_maxlen = 0;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&bar, blob_bytes);
-    tma_bulk_g2s(smem, A.F.blob + (size_t)parent * A.F.pstride, blob_bytes, &bar);
-  }
-  for (int t = tid; t < 2 * (n_x + 1) * LWT; t += blockDim.x) occ[t] = 0;
-  mbar_wait(&bar, 0);
+  uint32_t* rowcnt = occ + (size_t)2 * (A.nx_max + 1) * LWT;  // fixed by the launch (expand_rows_smem)
+  for (int t = tid; t < 2 * (n_x + 1) * LWA; t += blockDim.x) occ[t] = 0;
+  mbar_wait(bar, 0);
   __syncthreads();
   for (int t = tid; t < L; t += blockDim.x) {
     const int v = seq[t];
     const int b = v < 0 ? -v : v;
-    atomicOr(&occ[((size_t)(v < 0 ? 1 : 0) * (n_x + 1) + b) * LWT + (t >> 5)], 1u << (t & 31));
+    atomicOr(&occ[((size_t)(v < 0 ? 1 : 0) * (n_x + 1) + b) * LWA + (t >> 5)], 1u << (t & 31));
   }
   __syncthreads();
   // ---- pass 1: candidate count of every row (the masks of a thread's first row stay in registers for pass 2) ----
   int maxlen = 0;
-  uint32_t ddm0[LWT], ivm0[LWT];
+  uint32_t ddm0[LWA], ivm0[LWA];
   uint32_t cnt0 = 0;
   for (int i = tid + 1; i <= L; i += blockDim.x) {
     uint32_t ddm[LWT], ivm[LWT];
     int top;
-    const uint32_t cnt = row_masks<LWT>(R, n_x, seq, occ, i, dupok, ddm, ivm, top);
+    const uint32_t cnt = row_masks<LWT, LWA>(R, n_x, seq, occ, i, dupok, ddm, ivm, top);
     rowcnt[i - 1] = cnt;
     if (dupok && top >= 0) maxlen = max(maxlen, L + (top + 1 - i));
     if (EMIT && i == tid + 1) {
       cnt0 = cnt;
 #pragma unroll
-      for (int x = 0; x < LWT; ++x) {
+      for (int x = 0; x < LWA; ++x) {
         ddm0[x] = ddm[x];
         ivm0[x] = ivm[x];
       }
     }
   }
-  if (!EMIT && maxlen > 0) atomicMax(&s_maxlen, maxlen);
+  if (!EMIT && maxlen > 0) atomicMax(s_maxlen, maxlen);
   __syncthreads();
   // ---- exclusive scan of rowcnt over rows (warp 0) ----
   if (warp == 0) {
@@ -327,13 +316,13 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
       if (r < L) rowcnt[r] = carry + inc - v;
       carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) s_tot = carry;
+    if (lane == 0) *s_tot = carry;
   }
   __syncthreads();
   if (!EMIT) {
     if (tid == 0) {
-      A.cnt[parent] = s_tot;
-      if (s_maxlen > 0) atomicMax(A.maxlen, s_maxlen);
+      A.cnt[parent] = *s_tot;
+      if (*s_maxlen > 0) atomicMax(A.maxlen, *s_maxlen);
     }
     return;
   }
@@ -344,17 +333,17 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
     if (i == tid + 1) {
       if (cnt0 == 0) continue;
 #pragma unroll
-      for (int x = 0; x < LWT; ++x) {
+      for (int x = 0; x < LWA; ++x) {
         ddm[x] = ddm0[x];
         ivm[x] = ivm0[x];
       }
     } else {  // indices longer than the CTA: the further rows of a thread are recomputed
       int top;
-      if (row_masks<LWT>(R, n_x, seq, occ, i, dupok, ddm, ivm, top) == 0) continue;
+      if (row_masks<LWT, LWA>(R, n_x, seq, occ, i, dupok, ddm, ivm, top) == 0) continue;
     }
     uint32_t pos = base + rowcnt[i - 1];
 #pragma unroll
-    for (int x = 0; x < LWT; ++x) {
+    for (int x = 0; x < LWA; ++x) {
       const uint32_t dd = ddm[x], iv = ivm[x];
       uint32_t any = dd | iv;
       while (any) {
@@ -369,6 +358,35 @@ __global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
       }
     }
   }
+}
+
+template <bool EMIT, int LWT>
+__global__ void __launch_bounds__(128) k_expand(ExpandArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_tot;
+  __shared__ int s_maxlen;
+  const int parent = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int L = A.F.len[parent];
+  const uint32_t blob_bytes = (uint32_t)A.F.LS * 2;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    s_maxlen = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, blob_bytes);
+    tma_bulk_g2s(smem, A.F.blob + (size_t)parent * A.F.pstride, blob_bytes, &bar);
+  }
+  // size class of this parent (CTA-uniform): regions of very different sizes share one launch in regionfile mode
+  const int lw = (L + 31) >> 5;
+  if (LWT > 1 && lw <= 1) expand_parent<EMIT, LWT, 1>(A, smem, &bar, &s_tot, &s_maxlen, parent, L);
+  else if (LWT > 2 && lw <= 2) expand_parent<EMIT, LWT, (LWT > 2 ? 2 : LWT)>(A, smem, &bar, &s_tot, &s_maxlen, parent, L);
+  else if (LWT > 4 && lw <= 4) expand_parent<EMIT, LWT, (LWT > 4 ? 4 : LWT)>(A, smem, &bar, &s_tot, &s_maxlen, parent, L);
+  else if (LWT > 8 && lw <= 8) expand_parent<EMIT, LWT, (LWT > 8 ? 8 : LWT)>(A, smem, &bar, &s_tot, &s_maxlen, parent, L);
+  else if (LWT > 16 && lw <= 16) expand_parent<EMIT, LWT, (LWT > 16 ? 16 : LWT)>(A, smem, &bar, &s_tot, &s_maxlen, parent, L);
+  else expand_parent<EMIT, LWT, LWT>(A, smem, &bar, &s_tot, &s_maxlen, parent, L);
 }
 
 template <int LWT>
