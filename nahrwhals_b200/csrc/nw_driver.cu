@@ -580,11 +580,13 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
     if (cells_out) cells_out[r] += (int64_t)bins[k].n * T.cells;
   }
   {
-    // A register-window class that would not fill the device on its own is folded into the next wider class that is
+    // A register-window class that would not fill the device on its own (under 1536 CTAs: a wave of the packed kernel is
+    // 148 x 8 CTAs; NW_CLASS_MERGE_CTAS) is folded into the next wider class that is
     // present: a wider window only carries idle columns (masks and band rows are per length, the region context is
     // padded for WINDOW_MAX), while a launch of its own costs the whole single-thread latency of a DP (~70-100 us at 150
     // blocks) again.  S150: windows 60 and 64 become one launch per level.
     static const bool no_merge = getenv("NW_NO_CLASS_MERGE") != nullptr;
+    static const int merge_ctas = getenv("NW_CLASS_MERGE_CTAS") ? atoi(getenv("NW_CLASS_MERGE_CTAS")) : 1536;
     std::map<int, uint64_t> cta_of;  // fast classes present -> work slots
     for (const Bucket& b : bk)
       if (b.cls) cta_of[b.cls] += (b.n + 31) & ~31u;
@@ -593,7 +595,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
       for (auto it = cta_of.begin(); it != cta_of.end(); ++it) {
         auto nx = std::next(it);
         if (nx == cta_of.end()) break;
-        if (((it->first ^ nx->first) & CLS_PAIR) == 0 && (it->second + 127) / 128 < 4 * 148) {
+        if (((it->first ^ nx->first) & CLS_PAIR) == 0 && (it->second + 127) / 128 < (uint64_t)merge_ctas) {
           into[it->first] = nx->first;
           nx->second += it->second;
         }
