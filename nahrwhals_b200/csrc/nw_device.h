@@ -223,12 +223,19 @@ NW_HD void dp_row_shift1(T (&S)[W]) {
 constexpr int PAIR_TOTAL_MAX = 32767;
 constexpr uint32_t PAIR_NEG = 0x80008000u;  // (-32768, -32768)
 
+#if !defined(__CUDACC__)
+inline long pair_wraps = 0;  // host restatement only: 16-bit additions that wrapped (the range argument says: none, ever)
+#endif
 NW_HD uint32_t viaddmax2(uint32_t a, uint32_t b, uint32_t c) {
 #if defined(__CUDA_ARCH__)
   return __viaddmax_s16x2(a, b, c);
 #else
   uint32_t out = 0;
   for (int h = 0; h < 2; ++h) {
+#if !defined(__CUDACC__)
+    const int wide = (int)(int16_t)(uint16_t)((a >> (16 * h)) & 0xffffu) + (int)(int16_t)(uint16_t)((b >> (16 * h)) & 0xffffu);
+    if (wide < -32768 || wide > 32767) ++pair_wraps;
+#endif
     const int16_t x = (int16_t)(uint16_t)(((a >> (16 * h)) + (b >> (16 * h))) & 0xffffu);  // wrapping 16-bit add
     const int16_t y = (int16_t)(uint16_t)((c >> (16 * h)) & 0xffffu);
     out |= (uint32_t)(uint16_t)(x > y ? x : y) << (16 * h);

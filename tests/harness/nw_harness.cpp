@@ -201,6 +201,9 @@ int h_score_pair(const int8_t* aln, int n_x, int n_y, const int64_t* len_x, cons
   return 1;
 }
 
+// 16-bit additions of the packed row step that wrapped since the library was loaded (must stay 0: pair_range_ok)
+long h_pair_wraps() { return pair_wraps; }
+
 // k3 (score*1000) from integer cost/total, the product's scoring arithmetic
 int h_score_k3(int64_t cost, int64_t total) { return score_k3(cost, total); }
 

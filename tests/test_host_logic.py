@@ -225,6 +225,45 @@ def test_packed_register_dp_matches_oracle(H, oracle):
                 assert cost.tolist() == [int(v) for v in co], (trial, moves, force)
                 assert tot.tolist() == [int(v) for v in to]
     assert npair > 1500 and nreject > 0
+    # totals right below the 15-bit limit: block lengths in bp with gcd 1, scaled so that sum_rt + L * max_up lands in
+    # (31 000, 32 767] for the children scored
+    nedge = 0
+    for trial in range(40):
+        n_x = int(rng.integers(12, 40))
+        m, lx, ly = random_grid(n_x, n_x, 0.12, 500 + trial, len_choices=tuple(int(v) for v in rng.integers(1, 60, 6)) + (1,))
+        lx, ly = lx // 1000, ly // 1000  # random_grid hands out multiples of 1000: back to small integers
+        aln = to_solver_inputs(m)
+        par = list(range(1, aln.shape[0] + 1))
+        L = len(par)
+        f = 32767 // (int(ly.sum()) + L * int(lx.max()))
+        if f < 1:
+            continue
+        lx2, ly2 = lx * f, ly * f
+        lx2[0] += 1 if (int(ly2.sum()) + L * int(max(lx2.max(), lx2[0] + 1)) <= 32767) else 0
+        parr = np.ascontiguousarray(par, np.int16)
+        for _ in range(6):
+            moves = []
+            for _ in range(2):
+                a = int(rng.integers(1, L))
+                moves.append((2, a, int(rng.integers(a + 1, L + 1))))
+            seqs = [_child(H, par, *mv) for mv in moves]
+            kind = np.array([mv[0] for mv in moves], np.int32)
+            pp = np.array([mv[1] for mv in moves], np.int32)
+            qq = np.array([mv[2] for mv in moves], np.int32)
+            cost = np.zeros(2, np.int64)
+            tot = np.zeros(2, np.int64)
+            rc = H.h_score_pair(_p(aln), aln.shape[0], aln.shape[1], _p(lx2), _p(ly2), _p(parr), L, _p(kind), _p(pp), _p(qq),
+                                1, _p(cost), _p(tot))
+            if rc != 1:
+                continue
+            _, co, to, _ = oracle.score_batch(aln, lx2, ly2, seqs, force=True)
+            assert cost.tolist() == [int(v) for v in co] and tot.tolist() == [int(v) for v in to]
+            g = int(np.gcd.reduce(np.concatenate([lx2, ly2])))
+            nedge += int(max(to)) // g > 20000
+    assert nedge > 20
+    # the range argument behind pair_range_ok: no 16-bit addition of the packed step ever wrapped, masked cells included
+    H.h_pair_wraps.restype = C.c_long
+    assert H.h_pair_wraps() == 0
 
 
 def test_score_string_all_values(H, oracle):
