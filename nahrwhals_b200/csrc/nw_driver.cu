@@ -580,13 +580,15 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
     if (cells_out) cells_out[r] += (int64_t)bins[k].n * T.cells;
   }
   {
-    // A register-window class that would not fill the device on its own (under 1536 CTAs: a wave of the packed kernel is
-    // 148 x 8 CTAs; NW_CLASS_MERGE_CTAS) is folded into the next wider class that is
-    // present: a wider window only carries idle columns (masks and band rows are per length, the region context is
-    // padded for WINDOW_MAX), while a launch of its own costs the whole single-thread latency of a DP (~70-100 us at 150
-    // blocks) again.  S150: windows 60 and 64 become one launch per level.
+    // A register-window class is folded into the next wider class that is present when walking the wider window costs
+    // less than a launch of its own: a wider window only carries idle columns (masks and band rows are per length, the
+    // region context is padded for WINDOW_MAX), i.e. n CTAs pay (B - A) / A more each, while a separate launch ends in a
+    // partly filled wave and costs at least the latency of ONE thread's DP (~70-100 us at 150 blocks).  Rule: fold iff
+    // n * (B - A) / A < half a wave (a wave ~ 148 x 6 CTAs).  S150: windows 60 and 64 become one launch per level;
+    // regionfile passes: 22 -> ~13 launches; the full-corridor pre-pass of the region stage keeps its narrow classes out
+    // of the 112 / 128 windows.  NW_CLASS_MERGE_CTAS overrides the wave size, NW_NO_CLASS_MERGE disables.
     static const bool no_merge = getenv("NW_NO_CLASS_MERGE") != nullptr;
-    static const int merge_ctas = getenv("NW_CLASS_MERGE_CTAS") ? atoi(getenv("NW_CLASS_MERGE_CTAS")) : 1536;
+    static const int merge_ctas = getenv("NW_CLASS_MERGE_CTAS") ? atoi(getenv("NW_CLASS_MERGE_CTAS")) : 148 * 6;
     std::map<int, uint64_t> cta_of;  // fast classes present -> work slots
     for (const Bucket& b : bk)
       if (b.cls) cta_of[b.cls] += (b.n + 31) & ~31u;
@@ -595,7 +597,8 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
       for (auto it = cta_of.begin(); it != cta_of.end(); ++it) {
         auto nx = std::next(it);
         if (nx == cta_of.end()) break;
-        if (((it->first ^ nx->first) & CLS_PAIR) == 0 && (it->second + 127) / 128 < (uint64_t)merge_ctas) {
+        const uint64_t wa = (uint64_t)(it->first & ~CLS_PAIR), wb = (uint64_t)(nx->first & ~CLS_PAIR);
+        if (((it->first ^ nx->first) & CLS_PAIR) == 0 && ((it->second + 127) / 128) * (wb - wa) * 2 < (uint64_t)merge_ctas * wa) {
           into[it->first] = nx->first;
           nx->second += it->second;
         }
