@@ -7,8 +7,9 @@ import os
 import sys
 import time
 
-import torch
-import torch.distributed as dist
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout = the JSON line only
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nahrwhals_b200 as nb  # noqa: E402
