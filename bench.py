@@ -27,6 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # stdout carries exactly ONE line (the JSON): whatever NCCL has to say under NCCL_DEBUG (its version banner included)
 # goes to stderr, for torch's communicator and for the one libnwsolve opens itself
+# (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, and prints the banner to stdout when NCCL_DEBUG is unset)
+os.environ.setdefault("NCCL_DEBUG", "WARN")
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "mutation_candidates_scored_per_s"

@@ -7,7 +7,8 @@ import os
 import sys
 import time
 
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout = the JSON line only
+os.environ.setdefault("NCCL_DEBUG", "WARN")  # with the file below: NCCL's banner goes to stderr, stdout = the JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
