@@ -1,3 +1,4 @@
+# A/B of prebuilt library variants on ONE box: VARS="A B" WLS="s64 s150d3" bash tools/ab_variants.sh  (build/variants/lib_<X>.so are swapped in for libnwsolve.so)
 cp nahrwhals_b200/csrc/libnwsolve.so /tmp/orig.so
 for v in $VARS; do
   cp build/variants/lib_$v.so nahrwhals_b200/csrc/libnwsolve.so
