@@ -1673,27 +1673,31 @@ __device__ __forceinline__ void move_params(int L, int kind, int p, int q, uint3
   sh = kind == KIND_DUP ? p - q : (kind == KIND_DEL ? q - p : 0);
   lo_hi = (uint32_t)lo | ((uint32_t)hi << 16);
 }
+// element t of a child as its low 16 bits (upper bits undefined): equality of two int16 values is equality of their low
+// 16 bits, so neither the load nor the inversion's negation needs a sign extension
 template <bool INV>
-__device__ __forceinline__ int ver_elem(const int16_t* seq, int lo, int hi, int sh, int t) {
+__device__ __forceinline__ uint32_t ver_elem(const uint16_t* seq, int lo, int hi, int sh, int t) {
   if (INV) {
     const bool flip = t > lo && t < hi;
-    const int v = seq[(unsigned)(flip ? lo + hi - t - 1 : t - 1)];
-    return flip ? -v : v;
+    const uint32_t v = seq[(unsigned)(flip ? lo + hi - t - 1 : t - 1)];
+    return flip ? 0u - v : v;
   }
   return seq[(unsigned)(t - 1 + (t > lo ? sh : 0))];
 }
 template <bool INVA, bool INVB>
-__device__ __forceinline__ bool ver_compare(const int16_t* sa, int loA, int hiA, int shA, const int16_t* sb, int loB, int hiB,
+__device__ __forceinline__ bool ver_compare(const int16_t* sa_, int loA, int hiA, int shA, const int16_t* sb_, int loB, int hiB,
                                             int shB, int n, int gl) {
-  bool diff = false;
+  const uint16_t* sa = reinterpret_cast<const uint16_t*>(sa_);
+  const uint16_t* sb = reinterpret_cast<const uint16_t*>(sb_);
+  uint32_t acc = 0;
   int t = 1 + gl;
   for (; t + 8 <= n; t += 16) {  // two elements per lane and step: four loads in flight
-    const int a0 = ver_elem<INVA>(sa, loA, hiA, shA, t), b0 = ver_elem<INVB>(sb, loB, hiB, shB, t);
-    const int a1 = ver_elem<INVA>(sa, loA, hiA, shA, t + 8), b1 = ver_elem<INVB>(sb, loB, hiB, shB, t + 8);
-    diff |= (a0 != b0) | (a1 != b1);
+    const uint32_t a0 = ver_elem<INVA>(sa, loA, hiA, shA, t), b0 = ver_elem<INVB>(sb, loB, hiB, shB, t);
+    const uint32_t a1 = ver_elem<INVA>(sa, loA, hiA, shA, t + 8), b1 = ver_elem<INVB>(sb, loB, hiB, shB, t + 8);
+    acc |= (a0 ^ b0) | (a1 ^ b1);
   }
-  if (t <= n) diff |= ver_elem<INVA>(sa, loA, hiA, shA, t) != ver_elem<INVB>(sb, loB, hiB, shB, t);
-  return diff;
+  if (t <= n) acc |= ver_elem<INVA>(sa, loA, hiA, shA, t) ^ ver_elem<INVB>(sb, loB, hiB, shB, t);
+  return (acc & 0xffffu) != 0;
 }
 // Element-wise dedup verifier.  A CTA takes 1024 consecutive candidates.  Phase 1 (4 candidates per thread): every merged
 // candidate reads its own move and -- one random read -- its owner's, and leaves a 32-byte item in shared memory, filed
