@@ -16,13 +16,14 @@
 namespace nw {
 
 constexpr int PAIR_THREADS = 64;
-// CTAs per SM the register allocation has to leave room for (64 threads each): 128 registers up to W = 28, 168 up to 40
+// Build knobs, both measured on the B200 (profiles/README.md): the defaults are the fastest.
 #ifndef NW_PAIR_RTREG_MAX
 #define NW_PAIR_RTREG_MAX 64  // widest window whose packed rt values are held in registers (LDS.128) instead of read per cell
 #endif
 #ifndef NW_PAIR_MINB_WIDE
-#define NW_PAIR_MINB_WIDE 4
+#define NW_PAIR_MINB_WIDE 4   // CTAs per SM for 40 < W <= 64 (6 = 168 registers, by spilling: 2 x slower)
 #endif
+// CTAs per SM the register allocation has to leave room for (64 threads each): 128 registers up to W = 28, 168 up to 40
 constexpr int pair_min_ctas(int W) { return W <= 28 ? 8 : (W <= 40 ? 6 : (W <= 64 ? NW_PAIR_MINB_WIDE : 4)); }
 constexpr int PAIR_BROW = 8;  // uint32 per staged band row: {r0, plane word offset, rt byte offset, sb, mask[0..3]} = two LDS.128
 
