@@ -557,7 +557,6 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
     int rid, L, cls;  // cls: window W (32-bit register kernel), W | CLS_PAIR (packed register kernel) or 0 (generic)
     uint32_t n, bin;
   };
-  constexpr int CLS_PAIR = 0x1000;
   // NW_DP_PAIR=0 keeps every bucket on the 32-bit register kernel (experiments, A/B parity tests)
   static const bool pair_on = !getenv("NW_DP_PAIR") || atoi(getenv("NW_DP_PAIR")) != 0;
   auto cls_smem = [&](int cls, int L) {
@@ -580,29 +579,17 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
     if (cells_out) cells_out[r] += (int64_t)bins[k].n * T.cells;
   }
   {
-    // A register-window class is folded into the next wider class that is present when walking the wider window costs
-    // less than a launch of its own: a wider window only carries idle columns (masks and band rows are per length, the
-    // region context is padded for WINDOW_MAX), i.e. n CTAs pay (B - A) / A more each, while a separate launch ends in a
-    // partly filled wave and costs at least the latency of ONE thread's DP (~70-100 us at 150 blocks).  Rule: fold iff
-    // n * (B - A) / A < half a wave (a wave ~ 148 x 6 CTAs).  S150: windows 60 and 64 become one launch per level;
-    // regionfile passes: 22 -> ~13 launches; the full-corridor pre-pass of the region stage keeps its narrow classes out
-    // of the 112 / 128 windows.  NW_CLASS_MERGE_CTAS overrides the wave size, NW_NO_CLASS_MERGE disables.
+    // window classes that would not fill a launch of their own are folded into the next wider class present
+    // (fold_window_classes, nw_host.h: S150 windows 60 and 64 become one launch per level, regionfile passes 22 -> ~13
+    // launches, the full-corridor pre-pass of the region stage keeps its narrow classes out of the 112 / 128 windows).
+    // NW_CLASS_MERGE_CTAS overrides the wave size (148 x 6 CTAs), NW_NO_CLASS_MERGE disables.
     static const bool no_merge = getenv("NW_NO_CLASS_MERGE") != nullptr;
     static const int merge_ctas = getenv("NW_CLASS_MERGE_CTAS") ? atoi(getenv("NW_CLASS_MERGE_CTAS")) : 148 * 6;
     std::map<int, uint64_t> cta_of;  // fast classes present -> work slots
     for (const Bucket& b : bk)
       if (b.cls) cta_of[b.cls] += (b.n + 31) & ~31u;
     std::map<int, int> into;
-    if (!no_merge)
-      for (auto it = cta_of.begin(); it != cta_of.end(); ++it) {
-        auto nx = std::next(it);
-        if (nx == cta_of.end()) break;
-        const uint64_t wa = (uint64_t)(it->first & ~CLS_PAIR), wb = (uint64_t)(nx->first & ~CLS_PAIR);
-        if (((it->first ^ nx->first) & CLS_PAIR) == 0 && ((it->second + 127) / 128) * (wb - wa) * 2 < (uint64_t)merge_ctas * wa) {
-          into[it->first] = nx->first;
-          nx->second += it->second;
-        }
-      }
+    if (!no_merge) into = fold_window_classes(cta_of, (uint64_t)merge_ctas);
     for (Bucket& b : bk) {
       int cls = b.cls;
       while (cls && into.count(cls)) {

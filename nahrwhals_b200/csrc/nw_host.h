@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <cmath>
+#include <map>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -132,6 +133,27 @@ inline RegionHost build_region(const int8_t* aln, int n_x, int n_y, const int64_
 // bound fits 15 bits no half-register of the packed row step can overflow (nw_device.h).
 inline bool pair_range_ok(const RegionHost& R, int Lc) {
   return R.sum_rt + (int64_t)Lc * R.max_up <= (int64_t)PAIR_TOTAL_MAX;
+}
+
+// Folding of DP window classes (run_scoring).  `slots_of`: kernel class -> work slots of a level, class = window W, with
+// CLS_PAIR set for the packed kernel.  A class is folded into the next wider class that is present (same kernel kind)
+// when walking the wider window costs less than a launch of its own: n CTAs pay (B - A) / A more each, a separate
+// launch ends in a partly filled wave and costs at least the latency of one thread's DP.  Rule: fold iff
+// n * (B - A) / A < wave_ctas / 2.  Folds chain (A into B, then B with A's slots into C).  Returns class -> target.
+constexpr int CLS_PAIR = 0x1000;
+inline std::map<int, int> fold_window_classes(std::map<int, uint64_t> slots_of, uint64_t wave_ctas) {
+  std::map<int, int> into;
+  for (auto it = slots_of.begin(); it != slots_of.end(); ++it) {
+    auto nx = std::next(it);
+    if (nx == slots_of.end()) break;
+    if (it->first == 0 || ((it->first ^ nx->first) & CLS_PAIR) != 0) continue;
+    const uint64_t wa = (uint64_t)(it->first & ~CLS_PAIR), wb = (uint64_t)(nx->first & ~CLS_PAIR);
+    if (((it->second + 127) / 128) * (wb - wa) * 2 < wave_ctas * wa) {
+      into[it->first] = nx->first;
+      nx->second += it->second;
+    }
+  }
+  return into;
 }
 
 // ---- fingerprint power tables: pw[e + FP_EMAX] = B_k^e mod p for four fixed (seeded) bases ----

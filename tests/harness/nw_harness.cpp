@@ -4,6 +4,7 @@
 // tables) against the oracle.  It is never loaded by the product and is not a CPU fallback: it cannot run a search.
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "../../nahrwhals_b200/csrc/nw_band.h"
@@ -199,6 +200,18 @@ int h_score_pair(const int8_t* aln, int n_x, int n_y, const int64_t* len_x, cons
     total_bp[h] = total * R.gcd;
   }
   return 1;
+}
+
+// fold_window_classes (nw_host.h): n classes (cls[k], slots[k]) -> out[k] = class cls[k] is folded into (itself if not)
+void h_fold_classes(int n, const int* cls, const uint64_t* slots, uint64_t wave_ctas, int* out) {
+  std::map<int, uint64_t> m;
+  for (int k = 0; k < n; ++k) m[cls[k]] += slots[k];
+  const std::map<int, int> into = fold_window_classes(m, wave_ctas);
+  for (int k = 0; k < n; ++k) {
+    int c = cls[k];
+    while (into.count(c)) c = into.at(c);
+    out[k] = c;
+  }
 }
 
 // 16-bit additions of the packed row step that wrapped since the library was loaded (must stay 0: pair_range_ok)

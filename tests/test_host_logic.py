@@ -266,6 +266,35 @@ def test_packed_register_dp_matches_oracle(H, oracle):
     assert H.h_pair_wraps() == 0
 
 
+def test_window_class_folding(H):
+    """fold_window_classes (run_scoring's launch grouping): fold iff n * (B - A) / A < half a wave; folds chain with the
+    accumulated work; the packed and the 32-bit kernel never mix; the generic class (0) is never folded."""
+    PAIR = 0x1000
+    wave = 148 * 6
+
+    def fold(classes):
+        cls = np.array([c for c, _ in classes], np.int32)
+        slots = np.array([s for _, s in classes], np.uint64)
+        out = np.zeros(len(classes), np.int32)
+        H.h_fold_classes(len(classes), _p(cls), _p(slots), C.c_uint64(wave), _p(out))
+        return out.tolist()
+
+    # S150: window 60 (a few thousand CTAs) folds into 64: 4 / 60 more work each
+    assert fold([(PAIR | 60, 128 * 3000), (PAIR | 64, 128 * 20000)]) == [PAIR | 64, PAIR | 64]
+    # ... but not when it is a launch of many waves on its own
+    assert fold([(PAIR | 60, 128 * 7000), (PAIR | 64, 128 * 20000)]) == [PAIR | 60, PAIR | 64]
+    # a narrow class is kept out of a much wider window unless it is tiny (28 -> 128: 100 / 28 more work each)
+    assert fold([(PAIR | 28, 128 * 200), (PAIR | 128, 128 * 50)]) == [PAIR | 28, PAIR | 128]
+    assert fold([(PAIR | 28, 128 * 100), (PAIR | 128, 128 * 50)]) == [PAIR | 128, PAIR | 128]
+    # chains accumulate: 40 -> 44, then 44 (with 40's work) is too big for 48
+    n40, n44 = 128 * 3000, 128 * 3000
+    assert fold([(PAIR | 40, n40), (PAIR | 44, n44), (PAIR | 48, 128 * 9000)]) == [PAIR | 44, PAIR | 44, PAIR | 48]
+    assert fold([(PAIR | 40, 128 * 500), (PAIR | 44, 128 * 500), (PAIR | 48, 128 * 9000)]) == [PAIR | 48] * 3
+    # kinds never mix, generic stays
+    assert fold([(0, 128), (64, 128), (PAIR | 8, 128), (PAIR | 12, 128)]) == [0, 64, PAIR | 12, PAIR | 12]
+    assert fold([(128, 128 * 10), (PAIR | 8, 128 * 10)]) == [128, PAIR | 8]
+
+
 def test_score_string_all_values(H, oracle):
     """The product's TSV score formatter vs a generic shortest-round-trip Float32 printer, all 100001 values."""
     buf = C.create_string_buffer(64)
