@@ -25,11 +25,17 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE line (the JSON): whatever NCCL has to say under NCCL_DEBUG (its version banner included)
-# goes to stderr, for torch's communicator and for the one libnwsolve opens itself
-# (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, and prints the banner to stdout when NCCL_DEBUG is unset)
+# stdout carries exactly ONE line (the JSON).  Native libraries write to file descriptor 1 behind Python's back (NCCL
+# prints its version banner there, for torch's communicator and for the one libnwsolve opens itself, whatever
+# NCCL_DEBUG_FILE says): descriptor 1 is pointed at stderr for the whole run and Python's own sys.stdout keeps the
+# real one.
 os.environ.setdefault("NCCL_DEBUG", "WARN")
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if __name__ == "__main__":  # not when a tool imports make_workload from here
+    sys.stdout.flush()
+    _REAL_STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_REAL_STDOUT_FD, "w", buffering=1)
 
 METRIC = "mutation_candidates_scored_per_s"
 UNIT = "candidates/s"

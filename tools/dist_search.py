@@ -7,8 +7,11 @@ import os
 import sys
 import time
 
-os.environ.setdefault("NCCL_DEBUG", "WARN")  # with the file below: NCCL's banner goes to stderr, stdout = the JSON line
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout = the JSON line only: native writes to descriptor 1 (NCCL's version banner) are pointed at stderr
+sys.stdout.flush()
+_REAL_STDOUT_FD = os.dup(1)
+os.dup2(2, 1)
+sys.stdout = os.fdopen(_REAL_STDOUT_FD, "w", buffering=1)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
