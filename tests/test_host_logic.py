@@ -382,6 +382,7 @@ def test_bench_reference_arm_contract():
     import sys
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup",
                           "0", "--cpu-sample", "3000"], capture_output=True, text=True, timeout=300, check=True).stdout
+    assert len([l for l in out.split("\n") if l.strip()]) == 1  # stdout is exactly the JSON line
     line = json.loads(out.strip().split("\n")[-1])
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
