@@ -580,7 +580,7 @@ void run_scoring(nw_ctx* c, const ScoreView& Lv, const uint32_t* hist_dev, int l
   }
   {
     // window classes that would not fill a launch of their own are folded into the next wider class present
-    // (fold_window_classes, nw_host.h: S150 windows 60 and 64 become one launch per level, regionfile passes 22 -> ~13
+    // (fold_window_classes, nw_host.h: S150 windows 60 and 64 become one launch per level, regionfile passes need fewer
     // launches, the full-corridor pre-pass of the region stage keeps its narrow classes out of the 112 / 128 windows).
     // NW_CLASS_MERGE_CTAS overrides the wave size (148 x 6 CTAs), NW_NO_CLASS_MERGE disables.
     static const bool no_merge = getenv("NW_NO_CLASS_MERGE") != nullptr;
