@@ -85,4 +85,7 @@ int hr_region(const int64_t* grid, int nx, int ny, const int64_t* lx, const int6
   }
 }
 
+// round(x, 3) as the region stage computes it (nw_region_host.h round3)
+double hr_round3(double x) { return round3(x); }
+
 }  // extern "C"

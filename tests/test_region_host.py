@@ -177,3 +177,43 @@ def test_host_flow_single_block(HR, oracle):
     numbers = tuple(np.zeros(1, t) for t in (np.int64, np.int64, np.int64, np.int64, np.float64))
     rc = run_host(HR, np.array([[5000, 0, 3000]]), [5000], [5000, 2000, 3000], [0, 5000, 7000, 10000], {}, numbers, None)[0]
     assert rc == -1
+
+
+def test_round3_near_ties(HR):
+    """R's round(x, 3) (R/evaltools.R:300-302) as the region stage computes it: nearbyint(x * 1000) / 1000 in the host code
+    == the restatement, on scores of the form (1 - cost / total) * 100 incl. every exact tie a total of 2^a 5^b units
+    produces.  R >= 4.0 rounds by comparing the two 3-decimal candidates floor(x * 1000) / 1000 and ceil(x * 1000) / 1000
+    with x itself (its exact rule is not restated here: there is no R in the image to pin it); this test states how far
+    ANY rule of that family can be from what is computed here: the results agree except within one part in 10^12 of a
+    half-way point, where they may differ by 0.001 ("Contract details")."""
+    import math
+    HR.hr_round3.restype = C.c_double
+    HR.hr_round3.argtypes = [C.c_double]
+
+    def r4_round3(x):  # a candidate-distance rounding (nearer of the two 3-decimal neighbours, ties to the even one)
+        x10 = 1000.0 * x
+        i10 = math.floor(x10)
+        xd, xu = i10 / 1000.0, math.ceil(x10) / 1000.0
+        dd, du = x - xd, xu - x
+        return xd if (dd < du or (dd == du and i10 % 2 == 0)) else xu
+
+    rng = np.random.default_rng(4)
+    xs = []
+    for total in (3200000, 2830000, 160000, 1 << 20, 5 ** 8, 64 * 5 ** 6, 2470000):
+        for cost in rng.integers(0, total, 3000):
+            xs.append((1 - int(cost) / total) * 100)
+        step = total // 200000 if total % 200000 == 0 else 0  # cost = odd multiples of total / 200000: x * 1000 = k + 0.5
+        if step:
+            for k in range(1, 4000, 2):
+                xs.append((1 - (k * step) / total) * 100)
+    xs += [0.0, 100.0, 71.378, 99.595, 0.0005, 0.3125, 12.3455, 12.3465]
+    ndiff = 0
+    for x in xs:
+        got = HR.hr_round3(x)
+        assert got == ro.r_round3(x)
+        alt = r4_round3(x)
+        if got != alt:
+            ndiff += 1
+            frac = x * 1000.0 - math.floor(x * 1000.0)
+            assert abs(frac - 0.5) < 1e-9 * max(1.0, x * 1000.0) and abs(got - alt) < 0.0011
+    assert ndiff < len(xs) // 20
