@@ -1151,6 +1151,8 @@ def main():
                 config=dict(workload=desc + ("; one such region per GPU (%d independent regions, no collective on the data path)" % world if world > 1 else ""),
                             scored_per_step=scored_all / args.steps, l2="flushed between timed steps (256 MiB write)",
                             dedup="exact (default): every merged candidate compared element-wise with its owner on the device",
+                            dp_arith="int16 x 2 (packed DPX, two candidates per register) where a bucket's totals fit 15 bits -- "
+                                     "every bucket of this workload --, int32 otherwise; results are exact integers either way",
                             fingerprint_only_dedup=dict(ms_per_step=nv_ms, e2e_ms_per_step=nv_e2e,
                                                         note="NW_FLAG_NO_VERIFY, this rank; not the metric"),
                             dp_share_of_step=(score_ms / (dev_ms if dist is None else max(dev_ms, 1e-9)))),
